@@ -1,0 +1,119 @@
+"""ctypes loader for lib/libvscuda.so (built by csrc/Makefile via __graft_entry__.build())."""
+import ctypes as C
+import os
+import threading
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+_SO = os.path.join(_HERE, "lib", "libvscuda.so")
+
+VS_OK, VS_EINVAL, VS_EEMPTY, VS_EDIM, VS_ECUDA, VS_ENODEV, VS_ENOMEM, VS_ERANGE = 0, -1, -2, -3, -4, -5, -6, -7
+
+# every symbol include/vscuda.h declares (checked by tests/test_abi.py)
+SYMBOLS = [
+    "vs_init", "vs_shutdown", "vs_last_error", "vs_device_info",
+    "vs_ctx_create", "vs_ctx_destroy", "vs_ctx_sync", "vs_ctx_stream", "vs_ctx_launch_count",
+    "vs_ctx_slowpath_count", "vs_ctx_timer_start", "vs_ctx_timer_stop",
+    "vs_quantize_f32", "vs_quantize_f64", "vs_dequantize_f32", "vs_dequantize_f64",
+    "vs_quantize_f32_dev", "vs_quantize_f64_dev",
+    "vs_matrix_create", "vs_matrix_create_dev", "vs_matrix_from_f32_dev", "vs_matrix_retain",
+    "vs_matrix_release", "vs_matrix_rows", "vs_matrix_cols", "vs_matrix_read_rows",
+    "vs_cosine_1xN", "vs_dot_1xN", "vs_argmax_MxN", "vs_argmax_MxN_dev",
+    "vs_index_build", "vs_index_build_assigned", "vs_index_build_dev", "vs_index_release",
+    "vs_index_rows", "vs_index_lists", "vs_search", "vs_search_flat", "vs_search_dev",
+    "vs_search_resolve", "vs_select_probes", "vs_topk_merge_dev",
+    "vs_kmeans_step", "vs_recenter",
+]
+
+
+class BackendUnavailable(RuntimeError):
+    """libvscuda.so is missing or there is no B200: the product path has no CPU fallback."""
+
+
+_lib = None
+_inited = False
+_lock = threading.Lock()
+
+
+def lib_path():
+    return _SO
+
+
+def load():
+    """dlopen libvscuda.so and declare prototypes. Does not touch the GPU."""
+    global _lib
+    with _lock:
+        if _lib is not None:
+            return _lib
+        if not os.path.exists(_SO):
+            raise BackendUnavailable(
+                f"{_SO} not found: build it with `python -c 'import __graft_entry__ as g; g.build()'` "
+                "(nvcc, sm_100a). There is no CPU fallback.")
+        L = C.CDLL(_SO)
+        vp, sz, u64 = C.c_void_p, C.c_size_t, C.c_uint64
+        L.vs_last_error.restype = C.c_char_p
+        L.vs_ctx_stream.restype = vp
+        L.vs_ctx_launch_count.restype = u64
+        L.vs_ctx_slowpath_count.restype = u64
+        L.vs_matrix_rows.restype = sz
+        L.vs_matrix_cols.restype = sz
+        L.vs_index_rows.restype = sz
+        L.vs_index_lists.restype = sz
+        L.vs_matrix_retain.restype = None
+        L.vs_matrix_release.restype = None
+        L.vs_index_release.restype = None
+        L.vs_ctx_destroy.restype = None
+        L.vs_shutdown.restype = None
+        for name in ("vs_ctx_stream", "vs_ctx_launch_count", "vs_ctx_slowpath_count", "vs_ctx_destroy", "vs_ctx_sync",
+                     "vs_ctx_timer_start", "vs_matrix_retain", "vs_matrix_release", "vs_matrix_rows", "vs_matrix_cols",
+                     "vs_index_release", "vs_index_rows", "vs_index_lists"):
+            getattr(L, name).argtypes = [vp]
+        L.vs_init.argtypes = [C.c_int]
+        L.vs_ctx_create.argtypes = [C.POINTER(vp)]
+        L.vs_ctx_timer_stop.argtypes = [vp, C.POINTER(C.c_float)]
+        L.vs_device_info.argtypes = [C.c_char_p, sz, C.POINTER(C.c_int), C.POINTER(sz)]
+        L.vs_quantize_f32.argtypes = [vp, vp, sz, sz, vp]
+        L.vs_quantize_f64.argtypes = [vp, vp, sz, sz, vp]
+        L.vs_dequantize_f32.argtypes = [vp, vp, sz, sz, vp]
+        L.vs_dequantize_f64.argtypes = [vp, vp, sz, sz, vp]
+        L.vs_quantize_f32_dev.argtypes = [vp, vp, sz, sz, vp]
+        L.vs_quantize_f64_dev.argtypes = [vp, vp, sz, sz, vp]
+        L.vs_matrix_create.argtypes = [vp, vp, sz, sz, C.POINTER(vp)]
+        L.vs_matrix_create_dev.argtypes = [vp, vp, sz, sz, C.POINTER(vp)]
+        L.vs_matrix_from_f32_dev.argtypes = [vp, vp, sz, sz, C.POINTER(vp)]
+        L.vs_matrix_read_rows.argtypes = [vp, vp, sz, sz, vp]
+        L.vs_cosine_1xN.argtypes = [vp, vp, sz, vp, vp]
+        L.vs_dot_1xN.argtypes = [vp, vp, sz, vp, vp]
+        L.vs_argmax_MxN.argtypes = [vp, vp, vp, vp, vp]
+        L.vs_argmax_MxN_dev.argtypes = [vp, vp, vp, vp]
+        L.vs_index_build.argtypes = [vp, vp, sz, sz, vp, vp, vp, sz, C.POINTER(vp)]
+        L.vs_index_build_assigned.argtypes = [vp, vp, sz, sz, vp, vp, vp, sz, C.POINTER(vp)]
+        L.vs_index_build_dev.argtypes = [vp, vp, vp, vp, u64, vp, C.POINTER(vp)]
+        L.vs_search.argtypes = [vp, vp, vp, sz, sz, sz, vp, vp, vp]
+        L.vs_search_flat.argtypes = [vp, vp, vp, vp, sz, sz, vp, vp, vp]
+        L.vs_search_dev.argtypes = [vp, vp, vp, sz, sz, vp, vp, vp, vp]
+        L.vs_search_resolve.argtypes = [vp, vp, vp, sz, sz, vp, vp, vp, vp, C.POINTER(C.c_int)]
+        L.vs_select_probes.argtypes = [vp, vp, vp, sz, sz, vp, vp]
+        L.vs_topk_merge_dev.argtypes = [vp, vp, vp, vp, sz, sz, sz, vp, vp, vp]
+        L.vs_kmeans_step.argtypes = [vp, vp, vp, sz, vp, vp, vp, vp, C.POINTER(C.c_int)]
+        L.vs_recenter.argtypes = [vp, vp, vp]
+        _lib = L
+        return L
+
+
+def last_error():
+    return load().vs_last_error().decode("utf-8", "replace")
+
+
+def init(device=None):
+    """vs_init on LOCAL_RANK (or `device`). Raises BackendUnavailable without a B200."""
+    global _inited
+    L = load()
+    if _inited and device is None:
+        return L
+    if device is None:
+        device = int(os.environ.get("LOCAL_RANK", "0"))
+    rc = L.vs_init(int(device))
+    if rc != VS_OK:
+        raise BackendUnavailable(f"vs_init({device}) failed: {last_error()}")
+    _inited = True
+    return L

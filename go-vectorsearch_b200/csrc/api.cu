@@ -1,0 +1,1017 @@
+// api.cu -- the C ABI of libvscuda.so (include/vscuda.h): handles, arenas and launch orchestration.
+// No torch types, no CPU fallback: every compute entry point needs a CUDA device.
+#include <cub/device/device_radix_sort.cuh>
+
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+#include <mutex>
+#include <vector>
+
+#include "../../include/vscuda.h"
+#include "internal.h"
+
+using namespace vs;
+
+// ------------------------------------------------------------------------------------------------
+static thread_local char g_err[512] = "";
+static int g_device = -1;
+static int g_sm_count = 0;
+static std::mutex g_mu;
+
+static int fail(int code, const char *fmt, ...) {
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(g_err, sizeof(g_err), fmt, ap);
+    va_end(ap);
+    return code;
+}
+#define CU(call)                                                                                        \
+    do {                                                                                                \
+        cudaError_t _e = (call);                                                                        \
+        if (_e != cudaSuccess) return fail(VS_ECUDA, "%s:%d %s: %s", __FILE__, __LINE__, #call, cudaGetErrorString(_e)); \
+    } while (0)
+#define VS(call)              \
+    do {                      \
+        int _r = (call);      \
+        if (_r != VS_OK) return _r; \
+    } while (0)
+
+extern "C" const char *vs_last_error(void) { return g_err; }
+
+extern "C" int vs_init(int device) {
+    std::lock_guard<std::mutex> lk(g_mu);
+    int count = 0;
+    cudaError_t e = cudaGetDeviceCount(&count);
+    if (e != cudaSuccess || count == 0)
+        return fail(VS_ENODEV, "no CUDA device (%s); libvscuda has no CPU fallback", e != cudaSuccess ? cudaGetErrorString(e) : "count=0");
+    if (device < 0 || device >= count) return fail(VS_EINVAL, "device %d out of range (%d devices)", device, count);
+    CU(cudaSetDevice(device));
+    cudaDeviceProp prop;
+    CU(cudaGetDeviceProperties(&prop, device));
+    if (prop.major < 10) return fail(VS_ENODEV, "device %s is sm_%d%d; libvscuda is built for sm_100a only", prop.name, prop.major, prop.minor);
+    g_device = device;
+    g_sm_count = prop.multiProcessorCount;
+    return VS_OK;
+}
+
+extern "C" void vs_shutdown(void) {
+    std::lock_guard<std::mutex> lk(g_mu);
+    if (g_device >= 0) cudaDeviceSynchronize();
+    g_device = -1;
+}
+
+extern "C" int vs_device_info(char *name, size_t name_cap, int *sm_count, size_t *total_mem) {
+    if (g_device < 0) return fail(VS_ENODEV, "vs_init not called");
+    cudaDeviceProp prop;
+    CU(cudaGetDeviceProperties(&prop, g_device));
+    if (name && name_cap) snprintf(name, name_cap, "%s", prop.name);
+    if (sm_count) *sm_count = prop.multiProcessorCount;
+    if (total_mem) *total_mem = prop.totalGlobalMem;
+    return VS_OK;
+}
+
+static int need_dev() {
+    if (g_device < 0) return fail(VS_ENODEV, "vs_init not called (or no CUDA device); libvscuda has no CPU fallback");
+    cudaSetDevice(g_device);
+    return VS_OK;
+}
+
+// ------------------------------------------------------------------------------------------------
+extern "C" int vs_ctx_create(vs_ctx **out) {
+    VS(need_dev());
+    if (!out) return fail(VS_EINVAL, "out is null");
+    vs_ctx *c = new vs_ctx();
+    c->device = g_device;
+    CU(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
+    CU(cudaEventCreate(&c->ev0));
+    CU(cudaEventCreate(&c->ev1));
+    *out = c;
+    return VS_OK;
+}
+
+extern "C" void vs_ctx_destroy(vs_ctx *c) {
+    if (!c) return;
+    cudaSetDevice(c->device);
+    cudaStreamSynchronize(c->stream);
+    if (c->scratch) cudaFree(c->scratch);
+    if (c->pinned) cudaFreeHost(c->pinned);
+    cudaEventDestroy(c->ev0);
+    cudaEventDestroy(c->ev1);
+    cudaStreamDestroy(c->stream);
+    delete c;
+}
+
+extern "C" int vs_ctx_sync(vs_ctx *c) {
+    if (!c) return fail(VS_EINVAL, "ctx is null");
+    CU(cudaStreamSynchronize(c->stream));
+    return VS_OK;
+}
+extern "C" void *vs_ctx_stream(vs_ctx *c) { return c ? (void *)c->stream : nullptr; }
+extern "C" uint64_t vs_ctx_launch_count(const vs_ctx *c) { return c ? c->launches : 0; }
+extern "C" uint64_t vs_ctx_slowpath_count(const vs_ctx *c) { return c ? c->slowpath : 0; }
+extern "C" int vs_ctx_timer_start(vs_ctx *c) {
+    CU(cudaEventRecord(c->ev0, c->stream));
+    return VS_OK;
+}
+extern "C" int vs_ctx_timer_stop(vs_ctx *c, float *ms) {
+    CU(cudaEventRecord(c->ev1, c->stream));
+    CU(cudaEventSynchronize(c->ev1));
+    CU(cudaEventElapsedTime(ms, c->ev0, c->ev1));
+    return VS_OK;
+}
+
+// Bump arena over the ctx scratch buffer. Growing synchronizes the stream first (kernels in flight may
+// still be using the old buffer).
+struct Arena {
+    vs_ctx *c;
+    size_t off = 0;
+    Arena(vs_ctx *c_) : c(c_) {}
+    int reserve(size_t bytes) {
+        bytes += 4096;
+        if (bytes <= c->scratch_cap) return VS_OK;
+        CU(cudaStreamSynchronize(c->stream));
+        if (c->scratch) CU(cudaFree(c->scratch));
+        c->scratch = nullptr;
+        c->scratch_cap = 0;
+        size_t cap = bytes + bytes / 4;
+        cudaError_t e = cudaMalloc(&c->scratch, cap);
+        if (e != cudaSuccess) return fail(VS_ENOMEM, "cudaMalloc(%zu) for scratch: %s", cap, cudaGetErrorString(e));
+        c->scratch_cap = cap;
+        return VS_OK;
+    }
+    template <typename T>
+    T *take(size_t count) {
+        off = (off + 255) & ~size_t(255);
+        T *p = reinterpret_cast<T *>(static_cast<char *>(c->scratch) + off);
+        off += count * sizeof(T);
+        return p;
+    }
+    static size_t pad(size_t bytes) { return (bytes + 255) & ~size_t(255); }
+};
+
+static int pinned_reserve(vs_ctx *c, size_t bytes) {
+    if (bytes <= c->pinned_cap) return VS_OK;
+    CU(cudaStreamSynchronize(c->stream));
+    if (c->pinned) CU(cudaFreeHost(c->pinned));
+    c->pinned = nullptr;
+    c->pinned_cap = 0;
+    cudaError_t e = cudaMallocHost(&c->pinned, bytes);
+    if (e != cudaSuccess) return fail(VS_ENOMEM, "cudaMallocHost(%zu): %s", bytes, cudaGetErrorString(e));
+    c->pinned_cap = bytes;
+    return VS_OK;
+}
+
+#define LAUNCH(c, call)                                                                                  \
+    do {                                                                                                 \
+        cudaError_t _e = (call);                                                                         \
+        if (_e != cudaSuccess) return fail(VS_ECUDA, "%s:%d launch %s: %s", __FILE__, __LINE__, #call, cudaGetErrorString(_e)); \
+        (c)->launches++;                                                                                 \
+    } while (0)
+
+// ------------------------------------------------------------------------------------------------
+// quantization
+static int quantize_host(vs_ctx *c, const void *in, size_t n, size_t d, uint8_t *out, bool f64) {
+    VS(need_dev());
+    if (!c) return fail(VS_EINVAL, "ctx is null");
+    if (n == 0) return VS_OK;
+    if (!in || !out) return fail(VS_EINVAL, "null buffer");
+    if (d > (1u << 20)) return fail(VS_ERANGE, "d=%zu too large", d);
+    const size_t esz = f64 ? 8 : 4;
+    const size_t rb = 8 + d;
+    size_t chunk = (size_t(256) << 20) / (d * esz + rb + 1);
+    if (chunk < 1) chunk = 1;
+    if (chunk > n) chunk = n;
+    Arena a(c);
+    VS(a.reserve(Arena::pad(chunk * d * esz) + Arena::pad(chunk * rb) + 1024));
+    char *d_in = a.take<char>(chunk * d * esz);
+    uint8_t *d_out = a.take<uint8_t>(chunk * rb);
+    for (size_t r0 = 0; r0 < n; r0 += chunk) {
+        size_t m = n - r0 < chunk ? n - r0 : chunk;
+        if (d) CU(cudaMemcpyAsync(d_in, (const char *)in + r0 * d * esz, m * d * esz, cudaMemcpyHostToDevice, c->stream));
+        if (f64) LAUNCH(c, launch_quantize_f64((const double *)d_in, m, (int)d, d_out, c->stream));
+        else LAUNCH(c, launch_quantize_f32((const float *)d_in, m, (int)d, d_out, c->stream));
+        CU(cudaMemcpyAsync(out + r0 * rb, d_out, m * rb, cudaMemcpyDeviceToHost, c->stream));
+        CU(cudaStreamSynchronize(c->stream));
+    }
+    return VS_OK;
+}
+
+extern "C" int vs_quantize_f32(vs_ctx *c, const float *in, size_t n, size_t d, uint8_t *out) {
+    return quantize_host(c, in, n, d, out, false);
+}
+extern "C" int vs_quantize_f64(vs_ctx *c, const double *in, size_t n, size_t d, uint8_t *out) {
+    return quantize_host(c, in, n, d, out, true);
+}
+extern "C" int vs_quantize_f32_dev(vs_ctx *c, const float *d_in, size_t n, size_t d, uint8_t *d_out) {
+    VS(need_dev());
+    if (n == 0) return VS_OK;
+    LAUNCH(c, launch_quantize_f32(d_in, n, (int)d, d_out, c->stream));
+    return VS_OK;
+}
+extern "C" int vs_quantize_f64_dev(vs_ctx *c, const double *d_in, size_t n, size_t d, uint8_t *d_out) {
+    VS(need_dev());
+    if (n == 0) return VS_OK;
+    LAUNCH(c, launch_quantize_f64(d_in, n, (int)d, d_out, c->stream));
+    return VS_OK;
+}
+
+static int dequantize_host(vs_ctx *c, const uint8_t *rows, size_t n, size_t row_bytes, void *out, bool f64) {
+    VS(need_dev());
+    if (!c) return fail(VS_EINVAL, "ctx is null");
+    if (n == 0) return VS_OK;
+    if (row_bytes < 8) return fail(VS_EINVAL, "row_bytes=%zu < 8", row_bytes);
+    const size_t d = row_bytes - 8;
+    if (d == 0) return VS_OK;
+    const size_t esz = f64 ? 8 : 4;
+    size_t chunk = (size_t(256) << 20) / (d * esz + row_bytes);
+    if (chunk < 1) chunk = 1;
+    if (chunk > n) chunk = n;
+    Arena a(c);
+    VS(a.reserve(Arena::pad(chunk * d * esz) + Arena::pad(chunk * row_bytes) + 1024));
+    uint8_t *d_rows = a.take<uint8_t>(chunk * row_bytes);
+    char *d_out = a.take<char>(chunk * d * esz);
+    for (size_t r0 = 0; r0 < n; r0 += chunk) {
+        size_t m = n - r0 < chunk ? n - r0 : chunk;
+        CU(cudaMemcpyAsync(d_rows, rows + r0 * row_bytes, m * row_bytes, cudaMemcpyHostToDevice, c->stream));
+        if (f64) LAUNCH(c, launch_dequantize_f64(d_rows, m, (int)row_bytes, (double *)d_out, c->stream));
+        else LAUNCH(c, launch_dequantize_f32(d_rows, m, (int)row_bytes, (float *)d_out, c->stream));
+        CU(cudaMemcpyAsync((char *)out + r0 * d * esz, d_out, m * d * esz, cudaMemcpyDeviceToHost, c->stream));
+        CU(cudaStreamSynchronize(c->stream));
+    }
+    return VS_OK;
+}
+extern "C" int vs_dequantize_f32(vs_ctx *c, const uint8_t *rows, size_t n, size_t row_bytes, float *out) {
+    return dequantize_host(c, rows, n, row_bytes, out, false);
+}
+extern "C" int vs_dequantize_f64(vs_ctx *c, const uint8_t *rows, size_t n, size_t row_bytes, double *out) {
+    return dequantize_host(c, rows, n, row_bytes, out, true);
+}
+
+// ------------------------------------------------------------------------------------------------
+// matrices
+static int matrix_alloc(size_t n, size_t d, vs_matrix **out) {
+    if (d > 4096) return fail(VS_ERANGE, "d=%zu: kernels support d <= 4096", d);
+    if (n > 0xFFFFFFF0ull) return fail(VS_ERANGE, "n=%zu: a device matrix holds < 2^32 rows", n);
+    vs_matrix *m = new vs_matrix();
+    m->device = g_device;
+    m->n = n;
+    m->d = (int)d;
+    m->d_pad = (int)((d + 15) & ~size_t(15));
+    cudaError_t e = cudaMalloc(&m->codes, n * (size_t)m->d_pad + 256);
+    if (e == cudaSuccess) e = cudaMalloc(&m->hdr, n * sizeof(float2) + 256);
+    if (e == cudaSuccess) e = cudaMalloc(&m->sums, n * sizeof(uint2) + 256);
+    if (e != cudaSuccess) {
+        if (m->codes) cudaFree(m->codes);
+        if (m->hdr) cudaFree(m->hdr);
+        if (m->sums) cudaFree(m->sums);
+        delete m;
+        return fail(VS_ENOMEM, "cudaMalloc for %zu x %zu matrix: %s", n, d, cudaGetErrorString(e));
+    }
+    *out = m;
+    return VS_OK;
+}
+
+extern "C" void vs_matrix_retain(vs_matrix *m) {
+    if (m) m->refs.fetch_add(1);
+}
+extern "C" void vs_matrix_release(vs_matrix *m) {
+    if (!m) return;
+    if (m->refs.fetch_sub(1) == 1) {
+        cudaSetDevice(m->device);
+        if (m->owns) {
+            cudaFree(m->codes);
+            cudaFree(m->hdr);
+            cudaFree(m->sums);
+        }
+        delete m;
+    }
+}
+extern "C" size_t vs_matrix_rows(const vs_matrix *m) { return m ? m->n : 0; }
+extern "C" size_t vs_matrix_cols(const vs_matrix *m) { return m ? (size_t)m->d : 0; }
+
+static int check_rows(size_t n, size_t row_bytes) {
+    if (n == 0) return fail(VS_EEMPTY, "matrix rows are empty");          // compute.go:25-27
+    if (row_bytes <= 8) return fail(VS_EEMPTY, "matrix columns are empty");  // compute.go:29-31
+    return VS_OK;
+}
+
+extern "C" int vs_matrix_create_dev(vs_ctx *c, const uint8_t *d_rows, size_t n, size_t row_bytes, vs_matrix **out) {
+    VS(need_dev());
+    if (!c || !out) return fail(VS_EINVAL, "null argument");
+    VS(check_rows(n, row_bytes));
+    vs_matrix *m = nullptr;
+    VS(matrix_alloc(n, row_bytes - 8, &m));
+    cudaError_t e = launch_ingest(d_rows, n, (int)row_bytes, m->codes, m->d_pad, m->hdr, m->sums, c->stream);
+    if (e != cudaSuccess) {
+        vs_matrix_release(m);
+        return fail(VS_ECUDA, "ingest: %s", cudaGetErrorString(e));
+    }
+    c->launches++;
+    *out = m;
+    return VS_OK;
+}
+
+extern "C" int vs_matrix_create(vs_ctx *c, const uint8_t *rows, size_t n, size_t row_bytes, vs_matrix **out) {
+    VS(need_dev());
+    if (!c || !out) return fail(VS_EINVAL, "null argument");
+    VS(check_rows(n, row_bytes));
+    if (!rows) return fail(VS_EINVAL, "rows is null");
+    vs_matrix *m = nullptr;
+    VS(matrix_alloc(n, row_bytes - 8, &m));
+    size_t chunk = (size_t(256) << 20) / row_bytes;
+    if (chunk > n) chunk = n;
+    Arena a(c);
+    int rc = a.reserve(Arena::pad(chunk * row_bytes) + 1024);
+    if (rc != VS_OK) {
+        vs_matrix_release(m);
+        return rc;
+    }
+    uint8_t *stage = a.take<uint8_t>(chunk * row_bytes);
+    for (size_t r0 = 0; r0 < n; r0 += chunk) {
+        size_t cnt = n - r0 < chunk ? n - r0 : chunk;
+        cudaError_t e = cudaMemcpyAsync(stage, rows + r0 * row_bytes, cnt * row_bytes, cudaMemcpyHostToDevice, c->stream);
+        if (e == cudaSuccess)
+            e = launch_ingest(stage, cnt, (int)row_bytes, m->codes + r0 * (size_t)m->d_pad, m->d_pad, m->hdr + r0,
+                              m->sums + r0, c->stream);
+        if (e == cudaSuccess) e = cudaStreamSynchronize(c->stream);
+        if (e != cudaSuccess) {
+            vs_matrix_release(m);
+            return fail(VS_ECUDA, "matrix upload: %s", cudaGetErrorString(e));
+        }
+        c->launches++;
+    }
+    *out = m;
+    return VS_OK;
+}
+
+extern "C" int vs_matrix_from_f32_dev(vs_ctx *c, const float *d_in, size_t n, size_t d, vs_matrix **out) {
+    VS(need_dev());
+    if (!c || !out) return fail(VS_EINVAL, "null argument");
+    VS(check_rows(n, d + 8));
+    vs_matrix *m = nullptr;
+    VS(matrix_alloc(n, d, &m));
+    cudaError_t e = launch_quantize_f32_soa(d_in, n, (int)d, m->codes, m->d_pad, m->hdr, m->sums, c->stream);
+    if (e != cudaSuccess) {
+        vs_matrix_release(m);
+        return fail(VS_ECUDA, "quantize: %s", cudaGetErrorString(e));
+    }
+    c->launches++;
+    *out = m;
+    return VS_OK;
+}
+
+extern "C" int vs_matrix_read_rows(vs_ctx *c, const vs_matrix *m, size_t first, size_t count, uint8_t *out) {
+    VS(need_dev());
+    if (!c || !m || !out) return fail(VS_EINVAL, "null argument");
+    if (first + count > m->n) return fail(VS_EINVAL, "row range out of bounds");
+    if (count == 0) return VS_OK;
+    const size_t rb = 8 + (size_t)m->d;
+    Arena a(c);
+    VS(a.reserve(Arena::pad(count * rb) + 1024));
+    uint8_t *buf = a.take<uint8_t>(count * rb);
+    LAUNCH(c, launch_export(m->view(), first, count, buf, c->stream));
+    CU(cudaMemcpyAsync(out, buf, count * rb, cudaMemcpyDeviceToHost, c->stream));
+    CU(cudaStreamSynchronize(c->stream));
+    return VS_OK;
+}
+
+// A temporary (arena-resident) matrix built from host rows: queries, centroids.
+static int temp_matrix(vs_ctx *c, Arena &a, const uint8_t *rows, size_t n, size_t row_bytes, MatView *out) {
+    const size_t d = row_bytes - 8, d_pad = (d + 15) & ~size_t(15);
+    uint8_t *stage = a.take<uint8_t>(n * row_bytes);
+    uint8_t *codes = a.take<uint8_t>(n * d_pad);
+    float2 *hdr = a.take<float2>(n);
+    uint2 *sums = a.take<uint2>(n);
+    CU(cudaMemcpyAsync(stage, rows, n * row_bytes, cudaMemcpyHostToDevice, c->stream));
+    LAUNCH(c, launch_ingest(stage, n, (int)row_bytes, codes, (int)d_pad, hdr, sums, c->stream));
+    *out = MatView{codes, hdr, sums, n, (int)d, (int)d_pad};
+    return VS_OK;
+}
+static size_t temp_matrix_bytes(size_t n, size_t row_bytes) {
+    const size_t d = row_bytes - 8, d_pad = (d + 15) & ~size_t(15);
+    return Arena::pad(n * row_bytes) + Arena::pad(n * d_pad) + 2 * Arena::pad(n * 8) + 1024;
+}
+
+// ------------------------------------------------------------------------------------------------
+// cosine 1xN / dots
+static int cosine_common(vs_ctx *c, const uint8_t *q, size_t q_bytes, const vs_matrix *m, float *sims_out,
+                         uint32_t *dots_out) {
+    VS(need_dev());
+    if (!c || !m) return fail(VS_EINVAL, "null argument");
+    if (q_bytes <= 8) return fail(VS_EEMPTY, "vector columns are empty");  // compute.go:12-14
+    if (!q) return fail(VS_EINVAL, "q is null");
+    if ((size_t)m->d != q_bytes - 8)  // cosine.go:19-21
+        return fail(VS_EDIM, "vector/matrix column size does not match: %zu != %d", q_bytes - 8, m->d);
+    const size_t n = m->n;
+    Arena a(c);
+    VS(a.reserve(temp_matrix_bytes(1, q_bytes) + Arena::pad(n * 4) * 2 + Arena::pad((size_t)m->d * 8) + 4096));
+    MatView qv;
+    VS(temp_matrix(c, a, q, 1, q_bytes, &qv));
+    float *d_sims = sims_out ? a.take<float>(n) : nullptr;
+    uint32_t *d_dots = dots_out ? a.take<uint32_t>(n) : nullptr;
+    uint32_t *d_work = a.take<uint32_t>(n);
+    unsigned int *d_count = a.take<unsigned int>(1);
+    double *d_qn = a.take<double>(m->d);
+    CU(cudaMemsetAsync(d_count, 0, sizeof(unsigned int), c->stream));
+    LAUNCH(c, launch_cosine_1xN(m->view(), qv, d_sims, d_dots, d_work, d_count, g_sm_count, c->stream));
+    if (sims_out) {
+        unsigned int cnt = 0;
+        CU(cudaMemcpyAsync(&cnt, d_count, sizeof(cnt), cudaMemcpyDeviceToHost, c->stream));
+        CU(cudaStreamSynchronize(c->stream));
+        if (cnt > 0) {
+            LAUNCH(c, launch_query_normalize(qv, d_qn, c->stream));
+            LAUNCH(c, launch_cosine_fix(m->view(), d_qn, d_sims, d_work, d_count, g_sm_count, c->stream));
+            c->slowpath += cnt;
+        }
+        CU(cudaMemcpyAsync(sims_out, d_sims, n * sizeof(float), cudaMemcpyDeviceToHost, c->stream));
+    }
+    if (dots_out) CU(cudaMemcpyAsync(dots_out, d_dots, n * sizeof(uint32_t), cudaMemcpyDeviceToHost, c->stream));
+    CU(cudaStreamSynchronize(c->stream));
+    return VS_OK;
+}
+
+extern "C" int vs_cosine_1xN(vs_ctx *c, const uint8_t *q, size_t q_bytes, const vs_matrix *m, float *sims_out) {
+    if (!sims_out) return fail(VS_EINVAL, "sims_out is null");
+    return cosine_common(c, q, q_bytes, m, sims_out, nullptr);
+}
+extern "C" int vs_dot_1xN(vs_ctx *c, const uint8_t *q, size_t q_bytes, const vs_matrix *m, uint32_t *dots_out) {
+    if (!dots_out) return fail(VS_EINVAL, "dots_out is null");
+    return cosine_common(c, q, q_bytes, m, nullptr, dots_out);
+}
+
+// ------------------------------------------------------------------------------------------------
+// argmax MxN
+static int argmax_dev(vs_ctx *c, Arena &a, const MatView &cent, const MatView &data, int32_t *d_idx, float *d_sims) {
+    const size_t n = data.n, M = cent.n;
+    uint32_t *d_canon = a.take<uint32_t>(M);
+    uint32_t *d_work = a.take<uint32_t>(n);
+    unsigned int *d_count = a.take<unsigned int>(1);
+    CU(cudaMemsetAsync(d_count, 0, sizeof(unsigned int), c->stream));
+    LAUNCH(c, launch_canonical_rows(cent, d_canon, c->stream));
+    LAUNCH(c, launch_argmax(cent, data, d_canon, d_idx, d_sims, d_work, d_count, g_sm_count, c->stream));
+    unsigned int cnt = 0;
+    CU(cudaMemcpyAsync(&cnt, d_count, sizeof(cnt), cudaMemcpyDeviceToHost, c->stream));
+    CU(cudaStreamSynchronize(c->stream));
+    if (cnt > 0) {
+        double *d_cn = nullptr;  // normalized centroids: too big for the arena at large m, allocate
+        CU(cudaMalloc(&d_cn, M * (size_t)cent.d * sizeof(double)));
+        cudaError_t e = launch_query_normalize(cent, d_cn, c->stream);
+        if (e == cudaSuccess) e = launch_argmax_fix(cent, data, d_cn, d_idx, d_sims, d_work, d_count, g_sm_count, c->stream);
+        if (e == cudaSuccess) e = cudaStreamSynchronize(c->stream);
+        cudaFree(d_cn);
+        if (e != cudaSuccess) return fail(VS_ECUDA, "argmax fix: %s", cudaGetErrorString(e));
+        c->launches += 2;
+        c->slowpath += cnt;
+    }
+    return VS_OK;
+}
+static size_t argmax_bytes(size_t M, size_t n) { return Arena::pad(M * 4) + Arena::pad(n * 4) + 1024; }
+
+static int argmax_check(const vs_matrix *cent, const vs_matrix *data) {
+    if (!cent || !data) return fail(VS_EINVAL, "null matrix");
+    if (cent->d != data->d)  // cosine.go:77-79
+        return fail(VS_EDIM, "matrix/matrix column size does not match: %d != %d", cent->d, data->d);
+    return VS_OK;
+}
+
+extern "C" int vs_argmax_MxN_dev(vs_ctx *c, const vs_matrix *cent, const vs_matrix *data, int32_t *d_idx_out) {
+    VS(need_dev());
+    if (!c || !d_idx_out) return fail(VS_EINVAL, "null argument");
+    VS(argmax_check(cent, data));
+    Arena a(c);
+    VS(a.reserve(argmax_bytes(cent->n, data->n)));
+    return argmax_dev(c, a, cent->view(), data->view(), d_idx_out, nullptr);
+}
+
+extern "C" int vs_argmax_MxN(vs_ctx *c, const vs_matrix *cent, const vs_matrix *data, float *sims_out, int64_t *idx_out) {
+    VS(need_dev());
+    if (!c || !idx_out) return fail(VS_EINVAL, "null argument");
+    VS(argmax_check(cent, data));
+    const size_t n = data->n;
+    Arena a(c);
+    VS(a.reserve(argmax_bytes(cent->n, n) + 2 * Arena::pad(n * 4) + 1024));
+    int32_t *d_idx = a.take<int32_t>(n);
+    float *d_sims = sims_out ? a.take<float>(n) : nullptr;
+    VS(argmax_dev(c, a, cent->view(), data->view(), d_idx, d_sims));
+    std::vector<int32_t> tmp(n);
+    CU(cudaMemcpyAsync(tmp.data(), d_idx, n * 4, cudaMemcpyDeviceToHost, c->stream));
+    if (sims_out) CU(cudaMemcpyAsync(sims_out, d_sims, n * 4, cudaMemcpyDeviceToHost, c->stream));
+    CU(cudaStreamSynchronize(c->stream));
+    for (size_t i = 0; i < n; i++) idx_out[i] = tmp[i];
+    return VS_OK;
+}
+
+// ------------------------------------------------------------------------------------------------
+// index
+__global__ void iota_kernel(uint32_t *p, size_t n) {
+    for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) p[i] = (uint32_t)i;
+}
+// off[c] = first position in sorted keys with key >= c, for c in [0, C]
+__global__ void lower_bound_kernel(const uint32_t *keys, size_t n, uint64_t *off64, uint32_t *off32, size_t C) {
+    size_t c = blockIdx.x * (size_t)blockDim.x + threadIdx.x;
+    if (c > C) return;
+    size_t lo = 0, hi = n;
+    while (lo < hi) {
+        size_t mid = (lo + hi) >> 1;
+        if (keys[mid] < (uint32_t)c) lo = mid + 1;
+        else hi = mid;
+    }
+    if (off64) off64[c] = lo;
+    if (off32) off32[c] = (uint32_t)lo;
+}
+
+// Stable sort of rows by key: d_order[i] = source row of sorted position i; d_sorted_keys optional.
+static int sort_rows_by_key(vs_ctx *c, const uint32_t *d_keys, size_t n, int key_bits, uint32_t *d_order,
+                            uint32_t *d_keys_sorted) {
+    uint32_t *d_iota = nullptr;
+    void *d_temp = nullptr;
+    size_t temp_bytes = 0;
+    CU(cudaMalloc(&d_iota, n * 4 + 4));
+    iota_kernel<<<g_sm_count * 4, 256, 0, c->stream>>>(d_iota, n);
+    c->launches++;
+    cudaError_t e = cub::DeviceRadixSort::SortPairs(nullptr, temp_bytes, d_keys, d_keys_sorted, d_iota, d_order, (int64_t)n, 0,
+                                                    key_bits, c->stream);
+    if (e == cudaSuccess) e = cudaMalloc(&d_temp, temp_bytes + 16);
+    if (e == cudaSuccess)
+        e = cub::DeviceRadixSort::SortPairs(d_temp, temp_bytes, d_keys, d_keys_sorted, d_iota, d_order, (int64_t)n, 0, key_bits,
+                                            c->stream);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(c->stream);
+    cudaFree(d_iota);
+    if (d_temp) cudaFree(d_temp);
+    if (e != cudaSuccess) return fail(VS_ECUDA, "radix sort: %s", cudaGetErrorString(e));
+    c->launches += 4;
+    return VS_OK;
+}
+
+static int bits_for(size_t C) {
+    int b = 1;
+    while ((size_t(1) << b) < C + 1 && b < 32) b++;
+    return b;
+}
+
+extern "C" void vs_index_release(vs_index *ix) {
+    if (!ix) return;
+    if (ix->data) cudaSetDevice(ix->data->device);
+    if (ix->doc_ids) cudaFree(ix->doc_ids);
+    if (ix->list_off) cudaFree(ix->list_off);
+    vs_matrix_release(ix->data);
+    vs_matrix_release(ix->centroids);
+    delete ix;
+}
+extern "C" size_t vs_index_rows(const vs_index *ix) { return ix ? ix->n : 0; }
+extern "C" size_t vs_index_lists(const vs_index *ix) { return ix ? ix->C : 0; }
+
+extern "C" int vs_index_build_dev(vs_ctx *c, const vs_matrix *data, const int32_t *d_list_of_row, const uint64_t *d_doc_ids,
+                                  uint64_t id_base, const vs_matrix *centroids, vs_index **out) {
+    VS(need_dev());
+    if (!c || !data || !centroids || !d_list_of_row || !out) return fail(VS_EINVAL, "null argument");
+    if (data->d != centroids->d) return fail(VS_EDIM, "data/centroid column size does not match: %d != %d", data->d, centroids->d);
+    const size_t n = data->n, C = centroids->n;
+    uint32_t *d_order = nullptr, *d_keys_sorted = nullptr;
+    CU(cudaMalloc(&d_order, n * 4 + 4));
+    CU(cudaMalloc(&d_keys_sorted, n * 4 + 4));
+    int rc = sort_rows_by_key(c, reinterpret_cast<const uint32_t *>(d_list_of_row), n, bits_for(C), d_order, d_keys_sorted);
+    vs_index *ix = nullptr;
+    vs_matrix *g = nullptr;
+    if (rc == VS_OK) rc = matrix_alloc(n, data->d, &g);
+    if (rc == VS_OK) {
+        ix = new vs_index();
+        ix->n = n;
+        ix->C = C;
+        ix->data = g;
+        ix->centroids = const_cast<vs_matrix *>(centroids);
+        vs_matrix_retain(ix->centroids);
+        cudaError_t e = cudaMalloc(&ix->doc_ids, n * 8 + 8);
+        if (e == cudaSuccess) e = cudaMalloc(&ix->list_off, (C + 1) * 8);
+        if (e == cudaSuccess)
+            e = launch_gather_rows(data->view(), d_order, n, g->codes, g->hdr, g->sums, d_doc_ids, id_base, ix->doc_ids, c->stream);
+        if (e == cudaSuccess) {
+            lower_bound_kernel<<<(unsigned)((C + 1 + 255) / 256), 256, 0, c->stream>>>(d_keys_sorted, n, ix->list_off, nullptr, C);
+            e = cudaGetLastError();
+        }
+        if (e == cudaSuccess) e = cudaStreamSynchronize(c->stream);
+        if (e != cudaSuccess) rc = fail(VS_ECUDA, "index build: %s", cudaGetErrorString(e));
+        c->launches += 2;
+    }
+    cudaFree(d_order);
+    cudaFree(d_keys_sorted);
+    if (rc != VS_OK) {
+        if (ix) vs_index_release(ix);
+        else if (g) vs_matrix_release(g);
+        return rc;
+    }
+    *out = ix;
+    return VS_OK;
+}
+
+extern "C" int vs_index_build_assigned(vs_ctx *c, const uint8_t *rows, size_t n, size_t row_bytes, const uint64_t *doc_ids,
+                                       const uint32_t *list_of_row, const uint8_t *centroids, size_t C, vs_index **out) {
+    VS(need_dev());
+    if (!c || !rows || !list_of_row || !centroids || !out) return fail(VS_EINVAL, "null argument");
+    VS(check_rows(n, row_bytes));
+    VS(check_rows(C, row_bytes));
+    for (size_t i = 0; i < n; i++)
+        if (list_of_row[i] >= C) return fail(VS_EINVAL, "list_of_row[%zu]=%u >= C=%zu", i, list_of_row[i], C);
+    vs_matrix *data = nullptr, *cent = nullptr;
+    VS(vs_matrix_create(c, rows, n, row_bytes, &data));
+    int rc = vs_matrix_create(c, centroids, C, row_bytes, &cent);
+    int32_t *d_list = nullptr;
+    uint64_t *d_ids = nullptr;
+    if (rc == VS_OK && cudaMalloc(&d_list, n * 4 + 4) != cudaSuccess) rc = fail(VS_ENOMEM, "cudaMalloc list_of_row");
+    if (rc == VS_OK && doc_ids && cudaMalloc(&d_ids, n * 8 + 8) != cudaSuccess) rc = fail(VS_ENOMEM, "cudaMalloc doc_ids");
+    if (rc == VS_OK) {
+        cudaError_t e = cudaMemcpyAsync(d_list, list_of_row, n * 4, cudaMemcpyHostToDevice, c->stream);
+        if (e == cudaSuccess && doc_ids) e = cudaMemcpyAsync(d_ids, doc_ids, n * 8, cudaMemcpyHostToDevice, c->stream);
+        if (e == cudaSuccess) e = cudaStreamSynchronize(c->stream);
+        if (e != cudaSuccess) rc = fail(VS_ECUDA, "index upload: %s", cudaGetErrorString(e));
+    }
+    if (rc == VS_OK) rc = vs_index_build_dev(c, data, d_list, d_ids, 0, cent, out);
+    if (d_list) cudaFree(d_list);
+    if (d_ids) cudaFree(d_ids);
+    vs_matrix_release(data);
+    if (cent) vs_matrix_release(cent);
+    return rc;
+}
+
+extern "C" int vs_index_build(vs_ctx *c, const uint8_t *rows, size_t n, size_t row_bytes, const uint64_t *doc_ids,
+                              const uint64_t *list_offsets, const uint8_t *centroids, size_t C, vs_index **out) {
+    VS(need_dev());
+    if (!c || !rows || !list_offsets || !centroids || !out) return fail(VS_EINVAL, "null argument");
+    VS(check_rows(n, row_bytes));
+    VS(check_rows(C, row_bytes));
+    if (list_offsets[0] != 0 || list_offsets[C] != n) return fail(VS_EINVAL, "list_offsets must start at 0 and end at n");
+    for (size_t i = 0; i < C; i++)
+        if (list_offsets[i] > list_offsets[i + 1]) return fail(VS_EINVAL, "list_offsets not monotone at %zu", i);
+    vs_index *ix = new vs_index();
+    ix->n = n;
+    ix->C = C;
+    int rc = vs_matrix_create(c, rows, n, row_bytes, &ix->data);
+    if (rc == VS_OK) rc = vs_matrix_create(c, centroids, C, row_bytes, &ix->centroids);
+    if (rc == VS_OK) {
+        cudaError_t e = cudaMalloc(&ix->list_off, (C + 1) * 8);
+        if (e == cudaSuccess) e = cudaMemcpyAsync(ix->list_off, list_offsets, (C + 1) * 8, cudaMemcpyHostToDevice, c->stream);
+        if (e == cudaSuccess && doc_ids) {
+            e = cudaMalloc(&ix->doc_ids, n * 8 + 8);
+            if (e == cudaSuccess) e = cudaMemcpyAsync(ix->doc_ids, doc_ids, n * 8, cudaMemcpyHostToDevice, c->stream);
+        }
+        if (e == cudaSuccess) e = cudaStreamSynchronize(c->stream);
+        if (e != cudaSuccess) rc = fail(VS_ECUDA, "index upload: %s", cudaGetErrorString(e));
+    }
+    if (rc != VS_OK) {
+        vs_index_release(ix);
+        return rc;
+    }
+    *out = ix;
+    return VS_OK;
+}
+
+// ------------------------------------------------------------------------------------------------
+// search
+static int kpl_for(size_t k) {
+    if (k <= 32) return 1;
+    if (k <= 64) return 2;
+    if (k <= 128) return 4;
+    return 0;
+}
+
+struct SearchBufs {
+    uint32_t *probe;      // [nq][npe]
+    Cand *partial1;       // stage-1 partial lists
+    Cand *partial2;       // stage-2 partial lists
+    unsigned int *tickets;  // [nq]
+    double *qnorm;        // exact only
+    uint32_t *q_select;   // exact only
+    int bpq1, bpq2;
+};
+
+static int search_plan(const vs_index *ix, size_t nq, size_t npe, int kpl1, int kpl2, bool flat, int *bpq1, int *bpq2) {
+    // Stage 1 scans C centroid rows per query, stage 2 about npe average-length lists.
+    const size_t tiles1 = (ix->C + kTileRows - 1) / kTileRows;
+    const size_t avg = ix->C ? (ix->n + ix->C - 1) / ix->C : 0;
+    const size_t tiles2 = flat ? (ix->n + kTileRows - 1) / kTileRows : npe * ((avg + kTileRows - 1) / kTileRows + 1);
+    auto pick = [&](size_t tiles, int kpl) {
+        size_t by_tiles = (tiles + kStageWarps - 1) / kStageWarps;
+        size_t occ = 2;  // resident blocks per SM (__launch_bounds__ of stage_kernel)
+        (void)kpl;
+        size_t by_sm = ((size_t)g_sm_count * occ + nq - 1) / nq;
+        size_t b = by_tiles < by_sm ? by_tiles : by_sm;
+        if (b < 1) b = 1;
+        return (int)b;
+    };
+    *bpq1 = pick(tiles1, kpl1);
+    *bpq2 = pick(tiles2, kpl2);
+    return VS_OK;
+}
+
+static size_t search_bytes(size_t nq, size_t npe, int kpl1, int kpl2, int bpq1, int bpq2, size_t d) {
+    return Arena::pad(nq * npe * 4) + Arena::pad(nq * (size_t)bpq1 * 32 * kpl1 * sizeof(Cand)) +
+           Arena::pad(nq * (size_t)bpq2 * 32 * kpl2 * sizeof(Cand)) + Arena::pad(nq * 4) + Arena::pad(nq * d * 8) +
+           Arena::pad(nq * 4) + 4096;
+}
+
+// Enqueue the two stages for nq_launch queries (all, or those listed in d_select).
+static int search_enqueue(vs_ctx *c, const vs_index *ix, const MatView &qv, size_t nq_launch, const uint32_t *d_select,
+                          size_t npe, size_t k, int kpl1, int kpl2, bool flat, bool exact, const SearchBufs &b,
+                          uint64_t *d_ids, float *d_sims, int32_t *d_counts, uint32_t *d_status, float *d_probe_sims,
+                          bool stage1_only) {
+    StageParams p{};
+    p.queries = qv;
+    p.qnorm = b.qnorm;
+    p.q_select = d_select;
+    p.nq = (int)nq_launch;
+    p.tickets = b.tickets;
+    p.out_status = d_status;
+    if (!flat) {
+        p.rows = ix->centroids->view();
+        p.ids = nullptr;
+        p.id_base = 0;
+        p.seg_list = nullptr;
+        p.single_start = 0;
+        p.single_count = ix->C;
+        p.nseg = 1;
+        p.partial = b.partial1;
+        p.mode = 1;
+        p.k = (int)npe;
+        p.out_probe = b.probe;
+        p.out_sims = d_probe_sims;
+        p.status_bit = kStatusProbeAmbiguous;
+        LAUNCH(c, launch_stage(p, kpl1, exact, b.bpq1, c->stream));
+        if (stage1_only) return VS_OK;
+    }
+    p.rows = ix->data->view();
+    p.ids = ix->doc_ids;
+    p.id_base = ix->id_base;
+    if (flat) {
+        p.seg_list = nullptr;
+        p.single_start = 0;
+        p.single_count = ix->n;
+        p.nseg = 1;
+    } else {
+        p.seg_list = b.probe;
+        p.seg_stride = (int)npe;
+        p.list_off = ix->list_off;
+        p.nseg = (int)npe;
+    }
+    p.partial = b.partial2;
+    p.mode = 0;
+    p.k = (int)k;
+    p.out_ids = d_ids;
+    p.out_sims = d_sims;
+    p.out_counts = d_counts;
+    p.out_probe = nullptr;
+    p.status_bit = kStatusListAmbiguous;
+    LAUNCH(c, launch_stage(p, kpl2, exact, b.bpq2, c->stream));
+    return VS_OK;
+}
+
+struct SearchSetup {
+    size_t npe;
+    bool flat;
+    int kpl1, kpl2;
+    SearchBufs b;
+};
+
+static int search_setup(vs_ctx *c, Arena &a, const vs_index *ix, size_t nq, size_t nprobe, size_t k, size_t extra_bytes,
+                        SearchSetup *s, bool rank_all = false) {
+    if (nq == 0) return fail(VS_EINVAL, "nq == 0");
+    if (nq > 65535) return fail(VS_ERANGE, "nq=%zu: at most 65535 queries per call", nq);
+    if (k == 0) return fail(VS_EINVAL, "k == 0");
+    if (nprobe == 0) nprobe = 1;  // search.go:118-119
+    s->flat = nprobe >= ix->C && !rank_all;  // rank_all: stage 1 only, the caller wants the ranked list itself
+    s->npe = nprobe >= ix->C ? ix->C : nprobe;
+    s->kpl2 = kpl_for(k);
+    s->kpl1 = s->flat ? 1 : kpl_for(s->npe);
+    if (!s->kpl2) return fail(VS_ERANGE, "k=%zu: at most 128 hits (Count+Offset) per query", k);
+    if (!s->kpl1) return fail(VS_ERANGE, "nprobe=%zu: at most 128 probed lists unless nprobe >= number of lists", nprobe);
+    VS(search_plan(ix, nq, s->npe, s->kpl1, s->kpl2, s->flat, &s->b.bpq1, &s->b.bpq2));
+    VS(a.reserve(a.off + extra_bytes + search_bytes(nq, s->npe, s->kpl1, s->kpl2, s->b.bpq1, s->b.bpq2, ix->data->d)));
+    return VS_OK;
+}
+
+static void search_take(Arena &a, const vs_index *ix, size_t nq, SearchSetup *s) {
+    s->b.probe = a.take<uint32_t>(nq * s->npe);
+    s->b.partial1 = a.take<Cand>(nq * (size_t)s->b.bpq1 * 32 * s->kpl1);
+    s->b.partial2 = a.take<Cand>(nq * (size_t)s->b.bpq2 * 32 * s->kpl2);
+    s->b.tickets = a.take<unsigned int>(nq);
+    s->b.qnorm = a.take<double>(nq * (size_t)ix->data->d);
+    s->b.q_select = a.take<uint32_t>(nq);
+}
+
+// Finish the queries whose status is non-zero with literal arithmetic. h_status: host copy of d_status.
+static int search_resolve_flagged(vs_ctx *c, const vs_index *ix, const MatView &qv, size_t nq, const uint32_t *h_status,
+                                  const SearchSetup &s, size_t k, uint64_t *d_ids, float *d_sims, int32_t *d_counts,
+                                  uint32_t *d_status, float *d_probe_sims, bool stage1_only, int *n_resolved) {
+    std::vector<uint32_t> sel;
+    for (size_t i = 0; i < nq; i++)
+        if (h_status[i] & (kStatusProbeAmbiguous | kStatusListAmbiguous)) sel.push_back((uint32_t)i);
+    if (n_resolved) *n_resolved = (int)sel.size();
+    if (sel.empty()) return VS_OK;
+    CU(cudaMemcpyAsync(s.b.q_select, sel.data(), sel.size() * 4, cudaMemcpyHostToDevice, c->stream));
+    LAUNCH(c, launch_query_normalize(qv, s.b.qnorm, c->stream));
+    VS(search_enqueue(c, ix, qv, sel.size(), s.b.q_select, s.npe, k, s.kpl1, s.kpl2, s.flat, true, s.b, d_ids, d_sims,
+                      d_counts, d_status, d_probe_sims, stage1_only));
+    CU(cudaStreamSynchronize(c->stream));  // sel (host) must outlive the copy
+    c->slowpath += sel.size();
+    return VS_OK;
+}
+
+static int search_check(vs_ctx *c, const vs_index *ix) {
+    VS(need_dev());
+    if (!c || !ix) return fail(VS_EINVAL, "null argument");
+    return VS_OK;
+}
+
+extern "C" int vs_search_dev(vs_ctx *c, const vs_index *ix, const vs_matrix *queries, size_t nprobe, size_t k,
+                             uint64_t *d_ids, float *d_sims, int32_t *d_counts, uint32_t *d_status) {
+    VS(search_check(c, ix));
+    if (!queries || !d_ids || !d_sims || !d_counts || !d_status) return fail(VS_EINVAL, "null argument");
+    if (queries->d != ix->data->d)
+        return fail(VS_EDIM, "vector/matrix column size does not match: %d != %d", queries->d, ix->data->d);
+    const size_t nq = queries->n;
+    Arena a(c);
+    SearchSetup s;
+    VS(search_setup(c, a, ix, nq, nprobe, k, 0, &s));
+    search_take(a, ix, nq, &s);
+    CU(cudaMemsetAsync(d_status, 0, nq * 4, c->stream));
+    CU(cudaMemsetAsync(s.b.tickets, 0, nq * 4, c->stream));
+    return search_enqueue(c, ix, queries->view(), nq, nullptr, s.npe, k, s.kpl1, s.kpl2, s.flat, false, s.b, d_ids, d_sims,
+                          d_counts, d_status, nullptr, false);
+}
+
+extern "C" int vs_search_resolve(vs_ctx *c, const vs_index *ix, const vs_matrix *queries, size_t nprobe, size_t k,
+                                 uint64_t *d_ids, float *d_sims, int32_t *d_counts, uint32_t *d_status, int *n_resolved_out) {
+    VS(search_check(c, ix));
+    if (!queries || !d_status) return fail(VS_EINVAL, "null argument");
+    const size_t nq = queries->n;
+    VS(pinned_reserve(c, nq * 4));
+    uint32_t *h_status = static_cast<uint32_t *>(c->pinned);
+    CU(cudaMemcpyAsync(h_status, d_status, nq * 4, cudaMemcpyDeviceToHost, c->stream));
+    CU(cudaStreamSynchronize(c->stream));
+    bool any = false;
+    for (size_t i = 0; i < nq; i++) any |= (h_status[i] & (kStatusProbeAmbiguous | kStatusListAmbiguous)) != 0;
+    if (n_resolved_out) *n_resolved_out = 0;
+    if (!any) return VS_OK;
+    Arena a(c);
+    SearchSetup s;
+    VS(search_setup(c, a, ix, nq, nprobe, k, 0, &s));
+    search_take(a, ix, nq, &s);
+    CU(cudaMemsetAsync(s.b.tickets, 0, nq * 4, c->stream));
+    return search_resolve_flagged(c, ix, queries->view(), nq, h_status, s, k, d_ids, d_sims, d_counts, d_status, nullptr,
+                                  false, n_resolved_out);
+}
+
+static int search_host(vs_ctx *c, const vs_index *ix, const uint8_t *queries, size_t nq, size_t nprobe, size_t k,
+                       uint64_t *ids_out, float *sims_out, int32_t *counts_out, uint32_t *probe_out, float *probe_sims_out,
+                       bool stage1_only) {
+    VS(search_check(c, ix));
+    if (!queries) return fail(VS_EINVAL, "queries is null");
+    const size_t row_bytes = 8 + (size_t)ix->data->d;
+    Arena a(c);
+    SearchSetup s;
+    const size_t out_bytes = Arena::pad(nq * k * 8) + Arena::pad(nq * k * 4) + 2 * Arena::pad(nq * 4) + Arena::pad(nq * 128 * 4) + 4096;
+    VS(search_setup(c, a, ix, nq, nprobe, k, temp_matrix_bytes(nq, row_bytes) + out_bytes, &s, stage1_only));
+    MatView qv;
+    VS(temp_matrix(c, a, queries, nq, row_bytes, &qv));
+    search_take(a, ix, nq, &s);
+    uint64_t *d_ids = a.take<uint64_t>(nq * k);
+    float *d_sims = a.take<float>(nq * k);
+    int32_t *d_counts = a.take<int32_t>(nq);
+    uint32_t *d_status = a.take<uint32_t>(nq);
+    float *d_psims = a.take<float>(nq * s.npe);
+    CU(cudaMemsetAsync(d_status, 0, nq * 4, c->stream));
+    CU(cudaMemsetAsync(s.b.tickets, 0, nq * 4, c->stream));
+    VS(search_enqueue(c, ix, qv, nq, nullptr, s.npe, k, s.kpl1, s.kpl2, s.flat, false, s.b, d_ids, d_sims, d_counts, d_status,
+                      stage1_only ? d_psims : nullptr, stage1_only));
+    VS(pinned_reserve(c, nq * 4));
+    uint32_t *h_status = static_cast<uint32_t *>(c->pinned);
+    CU(cudaMemcpyAsync(h_status, d_status, nq * 4, cudaMemcpyDeviceToHost, c->stream));
+    if (!stage1_only) {
+        CU(cudaMemcpyAsync(ids_out, d_ids, nq * k * 8, cudaMemcpyDeviceToHost, c->stream));
+        CU(cudaMemcpyAsync(sims_out, d_sims, nq * k * 4, cudaMemcpyDeviceToHost, c->stream));
+        CU(cudaMemcpyAsync(counts_out, d_counts, nq * 4, cudaMemcpyDeviceToHost, c->stream));
+    } else {
+        CU(cudaMemcpyAsync(probe_out, s.b.probe, nq * s.npe * 4, cudaMemcpyDeviceToHost, c->stream));
+        if (probe_sims_out) CU(cudaMemcpyAsync(probe_sims_out, d_psims, nq * s.npe * 4, cudaMemcpyDeviceToHost, c->stream));
+    }
+    CU(cudaStreamSynchronize(c->stream));
+    bool any = false;
+    for (size_t i = 0; i < nq; i++) any |= (h_status[i] & (kStatusProbeAmbiguous | kStatusListAmbiguous)) != 0;
+    if (any) {
+        int nres = 0;
+        VS(search_resolve_flagged(c, ix, qv, nq, h_status, s, k, d_ids, d_sims, d_counts, d_status,
+                                  stage1_only ? d_psims : nullptr, stage1_only, &nres));
+        if (!stage1_only) {
+            CU(cudaMemcpyAsync(ids_out, d_ids, nq * k * 8, cudaMemcpyDeviceToHost, c->stream));
+            CU(cudaMemcpyAsync(sims_out, d_sims, nq * k * 4, cudaMemcpyDeviceToHost, c->stream));
+            CU(cudaMemcpyAsync(counts_out, d_counts, nq * 4, cudaMemcpyDeviceToHost, c->stream));
+        } else {
+            CU(cudaMemcpyAsync(probe_out, s.b.probe, nq * s.npe * 4, cudaMemcpyDeviceToHost, c->stream));
+            if (probe_sims_out) CU(cudaMemcpyAsync(probe_sims_out, d_psims, nq * s.npe * 4, cudaMemcpyDeviceToHost, c->stream));
+        }
+        CU(cudaStreamSynchronize(c->stream));
+    }
+    return VS_OK;
+}
+
+extern "C" int vs_search(vs_ctx *c, const vs_index *ix, const uint8_t *queries, size_t nq, size_t nprobe, size_t k,
+                         uint64_t *ids_out, float *sims_out, int32_t *counts_out) {
+    if (!ids_out || !sims_out || !counts_out) return fail(VS_EINVAL, "null output");
+    return search_host(c, ix, queries, nq, nprobe, k, ids_out, sims_out, counts_out, nullptr, nullptr, false);
+}
+
+extern "C" int vs_select_probes(vs_ctx *c, const vs_index *ix, const uint8_t *queries, size_t nq, size_t nprobe,
+                                uint32_t *probe_out, float *probe_sims_out) {
+    if (!probe_out) return fail(VS_EINVAL, "null output");
+    return search_host(c, ix, queries, nq, nprobe, 1, nullptr, nullptr, nullptr, probe_out, probe_sims_out, true);
+}
+
+extern "C" int vs_search_flat(vs_ctx *c, const vs_matrix *m, const uint64_t *d_doc_ids, const uint8_t *queries, size_t nq,
+                              size_t k, uint64_t *ids_out, float *sims_out, int32_t *counts_out) {
+    VS(need_dev());
+    if (!c || !m) return fail(VS_EINVAL, "null argument");
+    // A flat scan is an index with one list and no centroid stage.
+    vs_index ix;
+    ix.data = const_cast<vs_matrix *>(m);
+    ix.centroids = nullptr;
+    ix.doc_ids = const_cast<uint64_t *>(d_doc_ids);
+    ix.n = m->n;
+    ix.C = 1;
+    return vs_search(c, &ix, queries, nq, 1, k, ids_out, sims_out, counts_out);
+}
+
+extern "C" int vs_topk_merge_dev(vs_ctx *c, const uint64_t *d_ids_in, const float *d_sims_in, const int32_t *d_counts_in,
+                                 size_t G, size_t nq, size_t k, uint64_t *d_ids_out, float *d_sims_out, int32_t *d_counts_out) {
+    VS(need_dev());
+    if (!c) return fail(VS_EINVAL, "ctx is null");
+    if (k > 128) return fail(VS_ERANGE, "k=%zu > 128", k);
+    if (nq == 0) return VS_OK;
+    LAUNCH(c, launch_topk_merge(d_ids_in, d_sims_in, d_counts_in, (int)G, (int)nq, (int)k, d_ids_out, d_sims_out, d_counts_out,
+                                c->stream));
+    return VS_OK;
+}
+
+// ------------------------------------------------------------------------------------------------
+// k-means step / recenter
+extern "C" int vs_kmeans_step(vs_ctx *c, const vs_matrix *data, const uint8_t *centroids, size_t k, float *means,
+                              int64_t *assign_out, int64_t *counts_out, uint8_t *new_centroids_out, int *converged_out) {
+    VS(need_dev());
+    if (!c || !data || !centroids || !means || !counts_out || !new_centroids_out) return fail(VS_EINVAL, "null argument");
+    if (k == 0) return fail(VS_EEMPTY, "matrix rows are empty");
+    const size_t n = data->n, d = data->d, rb = 8 + d;
+    Arena a(c);
+    VS(a.reserve(temp_matrix_bytes(k, rb) + argmax_bytes(k, n) + 4 * Arena::pad(n * 4) + Arena::pad((k + 1) * 4) +
+                 Arena::pad(k * d * 4) + Arena::pad(k * 8) + Arena::pad(k * rb) + 8192));
+    MatView cv;
+    VS(temp_matrix(c, a, centroids, k, rb, &cv));
+    int32_t *d_assign = a.take<int32_t>(n);
+    uint32_t *d_order = a.take<uint32_t>(n);
+    uint32_t *d_sorted = a.take<uint32_t>(n);
+    uint32_t *d_segoff = a.take<uint32_t>(k + 1);
+    float *d_means = a.take<float>(k * d);
+    int64_t *d_counts = a.take<int64_t>(k);
+    uint8_t *d_newc = a.take<uint8_t>(k * rb);
+    // k_means.go:73-77: nearest centroid of every row
+    VS(argmax_dev(c, a, cv, data->view(), d_assign, nullptr));
+    // member lists in ascending row order (stable sort by centroid index)
+    VS(sort_rows_by_key(c, reinterpret_cast<const uint32_t *>(d_assign), n, bits_for(k), d_order, d_sorted));
+    lower_bound_kernel<<<(unsigned)((k + 1 + 255) / 256), 256, 0, c->stream>>>(d_sorted, n, nullptr, d_segoff, k);
+    c->launches++;
+    CU(cudaMemcpyAsync(d_means, means, k * d * 4, cudaMemcpyHostToDevice, c->stream));
+    // k_means.go:80-96 accumulate + mean, :99 requantize
+    LAUNCH(c, launch_kmeans_accumulate(data->view(), d_order, d_segoff, (int)k, d_means, d_counts, c->stream));
+    LAUNCH(c, launch_quantize_f32(d_means, k, (int)d, d_newc, c->stream));
+    std::vector<int32_t> tmp;
+    if (assign_out) {
+        tmp.resize(n);
+        CU(cudaMemcpyAsync(tmp.data(), d_assign, n * 4, cudaMemcpyDeviceToHost, c->stream));
+    }
+    CU(cudaMemcpyAsync(means, d_means, k * d * 4, cudaMemcpyDeviceToHost, c->stream));
+    CU(cudaMemcpyAsync(counts_out, d_counts, k * 8, cudaMemcpyDeviceToHost, c->stream));
+    CU(cudaMemcpyAsync(new_centroids_out, d_newc, k * rb, cudaMemcpyDeviceToHost, c->stream));
+    CU(cudaStreamSynchronize(c->stream));
+    if (assign_out)
+        for (size_t i = 0; i < n; i++) assign_out[i] = tmp[i];
+    if (converged_out) {  // k_means.go:102-108: code bytes [8:] unchanged for every centroid
+        int conv = 1;
+        for (size_t j = 0; j < k && conv; j++)
+            if (memcmp(new_centroids_out + j * rb + 8, centroids + j * rb + 8, d) != 0) conv = 0;
+        *converged_out = conv;
+    }
+    return VS_OK;
+}
+
+extern "C" int vs_recenter(vs_ctx *c, const vs_matrix *m, uint8_t *out_row) {
+    VS(need_dev());
+    if (!c || !m || !out_row) return fail(VS_EINVAL, "null argument");
+    const size_t d = m->d, rb = 8 + d;
+    Arena a(c);
+    VS(a.reserve(Arena::pad(d * 8) + Arena::pad(rb) + 1024));
+    double *d_mean = a.take<double>(d);
+    uint8_t *d_row = a.take<uint8_t>(rb);
+    LAUNCH(c, launch_recenter(m->view(), d_mean, c->stream));
+    LAUNCH(c, launch_quantize_f64(d_mean, 1, (int)d, d_row, c->stream));
+    CU(cudaMemcpyAsync(out_row, d_row, rb, cudaMemcpyDeviceToHost, c->stream));
+    CU(cudaStreamSynchronize(c->stream));
+    return VS_OK;
+}

@@ -1,0 +1,123 @@
+// internal.h -- host-side declarations shared by the .cu translation units of libvscuda.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include <atomic>
+
+#include "common.cuh"
+
+struct vs_ctx {
+    int device = 0;
+    cudaStream_t stream = nullptr;
+    cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+    uint64_t launches = 0;
+    uint64_t slowpath = 0;
+    // scratch arena (device) grown on demand; pinned host staging
+    void *scratch = nullptr;
+    size_t scratch_cap = 0;
+    void *pinned = nullptr;
+    size_t pinned_cap = 0;
+};
+
+struct vs_matrix {
+    std::atomic<int> refs{1};
+    int device = 0;
+    uint8_t *codes = nullptr;
+    float2 *hdr = nullptr;
+    uint2 *sums = nullptr;
+    size_t n = 0;
+    int d = 0;
+    int d_pad = 0;
+    bool owns = true;
+    vs::MatView view() const { return vs::MatView{codes, hdr, sums, n, d, d_pad}; }
+};
+
+struct vs_index {
+    vs_matrix *data = nullptr;       // rows grouped by list
+    vs_matrix *centroids = nullptr;  // C rows
+    uint64_t *doc_ids = nullptr;     // [n] device (may be null -> id = id_base + row)
+    uint64_t id_base = 0;
+    uint64_t *list_off = nullptr;    // [C+1] device
+    size_t n = 0, C = 0;
+};
+
+namespace vs {
+
+constexpr int kMaxSeg = 1024;     // max probed lists per query handled by one stage launch
+constexpr int kStageWarps = 8;    // warps per block of the stage kernel
+constexpr int kTileRows = 32;     // rows scored per warp tile
+
+// Parameters of one stage launch (probe selection, list scan or flat scan) for nq queries.
+struct StageParams {
+    MatView rows;                 // matrix being scanned
+    const uint64_t *ids;          // per-row id (doc id) or null -> id_base + row
+    uint64_t id_base;
+    MatView queries;              // nq query rows
+    const double *qnorm;          // EXACT only: [nq][d] normalized queries
+    const uint32_t *q_select;     // optional: [nq_launch] indices into queries/outputs (resolve path) or null
+    int nq;                       // queries in this launch (gridDim.y)
+    // segments
+    const uint32_t *seg_list;     // [q][seg_stride] list ids, or null = single segment
+    int seg_stride;
+    const uint64_t *list_off;     // CSR offsets when seg_list != null
+    int nseg;
+    uint64_t single_start, single_count;
+    // merge state
+    Cand *partial;                // [nq][gridDim.x][CAP]
+    unsigned int *tickets;        // [nq], zeroed; reset by the last block
+    // outputs
+    int mode;                     // 0 = final hits, 1 = probe list
+    int k;                        // hits (mode 0) or probes (mode 1) to emit
+    uint64_t *out_ids;            // mode 0: [q][k]
+    float *out_sims;              // mode 0: [q][k]; mode 1 (optional): [q][k]
+    int32_t *out_counts;          // mode 0: [q]
+    uint32_t *out_probe;          // mode 1: [q][k]
+    uint32_t *out_status;         // [q], OR-ed with status_bit / need-more bit
+    uint32_t status_bit;
+};
+
+constexpr uint32_t kStatusProbeAmbiguous = 1u;
+constexpr uint32_t kStatusListAmbiguous = 2u;
+constexpr uint32_t kStatusNeedMore = 4u;
+
+// scan.cu
+cudaError_t launch_stage(const StageParams &p, int kpl, bool exact, int blocks_per_query, cudaStream_t st);
+int stage_cap(int kpl);
+cudaError_t launch_query_normalize(const MatView &queries, double *qnorm, cudaStream_t st);
+cudaError_t launch_cosine_1xN(const MatView &rows, const MatView &query, float *sims, uint32_t *dots,
+                              uint32_t *worklist, unsigned int *work_count, int sm_count, cudaStream_t st);
+cudaError_t launch_cosine_fix(const MatView &rows, const double *qnorm, float *sims, const uint32_t *worklist,
+                              const unsigned int *work_count, int sm_count, cudaStream_t st);
+cudaError_t launch_topk_merge(const uint64_t *ids_in, const float *sims_in, const int32_t *counts_in, int G, int nq,
+                              int k, uint64_t *ids_out, float *sims_out, int32_t *counts_out, cudaStream_t st);
+
+// quantize.cu
+cudaError_t launch_quantize_f32(const float *in, size_t n, int d, uint8_t *out_rows, cudaStream_t st);
+cudaError_t launch_quantize_f64(const double *in, size_t n, int d, uint8_t *out_rows, cudaStream_t st);
+cudaError_t launch_quantize_f32_soa(const float *in, size_t n, int d, uint8_t *codes, int d_pad, float2 *hdr,
+                                    uint2 *sums, cudaStream_t st);
+cudaError_t launch_dequantize_f32(const uint8_t *rows, size_t n, int row_bytes, float *out, cudaStream_t st);
+cudaError_t launch_dequantize_f64(const uint8_t *rows, size_t n, int row_bytes, double *out, cudaStream_t st);
+cudaError_t launch_ingest(const uint8_t *rows, size_t n, int row_bytes, uint8_t *codes, int d_pad, float2 *hdr,
+                          uint2 *sums, cudaStream_t st);
+cudaError_t launch_export(const MatView &m, size_t first, size_t count, uint8_t *rows_out, cudaStream_t st);
+cudaError_t launch_gather_rows(const MatView &src, const uint32_t *order, size_t n, uint8_t *codes, float2 *hdr,
+                               uint2 *sums, const uint64_t *ids_in, uint64_t id_base, uint64_t *ids_out,
+                               cudaStream_t st);
+
+// argmax.cu
+cudaError_t launch_argmax(const MatView &cent, const MatView &data, const uint32_t *canon, int32_t *idx_out,
+                          float *sims_out, uint32_t *worklist, unsigned int *work_count, int sm_count,
+                          cudaStream_t st);
+cudaError_t launch_argmax_fix(const MatView &cent, const MatView &data, const double *cnorm, int32_t *idx_out,
+                              float *sims_out, const uint32_t *worklist, const unsigned int *work_count, int sm_count,
+                              cudaStream_t st);
+cudaError_t launch_canonical_rows(const MatView &m, uint32_t *canon, cudaStream_t st);
+
+// kmeans.cu
+cudaError_t launch_kmeans_accumulate(const MatView &data, const uint32_t *order, const uint32_t *seg_off, int k,
+                                     float *means, int64_t *counts, cudaStream_t st);
+cudaError_t launch_recenter(const MatView &data, double *mean_out, cudaStream_t st);
+
+}  // namespace vs

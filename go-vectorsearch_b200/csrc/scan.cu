@@ -1,0 +1,601 @@
+// scan.cu -- the streaming uint8 scan with fused top-k (K3 + K5 of SURVEY.md 2b).
+//
+// Replaces: compute/cosine.go:13-57 (vector x matrix cosine) as driven by server/search.go:214
+// (centroid scoring), :220-223 (nprobe cut), :241-273 (posting-list scan, running sort, dedup,
+// truncate).  One kernel template serves the three shapes -- probe selection over the centroid
+// table, the scan of the probed lists, and a flat scan -- as "segments" of a device matrix.
+//
+// Per row the only vector x vector work is the exact integer dot sum(q*v) (dp4a); the float64 cosine
+// is rebuilt from it and per-row integer sums (common.cuh), with a rigorous error bound that tells
+// when float32(score) is certain to equal the reference's.  Uncertain rows are flagged and resolved
+// by the literal-arithmetic variant (EXACT=true) of the same kernel.
+//
+// Layout: a warp owns a tile of 32 consecutive rows. Lane groups of G lanes each stream one row per
+// iteration with 128-bit loads (G*16 contiguous bytes per load instruction per group); the G-lane
+// shuffle reduction leaves row (g*G+it)'s dot in lane g*G+it, so after G iterations every lane holds
+// one row's dot and the float64 finishing math runs on all 32 lanes at once.
+#include <cstdio>
+
+#include "internal.h"
+
+namespace vs {
+
+#define FULL 0xFFFFFFFFu
+
+// ---------------------------------------------------------------------------------------------------
+// Warp-distributed sorted top list: rank r lives in slot r/32 of lane r%32, best first.
+template <int KPL>
+struct WarpTopK {
+    uint32_t skey[KPL];
+    uint32_t meta[KPL];
+    uint64_t id[KPL];
+    uint32_t thr_key;  // worst kept entry (rank 32*KPL-1), warp-uniform
+    uint64_t thr_id;
+
+    __device__ __forceinline__ void init() {
+#pragma unroll
+        for (int s = 0; s < KPL; s++) {
+            skey[s] = 0;
+            meta[s] = 0;
+            id[s] = kEmptyId;
+        }
+        thr_key = 0;
+        thr_id = kEmptyId;
+    }
+
+    // Insert one (warp-uniform) candidate.
+    __device__ __forceinline__ void insert(uint32_t ck, uint32_t cm, uint64_t cid, int lane) {
+        int pos = 0;
+#pragma unroll
+        for (int s = 0; s < KPL; s++) {
+            bool ahead = !cand_better(ck, cid, skey[s], id[s]);
+            pos += __popc(__ballot_sync(FULL, ahead));
+        }
+        if (pos >= 32 * KPL) return;
+        uint32_t ck_prev = 0, cm_prev = 0;
+        uint64_t cid_prev = 0;
+        const int src = (lane + 31) & 31;
+#pragma unroll
+        for (int s = 0; s < KPL; s++) {
+            uint32_t rk = __shfl_sync(FULL, skey[s], src);
+            uint32_t rm = __shfl_sync(FULL, meta[s], src);
+            uint64_t rid = __shfl_sync(FULL, id[s], src);
+            uint32_t sk = lane == 0 ? ck_prev : rk;
+            uint32_t sm = lane == 0 ? cm_prev : rm;
+            uint64_t sid = lane == 0 ? cid_prev : rid;
+            int r = s * 32 + lane;
+            if (r == pos) {
+                skey[s] = ck;
+                meta[s] = cm;
+                id[s] = cid;
+            } else if (r > pos) {
+                skey[s] = sk;
+                meta[s] = sm;
+                id[s] = sid;
+            }
+            ck_prev = rk;  // on lane 0: the old rank 32*s+31, which moves to rank 32*(s+1)
+            cm_prev = rm;
+            cid_prev = rid;
+        }
+        thr_key = __shfl_sync(FULL, skey[KPL - 1], 31);
+        thr_id = __shfl_sync(FULL, id[KPL - 1], 31);
+    }
+
+    // Offer one candidate per lane.
+    __device__ __forceinline__ void offer(bool valid, uint32_t ck, uint32_t cm, uint64_t cid, int lane) {
+        bool pass = valid && cand_better(ck, cid, thr_key, thr_id);
+        unsigned m = __ballot_sync(FULL, pass);
+        while (m) {
+            int src = __ffs(m) - 1;
+            m &= m - 1;
+            uint32_t bk = __shfl_sync(FULL, ck, src);
+            uint32_t bm = __shfl_sync(FULL, cm, src);
+            uint64_t bid = __shfl_sync(FULL, cid, src);
+            insert(bk, bm, bid, lane);
+        }
+    }
+
+    __device__ __forceinline__ void store(Cand *dst, int lane) const {
+#pragma unroll
+        for (int s = 0; s < KPL; s++) {
+            Cand c;
+            c.skey = skey[s];
+            c.meta = meta[s];
+            c.id = id[s];
+            dst[s * 32 + lane] = c;
+        }
+    }
+
+    // Offer a stored list (32*KPL entries, sorted best-first).
+    __device__ __forceinline__ void merge_from(const Cand *src, int lane, bool use_ldcg) {
+#pragma unroll
+        for (int s = 0; s < KPL; s++) {
+            Cand c;
+            if (use_ldcg) {
+                const uint4 *p = reinterpret_cast<const uint4 *>(src + s * 32 + lane);
+                uint4 v = __ldcg(p);
+                c.skey = v.x;
+                c.meta = v.y;
+                c.id = (uint64_t)v.z | ((uint64_t)v.w << 32);
+            } else {
+                c = src[s * 32 + lane];
+            }
+            // lists are sorted: once a whole chunk fails the threshold the rest fails too
+            bool any = __any_sync(FULL, c.skey != 0 && cand_better(c.skey, c.id, thr_key, thr_id));
+            if (!any) break;
+            offer(c.skey != 0, c.skey, c.meta, c.id, lane);
+        }
+    }
+};
+
+// ---------------------------------------------------------------------------------------------------
+// Tile dot products. Returns in each lane the integer dot of row (row0 + lane) with the query.
+template <int G, int CPL>
+__device__ __forceinline__ uint32_t tile_dots(const uint8_t *__restrict__ codes, size_t row0, int nrows, int d_pad,
+                                              const uint4 (&q)[CPL], int lane) {
+    constexpr int U = (CPL <= 3) ? 4 : 2;  // rows in flight per lane group
+    const int g = lane / G, l = lane % G;
+    uint32_t mydot = 0;
+#pragma unroll 1
+    for (int it0 = 0; it0 < G; it0 += U) {
+        uint4 v[U][CPL];
+#pragma unroll
+        for (int u = 0; u < U; u++) {
+            int r = g * G + it0 + u;
+            bool ok = (it0 + u < G) && (r < nrows);
+            const uint8_t *p = codes + (row0 + (size_t)(ok ? r : 0)) * (size_t)d_pad + l * 16;
+#pragma unroll
+            for (int j = 0; j < CPL; j++) v[u][j] = ok ? ld_stream_u4(p + j * G * 16) : make_uint4(0, 0, 0, 0);
+        }
+#pragma unroll
+        for (int u = 0; u < U; u++) {
+            uint32_t acc = 0;
+#pragma unroll
+            for (int j = 0; j < CPL; j++) acc = dot16(v[u][j], q[j], acc);
+#pragma unroll
+            for (int o = G / 2; o > 0; o >>= 1) acc += __shfl_xor_sync(FULL, acc, o);
+            if (l == it0 + u) mydot = acc;
+        }
+    }
+    return mydot;
+}
+
+// Any dimension: whole warp per row, query chunks read from shared memory.
+__device__ __forceinline__ uint32_t tile_dots_generic(const uint8_t *__restrict__ codes, size_t row0, int nrows,
+                                                      int d_pad, const uint4 *__restrict__ qs, int lane) {
+    const int CH = d_pad >> 4;
+    uint32_t mydot = 0;
+    for (int r = 0; r < nrows; r++) {
+        const uint8_t *p = codes + (row0 + r) * (size_t)d_pad;
+        uint32_t acc = 0;
+        for (int c = lane; c < CH; c += 32) acc = dot16(ld_stream_u4(p + c * 16), qs[c], acc);
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(FULL, acc, o);
+        if (lane == r) mydot = acc;
+    }
+    return mydot;
+}
+
+// ---------------------------------------------------------------------------------------------------
+struct StageShared {
+    uint32_t tile_prefix[kMaxSeg + 1];
+    uint64_t seg_start[kMaxSeg];
+    uint32_t seg_len[kMaxSeg];
+    SideConst qside;
+    unsigned int is_last;
+};
+
+// G == 0 selects the generic (any d) tile routine; EXACT selects literal reference arithmetic.
+template <int G, int CPL, int KPL, bool EXACT>
+__global__ void __launch_bounds__(kStageWarps * 32, 2)
+stage_kernel(const StageParams p) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    StageShared &sh = *reinterpret_cast<StageShared *>(smem_raw);
+    Cand *sh_lists = reinterpret_cast<Cand *>(smem_raw + ((sizeof(StageShared) + 15) & ~size_t(15)));
+    uint4 *sh_q = reinterpret_cast<uint4 *>(sh_lists + (size_t)kStageWarps * 32 * KPL);  // generic path only
+
+    constexpr int CAP = 32 * KPL;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int qslot = blockIdx.y;
+    const int qi = p.q_select ? (int)p.q_select[qslot] : qslot;
+    const int D = p.rows.d, d_pad = p.rows.d_pad;
+
+    // ---- prologue: segment table, query constants ----
+    const int nseg = p.seg_list ? p.nseg : 1;
+    for (int s = threadIdx.x; s < nseg; s += blockDim.x) {
+        uint64_t st, len;
+        if (p.seg_list) {
+            uint32_t L = p.seg_list[(size_t)qi * p.seg_stride + s];
+            st = p.list_off[L];
+            len = p.list_off[L + 1] - st;
+        } else {
+            st = p.single_start;
+            len = p.single_count;
+        }
+        sh.seg_start[s] = st;
+        sh.seg_len[s] = (uint32_t)len;
+    }
+    if (threadIdx.x == 0) {
+        float2 h = p.queries.hdr[qi];
+        uint2 s = p.queries.sums[qi];
+        sh.qside = make_side(h.x, h.y, s.x, s.y, D);
+    }
+    if (G == 0 && !EXACT) {
+        const uint4 *qsrc = reinterpret_cast<const uint4 *>(p.queries.codes + (size_t)qi * d_pad);
+        for (int c = threadIdx.x; c < (d_pad >> 4); c += blockDim.x) sh_q[c] = qsrc[c];
+    }
+    __syncthreads();
+    if (warp == 0) {  // inclusive scan of tiles per segment
+        uint32_t carry = 0;
+        for (int base = 0; base < nseg; base += 32) {
+            int s = base + lane;
+            uint32_t v = s < nseg ? (sh.seg_len[s] + kTileRows - 1) / kTileRows : 0;
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) {
+                uint32_t t = __shfl_up_sync(FULL, v, o);
+                if (lane >= o) v += t;
+            }
+            if (s < nseg) sh.tile_prefix[s + 1] = carry + v;
+            carry += __shfl_sync(FULL, v, 31);
+        }
+        if (lane == 0) sh.tile_prefix[0] = 0;
+    }
+    __syncthreads();
+    const uint32_t total_tiles = sh.tile_prefix[nseg];
+    const SideConst xq = sh.qside;
+    const double sqrtD = sqrt((double)D);
+
+    uint4 qreg[CPL > 0 ? CPL : 1];
+    if constexpr (G != 0 && !EXACT) {
+        const uint8_t *qc = p.queries.codes + (size_t)qi * d_pad;
+#pragma unroll
+        for (int j = 0; j < CPL; j++) qreg[j] = *reinterpret_cast<const uint4 *>(qc + ((lane % G) + G * j) * 16);
+    }
+    const double *qn = EXACT ? p.qnorm + (size_t)qi * D : nullptr;
+
+    WarpTopK<KPL> top;
+    top.init();
+
+    // ---- main loop: warp tiles ----
+    const uint32_t wstride = gridDim.x * kStageWarps;
+    for (uint32_t t = blockIdx.x * kStageWarps + warp; t < total_tiles; t += wstride) {
+        int lo = 0, hi = nseg;  // find seg with prefix[seg] <= t < prefix[seg+1]
+        while (hi - lo > 1) {
+            int mid = (lo + hi) >> 1;
+            if (sh.tile_prefix[mid] <= t) lo = mid;
+            else hi = mid;
+        }
+        const uint32_t tin = t - sh.tile_prefix[lo];
+        const size_t row0 = sh.seg_start[lo] + (size_t)tin * kTileRows;
+        const int nrows = min((uint32_t)kTileRows, sh.seg_len[lo] - tin * kTileRows);
+        const size_t row = row0 + lane;
+        const bool valid = lane < nrows;
+
+        float sim;
+        bool flag = false;
+        if constexpr (EXACT) {
+            sim = 0.0f;
+            if (valid) {
+                float2 h = p.rows.hdr[row];
+                sim = ref_cosine_row(p.rows.codes + row * (size_t)d_pad, h.x, h.y, qn, D);
+            }
+        } else {
+            uint32_t mydot;
+            if constexpr (G != 0) mydot = tile_dots<G, CPL>(p.rows.codes, row0, nrows, d_pad, qreg, lane);
+            else mydot = tile_dots_generic(p.rows.codes, row0, nrows, d_pad, sh_q, lane);
+            float2 h = valid ? p.rows.hdr[row] : make_float2(0.f, 0.f);
+            uint2 s = valid ? p.rows.sums[row] : make_uint2(0, 0);
+            SideConst y = make_side(h.x, h.y, s.x, s.y, D);
+            sim = score_certified(xq, y, mydot, D, sqrtD, &flag);
+        }
+        uint32_t key = f32_to_key(sim);
+        // lazy id: only rows that can still enter the list need their document id
+        uint64_t cid = kEmptyId;
+        if (valid && key >= top.thr_key) cid = p.ids ? p.ids[row] : p.id_base + row;
+        top.offer(valid && key >= top.thr_key, key, flag ? kFlagBit : 0u, cid, lane);
+    }
+
+    // ---- block merge: all warps -> warp 0 ----
+    top.store(sh_lists + (size_t)warp * CAP, lane);
+    __syncthreads();
+    Cand *my_partial = p.partial + ((size_t)qslot * gridDim.x + blockIdx.x) * CAP;
+    if (warp == 0) {
+        for (int w = 1; w < kStageWarps; w++) top.merge_from(sh_lists + (size_t)w * CAP, lane, false);
+        top.store(my_partial, lane);
+        __threadfence();
+        if (lane == 0) {
+            unsigned int tk = atomicAdd(&p.tickets[qslot], 1u);
+            sh.is_last = (tk == gridDim.x - 1) ? 1u : 0u;
+        }
+    }
+    __syncthreads();
+    if (!sh.is_last) return;
+
+    // ---- last block of this query: merge every block's list ----
+    __threadfence();
+    top.init();
+    for (int b = warp; b < (int)gridDim.x; b += kStageWarps)
+        top.merge_from(p.partial + ((size_t)qslot * gridDim.x + b) * CAP, lane, true);
+    __syncthreads();
+    top.store(sh_lists + (size_t)warp * CAP, lane);
+    __syncthreads();
+    if (warp != 0) return;
+    for (int w = 1; w < kStageWarps; w++) top.merge_from(sh_lists + (size_t)w * CAP, lane, false);
+    if (lane == 0) p.tickets[qslot] = 0;  // re-arm for the next launch
+
+    // ---- emit ----
+    uint32_t status = 0;
+    if (p.mode == 1) {  // probe list: ids are unique list indices, no dedup
+        bool anyflag = false;
+#pragma unroll
+        for (int s = 0; s < KPL; s++) {
+            int r = s * 32 + lane;
+            bool in = r < p.k && top.skey[s] != 0;
+            if (in) {
+                p.out_probe[(size_t)qi * p.k + r] = (uint32_t)top.id[s];
+                if (p.out_sims) p.out_sims[(size_t)qi * p.k + r] = key_to_f32(top.skey[s]);
+            }
+            anyflag |= __any_sync(FULL, in && (top.meta[s] & kFlagBit));
+        }
+        if (anyflag) status |= p.status_bit;
+    } else {
+        // dedup by id keeping the best-ranked entry (server/search.go:260-268)
+        bool dup[KPL];
+#pragma unroll
+        for (int s = 0; s < KPL; s++) dup[s] = false;
+#pragma unroll
+        for (int s0 = 0; s0 < KPL; s0++) {
+            for (int l0 = 0; l0 < 32; l0++) {
+                uint64_t bid = __shfl_sync(FULL, top.id[s0], l0);
+                uint32_t bk = __shfl_sync(FULL, top.skey[s0], l0);
+                if (bk == 0) break;  // rest of the list is empty (warp-uniform)
+#pragma unroll
+                for (int s = 0; s < KPL; s++) {
+                    int r = s * 32 + lane;
+                    if (r > s0 * 32 + l0 && top.skey[s] != 0 && top.id[s] == bid) dup[s] = true;
+                }
+            }
+        }
+        int base = 0;
+        int uniq_total = 0;
+        bool anyflag = false;
+        bool full = __shfl_sync(FULL, top.skey[KPL - 1], 31) != 0;
+#pragma unroll
+        for (int s = 0; s < KPL; s++) {
+            bool keep = top.skey[s] != 0 && !dup[s];
+            unsigned m = __ballot_sync(FULL, keep);
+            int outpos = base + __popc(m & ((1u << lane) - 1u));
+            if (keep && outpos < p.k) {
+                p.out_ids[(size_t)qi * p.k + outpos] = top.id[s];
+                p.out_sims[(size_t)qi * p.k + outpos] = key_to_f32(top.skey[s]);
+            }
+            // every entry (kept or duplicate) ranked before the k-th unique one must be certain
+            anyflag |= __any_sync(FULL, top.skey[s] != 0 && outpos < p.k && (top.meta[s] & kFlagBit));
+            base += __popc(m);
+        }
+        uniq_total = base;
+        if (anyflag) status |= p.status_bit;
+        if (uniq_total < p.k && full) status |= kStatusNeedMore;
+        if (lane == 0) p.out_counts[qi] = min(uniq_total, p.k);
+    }
+    if (lane == 0 && p.out_status) {
+        if (EXACT) p.out_status[qi] = (p.out_status[qi] & ~p.status_bit) | (status & kStatusNeedMore);
+        else p.out_status[qi] |= status;
+    }
+}
+
+// ---------------------------------------------------------------------------------------------------
+int stage_cap(int kpl) { return 32 * kpl; }
+
+template <int G, int CPL, int KPL, bool EXACT>
+static cudaError_t launch_stage_t(const StageParams &p, int blocks_per_query, cudaStream_t st) {
+    size_t smem = ((sizeof(StageShared) + 15) & ~size_t(15)) + (size_t)kStageWarps * 32 * KPL * sizeof(Cand);
+    if (G == 0) smem += (size_t)p.rows.d_pad;
+    auto kern = stage_kernel<G, CPL, KPL, EXACT>;
+    if (smem > 48 * 1024) {
+        cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (e != cudaSuccess) return e;
+    }
+    dim3 grid(blocks_per_query, p.nq);
+    kern<<<grid, kStageWarps * 32, smem, st>>>(p);
+    return cudaGetLastError();
+}
+
+template <int KPL>
+static cudaError_t launch_stage_k(const StageParams &p, bool exact, int bpq, cudaStream_t st) {
+    if (exact) return launch_stage_t<0, 0, KPL, true>(p, bpq, st);
+    const int ch = p.rows.d_pad >> 4;
+    switch (ch) {
+        case 48: return launch_stage_t<16, 3, KPL, false>(p, bpq, st);  // 768-d (nomic-embed-text)
+        case 32: return launch_stage_t<32, 1, KPL, false>(p, bpq, st);  // 512-d (noop/ai.go)
+        case 64: return launch_stage_t<32, 2, KPL, false>(p, bpq, st);  // 1024-d
+        case 96: return launch_stage_t<32, 3, KPL, false>(p, bpq, st);  // 1536-d
+        case 24: return launch_stage_t<8, 3, KPL, false>(p, bpq, st);   // 384-d
+        default: return launch_stage_t<0, 0, KPL, false>(p, bpq, st);
+    }
+}
+
+cudaError_t launch_stage(const StageParams &p, int kpl, bool exact, int blocks_per_query, cudaStream_t st) {
+    switch (kpl) {
+        case 1: return launch_stage_k<1>(p, exact, blocks_per_query, st);
+        case 2: return launch_stage_k<2>(p, exact, blocks_per_query, st);
+        case 4: return launch_stage_k<4>(p, exact, blocks_per_query, st);
+        default: return cudaErrorInvalidValue;
+    }
+}
+
+// ---------------------------------------------------------------------------------------------------
+// normalizeVector of each query (compute/cosine.go:26,138-149) in literal float64: one thread sums
+// sequentially, then the block divides.
+__global__ void query_normalize_kernel(MatView q, double *qnorm) {
+    __shared__ double s_norm;
+    const int qi = blockIdx.x;
+    const int D = q.d;
+    const uint8_t *codes = q.codes + (size_t)qi * q.d_pad;
+    const float2 h = q.hdr[qi];
+    const double mn = (double)h.x, range = __dsub_rn((double)h.y, (double)h.x);
+    if (threadIdx.x == 0) {
+        double norm = 0.0;
+        for (int i = 0; i < D; i++) {
+            double x = ref_dequant_f64(codes[i], mn, range);
+            norm = __dadd_rn(norm, __dmul_rn(x, x));
+        }
+        s_norm = __dsqrt_rn(norm);
+    }
+    __syncthreads();
+    const double norm = s_norm;
+    for (int i = threadIdx.x; i < D; i += blockDim.x) {
+        double x = ref_dequant_f64(codes[i], mn, range);
+        if (norm != 0.0) x = __ddiv_rn(x, norm);
+        qnorm[(size_t)qi * D + i] = x;
+    }
+}
+
+cudaError_t launch_query_normalize(const MatView &queries, double *qnorm, cudaStream_t st) {
+    query_normalize_kernel<<<(unsigned)queries.n, 128, 0, st>>>(queries, qnorm);
+    return cudaGetLastError();
+}
+
+// ---------------------------------------------------------------------------------------------------
+// Full 1xN scores (compute/cosine.go:13-57 as an API: sims[i] for every row).
+template <int G, int CPL>
+__global__ void __launch_bounds__(256, 3)
+cosine_1xN_kernel(MatView rows, MatView query, float *sims, uint32_t *dots, uint32_t *worklist,
+                  unsigned int *work_count) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    uint4 *sh_q = reinterpret_cast<uint4 *>(smem_raw);
+    __shared__ SideConst s_q;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int D = rows.d, d_pad = rows.d_pad;
+    if (threadIdx.x == 0) {
+        float2 h = query.hdr[0];
+        uint2 s = query.sums[0];
+        s_q = make_side(h.x, h.y, s.x, s.y, D);
+    }
+    if (G == 0) {
+        const uint4 *qsrc = reinterpret_cast<const uint4 *>(query.codes);
+        for (int c = threadIdx.x; c < (d_pad >> 4); c += blockDim.x) sh_q[c] = qsrc[c];
+    }
+    __syncthreads();
+    const SideConst xq = s_q;
+    const double sqrtD = sqrt((double)D);
+    uint4 qreg[CPL > 0 ? CPL : 1];
+    if constexpr (G != 0) {
+#pragma unroll
+        for (int j = 0; j < CPL; j++) qreg[j] = *reinterpret_cast<const uint4 *>(query.codes + ((lane % G) + G * j) * 16);
+    }
+    const size_t ntiles = (rows.n + kTileRows - 1) / kTileRows;
+    const size_t wstride = (size_t)gridDim.x * (blockDim.x >> 5);
+    for (size_t t = (size_t)blockIdx.x * (blockDim.x >> 5) + warp; t < ntiles; t += wstride) {
+        const size_t row0 = t * kTileRows;
+        const int nrows = (int)min((size_t)kTileRows, rows.n - row0);
+        uint32_t mydot;
+        if constexpr (G != 0) mydot = tile_dots<G, CPL>(rows.codes, row0, nrows, d_pad, qreg, lane);
+        else mydot = tile_dots_generic(rows.codes, row0, nrows, d_pad, sh_q, lane);
+        if (lane < nrows) {
+            const size_t row = row0 + lane;
+            if (dots) dots[row] = mydot;
+            if (sims) {
+                float2 h = rows.hdr[row];
+                uint2 s = rows.sums[row];
+                SideConst y = make_side(h.x, h.y, s.x, s.y, D);
+                bool flag;
+                float sim = score_certified(xq, y, mydot, D, sqrtD, &flag);
+                sims[row] = sim;
+                if (flag) worklist[atomicAdd(work_count, 1u)] = (uint32_t)row;
+            }
+        }
+    }
+}
+
+cudaError_t launch_cosine_1xN(const MatView &rows, const MatView &query, float *sims, uint32_t *dots,
+                              uint32_t *worklist, unsigned int *work_count, int sm_count, cudaStream_t st) {
+    const size_t ntiles = (rows.n + kTileRows - 1) / kTileRows;
+    size_t blocks = (ntiles + 7) / 8;
+    const size_t maxb = (size_t)sm_count * 8;
+    if (blocks > maxb) blocks = maxb;
+    if (blocks < 1) blocks = 1;
+    const int ch = rows.d_pad >> 4;
+    switch (ch) {
+        case 48: cosine_1xN_kernel<16, 3><<<(unsigned)blocks, 256, 0, st>>>(rows, query, sims, dots, worklist, work_count); break;
+        case 32: cosine_1xN_kernel<32, 1><<<(unsigned)blocks, 256, 0, st>>>(rows, query, sims, dots, worklist, work_count); break;
+        case 64: cosine_1xN_kernel<32, 2><<<(unsigned)blocks, 256, 0, st>>>(rows, query, sims, dots, worklist, work_count); break;
+        case 96: cosine_1xN_kernel<32, 3><<<(unsigned)blocks, 256, 0, st>>>(rows, query, sims, dots, worklist, work_count); break;
+        case 24: cosine_1xN_kernel<8, 3><<<(unsigned)blocks, 256, 0, st>>>(rows, query, sims, dots, worklist, work_count); break;
+        default: cosine_1xN_kernel<0, 0><<<(unsigned)blocks, 256, rows.d_pad, st>>>(rows, query, sims, dots, worklist, work_count); break;
+    }
+    return cudaGetLastError();
+}
+
+// Rows whose float32 rounding could not be certified: literal reference arithmetic, one thread per row.
+__global__ void cosine_fix_kernel(MatView rows, const double *qnorm, float *sims, const uint32_t *worklist,
+                                  const unsigned int *work_count) {
+    const unsigned int n = *work_count;
+    for (unsigned int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+        const uint32_t row = worklist[i];
+        const float2 h = rows.hdr[row];
+        sims[row] = ref_cosine_row(rows.codes + (size_t)row * rows.d_pad, h.x, h.y, qnorm, rows.d);
+    }
+}
+
+cudaError_t launch_cosine_fix(const MatView &rows, const double *qnorm, float *sims, const uint32_t *worklist,
+                              const unsigned int *work_count, int sm_count, cudaStream_t st) {
+    cosine_fix_kernel<<<sm_count * 4, 64, 0, st>>>(rows, qnorm, sims, worklist, work_count);
+    return cudaGetLastError();
+}
+
+// ---------------------------------------------------------------------------------------------------
+// Multi-GPU merge: G shard-local hit lists per query -> global top-k (same order and dedup rule).
+__global__ void topk_merge_kernel(const uint64_t *ids_in, const float *sims_in, const int32_t *counts_in, int G, int nq,
+                                  int k, uint64_t *ids_out, float *sims_out, int32_t *counts_out) {
+    const int qi = blockIdx.x;
+    const int lane = threadIdx.x;
+    WarpTopK<4> top;
+    top.init();
+    for (int g = 0; g < G; g++) {
+        const int cnt = counts_in[(size_t)g * nq + qi];
+        for (int base = 0; base < cnt; base += 32) {
+            int j = base + lane;
+            bool valid = j < cnt;
+            size_t off = ((size_t)g * nq + qi) * k + (valid ? j : 0);
+            uint32_t key = valid ? f32_to_key(sims_in[off]) : 0u;
+            uint64_t id = valid ? ids_in[off] : kEmptyId;
+            top.offer(valid, key, 0u, id, lane);
+        }
+    }
+    bool dup[4] = {false, false, false, false};
+    for (int s0 = 0; s0 < 4; s0++) {
+        for (int l0 = 0; l0 < 32; l0++) {
+            uint64_t bid = __shfl_sync(FULL, top.id[s0], l0);
+            uint32_t bk = __shfl_sync(FULL, top.skey[s0], l0);
+            if (bk == 0) break;
+#pragma unroll
+            for (int s = 0; s < 4; s++) {
+                int r = s * 32 + lane;
+                if (r > s0 * 32 + l0 && top.skey[s] != 0 && top.id[s] == bid) dup[s] = true;
+            }
+        }
+    }
+    int base = 0;
+#pragma unroll
+    for (int s = 0; s < 4; s++) {
+        bool keep = top.skey[s] != 0 && !dup[s];
+        unsigned m = __ballot_sync(FULL, keep);
+        int outpos = base + __popc(m & ((1u << lane) - 1u));
+        if (keep && outpos < k) {
+            ids_out[(size_t)qi * k + outpos] = top.id[s];
+            sims_out[(size_t)qi * k + outpos] = key_to_f32(top.skey[s]);
+        }
+        base += __popc(m);
+    }
+    if (lane == 0) counts_out[qi] = min(base, k);
+}
+
+cudaError_t launch_topk_merge(const uint64_t *ids_in, const float *sims_in, const int32_t *counts_in, int G, int nq,
+                              int k, uint64_t *ids_out, float *sims_out, int32_t *counts_out, cudaStream_t st) {
+    if (k > 128) return cudaErrorInvalidValue;
+    topk_merge_kernel<<<nq, 32, 0, st>>>(ids_in, sims_in, counts_in, G, nq, k, ids_out, sims_out, counts_out);
+    return cudaGetLastError();
+}
+
+}  // namespace vs

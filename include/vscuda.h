@@ -1,0 +1,163 @@
+/*
+ * vscuda.h -- C ABI of libvscuda.so, the B200 (sm_100a) backend for go-vectorsearch's
+ * similarity-search hot path.
+ *
+ * This is the drop-in boundary: the entry points below are what a `//go:build cuda`
+ * sibling of compute/compute_gonum.go + compute/cosine_gonum.go binds through cgo
+ * (see INTEGRATION.md and go-vectorsearch_b200/goshim/).  Plain pointers and sizes only.
+ * Every entry point cites the reference interface (file:line under the reference repo)
+ * it replaces.  All functions return VS_OK (0) or a negative VS_E* code; the message is
+ * available from vs_last_error() (thread-local).  The Go shim turns a non-zero status into
+ * panic()/logger.Fatalf exactly where the reference panics / Fatalf's.
+ *
+ * Row format ("row776"): the reference's own stored vector, compute/quantization.go:82-91 --
+ * float32 min LE, float32 max LE, then D uint8 codes; 8+D bytes (776 for D=768).
+ * "packed rows" = n such rows back to back (dnc/dataset.go:53-56 spool format).
+ *
+ * There is NO CPU fallback: every compute entry point needs a CUDA device and fails with
+ * VS_ENODEV otherwise.
+ */
+#ifndef VSCUDA_H
+#define VSCUDA_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define VS_API __attribute__((visibility("default")))
+
+#define VS_OK 0
+#define VS_EINVAL (-1)   /* bad argument */
+#define VS_EEMPTY (-2)   /* reference panics: "vector columns are empty" / "matrix rows are empty" (compute.go:13,26,30) */
+#define VS_EDIM (-3)     /* reference Fatalf: "column size does not match" (cosine.go:19-21,77-79) */
+#define VS_ECUDA (-4)    /* CUDA runtime error */
+#define VS_ENODEV (-5)   /* no CUDA device / library not initialised */
+#define VS_ENOMEM (-6)
+#define VS_ERANGE (-7)   /* k / nprobe / dimension beyond what the kernels support */
+
+typedef struct vs_ctx vs_ctx;       /* one CUDA stream + scratch arena; one per goroutine/closure */
+typedef struct vs_matrix vs_matrix; /* immutable device-resident quantized matrix, ref-counted */
+typedef struct vs_index vs_index;   /* device-resident IVF-Flat index */
+
+/* ---- lifecycle --------------------------------------------------------------------- */
+VS_API int vs_init(int device);            /* select device (LOCAL_RANK); idempotent */
+VS_API void vs_shutdown(void);
+VS_API const char *vs_last_error(void);
+VS_API int vs_device_info(char *name, size_t name_cap, int *sm_count, size_t *total_mem);
+
+/* compute/cosine.go:60-66,129-135: VectorMatrixCosineSimilarity()/MatrixCosineSimilarity()
+ * return (calculate, done).  calculate-closure creation == vs_ctx_create, done() == vs_ctx_destroy.
+ * Contexts are independent and may be used concurrently from different threads (dnc/dnc.go:30-33). */
+VS_API int vs_ctx_create(vs_ctx **out);
+VS_API void vs_ctx_destroy(vs_ctx *ctx);
+VS_API int vs_ctx_sync(vs_ctx *ctx);
+VS_API void *vs_ctx_stream(vs_ctx *ctx);                 /* cudaStream_t, for callers that time with events */
+VS_API uint64_t vs_ctx_launch_count(const vs_ctx *ctx);  /* kernels launched through this ctx so far */
+VS_API uint64_t vs_ctx_slowpath_count(const vs_ctx *ctx);/* rows / queries that took the literal-arithmetic path */
+/* CUDA-event timing on the ctx stream (bench.py): start/stop bracket, elapsed in ms after sync. */
+VS_API int vs_ctx_timer_start(vs_ctx *ctx);
+VS_API int vs_ctx_timer_stop(vs_ctx *ctx, float *ms_out);
+
+/* ---- compute/quantization.go ------------------------------------------------------- */
+/* QuantizeMatrixFloat32 (quantization.go:142-148) / QuantizeVectorFloat32 (:82-91; n=1).
+ * in: n*d floats (host); out: n*(8+d) bytes (host). */
+VS_API int vs_quantize_f32(vs_ctx *ctx, const float *in, size_t n, size_t d, uint8_t *out);
+/* QuantizeMatrixFloat64 (:150-156) / QuantizeVectorFloat64 (:93-102). */
+VS_API int vs_quantize_f64(vs_ctx *ctx, const double *in, size_t n, size_t d, uint8_t *out);
+/* DequantizeMatrixFloat32 (:166-172) / DequantizeVectorFloat32 (:114-122). */
+VS_API int vs_dequantize_f32(vs_ctx *ctx, const uint8_t *rows, size_t n, size_t row_bytes, float *out);
+/* DequantizeMatrixFloat64 (:174-180) / DequantizeVectorFloat64 (:124-132). */
+VS_API int vs_dequantize_f64(vs_ctx *ctx, const uint8_t *rows, size_t n, size_t row_bytes, double *out);
+/* Device-pointer forms of the above (no host copies, asynchronous on the ctx stream). */
+VS_API int vs_quantize_f32_dev(vs_ctx *ctx, const float *d_in, size_t n, size_t d, uint8_t *d_out);
+VS_API int vs_quantize_f64_dev(vs_ctx *ctx, const double *d_in, size_t n, size_t d, uint8_t *d_out);
+
+/* ---- compute/compute.go: NewMatrix / NewVector / Clone ----------------------------- */
+/* NewMatrix (compute.go:23-44): rows_packed = n rows of row_bytes (host).  Unlike the reference
+ * nothing is dequantized: the device keeps codes[n][D], the 8-byte headers and two integer sums
+ * per row.  VS_EEMPTY for n==0 or row_bytes<=8 (the reference's panics). */
+VS_API int vs_matrix_create(vs_ctx *ctx, const uint8_t *rows_packed, size_t n, size_t row_bytes, vs_matrix **out);
+VS_API int vs_matrix_create_dev(vs_ctx *ctx, const uint8_t *d_rows_packed, size_t n, size_t row_bytes, vs_matrix **out);
+/* Quantize n*d device floats straight into a device matrix (QuantizeMatrixFloat32 + NewMatrix fused). */
+VS_API int vs_matrix_from_f32_dev(vs_ctx *ctx, const float *d_in, size_t n, size_t d, vs_matrix **out);
+/* Clone (compute.go:65-77): device matrices are immutable, so Clone is a reference-count bump. */
+VS_API void vs_matrix_retain(vs_matrix *m);
+VS_API void vs_matrix_release(vs_matrix *m);
+VS_API size_t vs_matrix_rows(const vs_matrix *m);
+VS_API size_t vs_matrix_cols(const vs_matrix *m);
+/* Read rows back in row776 format (host out: count*(8+D) bytes). */
+VS_API int vs_matrix_read_rows(vs_ctx *ctx, const vs_matrix *m, size_t first, size_t count, uint8_t *out);
+
+/* ---- compute/cosine.go ------------------------------------------------------------- */
+/* (*vectorContainer).MatrixCosineSimilarity (cosine.go:13-57): sims_out[i] = float32 cosine of the
+ * query row776 against row i; n floats (host).  Bit-equal to the reference's default backend. */
+VS_API int vs_cosine_1xN(vs_ctx *ctx, const uint8_t *q, size_t q_bytes, const vs_matrix *m, float *sims_out);
+/* The integer dot product sum_j q[j]*v[j] (uint8 x uint8 -> uint32) the scores are built from. */
+VS_API int vs_dot_1xN(vs_ctx *ctx, const uint8_t *q, size_t q_bytes, const vs_matrix *m, uint32_t *dots_out);
+/* (*matrixContainer).MatrixCosineSimilarity (cosine.go:70-125): receiver = centroids, argument = data.
+ * idx_out[i] = argmax over centroids for data row i (strict '>' from -1.0: lowest index wins ties);
+ * sims_out (nullable; every reference call site discards it) = float32 of the winning cosine. */
+VS_API int vs_argmax_MxN(vs_ctx *ctx, const vs_matrix *centroids, const vs_matrix *data, float *sims_out, int64_t *idx_out);
+/* Same with the result left on the device (int32 indices), asynchronous. */
+VS_API int vs_argmax_MxN_dev(vs_ctx *ctx, const vs_matrix *centroids, const vs_matrix *data, int32_t *d_idx_out);
+
+/* ---- server/search.go:202-273: device-resident IVF-Flat probe-and-scan ------------- */
+/* Build from rows already grouped by list: list_offsets[C+1] (CSR, rows of list c are
+ * [list_offsets[c], list_offsets[c+1])), doc_ids[n] = Embedding.DocumentID (database/model.go:14),
+ * centroids = C rows (database/model.go:35-37).  Host pointers. doc_ids may be NULL (id = row index). */
+VS_API int vs_index_build(vs_ctx *ctx, const uint8_t *rows_packed, size_t n, size_t row_bytes, const uint64_t *doc_ids,
+                   const uint64_t *list_offsets, const uint8_t *centroids_packed, size_t C, vs_index **out);
+/* Build from ungrouped rows + the centroid index of each row (Embedding.CentroidID, model.go:16);
+ * groups on device with a stable sort so rows keep primary-key order inside each list. */
+VS_API int vs_index_build_assigned(vs_ctx *ctx, const uint8_t *rows_packed, size_t n, size_t row_bytes,
+                            const uint64_t *doc_ids, const uint32_t *list_of_row, const uint8_t *centroids_packed,
+                            size_t C, vs_index **out);
+/* Device-resident build: data and centroids are vs_matrix handles, d_list_of_row/d_doc_ids device arrays
+ * (d_doc_ids may be NULL -> id = id_base + row index). */
+VS_API int vs_index_build_dev(vs_ctx *ctx, const vs_matrix *data, const int32_t *d_list_of_row, const uint64_t *d_doc_ids,
+                       uint64_t id_base, const vs_matrix *centroids, vs_index **out);
+VS_API void vs_index_release(vs_index *ix);
+VS_API size_t vs_index_rows(const vs_index *ix);
+VS_API size_t vs_index_lists(const vs_index *ix);
+/* Search (search.go:115-273 minus embedding/DB hops): nq query rows (row776, host), nprobe =
+ * SearchRequest.Centroids (>= number of lists means "all"), k = Count+Offset.  Outputs (host):
+ * ids_out[nq*k] document IDs, sims_out[nq*k] float32 similarities, counts_out[nq] valid entries.
+ * Order: similarity desc (float32), then document ID asc; one entry per document (search.go:260-268). */
+VS_API int vs_search(vs_ctx *ctx, const vs_index *ix, const uint8_t *queries_packed, size_t nq, size_t nprobe, size_t k,
+              uint64_t *ids_out, float *sims_out, int32_t *counts_out);
+/* Brute force over a matrix (BASELINE config 1): same contract, ids = doc_ids[row] or row index. */
+VS_API int vs_search_flat(vs_ctx *ctx, const vs_matrix *m, const uint64_t *d_doc_ids, const uint8_t *queries_packed,
+                   size_t nq, size_t k, uint64_t *ids_out, float *sims_out, int32_t *counts_out);
+/* Device-resident search: queries already a device matrix; results stay in device buffers
+ * (d_ids[nq*k], d_sims[nq*k], d_counts[nq], d_status[nq]); asynchronous on the ctx stream.
+ * d_status bit0/bit1 = a float32 rounding could not be certified in the probe/list stage, bit2 =
+ * fewer than k unique documents among the kept candidates: call vs_search_resolve to finish those
+ * queries with literal reference arithmetic. */
+VS_API int vs_search_dev(vs_ctx *ctx, const vs_index *ix, const vs_matrix *queries, size_t nprobe, size_t k,
+                  uint64_t *d_ids, float *d_sims, int32_t *d_counts, uint32_t *d_status);
+VS_API int vs_search_resolve(vs_ctx *ctx, const vs_index *ix, const vs_matrix *queries, size_t nprobe, size_t k,
+                      uint64_t *d_ids, float *d_sims, int32_t *d_counts, uint32_t *d_status, int *n_resolved_out);
+/* Stage 1 only (search.go:202-227): probe_out[nq*min(nprobe,C)] list indices in rank order (host). */
+VS_API int vs_select_probes(vs_ctx *ctx, const vs_index *ix, const uint8_t *queries_packed, size_t nq, size_t nprobe,
+                     uint32_t *probe_out, float *probe_sims_out);
+/* Multi-GPU (row-striped shards): merge G gathered shard-local results per query into the global
+ * top-k.  d_ids_in/d_sims_in [G][nq][k], d_counts_in [G][nq] device arrays. */
+VS_API int vs_topk_merge_dev(vs_ctx *ctx, const uint64_t *d_ids_in, const float *d_sims_in, const int32_t *d_counts_in,
+                      size_t G, size_t nq, size_t k, uint64_t *d_ids_out, float *d_sims_out, int32_t *d_counts_out);
+
+/* ---- dnc/k_means.go:67-117 and dnc/dnc.go:417-449 ---------------------------------- */
+/* One Lloyd iteration.  data: device matrix; centroids_packed: k rows (host); means: [k][D] float32
+ * (host, in/out: the state k_means.go:60-65 carries; an empty cluster keeps its previous mean).
+ * Outputs (host): assign_out[n] (nullable), counts_out[k], new_centroids_out[k*(8+D)], *converged_out. */
+VS_API int vs_kmeans_step(vs_ctx *ctx, const vs_matrix *data, const uint8_t *centroids_packed, size_t k, float *means,
+                   int64_t *assign_out, int64_t *counts_out, uint8_t *new_centroids_out, int *converged_out);
+/* recenterDbCentroid (dnc.go:417-449): float64 mean of all rows of m in row order -> row776. */
+VS_API int vs_recenter(vs_ctx *ctx, const vs_matrix *m, uint8_t *out_row);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* VSCUDA_H */

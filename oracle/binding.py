@@ -1,0 +1,221 @@
+"""ctypes binding of oracle/_build/liboracle.so (built by oracle/Makefile)."""
+import ctypes as C
+import os
+import subprocess
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+_SO = os.path.join(_HERE, "_build", "liboracle.so")
+
+
+def build(force=False):
+    src = os.path.join(_HERE, "oracle.c")
+    if force or not os.path.exists(_SO) or os.path.getmtime(_SO) < os.path.getmtime(src):
+        subprocess.check_call(["make", "-s", "-C", _HERE])
+    return _SO
+
+
+_lib = None
+
+
+def lib():
+    global _lib
+    if _lib is None:
+        if not os.path.exists(_SO):
+            build()
+        _lib = C.CDLL(_SO)
+        _lib.ora_quantize_f32.restype = C.c_uint8
+        _lib.ora_quantize_f32.argtypes = [C.c_float] * 3
+        _lib.ora_quantize_f64.restype = C.c_uint8
+        _lib.ora_quantize_f64.argtypes = [C.c_double] * 3
+        _lib.ora_dequantize_f32.restype = C.c_float
+        _lib.ora_dequantize_f32.argtypes = [C.c_uint8, C.c_float, C.c_float]
+        _lib.ora_dequantize_f64.restype = C.c_double
+        _lib.ora_dequantize_f64.argtypes = [C.c_uint8, C.c_double, C.c_double]
+    return _lib
+
+
+def _p(a):
+    return a.ctypes.data_as(C.c_void_p)
+
+
+def _u8(a):
+    a = np.ascontiguousarray(a, dtype=np.uint8)
+    return a
+
+
+def quantize_vector_f32(v):
+    v = np.ascontiguousarray(v, dtype=np.float32)
+    out = np.empty(8 + v.shape[0], np.uint8)
+    lib().ora_quantize_vector_f32(_p(v), C.c_size_t(v.shape[0]), _p(out))
+    return out
+
+
+def quantize_vector_f64(v):
+    v = np.ascontiguousarray(v, dtype=np.float64)
+    out = np.empty(8 + v.shape[0], np.uint8)
+    lib().ora_quantize_vector_f64(_p(v), C.c_size_t(v.shape[0]), _p(out))
+    return out
+
+
+def quantize_matrix_f32(m):
+    m = np.ascontiguousarray(m, dtype=np.float32)
+    n, d = m.shape
+    out = np.empty((n, 8 + d), np.uint8)
+    lib().ora_quantize_matrix_f32(_p(m), C.c_size_t(n), C.c_size_t(d), _p(out))
+    return out
+
+
+def quantize_matrix_f64(m):
+    m = np.ascontiguousarray(m, dtype=np.float64)
+    n, d = m.shape
+    out = np.empty((n, 8 + d), np.uint8)
+    lib().ora_quantize_matrix_f64(_p(m), C.c_size_t(n), C.c_size_t(d), _p(out))
+    return out
+
+
+def dequantize_matrix_f32(rows):
+    rows = _u8(rows)
+    n, rb = rows.shape
+    out = np.empty((n, rb - 8), np.float32)
+    lib().ora_dequantize_matrix_f32(_p(rows), C.c_size_t(n), C.c_size_t(rb), _p(out))
+    return out
+
+
+def dequantize_matrix_f64(rows):
+    rows = _u8(rows)
+    n, rb = rows.shape
+    out = np.empty((n, rb - 8), np.float64)
+    lib().ora_dequantize_matrix_f64(_p(rows), C.c_size_t(n), C.c_size_t(rb), _p(out))
+    return out
+
+
+def dot_u8_1xN(q, rows):
+    q = _u8(q)
+    rows = _u8(rows)
+    n, rb = rows.shape
+    out = np.empty(n, np.uint32)
+    lib().ora_dot_u8_1xN(_p(q), _p(rows), C.c_size_t(n), C.c_size_t(rb), _p(out))
+    return out
+
+
+class OraclePanic(Exception):
+    """The reference panics / Fatalf's here (compute.go:13,26,30; cosine.go:19-21,77-79)."""
+
+
+def _check(rc):
+    if rc == -1:
+        raise OraclePanic("empty vector/matrix")
+    if rc == -2:
+        raise OraclePanic("column size does not match")
+
+
+def cosine_1xN(q, rows):
+    q = _u8(q)
+    rows = _u8(rows)
+    n, rb = rows.shape if rows.ndim == 2 else (0, 0)
+    out = np.empty(n, np.float32)
+    rc = lib().ora_cosine_1xN(_p(q), C.c_size_t(q.shape[0]), _p(rows), C.c_size_t(n), C.c_size_t(rb), _p(out))
+    _check(rc)
+    return out
+
+
+def argmax_MxN(cent, rows):
+    cent = _u8(cent)
+    rows = _u8(rows)
+    m, cb = cent.shape if cent.ndim == 2 else (0, 0)
+    n, rb = rows.shape if rows.ndim == 2 else (0, 0)
+    sims = np.empty(n, np.float32)
+    idx = np.empty(n, np.int64)
+    rc = lib().ora_argmax_MxN(_p(cent), C.c_size_t(m), C.c_size_t(cb), _p(rows), C.c_size_t(n), C.c_size_t(rb),
+                              _p(sims), _p(idx))
+    _check(rc)
+    return sims, idx
+
+
+def select_probes(q, centroids, nprobe):
+    q = _u8(q)
+    centroids = _u8(centroids)
+    Cn, rb = centroids.shape
+    keep = min(nprobe, Cn)
+    probes = np.empty(max(keep, 1), np.uint32)
+    sims = np.empty(max(keep, 1), np.float32)
+    rc = lib().ora_select_probes(_p(q), _p(centroids), C.c_size_t(Cn), C.c_size_t(rb), C.c_size_t(nprobe),
+                                 _p(probes), _p(sims))
+    _check(rc)
+    return probes[:rc], sims[:rc]
+
+
+def search(q, centroids, rows, list_of_row, doc_ids, nprobe, k):
+    q = _u8(q)
+    centroids = _u8(centroids)
+    rows = _u8(rows)
+    list_of_row = np.ascontiguousarray(list_of_row, dtype=np.uint32)
+    doc_ids = np.ascontiguousarray(doc_ids, dtype=np.uint64)
+    Cn, rb = centroids.shape
+    n = rows.shape[0]
+    ids = np.empty(k, np.uint64)
+    sims = np.empty(k, np.float32)
+    rc = lib().ora_search(_p(q), _p(centroids), C.c_size_t(Cn), _p(rows), C.c_size_t(n), C.c_size_t(rb),
+                          _p(list_of_row), _p(doc_ids), C.c_size_t(nprobe), C.c_size_t(k), _p(ids), _p(sims))
+    _check(rc)
+    return ids[:rc], sims[:rc]
+
+
+def search_many(qs, centroids, rows, list_of_row, doc_ids, nprobe, k, threads=1):
+    qs = _u8(qs)
+    centroids = _u8(centroids)
+    rows = _u8(rows)
+    list_of_row = np.ascontiguousarray(list_of_row, dtype=np.uint32)
+    doc_ids = np.ascontiguousarray(doc_ids, dtype=np.uint64)
+    nq = qs.shape[0]
+    Cn, rb = centroids.shape
+    n = rows.shape[0]
+    ids = np.zeros((nq, k), np.uint64)
+    sims = np.zeros((nq, k), np.float32)
+    counts = np.zeros(nq, np.int32)
+    rc = lib().ora_search_many(_p(qs), C.c_size_t(nq), _p(centroids), C.c_size_t(Cn), _p(rows), C.c_size_t(n),
+                               C.c_size_t(rb), _p(list_of_row), _p(doc_ids), C.c_size_t(nprobe), C.c_size_t(k),
+                               _p(ids), _p(sims), _p(counts), C.c_int(threads))
+    _check(rc)
+    return ids, sims, counts
+
+
+def search_flat(q, rows, doc_ids, k):
+    q = _u8(q)
+    rows = _u8(rows)
+    n, rb = rows.shape
+    ids = np.empty(k, np.uint64)
+    sims = np.empty(k, np.float32)
+    dp = None
+    if doc_ids is not None:
+        doc_ids = np.ascontiguousarray(doc_ids, dtype=np.uint64)
+        dp = _p(doc_ids)
+    rc = lib().ora_search_flat(_p(q), _p(rows), C.c_size_t(n), C.c_size_t(rb), dp, C.c_size_t(k), _p(ids), _p(sims))
+    _check(rc)
+    return ids[:rc], sims[:rc]
+
+
+def kmeans_step(data, centroids, means):
+    """One Lloyd iteration (dnc/k_means.go:67-117). `means` ([k][d] float32) is updated in place."""
+    data = _u8(data)
+    centroids = _u8(centroids)
+    assert means.dtype == np.float32 and means.flags.c_contiguous
+    n, rb = data.shape
+    k = centroids.shape[0]
+    assign = np.empty(n, np.int64)
+    counts = np.empty(k, np.int64)
+    newc = np.empty((k, rb), np.uint8)
+    rc = lib().ora_kmeans_step(_p(data), C.c_size_t(n), _p(centroids), C.c_size_t(k), C.c_size_t(rb), _p(means),
+                               _p(assign), _p(counts), _p(newc))
+    _check(rc)
+    return assign, counts, newc, bool(rc)
+
+
+def recenter(rows):
+    rows = _u8(rows)
+    n, rb = rows.shape
+    out = np.empty(rb, np.uint8)
+    lib().ora_recenter(_p(rows), C.c_size_t(n), C.c_size_t(rb), _p(out))
+    return out

@@ -1,0 +1,143 @@
+"""Writes tests/golden/kat.json: known-answer vectors for the hot path.
+
+The reference ships no golden vectors (PARITY UNPINNED), so these are derived here
+WITHOUT the oracle: quantization cases by hand from compute/quantization.go (the arithmetic is written
+out in each `why`), dequantization / cosine cases by plain Python float arithmetic (IEEE-754 binary64,
+round-to-nearest, no fusion) following compute/cosine.go line by line.  Both oracles (oracle.c and
+oracle_np.py) and the CUDA path must reproduce them bit-for-bit.
+
+Run: python tests/golden/make_golden.py   (rewrites kat.json deterministically)
+"""
+import json
+import math
+import os
+import struct
+
+
+def f32_le(x):
+    return list(struct.pack("<f", x))
+
+
+def row(mn, mx, codes):
+    return f32_le(mn) + f32_le(mx) + list(codes)
+
+
+def f64_hex(x):
+    return struct.pack(">d", x).hex()
+
+
+def f32_hex(x):
+    return struct.pack(">f", x).hex()
+
+
+quantize_f32 = [
+    dict(name="positive_keeps_min_zero", input=[0.5, 1.0, 0.25], expect=row(0.0, 1.0, [127, 255, 63]),
+         why="range seeded at 0 -> min=0,max=1; 0.5*255=127.5 -> 127 (truncation), 1.0 -> 255, 0.25*255=63.75 -> 63"),
+    dict(name="symmetric", input=[-1.0, 0.0, 1.0], expect=row(-1.0, 1.0, [0, 127, 255]),
+         why="(v+1)/2*255: 0, 127.5 -> 127, 255"),
+    dict(name="all_positive", input=[2.0, 4.0], expect=row(0.0, 4.0, [127, 255]),
+         why="min stays 0 (seed), 2/4*255=127.5 -> 127"),
+    dict(name="all_negative", input=[-2.0, -4.0], expect=row(-4.0, 0.0, [127, 0]),
+         why="max stays 0 (seed), (-2+4)/4*255=127.5 -> 127, -4 -> 0"),
+    dict(name="all_zero", input=[0.0, 0.0, 0.0], expect=row(0.0, 0.0, [0, 0, 0]),
+         why="0/0 = NaN; uint8(NaN*255) is 0 on amd64 (CVTTSS2SL low byte)"),
+    dict(name="nan_ignored_by_range", input=[float("nan"), 1.0], expect=row(0.0, 1.0, [0, 255]),
+         why="NaN fails both comparisons in rangeFloat32 and both clamps; NaN code -> 0"),
+    dict(name="truncation_not_rounding", input=[0.0, 1.0, 0.999], expect=row(0.0, 1.0, [0, 255, 254]),
+         why="0.999*255 = 254.745 -> 254"),
+    dict(name="single_positive", input=[5.0], expect=row(0.0, 5.0, [255]), why="5/5*255"),
+    dict(name="single_negative", input=[-5.0], expect=row(-5.0, 0.0, [0]), why="(-5+5)/5*255 = 0"),
+    dict(name="empty", input=[], expect=row(0.0, 0.0, []), why="8-byte header of zeros, no codes"),
+    dict(name="value_equals_max_is_255", input=[-0.25, 0.75, 0.75], expect=row(-0.25, 0.75, [0, 255, 255]),
+         why="(0.75+0.25)/1.0*255 = 255 exactly"),
+]
+
+quantize_f64 = [
+    dict(name="header_is_float32_rounded_codes_use_float64_range", input=[0.1, -0.3],
+         expect=row(0.1, -0.3, [])[4:8] + row(0.1, -0.3, [])[0:4] + [255, 0],
+         why="header = float32(-0.3), float32(0.1); (0.1-(-0.3))/(0.1-(-0.3)) = 1.0 in float64 -> 255; min -> 0"),
+    dict(name="f64_truncation", input=[0.0, 1.0, 0.999], expect=row(0.0, 1.0, [0, 255, 254]), why="as float32 case"),
+    dict(name="f64_all_zero", input=[0.0, 0.0], expect=row(0.0, 0.0, [0, 0]), why="NaN -> 0 (CVTTSD2SQ low byte)"),
+]
+# the first f64 case above builds the header by hand: float32(-0.3) then float32(0.1)
+quantize_f64[0]["expect"] = f32_le(-0.3) + f32_le(0.1) + [255, 0]
+
+
+def deq64(q, mn, mx):
+    normalized = float(q) / 255.0
+    return mn + normalized * (mx - mn)
+
+
+def deq32(q, mn, mx):
+    f = lambda x: struct.unpack("<f", struct.pack("<f", x))[0]  # round to float32
+    normalized = f(float(q) / 255.0)   # float32 division of exactly representable operands
+    rng = f(mx - mn)
+    return f(mn + f(normalized * rng))
+
+
+dequantize = []
+for (mn, mx, codes) in [(-1.0, 1.0, [0, 255, 51, 127, 128]), (0.0, 1.0, [0, 1, 254, 255]), (-0.125, 0.375, [17, 200])]:
+    dequantize.append(dict(row=row(mn, mx, codes),
+                           f64=[f64_hex(deq64(q, mn, mx)) for q in codes],
+                           f32=[f32_hex(deq32(q, mn, mx)) for q in codes]))
+
+
+def normalize(v):
+    norm = 0.0
+    for x in v:
+        norm += x * x
+    norm = math.sqrt(norm)
+    if norm != 0:
+        v = [x / norm for x in v]
+    return v
+
+
+def cosine(qrow, r):
+    d = len(qrow) - 8
+    qmn, qmx = struct.unpack("<ff", bytes(qrow[:8]))
+    rmn, rmx = struct.unpack("<ff", bytes(r[:8]))
+    A = normalize([deq64(qrow[8 + i], qmn, qmx) for i in range(d)])
+    B = normalize([deq64(r[8 + i], rmn, rmx) for i in range(d)])
+    dot = 0.0
+    for a, b in zip(A, B):
+        dot += a * b
+    return struct.unpack("<f", struct.pack("<f", dot))[0]
+
+
+q = row(0.0, 1.0, [255, 0])
+cos_rows = [row(0.0, 1.0, [0, 255]), row(0.0, 1.0, [255, 255]), row(0.0, 1.0, [255, 0]), row(0.0, 0.0, [7, 9]),
+            row(-1.0, 1.0, [0, 255]), row(-1.0, 0.0, [0, 255])]
+cosine_cases = dict(
+    query=q, rows=cos_rows,
+    dots=[0, 255 * 255, 255 * 255, 255 * 7, 0, 0],
+    sims_f32=[f32_hex(cosine(q, r)) for r in cos_rows],
+    why=["orthogonal -> 0", "(1,1)/sqrt2 . (1,0) = 0.70710677", "identical -> 1",
+         "header 0/0: every value dequantizes to 0, norm 0, left unnormalized, dot = +0",
+         "(-1,1)/sqrt2 . (1,0) = -0.70710677", "(-1,0) . (1,0) = -1"])
+
+argmax_cases = dict(
+    centroids=[row(0.0, 1.0, [255, 0]), row(0.0, 1.0, [0, 255]), row(0.0, 1.0, [255, 0])],
+    data=[row(0.0, 1.0, [255, 0]), row(0.0, 1.0, [0, 255]), row(0.0, 0.0, [0, 0]), row(0.0, 1.0, [255, 255]),
+          row(-1.0, 0.0, [0, 255])],
+    argmax=[0, 1, 0, 0, 1],
+    why=["tie between identical centroids 0 and 2: strict '>' keeps the lowest index", "centroid 1",
+         "zero row: every dot is +0 > -1.0 -> index 0", "tie 0.7071 between 0 and 1 -> lowest index",
+         "(-1,0): dots are -1,0,-1 -> centroid 1"])
+
+out = dict(quantize_f32=quantize_f32, quantize_f64=quantize_f64, dequantize=dequantize, cosine=cosine_cases,
+           argmax=argmax_cases)
+
+
+def clean(o):
+    if isinstance(o, float) and o != o:
+        return "nan"
+    if isinstance(o, dict):
+        return {k: clean(v) for k, v in o.items()}
+    if isinstance(o, list):
+        return [clean(v) for v in o]
+    return o
+
+
+with open(os.path.join(os.path.dirname(os.path.abspath(__file__)), "kat.json"), "w") as f:
+    json.dump(clean(out), f, indent=1)
+print("wrote kat.json")

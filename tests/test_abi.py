@@ -1,0 +1,60 @@
+"""CPU: the C-ABI library loads and exports every symbol include/vscuda.h declares; the host mirror's
+argument checks behave like the reference's panics; and the product path fails loudly without a GPU."""
+import ctypes
+import os
+import re
+
+import numpy as np
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def _declared():
+    text = open(os.path.join(ROOT, "include", "vscuda.h")).read()
+    text = re.sub(r"/\*.*?\*/", "", text, flags=re.S)
+    return sorted(set(re.findall(r"\b(vs_[a-z0-9_A-Z]+)\s*\(", text)))
+
+
+def test_header_symbols_exported(pkg):
+    names = _declared()
+    assert len(names) >= 40
+    L = ctypes.CDLL(pkg.lib_path())
+    missing = [n for n in names if not hasattr(L, n)]
+    assert not missing, missing
+    assert sorted(pkg._lib.SYMBOLS) == names
+
+
+def test_no_torch_types_in_header():
+    text = open(os.path.join(ROOT, "include", "vscuda.h")).read()
+    assert "torch" not in text.lower() and "at::" not in text and "Tensor" not in text
+
+
+def test_product_never_imports_oracle():
+    pkgdir = os.path.join(ROOT, "go-vectorsearch_b200")
+    for dirpath, _, files in os.walk(pkgdir):
+        for f in files:
+            if f.endswith((".py", ".cu", ".cuh", ".h", ".hpp", ".cc", ".cpp", ".go")):
+                src = open(os.path.join(dirpath, f), errors="replace").read()
+                assert "oracle" not in src.lower(), f"{f} mentions the oracle"
+
+
+def test_host_mirror_panics_like_reference(pkg):
+    c = pkg.compute
+    with pytest.raises(c.ComputePanic, match="vector columns are empty"):
+        c.NewVector(np.zeros(8, np.uint8))          # compute.go:12-14
+    with pytest.raises(c.ComputePanic, match="matrix rows are empty"):
+        c.NewMatrix([])                             # compute.go:25-27
+    with pytest.raises(c.ComputePanic):
+        c.NewMatrix([np.zeros(12, np.uint8), np.zeros(13, np.uint8)])
+
+
+def test_fails_loudly_without_gpu(pkg):
+    """No CPU fallback: on a box without a CUDA device every compute entry point raises."""
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("a GPU is present")
+    with pytest.raises(pkg.BackendUnavailable):
+        pkg.compute.NewMatrix(np.zeros((2, 16), np.uint8))
+    with pytest.raises(pkg.BackendUnavailable):
+        pkg.compute.QuantizeVectorFloat32(np.ones(4, np.float32))

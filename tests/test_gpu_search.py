@@ -1,0 +1,158 @@
+"""GPU parity: IVF-Flat probe-and-scan (server/search.go:202-273) and flat scan, top-k ids bit-exact."""
+import numpy as np
+import pytest
+
+from _util import f32_bits, noop_rows, unit_rows
+
+pytestmark = pytest.mark.gpu
+
+
+def _index_inputs(oracle, n, d, C, seed, docs_per=1):
+    rows = oracle.quantize_matrix_f32(unit_rows(n, d, seed))
+    cent = oracle.quantize_matrix_f32(unit_rows(C, d, seed + 1))
+    _, lists = oracle.argmax_MxN(cent, rows)
+    if docs_per == 1:
+        doc = np.arange(n, dtype=np.uint64) + 1000
+    else:
+        doc = np.random.default_rng(seed + 2).integers(0, max(1, n // docs_per), n).astype(np.uint64)
+    return rows, cent, lists.astype(np.uint32), doc
+
+
+def _check(oracle, ix, qs, cent, rows, lists, doc, nprobe, k):
+    ids, sims, counts = ix.Search(qs, nprobe, k)
+    for i, q in enumerate(qs):
+        want_ids, want_sims = oracle.search(q, cent, rows, lists, doc, nprobe, k)
+        c = counts[i]
+        assert c == len(want_ids), (i, c, len(want_ids))
+        assert ids[i, :c].tolist() == want_ids.tolist(), f"query {i}"
+        assert (f32_bits(sims[i, :c]) == f32_bits(want_sims)).all(), f"query {i}"
+
+
+@pytest.mark.parametrize("nprobe,k", [(8, 10), (1, 10), (32, 20), (3, 40), (64, 100), (200, 10)])
+def test_ivf_search_parity(vs, oracle, nprobe, k):
+    n, d, C = 30000, 768, 96
+    rows, cent, lists, doc = _index_inputs(oracle, n, d, C, 5)
+    ix = vs.ivf.Index.build_assigned(rows, doc, lists, cent)
+    assert ix.rows == n and ix.lists == C
+    qs = oracle.quantize_matrix_f32(unit_rows(6, d, 99))
+    _check(oracle, ix, qs, cent, rows, lists, doc, nprobe, k)
+
+
+def test_ivf_probe_selection_parity(vs, oracle):
+    n, d, C = 5000, 768, 300
+    rows, cent, lists, doc = _index_inputs(oracle, n, d, C, 8)
+    ix = vs.ivf.Index.build_assigned(rows, doc, lists, cent)
+    qs = oracle.quantize_matrix_f32(unit_rows(9, d, 3))
+    for nprobe in (1, 32, 64, 100):
+        probes, sims = ix.SelectProbes(qs, nprobe)
+        for i, q in enumerate(qs):
+            wp, ws = oracle.select_probes(q, cent, nprobe)
+            assert probes[i].tolist() == wp.tolist()
+            assert (f32_bits(sims[i]) == f32_bits(ws)).all()
+
+
+def test_ivf_dedup_by_document(vs, oracle):
+    """search.go:260-268: one hit per document, keeping its best embedding."""
+    n, d, C = 8000, 256, 16
+    rows, cent, lists, doc = _index_inputs(oracle, n, d, C, 21, docs_per=3)
+    ix = vs.ivf.Index.build_assigned(rows, doc, lists, cent)
+    qs = oracle.quantize_matrix_f32(unit_rows(5, d, 4))
+    _check(oracle, ix, qs, cent, rows, lists, doc, nprobe=6, k=15)
+
+
+def test_ivf_ties_broken_by_id(vs, oracle):
+    n, d, C = 4000, 768, 8
+    rows, cent, lists, doc = _index_inputs(oracle, n, d, C, 33)
+    rows[100:140] = rows[100]      # 40 identical rows with distinct ids
+    _, lists = oracle.argmax_MxN(cent, rows)
+    lists = lists.astype(np.uint32)
+    doc = np.random.default_rng(0).permutation(n).astype(np.uint64)   # ids not in row order
+    ix = vs.ivf.Index.build_assigned(rows, doc, lists, cent)
+    qs = np.stack([rows[100], oracle.quantize_vector_f32(unit_rows(1, d, 1)[0])])
+    _check(oracle, ix, qs, cent, rows, lists, doc, nprobe=8, k=25)
+
+
+def test_ivf_ragged_and_empty_lists(vs, oracle):
+    d, C = 768, 10
+    rows = oracle.quantize_matrix_f32(unit_rows(1000, d, 2))
+    cent = oracle.quantize_matrix_f32(unit_rows(C, d, 3))
+    sizes = [0, 1, 31, 32, 33, 0, 500, 7, 396, 0]
+    lists = np.repeat(np.arange(C), sizes).astype(np.uint32)
+    doc = np.arange(1000, dtype=np.uint64)
+    offs = np.concatenate([[0], np.cumsum(sizes)]).astype(np.uint64)
+    ix = vs.ivf.Index.build(rows, doc, offs, cent)     # rows already grouped
+    qs = oracle.quantize_matrix_f32(unit_rows(4, d, 5))
+    for nprobe, k in ((3, 10), (10, 10), (1, 5)):
+        _check(oracle, ix, qs, cent, rows, lists, doc, nprobe, k)
+    ix2 = vs.ivf.Index.build_assigned(rows[::-1].copy(), doc[::-1].copy(), lists[::-1].copy(), cent)
+    _check(oracle, ix2, qs, cent, rows[::-1], lists[::-1], doc[::-1], 4, 10)
+
+
+def test_fewer_rows_than_k(vs, oracle):
+    d = 768
+    rows = oracle.quantize_matrix_f32(unit_rows(7, d, 2))
+    m = vs.compute.NewMatrix(rows)
+    q = oracle.quantize_vector_f32(unit_rows(1, d, 9)[0])
+    ids, sims, counts = vs.ivf.SearchFlat(m, q, 10)
+    want_ids, want_sims = oracle.search_flat(q, rows, None, 10)
+    assert counts[0] == 7 and ids[0, :7].tolist() == want_ids.tolist()
+    assert (f32_bits(sims[0, :7]) == f32_bits(want_sims)).all()
+
+
+@pytest.mark.parametrize("d,n", [(768, 100000), (512, 20000), (100, 5000)])
+def test_flat_search_parity(vs, oracle, d, n):
+    """BASELINE config 1: brute force over 100k x 768, 1 query, top-10."""
+    rows = oracle.quantize_matrix_f32(unit_rows(n, d, 1234))
+    m = vs.compute.NewMatrix(rows)
+    qs = oracle.quantize_matrix_f32(unit_rows(3, d, 4321))
+    ids, sims, counts = vs.ivf.SearchFlat(m, qs, 10)
+    for i, q in enumerate(qs):
+        want_ids, want_sims = oracle.search_flat(q, rows, None, 10)
+        assert ids[i].tolist() == want_ids.tolist()
+        assert (f32_bits(sims[i]) == f32_bits(want_sims)).all()
+
+
+def test_search_adversarial_rows_take_literal_path(vs, oracle):
+    """Rows whose float32 rounding cannot be certified must be resolved with reference arithmetic."""
+    d, n, C = 768, 3000, 6
+    rng = np.random.default_rng(5)
+    rows = noop_rows(n, d, 5)
+    rows[:, 8:] = rng.integers(126, 130, (n, d), dtype=np.uint8)
+    cent = rows[:C].copy()
+    _, lists = oracle.argmax_MxN(cent, rows)
+    lists = lists.astype(np.uint32)
+    doc = np.arange(n, dtype=np.uint64)
+    ctx = vs.compute.Context()
+    ix = vs.ivf.Index.build_assigned(rows, doc, lists, cent, ctx=ctx)
+    qs = rows[10:13]
+    ids, sims, counts = ix.Search(qs, 3, 10, ctx=ctx)
+    assert ctx.slowpath_count() > 0
+    for i, q in enumerate(qs):
+        want_ids, want_sims = oracle.search(q, cent, rows, lists, doc, 3, 10)
+        assert ids[i, :counts[i]].tolist() == want_ids.tolist()
+        assert (f32_bits(sims[i, :counts[i]]) == f32_bits(want_sims)).all()
+    ctx.close()
+
+
+def test_full_size_properties(vs):
+    """Size-independent properties at a larger size than the oracle handles quickly: the flat top-k
+    must be sorted, unique, idempotent, and equal to the IVF search that probes every list."""
+    d, n, C = 768, 400000, 64
+    rows = noop_rows(n, d, 17)
+    m = vs.compute.NewMatrix(rows)
+    q = noop_rows(4, d, 18)
+    ids, sims, counts = vs.ivf.SearchFlat(m, q, 10)
+    ids2, sims2, _ = vs.ivf.SearchFlat(m, q, 10)
+    assert (ids == ids2).all() and (f32_bits(sims) == f32_bits(sims2)).all()
+    assert (counts == 10).all()
+    for i in range(4):
+        assert all(sims[i, j] > sims[i, j + 1] or (sims[i, j] == sims[i, j + 1] and ids[i, j] < ids[i, j + 1])
+                   for j in range(9))
+        full = vs.compute.NewVector(q[i]).MatrixCosineSimilarity(m)
+        order = np.lexsort((np.arange(n), -full.astype(np.float64)))[:10]
+        assert ids[i].tolist() == order.tolist()
+        assert (f32_bits(sims[i]) == f32_bits(full[order])).all()
+    lists = (np.arange(n) % C).astype(np.uint32)
+    ix = vs.ivf.Index.build_assigned(rows, None, lists, rows[:C])
+    ids3, sims3, _ = ix.Search(q, C, 10)
+    assert (ids3 == ids).all() and (f32_bits(sims3) == f32_bits(sims)).all()

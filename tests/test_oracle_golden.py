@@ -1,0 +1,137 @@
+"""CPU: both oracles against the hand-derived golden vectors, and against each other.
+
+The reference has no tests, so these known-answer vectors (tests/golden/kat.json, built by
+tests/golden/make_golden.py without the oracle) are what pins oracle.c; oracle_np.py is a second
+restatement that must agree bit-for-bit on random inputs.
+"""
+import json
+import os
+import struct
+
+import numpy as np
+import pytest
+
+from _util import f32_bits, noop_rows, unit_rows
+
+KAT = json.load(open(os.path.join(os.path.dirname(__file__), "golden", "kat.json")))
+
+
+def _inp(v):
+    return [float("nan") if x == "nan" else x for x in v]
+
+
+@pytest.mark.parametrize("case", KAT["quantize_f32"], ids=lambda c: c["name"])
+def test_quantize_f32_kat(oracle, case):
+    from oracle import oracle_np as onp
+    v = np.array(_inp(case["input"]), np.float32)
+    want = np.array(case["expect"], np.uint8)
+    assert (oracle.quantize_vector_f32(v) == want).all(), case["why"]
+    assert (onp.quantize_vector(v, np.float32) == want).all(), case["why"]
+
+
+@pytest.mark.parametrize("case", KAT["quantize_f64"], ids=lambda c: c["name"])
+def test_quantize_f64_kat(oracle, case):
+    from oracle import oracle_np as onp
+    v = np.array(_inp(case["input"]), np.float64)
+    want = np.array(case["expect"], np.uint8)
+    assert (oracle.quantize_vector_f64(v) == want).all(), case["why"]
+    assert (onp.quantize_vector(v, np.float64) == want).all(), case["why"]
+
+
+def test_dequantize_kat(oracle):
+    for case in KAT["dequantize"]:
+        row = np.array(case["row"], np.uint8)[None, :]
+        f64 = oracle.dequantize_matrix_f64(row)[0]
+        f32 = oracle.dequantize_matrix_f32(row)[0]
+        assert [struct.pack(">d", x).hex() for x in f64] == case["f64"]
+        assert [struct.pack(">f", x).hex() for x in f32] == case["f32"]
+
+
+def test_cosine_kat(oracle):
+    from oracle import oracle_np as onp
+    c = KAT["cosine"]
+    q = np.array(c["query"], np.uint8)
+    rows = np.array(c["rows"], np.uint8)
+    sims = oracle.cosine_1xN(q, rows)
+    assert [struct.pack(">f", x).hex() for x in sims] == c["sims_f32"], c["why"]
+    assert [struct.pack(">f", x).hex() for x in onp.cosine_1xN(q, rows)] == c["sims_f32"]
+    assert oracle.dot_u8_1xN(q, rows).tolist() == c["dots"]
+
+
+def test_argmax_kat(oracle):
+    from oracle import oracle_np as onp
+    c = KAT["argmax"]
+    cent = np.array(c["centroids"], np.uint8)
+    data = np.array(c["data"], np.uint8)
+    assert oracle.argmax_MxN(cent, data)[1].tolist() == c["argmax"], c["why"]
+    assert onp.argmax_MxN(cent, data)[1].tolist() == c["argmax"]
+
+
+def test_reference_panics(oracle):
+    q = np.zeros(8, np.uint8)
+    rows = np.zeros((2, 10), np.uint8)
+    with pytest.raises(oracle.OraclePanic):
+        oracle.cosine_1xN(q, rows)                      # compute.go:12-14 empty vector
+    with pytest.raises(oracle.OraclePanic):
+        oracle.cosine_1xN(np.zeros(10, np.uint8), np.zeros((0, 10), np.uint8))  # compute.go:25-27
+    with pytest.raises(oracle.OraclePanic):
+        oracle.cosine_1xN(np.zeros(12, np.uint8), rows)  # cosine.go:19-21 dimension mismatch
+
+
+@pytest.mark.parametrize("d", [1, 3, 64, 768])
+def test_two_restatements_agree(oracle, d):
+    from oracle import oracle_np as onp
+    rng = np.random.default_rng(d)
+    x = rng.standard_normal((24, d)).astype(np.float32)
+    x[3] = np.abs(x[3])
+    x[4] = 0
+    if d > 2:
+        x[5, 1] = np.nan
+    rows = oracle.quantize_matrix_f32(x)
+    assert (rows == np.stack([onp.quantize_vector(r, np.float32) for r in x])).all()
+    x64 = rng.standard_normal((8, d))
+    assert (oracle.quantize_matrix_f64(x64) == np.stack([onp.quantize_vector(r, np.float64) for r in x64])).all()
+    assert (f32_bits(oracle.dequantize_matrix_f32(rows)) ==
+            f32_bits(np.stack([onp.dequantize_vector(r, np.float32) for r in rows]))).all()
+    assert (oracle.dequantize_matrix_f64(rows).view(np.uint64) ==
+            np.stack([onp.dequantize_vector(r, np.float64) for r in rows]).view(np.uint64)).all()
+    assert (f32_bits(oracle.cosine_1xN(rows[0], rows)) == f32_bits(onp.cosine_1xN(rows[0], rows))).all()
+    s1, i1 = oracle.argmax_MxN(rows[:5], rows)
+    s2, i2 = onp.argmax_MxN(rows[:5], rows)
+    assert (i1 == i2).all() and (f32_bits(s1) == f32_bits(s2)).all()
+    means = np.zeros((5, d), np.float32)
+    a, c, nc, _ = oracle.kmeans_step(rows, rows[:5], means)
+    c2, m2, nc2 = onp.kmeans_update(rows, a, 5, np.zeros((5, d), np.float32))
+    assert (c == c2).all() and (nc == nc2).all() and (f32_bits(means) == f32_bits(m2)).all()
+    assert (oracle.recenter(rows) == onp.recenter(rows)).all()
+
+
+def test_search_oracle_properties(oracle):
+    """ora_search (batched running sort+dedup+truncate, search.go:239-273) == global sort of the probed rows."""
+    d, n, C = 32, 3000, 12
+    rows = oracle.quantize_matrix_f32(unit_rows(n, d, 1))
+    cent = oracle.quantize_matrix_f32(unit_rows(C, d, 2))
+    _, lists = oracle.argmax_MxN(cent, rows)
+    rng = np.random.default_rng(3)
+    doc = rng.integers(0, n // 2, n).astype(np.uint64)   # several embeddings per document
+    q = oracle.quantize_vector_f32(unit_rows(1, d, 4)[0])
+    ids, sims = oracle.search(q, cent, rows, lists, doc, nprobe=4, k=15)
+    probes, _ = oracle.select_probes(q, cent, 4)
+    mask = np.isin(lists, probes)
+    s = oracle.cosine_1xN(q, rows[mask])
+    order = sorted(zip(-s.astype(np.float64), doc[mask].tolist()))
+    seen, want = set(), []
+    for negs, dd in order:
+        if dd not in seen:
+            seen.add(dd)
+            want.append((dd, np.float32(-negs)))
+        if len(want) == 15:
+            break
+    assert ids.tolist() == [w[0] for w in want]
+    assert (f32_bits(sims) == f32_bits(np.array([w[1] for w in want], np.float32))).all()
+    assert len(set(ids.tolist())) == len(ids)
+
+
+def test_noop_fixture_shape():
+    r = noop_rows(4, 512, 0)
+    assert r.shape == (4, 520) and struct.unpack("<ff", r[0, :8].tobytes()) == (-1.0, 1.0)
