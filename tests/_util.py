@@ -32,3 +32,12 @@ def clustered_rows(n, d, k, seed, spread=0.35):
 
 def f32_bits(a):
     return np.ascontiguousarray(a, dtype=np.float32).view(np.uint32)
+
+
+def same_float(a, b):
+    """Bit-equal, except that any NaN matches any NaN (x86 and CUDA produce different NaN payloads)."""
+    a = np.ascontiguousarray(a)
+    b = np.ascontiguousarray(b)
+    assert a.dtype == b.dtype and a.shape == b.shape
+    u = np.uint32 if a.dtype == np.float32 else np.uint64
+    return bool(((a.view(u) == b.view(u)) | (np.isnan(a) & np.isnan(b))).all())

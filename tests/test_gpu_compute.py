@@ -8,7 +8,7 @@ import threading
 import numpy as np
 import pytest
 
-from _util import f32_bits, noop_rows, unit_rows
+from _util import f32_bits, noop_rows, same_float, unit_rows
 
 pytestmark = pytest.mark.gpu
 KAT = json.load(open(os.path.join(os.path.dirname(__file__), "golden", "kat.json")))
@@ -49,9 +49,8 @@ def test_quantize_random_parity(vs, oracle, d):
     x64[2] = 0
     assert (vs.compute.QuantizeMatrixFloat64(x64) == oracle.quantize_matrix_f64(x64)).all()
     rows = oracle.quantize_matrix_f32(x)
-    assert (f32_bits(vs.compute.DequantizeMatrixFloat32(rows)) == f32_bits(oracle.dequantize_matrix_f32(rows))).all()
-    assert (vs.compute.DequantizeMatrixFloat64(rows).view(np.uint64) ==
-            oracle.dequantize_matrix_f64(rows).view(np.uint64)).all()
+    assert same_float(vs.compute.DequantizeMatrixFloat32(rows), oracle.dequantize_matrix_f32(rows))
+    assert same_float(vs.compute.DequantizeMatrixFloat64(rows), oracle.dequantize_matrix_f64(rows))
 
 
 def test_quantize_unit_rows_768(vs, oracle):
