@@ -1,0 +1,463 @@
+#!/usr/bin/env python
+"""bench.py -- headline benchmark of the go-vectorsearch hot path on B200.
+
+Workload (BASELINE.json configs[1]): IVF-Flat search on 10M synthetic 768-d uint8-quantized vectors,
+4096 centroids, nprobe=32, top-10.  A "step" is one call of the search path over a batch of `--batch`
+independent queries (distinct queries every step; the 7.7 GB store is >> the 126 MB L2).
+
+  value   queries/s with the index and the queries resident in HBM (vs_search_dev + status check)
+  e2e     queries/s through the host-buffer C ABI call vs_search (H2D of the query rows and D2H of the
+          hits inside the timed region)
+  roofline  the list-scan kernel: rows scored x 776 B / its CUDA-event duration, vs measured HBM peak
+  cpu_baseline  the oracle (CPU restatement of the reference's default backend) on the host cores
+
+N > 1 (torchrun): strong scaling -- the same 10M-row store striped across the ranks by row id, the
+centroid table replicated, shard-local top-k all-gathered over NCCL and merged on device.
+
+`--impl reference` times the reference's own CPU algorithm (the oracle port; Go is not in this image).
+"""
+import argparse
+import json
+import os
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+D = 768
+ROW_BYTES = 8 + D
+SEED_DATA, SEED_QUERY, SEED_CENT = 0x5EED0001, 0x5EED0002, 0x5EED0003
+CHUNK = 1 << 18  # rows generated per chunk
+
+
+def parse():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=200)
+    ap.add_argument("--warmup", type=int, default=10)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--rows", type=int, default=int(os.environ.get("VS_BENCH_ROWS", 10_000_000)))
+    ap.add_argument("--centroids", type=int, default=4096)
+    ap.add_argument("--nprobe", type=int, default=32)
+    ap.add_argument("--k", type=int, default=10)
+    ap.add_argument("--batch", type=int, default=int(os.environ.get("VS_BENCH_BATCH", 64)))
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    return ap.parse_args()
+
+
+def workload_name(a):
+    return (f"IVF-Flat search, {a.rows} x {D}-d uint8 rows, {a.centroids} centroids, nprobe={a.nprobe}, "
+            f"top-{a.k}, batch={a.batch} queries/step")
+
+
+# ------------------------------------------------------------------------------------------------
+class ClockSampler:
+    """nvidia-smi-equivalent clock/throttle sampling (NVML) during the measured regions."""
+
+    def __init__(self, index):
+        self.samples, self.reasons, self.max_mhz = [], set(), None
+        self._stop = threading.Event()
+        self._t = None
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            self.nv = pynvml
+            self.h = pynvml.nvmlDeviceGetHandleByIndex(index)
+            self.max_mhz = pynvml.nvmlDeviceGetMaxClockInfo(self.h, pynvml.NVML_CLOCK_SM)
+        except Exception:  # noqa: BLE001
+            self.nv = None
+
+    def _run(self):
+        nv = self.nv
+        names = {
+            "hw_slowdown": getattr(nv, "nvmlClocksEventReasonHwSlowdown", 0x8),
+            "hw_thermal_slowdown": getattr(nv, "nvmlClocksEventReasonHwThermalSlowdown", 0x40),
+            "sw_thermal_slowdown": getattr(nv, "nvmlClocksEventReasonSwThermalSlowdown", 0x20),
+            "sw_power_cap": getattr(nv, "nvmlClocksEventReasonSwPowerCap", 0x4),
+        }
+        while not self._stop.is_set():
+            try:
+                self.samples.append(nv.nvmlDeviceGetClockInfo(self.h, nv.NVML_CLOCK_SM))
+                try:
+                    r = nv.nvmlDeviceGetCurrentClocksEventReasons(self.h)
+                except Exception:  # noqa: BLE001
+                    r = nv.nvmlDeviceGetCurrentClocksThrottleReasons(self.h)
+                for k, bit in names.items():
+                    if r & bit:
+                        self.reasons.add(k)
+            except Exception:  # noqa: BLE001
+                pass
+            self._stop.wait(0.05)
+
+    def start(self):
+        if self.nv:
+            self._t = threading.Thread(target=self._run, daemon=True)
+            self._t.start()
+
+    def stop(self):
+        self._stop.set()
+        if self._t:
+            self._t.join()
+        s = sorted(self.samples)
+        return {"sm_mhz": (s[len(s) // 2] if s else None), "sm_max_mhz": self.max_mhz, "reasons": sorted(self.reasons),
+                "samples": len(s)}
+
+
+# ------------------------------------------------------------------------------------------------
+def gen_unit_rows(torch, seed, chunk_index, count, device):
+    """x ~ N(0, I_768), L2-normalized, float32 -- keyed by (seed, chunk) so any rank regenerates any chunk."""
+    g = torch.Generator(device=device)
+    g.manual_seed(seed * 1_000_003 + chunk_index)
+    x = torch.randn(count, D, generator=g, device=device, dtype=torch.float32)
+    x /= x.norm(dim=1, keepdim=True)
+    return x
+
+
+def build_index(pkg, torch, ctx, a, rank, world, device):
+    """Synthetic store, generated and quantized on device, assigned to its nearest centroid, grouped into lists."""
+    cp = pkg.compute
+    t0 = time.time()
+    cent = cp.EmptyMatrix(a.centroids, D, ctx=ctx)
+    x = gen_unit_rows(torch, SEED_CENT, 0, a.centroids, device)
+    torch.cuda.synchronize()
+    cent.FillFloat32Dev(0, x.data_ptr(), a.centroids, ctx=ctx)
+    ctx.sync()
+    n_local = pkg.shard.local_count(a.rows, rank, world)
+    data = cp.EmptyMatrix(n_local, D, ctx=ctx)
+    filled = 0
+    for ci, r0 in enumerate(range(0, a.rows, CHUNK)):
+        cnt = min(CHUNK, a.rows - r0)
+        x = gen_unit_rows(torch, SEED_DATA, ci, cnt, device)
+        first = (rank - r0) % world          # first row of this chunk owned by this rank
+        xs = x[first::world].contiguous()
+        torch.cuda.synchronize()
+        data.FillFloat32Dev(filled, xs.data_ptr(), xs.shape[0], ctx=ctx)
+        ctx.sync()
+        filled += xs.shape[0]
+        del x, xs
+    assert filled == n_local, (filled, n_local)
+    ids = torch.arange(rank, a.rows, world, device=device, dtype=torch.int64)
+    assign = torch.empty(n_local, device=device, dtype=torch.int32)
+    torch.cuda.synchronize()
+    t1 = time.time()
+    cent.ArgmaxDev(data, assign.data_ptr(), ctx=ctx)   # nearest centroid of every row (compute/cosine.go:70-125)
+    ctx.sync()
+    t2 = time.time()
+    ix = pkg.ivf.Index.build_dev(data, assign.data_ptr(), ids.data_ptr(), cent, ctx=ctx)
+    ix._d = D
+    ctx.sync()
+    del data, assign, ids
+    torch.cuda.empty_cache()
+    return ix, cent, {"gen_quantize_s": round(t1 - t0, 2), "assign_s": round(t2 - t1, 2), "group_s": round(time.time() - t2, 2)}
+
+
+def run_b200(a):
+    import torch
+    from __graft_entry__ import load_pkg
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local_rank)
+    device = torch.device("cuda", local_rank)
+    dist = None
+    if world > 1:
+        import torch.distributed as dist
+        dist.init_process_group("nccl", device_id=device)
+    pkg = load_pkg()
+    pkg._lib.init(local_rank)
+    cp = pkg.compute
+
+    stream = torch.cuda.Stream(device=device)
+    ctx = cp.Context(cuda_stream=stream.cuda_stream)   # libvscuda kernels and NCCL share one stream
+    ix, cent, build_info = build_index(pkg, torch, ctx, a, rank, world, device)
+    offsets = ix.ListOffsets(ctx=ctx).astype(np.int64)
+    list_len = np.diff(offsets)
+
+    B, k, K, W = a.batch, a.k, a.steps, a.warmup
+    nsteps = K + W
+    # distinct queries every step, generated on device, kept as device matrices; host copies for e2e/oracle
+    qmats, qhost = [], []
+    for s in range(nsteps):
+        x = gen_unit_rows(torch, SEED_QUERY, s, B, device)
+        torch.cuda.synchronize()
+        m = cp.EmptyMatrix(B, D, ctx=ctx)
+        m.FillFloat32Dev(0, x.data_ptr(), B, ctx=ctx)
+        ctx.sync()
+        qmats.append(m)
+        qhost.append(m.ReadRows())
+    # rows each step scores on this rank (for GB/s): probed lists x local list lengths
+    rows_scored = []
+    for s in range(nsteps):
+        probes, _ = ix.SelectProbes(qhost[s], a.nprobe, ctx=ctx)
+        rows_scored.append(int(list_len[probes.astype(np.int64)].sum()))
+
+    d_ids = torch.zeros((B, k), device=device, dtype=torch.int64)
+    d_sims = torch.zeros((B, k), device=device, dtype=torch.float32)
+    d_counts = torch.zeros(B, device=device, dtype=torch.int32)
+    d_status = torch.zeros(B, device=device, dtype=torch.int32)
+    f_ids, f_sims, f_counts = torch.zeros_like(d_ids), torch.zeros_like(d_sims), torch.zeros_like(d_counts)
+
+    def step(s):
+        q = qmats[s]
+        ix.SearchDev(q, a.nprobe, k, d_ids.data_ptr(), d_sims.data_ptr(), d_counts.data_ptr(), d_status.data_ptr(), ctx=ctx)
+        ix.Resolve(q, a.nprobe, k, d_ids.data_ptr(), d_sims.data_ptr(), d_counts.data_ptr(), d_status.data_ptr(), ctx=ctx)
+        if world > 1:
+            with torch.cuda.stream(stream):
+                g = pkg.shard.gather_hits(d_ids, d_sims, d_counts)
+                pkg.shard.merge_hits_dev(g[0], g[1], g[2], k, f_ids, f_sims, f_counts, ctx=ctx)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    sampler = ClockSampler(local_rank)
+    sampler.start()
+    for s in range(W):
+        step(s)
+    barrier()
+    ctx.profile_enable(True)
+    launches0 = ctx.launch_count()
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    with torch.cuda.stream(stream):
+        ev0.record(stream)
+        for s in range(W, W + K):
+            step(s)
+        ev1.record(stream)
+    barrier()
+    ms_total = ev0.elapsed_time(ev1)
+    scan_ms, scan_launches = ctx.profile_read()
+    ctx.profile_enable(False)
+    launches = ctx.launch_count() - launches0
+    if world > 1:
+        t = torch.tensor([ms_total], device=device, dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms_total = float(t.item())
+    ms_per_step = ms_total / K
+    qps = B * K / (ms_total / 1e3)
+    result_ids = (f_ids if world > 1 else d_ids).cpu().numpy().view(np.uint64)
+    result_sims = (f_sims if world > 1 else d_sims).cpu().numpy()
+
+    # ---- single-query latency (batch 1), device resident ----
+    lat = []
+    one = cp.EmptyMatrix(1, D, ctx=ctx)
+    for i in range(min(64, B)):
+        one.LoadRows(0, qhost[0][i:i + 1], ctx=ctx)
+        ctx.sync()
+        ctx.timer_start()
+        ix.SearchDev(one, a.nprobe, k, d_ids.data_ptr(), d_sims.data_ptr(), d_counts.data_ptr(), d_status.data_ptr(), ctx=ctx)
+        lat.append(ctx.timer_stop() * 1e3)
+    lat = sorted(lat[4:]) if len(lat) > 8 else sorted(lat)
+
+    # ---- e2e: host query rows in pinned memory -> vs_search -> hits in pinned host memory ----
+    hq = torch.empty((B, ROW_BYTES), dtype=torch.uint8).pin_memory()
+    h_ids = torch.empty((B, k), dtype=torch.int64).pin_memory()
+    h_sims = torch.empty((B, k), dtype=torch.float32).pin_memory()
+    h_counts = torch.empty(B, dtype=torch.int32).pin_memory()
+    L = pkg._lib.load()
+    import ctypes as C
+    vp = lambda t: C.c_void_p(t.data_ptr())
+    qdev = cp.EmptyMatrix(B, D, ctx=ctx)
+
+    def e2e_step(s):
+        hq.numpy()[:] = qhost[s]
+        if world == 1:
+            rc = L.vs_search(ctx.handle, ix.handle, vp(hq), B, a.nprobe, k, vp(h_ids), vp(h_sims), vp(h_counts))
+            assert rc == 0, pkg._lib.last_error()
+        else:
+            qdev.LoadRows(0, hq.numpy(), ctx=ctx)
+            ix.SearchDev(qdev, a.nprobe, k, d_ids.data_ptr(), d_sims.data_ptr(), d_counts.data_ptr(), d_status.data_ptr(), ctx=ctx)
+            ix.Resolve(qdev, a.nprobe, k, d_ids.data_ptr(), d_sims.data_ptr(), d_counts.data_ptr(), d_status.data_ptr(), ctx=ctx)
+            with torch.cuda.stream(stream):
+                g = pkg.shard.gather_hits(d_ids, d_sims, d_counts)
+                pkg.shard.merge_hits_dev(g[0], g[1], g[2], k, f_ids, f_sims, f_counts, ctx=ctx)
+                h_ids.copy_(f_ids, non_blocking=True)
+                h_sims.copy_(f_sims, non_blocking=True)
+                h_counts.copy_(f_counts, non_blocking=True)
+            stream.synchronize()
+
+    for s in range(min(W, 3)):
+        e2e_step(s)
+    barrier()
+    t0 = time.perf_counter()
+    for s in range(W, W + K):
+        e2e_step(s)
+    barrier()
+    e2e_s = time.perf_counter() - t0
+    if world > 1:
+        t = torch.tensor([e2e_s], device=device, dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        e2e_s = float(t.item())
+    e2e_qps = B * K / e2e_s
+    e2e_match = bool((h_ids.numpy().view(np.uint64) == result_ids).all() and
+                     (h_sims.numpy().view(np.uint32) == result_sims.view(np.uint32)).all())
+    clocks = sampler.stop()
+
+    if rank != 0:
+        if world > 1:
+            dist.barrier()
+            dist.destroy_process_group()
+        return
+
+    peaks = {}
+    try:
+        peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+    except Exception:  # noqa: BLE001
+        pass
+    peak = float(peaks.get("hbm_gbs", 6650.0))
+    peak_src = "measured (MEASURED_PEAKS.json hbm_gbs)" if "hbm_gbs" in peaks else "fallback 6.65 TB/s (B200_PROFILING.md)"
+    scored = rows_scored[W:W + K]
+    bytes_per_launch = float(np.mean(scored)) * ROW_BYTES
+    scan_ms_avg = scan_ms / max(1, scan_launches)
+    achieved = bytes_per_launch / (scan_ms_avg * 1e-3) / 1e9 if scan_ms_avg > 0 else 0.0
+    traffic = None
+    try:
+        traffic = json.load(open(os.path.join(ROOT, "profiles", "scan_traffic.json"))).get("dram_bytes_per_launch")
+    except Exception:  # noqa: BLE001
+        pass
+    scan_gbs_step = (float(np.mean(scored)) + B * a.centroids) * ROW_BYTES / (ms_per_step * 1e-3) / 1e9
+
+    out = {
+        "metric": "IVF-Flat search queries/s (768-d uint8, top-10, bit-exact IDs)",
+        "value": round(qps, 1), "unit": "queries/s", "n_gpus": world, "steps": K, "warmup": W,
+        "ms_per_step": round(ms_per_step, 4), "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
+        "dtype": "u8", "data": "synthetic",
+        "config": {"workload": workload_name(a), "rows": a.rows, "dim": D, "centroids": a.centroids, "nprobe": a.nprobe,
+                   "k": k, "batch": B, "sharding": f"rows striped over {world} rank(s), centroids replicated",
+                   "l2": "store (rows x 768 B) >> 126 MB L2 and every step uses distinct queries; no flush needed",
+                   "build": build_info},
+        "scan_gbs": round(scan_gbs_step, 1),
+        "latency_us_batch1": {"p50": round(lat[len(lat) // 2], 1), "p99": round(lat[min(len(lat) - 1, int(len(lat) * 0.99))], 1),
+                              "n": len(lat)} if lat else None,
+        "roofline": {"bound": "hbm", "kernel": "stage_kernel (list scan + fused top-k)", "achieved": round(achieved, 1),
+                     "peak": peak, "peak_source": peak_src, "unit": "GB/s", "frac": round(achieved / peak, 4),
+                     "traffic": traffic, "bytes_per_launch": round(bytes_per_launch), "ms_per_launch": round(scan_ms_avg, 5),
+                     "launches_timed": scan_launches},
+        "e2e": {"value": round(e2e_qps, 1), "unit": "queries/s", "h2d_bytes_per_step": B * ROW_BYTES,
+                "d2h_bytes_per_step": B * k * 12 + B * 4 + B * 4, "results_match_device_path": e2e_match},
+        "gpu_launches": int(launches),
+        "slowpath_queries": ctx.slowpath_count(),
+        "clocks": clocks,
+    }
+
+    if world == 1 and not a.no_cpu_baseline:
+        out["cpu_baseline"] = cpu_baseline(pkg, ctx, ix, cent, a, qhost[W + K - 1], result_ids, result_sims, offsets)
+    print(json.dumps(out), flush=True)
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
+def cpu_baseline(pkg, ctx, ix, cent, a, queries, gpu_ids, gpu_sims, offsets):
+    """The oracle on the host cores, on a bounded sample: the first `nq` queries of the last timed step, each doing the
+    full per-query work (all centroids + its probed lists). Doubles as a parity check of the timed GPU results."""
+    import oracle
+    cores = os.cpu_count() or 1
+    centroids = cent.ReadRows()
+    nq_max = min(queries.shape[0], max(8, 2 * cores))
+
+    def host_index(qs):
+        lists = set()
+        for q in qs:
+            p, _ = oracle.select_probes(q, centroids, a.nprobe)
+            lists.update(int(x) for x in p)
+        rows, ids, lor = [], [], []
+        for Lx in sorted(lists):
+            r, i = ix.ReadRows(int(offsets[Lx]), int(offsets[Lx + 1] - offsets[Lx]), ctx=ctx)
+            rows.append(r)
+            ids.append(i)
+            lor.append(np.full(r.shape[0], Lx, np.uint32))
+        rows, ids, lor = np.concatenate(rows), np.concatenate(ids), np.concatenate(lor)
+        order = np.argsort(ids, kind="stable")   # the reference streams rows in primary-key order
+        return rows[order], ids[order], lor[order]
+
+    t0 = time.perf_counter()
+    rows1, ids1, lor1 = host_index(queries[:1])
+    t0 = time.perf_counter()
+    oracle.search_many(queries[:1], centroids, rows1, lor1, ids1, a.nprobe, a.k, threads=1)
+    t1 = time.perf_counter() - t0
+    nq = int(max(1, min(nq_max, round(15.0 * cores / max(t1, 1e-3)))))
+    rows, ids, lor = host_index(queries[:nq])
+    t0 = time.perf_counter()
+    o_ids, o_sims, o_counts = oracle.search_many(queries[:nq], centroids, rows, lor, ids, a.nprobe, a.k, threads=cores)
+    dt = time.perf_counter() - t0
+    parity = bool((o_ids == gpu_ids[:nq]).all() and (o_sims.view(np.uint32) == gpu_sims[:nq].view(np.uint32)).all())
+    return {"value": round(nq / dt, 3), "unit": "queries/s", "cores": cores, "kind": "port",
+            "sample": f"{nq} queries of the last timed step, full per-query work (4096 centroids + {a.nprobe} probed lists "
+                      f"~{int(rows.shape[0] / max(1, nq))} rows/query incl. overlap), oracle (default-backend restatement) on "
+                      f"{cores} threads; single-thread {round(1.0 / t1, 3)} q/s",
+            "seconds": round(dt, 2), "parity_vs_gpu_topk": parity}
+
+
+# ------------------------------------------------------------------------------------------------
+def run_reference(a):
+    """The reference's own CPU implementation of the path (oracle port of the default backend: Go cannot be built here),
+    all host threads, on a bounded sample per step: `nq` = min(batch, cores) queries, each scoring all centroids and
+    nprobe lists of the average list length (rows x 1/centroids).  The cost per query does not depend on the data, so
+    the probed lists are synthesized directly (no GPU involved): one pool of nprobe x avg rows is labelled, per query,
+    with that query's own probe list."""
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    import concurrent.futures as cf
+    import oracle
+    cores = os.cpu_count() or 1
+    rng = np.random.default_rng(SEED_DATA)
+
+    def unit(n):
+        x = rng.standard_normal((n, D), dtype=np.float32)
+        x /= np.linalg.norm(x, axis=1, keepdims=True)
+        return x
+
+    centroids = oracle.quantize_matrix_f32(unit(a.centroids))
+    avg = max(1, a.rows // a.centroids)
+    npe = min(a.nprobe, a.centroids)
+    rows = oracle.quantize_matrix_f32(unit(npe * avg))
+    doc = np.arange(rows.shape[0], dtype=np.uint64)
+    nq = max(1, min(a.batch, cores))
+    queries = oracle.quantize_matrix_f32(unit(nq * (a.steps + a.warmup)))
+
+    def one(q):
+        probes, _ = oracle.select_probes(q, centroids, a.nprobe)      # untimed relabelling of the pool
+        lor = np.repeat(probes.astype(np.uint32), avg)
+        t0 = time.perf_counter()
+        oracle.search(q, centroids, rows, lor, doc, a.nprobe, a.k)    # search.go:202-273 for this query
+        return time.perf_counter() - t0
+
+    def run_step(s):
+        with cf.ThreadPoolExecutor(cores) as ex:
+            return max(ex.map(one, queries[s * nq:(s + 1) * nq]))
+
+    for s in range(a.warmup):
+        run_step(s)
+    t0 = time.perf_counter()
+    for s in range(a.warmup, a.warmup + a.steps):
+        run_step(s)
+    dt = time.perf_counter() - t0
+    qps = nq * a.steps / dt
+    out = {
+        "impl": "reference",
+        "metric": "IVF-Flat search queries/s (768-d uint8, top-10, bit-exact IDs)",
+        "value": round(qps, 3), "unit": "queries/s", "n_gpus": a.gpus, "steps": a.steps, "warmup": a.warmup,
+        "ms_per_step": round(dt / a.steps * 1e3, 3), "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
+        "dtype": "f64", "data": "synthetic",
+        "config": {"workload": workload_name(a), "rows": a.rows, "dim": D, "centroids": a.centroids, "nprobe": a.nprobe,
+                   "k": a.k, "batch": a.batch},
+        "cpu_baseline": {"value": round(qps, 3), "unit": "queries/s", "cores": cores, "kind": "port",
+                         "sample": f"{nq} queries per step (one thread each, {cores} threads), each scoring {a.centroids} centroids "
+                                   f"+ {npe} lists x {avg} rows with the reference's default float64 backend restated in C"},
+        "e2e": {"value": round(qps, 3), "unit": "queries/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+    }
+    print(json.dumps(out), flush=True)
+
+
+if __name__ == "__main__":
+    args = parse()
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_b200(args)

@@ -11,4 +11,4 @@ B200; both failures raise loudly (BackendUnavailable).
 """
 from . import _lib  # noqa: F401
 from ._lib import BackendUnavailable, load, lib_path  # noqa: F401
-from . import compute, ivf, dnc  # noqa: F401
+from . import compute, ivf, dnc, shard  # noqa: F401

@@ -11,15 +11,15 @@ VS_OK, VS_EINVAL, VS_EEMPTY, VS_EDIM, VS_ECUDA, VS_ENODEV, VS_ENOMEM, VS_ERANGE 
 # every symbol include/vscuda.h declares (checked by tests/test_abi.py)
 SYMBOLS = [
     "vs_init", "vs_shutdown", "vs_last_error", "vs_device_info",
-    "vs_ctx_create", "vs_ctx_destroy", "vs_ctx_sync", "vs_ctx_stream", "vs_ctx_launch_count",
+    "vs_ctx_create", "vs_ctx_create_on_stream", "vs_ctx_profile_enable", "vs_ctx_profile_read", "vs_ctx_destroy", "vs_ctx_sync", "vs_ctx_stream", "vs_ctx_launch_count",
     "vs_ctx_slowpath_count", "vs_ctx_timer_start", "vs_ctx_timer_stop",
     "vs_quantize_f32", "vs_quantize_f64", "vs_dequantize_f32", "vs_dequantize_f64",
     "vs_quantize_f32_dev", "vs_quantize_f64_dev",
-    "vs_matrix_create", "vs_matrix_create_dev", "vs_matrix_from_f32_dev", "vs_matrix_retain",
+    "vs_matrix_create", "vs_matrix_create_empty", "vs_matrix_fill_f32_dev", "vs_matrix_load_rows", "vs_matrix_create_dev", "vs_matrix_from_f32_dev", "vs_matrix_retain",
     "vs_matrix_release", "vs_matrix_rows", "vs_matrix_cols", "vs_matrix_read_rows",
     "vs_cosine_1xN", "vs_dot_1xN", "vs_argmax_MxN", "vs_argmax_MxN_dev",
     "vs_index_build", "vs_index_build_assigned", "vs_index_build_dev", "vs_index_release",
-    "vs_index_rows", "vs_index_lists", "vs_search", "vs_search_flat", "vs_search_dev",
+    "vs_index_rows", "vs_index_lists", "vs_index_list_offsets", "vs_index_read_rows", "vs_search", "vs_search_flat", "vs_search_dev",
     "vs_search_resolve", "vs_select_probes", "vs_topk_merge_dev",
     "vs_kmeans_step", "vs_recenter",
 ]
@@ -69,6 +69,14 @@ def load():
             getattr(L, name).argtypes = [vp]
         L.vs_init.argtypes = [C.c_int]
         L.vs_ctx_create.argtypes = [C.POINTER(vp)]
+        L.vs_ctx_create_on_stream.argtypes = [vp, C.POINTER(vp)]
+        L.vs_ctx_profile_enable.argtypes = [vp, C.c_int]
+        L.vs_ctx_profile_read.argtypes = [vp, C.POINTER(C.c_double), C.POINTER(u64)]
+        L.vs_matrix_create_empty.argtypes = [vp, sz, sz, C.POINTER(vp)]
+        L.vs_matrix_fill_f32_dev.argtypes = [vp, vp, sz, vp, sz]
+        L.vs_matrix_load_rows.argtypes = [vp, vp, sz, vp, sz]
+        L.vs_index_list_offsets.argtypes = [vp, vp, vp]
+        L.vs_index_read_rows.argtypes = [vp, vp, sz, sz, vp, vp]
         L.vs_ctx_timer_stop.argtypes = [vp, C.POINTER(C.c_float)]
         L.vs_device_info.argtypes = [C.c_char_p, sz, C.POINTER(C.c_int), C.POINTER(sz)]
         L.vs_quantize_f32.argtypes = [vp, vp, sz, sz, vp]

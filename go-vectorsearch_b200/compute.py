@@ -51,12 +51,25 @@ def _p(a):
 class Context:
     """One CUDA stream + scratch arena (vs_ctx). One per closure / goroutine (dnc/dnc.go:349)."""
 
-    def __init__(self):
+    def __init__(self, cuda_stream=None):
+        """cuda_stream: optional raw cudaStream_t (int) to enqueue on, e.g. the stream NCCL uses."""
         L = _lib.init()
         h = C.c_void_p()
-        _check(L.vs_ctx_create(C.byref(h)))
+        if cuda_stream is None:
+            _check(L.vs_ctx_create(C.byref(h)))
+        else:
+            _check(L.vs_ctx_create_on_stream(C.c_void_p(int(cuda_stream)), C.byref(h)))
         self._h = h
         self._L = L
+
+    def profile_enable(self, on=True):
+        _check(self._L.vs_ctx_profile_enable(self.handle, 1 if on else 0))
+
+    def profile_read(self):
+        """(summed list-scan kernel ms, launches) since the last read."""
+        ms, cnt = C.c_double(), C.c_uint64()
+        _check(self._L.vs_ctx_profile_read(self.handle, C.byref(ms), C.byref(cnt)))
+        return ms.value, int(cnt.value)
 
     @property
     def handle(self):
@@ -155,6 +168,21 @@ class Matrix:
         _check(self._L.vs_argmax_MxN(ctx.handle, self._h, matrix._h, _p(sims) if want_sims else None, _p(idx)))
         return sims, idx
 
+    def FillFloat32Dev(self, first, d_ptr, count, ctx=None):
+        """Quantize `count` device float32 rows (raw pointer) into rows [first, first+count)."""
+        ctx = ctx or default_context()
+        _check(self._L.vs_matrix_fill_f32_dev(ctx.handle, self._h, int(first), C.c_void_p(int(d_ptr)), int(count)))
+
+    def LoadRows(self, first, rows, ctx=None):
+        """Overwrite rows from host row776 rows (async on the ctx stream; keep `rows` alive until sync)."""
+        ctx = ctx or default_context()
+        _check(self._L.vs_matrix_load_rows(ctx.handle, self._h, int(first), _p(rows), rows.shape[0]))
+
+    def ArgmaxDev(self, data, d_idx_ptr, ctx=None):
+        """Receiver = centroids; int32 nearest-centroid index per data row written to a device pointer."""
+        ctx = ctx or default_context()
+        _check(self._L.vs_argmax_MxN_dev(ctx.handle, self._h, data._h, C.c_void_p(int(d_idx_ptr))))
+
     def ReadRows(self, first=0, count=None):
         count = self.rows - first if count is None else count
         out = np.empty((count, 8 + self.cols), np.uint8)
@@ -215,6 +243,15 @@ def NewMatrix(matrixQuantized, ctx=None):
     ctx = ctx or default_context()
     h = C.c_void_p()
     _check(L.vs_matrix_create(ctx.handle, _p(rows), rows.shape[0], rows.shape[1], C.byref(h)))
+    return Matrix(h, L)
+
+
+def EmptyMatrix(n, d, ctx=None):
+    """Device matrix of n x d to be filled by Matrix.FillFloat32Dev / LoadRows (bulk loaders)."""
+    L = _lib.init()
+    ctx = ctx or default_context()
+    h = C.c_void_p()
+    _check(L.vs_matrix_create_empty(ctx.handle, int(n), int(d), C.byref(h)))
     return Matrix(h, L)
 
 

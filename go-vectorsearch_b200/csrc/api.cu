@@ -86,6 +86,23 @@ extern "C" int vs_ctx_create(vs_ctx **out) {
     CU(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
     CU(cudaEventCreate(&c->ev0));
     CU(cudaEventCreate(&c->ev1));
+    CU(cudaMalloc(&c->d_fix_counter, 8));
+    CU(cudaMemset(c->d_fix_counter, 0, 8));
+    *out = c;
+    return VS_OK;
+}
+
+extern "C" int vs_ctx_create_on_stream(void *cuda_stream, vs_ctx **out) {
+    VS(need_dev());
+    if (!out) return fail(VS_EINVAL, "out is null");
+    vs_ctx *c = new vs_ctx();
+    c->device = g_device;
+    c->stream = static_cast<cudaStream_t>(cuda_stream);
+    c->owns_stream = false;
+    CU(cudaEventCreate(&c->ev0));
+    CU(cudaEventCreate(&c->ev1));
+    CU(cudaMalloc(&c->d_fix_counter, 8));
+    CU(cudaMemset(c->d_fix_counter, 0, 8));
     *out = c;
     return VS_OK;
 }
@@ -96,10 +113,46 @@ extern "C" void vs_ctx_destroy(vs_ctx *c) {
     cudaStreamSynchronize(c->stream);
     if (c->scratch) cudaFree(c->scratch);
     if (c->pinned) cudaFreeHost(c->pinned);
+    if (c->d_fix_counter) cudaFree(c->d_fix_counter);
+    for (cudaEvent_t e : c->prof_events) cudaEventDestroy(e);
     cudaEventDestroy(c->ev0);
     cudaEventDestroy(c->ev1);
-    cudaStreamDestroy(c->stream);
+    if (c->owns_stream) cudaStreamDestroy(c->stream);
     delete c;
+}
+
+extern "C" int vs_ctx_profile_enable(vs_ctx *c, int on) {
+    if (!c) return fail(VS_EINVAL, "ctx is null");
+    CU(cudaStreamSynchronize(c->stream));
+    c->profile = on != 0;
+    c->prof_used = 0;
+    return VS_OK;
+}
+
+extern "C" int vs_ctx_profile_read(vs_ctx *c, double *ms_out, uint64_t *launches_out) {
+    if (!c) return fail(VS_EINVAL, "ctx is null");
+    CU(cudaStreamSynchronize(c->stream));
+    double total = 0;
+    for (size_t i = 0; i + 1 < c->prof_used; i += 2) {
+        float ms = 0;
+        CU(cudaEventElapsedTime(&ms, c->prof_events[i], c->prof_events[i + 1]));
+        total += ms;
+    }
+    if (ms_out) *ms_out = total;
+    if (launches_out) *launches_out = c->prof_used / 2;
+    c->prof_used = 0;
+    return VS_OK;
+}
+
+static int prof_mark(vs_ctx *c) {
+    if (!c->profile) return VS_OK;
+    if (c->prof_used == c->prof_events.size()) {
+        cudaEvent_t e;
+        CU(cudaEventCreate(&e));
+        c->prof_events.push_back(e);
+    }
+    CU(cudaEventRecord(c->prof_events[c->prof_used++], c->stream));
+    return VS_OK;
 }
 
 extern "C" int vs_ctx_sync(vs_ctx *c) {
@@ -109,7 +162,13 @@ extern "C" int vs_ctx_sync(vs_ctx *c) {
 }
 extern "C" void *vs_ctx_stream(vs_ctx *c) { return c ? (void *)c->stream : nullptr; }
 extern "C" uint64_t vs_ctx_launch_count(const vs_ctx *c) { return c ? c->launches : 0; }
-extern "C" uint64_t vs_ctx_slowpath_count(const vs_ctx *c) { return c ? c->slowpath : 0; }
+extern "C" uint64_t vs_ctx_slowpath_count(const vs_ctx *c) {
+    if (!c) return 0;
+    unsigned long long dev = 0;  // candidates re-scored inside the search kernels (synchronizes the stream)
+    cudaStreamSynchronize(c->stream);
+    cudaMemcpy(&dev, c->d_fix_counter, 8, cudaMemcpyDeviceToHost);
+    return c->slowpath + dev;
+}
 extern "C" int vs_ctx_timer_start(vs_ctx *c) {
     CU(cudaEventRecord(c->ev0, c->stream));
     return VS_OK;
@@ -252,7 +311,7 @@ extern "C" int vs_dequantize_f64(vs_ctx *c, const uint8_t *rows, size_t n, size_
 // matrices
 static int matrix_alloc(size_t n, size_t d, vs_matrix **out) {
     if (d > 4096) return fail(VS_ERANGE, "d=%zu: kernels support d <= 4096", d);
-    if (n > 0xFFFFFFF0ull) return fail(VS_ERANGE, "n=%zu: a device matrix holds < 2^32 rows", n);
+    if (n > 0x7FFFFFFFull) return fail(VS_ERANGE, "n=%zu: a device matrix holds < 2^31 rows", n);
     vs_matrix *m = new vs_matrix();
     m->device = g_device;
     m->n = n;
@@ -358,6 +417,38 @@ extern "C" int vs_matrix_from_f32_dev(vs_ctx *c, const float *d_in, size_t n, si
     }
     c->launches++;
     *out = m;
+    return VS_OK;
+}
+
+extern "C" int vs_matrix_create_empty(vs_ctx *c, size_t n, size_t d, vs_matrix **out) {
+    VS(need_dev());
+    if (!c || !out) return fail(VS_EINVAL, "null argument");
+    VS(check_rows(n, d + 8));
+    return matrix_alloc(n, d, out);
+}
+
+extern "C" int vs_matrix_fill_f32_dev(vs_ctx *c, vs_matrix *m, size_t first, const float *d_in, size_t count) {
+    VS(need_dev());
+    if (!c || !m || !d_in) return fail(VS_EINVAL, "null argument");
+    if (first + count > m->n) return fail(VS_EINVAL, "row range out of bounds");
+    if (count == 0) return VS_OK;
+    LAUNCH(c, launch_quantize_f32_soa(d_in, count, m->d, m->codes + first * (size_t)m->d_pad, m->d_pad, m->hdr + first,
+                                      m->sums + first, c->stream));
+    return VS_OK;
+}
+
+extern "C" int vs_matrix_load_rows(vs_ctx *c, vs_matrix *m, size_t first, const uint8_t *rows, size_t count) {
+    VS(need_dev());
+    if (!c || !m || !rows) return fail(VS_EINVAL, "null argument");
+    if (first + count > m->n) return fail(VS_EINVAL, "row range out of bounds");
+    if (count == 0) return VS_OK;
+    const size_t rb = 8 + (size_t)m->d;
+    Arena a(c);
+    VS(a.reserve(Arena::pad(count * rb) + 1024));
+    uint8_t *stage = a.take<uint8_t>(count * rb);
+    CU(cudaMemcpyAsync(stage, rows, count * rb, cudaMemcpyHostToDevice, c->stream));
+    LAUNCH(c, launch_ingest(stage, count, (int)rb, m->codes + first * (size_t)m->d_pad, m->d_pad, m->hdr + first,
+                            m->sums + first, c->stream));
     return VS_OK;
 }
 
@@ -562,6 +653,31 @@ extern "C" void vs_index_release(vs_index *ix) {
 extern "C" size_t vs_index_rows(const vs_index *ix) { return ix ? ix->n : 0; }
 extern "C" size_t vs_index_lists(const vs_index *ix) { return ix ? ix->C : 0; }
 
+extern "C" int vs_index_list_offsets(vs_ctx *c, const vs_index *ix, uint64_t *out) {
+    VS(need_dev());
+    if (!c || !ix || !out) return fail(VS_EINVAL, "null argument");
+    CU(cudaMemcpyAsync(out, ix->list_off, (ix->C + 1) * 8, cudaMemcpyDeviceToHost, c->stream));
+    CU(cudaStreamSynchronize(c->stream));
+    return VS_OK;
+}
+
+extern "C" int vs_index_read_rows(vs_ctx *c, const vs_index *ix, size_t first, size_t count, uint8_t *rows_out,
+                                  uint64_t *ids_out) {
+    VS(need_dev());
+    if (!c || !ix) return fail(VS_EINVAL, "null argument");
+    if (first + count > ix->n) return fail(VS_EINVAL, "row range out of bounds");
+    if (rows_out) VS(vs_matrix_read_rows(c, ix->data, first, count, rows_out));
+    if (ids_out) {
+        if (ix->doc_ids) {
+            CU(cudaMemcpyAsync(ids_out, ix->doc_ids + first, count * 8, cudaMemcpyDeviceToHost, c->stream));
+            CU(cudaStreamSynchronize(c->stream));
+        } else {
+            for (size_t i = 0; i < count; i++) ids_out[i] = ix->id_base + first + i;
+        }
+    }
+    return VS_OK;
+}
+
 extern "C" int vs_index_build_dev(vs_ctx *c, const vs_matrix *data, const int32_t *d_list_of_row, const uint64_t *d_doc_ids,
                                   uint64_t id_base, const vs_matrix *centroids, vs_index **out) {
     VS(need_dev());
@@ -669,45 +785,55 @@ extern "C" int vs_index_build(vs_ctx *c, const uint8_t *rows, size_t n, size_t r
 // ------------------------------------------------------------------------------------------------
 // search
 static int kpl_for(size_t k) {
-    if (k <= 32) return 1;
-    if (k <= 64) return 2;
-    if (k <= 128) return 4;
+    // capacity stays strictly above k so that a re-scored candidate can be certified against the tail
+    if (k <= 24) return 1;
+    if (k <= 56) return 2;
+    if (k <= 120) return 4;
     return 0;
 }
 
 struct SearchBufs {
-    uint32_t *probe;      // [nq][npe]
-    Cand *partial1;       // stage-1 partial lists
-    Cand *partial2;       // stage-2 partial lists
+    uint32_t *probe;        // [nq][npe]
+    uint32_t *qtiles;       // [nq] stage-2 tiles per query, written by stage 1
+    Cand *partial1;         // stage-1 partial lists
+    Cand *partial2;         // stage-2 partial lists
     unsigned int *tickets;  // [nq]
-    double *qnorm;        // exact only
-    uint32_t *q_select;   // exact only
-    int bpq1, bpq2;
+    double *qnorm;          // exact only
+    uint32_t *q_select;     // exact only
+    int grid;               // blocks per stage launch
+    int iters1, iters2;     // rows per lane group (tile height) of each stage
+    int tile_rows1, tile_rows2;
 };
 
-static int search_plan(const vs_index *ix, size_t nq, size_t npe, int kpl1, int kpl2, bool flat, int *bpq1, int *bpq2) {
-    // Stage 1 scans C centroid rows per query, stage 2 about npe average-length lists.
-    const size_t tiles1 = (ix->C + kTileRows - 1) / kTileRows;
+// Tile height: 32 rows when there is plenty of work per warp, 16 or 8 when a launch would otherwise give
+// each resident warp fewer than ~4 tiles (single-query latency).
+static void pick_tile(int d_pad, size_t rows_total, int grid, int *iters, int *tile_rows) {
+    const int G = stage_lanes_per_row(d_pad);
+    if (G == 0) {
+        *iters = 32;
+        *tile_rows = 32;
+        return;
+    }
+    const int NG = 32 / G;
+    int tr = 32;
+    const size_t warps = (size_t)grid * kStageWarps;
+    while (tr > 8 && rows_total / tr < 4 * warps) tr >>= 1;
+    *tile_rows = tr;
+    *iters = tr / NG;
+}
+
+static int search_plan(const vs_index *ix, size_t nq, size_t npe, bool flat, SearchBufs *b) {
+    b->grid = g_sm_count * 2;  // resident blocks per SM (__launch_bounds__ of stage_kernel)
+    const int d_pad = ix->data->d_pad;
+    pick_tile(d_pad, ix->C * nq, b->grid, &b->iters1, &b->tile_rows1);
     const size_t avg = ix->C ? (ix->n + ix->C - 1) / ix->C : 0;
-    const size_t tiles2 = flat ? (ix->n + kTileRows - 1) / kTileRows : npe * ((avg + kTileRows - 1) / kTileRows + 1);
-    auto pick = [&](size_t tiles, int kpl) {
-        size_t by_tiles = (tiles + kStageWarps - 1) / kStageWarps;
-        size_t occ = 2;  // resident blocks per SM (__launch_bounds__ of stage_kernel)
-        (void)kpl;
-        size_t by_sm = ((size_t)g_sm_count * occ + nq - 1) / nq;
-        size_t b = by_tiles < by_sm ? by_tiles : by_sm;
-        if (b < 1) b = 1;
-        return (int)b;
-    };
-    *bpq1 = pick(tiles1, kpl1);
-    *bpq2 = pick(tiles2, kpl2);
+    pick_tile(d_pad, (flat ? ix->n : npe * avg) * nq, b->grid, &b->iters2, &b->tile_rows2);
     return VS_OK;
 }
 
-static size_t search_bytes(size_t nq, size_t npe, int kpl1, int kpl2, int bpq1, int bpq2, size_t d) {
-    return Arena::pad(nq * npe * 4) + Arena::pad(nq * (size_t)bpq1 * 32 * kpl1 * sizeof(Cand)) +
-           Arena::pad(nq * (size_t)bpq2 * 32 * kpl2 * sizeof(Cand)) + Arena::pad(nq * 4) + Arena::pad(nq * d * 8) +
-           Arena::pad(nq * 4) + 4096;
+static size_t search_bytes(size_t nq, size_t npe, int kpl1, int kpl2, int grid, size_t d) {
+    return Arena::pad(nq * npe * 4) + Arena::pad((nq + grid) * (size_t)32 * kpl1 * sizeof(Cand)) +
+           Arena::pad((nq + grid) * (size_t)32 * kpl2 * sizeof(Cand)) + 3 * Arena::pad(nq * 4) + Arena::pad(nq * d * 8) + 4096;
 }
 
 // Enqueue the two stages for nq_launch queries (all, or those listed in d_select).
@@ -722,6 +848,8 @@ static int search_enqueue(vs_ctx *c, const vs_index *ix, const MatView &qv, size
     p.nq = (int)nq_launch;
     p.tickets = b.tickets;
     p.out_status = d_status;
+    p.fix_counter = c->d_fix_counter;
+    const uint32_t tr1 = exact ? 32 : b.tile_rows1, tr2 = exact ? 32 : b.tile_rows2;
     if (!flat) {
         p.rows = ix->centroids->view();
         p.ids = nullptr;
@@ -730,13 +858,19 @@ static int search_enqueue(vs_ctx *c, const vs_index *ix, const MatView &qv, size
         p.single_start = 0;
         p.single_count = ix->C;
         p.nseg = 1;
+        p.qtiles = nullptr;
+        p.uniform_tiles = (uint32_t)((ix->C + tr1 - 1) / tr1);
+        p.iters = b.iters1;
         p.partial = b.partial1;
         p.mode = 1;
         p.k = (int)npe;
         p.out_probe = b.probe;
         p.out_sims = d_probe_sims;
+        p.out_qtiles = b.qtiles;
+        p.next_list_off = ix->list_off;
+        p.next_tile_rows = tr2;
         p.status_bit = kStatusProbeAmbiguous;
-        LAUNCH(c, launch_stage(p, kpl1, exact, b.bpq1, c->stream));
+        LAUNCH(c, launch_stage(p, kpl1, exact, b.grid, c->stream));
         if (stage1_only) return VS_OK;
     }
     p.rows = ix->data->view();
@@ -747,12 +881,18 @@ static int search_enqueue(vs_ctx *c, const vs_index *ix, const MatView &qv, size
         p.single_start = 0;
         p.single_count = ix->n;
         p.nseg = 1;
+        p.qtiles = nullptr;
+        p.uniform_tiles = (uint32_t)((ix->n + tr2 - 1) / tr2);
+        if (p.uniform_tiles == 0) p.uniform_tiles = 1;
     } else {
         p.seg_list = b.probe;
         p.seg_stride = (int)npe;
         p.list_off = ix->list_off;
         p.nseg = (int)npe;
+        p.qtiles = b.qtiles;
+        p.uniform_tiles = 0;
     }
+    p.iters = b.iters2;
     p.partial = b.partial2;
     p.mode = 0;
     p.k = (int)k;
@@ -760,8 +900,11 @@ static int search_enqueue(vs_ctx *c, const vs_index *ix, const MatView &qv, size
     p.out_sims = d_sims;
     p.out_counts = d_counts;
     p.out_probe = nullptr;
+    p.out_qtiles = nullptr;
     p.status_bit = kStatusListAmbiguous;
-    LAUNCH(c, launch_stage(p, kpl2, exact, b.bpq2, c->stream));
+    VS(prof_mark(c));
+    LAUNCH(c, launch_stage(p, kpl2, exact, b.grid, c->stream));
+    VS(prof_mark(c));
     return VS_OK;
 }
 
@@ -775,24 +918,26 @@ struct SearchSetup {
 static int search_setup(vs_ctx *c, Arena &a, const vs_index *ix, size_t nq, size_t nprobe, size_t k, size_t extra_bytes,
                         SearchSetup *s, bool rank_all = false) {
     if (nq == 0) return fail(VS_EINVAL, "nq == 0");
-    if (nq > 65535) return fail(VS_ERANGE, "nq=%zu: at most 65535 queries per call", nq);
+    if (nq > (size_t)kMaxStageQueries) return fail(VS_ERANGE, "nq=%zu: at most %d queries per call", nq, kMaxStageQueries);
     if (k == 0) return fail(VS_EINVAL, "k == 0");
+    if (ix->n > 0x7FFFFFFFull) return fail(VS_ERANGE, "a device store holds < 2^31 rows per GPU");
     if (nprobe == 0) nprobe = 1;  // search.go:118-119
     s->flat = nprobe >= ix->C && !rank_all;  // rank_all: stage 1 only, the caller wants the ranked list itself
     s->npe = nprobe >= ix->C ? ix->C : nprobe;
     s->kpl2 = kpl_for(k);
     s->kpl1 = s->flat ? 1 : kpl_for(s->npe);
-    if (!s->kpl2) return fail(VS_ERANGE, "k=%zu: at most 128 hits (Count+Offset) per query", k);
-    if (!s->kpl1) return fail(VS_ERANGE, "nprobe=%zu: at most 128 probed lists unless nprobe >= number of lists", nprobe);
-    VS(search_plan(ix, nq, s->npe, s->kpl1, s->kpl2, s->flat, &s->b.bpq1, &s->b.bpq2));
-    VS(a.reserve(a.off + extra_bytes + search_bytes(nq, s->npe, s->kpl1, s->kpl2, s->b.bpq1, s->b.bpq2, ix->data->d)));
+    if (!s->kpl2) return fail(VS_ERANGE, "k=%zu: at most 120 hits (Count+Offset) per query", k);
+    if (!s->kpl1) return fail(VS_ERANGE, "nprobe=%zu: at most 120 probed lists unless nprobe >= number of lists", nprobe);
+    VS(search_plan(ix, nq, s->npe, s->flat, &s->b));
+    VS(a.reserve(a.off + extra_bytes + search_bytes(nq, s->npe, s->kpl1, s->kpl2, s->b.grid, ix->data->d)));
     return VS_OK;
 }
 
 static void search_take(Arena &a, const vs_index *ix, size_t nq, SearchSetup *s) {
     s->b.probe = a.take<uint32_t>(nq * s->npe);
-    s->b.partial1 = a.take<Cand>(nq * (size_t)s->b.bpq1 * 32 * s->kpl1);
-    s->b.partial2 = a.take<Cand>(nq * (size_t)s->b.bpq2 * 32 * s->kpl2);
+    s->b.qtiles = a.take<uint32_t>(nq);
+    s->b.partial1 = a.take<Cand>((nq + s->b.grid) * (size_t)32 * s->kpl1);
+    s->b.partial2 = a.take<Cand>((nq + s->b.grid) * (size_t)32 * s->kpl2);
     s->b.tickets = a.take<unsigned int>(nq);
     s->b.qnorm = a.take<double>(nq * (size_t)ix->data->d);
     s->b.q_select = a.take<uint32_t>(nq);

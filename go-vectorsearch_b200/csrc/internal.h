@@ -4,6 +4,7 @@
 #include <stdint.h>
 
 #include <atomic>
+#include <vector>
 
 #include "common.cuh"
 
@@ -18,6 +19,12 @@ struct vs_ctx {
     size_t scratch_cap = 0;
     void *pinned = nullptr;
     size_t pinned_cap = 0;
+    bool owns_stream = true;
+    unsigned long long *d_fix_counter = nullptr;  // in-kernel literal re-scores (device)
+    // optional per-kernel timing of the list-scan stage
+    bool profile = false;
+    std::vector<cudaEvent_t> prof_events;  // pairs (start, stop), recycled
+    size_t prof_used = 0;
 };
 
 struct vs_matrix {
@@ -44,7 +51,8 @@ struct vs_index {
 
 namespace vs {
 
-constexpr int kMaxSeg = 1024;     // max probed lists per query handled by one stage launch
+constexpr int kMaxSeg = 128;      // max probed lists per query (the probe list is a top-k of capacity <= 128)
+constexpr int kMaxStageQueries = 4096;  // queries per stage launch (their tile prefix lives in shared memory)
 constexpr int kStageWarps = 8;    // warps per block of the stage kernel
 constexpr int kTileRows = 32;     // rows scored per warp tile
 
@@ -63,8 +71,12 @@ struct StageParams {
     const uint64_t *list_off;     // CSR offsets when seg_list != null
     int nseg;
     uint64_t single_start, single_count;
+    // work decomposition: tiles per query (stage 2: written by stage 1) or a uniform count
+    const uint32_t *qtiles;       // [total queries] indexed like the outputs, or null
+    uint32_t uniform_tiles;       // used when qtiles == null
+    int iters;                    // rows per lane group in a tile (tile height = (32/G) * iters)
     // merge state
-    Cand *partial;                // [nq][gridDim.x][CAP]
+    Cand *partial;                // [nq + gridDim.x][CAP]: slot = query slot + block
     unsigned int *tickets;        // [nq], zeroed; reset by the last block
     // outputs
     int mode;                     // 0 = final hits, 1 = probe list
@@ -73,6 +85,10 @@ struct StageParams {
     float *out_sims;              // mode 0: [q][k]; mode 1 (optional): [q][k]
     int32_t *out_counts;          // mode 0: [q]
     uint32_t *out_probe;          // mode 1: [q][k]
+    uint32_t *out_qtiles;         // mode 1 (optional): [q] tiles the next stage will scan for this query
+    const uint64_t *next_list_off;  // CSR of the store scanned by the next stage (for out_qtiles)
+    uint32_t next_tile_rows;
+    unsigned long long *fix_counter;  // device counter: candidates re-scored with literal arithmetic in-kernel
     uint32_t *out_status;         // [q], OR-ed with status_bit / need-more bit
     uint32_t status_bit;
 };
@@ -82,7 +98,8 @@ constexpr uint32_t kStatusListAmbiguous = 2u;
 constexpr uint32_t kStatusNeedMore = 4u;
 
 // scan.cu
-cudaError_t launch_stage(const StageParams &p, int kpl, bool exact, int blocks_per_query, cudaStream_t st);
+cudaError_t launch_stage(const StageParams &p, int kpl, bool exact, int grid_blocks, cudaStream_t st);
+int stage_lanes_per_row(int d_pad);
 int stage_cap(int kpl);
 cudaError_t launch_query_normalize(const MatView &queries, double *qnorm, cudaStream_t st);
 cudaError_t launch_cosine_1xN(const MatView &rows, const MatView &query, float *sims, uint32_t *dots,

@@ -106,20 +106,11 @@ struct WarpTopK {
         }
     }
 
-    // Offer a stored list (32*KPL entries, sorted best-first).
-    __device__ __forceinline__ void merge_from(const Cand *src, int lane, bool use_ldcg) {
+    // Offer a stored list (32*KPL entries, sorted best-first) from shared memory.
+    __device__ __forceinline__ void merge_from(const Cand *src, int lane) {
 #pragma unroll
         for (int s = 0; s < KPL; s++) {
-            Cand c;
-            if (use_ldcg) {
-                const uint4 *p = reinterpret_cast<const uint4 *>(src + s * 32 + lane);
-                uint4 v = __ldcg(p);
-                c.skey = v.x;
-                c.meta = v.y;
-                c.id = (uint64_t)v.z | ((uint64_t)v.w << 32);
-            } else {
-                c = src[s * 32 + lane];
-            }
+            Cand c = src[s * 32 + lane];
             // lists are sorted: once a whole chunk fails the threshold the rest fails too
             bool any = __any_sync(FULL, c.skey != 0 && cand_better(c.skey, c.id, thr_key, thr_id));
             if (!any) break;
@@ -129,20 +120,21 @@ struct WarpTopK {
 };
 
 // ---------------------------------------------------------------------------------------------------
-// Tile dot products. Returns in each lane the integer dot of row (row0 + lane) with the query.
+// Tile dot products. A tile is NG*iters consecutive rows (NG = 32/G lane groups, `iters` rows per group):
+// group g streams rows g*iters+it. Returns in lane g*G+it (it < iters) the integer dot of that row.
 template <int G, int CPL>
 __device__ __forceinline__ uint32_t tile_dots(const uint8_t *__restrict__ codes, size_t row0, int nrows, int d_pad,
-                                              const uint4 (&q)[CPL], int lane) {
+                                              const uint4 (&q)[CPL], int lane, int iters) {
     constexpr int U = (CPL <= 3) ? 4 : 2;  // rows in flight per lane group
     const int g = lane / G, l = lane % G;
     uint32_t mydot = 0;
 #pragma unroll 1
-    for (int it0 = 0; it0 < G; it0 += U) {
+    for (int it0 = 0; it0 < iters; it0 += U) {
         uint4 v[U][CPL];
 #pragma unroll
         for (int u = 0; u < U; u++) {
-            int r = g * G + it0 + u;
-            bool ok = (it0 + u < G) && (r < nrows);
+            int r = g * iters + it0 + u;
+            bool ok = (it0 + u < iters) && (r < nrows);
             const uint8_t *p = codes + (row0 + (size_t)(ok ? r : 0)) * (size_t)d_pad + l * 16;
 #pragma unroll
             for (int j = 0; j < CPL; j++) v[u][j] = ok ? ld_stream_u4(p + j * G * 16) : make_uint4(0, 0, 0, 0);
@@ -160,7 +152,7 @@ __device__ __forceinline__ uint32_t tile_dots(const uint8_t *__restrict__ codes,
     return mydot;
 }
 
-// Any dimension: whole warp per row, query chunks read from shared memory.
+// Any dimension: whole warp per row (G = 32, NG = 1), query chunks read from shared memory.
 __device__ __forceinline__ uint32_t tile_dots_generic(const uint8_t *__restrict__ codes, size_t row0, int nrows,
                                                       int d_pad, const uint4 *__restrict__ qs, int lane) {
     const int CH = d_pad >> 4;
@@ -182,205 +174,384 @@ struct StageShared {
     uint64_t seg_start[kMaxSeg];
     uint32_t seg_len[kMaxSeg];
     SideConst qside;
+    double norm;
     unsigned int is_last;
+    unsigned int need_fix;
+    uint32_t tail_key;
+    uint64_t tail_id;
 };
+
+// Work decomposition (both stages, any batch): the launch's tiles form one global sequence -- query 0's
+// tiles, then query 1's, ... -- cut into gridDim.x equal contiguous ranges, one per block, so every SM
+// gets the same amount of scanning whatever nq is.  Block b owns tiles [ceil(b*T/Gd), ceil((b+1)*T/Gd));
+// tile t belongs to block floor(t*Gd/T).  A block walks the queries its range overlaps; per (query, block)
+// pair it leaves one partial top list in slot q+b (unique because q and b both only grow along the walk),
+// and the last block to finish a query merges that query's slots and emits.
+__device__ __forceinline__ uint32_t block_of_tile(uint64_t t, uint64_t T, uint32_t Gd) { return (uint32_t)((t * Gd) / T); }
+__device__ __forceinline__ uint64_t first_tile_of_block(uint64_t b, uint64_t T, uint32_t Gd) { return (b * T + Gd - 1) / Gd; }
 
 // G == 0 selects the generic (any d) tile routine; EXACT selects literal reference arithmetic.
 template <int G, int CPL, int KPL, bool EXACT>
 __global__ void __launch_bounds__(kStageWarps * 32, 2)
 stage_kernel(const StageParams p) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
-    StageShared &sh = *reinterpret_cast<StageShared *>(smem_raw);
-    Cand *sh_lists = reinterpret_cast<Cand *>(smem_raw + ((sizeof(StageShared) + 15) & ~size_t(15)));
-    uint4 *sh_q = reinterpret_cast<uint4 *>(sh_lists + (size_t)kStageWarps * 32 * KPL);  // generic path only
-
     constexpr int CAP = 32 * KPL;
+    StageShared &sh = *reinterpret_cast<StageShared *>(smem_raw);
+    size_t off = (sizeof(StageShared) + 15) & ~size_t(15);
+    Cand *sh_lists = reinterpret_cast<Cand *>(smem_raw + off);  // [kStageWarps][CAP]
+    off += (size_t)kStageWarps * CAP * sizeof(Cand);
+    double *sh_qn = reinterpret_cast<double *>(smem_raw + off);  // [D] normalized query (fix path)
+    off += (size_t)p.rows.d * sizeof(double);
+    uint32_t *sh_qprefix = reinterpret_cast<uint32_t *>(smem_raw + off);  // [nq+1] when p.qtiles
+    off += p.qtiles ? (((size_t)p.nq + 1) * 4 + 15) & ~size_t(15) : 0;
+    uint4 *sh_q = reinterpret_cast<uint4 *>(smem_raw + off);  // generic path only
+
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    const int qslot = blockIdx.y;
-    const int qi = p.q_select ? (int)p.q_select[qslot] : qslot;
     const int D = p.rows.d, d_pad = p.rows.d_pad;
-
-    // ---- prologue: segment table, query constants ----
-    const int nseg = p.seg_list ? p.nseg : 1;
-    for (int s = threadIdx.x; s < nseg; s += blockDim.x) {
-        uint64_t st, len;
-        if (p.seg_list) {
-            uint32_t L = p.seg_list[(size_t)qi * p.seg_stride + s];
-            st = p.list_off[L];
-            len = p.list_off[L + 1] - st;
-        } else {
-            st = p.single_start;
-            len = p.single_count;
-        }
-        sh.seg_start[s] = st;
-        sh.seg_len[s] = (uint32_t)len;
-    }
-    if (threadIdx.x == 0) {
-        float2 h = p.queries.hdr[qi];
-        uint2 s = p.queries.sums[qi];
-        sh.qside = make_side(h.x, h.y, s.x, s.y, D);
-    }
-    if (G == 0 && !EXACT) {
-        const uint4 *qsrc = reinterpret_cast<const uint4 *>(p.queries.codes + (size_t)qi * d_pad);
-        for (int c = threadIdx.x; c < (d_pad >> 4); c += blockDim.x) sh_q[c] = qsrc[c];
-    }
-    __syncthreads();
-    if (warp == 0) {  // inclusive scan of tiles per segment
-        uint32_t carry = 0;
-        for (int base = 0; base < nseg; base += 32) {
-            int s = base + lane;
-            uint32_t v = s < nseg ? (sh.seg_len[s] + kTileRows - 1) / kTileRows : 0;
-#pragma unroll
-            for (int o = 1; o < 32; o <<= 1) {
-                uint32_t t = __shfl_up_sync(FULL, v, o);
-                if (lane >= o) v += t;
-            }
-            if (s < nseg) sh.tile_prefix[s + 1] = carry + v;
-            carry += __shfl_sync(FULL, v, 31);
-        }
-        if (lane == 0) sh.tile_prefix[0] = 0;
-    }
-    __syncthreads();
-    const uint32_t total_tiles = sh.tile_prefix[nseg];
-    const SideConst xq = sh.qside;
     const double sqrtD = sqrt((double)D);
+    constexpr int GG = (G == 0) ? 32 : G;
+    const int iters = (G == 0 || EXACT) ? 32 : p.iters;  // rows per lane group in a tile
+    const int tile_rows = (G == 0 || EXACT) ? 32 : (32 / GG) * iters;
 
-    uint4 qreg[CPL > 0 ? CPL : 1];
-    if constexpr (G != 0 && !EXACT) {
-        const uint8_t *qc = p.queries.codes + (size_t)qi * d_pad;
+    // ---- global tile space ----
+    uint64_t T;
+    if (p.qtiles) {
+        if (warp == 0) {
+            uint32_t carry = 0;
+            for (int base = 0; base < p.nq; base += 32) {
+                int s = base + lane;
+                uint32_t v = 0;
+                if (s < p.nq) v = p.qtiles[p.q_select ? p.q_select[s] : s];
 #pragma unroll
-        for (int j = 0; j < CPL; j++) qreg[j] = *reinterpret_cast<const uint4 *>(qc + ((lane % G) + G * j) * 16);
+                for (int o = 1; o < 32; o <<= 1) {
+                    uint32_t t = __shfl_up_sync(FULL, v, o);
+                    if (lane >= o) v += t;
+                }
+                if (s < p.nq) sh_qprefix[s + 1] = carry + v;
+                carry += __shfl_sync(FULL, v, 31);
+            }
+            if (lane == 0) sh_qprefix[0] = 0;
+        }
+        __syncthreads();
+        T = sh_qprefix[p.nq];
+    } else {
+        T = (uint64_t)p.uniform_tiles * p.nq;
     }
-    const double *qn = EXACT ? p.qnorm + (size_t)qi * D : nullptr;
-
-    WarpTopK<KPL> top;
-    top.init();
-
-    // ---- main loop: warp tiles ----
-    const uint32_t wstride = gridDim.x * kStageWarps;
-    for (uint32_t t = blockIdx.x * kStageWarps + warp; t < total_tiles; t += wstride) {
-        int lo = 0, hi = nseg;  // find seg with prefix[seg] <= t < prefix[seg+1]
+    if (T == 0) return;
+    const uint32_t Gd = (uint64_t)gridDim.x < T ? gridDim.x : (uint32_t)T;  // never more blocks than tiles
+    if (blockIdx.x >= Gd) return;
+    uint64_t t0 = first_tile_of_block(blockIdx.x, T, Gd);
+    const uint64_t t1 = first_tile_of_block((uint64_t)blockIdx.x + 1, T, Gd);
+    if (t0 >= t1) return;
+    int qslot;
+    if (p.qtiles) {
+        int lo = 0, hi = p.nq;
         while (hi - lo > 1) {
             int mid = (lo + hi) >> 1;
-            if (sh.tile_prefix[mid] <= t) lo = mid;
+            if (sh_qprefix[mid] <= t0) lo = mid;
             else hi = mid;
         }
-        const uint32_t tin = t - sh.tile_prefix[lo];
-        const size_t row0 = sh.seg_start[lo] + (size_t)tin * kTileRows;
-        const int nrows = min((uint32_t)kTileRows, sh.seg_len[lo] - tin * kTileRows);
-        const size_t row = row0 + lane;
-        const bool valid = lane < nrows;
-
-        float sim;
-        bool flag = false;
-        if constexpr (EXACT) {
-            sim = 0.0f;
-            if (valid) {
-                float2 h = p.rows.hdr[row];
-                sim = ref_cosine_row(p.rows.codes + row * (size_t)d_pad, h.x, h.y, qn, D);
-            }
-        } else {
-            uint32_t mydot;
-            if constexpr (G != 0) mydot = tile_dots<G, CPL>(p.rows.codes, row0, nrows, d_pad, qreg, lane);
-            else mydot = tile_dots_generic(p.rows.codes, row0, nrows, d_pad, sh_q, lane);
-            float2 h = valid ? p.rows.hdr[row] : make_float2(0.f, 0.f);
-            uint2 s = valid ? p.rows.sums[row] : make_uint2(0, 0);
-            SideConst y = make_side(h.x, h.y, s.x, s.y, D);
-            sim = score_certified(xq, y, mydot, D, sqrtD, &flag);
-        }
-        uint32_t key = f32_to_key(sim);
-        // lazy id: only rows that can still enter the list need their document id
-        uint64_t cid = kEmptyId;
-        if (valid && key >= top.thr_key) cid = p.ids ? p.ids[row] : p.id_base + row;
-        top.offer(valid && key >= top.thr_key, key, flag ? kFlagBit : 0u, cid, lane);
-    }
-
-    // ---- block merge: all warps -> warp 0 ----
-    top.store(sh_lists + (size_t)warp * CAP, lane);
-    __syncthreads();
-    Cand *my_partial = p.partial + ((size_t)qslot * gridDim.x + blockIdx.x) * CAP;
-    if (warp == 0) {
-        for (int w = 1; w < kStageWarps; w++) top.merge_from(sh_lists + (size_t)w * CAP, lane, false);
-        top.store(my_partial, lane);
-        __threadfence();
-        if (lane == 0) {
-            unsigned int tk = atomicAdd(&p.tickets[qslot], 1u);
-            sh.is_last = (tk == gridDim.x - 1) ? 1u : 0u;
-        }
-    }
-    __syncthreads();
-    if (!sh.is_last) return;
-
-    // ---- last block of this query: merge every block's list ----
-    __threadfence();
-    top.init();
-    for (int b = warp; b < (int)gridDim.x; b += kStageWarps)
-        top.merge_from(p.partial + ((size_t)qslot * gridDim.x + b) * CAP, lane, true);
-    __syncthreads();
-    top.store(sh_lists + (size_t)warp * CAP, lane);
-    __syncthreads();
-    if (warp != 0) return;
-    for (int w = 1; w < kStageWarps; w++) top.merge_from(sh_lists + (size_t)w * CAP, lane, false);
-    if (lane == 0) p.tickets[qslot] = 0;  // re-arm for the next launch
-
-    // ---- emit ----
-    uint32_t status = 0;
-    if (p.mode == 1) {  // probe list: ids are unique list indices, no dedup
-        bool anyflag = false;
-#pragma unroll
-        for (int s = 0; s < KPL; s++) {
-            int r = s * 32 + lane;
-            bool in = r < p.k && top.skey[s] != 0;
-            if (in) {
-                p.out_probe[(size_t)qi * p.k + r] = (uint32_t)top.id[s];
-                if (p.out_sims) p.out_sims[(size_t)qi * p.k + r] = key_to_f32(top.skey[s]);
-            }
-            anyflag |= __any_sync(FULL, in && (top.meta[s] & kFlagBit));
-        }
-        if (anyflag) status |= p.status_bit;
+        qslot = lo;
     } else {
-        // dedup by id keeping the best-ranked entry (server/search.go:260-268)
-        bool dup[KPL];
+        qslot = (int)(t0 / p.uniform_tiles);
+    }
+
+    for (; t0 < t1; qslot++) {
+        const uint64_t P0 = p.qtiles ? sh_qprefix[qslot] : (uint64_t)qslot * p.uniform_tiles;
+        const uint64_t P1 = p.qtiles ? sh_qprefix[qslot + 1] : P0 + p.uniform_tiles;
+        if (P1 <= t0) continue;  // a query with no tiles
+        const uint64_t tend = t1 < P1 ? t1 : P1;
+        const uint32_t ta = (uint32_t)(t0 - P0), tb = (uint32_t)(tend - P0);  // this block's tiles of this query
+        t0 = tend;
+        const int qi = p.q_select ? (int)p.q_select[qslot] : qslot;
+
+        // ---- per-query prologue: segment table, query constants ----
+        __syncthreads();
+        const int nseg = p.seg_list ? p.nseg : 1;
+        for (int s = threadIdx.x; s < nseg; s += blockDim.x) {
+            uint64_t st, len;
+            if (p.seg_list) {
+                uint32_t L = p.seg_list[(size_t)qi * p.seg_stride + s];
+                st = p.list_off[L];
+                len = p.list_off[L + 1] - st;
+            } else {
+                st = p.single_start;
+                len = p.single_count;
+            }
+            sh.seg_start[s] = st;
+            sh.seg_len[s] = (uint32_t)len;
+        }
+        if (threadIdx.x == 0) {
+            float2 h = p.queries.hdr[qi];
+            uint2 s = p.queries.sums[qi];
+            sh.qside = make_side(h.x, h.y, s.x, s.y, D);
+        }
+        if constexpr (G == 0 && !EXACT) {
+            const uint4 *qsrc = reinterpret_cast<const uint4 *>(p.queries.codes + (size_t)qi * d_pad);
+            for (int c = threadIdx.x; c < (d_pad >> 4); c += blockDim.x) sh_q[c] = qsrc[c];
+        }
+        __syncthreads();
+        if (warp == 0) {  // inclusive scan of tiles per segment
+            uint32_t carry = 0;
+            for (int base = 0; base < nseg; base += 32) {
+                int s = base + lane;
+                uint32_t v = s < nseg ? (sh.seg_len[s] + tile_rows - 1) / tile_rows : 0;
 #pragma unroll
-        for (int s = 0; s < KPL; s++) dup[s] = false;
+                for (int o = 1; o < 32; o <<= 1) {
+                    uint32_t t = __shfl_up_sync(FULL, v, o);
+                    if (lane >= o) v += t;
+                }
+                if (s < nseg) sh.tile_prefix[s + 1] = carry + v;
+                carry += __shfl_sync(FULL, v, 31);
+            }
+            if (lane == 0) sh.tile_prefix[0] = 0;
+        }
+        __syncthreads();
+        const uint32_t seg_tiles = sh.tile_prefix[nseg];
+        const SideConst xq = sh.qside;
+
+        uint4 qreg[CPL > 0 ? CPL : 1];
+        if constexpr (G != 0 && !EXACT) {
+            const uint8_t *qc = p.queries.codes + (size_t)qi * d_pad;
 #pragma unroll
-        for (int s0 = 0; s0 < KPL; s0++) {
-            for (int l0 = 0; l0 < 32; l0++) {
-                uint64_t bid = __shfl_sync(FULL, top.id[s0], l0);
-                uint32_t bk = __shfl_sync(FULL, top.skey[s0], l0);
-                if (bk == 0) break;  // rest of the list is empty (warp-uniform)
+            for (int j = 0; j < CPL; j++) qreg[j] = *reinterpret_cast<const uint4 *>(qc + ((lane % G) + G * j) * 16);
+        }
+        const double *qn = EXACT ? p.qnorm + (size_t)qi * D : nullptr;
+
+        WarpTopK<KPL> top;
+        top.init();
+
+        // ---- main loop: this block's tiles of this query, round-robin over its warps ----
+        const uint32_t tb_eff = tb < seg_tiles ? tb : seg_tiles;  // a query padded to 1 tile may have none
+        for (uint32_t t = ta + warp; t < tb_eff; t += kStageWarps) {
+            int lo = 0, hi = nseg;  // segment with tile_prefix[seg] <= t < tile_prefix[seg+1]
+            while (hi - lo > 1) {
+                int mid = (lo + hi) >> 1;
+                if (sh.tile_prefix[mid] <= t) lo = mid;
+                else hi = mid;
+            }
+            const uint32_t tin = t - sh.tile_prefix[lo];
+            const size_t row0 = sh.seg_start[lo] + (size_t)tin * tile_rows;
+            const int nrows = min((uint32_t)tile_rows, sh.seg_len[lo] - tin * tile_rows);
+            const int myr = (lane / GG) * iters + (lane % GG);  // tile row finished by this lane
+            const bool valid = (lane % GG) < iters && myr < nrows;
+            const size_t row = row0 + (valid ? myr : 0);
+
+            float sim;
+            bool flag = false;
+            if constexpr (EXACT) {
+                sim = 0.0f;
+                if (valid) {
+                    float2 h = p.rows.hdr[row];
+                    sim = ref_cosine_row(p.rows.codes + row * (size_t)d_pad, h.x, h.y, qn, D);
+                }
+            } else {
+                uint32_t mydot;
+                if constexpr (G != 0) mydot = tile_dots<G, CPL>(p.rows.codes, row0, nrows, d_pad, qreg, lane, iters);
+                else mydot = tile_dots_generic(p.rows.codes, row0, nrows, d_pad, sh_q, lane);
+                float2 h = valid ? p.rows.hdr[row] : make_float2(0.f, 0.f);
+                uint2 s = valid ? p.rows.sums[row] : make_uint2(0, 0);
+                SideConst y = make_side(h.x, h.y, s.x, s.y, D);
+                sim = score_certified(xq, y, mydot, D, sqrtD, &flag);
+            }
+            uint32_t key = f32_to_key(sim);
+            // lazy id: only rows that can still enter the list need their document id
+            const bool cand = valid && key >= top.thr_key;
+            uint64_t cid = kEmptyId;
+            if (cand) cid = p.ids ? p.ids[row] : p.id_base + row;
+            top.offer(cand, key, (uint32_t)row | (flag ? kFlagBit : 0u), cid, lane);
+        }
+
+        // ---- block merge: all warps -> warp 0 -> partial slot (qslot + block) ----
+        top.store(sh_lists + (size_t)warp * CAP, lane);
+        __syncthreads();
+        const uint32_t blo = block_of_tile(P0, T, Gd), bhi = block_of_tile(P1 - 1, T, Gd);
+        if (warp == 0) {
+            for (int w = 1; w < kStageWarps; w++) top.merge_from(sh_lists + (size_t)w * CAP, lane);
+            top.store(p.partial + ((size_t)qslot + blockIdx.x) * CAP, lane);
+            __threadfence();
+            if (lane == 0) {
+                unsigned int tk = atomicAdd(&p.tickets[qslot], 1u);
+                sh.is_last = (tk == bhi - blo) ? 1u : 0u;
+            }
+        }
+        __syncthreads();
+        if (!sh.is_last) continue;
+
+        // ---- last block of this query: merge its slots (loads batched 4 deep), fix, emit ----
+        __threadfence();
+        top.init();
+        {
+            const Cand *base = p.partial + ((size_t)qslot + blo) * CAP;
+            const int nslots = (int)(bhi - blo + 1);
+            for (int s0 = warp; s0 < nslots; s0 += kStageWarps * 4) {
+                uint4 v[4];
 #pragma unroll
-                for (int s = 0; s < KPL; s++) {
-                    int r = s * 32 + lane;
-                    if (r > s0 * 32 + l0 && top.skey[s] != 0 && top.id[s] == bid) dup[s] = true;
+                for (int u = 0; u < 4; u++) {
+                    int s = s0 + u * kStageWarps;
+                    v[u] = s < nslots ? __ldcg(reinterpret_cast<const uint4 *>(base + (size_t)s * CAP + lane))
+                                      : make_uint4(0, 0, 0, 0);
+                }
+#pragma unroll
+                for (int u = 0; u < 4; u++) {
+                    int s = s0 + u * kStageWarps;
+                    if (s >= nslots) break;
+                    uint64_t id = (uint64_t)v[u].z | ((uint64_t)v[u].w << 32);
+                    top.offer(v[u].x != 0, v[u].x, v[u].y, id, lane);
+                    if (KPL > 1) {  // deeper chunks only matter if the first chunk's last entry made it
+                        for (int c = 1; c < KPL; c++) {
+                            uint4 w = __ldcg(reinterpret_cast<const uint4 *>(base + (size_t)s * CAP + c * 32 + lane));
+                            uint64_t wid = (uint64_t)w.z | ((uint64_t)w.w << 32);
+                            bool any = __any_sync(FULL, w.x != 0 && cand_better(w.x, wid, top.thr_key, top.thr_id));
+                            if (!any) break;
+                            top.offer(w.x != 0, w.x, w.y, wid, lane);
+                        }
+                    }
                 }
             }
         }
-        int base = 0;
-        int uniq_total = 0;
-        bool anyflag = false;
-        bool full = __shfl_sync(FULL, top.skey[KPL - 1], 31) != 0;
-#pragma unroll
-        for (int s = 0; s < KPL; s++) {
-            bool keep = top.skey[s] != 0 && !dup[s];
-            unsigned m = __ballot_sync(FULL, keep);
-            int outpos = base + __popc(m & ((1u << lane) - 1u));
-            if (keep && outpos < p.k) {
-                p.out_ids[(size_t)qi * p.k + outpos] = top.id[s];
-                p.out_sims[(size_t)qi * p.k + outpos] = key_to_f32(top.skey[s]);
-            }
-            // every entry (kept or duplicate) ranked before the k-th unique one must be certain
-            anyflag |= __any_sync(FULL, top.skey[s] != 0 && outpos < p.k && (top.meta[s] & kFlagBit));
-            base += __popc(m);
+        top.store(sh_lists + (size_t)warp * CAP, lane);
+        __syncthreads();
+        if (warp == 0) {
+            for (int w = 1; w < kStageWarps; w++) top.merge_from(sh_lists + (size_t)w * CAP, lane);
+            if (lane == 0) p.tickets[qslot] = 0;  // re-arm for the next launch
         }
-        uniq_total = base;
-        if (anyflag) status |= p.status_bit;
-        if (uniq_total < p.k && full) status |= kStatusNeedMore;
-        if (lane == 0) p.out_counts[qi] = min(uniq_total, p.k);
-    }
-    if (lane == 0 && p.out_status) {
-        if (EXACT) p.out_status[qi] = (p.out_status[qi] & ~p.status_bit) | (status & kStatusNeedMore);
-        else p.out_status[qi] |= status;
+
+        // Emit; first (non-EXACT) re-score flagged candidates inside the emit window with literal arithmetic.
+        uint32_t status = 0;
+        for (int pass = 0; pass < 2; pass++) {
+            bool need_fix = false;
+            if (warp == 0) {
+                bool dup[KPL];
+                int outpos[KPL];
+#pragma unroll
+                for (int s = 0; s < KPL; s++) dup[s] = false;
+                if (p.mode == 0) {  // dedup by id keeping the best-ranked entry (server/search.go:260-268)
+#pragma unroll
+                    for (int s0 = 0; s0 < KPL; s0++) {
+                        for (int l0 = 0; l0 < 32; l0++) {
+                            uint64_t bid = __shfl_sync(FULL, top.id[s0], l0);
+                            uint32_t bk = __shfl_sync(FULL, top.skey[s0], l0);
+                            if (bk == 0) break;  // rest of the list is empty (warp-uniform)
+#pragma unroll
+                            for (int s = 0; s < KPL; s++) {
+                                int r = s * 32 + lane;
+                                if (r > s0 * 32 + l0 && top.skey[s] != 0 && top.id[s] == bid) dup[s] = true;
+                            }
+                        }
+                    }
+                }
+                int base = 0;
+                bool anyflag = false;
+                uint32_t kth_key = 0;
+                uint64_t kth_id = kEmptyId;
+#pragma unroll
+                for (int s = 0; s < KPL; s++) {
+                    bool keep = top.skey[s] != 0 && !dup[s];
+                    unsigned m = __ballot_sync(FULL, keep);
+                    outpos[s] = base + __popc(m & ((1u << lane) - 1u));
+                    // every entry (kept or duplicate) ranked before the k-th unique one must be certain
+                    anyflag |= __any_sync(FULL, top.skey[s] != 0 && outpos[s] < p.k && (top.meta[s] & kFlagBit));
+                    unsigned mk = __ballot_sync(FULL, keep && outpos[s] == p.k - 1);
+                    if (mk) {
+                        kth_key = __shfl_sync(FULL, top.skey[s], __ffs(mk) - 1);
+                        kth_id = __shfl_sync(FULL, top.id[s], __ffs(mk) - 1);
+                    }
+                    base += __popc(m);
+                }
+                const bool full = top.thr_key != 0;
+                if (pass == 0 && anyflag && !EXACT) {
+                    need_fix = true;
+                    top.store(sh_lists, lane);
+                    if (lane == 0) {
+                        sh.tail_key = top.thr_key;
+                        sh.tail_id = top.thr_id;
+                    }
+                } else {
+                    if (anyflag) status |= p.status_bit;  // (EXACT never flags; defensive)
+                    if (pass == 1 && full && kth_key != 0 && cand_better(sh.tail_key, sh.tail_id, kth_key, kth_id))
+                        status |= p.status_bit;  // a re-scored entry fell below rows that were not kept
+                    if (p.mode == 1) {
+                        uint32_t mytiles = 0;
+#pragma unroll
+                        for (int s = 0; s < KPL; s++) {
+                            int r = s * 32 + lane;
+                            if (r < p.k && top.skey[s] != 0) {
+                                uint32_t L = (uint32_t)top.id[s];
+                                p.out_probe[(size_t)qi * p.k + r] = L;
+                                if (p.out_sims) p.out_sims[(size_t)qi * p.k + r] = key_to_f32(top.skey[s]);
+                                if (p.out_qtiles) {
+                                    uint32_t len = (uint32_t)(p.next_list_off[L + 1] - p.next_list_off[L]);
+                                    mytiles += (len + p.next_tile_rows - 1) / p.next_tile_rows;
+                                }
+                            }
+                        }
+                        if (p.out_qtiles) {
+#pragma unroll
+                            for (int o = 16; o > 0; o >>= 1) mytiles += __shfl_xor_sync(FULL, mytiles, o);
+                            if (lane == 0) p.out_qtiles[qi] = mytiles ? mytiles : 1u;
+                        }
+                    } else {
+#pragma unroll
+                        for (int s = 0; s < KPL; s++) {
+                            bool keep = top.skey[s] != 0 && !dup[s];
+                            if (keep && outpos[s] < p.k) {
+                                p.out_ids[(size_t)qi * p.k + outpos[s]] = top.id[s];
+                                p.out_sims[(size_t)qi * p.k + outpos[s]] = key_to_f32(top.skey[s]);
+                            }
+                        }
+                        if (base < p.k && full) status |= kStatusNeedMore;
+                        if (lane == 0) p.out_counts[qi] = min(base, p.k);
+                    }
+                    if (lane == 0 && p.out_status) {
+                        if (EXACT) p.out_status[qi] = (p.out_status[qi] & ~p.status_bit) | (status & kStatusNeedMore);
+                        else p.out_status[qi] |= status;
+                    }
+                }
+                if (lane == 0) sh.need_fix = need_fix ? 1u : 0u;
+            }
+            __syncthreads();
+            if (!sh.need_fix) break;
+            // normalizeVector of the query (compute/cosine.go:26,138-149), literal: parallel dequantize,
+            // one thread sums the squares in order, parallel divide.
+            {
+                const uint8_t *qc = p.queries.codes + (size_t)qi * d_pad;
+                const float2 qh = p.queries.hdr[qi];
+                const double mn = (double)qh.x, range = __dsub_rn((double)qh.y, (double)qh.x);
+                for (int i = threadIdx.x; i < D; i += blockDim.x) sh_qn[i] = ref_dequant_f64(qc[i], mn, range);
+                __syncthreads();
+                if (threadIdx.x == 0) {
+                    double norm = 0.0;
+                    for (int i = 0; i < D; i++) norm = __dadd_rn(norm, __dmul_rn(sh_qn[i], sh_qn[i]));
+                    sh.norm = __dsqrt_rn(norm);
+                }
+                __syncthreads();
+                const double norm = sh.norm;
+                if (norm != 0.0)
+                    for (int i = threadIdx.x; i < D; i += blockDim.x) sh_qn[i] = __ddiv_rn(sh_qn[i], norm);
+                __syncthreads();
+                for (int e = threadIdx.x; e < CAP; e += blockDim.x) {
+                    Cand c = sh_lists[e];
+                    if (c.skey != 0 && (c.meta & kFlagBit)) {
+                        const size_t row = c.meta & ~kFlagBit;
+                        const float2 h = p.rows.hdr[row];
+                        c.skey = f32_to_key(ref_cosine_row(p.rows.codes + row * (size_t)d_pad, h.x, h.y, sh_qn, D));
+                        c.meta &= ~kFlagBit;
+                        sh_lists[e] = c;
+                        if (p.fix_counter) atomicAdd(p.fix_counter, 1ull);
+                    }
+                }
+                __syncthreads();
+                if (warp == 0) {  // re-sort: entries only moved down by at most one float32 step
+                    top.init();
+#pragma unroll
+                    for (int s = 0; s < KPL; s++) {
+                        Cand c = sh_lists[s * 32 + lane];
+                        top.offer(c.skey != 0, c.skey, c.meta, c.id, lane);
+                    }
+                }
+            }
+        }
     }
 }
 
@@ -388,38 +559,50 @@ stage_kernel(const StageParams p) {
 int stage_cap(int kpl) { return 32 * kpl; }
 
 template <int G, int CPL, int KPL, bool EXACT>
-static cudaError_t launch_stage_t(const StageParams &p, int blocks_per_query, cudaStream_t st) {
-    size_t smem = ((sizeof(StageShared) + 15) & ~size_t(15)) + (size_t)kStageWarps * 32 * KPL * sizeof(Cand);
+static cudaError_t launch_stage_t(const StageParams &p, int grid_blocks, cudaStream_t st) {
+    size_t smem = ((sizeof(StageShared) + 15) & ~size_t(15)) + (size_t)kStageWarps * 32 * KPL * sizeof(Cand) +
+                  (size_t)p.rows.d * sizeof(double);
+    if (p.qtiles) smem += (((size_t)p.nq + 1) * 4 + 15) & ~size_t(15);
     if (G == 0) smem += (size_t)p.rows.d_pad;
     auto kern = stage_kernel<G, CPL, KPL, EXACT>;
     if (smem > 48 * 1024) {
         cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         if (e != cudaSuccess) return e;
     }
-    dim3 grid(blocks_per_query, p.nq);
-    kern<<<grid, kStageWarps * 32, smem, st>>>(p);
+    kern<<<grid_blocks, kStageWarps * 32, smem, st>>>(p);
     return cudaGetLastError();
 }
 
 template <int KPL>
-static cudaError_t launch_stage_k(const StageParams &p, bool exact, int bpq, cudaStream_t st) {
-    if (exact) return launch_stage_t<0, 0, KPL, true>(p, bpq, st);
+static cudaError_t launch_stage_k(const StageParams &p, bool exact, int grid_blocks, cudaStream_t st) {
+    if (exact) return launch_stage_t<0, 0, KPL, true>(p, grid_blocks, st);
     const int ch = p.rows.d_pad >> 4;
     switch (ch) {
-        case 48: return launch_stage_t<16, 3, KPL, false>(p, bpq, st);  // 768-d (nomic-embed-text)
-        case 32: return launch_stage_t<32, 1, KPL, false>(p, bpq, st);  // 512-d (noop/ai.go)
-        case 64: return launch_stage_t<32, 2, KPL, false>(p, bpq, st);  // 1024-d
-        case 96: return launch_stage_t<32, 3, KPL, false>(p, bpq, st);  // 1536-d
-        case 24: return launch_stage_t<8, 3, KPL, false>(p, bpq, st);   // 384-d
-        default: return launch_stage_t<0, 0, KPL, false>(p, bpq, st);
+        case 48: return launch_stage_t<16, 3, KPL, false>(p, grid_blocks, st);  // 768-d (nomic-embed-text)
+        case 32: return launch_stage_t<32, 1, KPL, false>(p, grid_blocks, st);  // 512-d (noop/ai.go)
+        case 64: return launch_stage_t<32, 2, KPL, false>(p, grid_blocks, st);  // 1024-d
+        case 96: return launch_stage_t<32, 3, KPL, false>(p, grid_blocks, st);  // 1536-d
+        case 24: return launch_stage_t<8, 3, KPL, false>(p, grid_blocks, st);   // 384-d
+        default: return launch_stage_t<0, 0, KPL, false>(p, grid_blocks, st);
     }
 }
 
-cudaError_t launch_stage(const StageParams &p, int kpl, bool exact, int blocks_per_query, cudaStream_t st) {
+// Lanes per row for this row width (0 = generic routine): decides the tile heights the host may choose.
+int stage_lanes_per_row(int d_pad) {
+    switch (d_pad >> 4) {
+        case 48: return 16;
+        case 32: case 64: case 96: return 32;
+        case 24: return 8;
+        default: return 0;
+    }
+}
+
+cudaError_t launch_stage(const StageParams &p, int kpl, bool exact, int grid_blocks, cudaStream_t st) {
+    if (p.nq > kMaxStageQueries) return cudaErrorInvalidValue;
     switch (kpl) {
-        case 1: return launch_stage_k<1>(p, exact, blocks_per_query, st);
-        case 2: return launch_stage_k<2>(p, exact, blocks_per_query, st);
-        case 4: return launch_stage_k<4>(p, exact, blocks_per_query, st);
+        case 1: return launch_stage_k<1>(p, exact, grid_blocks, st);
+        case 2: return launch_stage_k<2>(p, exact, grid_blocks, st);
+        case 4: return launch_stage_k<4>(p, exact, grid_blocks, st);
         default: return cudaErrorInvalidValue;
     }
 }
@@ -490,7 +673,7 @@ cosine_1xN_kernel(MatView rows, MatView query, float *sims, uint32_t *dots, uint
         const size_t row0 = t * kTileRows;
         const int nrows = (int)min((size_t)kTileRows, rows.n - row0);
         uint32_t mydot;
-        if constexpr (G != 0) mydot = tile_dots<G, CPL>(rows.codes, row0, nrows, d_pad, qreg, lane);
+        if constexpr (G != 0) mydot = tile_dots<G, CPL>(rows.codes, row0, nrows, d_pad, qreg, lane, G);
         else mydot = tile_dots_generic(rows.codes, row0, nrows, d_pad, sh_q, lane);
         if (lane < nrows) {
             const size_t row = row0 + lane;

@@ -51,6 +51,53 @@ class Index:
                                          centroids.shape[0], C.byref(h)))
         return cls(h, L)
 
+    @classmethod
+    def build_dev(cls, data, d_list_of_row_ptr, d_doc_ids_ptr, centroids, id_base=0, ctx=None):
+        """Device-resident build: data/centroids are compute.Matrix, the two pointers are device arrays
+        (int32 list index per row; uint64 ids or 0/None for id_base + row)."""
+        L = _lib.init()
+        ctx = ctx or default_context()
+        h = C.c_void_p()
+        _check(L.vs_index_build_dev(ctx.handle, data.handle, C.c_void_p(int(d_list_of_row_ptr)),
+                                    C.c_void_p(int(d_doc_ids_ptr)) if d_doc_ids_ptr else None, int(id_base),
+                                    centroids.handle, C.byref(h)))
+        return cls(h, L)
+
+    def ListOffsets(self, ctx=None):
+        ctx = ctx or default_context()
+        out = np.empty(self.lists + 1, np.uint64)
+        _check(self._L.vs_index_list_offsets(ctx.handle, self._h, _p(out)))
+        return out
+
+    def ReadRows(self, first, count, ctx=None):
+        """(rows776, ids) of the grouped store."""
+        ctx = ctx or default_context()
+        width = 8 + self._cols(ctx)
+        rows = np.empty((count, width), np.uint8)
+        ids = np.empty(count, np.uint64)
+        _check(self._L.vs_index_read_rows(ctx.handle, self._h, int(first), int(count), _p(rows), _p(ids)))
+        return rows, ids
+
+    def _cols(self, ctx):
+        if not hasattr(self, "_d"):
+            raise RuntimeError("set index._d (dimension) before ReadRows")
+        return self._d
+
+    def SearchDev(self, queries, nprobe, k, d_ids, d_sims, d_counts, d_status, ctx=None):
+        """Asynchronous device-resident search: queries is a compute.Matrix, outputs are raw device pointers."""
+        ctx = ctx or default_context()
+        _check(self._L.vs_search_dev(ctx.handle, self._h, queries.handle, int(nprobe), int(k), C.c_void_p(int(d_ids)),
+                                     C.c_void_p(int(d_sims)), C.c_void_p(int(d_counts)), C.c_void_p(int(d_status))))
+
+    def Resolve(self, queries, nprobe, k, d_ids, d_sims, d_counts, d_status, ctx=None):
+        """Finish queries whose float32 roundings could not be certified (reads the status: synchronizes)."""
+        ctx = ctx or default_context()
+        n = C.c_int(0)
+        _check(self._L.vs_search_resolve(ctx.handle, self._h, queries.handle, int(nprobe), int(k),
+                                         C.c_void_p(int(d_ids)), C.c_void_p(int(d_sims)), C.c_void_p(int(d_counts)),
+                                         C.c_void_p(int(d_status)), C.byref(n)))
+        return n.value
+
     @property
     def rows(self):
         return int(self._L.vs_index_rows(self._h))
@@ -100,3 +147,12 @@ def SearchFlat(matrix, queries, k, ctx=None):
     counts = np.zeros(nq, np.int32)
     _check(matrix._L.vs_search_flat(ctx.handle, matrix.handle, None, _p(q), nq, int(k), _p(ids), _p(sims), _p(counts)))
     return ids, sims, counts
+
+
+def TopKMergeDev(d_ids_in, d_sims_in, d_counts_in, G, nq, k, d_ids_out, d_sims_out, d_counts_out, ctx=None):
+    """Merge G gathered shard-local hit lists per query ([G][nq][k] device arrays) into the global top-k."""
+    L = _lib.init()
+    ctx = ctx or default_context()
+    vp = lambda x: C.c_void_p(int(x))
+    _check(L.vs_topk_merge_dev(ctx.handle, vp(d_ids_in), vp(d_sims_in), vp(d_counts_in), int(G), int(nq), int(k),
+                               vp(d_ids_out), vp(d_sims_out), vp(d_counts_out)))

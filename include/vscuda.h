@@ -52,6 +52,8 @@ VS_API int vs_device_info(char *name, size_t name_cap, int *sm_count, size_t *to
  * return (calculate, done).  calculate-closure creation == vs_ctx_create, done() == vs_ctx_destroy.
  * Contexts are independent and may be used concurrently from different threads (dnc/dnc.go:30-33). */
 VS_API int vs_ctx_create(vs_ctx **out);
+/* Same, but work is enqueued on a caller-owned cudaStream_t (e.g. the stream NCCL collectives run on). */
+VS_API int vs_ctx_create_on_stream(void *cuda_stream, vs_ctx **out);
 VS_API void vs_ctx_destroy(vs_ctx *ctx);
 VS_API int vs_ctx_sync(vs_ctx *ctx);
 VS_API void *vs_ctx_stream(vs_ctx *ctx);                 /* cudaStream_t, for callers that time with events */
@@ -60,6 +62,11 @@ VS_API uint64_t vs_ctx_slowpath_count(const vs_ctx *ctx);/* rows / queries that 
 /* CUDA-event timing on the ctx stream (bench.py): start/stop bracket, elapsed in ms after sync. */
 VS_API int vs_ctx_timer_start(vs_ctx *ctx);
 VS_API int vs_ctx_timer_stop(vs_ctx *ctx, float *ms_out);
+/* Per-kernel timing of the dominant kernel (the list-scan stage of vs_search*): when enabled, every
+ * launch of it is bracketed by CUDA events on the ctx stream; read returns the summed duration and the
+ * number of launches since the last read (synchronizes). */
+VS_API int vs_ctx_profile_enable(vs_ctx *ctx, int on);
+VS_API int vs_ctx_profile_read(vs_ctx *ctx, double *scan_ms_out, uint64_t *scan_launches_out);
 
 /* ---- compute/quantization.go ------------------------------------------------------- */
 /* QuantizeMatrixFloat32 (quantization.go:142-148) / QuantizeVectorFloat32 (:82-91; n=1).
@@ -83,6 +90,12 @@ VS_API int vs_matrix_create(vs_ctx *ctx, const uint8_t *rows_packed, size_t n, s
 VS_API int vs_matrix_create_dev(vs_ctx *ctx, const uint8_t *d_rows_packed, size_t n, size_t row_bytes, vs_matrix **out);
 /* Quantize n*d device floats straight into a device matrix (QuantizeMatrixFloat32 + NewMatrix fused). */
 VS_API int vs_matrix_from_f32_dev(vs_ctx *ctx, const float *d_in, size_t n, size_t d, vs_matrix **out);
+/* Allocate an n x d matrix and fill row ranges from device float32 rows (bulk loaders). */
+VS_API int vs_matrix_create_empty(vs_ctx *ctx, size_t n, size_t d, vs_matrix **out);
+VS_API int vs_matrix_fill_f32_dev(vs_ctx *ctx, vs_matrix *m, size_t first_row, const float *d_in, size_t count);
+/* Overwrite rows [first_row, first_row+count) from host row776 rows (asynchronous H2D + ingest on the ctx
+ * stream; the host buffer must stay valid until the next vs_ctx_sync). Used to refill a query matrix. */
+VS_API int vs_matrix_load_rows(vs_ctx *ctx, vs_matrix *m, size_t first_row, const uint8_t *rows_packed, size_t count);
 /* Clone (compute.go:65-77): device matrices are immutable, so Clone is a reference-count bump. */
 VS_API void vs_matrix_retain(vs_matrix *m);
 VS_API void vs_matrix_release(vs_matrix *m);
@@ -122,6 +135,9 @@ VS_API int vs_index_build_dev(vs_ctx *ctx, const vs_matrix *data, const int32_t 
 VS_API void vs_index_release(vs_index *ix);
 VS_API size_t vs_index_rows(const vs_index *ix);
 VS_API size_t vs_index_lists(const vs_index *ix);
+/* Read back the CSR offsets (C+1 values) and rows [first, first+count) of the grouped store with their ids. */
+VS_API int vs_index_list_offsets(vs_ctx *ctx, const vs_index *ix, uint64_t *offsets_out);
+VS_API int vs_index_read_rows(vs_ctx *ctx, const vs_index *ix, size_t first, size_t count, uint8_t *rows_out, uint64_t *ids_out);
 /* Search (search.go:115-273 minus embedding/DB hops): nq query rows (row776, host), nprobe =
  * SearchRequest.Centroids (>= number of lists means "all"), k = Count+Offset.  Outputs (host):
  * ids_out[nq*k] document IDs, sims_out[nq*k] float32 similarities, counts_out[nq] valid entries.
