@@ -11,7 +11,7 @@ VS_OK, VS_EINVAL, VS_EEMPTY, VS_EDIM, VS_ECUDA, VS_ENODEV, VS_ENOMEM, VS_ERANGE 
 # every symbol include/vscuda.h declares (checked by tests/test_abi.py)
 SYMBOLS = [
     "vs_init", "vs_shutdown", "vs_last_error", "vs_device_info",
-    "vs_ctx_create", "vs_ctx_create_on_stream", "vs_ctx_profile_enable", "vs_ctx_profile_read", "vs_ctx_destroy", "vs_ctx_sync", "vs_ctx_stream", "vs_ctx_launch_count",
+    "vs_ctx_create", "vs_ctx_create_on_stream", "vs_ctx_profile_enable", "vs_ctx_profile_read", "vs_ctx_trace_enable", "vs_ctx_trace_read", "vs_ctx_destroy", "vs_ctx_sync", "vs_ctx_stream", "vs_ctx_launch_count",
     "vs_ctx_slowpath_count", "vs_ctx_timer_start", "vs_ctx_timer_stop",
     "vs_quantize_f32", "vs_quantize_f64", "vs_dequantize_f32", "vs_dequantize_f64",
     "vs_quantize_f32_dev", "vs_quantize_f64_dev",
@@ -72,6 +72,8 @@ def load():
         L.vs_ctx_create_on_stream.argtypes = [vp, C.POINTER(vp)]
         L.vs_ctx_profile_enable.argtypes = [vp, C.c_int]
         L.vs_ctx_profile_read.argtypes = [vp, C.POINTER(C.c_double), C.POINTER(u64)]
+        L.vs_ctx_trace_enable.argtypes = [vp, C.c_int]
+        L.vs_ctx_trace_read.argtypes = [vp, C.c_int, vp, sz, C.POINTER(sz)]
         L.vs_matrix_create_empty.argtypes = [vp, sz, sz, C.POINTER(vp)]
         L.vs_matrix_fill_f32_dev.argtypes = [vp, vp, sz, vp, sz]
         L.vs_matrix_load_rows.argtypes = [vp, vp, sz, vp, sz]

@@ -65,6 +65,16 @@ class Context:
     def profile_enable(self, on=True):
         _check(self._L.vs_ctx_profile_enable(self.handle, 1 if on else 0))
 
+    def trace_enable(self, on=True):
+        _check(self._L.vs_ctx_trace_enable(self.handle, 1 if on else 0))
+
+    def trace_read(self, stage):
+        """[blocks, 16] uint64 %globaltimer stamps (ns) of the latest launch of search stage 1 or 2."""
+        out = np.zeros((4096, 16), np.uint64)
+        nb = C.c_size_t()
+        _check(self._L.vs_ctx_trace_read(self.handle, int(stage), _p(out), 4096, C.byref(nb)))
+        return out[:nb.value]
+
     def profile_read(self):
         """(summed list-scan kernel ms, launches) since the last read."""
         ms, cnt = C.c_double(), C.c_uint64()

@@ -114,6 +114,7 @@ extern "C" void vs_ctx_destroy(vs_ctx *c) {
     if (c->scratch) cudaFree(c->scratch);
     if (c->pinned) cudaFreeHost(c->pinned);
     if (c->d_fix_counter) cudaFree(c->d_fix_counter);
+    if (c->d_trace) cudaFree(c->d_trace);
     for (cudaEvent_t e : c->prof_events) cudaEventDestroy(e);
     cudaEventDestroy(c->ev0);
     cudaEventDestroy(c->ev1);
@@ -141,6 +142,29 @@ extern "C" int vs_ctx_profile_read(vs_ctx *c, double *ms_out, uint64_t *launches
     if (ms_out) *ms_out = total;
     if (launches_out) *launches_out = c->prof_used / 2;
     c->prof_used = 0;
+    return VS_OK;
+}
+
+constexpr size_t kTraceBlocks = 2048;
+extern "C" int vs_ctx_trace_enable(vs_ctx *c, int on) {
+    if (!c) return fail(VS_EINVAL, "ctx is null");
+    CU(cudaStreamSynchronize(c->stream));
+    if (on && !c->d_trace) {
+        CU(cudaMalloc(&c->d_trace, 2 * kTraceBlocks * 16 * sizeof(unsigned long long)));
+        CU(cudaMemset(c->d_trace, 0, 2 * kTraceBlocks * 16 * sizeof(unsigned long long)));
+    }
+    c->trace = on != 0;
+    return VS_OK;
+}
+extern "C" int vs_ctx_trace_read(vs_ctx *c, int stage, uint64_t *out, size_t max_blocks, size_t *blocks_out) {
+    if (!c || !out || !c->d_trace) return fail(VS_EINVAL, "trace not enabled");
+    if (stage < 1 || stage > 2) return fail(VS_EINVAL, "stage must be 1 or 2");
+    CU(cudaStreamSynchronize(c->stream));
+    size_t nb = (size_t)g_sm_count * 2;
+    if (nb > max_blocks) nb = max_blocks;
+    if (nb > kTraceBlocks) nb = kTraceBlocks;
+    CU(cudaMemcpy(out, c->d_trace + (size_t)(stage - 1) * kTraceBlocks * 16, nb * 16 * sizeof(unsigned long long), cudaMemcpyDeviceToHost));
+    if (blocks_out) *blocks_out = nb;
     return VS_OK;
 }
 
@@ -785,10 +809,9 @@ extern "C" int vs_index_build(vs_ctx *c, const uint8_t *rows, size_t n, size_t r
 // ------------------------------------------------------------------------------------------------
 // search
 static int kpl_for(size_t k) {
-    // capacity stays strictly above k so that a re-scored candidate can be certified against the tail
-    if (k <= 24) return 1;
-    if (k <= 56) return 2;
-    if (k <= 120) return 4;
+    if (k <= 32) return 1;
+    if (k <= 64) return 2;
+    if (k <= 128) return 4;
     return 0;
 }
 
@@ -870,6 +893,8 @@ static int search_enqueue(vs_ctx *c, const vs_index *ix, const MatView &qv, size
         p.next_list_off = ix->list_off;
         p.next_tile_rows = tr2;
         p.status_bit = kStatusProbeAmbiguous;
+        p.trace = c->trace ? c->d_trace : nullptr;
+        if (p.trace) CU(cudaMemsetAsync(p.trace, 0, kTraceBlocks * 16 * sizeof(unsigned long long), c->stream));
         LAUNCH(c, launch_stage(p, kpl1, exact, b.grid, c->stream));
         if (stage1_only) return VS_OK;
     }
@@ -902,6 +927,8 @@ static int search_enqueue(vs_ctx *c, const vs_index *ix, const MatView &qv, size
     p.out_probe = nullptr;
     p.out_qtiles = nullptr;
     p.status_bit = kStatusListAmbiguous;
+    p.trace = c->trace ? c->d_trace + kTraceBlocks * 16 : nullptr;
+    if (p.trace) CU(cudaMemsetAsync(p.trace, 0, kTraceBlocks * 16 * sizeof(unsigned long long), c->stream));
     VS(prof_mark(c));
     LAUNCH(c, launch_stage(p, kpl2, exact, b.grid, c->stream));
     VS(prof_mark(c));
@@ -926,8 +953,8 @@ static int search_setup(vs_ctx *c, Arena &a, const vs_index *ix, size_t nq, size
     s->npe = nprobe >= ix->C ? ix->C : nprobe;
     s->kpl2 = kpl_for(k);
     s->kpl1 = s->flat ? 1 : kpl_for(s->npe);
-    if (!s->kpl2) return fail(VS_ERANGE, "k=%zu: at most 120 hits (Count+Offset) per query", k);
-    if (!s->kpl1) return fail(VS_ERANGE, "nprobe=%zu: at most 120 probed lists unless nprobe >= number of lists", nprobe);
+    if (!s->kpl2) return fail(VS_ERANGE, "k=%zu: at most 128 hits (Count+Offset) per query", k);
+    if (!s->kpl1) return fail(VS_ERANGE, "nprobe=%zu: at most 128 probed lists unless nprobe >= number of lists", nprobe);
     VS(search_plan(ix, nq, s->npe, s->flat, &s->b));
     VS(a.reserve(a.off + extra_bytes + search_bytes(nq, s->npe, s->kpl1, s->kpl2, s->b.grid, ix->data->d)));
     return VS_OK;

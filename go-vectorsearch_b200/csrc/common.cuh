@@ -69,6 +69,11 @@ __device__ __forceinline__ uint4 ld_stream_u4(const void *p) {
     return r;
 }
 
+// TMA bulk prefetch of a contiguous, 16-byte aligned span into L2 (no shared memory, no completion to wait on).
+__device__ __forceinline__ void prefetch_l2_bulk(const void *p, uint32_t bytes) {
+    asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(p), "r"(bytes) : "memory");
+}
+
 __device__ __forceinline__ uint32_t dp4a_u(uint32_t a, uint32_t b, uint32_t c) { return __dp4a(a, b, c); }
 
 __device__ __forceinline__ uint32_t dot16(const uint4 &a, const uint4 &b, uint32_t acc) {
@@ -153,33 +158,60 @@ __device__ __forceinline__ SideConst make_side(float mn, float mx, uint32_t s1, 
     return c;
 }
 
+// Per-row side of the identity, without the slow float64 divide / sqrt: only what score_fast needs.
+struct RowSide {
+    double A, R, sum;  // 255*min, max-min, sum of codes
+    double P;          // 255^2 * |y|^2
+    float Tf;          // sum of |terms| of P, rounded up
+    float magf;        // 255*(|min| + |max-min|), rounded up
+};
+
+__device__ __forceinline__ RowSide make_row_side(float mn, float mx, uint32_t s1, uint32_t s2, int D) {
+    RowSide c;
+    double a = (double)mn, ap = (double)mx;
+    c.A = 255.0 * a;
+    c.R = ap - a;
+    c.sum = (double)s1;
+    double p1 = (double)D * c.A * c.A;
+    double p2 = 2.0 * c.A * c.R * c.sum;
+    double p3 = c.R * c.R * (double)s2;
+    c.P = p1 + p2 + p3;
+    c.Tf = __double2float_ru(p1 + fabs(p2) + p3);
+    c.magf = __double2float_ru(255.0 * (fabs(a) + fabs(c.R)));
+    return c;
+}
+
 // Returns the float32 similarity; *flag = the float32 rounding (or the value) cannot be certified
 // to equal the reference's float32(dot) -- such rows are recomputed with literal arithmetic.
 // Error model (DESIGN.md "certified scores"): |ours - reference| <= delta with
 //   delta = 2u * ( 8*T/den + 8*Tx/Px + 8*Ty/Py            (our own roundings, cancellation-aware)
 //                + (2D+16)                                  (reference: sequential norm, divide, dot)
 //                + 8*sqrt(D)*(mag_x/|x| + mag_y/|y|) )      (reference: dequantization roundings)
-__device__ __forceinline__ float score_certified(const SideConst &x, const SideConst &y, uint32_t dot_qv, int D,
-                                                 double sqrtD, bool *flag) {
+// The score itself is N * rsqrt(Px*Py) in float64 (one rsqrt, no divide); the delta terms only need to be
+// upper bounds, so they are evaluated in float32 with directed rounding / a 1.001 inflation.  Overflow,
+// underflow or NaN anywhere makes delta non-finite or huge and the row is flagged: never mis-certified.
+__device__ __forceinline__ float score_fast(const SideConst &x, const RowSide &y, uint32_t dot_qv, int D, float sqrtDf,
+                                            bool *flag) {
     double t1 = (double)D * x.A * y.A;
     double t2 = x.A * y.R * y.sum;
     double t3 = y.A * x.R * x.sum;
     double t4 = x.R * y.R * (double)dot_qv;
     double N = (t1 + t2) + (t3 + t4);
-    double T = fabs(t1) + fabs(t2) + fabs(t3) + fabs(t4);
-    double fin = T + x.T + y.T;
-    if (!(fin < 1.0e300)) {  // NaN / Inf header: let the literal path decide
-        *flag = true;
-        return 2.0f;
+    float Tf = __double2float_ru(fabs(t1) + fabs(t2) + fabs(t3) + fabs(t4));
+    if (x.T == 0.0 || y.Tf == 0.0f) {  // an exactly-zero vector (header 0/0 or all terms 0): the reference leaves it
+        bool finite = (x.T == x.T) && (y.Tf == y.Tf) && (Tf == Tf) && Tf < 3.0e38f;  // unnormalized, dot = +0
+        *flag = !finite;
+        return finite ? 0.0f : 2.0f;
     }
-    if (x.T == 0.0 || y.T == 0.0) {  // an exactly-zero vector: reference leaves it unnormalized, dot = +0
-        *flag = false;
-        return 0.0f;
-    }
-    double den = x.sqrtP * y.sqrtP;
-    double c = N / den;
-    double delta = 2.0 * kU * (8.0 * (T / den) + x.tp + y.tp + (double)(2 * D + 16) + sqrtD * (x.mg + y.mg));
-    bool ok = (x.P > 0.0) && (y.P > 0.0) && (delta < 1.0e-6);
+    double pp = x.P * y.P;
+    double c = N * rsqrt(pp);
+    float ppf = __double2float_rd(pp);
+    float rden = rsqrtf(ppf);                                  // ~ 1/den
+    float ry = rsqrtf(__double2float_rd(y.P));                 // ~ 1/sqrt(Py)
+    float e = 8.0f * (Tf * rden) + (float)x.tp + 8.0f * (y.Tf * ry * ry) + (float)(2 * D + 16) +
+              sqrtDf * ((float)x.mg + 8.0f * (y.magf * ry));
+    double delta = (2.0 * 1.001 * kU) * (double)e;
+    bool ok = (x.P > 0.0) && (y.P > 0.0) && (delta < 1.0e-6);   // false for NaN / Inf as well
     float lo = __double2float_rn(c - delta);
     float hi = __double2float_rn(c + delta);
     if (!ok) {

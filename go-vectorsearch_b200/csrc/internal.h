@@ -21,6 +21,8 @@ struct vs_ctx {
     size_t pinned_cap = 0;
     bool owns_stream = true;
     unsigned long long *d_fix_counter = nullptr;  // in-kernel literal re-scores (device)
+    unsigned long long *d_trace = nullptr;        // phase stamps of the last list-scan launch (when enabled)
+    bool trace = false;
     // optional per-kernel timing of the list-scan stage
     bool profile = false;
     std::vector<cudaEvent_t> prof_events;  // pairs (start, stop), recycled
@@ -88,6 +90,7 @@ struct StageParams {
     uint32_t *out_qtiles;         // mode 1 (optional): [q] tiles the next stage will scan for this query
     const uint64_t *next_list_off;  // CSR of the store scanned by the next stage (for out_qtiles)
     uint32_t next_tile_rows;
+    unsigned long long *trace;    // optional [gridDim.x][8] globaltimer phase stamps (profiling aid)
     unsigned long long *fix_counter;  // device counter: candidates re-scored with literal arithmetic in-kernel
     uint32_t *out_status;         // [q], OR-ed with status_bit / need-more bit
     uint32_t status_bit;

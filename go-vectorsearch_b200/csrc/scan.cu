@@ -106,6 +106,27 @@ struct WarpTopK {
         }
     }
 
+    template <typename B>
+    __device__ __forceinline__ void store_soa(B &b, int base, int lane) const {
+#pragma unroll
+        for (int s = 0; s < KPL; s++) {
+            b.key[base + s * 32 + lane] = skey[s];
+            b.meta[base + s * 32 + lane] = meta[s];
+            b.id[base + s * 32 + lane] = id[s];
+        }
+    }
+    template <typename B>
+    __device__ __forceinline__ void load_soa(const B &b, int base, int lane) {
+#pragma unroll
+        for (int s = 0; s < KPL; s++) {
+            skey[s] = b.key[base + s * 32 + lane];
+            meta[s] = b.meta[base + s * 32 + lane];
+            id[s] = b.id[base + s * 32 + lane];
+        }
+        thr_key = __shfl_sync(0xFFFFFFFFu, skey[KPL - 1], 31);
+        thr_id = __shfl_sync(0xFFFFFFFFu, id[KPL - 1], 31);
+    }
+
     // Offer a stored list (32*KPL entries, sorted best-first) from shared memory.
     __device__ __forceinline__ void merge_from(const Cand *src, int lane) {
 #pragma unroll
@@ -169,6 +190,112 @@ __device__ __forceinline__ uint32_t tile_dots_generic(const uint8_t *__restrict_
 }
 
 // ---------------------------------------------------------------------------------------------------
+// Block-wide merge machinery.  Candidates live in shared memory as three arrays (key, meta, id).  A
+// warp-shuffle insertion costs ~100 cycles per candidate and a barrier-per-step bitonic sort ~400 cycles
+// per step, so ordering is done by RANK instead: every thread computes the final position of its own
+// candidate (binary searches against the other sorted lists, or a count over an unsorted set) and
+// scatters it -- no barriers inside, one at the end.
+constexpr int kSortCap = 1024;  // input candidates per merge (>= kStageWarps * 128)
+constexpr int kOutCap = 512;    // output / slot-head buffer
+
+struct CandBuf {
+    uint32_t *key;
+    uint32_t *meta;
+    uint64_t *id;
+};
+struct SortSmem {
+    uint64_t id_a[kSortCap];
+    uint64_t id_b[kOutCap];
+    uint32_t key_a[kSortCap];
+    uint32_t meta_a[kSortCap];
+    uint32_t key_b[kOutCap];
+    uint32_t meta_b[kOutCap];
+};
+
+__device__ __forceinline__ void cand_put(const CandBuf &b, int i, uint32_t k, uint32_t m, uint64_t id) {
+    b.key[i] = k;
+    b.meta[i] = m;
+    b.id[i] = id;
+}
+
+// e precedes f in the merged order; equal (key,id) pairs are ordered by (list, position) to keep ranks unique.
+__device__ __forceinline__ bool cand_before(uint32_t ek, uint64_t eid, int eorder, uint32_t fk, uint64_t fid, int forder) {
+    return ek > fk || (ek == fk && (eid < fid || (eid == fid && eorder < forder)));
+}
+
+// Merge nl sorted lists (list l occupies src[l*stride .. l*stride+len[l]) or, when len == nullptr, `stride`
+// entries each) into dst[0..outcap) best-first.  One thread per input entry; ends with a barrier.
+__device__ __forceinline__ void rank_merge(const CandBuf &src, int nl, int stride, const int *len, const CandBuf &dst,
+                                           int outcap) {
+    const int total = nl * stride;
+    for (int e = threadIdx.x; e < total; e += blockDim.x) {
+        const int l = e / stride, pos = e - l * stride;
+        const int mylen = len ? len[l] : stride;
+        if (pos >= mylen) continue;
+        const uint32_t k = src.key[e];
+        const uint64_t id = src.id[e];
+        int rank = pos;
+        for (int o = 0; o < nl && rank < outcap; o++) {
+            if (o == l) continue;
+            const int base = o * stride;
+            int lo = 0, hi = len ? len[o] : stride;
+            while (lo < hi) {  // number of entries of list o that precede (k,id,l)
+                const int mid = (lo + hi) >> 1;
+                if (cand_before(src.key[base + mid], src.id[base + mid], o, k, id, l)) lo = mid + 1;
+                else hi = mid;
+            }
+            rank += lo;
+        }
+        if (rank < outcap) cand_put(dst, rank, k, src.meta[e], id);
+    }
+    __syncthreads();
+}
+
+// Warp bitonic sort of 32 candidates held one per lane (registers + shuffles, no shared memory).
+__device__ __forceinline__ void warp_sort32(uint32_t &k, uint32_t &m, uint64_t &id, int lane) {
+#pragma unroll
+    for (int kk = 2; kk <= 32; kk <<= 1) {
+#pragma unroll
+        for (int j = kk >> 1; j > 0; j >>= 1) {
+            const uint32_t ok = __shfl_xor_sync(FULL, k, j);
+            const uint32_t om = __shfl_xor_sync(FULL, m, j);
+            const uint64_t oid = __shfl_xor_sync(FULL, id, j);
+            const bool up = (lane & kk) == 0;        // this run ends up best-first
+            const bool lower = (lane & j) == 0;      // I hold the lower index of the pair
+            const bool want_better = (up == lower);  // the better of the two belongs here
+            const bool other_better = cand_better(ok, oid, k, id);
+            if (other_better == want_better && !(ok == k && oid == id)) {
+                k = ok;
+                m = om;
+                id = oid;
+            }
+        }
+    }
+}
+
+// Order an unsorted set src[0..n) (n <= kOutCap, src has room for n rounded up to 32) into dst[0..outcap)
+// best-first: every warp sorts 32-entry chunks in registers, then the chunks are rank-merged.  Barriers inside.
+__device__ __forceinline__ void block_sort_small(const CandBuf &src, int n, const CandBuf &dst, int outcap) {
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarp = blockDim.x >> 5;
+    const int nch = (n + 31) >> 5;
+    for (int ch = warp; ch < nch; ch += nwarp) {
+        const int e = ch * 32 + lane;
+        uint32_t k = 0, m = 0;
+        uint64_t id = kEmptyId;
+        if (e < n) {
+            k = src.key[e];
+            m = src.meta[e];
+            id = src.id[e];
+        }
+        warp_sort32(k, m, id, lane);
+        cand_put(src, e, k, m, id);
+    }
+    for (int e = threadIdx.x; e < outcap; e += blockDim.x) cand_put(dst, e, 0u, 0u, kEmptyId);
+    __syncthreads();
+    rank_merge(src, nch, 32, nullptr, dst, outcap);
+}
+
+// ---------------------------------------------------------------------------------------------------
 struct StageShared {
     uint32_t tile_prefix[kMaxSeg + 1];
     uint64_t seg_start[kMaxSeg];
@@ -177,6 +304,9 @@ struct StageShared {
     double norm;
     unsigned int is_last;
     unsigned int need_fix;
+    unsigned int extra_count;
+    unsigned int overflow;
+    int warp_cnt[kStageWarps];
     uint32_t tail_key;
     uint64_t tail_id;
 };
@@ -187,6 +317,16 @@ struct StageShared {
 // tile t belongs to block floor(t*Gd/T).  A block walks the queries its range overlaps; per (query, block)
 // pair it leaves one partial top list in slot q+b (unique because q and b both only grow along the walk),
 // and the last block to finish a query merges that query's slots and emits.
+__device__ __forceinline__ unsigned long long globaltimer_ns() {
+    unsigned long long t;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+    return t;
+}
+#define VS_TRACE(slot)                                                                  \
+    do {                                                                                \
+        if (p.trace && threadIdx.x == 0) p.trace[(size_t)blockIdx.x * 16 + (slot)] = globaltimer_ns(); \
+    } while (0)
+
 __device__ __forceinline__ uint32_t block_of_tile(uint64_t t, uint64_t T, uint32_t Gd) { return (uint32_t)((t * Gd) / T); }
 __device__ __forceinline__ uint64_t first_tile_of_block(uint64_t b, uint64_t T, uint32_t Gd) { return (b * T + Gd - 1) / Gd; }
 
@@ -198,8 +338,10 @@ stage_kernel(const StageParams p) {
     constexpr int CAP = 32 * KPL;
     StageShared &sh = *reinterpret_cast<StageShared *>(smem_raw);
     size_t off = (sizeof(StageShared) + 15) & ~size_t(15);
-    Cand *sh_lists = reinterpret_cast<Cand *>(smem_raw + off);  // [kStageWarps][CAP]
-    off += (size_t)kStageWarps * CAP * sizeof(Cand);
+    SortSmem &ss = *reinterpret_cast<SortSmem *>(smem_raw + off);
+    off += (sizeof(SortSmem) + 15) & ~size_t(15);
+    const CandBuf bufA{ss.key_a, ss.meta_a, ss.id_a};  // kSortCap entries
+    const CandBuf bufB{ss.key_b, ss.meta_b, ss.id_b};  // kOutCap entries
     double *sh_qn = reinterpret_cast<double *>(smem_raw + off);  // [D] normalized query (fix path)
     off += (size_t)p.rows.d * sizeof(double);
     uint32_t *sh_qprefix = reinterpret_cast<uint32_t *>(smem_raw + off);  // [nq+1] when p.qtiles
@@ -208,7 +350,7 @@ stage_kernel(const StageParams p) {
 
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int D = p.rows.d, d_pad = p.rows.d_pad;
-    const double sqrtD = sqrt((double)D);
+    const float sqrtDf = __double2float_ru(sqrt((double)D));
     constexpr int GG = (G == 0) ? 32 : G;
     const int iters = (G == 0 || EXACT) ? 32 : p.iters;  // rows per lane group in a tile
     const int tile_rows = (G == 0 || EXACT) ? 32 : (32 / GG) * iters;
@@ -238,6 +380,7 @@ stage_kernel(const StageParams p) {
         T = (uint64_t)p.uniform_tiles * p.nq;
     }
     if (T == 0) return;
+    VS_TRACE(0);
     const uint32_t Gd = (uint64_t)gridDim.x < T ? gridDim.x : (uint32_t)T;  // never more blocks than tiles
     if (blockIdx.x >= Gd) return;
     uint64_t t0 = first_tile_of_block(blockIdx.x, T, Gd);
@@ -320,10 +463,11 @@ stage_kernel(const StageParams p) {
 
         WarpTopK<KPL> top;
         top.init();
+        VS_TRACE(1);
 
         // ---- main loop: this block's tiles of this query, round-robin over its warps ----
         const uint32_t tb_eff = tb < seg_tiles ? tb : seg_tiles;  // a query padded to 1 tile may have none
-        for (uint32_t t = ta + warp; t < tb_eff; t += kStageWarps) {
+        auto locate = [&](uint32_t t, size_t &row0, int &nrows) {
             int lo = 0, hi = nseg;  // segment with tile_prefix[seg] <= t < tile_prefix[seg+1]
             while (hi - lo > 1) {
                 int mid = (lo + hi) >> 1;
@@ -331,14 +475,26 @@ stage_kernel(const StageParams p) {
                 else hi = mid;
             }
             const uint32_t tin = t - sh.tile_prefix[lo];
-            const size_t row0 = sh.seg_start[lo] + (size_t)tin * tile_rows;
-            const int nrows = min((uint32_t)tile_rows, sh.seg_len[lo] - tin * tile_rows);
+            row0 = sh.seg_start[lo] + (size_t)tin * tile_rows;
+            nrows = min((uint32_t)tile_rows, sh.seg_len[lo] - tin * tile_rows);
+        };
+        size_t row0 = 0;
+        int nrows = 0;
+        if (ta + warp < tb_eff) locate(ta + warp, row0, nrows);
+        for (uint32_t t = ta + warp; t < tb_eff; t += kStageWarps) {
+            // locate this warp's next tile one iteration ahead (keeps the shared-memory search off the load path)
+            size_t next_row0 = 0;
+            int next_nrows = 0;
+            if (t + kStageWarps < tb_eff) {
+                locate(t + kStageWarps, next_row0, next_nrows);
+            }
             const int myr = (lane / GG) * iters + (lane % GG);  // tile row finished by this lane
             const bool valid = (lane % GG) < iters && myr < nrows;
             const size_t row = row0 + (valid ? myr : 0);
 
             float sim;
             bool flag = false;
+            uint64_t cid = kEmptyId;
             if constexpr (EXACT) {
                 sim = 0.0f;
                 if (valid) {
@@ -346,76 +502,174 @@ stage_kernel(const StageParams p) {
                     sim = ref_cosine_row(p.rows.codes + row * (size_t)d_pad, h.x, h.y, qn, D);
                 }
             } else {
+                // issue the per-row header / sums (and, while the list is still filling, id) loads ahead of the
+                // code stream so their latency overlaps it instead of following it
+                float2 h = valid ? p.rows.hdr[row] : make_float2(0.f, 0.f);
+                uint2 s = valid ? p.rows.sums[row] : make_uint2(0, 0);
+                if (top.thr_key == 0 && valid) cid = p.ids ? p.ids[row] : p.id_base + row;
                 uint32_t mydot;
                 if constexpr (G != 0) mydot = tile_dots<G, CPL>(p.rows.codes, row0, nrows, d_pad, qreg, lane, iters);
                 else mydot = tile_dots_generic(p.rows.codes, row0, nrows, d_pad, sh_q, lane);
-                float2 h = valid ? p.rows.hdr[row] : make_float2(0.f, 0.f);
-                uint2 s = valid ? p.rows.sums[row] : make_uint2(0, 0);
-                SideConst y = make_side(h.x, h.y, s.x, s.y, D);
-                sim = score_certified(xq, y, mydot, D, sqrtD, &flag);
+                RowSide y = make_row_side(h.x, h.y, s.x, s.y, D);
+                sim = score_fast(xq, y, mydot, D, sqrtDf, &flag);
             }
             uint32_t key = f32_to_key(sim);
             // lazy id: only rows that can still enter the list need their document id
             const bool cand = valid && key >= top.thr_key;
-            uint64_t cid = kEmptyId;
-            if (cand) cid = p.ids ? p.ids[row] : p.id_base + row;
+            if (cand && cid == kEmptyId) cid = p.ids ? p.ids[row] : p.id_base + row;
             top.offer(cand, key, (uint32_t)row | (flag ? kFlagBit : 0u), cid, lane);
+            row0 = next_row0;
+            nrows = next_nrows;
         }
 
-        // ---- block merge: all warps -> warp 0 -> partial slot (qslot + block) ----
-        top.store(sh_lists + (size_t)warp * CAP, lane);
-        __syncthreads();
+        // ---- block merge: every warp's (sorted) list -> shared memory -> rank merge -> partial slot (qslot + block) ----
+        {
+            int cnt = 0;
+#pragma unroll
+            for (int s2 = 0; s2 < KPL; s2++) cnt += __popc(__ballot_sync(FULL, top.skey[s2] != 0));
+            if (lane == 0) sh.warp_cnt[warp] = cnt;
+            top.store_soa(bufA, warp * CAP, lane);
+            for (int e = threadIdx.x; e < CAP; e += blockDim.x) cand_put(bufB, e, 0u, 0u, kEmptyId);
+            __syncthreads();
+            VS_TRACE(2);
+            rank_merge(bufA, kStageWarps, CAP, sh.warp_cnt, bufB, CAP);  // top CAP of the block -> bufB
+        }
+        VS_TRACE(8);
         const uint32_t blo = block_of_tile(P0, T, Gd), bhi = block_of_tile(P1 - 1, T, Gd);
-        if (warp == 0) {
-            for (int w = 1; w < kStageWarps; w++) top.merge_from(sh_lists + (size_t)w * CAP, lane);
-            top.store(p.partial + ((size_t)qslot + blockIdx.x) * CAP, lane);
-            __threadfence();
-            if (lane == 0) {
-                unsigned int tk = atomicAdd(&p.tickets[qslot], 1u);
-                sh.is_last = (tk == bhi - blo) ? 1u : 0u;
+        {
+            Cand *slot = p.partial + ((size_t)qslot + blockIdx.x) * CAP;
+            for (int e = threadIdx.x; e < CAP; e += blockDim.x) {
+                uint4 v;
+                v.x = bufB.key[e];
+                v.y = bufB.meta[e];
+                v.z = (uint32_t)bufB.id[e];
+                v.w = (uint32_t)(bufB.id[e] >> 32);
+                *reinterpret_cast<uint4 *>(slot + e) = v;
             }
         }
+        VS_TRACE(9);
+        __threadfence();
         __syncthreads();
+        VS_TRACE(10);
+        if (threadIdx.x == 0) {
+            unsigned int tk = atomicAdd(&p.tickets[qslot], 1u);
+            sh.is_last = (tk == bhi - blo) ? 1u : 0u;
+            sh.extra_count = 0;
+            sh.overflow = 0;
+        }
+        __syncthreads();
+        VS_TRACE(3);
         if (!sh.is_last) continue;
 
-        // ---- last block of this query: merge its slots (loads batched 4 deep), fix, emit ----
+        // ---- last block of this query: merge its slots, fix, emit.  The final list ends up in bufB[0..CAP). ----
         __threadfence();
-        top.init();
         {
             const Cand *base = p.partial + ((size_t)qslot + blo) * CAP;
             const int nslots = (int)(bhi - blo + 1);
-            for (int s0 = warp; s0 < nslots; s0 += kStageWarps * 4) {
-                uint4 v[4];
-#pragma unroll
-                for (int u = 0; u < 4; u++) {
-                    int s = s0 + u * kStageWarps;
-                    v[u] = s < nslots ? __ldcg(reinterpret_cast<const uint4 *>(base + (size_t)s * CAP + lane))
-                                      : make_uint4(0, 0, 0, 0);
+            auto ld_cand = [&](int slot, int rank, uint32_t &k, uint32_t &m, uint64_t &id) {
+                uint4 v = __ldcg(reinterpret_cast<const uint4 *>(base + (size_t)slot * CAP + rank));
+                k = v.x;
+                m = v.y;
+                id = (uint64_t)v.z | ((uint64_t)v.w << 32);
+            };
+            if (nslots == 1) {
+                // the block's own sorted list is still in bufB[0..CAP)
+            } else if (nslots * CAP <= kSortCap) {
+                // few slots: merge them all by rank
+                for (int e = threadIdx.x; e < nslots * CAP; e += blockDim.x) {
+                    uint32_t k, m;
+                    uint64_t id;
+                    ld_cand(e / CAP, e % CAP, k, m, id);
+                    cand_put(bufA, e, k, m, id);
                 }
+                for (int e = threadIdx.x; e < CAP; e += blockDim.x) cand_put(bufB, e, 0u, 0u, kEmptyId);
+                __syncthreads();
+                rank_merge(bufA, nslots, CAP, nullptr, bufB, CAP);
+            } else {
+                // many slots: the CAP-th best of the slot heads bounds the CAP-th best overall from below, so only
+                // entries at least that good can matter; each slot is sorted, so they form a prefix of it.
+                const int mh = (CAP + nslots - 1) / nslots;  // heads per slot so that at least CAP are gathered
+                const int ng = nslots * mh;
+                bool slow = ng > 2 * (int)blockDim.x;
+                if (!slow) {
+                    // each thread holds up to two gathered heads
+                    uint32_t hk[2] = {0u, 0u}, hm[2] = {0u, 0u};
+                    uint64_t hid[2] = {kEmptyId, kEmptyId};
 #pragma unroll
-                for (int u = 0; u < 4; u++) {
-                    int s = s0 + u * kStageWarps;
-                    if (s >= nslots) break;
-                    uint64_t id = (uint64_t)v[u].z | ((uint64_t)v[u].w << 32);
-                    top.offer(v[u].x != 0, v[u].x, v[u].y, id, lane);
-                    if (KPL > 1) {  // deeper chunks only matter if the first chunk's last entry made it
-                        for (int c = 1; c < KPL; c++) {
-                            uint4 w = __ldcg(reinterpret_cast<const uint4 *>(base + (size_t)s * CAP + c * 32 + lane));
-                            uint64_t wid = (uint64_t)w.z | ((uint64_t)w.w << 32);
-                            bool any = __any_sync(FULL, w.x != 0 && cand_better(w.x, wid, top.thr_key, top.thr_id));
-                            if (!any) break;
-                            top.offer(w.x != 0, w.x, w.y, wid, lane);
+                    for (int u = 0; u < 2; u++) {
+                        const int e = threadIdx.x + u * blockDim.x;
+                        if (e < ng) ld_cand(e / mh, e % mh, hk[u], hm[u], hid[u]);
+                    }
+                    VS_TRACE(11);
+                    // exact CAP-th largest key among the heads, built bit by bit from block-wide counts
+                    uint32_t tkey = 0;
+                    for (int bit = 31; bit >= 0; bit--) {
+                        const uint32_t cand_t = tkey | (1u << bit);
+                        int c = __syncthreads_count(hk[0] >= cand_t);
+                        if (ng > (int)blockDim.x) c += __syncthreads_count(hk[1] >= cand_t);
+                        if (c >= CAP) tkey = cand_t;
+                    }
+                    VS_TRACE(12);
+                    // keep every entry whose key reaches the threshold: gathered heads first, then what the slots
+                    // hold below their last gathered head (each slot is sorted, so these form a prefix)
+#pragma unroll
+                    for (int u = 0; u < 2; u++) {
+                        const int e = threadIdx.x + u * blockDim.x;
+                        if (e >= ng || hk[u] == 0 || hk[u] < tkey) continue;
+                        unsigned int pos = atomicAdd(&sh.extra_count, 1u);
+                        if (pos >= (unsigned)kOutCap) {
+                            sh.overflow = 1;
+                            continue;
+                        }
+                        cand_put(bufA, (int)pos, hk[u], hm[u], hid[u]);
+                        if ((e % mh) == mh - 1) {  // last gathered head of its slot still qualifies: walk on
+                            const int sidx = e / mh;
+                            for (int r = mh; r < CAP; r++) {
+                                uint32_t k, m;
+                                uint64_t id;
+                                ld_cand(sidx, r, k, m, id);
+                                if (k == 0 || k < tkey) break;
+                                pos = atomicAdd(&sh.extra_count, 1u);
+                                if (pos >= (unsigned)kOutCap) {
+                                    sh.overflow = 1;
+                                    break;
+                                }
+                                cand_put(bufA, (int)pos, k, m, id);
+                            }
                         }
                     }
+                    __syncthreads();
+                    VS_TRACE(13);
+                    slow = sh.overflow != 0;
+                    if (!slow) block_sort_small(bufA, (int)sh.extra_count, bufB, CAP);  // final list -> bufB[0..CAP)
+                }
+                if (slow) {
+                    // degenerate (massive ties or an unusually wide grid): warp 0 inserts every slot in turn
+                    __syncthreads();
+                    if (warp == 0) {
+                        top.init();
+                        for (int sidx = 0; sidx < nslots; sidx++) {
+                            for (int c = 0; c < KPL; c++) {
+                                uint32_t k, m;
+                                uint64_t id;
+                                ld_cand(sidx, c * 32 + lane, k, m, id);
+                                bool any = __any_sync(FULL, k != 0 && cand_better(k, id, top.thr_key, top.thr_id));
+                                if (!any) break;
+                                top.offer(k != 0, k, m, id, lane);
+                            }
+                        }
+                        top.store_soa(bufB, 0, lane);
+                    }
+                    __syncthreads();
                 }
             }
         }
-        top.store(sh_lists + (size_t)warp * CAP, lane);
-        __syncthreads();
+        VS_TRACE(4);
         if (warp == 0) {
-            for (int w = 1; w < kStageWarps; w++) top.merge_from(sh_lists + (size_t)w * CAP, lane);
+            top.load_soa(bufB, 0, lane);
             if (lane == 0) p.tickets[qslot] = 0;  // re-arm for the next launch
         }
+        VS_TRACE(5);
 
         // Emit; first (non-EXACT) re-score flagged candidates inside the emit window with literal arithmetic.
         uint32_t status = 0;
@@ -462,7 +716,7 @@ stage_kernel(const StageParams p) {
                 const bool full = top.thr_key != 0;
                 if (pass == 0 && anyflag && !EXACT) {
                     need_fix = true;
-                    top.store(sh_lists, lane);
+                    top.store_soa(bufA, 0, lane);
                     if (lane == 0) {
                         sh.tail_key = top.thr_key;
                         sh.tail_id = top.thr_id;
@@ -511,6 +765,7 @@ stage_kernel(const StageParams p) {
                 if (lane == 0) sh.need_fix = need_fix ? 1u : 0u;
             }
             __syncthreads();
+            VS_TRACE(6 + (pass ? 1 : 0));
             if (!sh.need_fix) break;
             // normalizeVector of the query (compute/cosine.go:26,138-149), literal: parallel dequantize,
             // one thread sums the squares in order, parallel divide.
@@ -531,25 +786,17 @@ stage_kernel(const StageParams p) {
                     for (int i = threadIdx.x; i < D; i += blockDim.x) sh_qn[i] = __ddiv_rn(sh_qn[i], norm);
                 __syncthreads();
                 for (int e = threadIdx.x; e < CAP; e += blockDim.x) {
-                    Cand c = sh_lists[e];
-                    if (c.skey != 0 && (c.meta & kFlagBit)) {
-                        const size_t row = c.meta & ~kFlagBit;
+                    if (bufA.key[e] != 0 && (bufA.meta[e] & kFlagBit)) {
+                        const size_t row = bufA.meta[e] & ~kFlagBit;
                         const float2 h = p.rows.hdr[row];
-                        c.skey = f32_to_key(ref_cosine_row(p.rows.codes + row * (size_t)d_pad, h.x, h.y, sh_qn, D));
-                        c.meta &= ~kFlagBit;
-                        sh_lists[e] = c;
+                        bufA.key[e] = f32_to_key(ref_cosine_row(p.rows.codes + row * (size_t)d_pad, h.x, h.y, sh_qn, D));
+                        bufA.meta[e] &= ~kFlagBit;
                         if (p.fix_counter) atomicAdd(p.fix_counter, 1ull);
                     }
                 }
                 __syncthreads();
-                if (warp == 0) {  // re-sort: entries only moved down by at most one float32 step
-                    top.init();
-#pragma unroll
-                    for (int s = 0; s < KPL; s++) {
-                        Cand c = sh_lists[s * 32 + lane];
-                        top.offer(c.skey != 0, c.skey, c.meta, c.id, lane);
-                    }
-                }
+                block_sort_small(bufA, CAP, bufB, CAP);  // entries only moved down by at most one float32 step
+                if (warp == 0) top.load_soa(bufB, 0, lane);
             }
         }
     }
@@ -560,7 +807,7 @@ int stage_cap(int kpl) { return 32 * kpl; }
 
 template <int G, int CPL, int KPL, bool EXACT>
 static cudaError_t launch_stage_t(const StageParams &p, int grid_blocks, cudaStream_t st) {
-    size_t smem = ((sizeof(StageShared) + 15) & ~size_t(15)) + (size_t)kStageWarps * 32 * KPL * sizeof(Cand) +
+    size_t smem = ((sizeof(StageShared) + 15) & ~size_t(15)) + ((sizeof(SortSmem) + 15) & ~size_t(15)) +
                   (size_t)p.rows.d * sizeof(double);
     if (p.qtiles) smem += (((size_t)p.nq + 1) * 4 + 15) & ~size_t(15);
     if (G == 0) smem += (size_t)p.rows.d_pad;
@@ -661,7 +908,7 @@ cosine_1xN_kernel(MatView rows, MatView query, float *sims, uint32_t *dots, uint
     }
     __syncthreads();
     const SideConst xq = s_q;
-    const double sqrtD = sqrt((double)D);
+    const float sqrtDf = __double2float_ru(sqrt((double)D));
     uint4 qreg[CPL > 0 ? CPL : 1];
     if constexpr (G != 0) {
 #pragma unroll
@@ -681,9 +928,9 @@ cosine_1xN_kernel(MatView rows, MatView query, float *sims, uint32_t *dots, uint
             if (sims) {
                 float2 h = rows.hdr[row];
                 uint2 s = rows.sums[row];
-                SideConst y = make_side(h.x, h.y, s.x, s.y, D);
+                RowSide y = make_row_side(h.x, h.y, s.x, s.y, D);
                 bool flag;
-                float sim = score_certified(xq, y, mydot, D, sqrtD, &flag);
+                float sim = score_fast(xq, y, mydot, D, sqrtDf, &flag);
                 sims[row] = sim;
                 if (flag) worklist[atomicAdd(work_count, 1u)] = (uint32_t)row;
             }

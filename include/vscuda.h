@@ -67,6 +67,13 @@ VS_API int vs_ctx_timer_stop(vs_ctx *ctx, float *ms_out);
  * number of launches since the last read (synchronizes). */
 VS_API int vs_ctx_profile_enable(vs_ctx *ctx, int on);
 VS_API int vs_ctx_profile_read(vs_ctx *ctx, double *scan_ms_out, uint64_t *scan_launches_out);
+/* Phase trace (profiling aid): when enabled, thread 0 of every block of each search stage stamps
+ * %globaltimer (ns) into 16 slots: 0 start, 1 prologue done, 2 scan done, 8 block list sorted, 9 written,
+ * 10 fenced, 3 ticket taken; last block of a query: 11 slot heads gathered, 12 sorted, 13 slots walked,
+ * 4 merged, 5 final list, 6/7 emitted.  stage = 1 (probe) or 2 (list scan); out = blocks*16 values of the
+ * most recent launch of that stage. */
+VS_API int vs_ctx_trace_enable(vs_ctx *ctx, int on);
+VS_API int vs_ctx_trace_read(vs_ctx *ctx, int stage, uint64_t *out, size_t max_blocks, size_t *blocks_out);
 
 /* ---- compute/quantization.go ------------------------------------------------------- */
 /* QuantizeMatrixFloat32 (quantization.go:142-148) / QuantizeVectorFloat32 (:82-91; n=1).
