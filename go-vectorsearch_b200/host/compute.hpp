@@ -1,0 +1,181 @@
+// compute.hpp -- C++ host-side mirror of the reference's Go `compute` package over the C ABI (include/vscuda.h).
+//
+// The reference is compiled code (Go) whose toolchain is absent from the build image, so the host side
+// above the C ABI is written in C++ with the same names, argument meaning and error behaviour:
+//   compute/types.go:3-11       Vector, Matrix { Clone, MatrixCosineSimilarity }
+//   compute/compute.go:10-44    NewVector, NewMatrix          (Go panic -> compute::Panic)
+//   compute/cosine.go:60-66     VectorMatrixCosineSimilarity() -> {calculate, done}
+//   compute/cosine.go:129-135   MatrixCosineSimilarity()       -> {calculate, done}
+//   compute/quantization.go     Quantize{Vector,Matrix}Float{32,64}, Dequantize...
+// logger.Sugar().Fatalf (process exit in Go, cosine.go:19-21,77-79) surfaces as compute::Fatal.
+// The Go shim a maintainer adds is goshim/*.go; this header is what the C++ self-test and any C++ caller use.
+#pragma once
+#include <cstdint>
+#include <cstdlib>
+#include <functional>
+#include <memory>
+#include <stdexcept>
+#include <string>
+#include <utility>
+#include <vector>
+
+#include "../../include/vscuda.h"
+
+namespace compute {
+
+struct Panic : std::runtime_error { using std::runtime_error::runtime_error; };   // Go panic()
+struct Fatal : std::runtime_error { using std::runtime_error::runtime_error; };   // logger Fatalf
+struct Error : std::runtime_error { using std::runtime_error::runtime_error; };   // any other backend failure
+
+inline void check(int rc) {
+    if (rc == VS_OK) return;
+    std::string msg = vs_last_error();
+    if (rc == VS_EEMPTY) throw Panic(msg);
+    if (rc == VS_EDIM) throw Fatal(msg);
+    throw Error("libvscuda error " + std::to_string(rc) + ": " + msg);
+}
+
+inline void Init() {
+    static bool done = false;
+    if (done) return;
+    const char *lr = std::getenv("LOCAL_RANK");
+    check(vs_init(lr ? std::atoi(lr) : 0));  // no CPU fallback: throws without a B200
+    done = true;
+}
+
+// One CUDA stream + scratch arena; what a calculate-closure owns.
+class Context {
+  public:
+    Context() { Init(); check(vs_ctx_create(&h_)); }
+    ~Context() { Close(); }
+    Context(const Context &) = delete;
+    Context &operator=(const Context &) = delete;
+    void Close() { if (h_) { vs_ctx_destroy(h_); h_ = nullptr; } }
+    vs_ctx *handle() const { if (!h_) throw Error("context released (done() was called)"); return h_; }
+  private:
+    vs_ctx *h_ = nullptr;
+};
+
+inline Context &DefaultContext() { static Context c; return c; }
+
+using Row = std::vector<uint8_t>;
+using Rows = std::vector<Row>;
+
+inline std::vector<uint8_t> Pack(const Rows &rows) {
+    if (rows.empty()) throw Panic("matrix rows are empty");                      // compute.go:25-27
+    const size_t rb = rows[0].size();
+    if (rb <= 8) throw Panic("matrix columns are empty");                        // compute.go:29-31
+    std::vector<uint8_t> buf(rows.size() * rb);
+    for (size_t i = 0; i < rows.size(); i++) {
+        if (rows[i].size() != rb) throw Panic("matrix rows have different lengths");
+        std::copy(rows[i].begin(), rows[i].end(), buf.begin() + i * rb);
+    }
+    return buf;
+}
+
+class Matrix;
+class Vector {
+  public:
+    explicit Vector(Row row) : row_(std::make_shared<Row>(std::move(row))) {}
+    Vector Clone() const { return *this; }                                       // immutable: nothing to copy
+    std::vector<float> MatrixCosineSimilarity(const Matrix &m, Context *ctx = nullptr) const;  // cosine.go:13-57
+    const Row &row() const { return *row_; }
+  private:
+    std::shared_ptr<Row> row_;
+};
+
+class Matrix {
+  public:
+    explicit Matrix(vs_matrix *h) : h_(h, [](vs_matrix *p) { vs_matrix_release(p); }) {}
+    Matrix Clone() const { return *this; }                                       // reference-count bump
+    size_t rows() const { return vs_matrix_rows(h_.get()); }
+    size_t cols() const { return vs_matrix_cols(h_.get()); }
+    vs_matrix *handle() const { return h_.get(); }
+    // receiver = centroids, argument = data (cosine.go:70-125) -> {sims, nearestIndexList}
+    std::pair<std::vector<float>, std::vector<int64_t>> MatrixCosineSimilarity(const Matrix &data, Context *ctx = nullptr) const {
+        Context &c = ctx ? *ctx : DefaultContext();
+        std::vector<float> sims(data.rows());
+        std::vector<int64_t> idx(data.rows());
+        check(vs_argmax_MxN(c.handle(), h_.get(), data.h_.get(), sims.data(), idx.data()));
+        return {std::move(sims), std::move(idx)};
+    }
+  private:
+    std::shared_ptr<vs_matrix> h_;
+};
+
+inline std::vector<float> Vector::MatrixCosineSimilarity(const Matrix &m, Context *ctx) const {
+    Context &c = ctx ? *ctx : DefaultContext();
+    std::vector<float> sims(m.rows());
+    check(vs_cosine_1xN(c.handle(), row_->data(), row_->size(), m.handle(), sims.data()));
+    return sims;
+}
+
+inline Vector NewVector(const Row &vectorQuantized) {                             // compute.go:10-21
+    if (vectorQuantized.size() <= 8) throw Panic("vector columns are empty");
+    Init();
+    return Vector(vectorQuantized);
+}
+
+inline Matrix NewMatrix(const Rows &matrixQuantized) {                            // compute.go:23-44
+    std::vector<uint8_t> buf = Pack(matrixQuantized);
+    vs_matrix *h = nullptr;
+    check(vs_matrix_create(DefaultContext().handle(), buf.data(), matrixQuantized.size(), matrixQuantized[0].size(), &h));
+    return Matrix(h);
+}
+
+struct VectorMatrixClosure {
+    std::function<std::vector<float>(const Vector &, const Matrix &)> calculate;
+    std::function<void()> done;
+};
+inline VectorMatrixClosure VectorMatrixCosineSimilarity() {                       // cosine.go:60-66
+    auto ctx = std::make_shared<Context>();
+    return {[ctx](const Vector &v, const Matrix &m) { return v.MatrixCosineSimilarity(m, ctx.get()); },
+            [ctx]() { ctx->Close(); }};
+}
+struct MatrixMatrixClosure {
+    std::function<std::pair<std::vector<float>, std::vector<int64_t>>(const Matrix &, const Matrix &)> calculate;
+    std::function<void()> done;
+};
+inline MatrixMatrixClosure MatrixCosineSimilarity() {                             // cosine.go:129-135
+    auto ctx = std::make_shared<Context>();
+    return {[ctx](const Matrix &a, const Matrix &b) { return a.MatrixCosineSimilarity(b, ctx.get()); },
+            [ctx]() { ctx->Close(); }};
+}
+
+// ---- compute/quantization.go ----
+inline Rows QuantizeMatrixFloat32(const std::vector<std::vector<float>> &matrix) {  // :142-148
+    Rows out(matrix.size());
+    if (matrix.empty()) return out;
+    const size_t d = matrix[0].size();
+    std::vector<float> in(matrix.size() * d);
+    for (size_t i = 0; i < matrix.size(); i++) std::copy(matrix[i].begin(), matrix[i].end(), in.begin() + i * d);
+    std::vector<uint8_t> buf(matrix.size() * (8 + d));
+    check(vs_quantize_f32(DefaultContext().handle(), in.data(), matrix.size(), d, buf.data()));
+    for (size_t i = 0; i < matrix.size(); i++) out[i].assign(buf.begin() + i * (8 + d), buf.begin() + (i + 1) * (8 + d));
+    return out;
+}
+inline Row QuantizeVectorFloat32(const std::vector<float> &v) { return QuantizeMatrixFloat32({v})[0]; }  // :82-91
+inline Rows QuantizeMatrixFloat64(const std::vector<std::vector<double>> &matrix) {  // :150-156
+    Rows out(matrix.size());
+    if (matrix.empty()) return out;
+    const size_t d = matrix[0].size();
+    std::vector<double> in(matrix.size() * d);
+    for (size_t i = 0; i < matrix.size(); i++) std::copy(matrix[i].begin(), matrix[i].end(), in.begin() + i * d);
+    std::vector<uint8_t> buf(matrix.size() * (8 + d));
+    check(vs_quantize_f64(DefaultContext().handle(), in.data(), matrix.size(), d, buf.data()));
+    for (size_t i = 0; i < matrix.size(); i++) out[i].assign(buf.begin() + i * (8 + d), buf.begin() + (i + 1) * (8 + d));
+    return out;
+}
+inline Row QuantizeVectorFloat64(const std::vector<double> &v) { return QuantizeMatrixFloat64({v})[0]; }  // :93-102
+inline std::vector<float> DequantizeVectorFloat32(const Row &row) {               // :114-122
+    std::vector<float> out(row.size() - 8);
+    check(vs_dequantize_f32(DefaultContext().handle(), row.data(), 1, row.size(), out.data()));
+    return out;
+}
+inline std::vector<double> DequantizeVectorFloat64(const Row &row) {              // :124-132
+    std::vector<double> out(row.size() - 8);
+    check(vs_dequantize_f64(DefaultContext().handle(), row.data(), 1, row.size(), out.data()));
+    return out;
+}
+
+}  // namespace compute

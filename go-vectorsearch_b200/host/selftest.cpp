@@ -1,0 +1,70 @@
+// selftest.cpp -- exercises the C ABI through the C++ mirror of the reference's compute package with the
+// hand-derived known answers of tests/golden/kat.json (written out here so the binary is self-contained).
+// Exit code 0 = all checks passed. Needs a B200 (no CPU fallback): tests/test_gpu_host_cpp.py runs it.
+#include <cmath>
+#include <cstdio>
+#include <cstring>
+
+#include "compute.hpp"
+
+static int fails = 0;
+#define EXPECT(cond, what)                                   \
+    do {                                                     \
+        if (!(cond)) { std::printf("FAIL: %s\n", what); fails++; } \
+    } while (0)
+
+static compute::Row row(float mn, float mx, std::initializer_list<int> codes) {
+    compute::Row r(8);
+    std::memcpy(r.data(), &mn, 4);
+    std::memcpy(r.data() + 4, &mx, 4);
+    for (int c : codes) r.push_back((uint8_t)c);
+    return r;
+}
+
+int main() {
+    using namespace compute;
+    try {
+        // quantization.go:82-91 -- range seeded at 0, truncation
+        EXPECT(QuantizeVectorFloat32({0.5f, 1.0f, 0.25f}) == row(0.f, 1.f, {127, 255, 63}), "quantize positive_keeps_min_zero");
+        EXPECT(QuantizeVectorFloat32({-1.f, 0.f, 1.f}) == row(-1.f, 1.f, {0, 127, 255}), "quantize symmetric");
+        EXPECT(QuantizeVectorFloat32({0.f, 0.f, 0.f}) == row(0.f, 0.f, {0, 0, 0}), "quantize all_zero (NaN -> 0)");
+        EXPECT(QuantizeVectorFloat32({0.f, 1.f, 0.999f}) == row(0.f, 1.f, {0, 255, 254}), "quantize truncation");
+        EXPECT(QuantizeVectorFloat64({0.1, -0.3}) == row(-0.3f, 0.1f, {255, 0}), "quantize f64 header rounding");
+        // quantization.go:124-132
+        auto dq = DequantizeVectorFloat64(row(-1.f, 1.f, {0, 255, 51}));
+        EXPECT(dq[0] == -1.0 && dq[1] == 1.0 && dq[2] == -1.0 + (51.0 / 255.0) * 2.0, "dequantize f64");
+        // cosine.go:13-57
+        Vector q = NewVector(row(0.f, 1.f, {255, 0}));
+        Matrix m = NewMatrix({row(0.f, 1.f, {0, 255}), row(0.f, 1.f, {255, 255}), row(0.f, 1.f, {255, 0}), row(0.f, 0.f, {7, 9}),
+                              row(-1.f, 0.f, {0, 255})});
+        auto sims = q.Clone().MatrixCosineSimilarity(m);
+        const float s1 = (float)(1.0 / std::sqrt(2.0));
+        EXPECT(sims[0] == 0.f && sims[1] == s1 && sims[2] == 1.f && sims[3] == 0.f && sims[4] == -1.f, "cosine 1xN known answers");
+        auto cl = VectorMatrixCosineSimilarity();
+        EXPECT(cl.calculate(q.Clone(), m.Clone()) == sims, "closure calculate == method");
+        cl.done();
+        // cosine.go:70-125 -- strict '>' keeps the lowest index
+        Matrix cent = NewMatrix({row(0.f, 1.f, {255, 0}), row(0.f, 1.f, {0, 255}), row(0.f, 1.f, {255, 0})});
+        Matrix data = NewMatrix({row(0.f, 1.f, {255, 0}), row(0.f, 1.f, {0, 255}), row(0.f, 0.f, {0, 0}), row(0.f, 1.f, {255, 255}),
+                                 row(-1.f, 0.f, {0, 255})});
+        auto mm = MatrixCosineSimilarity();
+        auto res = mm.calculate(cent.Clone(), data.Clone());
+        mm.done();
+        EXPECT((res.second == std::vector<int64_t>{0, 1, 0, 0, 1}), "argmax known answers");
+        // error behaviour
+        bool panicked = false;
+        try { NewVector(compute::Row(8, 0)); } catch (const Panic &) { panicked = true; }
+        EXPECT(panicked, "NewVector panics on empty columns (compute.go:12-14)");
+        panicked = false;
+        try { NewMatrix({}); } catch (const Panic &) { panicked = true; }
+        EXPECT(panicked, "NewMatrix panics on empty rows (compute.go:25-27)");
+        bool fatal = false;
+        try { NewVector(row(0.f, 1.f, {1, 2, 3})).MatrixCosineSimilarity(m); } catch (const Fatal &) { fatal = true; }
+        EXPECT(fatal, "dimension mismatch is fatal (cosine.go:19-21)");
+    } catch (const std::exception &e) {
+        std::printf("FAIL: exception %s\n", e.what());
+        fails++;
+    }
+    std::printf(fails ? "selftest: %d FAILED\n" : "selftest: ok\n", fails);
+    return fails ? 1 : 0;
+}

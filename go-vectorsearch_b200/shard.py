@@ -22,12 +22,14 @@ def gather_hits(ids, sims, counts, group=None):
     import torch
     import torch.distributed as dist
     world = dist.get_world_size(group)
-    g_ids = torch.empty((world,) + tuple(ids.shape), dtype=ids.dtype, device=ids.device)
-    g_sims = torch.empty((world,) + tuple(sims.shape), dtype=sims.dtype, device=sims.device)
-    g_counts = torch.empty((world,) + tuple(counts.shape), dtype=counts.dtype, device=counts.device)
-    dist.all_gather_into_tensor(g_ids, ids.contiguous(), group=group)
-    dist.all_gather_into_tensor(g_sims, sims.contiguous(), group=group)
-    dist.all_gather_into_tensor(g_counts, counts.contiguous(), group=group)
+
+    def gather(t):
+        t = t.contiguous()
+        out = torch.empty((world * t.shape[0],) + tuple(t.shape[1:]), dtype=t.dtype, device=t.device)  # rank-major concat
+        dist.all_gather_into_tensor(out, t, group=group)
+        return out.view((world,) + tuple(t.shape))
+
+    g_ids, g_sims, g_counts = gather(ids), gather(sims), gather(counts)
     return g_ids, g_sims, g_counts
 
 

@@ -156,3 +156,40 @@ def test_full_size_properties(vs):
     ix = vs.ivf.Index.build_assigned(rows, None, lists, rows[:C])
     ids3, sims3, _ = ix.Search(q, C, 10)
     assert (ids3 == ids).all() and (f32_bits(sims3) == f32_bits(sims)).all()
+
+
+@pytest.mark.parametrize("G", [2, 4])
+def test_striped_shards_merge_matches_full(vs, oracle, G):
+    """Multi-GPU path emulated on one GPU: G row-striped shard indexes, shard-local top-k, device merge
+    (vs_topk_merge_dev) == the oracle's search over the whole store (the ranks of an N-GPU run do exactly this,
+    with an NCCL all-gather between the two steps)."""
+    import torch
+    n, d, C, nprobe, k, nq = 20000, 768, 40, 6, 10, 7
+    rows, cent, lists, doc = _index_inputs(oracle, n, d, C, 71, docs_per=2)
+    qs = oracle.quantize_matrix_f32(unit_rows(nq, d, 72))
+    dev = torch.device("cuda", 0)
+    g_ids = torch.zeros((G, nq, k), dtype=torch.int64, device=dev)
+    g_sims = torch.zeros((G, nq, k), dtype=torch.float32, device=dev)
+    g_counts = torch.zeros((G, nq), dtype=torch.int32, device=dev)
+    for r in range(G):
+        mine = vs.shard.stripe(n, r, G)
+        ix = vs.ivf.Index.build_assigned(rows[mine], doc[mine], lists[mine], cent)
+        ids, sims, counts = ix.Search(qs, nprobe, k)
+        g_ids[r] = torch.from_numpy(ids.view(np.int64)).to(dev)
+        g_sims[r] = torch.from_numpy(sims).to(dev)
+        g_counts[r] = torch.from_numpy(counts).to(dev)
+    out_ids = torch.zeros((nq, k), dtype=torch.int64, device=dev)
+    out_sims = torch.zeros((nq, k), dtype=torch.float32, device=dev)
+    out_counts = torch.zeros(nq, dtype=torch.int32, device=dev)
+    torch.cuda.synchronize()
+    ctx = vs.compute.default_context()
+    vs.shard.merge_hits_dev(g_ids, g_sims, g_counts, k, out_ids, out_sims, out_counts, ctx=ctx)
+    ctx.sync()
+    ids = out_ids.cpu().numpy().view(np.uint64)
+    sims = out_sims.cpu().numpy()
+    counts = out_counts.cpu().numpy()
+    for i in range(nq):
+        wi, ws = oracle.search(qs[i], cent, rows, lists, doc, nprobe, k)
+        assert counts[i] == len(wi)
+        assert ids[i, :counts[i]].tolist() == wi.tolist()
+        assert (f32_bits(sims[i, :counts[i]]) == f32_bits(ws)).all()

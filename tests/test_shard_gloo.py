@@ -1,0 +1,112 @@
+"""CPU, world_size 2 over gloo: the multi-GPU plumbing of the row-striped index (go-vectorsearch_b200/shard.py).
+
+Each rank owns the rows `rank, rank+world, ...` of every posting list, answers the query on its shard,
+all-gathers the shard-local top-k and merges.  On the GPU box the local search and the merge are libvscuda
+kernels; here the oracle stands in for the local search so that the host logic (striping covers every row
+exactly once, gather layout, merge order and dedup rule) is checked without a GPU.
+"""
+import os
+import socket
+import sys
+
+import numpy as np
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+sys.path.insert(0, os.path.dirname(os.path.abspath(__file__)))
+
+
+def _free_port():
+    s = socket.socket()
+    s.bind(("127.0.0.1", 0))
+    p = s.getsockname()[1]
+    s.close()
+    return p
+
+
+def _merge_np(g_ids, g_sims, g_counts, k):
+    """Reference merge: similarity desc (float32), id asc, one hit per id."""
+    out = []
+    for q in range(g_ids.shape[1]):
+        cand = []
+        for g in range(g_ids.shape[0]):
+            for j in range(int(g_counts[g, q])):
+                cand.append((-float(g_sims[g, q, j]), int(g_ids[g, q, j])))
+        cand.sort()
+        seen, hits = set(), []
+        for negs, i in cand:
+            if i not in seen:
+                seen.add(i)
+                hits.append((i, np.float32(-negs)))
+            if len(hits) == k:
+                break
+        out.append(hits)
+    return out
+
+
+def _worker(rank, world, port, q):
+    try:
+        os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world))
+        import torch
+        import torch.distributed as dist
+        import oracle
+        from conftest import load_pkg
+        from _util import unit_rows
+        pkg = load_pkg()
+        dist.init_process_group("gloo", rank=rank, world_size=world)
+        n, d, C, nprobe, k, nq = 3000, 64, 12, 4, 10, 5
+        rows = oracle.quantize_matrix_f32(unit_rows(n, d, 1))
+        cent = oracle.quantize_matrix_f32(unit_rows(C, d, 2))
+        _, lists = oracle.argmax_MxN(cent, rows)
+        lists = lists.astype(np.uint32)
+        doc = (np.arange(n) // 2).astype(np.uint64)           # two embeddings per document, split across ranks
+        qs = oracle.quantize_matrix_f32(unit_rows(nq, d, 3))
+        mine = pkg.shard.stripe(n, rank, world)
+        assert len(mine) == pkg.shard.local_count(n, rank, world)
+        ids = np.zeros((nq, k), np.uint64)
+        sims = np.zeros((nq, k), np.float32)
+        counts = np.zeros(nq, np.int32)
+        for i in range(nq):
+            li, ls = oracle.search(qs[i], cent, rows[mine], lists[mine], doc[mine], nprobe, k)
+            ids[i, :len(li)], sims[i, :len(li)], counts[i] = li, ls, len(li)
+        g = pkg.shard.gather_hits(torch.from_numpy(ids.view(np.int64)), torch.from_numpy(sims), torch.from_numpy(counts))
+        g_ids, g_sims, g_counts = g[0].numpy().view(np.uint64), g[1].numpy(), g[2].numpy()
+        assert g_ids.shape == (world, nq, k)
+        # every rank's stripe is disjoint and together they cover all rows
+        cover = torch.zeros(n, dtype=torch.int32)
+        cover[torch.from_numpy(mine)] = 1
+        dist.all_reduce(cover)
+        assert int(cover.min()) == 1 and int(cover.max()) == 1
+        merged = _merge_np(g_ids, g_sims, g_counts, k)
+        for i in range(nq):
+            wi, ws = oracle.search(qs[i], cent, rows, lists, doc, nprobe, k)
+            assert [h[0] for h in merged[i]] == wi.tolist(), f"rank {rank} query {i}"
+            assert np.array([h[1] for h in merged[i]], np.float32).view(np.uint32).tolist() == ws.view(np.uint32).tolist()
+        dist.destroy_process_group()
+        q.put((rank, "ok"))
+    except Exception as e:  # noqa: BLE001
+        import traceback
+        q.put((rank, "error: " + repr(e) + "\n" + traceback.format_exc()))
+
+
+def test_striped_search_world2_gloo():
+    import torch.multiprocessing as mp
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_worker, args=(r, 2, port, q)) for r in range(2)]
+    [p.start() for p in procs]
+    res = [q.get(timeout=180) for _ in procs]
+    [p.join(timeout=60) for p in procs]
+    assert all(r[1] == "ok" for r in res), res
+
+
+def test_stripe_partition():
+    from conftest import load_pkg
+    pkg = load_pkg()
+    for n in (0, 1, 7, 1000):
+        for world in (1, 2, 3, 8):
+            parts = [pkg.shard.stripe(n, r, world) for r in range(world)]
+            assert sorted(np.concatenate(parts).tolist()) == list(range(n))
+            assert [len(p) for p in parts] == [pkg.shard.local_count(n, r, world) for r in range(world)]
