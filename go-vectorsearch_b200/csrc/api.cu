@@ -88,6 +88,8 @@ extern "C" int vs_ctx_create(vs_ctx **out) {
     CU(cudaEventCreate(&c->ev1));
     CU(cudaMalloc(&c->d_fix_counter, 8));
     CU(cudaMemset(c->d_fix_counter, 0, 8));
+    CU(cudaMalloc(&c->d_tickets, kMaxStageQueries * sizeof(unsigned int)));
+    CU(cudaMemset(c->d_tickets, 0, kMaxStageQueries * sizeof(unsigned int)));
     *out = c;
     return VS_OK;
 }
@@ -103,6 +105,8 @@ extern "C" int vs_ctx_create_on_stream(void *cuda_stream, vs_ctx **out) {
     CU(cudaEventCreate(&c->ev1));
     CU(cudaMalloc(&c->d_fix_counter, 8));
     CU(cudaMemset(c->d_fix_counter, 0, 8));
+    CU(cudaMalloc(&c->d_tickets, kMaxStageQueries * sizeof(unsigned int)));
+    CU(cudaMemset(c->d_tickets, 0, kMaxStageQueries * sizeof(unsigned int)));
     *out = c;
     return VS_OK;
 }
@@ -114,6 +118,7 @@ extern "C" void vs_ctx_destroy(vs_ctx *c) {
     if (c->scratch) cudaFree(c->scratch);
     if (c->pinned) cudaFreeHost(c->pinned);
     if (c->d_fix_counter) cudaFree(c->d_fix_counter);
+    if (c->d_tickets) cudaFree(c->d_tickets);
     if (c->d_trace) cudaFree(c->d_trace);
     for (cudaEvent_t e : c->prof_events) cudaEventDestroy(e);
     cudaEventDestroy(c->ev0);
@@ -869,7 +874,7 @@ static int search_enqueue(vs_ctx *c, const vs_index *ix, const MatView &qv, size
     p.qnorm = b.qnorm;
     p.q_select = d_select;
     p.nq = (int)nq_launch;
-    p.tickets = b.tickets;
+    p.tickets = c->d_tickets;
     p.out_status = d_status;
     p.fix_counter = c->d_fix_counter;
     const uint32_t tr1 = exact ? 32 : b.tile_rows1, tr2 = exact ? 32 : b.tile_rows2;
@@ -893,6 +898,7 @@ static int search_enqueue(vs_ctx *c, const vs_index *ix, const MatView &qv, size
         p.next_list_off = ix->list_off;
         p.next_tile_rows = tr2;
         p.status_bit = kStatusProbeAmbiguous;
+        p.status_init = 1;
         p.trace = c->trace ? c->d_trace : nullptr;
         if (p.trace) CU(cudaMemsetAsync(p.trace, 0, kTraceBlocks * 16 * sizeof(unsigned long long), c->stream));
         LAUNCH(c, launch_stage(p, kpl1, exact, b.grid, c->stream));
@@ -927,6 +933,7 @@ static int search_enqueue(vs_ctx *c, const vs_index *ix, const MatView &qv, size
     p.out_probe = nullptr;
     p.out_qtiles = nullptr;
     p.status_bit = kStatusListAmbiguous;
+    p.status_init = flat ? 1 : 0;
     p.trace = c->trace ? c->d_trace + kTraceBlocks * 16 : nullptr;
     if (p.trace) CU(cudaMemsetAsync(p.trace, 0, kTraceBlocks * 16 * sizeof(unsigned long long), c->stream));
     VS(prof_mark(c));
@@ -1005,8 +1012,6 @@ extern "C" int vs_search_dev(vs_ctx *c, const vs_index *ix, const vs_matrix *que
     SearchSetup s;
     VS(search_setup(c, a, ix, nq, nprobe, k, 0, &s));
     search_take(a, ix, nq, &s);
-    CU(cudaMemsetAsync(d_status, 0, nq * 4, c->stream));
-    CU(cudaMemsetAsync(s.b.tickets, 0, nq * 4, c->stream));
     return search_enqueue(c, ix, queries->view(), nq, nullptr, s.npe, k, s.kpl1, s.kpl2, s.flat, false, s.b, d_ids, d_sims,
                           d_counts, d_status, nullptr, false);
 }
@@ -1028,7 +1033,6 @@ extern "C" int vs_search_resolve(vs_ctx *c, const vs_index *ix, const vs_matrix 
     SearchSetup s;
     VS(search_setup(c, a, ix, nq, nprobe, k, 0, &s));
     search_take(a, ix, nq, &s);
-    CU(cudaMemsetAsync(s.b.tickets, 0, nq * 4, c->stream));
     return search_resolve_flagged(c, ix, queries->view(), nq, h_status, s, k, d_ids, d_sims, d_counts, d_status, nullptr,
                                   false, n_resolved_out);
 }
@@ -1051,8 +1055,6 @@ static int search_host(vs_ctx *c, const vs_index *ix, const uint8_t *queries, si
     int32_t *d_counts = a.take<int32_t>(nq);
     uint32_t *d_status = a.take<uint32_t>(nq);
     float *d_psims = a.take<float>(nq * s.npe);
-    CU(cudaMemsetAsync(d_status, 0, nq * 4, c->stream));
-    CU(cudaMemsetAsync(s.b.tickets, 0, nq * 4, c->stream));
     VS(search_enqueue(c, ix, qv, nq, nullptr, s.npe, k, s.kpl1, s.kpl2, s.flat, false, s.b, d_ids, d_sims, d_counts, d_status,
                       stage1_only ? d_psims : nullptr, stage1_only));
     VS(pinned_reserve(c, nq * 4));
@@ -1118,8 +1120,23 @@ extern "C" int vs_topk_merge_dev(vs_ctx *c, const uint64_t *d_ids_in, const floa
     if (!c) return fail(VS_EINVAL, "ctx is null");
     if (k > 128) return fail(VS_ERANGE, "k=%zu > 128", k);
     if (nq == 0) return VS_OK;
-    LAUNCH(c, launch_topk_merge(d_ids_in, d_sims_in, d_counts_in, (int)G, (int)nq, (int)k, d_ids_out, d_sims_out, d_counts_out,
+    LAUNCH(c, launch_topk_merge(d_ids_in, d_sims_in, d_counts_in, 0, (int)G, (int)nq, (int)k, d_ids_out, d_sims_out, d_counts_out,
                                 c->stream));
+    return VS_OK;
+}
+
+extern "C" int vs_topk_merge_packed_dev(vs_ctx *c, const void *d_packed, size_t rank_stride_bytes, size_t ids_off, size_t sims_off,
+                                        size_t counts_off, size_t G, size_t nq, size_t k, uint64_t *d_ids_out, float *d_sims_out,
+                                        int32_t *d_counts_out) {
+    VS(need_dev());
+    if (!c || !d_packed) return fail(VS_EINVAL, "null argument");
+    if (k > 128) return fail(VS_ERANGE, "k=%zu > 128", k);
+    if ((ids_off | sims_off | counts_off | rank_stride_bytes) & 3) return fail(VS_EINVAL, "offsets must be 4-byte aligned");
+    if (nq == 0) return VS_OK;
+    const char *b = static_cast<const char *>(d_packed);
+    LAUNCH(c, launch_topk_merge(reinterpret_cast<const uint64_t *>(b + ids_off), reinterpret_cast<const float *>(b + sims_off),
+                                reinterpret_cast<const int32_t *>(b + counts_off), rank_stride_bytes, (int)G, (int)nq, (int)k,
+                                d_ids_out, d_sims_out, d_counts_out, c->stream));
     return VS_OK;
 }
 

@@ -21,6 +21,7 @@ struct vs_ctx {
     size_t pinned_cap = 0;
     bool owns_stream = true;
     unsigned long long *d_fix_counter = nullptr;  // in-kernel literal re-scores (device)
+    unsigned int *d_tickets = nullptr;            // [kMaxStageQueries] zeroed once; every launch re-arms them
     unsigned long long *d_trace = nullptr;        // phase stamps of the last list-scan launch (when enabled)
     bool trace = false;
     // optional per-kernel timing of the list-scan stage
@@ -94,6 +95,7 @@ struct StageParams {
     unsigned long long *fix_counter;  // device counter: candidates re-scored with literal arithmetic in-kernel
     uint32_t *out_status;         // [q], OR-ed with status_bit / need-more bit
     uint32_t status_bit;
+    int status_init;              // 1: this stage stores the query's status word, 0: it ORs into it
 };
 
 constexpr uint32_t kStatusProbeAmbiguous = 1u;
@@ -109,8 +111,8 @@ cudaError_t launch_cosine_1xN(const MatView &rows, const MatView &query, float *
                               uint32_t *worklist, unsigned int *work_count, int sm_count, cudaStream_t st);
 cudaError_t launch_cosine_fix(const MatView &rows, const double *qnorm, float *sims, const uint32_t *worklist,
                               const unsigned int *work_count, int sm_count, cudaStream_t st);
-cudaError_t launch_topk_merge(const uint64_t *ids_in, const float *sims_in, const int32_t *counts_in, int G, int nq,
-                              int k, uint64_t *ids_out, float *sims_out, int32_t *counts_out, cudaStream_t st);
+cudaError_t launch_topk_merge(const uint64_t *ids_in, const float *sims_in, const int32_t *counts_in, size_t rank_stride_bytes,
+                              int G, int nq, int k, uint64_t *ids_out, float *sims_out, int32_t *counts_out, cudaStream_t st);
 
 // quantize.cu
 cudaError_t launch_quantize_f32(const float *in, size_t n, int d, uint8_t *out_rows, cudaStream_t st);

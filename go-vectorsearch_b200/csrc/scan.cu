@@ -759,7 +759,7 @@ stage_kernel(const StageParams p) {
                     }
                     if (lane == 0 && p.out_status) {
                         if (EXACT) p.out_status[qi] = (p.out_status[qi] & ~p.status_bit) | (status & kStatusNeedMore);
-                        else p.out_status[qi] |= status;
+                        else p.out_status[qi] = p.status_init ? status : (p.out_status[qi] | status);
                     }
                 }
                 if (lane == 0) sh.need_fix = need_fix ? 1u : 0u;
@@ -976,20 +976,28 @@ cudaError_t launch_cosine_fix(const MatView &rows, const double *qnorm, float *s
 
 // ---------------------------------------------------------------------------------------------------
 // Multi-GPU merge: G shard-local hit lists per query -> global top-k (same order and dedup rule).
-__global__ void topk_merge_kernel(const uint64_t *ids_in, const float *sims_in, const int32_t *counts_in, int G, int nq,
-                                  int k, uint64_t *ids_out, float *sims_out, int32_t *counts_out) {
+__global__ void topk_merge_kernel(const uint64_t *ids_in, const float *sims_in, const int32_t *counts_in,
+                                  size_t rank_stride_bytes, int G, int nq, int k, uint64_t *ids_out, float *sims_out,
+                                  int32_t *counts_out) {
     const int qi = blockIdx.x;
     const int lane = threadIdx.x;
     WarpTopK<4> top;
     top.init();
     for (int g = 0; g < G; g++) {
-        const int cnt = counts_in[(size_t)g * nq + qi];
+        // rank g's arrays: either [G][nq][k] contiguous (stride 0 = derive) or one packed buffer per rank
+        const uint64_t *gi = rank_stride_bytes ? reinterpret_cast<const uint64_t *>(reinterpret_cast<const char *>(ids_in) + g * rank_stride_bytes)
+                                               : ids_in + (size_t)g * nq * k;
+        const float *gs = rank_stride_bytes ? reinterpret_cast<const float *>(reinterpret_cast<const char *>(sims_in) + g * rank_stride_bytes)
+                                            : sims_in + (size_t)g * nq * k;
+        const int32_t *gc = rank_stride_bytes ? reinterpret_cast<const int32_t *>(reinterpret_cast<const char *>(counts_in) + g * rank_stride_bytes)
+                                              : counts_in + (size_t)g * nq;
+        const int cnt = gc[qi];
         for (int base = 0; base < cnt; base += 32) {
             int j = base + lane;
             bool valid = j < cnt;
-            size_t off = ((size_t)g * nq + qi) * k + (valid ? j : 0);
-            uint32_t key = valid ? f32_to_key(sims_in[off]) : 0u;
-            uint64_t id = valid ? ids_in[off] : kEmptyId;
+            size_t off = (size_t)qi * k + (valid ? j : 0);
+            uint32_t key = valid ? f32_to_key(gs[off]) : 0u;
+            uint64_t id = valid ? gi[off] : kEmptyId;
             top.offer(valid, key, 0u, id, lane);
         }
     }
@@ -1021,10 +1029,10 @@ __global__ void topk_merge_kernel(const uint64_t *ids_in, const float *sims_in, 
     if (lane == 0) counts_out[qi] = min(base, k);
 }
 
-cudaError_t launch_topk_merge(const uint64_t *ids_in, const float *sims_in, const int32_t *counts_in, int G, int nq,
-                              int k, uint64_t *ids_out, float *sims_out, int32_t *counts_out, cudaStream_t st) {
+cudaError_t launch_topk_merge(const uint64_t *ids_in, const float *sims_in, const int32_t *counts_in, size_t rank_stride_bytes,
+                              int G, int nq, int k, uint64_t *ids_out, float *sims_out, int32_t *counts_out, cudaStream_t st) {
     if (k > 128) return cudaErrorInvalidValue;
-    topk_merge_kernel<<<nq, 32, 0, st>>>(ids_in, sims_in, counts_in, G, nq, k, ids_out, sims_out, counts_out);
+    topk_merge_kernel<<<nq, 32, 0, st>>>(ids_in, sims_in, counts_in, rank_stride_bytes, G, nq, k, ids_out, sims_out, counts_out);
     return cudaGetLastError();
 }
 

@@ -40,3 +40,38 @@ def merge_hits_dev(g_ids, g_sims, g_counts, k, out_ids, out_sims, out_counts, ct
     G, nq = int(g_ids.shape[0]), int(g_ids.shape[1])
     ivf.TopKMergeDev(g_ids.data_ptr(), g_sims.data_ptr(), g_counts.data_ptr(), G, nq, k, out_ids.data_ptr(),
                      out_sims.data_ptr(), out_counts.data_ptr(), ctx=ctx)
+
+
+class PackedHits:
+    """Shard-local hit buffers laid out for ONE all-gather per step: [ids nq*k u64 | sims nq*k f32 | counts nq i32]
+    in a single device allocation per rank, plus the gathered [world] copy and the merged outputs."""
+
+    def __init__(self, nq, k, device, world):
+        import torch
+        self.nq, self.k, self.world = nq, k, world
+        self.ids_off = 0
+        self.sims_off = nq * k * 8
+        self.counts_off = self.sims_off + ((nq * k * 4 + 7) // 8) * 8
+        self.nbytes = self.counts_off + ((nq * 4 + 15) // 16) * 16
+        self.local = torch.zeros(self.nbytes, dtype=torch.uint8, device=device)
+        self.gathered = torch.zeros(self.nbytes * world, dtype=torch.uint8, device=device)
+        self.ids = self.local[self.ids_off:self.ids_off + nq * k * 8].view(torch.int64).view(nq, k)
+        self.sims = self.local[self.sims_off:self.sims_off + nq * k * 4].view(torch.float32).view(nq, k)
+        self.counts = self.local[self.counts_off:self.counts_off + nq * 4].view(torch.int32)
+        self.out_ids = torch.zeros((nq, k), dtype=torch.int64, device=device)
+        self.out_sims = torch.zeros((nq, k), dtype=torch.float32, device=device)
+        self.out_counts = torch.zeros(nq, dtype=torch.int32, device=device)
+
+    def gather_and_merge(self, ctx=None, group=None):
+        """One NCCL all-gather of the packed buffer, then the device merge (asynchronous on the shared stream)."""
+        import ctypes as C
+        import torch.distributed as dist
+        from . import _lib
+        from .compute import _check, default_context
+        dist.all_gather_into_tensor(self.gathered, self.local, group=group)
+        ctx = ctx or default_context()
+        L = _lib.init()
+        vp = lambda t: C.c_void_p(t.data_ptr())
+        _check(L.vs_topk_merge_packed_dev(ctx.handle, vp(self.gathered), self.nbytes, self.ids_off, self.sims_off,
+                                          self.counts_off, self.world, self.nq, self.k, vp(self.out_ids), vp(self.out_sims),
+                                          vp(self.out_counts)))

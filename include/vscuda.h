@@ -171,6 +171,13 @@ VS_API int vs_select_probes(vs_ctx *ctx, const vs_index *ix, const uint8_t *quer
 VS_API int vs_topk_merge_dev(vs_ctx *ctx, const uint64_t *d_ids_in, const float *d_sims_in, const int32_t *d_counts_in,
                       size_t G, size_t nq, size_t k, uint64_t *d_ids_out, float *d_sims_out, int32_t *d_counts_out);
 
+/* Same for shard results packed one buffer per rank (a single all-gather): rank g's buffer starts at
+ * d_packed + g*rank_stride_bytes and holds ids[nq*k] (uint64) at ids_off, sims[nq*k] (float32) at sims_off and
+ * counts[nq] (int32) at counts_off (byte offsets, 8-byte aligned). */
+VS_API int vs_topk_merge_packed_dev(vs_ctx *ctx, const void *d_packed, size_t rank_stride_bytes, size_t ids_off,
+                                    size_t sims_off, size_t counts_off, size_t G, size_t nq, size_t k, uint64_t *d_ids_out,
+                                    float *d_sims_out, int32_t *d_counts_out);
+
 /* ---- dnc/k_means.go:67-117 and dnc/dnc.go:417-449 ---------------------------------- */
 /* One Lloyd iteration.  data: device matrix; centroids_packed: k rows (host); means: [k][D] float32
  * (host, in/out: the state k_means.go:60-65 carries; an empty cluster keeps its previous mean).
