@@ -12,7 +12,7 @@ VS_OK, VS_EINVAL, VS_EEMPTY, VS_EDIM, VS_ECUDA, VS_ENODEV, VS_ENOMEM, VS_ERANGE 
 SYMBOLS = [
     "vs_init", "vs_shutdown", "vs_last_error", "vs_device_info",
     "vs_ctx_create", "vs_ctx_create_on_stream", "vs_ctx_profile_enable", "vs_ctx_profile_read", "vs_ctx_trace_enable", "vs_ctx_trace_read", "vs_ctx_destroy", "vs_ctx_sync", "vs_ctx_stream", "vs_ctx_launch_count",
-    "vs_ctx_slowpath_count", "vs_ctx_timer_start", "vs_ctx_timer_stop",
+    "vs_ctx_slowpath_count", "vs_debug_set_certify_scale", "vs_ctx_timer_start", "vs_ctx_timer_stop",
     "vs_quantize_f32", "vs_quantize_f64", "vs_dequantize_f32", "vs_dequantize_f64",
     "vs_quantize_f32_dev", "vs_quantize_f64_dev",
     "vs_matrix_create", "vs_matrix_create_empty", "vs_matrix_fill_f32_dev", "vs_matrix_load_rows", "vs_matrix_create_dev", "vs_matrix_from_f32_dev", "vs_matrix_retain",
@@ -68,6 +68,7 @@ def load():
                      "vs_index_release", "vs_index_rows", "vs_index_lists"):
             getattr(L, name).argtypes = [vp]
         L.vs_init.argtypes = [C.c_int]
+        L.vs_debug_set_certify_scale.argtypes = [C.c_float]
         L.vs_ctx_create.argtypes = [C.POINTER(vp)]
         L.vs_ctx_create_on_stream.argtypes = [vp, C.POINTER(vp)]
         L.vs_ctx_profile_enable.argtypes = [vp, C.c_int]

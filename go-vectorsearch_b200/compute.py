@@ -48,6 +48,12 @@ def _p(a):
     return C.c_void_p(a.ctypes.data)
 
 
+def debug_set_certify_scale(scale):
+    """Test hook (vs_debug_set_certify_scale): inflate the certification half-widths so every score takes the
+    literal reference-arithmetic path; results must not change. 1.0 restores production behaviour."""
+    _check(_lib.init().vs_debug_set_certify_scale(C.c_float(scale)))
+
+
 class Context:
     """One CUDA stream + scratch arena (vs_ctx). One per closure / goroutine (dnc/dnc.go:349)."""
 

@@ -198,6 +198,15 @@ extern "C" uint64_t vs_ctx_slowpath_count(const vs_ctx *c) {
     cudaMemcpy(&dev, c->d_fix_counter, 8, cudaMemcpyDeviceToHost);
     return c->slowpath + dev;
 }
+extern "C" int vs_debug_set_certify_scale(float scale) {
+    if (need_dev()) return VS_ENODEV;
+    if (!(scale >= 1.0f)) return fail(VS_EINVAL, "certify scale must be >= 1");
+    cudaDeviceSynchronize();
+    CU(vs::scan_set_certify_scale(scale));
+    CU(vs::argmax_set_certify_scale(scale));
+    return VS_OK;
+}
+
 extern "C" int vs_ctx_timer_start(vs_ctx *c) {
     CU(cudaEventRecord(c->ev0, c->stream));
     return VS_OK;

@@ -307,4 +307,6 @@ cudaError_t launch_canonical_rows(const MatView &m, uint32_t *canon, cudaStream_
     return cudaGetLastError();
 }
 
+cudaError_t argmax_set_certify_scale(float scale) { return cudaMemcpyToSymbol(c_certify_scale, &scale, sizeof(float)); }
+
 }  // namespace vs

@@ -123,128 +123,166 @@ __device__ __forceinline__ uint32_t ref_quant_f64(double v, double mn, double mx
 }
 
 // ---- the certified integer-identity score ------------------------------------------------------
-// With x_i = a + q_i*(a'-a)/255 and y_i = b + v_i*(b'-b)/255 (the values the reference dequantizes to),
-//   255^2 * x.y   = D*A*B + A*S*sum(v) + B*R*sum(q) + R*S*sum(q*v),  A=255a, R=a'-a, B=255b, S=b'-b
-//   255^2 * |y|^2 = D*B^2 + 2*B*S*sum(v) + S^2*sum(v^2)
+// With x_i = a + q_i*R/255 and y_i = b + v_i*S/255 (the values the reference dequantizes to; R = a'-a,
+// S = b'-b in float64 exactly as the reference widens its float32 header) and A = 255a, B = 255b:
+//   ux = D*A + R*sum(q)                      ( = 255*D*mean(x) )
+//   Ix = D*sum(q^2) - sum(q)^2               ( exact int64: D^2 * variance of the codes )
+//   I1 = D*sum(q*v) - sum(q)*sum(v)          ( exact int64: D^2 * covariance of the codes )
+//   255^2*D * x.y   = R*S*I1 + ux*uy
+//   255^2*D * |x|^2 = R^2*Ix + ux^2          ( two non-negative terms: no cancellation )
+//   cos = (R*S*I1 + ux*uy) * rsqrt((R^2*Ix + ux^2)(S^2*Iy + uy^2))
+// The cancellation between the large "offset" terms of the naive expansion happens in integers, exactly.
 // Only sum(q*v) depends on both vectors; it is an exact uint8 dot product.
-struct SideConst {   // per vector: A, R and the derived norm terms
-    double A, R;     // 255*min, max-min (float64 of the float32 header, as the reference widens it)
-    double sum, sumsq;  // sum of codes, sum of squared codes
-    double P;        // 255^2 * |x|^2
-    double T;        // sum of |terms| of P (cancellation measure)
-    double sqrtP;
-    double tp;       // 8*T/P: relative rounding error of P in units of u
-    double mg;       // 8*255*(|a|+|a'-a|)/sqrt(P): reference dequantization error relative to |x|, per sqrt(D)
+struct SideConst {
+    double R;      // max - min
+    double ux;     // D*255*min + R*sum
+    double P;      // R^2*I + ux^2  = 255^2 * D * |x|^2
+    double epP;    // (rounding-error coefficient of P) / P, units of u
+    double mgs;    // 255*(|min| + |R|) / sqrt(P): reference dequantization error relative to |x| (times 1/sqrt(D))
+    float M;       // |D*A| + |R*sum|, rounded up (error scale of ux)
+    long long s1;  // sum of codes
+    int trivial_zero;  // every dequantized value is exactly 0 (min == 0 and (R == 0 or all codes 0))
 };
 
 __device__ __forceinline__ SideConst make_side(float mn, float mx, uint32_t s1, uint32_t s2, int D) {
     SideConst c;
-    double a = (double)mn, ap = (double)mx;
-    c.A = 255.0 * a;
-    c.R = ap - a;
-    c.sum = (double)s1;
-    c.sumsq = (double)s2;
-    double p1 = (double)D * c.A * c.A;
-    double p2 = 2.0 * c.A * c.R * c.sum;
-    double p3 = c.R * c.R * c.sumsq;
-    c.P = p1 + p2 + p3;
-    c.T = p1 + fabs(p2) + p3;
-    c.sqrtP = sqrt(c.P);
-    // magnitude bound of the reference's dequantization intermediates relative to |x|:
-    // (|a| + |a'-a|) / |x| = 255*(|a|+|R|)/sqrt(P)
-    double mag = 255.0 * (fabs(a) + fabs(c.R));
-    c.tp = 8.0 * (c.T / c.P);
-    c.mg = 8.0 * mag / c.sqrtP;
+    const double a = (double)mn;
+    c.R = (double)mx - a;
+    const double DA = (double)D * (255.0 * a);  // exact: 12 + 32 significant bits
+    const double rs = c.R * (double)s1;
+    c.ux = DA + rs;
+    const double Md = fabs(DA) + fabs(rs);
+    const long long I = (long long)D * (long long)s2 - (long long)s1 * (long long)s1;
+    const double r2i = c.R * c.R * (double)I;
+    const double u2 = c.ux * c.ux;
+    c.P = r2i + u2;
+    const double eP = 2.0 * r2i + 4.0 * fabs(c.ux) * Md + u2 + c.P;
+    c.epP = eP / c.P;
+    c.mgs = 255.0 * (fabs(a) + fabs(c.R)) / sqrt(c.P);
+    c.M = __double2float_ru(Md);
+    c.s1 = (long long)s1;
+    c.trivial_zero = (mn == 0.0f) && (c.R == c.R) && (fabs(c.R) < 1.0e300) && (c.R == 0.0 || s2 == 0u);
     return c;
 }
 
-// Per-row side of the identity, without the slow float64 divide / sqrt: only what score_fast needs.
-struct RowSide {
-    double A, R, sum;  // 255*min, max-min, sum of codes
-    double P;          // 255^2 * |y|^2
-    float Tf;          // sum of |terms| of P, rounded up
-    float magf;        // 255*(|min| + |max-min|), rounded up
-};
+// Test hook (vs_debug_set_certify_scale): inflates every certification half-width so that the parity tests can
+// drive all rows through the literal-arithmetic paths.  1.0 in production.  One copy per translation unit.
+static __constant__ float c_certify_scale = 1.0f;
 
-__device__ __forceinline__ RowSide make_row_side(float mn, float mx, uint32_t s1, uint32_t s2, int D) {
-    RowSide c;
-    double a = (double)mn, ap = (double)mx;
-    c.A = 255.0 * a;
-    c.R = ap - a;
-    c.sum = (double)s1;
-    double p1 = (double)D * c.A * c.A;
-    double p2 = 2.0 * c.A * c.R * c.sum;
-    double p3 = c.R * c.R * (double)s2;
-    c.P = p1 + p2 + p3;
-    c.Tf = __double2float_ru(p1 + fabs(p2) + p3);
-    c.magf = __double2float_ru(255.0 * (fabs(a) + fabs(c.R)));
-    return c;
-}
-
-// Returns the float32 similarity; *flag = the float32 rounding (or the value) cannot be certified
-// to equal the reference's float32(dot) -- such rows are recomputed with literal arithmetic.
-// Error model (DESIGN.md "certified scores"): |ours - reference| <= delta with
-//   delta = 2u * ( 8*T/den + 8*Tx/Px + 8*Ty/Py            (our own roundings, cancellation-aware)
-//                + (2D+16)                                  (reference: sequential norm, divide, dot)
-//                + 8*sqrt(D)*(mag_x/|x| + mag_y/|y|) )      (reference: dequantization roundings)
-// The score itself is N * rsqrt(Px*Py) in float64 (one rsqrt, no divide); the delta terms only need to be
-// upper bounds, so they are evaluated in float32 with directed rounding / a 1.001 inflation.  Overflow,
-// underflow or NaN anywhere makes delta non-finite or huge and the row is flagged: never mis-certified.
-__device__ __forceinline__ float score_fast(const SideConst &x, const RowSide &y, uint32_t dot_qv, int D, float sqrtDf,
-                                            bool *flag) {
-    double t1 = (double)D * x.A * y.A;
-    double t2 = x.A * y.R * y.sum;
-    double t3 = y.A * x.R * x.sum;
-    double t4 = x.R * y.R * (double)dot_qv;
-    double N = (t1 + t2) + (t3 + t4);
-    float Tf = __double2float_ru(fabs(t1) + fabs(t2) + fabs(t3) + fabs(t4));
-    if (x.T == 0.0 || y.Tf == 0.0f) {  // an exactly-zero vector (header 0/0 or all terms 0): the reference leaves it
-        bool finite = (x.T == x.T) && (y.Tf == y.Tf) && (Tf == Tf) && Tf < 3.0e38f;  // unnormalized, dot = +0
-        *flag = !finite;
-        return finite ? 0.0f : 2.0f;
+// Error model (DESIGN.md "certified scores"), all in units of u = 2^-53:
+//   ours      eN/den + 0.5|c| (ePx/Px + ePy/Py) + 4       (products / sums of the identity, rsqrt, final product)
+//   reference (D+4) + |c| (D+2)                            (sequential dot; sequential norms, sqrt, divides)
+//             3.5 * D * (mag_x/sqrt(Px) + mag_y/sqrt(Py))  (three roundings per dequantized element)
+//   delta = 1.25 * u * (ours + reference)
+// The delta terms only need to be upper bounds: they are evaluated in float32 (with a 1.001 inflation for the
+// float32 roundings).  Overflow, underflow or NaN anywhere makes delta non-finite or huge: flagged, never
+// mis-certified.  Measured |ours - reference| / delta <= 0.11 over seven data families.
+__device__ __forceinline__ bool score_core(const SideConst &x, double yR, double yux, double yP, float yM, float yepP,
+                                           float ymgs, long long ys1, int ytz, uint32_t dot_qv, int D, double *c_out,
+                                           double *delta_out) {
+    if (x.trivial_zero || ytz) {  // the reference leaves an all-zero vector unnormalized: dot = +0
+        *c_out = 0.0;
+        *delta_out = 0.0;
+        // the other side must still be finite (NaN * 0 = NaN in the reference)
+        return (x.P == x.P) && (yP == yP) && fabs(x.P) < 1.0e300 && fabs(yP) < 1.0e300;
     }
-    double pp = x.P * y.P;
-    double c = N * rsqrt(pp);
-    float ppf = __double2float_rd(pp);
-    float rden = rsqrtf(ppf);                                  // ~ 1/den
-    float ry = rsqrtf(__double2float_rd(y.P));                 // ~ 1/sqrt(Py)
-    float e = 8.0f * (Tf * rden) + (float)x.tp + 8.0f * (y.Tf * ry * ry) + (float)(2 * D + 16) +
-              sqrtDf * ((float)x.mg + 8.0f * (y.magf * ry));
-    double delta = (2.0 * 1.001 * kU) * (double)e;
-    bool ok = (x.P > 0.0) && (y.P > 0.0) && (delta < 1.0e-6);   // false for NaN / Inf as well
-    float lo = __double2float_rn(c - delta);
-    float hi = __double2float_rn(c + delta);
+    const long long I1 = (long long)D * (long long)dot_qv - x.s1 * ys1;
+    const double n1 = x.R * yR * (double)I1;
+    const double n2 = x.ux * yux;
+    const double N = n1 + n2;
+    const double pp = x.P * yP;
+    const double r = rsqrt(pp);
+    const double c = N * r;
+    const float rf = __double2float_ru(r);
+    const float eN = 2.0f * fabsf((float)n1) + 2.0f * (fabsf((float)yux) * x.M + fabsf((float)x.ux) * yM) +
+                     fabsf((float)n2) + fabsf((float)N);
+    const float ac = fabsf((float)c);
+    const float e = eN * rf + 0.5f * ac * ((float)x.epP + yepP) + 4.0f + (float)(D + 4) + ac * (float)(D + 2) +
+                    3.5f * (float)D * ((float)x.mgs + ymgs);
+    const double delta = (1.25 * 1.001 * kU) * (double)(e * c_certify_scale);
+    *c_out = c;
+    *delta_out = delta;
+    return (x.P > 0.0) && (yP > 0.0) && (delta < 1.0e-6);  // false for NaN / Inf as well
+}
+
+// Row side evaluated per scanned row (no float64 divide or sqrt: float32 reciprocal sqrt for the bound terms).
+__device__ __forceinline__ float score_fast(const SideConst &x, float mn, float mx, uint32_t s1, uint32_t s2, uint32_t dot_qv,
+                                            int D, bool *flag) {
+    const double a = (double)mn;
+    const double R = (double)mx - a;
+    const double DA = (double)D * (255.0 * a);
+    const double rs = R * (double)s1;
+    const double ux = DA + rs;
+    const double Md = fabs(DA) + fabs(rs);
+    const long long I = (long long)D * (long long)s2 - (long long)s1 * (long long)s1;
+    const double r2i = R * R * (double)I;
+    const double u2 = ux * ux;
+    const double P = r2i + u2;
+    const float rP = rsqrtf(__double2float_rd(P));  // ~ 1/sqrt(P), rounded toward larger
+    const float eP = 2.0f * (float)r2i + 4.0f * fabsf((float)ux) * __double2float_ru(Md) + (float)u2 + (float)P;
+    const int tz = (mn == 0.0f) && (R == R) && (fabs(R) < 1.0e300) && (R == 0.0 || s2 == 0u);
+    double c, delta;
+    const bool ok = score_core(x, R, ux, P, __double2float_ru(Md), eP * rP * rP, 255.0f * (fabsf(mn) + fabsf((float)R)) * rP,
+                               (long long)s1, tz, dot_qv, D, &c, &delta);
     if (!ok) {
         *flag = true;
         return 2.0f;
     }
+    const float lo = __double2float_rn(c - delta);
+    const float hi = __double2float_rn(c + delta);
     *flag = (lo != hi);
     return hi;
 }
 
-// Same model without the float32 rounding: value and rigorous half-width, for argmax comparisons
-// done in float64 (compute/cosine.go:114 `dot > maxVal`). ok=false -> needs the literal path.
-__device__ __forceinline__ bool score_interval(const SideConst &x, const SideConst &y, uint32_t dot_qv, int D,
-                                               double sqrtD, double *c_out, double *delta_out) {
-    double t1 = (double)D * x.A * y.A;
-    double t2 = x.A * y.R * y.sum;
-    double t3 = y.A * x.R * x.sum;
-    double t4 = x.R * y.R * (double)dot_qv;
-    double N = (t1 + t2) + (t3 + t4);
-    double T = fabs(t1) + fabs(t2) + fabs(t3) + fabs(t4);
-    double fin = T + x.T + y.T;
-    if (!(fin < 1.0e300)) return false;
-    if (x.T == 0.0 || y.T == 0.0) {
-        *c_out = 0.0;
-        *delta_out = 0.0;
-        return true;
+// Value and rigorous half-width for comparisons done in float64 (compute/cosine.go:114 `dot > maxVal`).
+// ok=false -> needs the literal path.
+__device__ __forceinline__ bool score_interval(const SideConst &x, const SideConst &y, uint32_t dot_qv, int D, double sqrtD,
+                                               double *c_out, double *delta_out) {
+    (void)sqrtD;
+    return score_core(x, y.R, y.ux, y.P, y.M, (float)y.epP, (float)y.mgs, y.s1, y.trivial_zero, dot_qv, D, c_out, delta_out);
+}
+
+// Ordered sum of D terms computed in parallel by the warp: lane L owns elements base+8L .. base+8L+7 of every
+// 256-element chunk; the additions run in element order (lane after lane), so the result equals a sequential
+// `for i { acc += term(i) }` bit for bit while the terms themselves are evaluated 32-wide.
+template <typename F>
+__device__ __forceinline__ double warp_ordered_sum(int D, int lane, F term) {
+    double acc = 0.0;
+    for (int base = 0; base < D; base += 256) {
+        double v[8];
+#pragma unroll
+        for (int j = 0; j < 8; j++) {
+            const int i = base + lane * 8 + j;
+            v[j] = i < D ? term(i) : 0.0;
+        }
+        const int lanes = min(32, (D - base + 7) >> 3);
+        for (int L = 0; L < lanes; L++) {
+            if (lane == L) {
+#pragma unroll
+                for (int j = 0; j < 8; j++)
+                    if (base + L * 8 + j < D) acc = __dadd_rn(acc, v[j]);
+            }
+            acc = __shfl_sync(0xFFFFFFFFu, acc, L);
+        }
     }
-    double den = x.sqrtP * y.sqrtP;
-    double c = N / den;
-    double delta = 2.0 * kU * (8.0 * (T / den) + x.tp + y.tp + (double)(2 * D + 16) + sqrtD * (x.mg + y.mg));
-    *c_out = c;
-    *delta_out = delta;
-    return (x.P > 0.0) && (y.P > 0.0) && (delta < 1.0e-6);
+    return acc;
+}
+
+// Literal reference cosine of one row (compute/cosine.go:29-33,43-50,138-149) by a whole warp; qn = the query
+// after normalizeVector. Every lane returns the same value.
+__device__ __forceinline__ double warp_ref_cosine_row_f64(const uint8_t *codes, float mn_f, float mx_f, const double *qn, int D,
+                                                          int lane) {
+    const double mn = (double)mn_f, range = __dsub_rn((double)mx_f, (double)mn_f);
+    const double normsq = warp_ordered_sum(D, lane, [&](int i) {
+        const double x = ref_dequant_f64(codes[i], mn, range);
+        return __dmul_rn(x, x);
+    });
+    const double norm = __dsqrt_rn(normsq);
+    return warp_ordered_sum(D, lane, [&](int i) {
+        double x = ref_dequant_f64(codes[i], mn, range);
+        if (norm != 0.0) x = __ddiv_rn(x, norm);
+        return __dmul_rn(qn[i], x);
+    });
 }
 
 // Literal reference cosine of one row against a pre-normalized query (compute/cosine.go:29-33,43-50,

@@ -114,6 +114,9 @@ cudaError_t launch_cosine_fix(const MatView &rows, const double *qnorm, float *s
 cudaError_t launch_topk_merge(const uint64_t *ids_in, const float *sims_in, const int32_t *counts_in, size_t rank_stride_bytes,
                               int G, int nq, int k, uint64_t *ids_out, float *sims_out, int32_t *counts_out, cudaStream_t st);
 
+cudaError_t scan_set_certify_scale(float scale);
+cudaError_t argmax_set_certify_scale(float scale);
+
 // quantize.cu
 cudaError_t launch_quantize_f32(const float *in, size_t n, int d, uint8_t *out_rows, cudaStream_t st);
 cudaError_t launch_quantize_f64(const double *in, size_t n, int d, uint8_t *out_rows, cudaStream_t st);

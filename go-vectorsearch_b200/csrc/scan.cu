@@ -350,7 +350,6 @@ stage_kernel(const StageParams p) {
 
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int D = p.rows.d, d_pad = p.rows.d_pad;
-    const float sqrtDf = __double2float_ru(sqrt((double)D));
     constexpr int GG = (G == 0) ? 32 : G;
     const int iters = (G == 0 || EXACT) ? 32 : p.iters;  // rows per lane group in a tile
     const int tile_rows = (G == 0 || EXACT) ? 32 : (32 / GG) * iters;
@@ -510,8 +509,7 @@ stage_kernel(const StageParams p) {
                 uint32_t mydot;
                 if constexpr (G != 0) mydot = tile_dots<G, CPL>(p.rows.codes, row0, nrows, d_pad, qreg, lane, iters);
                 else mydot = tile_dots_generic(p.rows.codes, row0, nrows, d_pad, sh_q, lane);
-                RowSide y = make_row_side(h.x, h.y, s.x, s.y, D);
-                sim = score_fast(xq, y, mydot, D, sqrtDf, &flag);
+                sim = score_fast(xq, h.x, h.y, s.x, s.y, mydot, D, &flag);
             }
             uint32_t key = f32_to_key(sim);
             // lazy id: only rows that can still enter the list need their document id
@@ -767,31 +765,35 @@ stage_kernel(const StageParams p) {
             __syncthreads();
             VS_TRACE(6 + (pass ? 1 : 0));
             if (!sh.need_fix) break;
-            // normalizeVector of the query (compute/cosine.go:26,138-149), literal: parallel dequantize,
-            // one thread sums the squares in order, parallel divide.
+            // normalizeVector of the query (compute/cosine.go:26,138-149), literal: the elementwise work is spread
+            // over the threads, only the additions are chained in element order (warp_ordered_sum).
             {
                 const uint8_t *qc = p.queries.codes + (size_t)qi * d_pad;
                 const float2 qh = p.queries.hdr[qi];
                 const double mn = (double)qh.x, range = __dsub_rn((double)qh.y, (double)qh.x);
                 for (int i = threadIdx.x; i < D; i += blockDim.x) sh_qn[i] = ref_dequant_f64(qc[i], mn, range);
                 __syncthreads();
-                if (threadIdx.x == 0) {
-                    double norm = 0.0;
-                    for (int i = 0; i < D; i++) norm = __dadd_rn(norm, __dmul_rn(sh_qn[i], sh_qn[i]));
-                    sh.norm = __dsqrt_rn(norm);
+                if (warp == 0) {
+                    const double nsq = warp_ordered_sum(D, lane, [&](int i) { return __dmul_rn(sh_qn[i], sh_qn[i]); });
+                    if (lane == 0) sh.norm = __dsqrt_rn(nsq);
                 }
                 __syncthreads();
                 const double norm = sh.norm;
                 if (norm != 0.0)
                     for (int i = threadIdx.x; i < D; i += blockDim.x) sh_qn[i] = __ddiv_rn(sh_qn[i], norm);
                 __syncthreads();
-                for (int e = threadIdx.x; e < CAP; e += blockDim.x) {
-                    if (bufA.key[e] != 0 && (bufA.meta[e] & kFlagBit)) {
-                        const size_t row = bufA.meta[e] & ~kFlagBit;
+                // one warp per flagged candidate
+                for (int e = warp; e < CAP; e += kStageWarps) {
+                    const uint32_t k0 = bufA.key[e], m0 = bufA.meta[e];
+                    if (k0 != 0 && (m0 & kFlagBit)) {
+                        const size_t row = m0 & ~kFlagBit;
                         const float2 h = p.rows.hdr[row];
-                        bufA.key[e] = f32_to_key(ref_cosine_row(p.rows.codes + row * (size_t)d_pad, h.x, h.y, sh_qn, D));
-                        bufA.meta[e] &= ~kFlagBit;
-                        if (p.fix_counter) atomicAdd(p.fix_counter, 1ull);
+                        const double dot = warp_ref_cosine_row_f64(p.rows.codes + row * (size_t)d_pad, h.x, h.y, sh_qn, D, lane);
+                        if (lane == 0) {
+                            bufA.key[e] = f32_to_key(__double2float_rn(dot));
+                            bufA.meta[e] = m0 & ~kFlagBit;
+                            if (p.fix_counter) atomicAdd(p.fix_counter, 1ull);
+                        }
                     }
                 }
                 __syncthreads();
@@ -908,7 +910,6 @@ cosine_1xN_kernel(MatView rows, MatView query, float *sims, uint32_t *dots, uint
     }
     __syncthreads();
     const SideConst xq = s_q;
-    const float sqrtDf = __double2float_ru(sqrt((double)D));
     uint4 qreg[CPL > 0 ? CPL : 1];
     if constexpr (G != 0) {
 #pragma unroll
@@ -928,9 +929,8 @@ cosine_1xN_kernel(MatView rows, MatView query, float *sims, uint32_t *dots, uint
             if (sims) {
                 float2 h = rows.hdr[row];
                 uint2 s = rows.sums[row];
-                RowSide y = make_row_side(h.x, h.y, s.x, s.y, D);
                 bool flag;
-                float sim = score_fast(xq, y, mydot, D, sqrtDf, &flag);
+                float sim = score_fast(xq, h.x, h.y, s.x, s.y, mydot, D, &flag);
                 sims[row] = sim;
                 if (flag) worklist[atomicAdd(work_count, 1u)] = (uint32_t)row;
             }
@@ -957,20 +957,23 @@ cudaError_t launch_cosine_1xN(const MatView &rows, const MatView &query, float *
     return cudaGetLastError();
 }
 
-// Rows whose float32 rounding could not be certified: literal reference arithmetic, one thread per row.
+// Rows whose float32 rounding could not be certified: literal reference arithmetic, one warp per row.
 __global__ void cosine_fix_kernel(MatView rows, const double *qnorm, float *sims, const uint32_t *worklist,
                                   const unsigned int *work_count) {
     const unsigned int n = *work_count;
-    for (unsigned int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+    const int lane = threadIdx.x & 31;
+    const unsigned int nwarps = gridDim.x * (blockDim.x >> 5);
+    for (unsigned int i = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5); i < n; i += nwarps) {
         const uint32_t row = worklist[i];
         const float2 h = rows.hdr[row];
-        sims[row] = ref_cosine_row(rows.codes + (size_t)row * rows.d_pad, h.x, h.y, qnorm, rows.d);
+        const double dot = warp_ref_cosine_row_f64(rows.codes + (size_t)row * rows.d_pad, h.x, h.y, qnorm, rows.d, lane);
+        if (lane == 0) sims[row] = __double2float_rn(dot);
     }
 }
 
 cudaError_t launch_cosine_fix(const MatView &rows, const double *qnorm, float *sims, const uint32_t *worklist,
                               const unsigned int *work_count, int sm_count, cudaStream_t st) {
-    cosine_fix_kernel<<<sm_count * 4, 64, 0, st>>>(rows, qnorm, sims, worklist, work_count);
+    cosine_fix_kernel<<<sm_count * 4, 128, 0, st>>>(rows, qnorm, sims, worklist, work_count);
     return cudaGetLastError();
 }
 
@@ -1035,5 +1038,7 @@ cudaError_t launch_topk_merge(const uint64_t *ids_in, const float *sims_in, cons
     topk_merge_kernel<<<nq, 32, 0, st>>>(ids_in, sims_in, counts_in, rank_stride_bytes, G, nq, k, ids_out, sims_out, counts_out);
     return cudaGetLastError();
 }
+
+cudaError_t scan_set_certify_scale(float scale) { return cudaMemcpyToSymbol(c_certify_scale, &scale, sizeof(float)); }
 
 }  // namespace vs

@@ -59,6 +59,9 @@ VS_API int vs_ctx_sync(vs_ctx *ctx);
 VS_API void *vs_ctx_stream(vs_ctx *ctx);                 /* cudaStream_t, for callers that time with events */
 VS_API uint64_t vs_ctx_launch_count(const vs_ctx *ctx);  /* kernels launched through this ctx so far */
 VS_API uint64_t vs_ctx_slowpath_count(const vs_ctx *ctx);/* rows / queries that took the literal-arithmetic path */
+/* Test hook: multiply every certification half-width by scale >= 1 so that rows are sent
+ * through the literal reference-arithmetic paths; results must not change.  Process-wide; 1.0 = production. */
+VS_API int vs_debug_set_certify_scale(float scale);
 /* CUDA-event timing on the ctx stream (bench.py): start/stop bracket, elapsed in ms after sync. */
 VS_API int vs_ctx_timer_start(vs_ctx *ctx);
 VS_API int vs_ctx_timer_stop(vs_ctx *ctx, float *ms_out);

@@ -112,8 +112,17 @@ def test_flat_search_parity(vs, oracle, d, n):
         assert (f32_bits(sims[i]) == f32_bits(want_sims)).all()
 
 
-def test_search_adversarial_rows_take_literal_path(vs, oracle):
-    """Rows whose float32 rounding cannot be certified must be resolved with reference arithmetic."""
+@pytest.fixture
+def force_literal(vs):
+    """Every certification fails -> all scores are resolved by the literal reference-arithmetic paths."""
+    vs.compute.debug_set_certify_scale(1.0e7)
+    yield
+    vs.compute.debug_set_certify_scale(1.0)
+
+
+def test_search_literal_path(vs, oracle, force_literal):
+    """Rows whose float32 rounding cannot be certified must be resolved with reference arithmetic: with the
+    certification disabled (test hook) the search must still return the oracle's bits."""
     d, n, C = 768, 3000, 6
     rng = np.random.default_rng(5)
     rows = noop_rows(n, d, 5)
@@ -131,6 +140,36 @@ def test_search_adversarial_rows_take_literal_path(vs, oracle):
         want_ids, want_sims = oracle.search(q, cent, rows, lists, doc, 3, 10)
         assert ids[i, :counts[i]].tolist() == want_ids.tolist()
         assert (f32_bits(sims[i, :counts[i]]) == f32_bits(want_sims)).all()
+    ctx.close()
+
+
+def test_search_literal_path_unit_rows(vs, oracle, force_literal):
+    n, d, C = 6000, 768, 24
+    rows, cent, lists, doc = _index_inputs(oracle, n, d, C, 15, docs_per=2)
+    ctx = vs.compute.Context()
+    ix = vs.ivf.Index.build_assigned(rows, doc, lists, cent, ctx=ctx)
+    qs = oracle.quantize_matrix_f32(unit_rows(4, d, 77))
+    ids, sims, counts = ix.Search(qs, 5, 12, ctx=ctx)
+    assert ctx.slowpath_count() > 0
+    for i, q in enumerate(qs):
+        want_ids, want_sims = oracle.search(q, cent, rows, lists, doc, 5, 12)
+        assert ids[i, :counts[i]].tolist() == want_ids.tolist()
+        assert (f32_bits(sims[i, :counts[i]]) == f32_bits(want_sims)).all()
+    ctx.close()
+
+
+def test_cosine_and_argmax_literal_path(vs, oracle, force_literal):
+    d, n, m = 768, 1500, 7
+    rows = oracle.quantize_matrix_f32(unit_rows(n, d, 3))
+    cent = oracle.quantize_matrix_f32(unit_rows(m, d, 4))
+    ctx = vs.compute.Context()
+    M = vs.compute.NewMatrix(rows, ctx=ctx)
+    got = vs.compute.NewVector(cent[0]).MatrixCosineSimilarity(M, ctx=ctx)
+    assert (f32_bits(got) == f32_bits(oracle.cosine_1xN(cent[0], rows))).all()
+    sims, idx = vs.compute.NewMatrix(cent, ctx=ctx).MatrixCosineSimilarity(M, ctx=ctx)
+    want_sims, want_idx = oracle.argmax_MxN(cent, rows)
+    assert (idx == want_idx).all()
+    assert ctx.slowpath_count() >= n
     ctx.close()
 
 
