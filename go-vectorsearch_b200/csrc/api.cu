@@ -204,6 +204,7 @@ extern "C" int vs_debug_set_certify_scale(float scale) {
     cudaDeviceSynchronize();
     CU(vs::scan_set_certify_scale(scale));
     CU(vs::argmax_set_certify_scale(scale));
+    CU(vs::gemm_set_certify_scale(scale));
     return VS_OK;
 }
 
@@ -1121,6 +1122,127 @@ extern "C" int vs_search_flat(vs_ctx *c, const vs_matrix *m, const uint64_t *d_d
     ix.n = m->n;
     ix.C = 1;
     return vs_search(c, &ix, queries, nq, 1, k, ids_out, sims_out, counts_out);
+}
+
+// ------------------------------------------------------------------------------------------------
+// query batches as a tensor-core GEMM (gemm.cu)
+static int gemm_search_core(vs_ctx *c, Arena &a, const vs_index *ix, const MatView &qv, size_t k, const SearchSetup &s,
+                            const GemmPlan &pl, uint64_t *d_ids, float *d_sims, int32_t *d_counts, uint32_t *d_status,
+                            uint64_t *stats) {
+    const size_t nq = qv.n;
+    GemmBufs gb;
+    gemm_take(a.take<char>(gemm_scratch_bytes(pl, nq)), pl, nq, &gb);
+    const MatView rows = ix->data->view();
+    CU(gemm_enqueue_filter(rows, qv, pl, gb, d_status, g_sm_count, c->stream, &c->launches));
+    VS(pinned_reserve(c, nq * 4 + 64));
+    uint32_t *h_status = static_cast<uint32_t *>(c->pinned);
+    unsigned int *h_count = reinterpret_cast<unsigned int *>(h_status + nq);
+    CU(cudaMemcpyAsync(h_count, gb.bounds + 4, sizeof(unsigned int), cudaMemcpyDeviceToHost, c->stream));
+    CU(cudaStreamSynchronize(c->stream));
+    const unsigned int cand = *h_count;
+    std::vector<uint32_t> sel;
+    if (cand > pl.cand_cap) {  // thresholds too loose for the candidate list: the scan answers everything
+        for (size_t i = 0; i < nq; i++) sel.push_back((uint32_t)i);
+    } else {
+        CU(gemm_enqueue_select(rows, ix->doc_ids, ix->id_base, qv, pl, gb, cand, (int)k, d_ids, d_sims, d_counts, d_status,
+                               c->d_fix_counter, c->stream, &c->launches));
+        CU(cudaMemcpyAsync(h_status, d_status, nq * 4, cudaMemcpyDeviceToHost, c->stream));
+        CU(cudaStreamSynchronize(c->stream));
+        for (size_t i = 0; i < nq; i++)
+            if (h_status[i] & kStatusNeedMore) sel.push_back((uint32_t)i);
+    }
+    if (stats) {
+        stats[0] = cand;
+        stats[1] = sel.size();
+        stats[2] = pl.tiles;
+        stats[3] = pl.sample_tiles;
+    }
+    if (sel.empty()) return VS_OK;
+    // queries the filter could not answer (unusable header, fewer than k documents above the threshold, overflow):
+    // the streaming scan, then its own literal-arithmetic resolve where needed
+    CU(cudaMemcpyAsync(s.b.q_select, sel.data(), sel.size() * 4, cudaMemcpyHostToDevice, c->stream));
+    VS(search_enqueue(c, ix, qv, sel.size(), s.b.q_select, s.npe, k, s.kpl1, s.kpl2, true, false, s.b, d_ids, d_sims, d_counts,
+                      d_status, nullptr, false));
+    CU(cudaMemcpyAsync(h_status, d_status, nq * 4, cudaMemcpyDeviceToHost, c->stream));
+    CU(cudaStreamSynchronize(c->stream));
+    for (size_t i = 0; i < nq; i++) h_status[i] &= (kStatusProbeAmbiguous | kStatusListAmbiguous);
+    bool any = false;
+    for (uint32_t i : sel) any |= h_status[i] != 0;
+    if (any) {
+        std::vector<uint32_t> hs(nq, 0u);
+        for (uint32_t i : sel) hs[i] = h_status[i];
+        VS(search_resolve_flagged(c, ix, qv, nq, hs.data(), s, k, d_ids, d_sims, d_counts, d_status, nullptr, false, nullptr));
+    }
+    return VS_OK;
+}
+
+static int gemm_check(vs_ctx *c, const vs_matrix *m, size_t nq, size_t d, size_t k) {
+    VS(need_dev());
+    if (!c || !m) return fail(VS_EINVAL, "null argument");
+    if (nq == 0 || k == 0) return fail(VS_EINVAL, "nq == 0 or k == 0");
+    if ((size_t)m->d != d) return fail(VS_EDIM, "vector/matrix column size does not match: %zu != %d", d, m->d);
+    if (!gemm_supported(m->view(), nq))
+        return fail(VS_ERANGE, "batched GEMM search needs d <= 1024 and at most %d queries per call", kMaxStageQueries);
+    return VS_OK;
+}
+
+extern "C" int vs_search_batch_dev(vs_ctx *c, const vs_matrix *m, const uint64_t *d_doc_ids, uint64_t id_base,
+                                   const vs_matrix *queries, size_t k, uint64_t *d_ids, float *d_sims, int32_t *d_counts,
+                                   uint64_t *stats_out) {
+    if (!queries || !d_ids || !d_sims || !d_counts) return fail(VS_EINVAL, "null argument");
+    VS(gemm_check(c, m, queries->n, (size_t)queries->d, k));
+    const size_t nq = queries->n;
+    vs_index ix;
+    ix.data = const_cast<vs_matrix *>(m);
+    ix.doc_ids = const_cast<uint64_t *>(d_doc_ids);
+    ix.id_base = id_base;
+    ix.n = m->n;
+    ix.C = 1;
+    const GemmPlan pl = gemm_plan(m->view(), nq, k, d_doc_ids == nullptr, g_sm_count);
+    Arena a(c);
+    SearchSetup s;
+    VS(search_setup(c, a, &ix, nq, 1, k, gemm_scratch_bytes(pl, nq) + Arena::pad(nq * 4) + 4096, &s));
+    search_take(a, &ix, nq, &s);
+    uint32_t *d_status = a.take<uint32_t>(nq);
+    const int rc = gemm_search_core(c, a, &ix, queries->view(), k, s, pl, d_ids, d_sims, d_counts, d_status, stats_out);
+    ix.data = nullptr;
+    return rc;
+}
+
+extern "C" int vs_search_flat_gemm(vs_ctx *c, const vs_matrix *m, const uint64_t *d_doc_ids, const uint8_t *queries, size_t nq,
+                                   size_t k, uint64_t *ids_out, float *sims_out, int32_t *counts_out) {
+    if (!queries || !ids_out || !sims_out || !counts_out) return fail(VS_EINVAL, "null argument");
+    VS(gemm_check(c, m, nq, m ? (size_t)m->d : 0, k));
+    vs_index ix;
+    ix.data = const_cast<vs_matrix *>(m);
+    ix.doc_ids = const_cast<uint64_t *>(d_doc_ids);
+    ix.n = m->n;
+    ix.C = 1;
+    const size_t row_bytes = 8 + (size_t)m->d;
+    const GemmPlan pl = gemm_plan(m->view(), nq, k, d_doc_ids == nullptr, g_sm_count);
+    Arena a(c);
+    SearchSetup s;
+    const size_t out_bytes = Arena::pad(nq * k * 8) + Arena::pad(nq * k * 4) + 2 * Arena::pad(nq * 4) + 4096;
+    VS(search_setup(c, a, &ix, nq, 1, k, gemm_scratch_bytes(pl, nq) + temp_matrix_bytes(nq, row_bytes) + out_bytes, &s));
+    MatView qv;
+    int rc = temp_matrix(c, a, queries, nq, row_bytes, &qv);
+    if (rc == VS_OK) {
+        search_take(a, &ix, nq, &s);
+        uint64_t *d_ids = a.take<uint64_t>(nq * k);
+        float *d_sims = a.take<float>(nq * k);
+        int32_t *d_counts = a.take<int32_t>(nq);
+        uint32_t *d_status = a.take<uint32_t>(nq);
+        rc = gemm_search_core(c, a, &ix, qv, k, s, pl, d_ids, d_sims, d_counts, d_status, nullptr);
+        if (rc == VS_OK) {
+            cudaMemcpyAsync(ids_out, d_ids, nq * k * 8, cudaMemcpyDeviceToHost, c->stream);
+            cudaMemcpyAsync(sims_out, d_sims, nq * k * 4, cudaMemcpyDeviceToHost, c->stream);
+            cudaMemcpyAsync(counts_out, d_counts, nq * 4, cudaMemcpyDeviceToHost, c->stream);
+            const cudaError_t e = cudaStreamSynchronize(c->stream);
+            if (e != cudaSuccess) rc = fail(VS_ECUDA, "batched search: %s", cudaGetErrorString(e));
+        }
+    }
+    ix.data = nullptr;
+    return rc;
 }
 
 extern "C" int vs_topk_merge_dev(vs_ctx *c, const uint64_t *d_ids_in, const float *d_sims_in, const int32_t *d_counts_in,

@@ -1,0 +1,833 @@
+// gemm.cu -- query batches as an int8 tensor-core GEMM (tcgen05.mma kind::i8, u8 x u8 -> s32 in TMEM) with a fused
+// per-pair filter, for sm_100a.  Replaces, for nq queries at once, the loop of 1xN scans the reference runs per query
+// (server/search.go:241-273 -> compute/cosine.go:13-57) when the list is the whole store (BASELINE config 3).
+//
+// The score matrix [nq x n] is never written.  The only term of the cosine identity (common.cuh) that couples a
+// query and a row is the integer dot product sum(q*v); the tensor cores produce it exactly, and the epilogue turns
+// "cos(q, v) >= tau_q" into "dot >= T(q, v)" with three FMAs per pair (T is a sum of three per-query x per-row
+// products, see GemmRowConst / the column constants).  Pairs that pass are appended to a candidate list and finished
+// by select_kernel with the certified float64 score of common.cuh (and literal reference arithmetic where the
+// float32 rounding cannot be certified), so the emitted float32 similarities and ids are the reference's bits.
+//
+// tau_q comes from a pre-pass of the same GEMM over a strided sample of the store (MODE_GROUPMAX): the r-th largest of
+// the per-32-row-group maxima is a lower bound of the r-th best score.  The result of a query is accepted only if k
+// distinct documents at or above tau_q were found (then nothing outside the candidate list can belong to the top k);
+// otherwise the query is flagged and the caller finishes it with the streaming scan.  Correctness therefore never
+// depends on how good tau_q is -- only the amount of work does.
+//
+// Kernel structure (one CTA per SM, 384 threads):
+//   warp 0      TMA producer: the 128-row store tile (K chunks of 128 bytes, SWIZZLE_128B) stays resident in shared
+//               memory while every 128-query tile is streamed through a ring of 16 KB stages; per-tile column
+//               constants arrive by cp.async.bulk.
+//   warp 1      one thread issues tcgen05.mma.cta_group::1.kind::i8 (M=128 store rows, N=128 queries, K=32 per
+//               instruction); tcgen05.commit releases smem stages and publishes accumulators.
+//   warp 2      TMEM allocation (4 accumulator stages x 128 columns = 512 columns).
+//   warps 4-11  epilogue: tcgen05.ld 32x32b, one store row per thread, 64 query columns per warp.
+#include <cuda.h>
+#include <cuda_runtime.h>
+#include <math.h>
+#include <stdint.h>
+
+#include <cub/device/device_radix_sort.cuh>
+
+#include "internal.h"
+
+namespace vs {
+namespace {
+
+constexpr int kTM = 128;                 // store rows per tile (TMEM lanes)
+constexpr int kTN = 128;                 // queries per tile (accumulator columns)
+constexpr int kChunkK = 128;             // K bytes per shared-memory chunk (one 128-byte swizzle atom)
+constexpr int kChunkBytes = kTM * kChunkK;  // 16 KB
+constexpr int kAccStages = 4;
+constexpr int kEpiWarps = 8;
+constexpr int kGemmThreads = (4 + kEpiWarps) * 32;
+constexpr int kMaxKC = 8;                // d_pad <= 1024
+constexpr int kMaxStages = 8;
+
+constexpr int MODE_GROUPMAX = 0;
+constexpr int MODE_FILTER = 1;
+
+struct GemmParams {
+    const float2 *row_hdr;
+    const uint2 *row_sums;
+    uint32_t n;                // store rows
+    int D;
+    int kc;                    // K chunks per row
+    int nstages;               // streamed-operand stages
+    uint32_t tile_first, tile_stride, tile_count;  // store tiles of this launch: tile_first + i * tile_stride
+    uint32_t nq_tiles;         // query tiles
+    const float4 *col_consts;  // [nq_tiles * 128]
+    // MODE_FILTER
+    unsigned int *cand_count;
+    uint32_t *cand_q;
+    uint2 *cand_rowdot;
+    unsigned int cand_cap;
+    // MODE_GROUPMAX
+    float *gmax;               // [nq_pad][G]
+    uint32_t G;
+};
+
+// ---- PTX wrappers -------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint32_t bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
+    uint32_t done;
+    long long t0 = 0;
+    do {
+        asm volatile(
+            "{\n\t.reg .pred p;\n\t"
+            "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+            "selp.u32 %0, 1, 0, p;\n\t}"
+            : "=r"(done)
+            : "r"(bar), "r"(parity)
+            : "memory");
+        if (!done) {  // a broken pipeline must fault, not hang the device: ~5 s at 2 GHz
+            const long long now = clock64();
+            if (t0 == 0) t0 = now;
+            else if (now - t0 > 10000000000ll) __trap();
+        }
+    } while (!done);
+}
+__device__ __forceinline__ void tma_load_2d(uint32_t dst, const CUtensorMap *tm, int c0, int c1, uint32_t bar) {
+    asm volatile(
+        "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3}], [%4];" ::"r"(dst),
+        "l"(tm), "r"(c0), "r"(c1), "r"(bar)
+        : "memory");
+}
+__device__ __forceinline__ void bulk_load_1d(uint32_t dst, const void *src, uint32_t bytes, uint32_t bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(dst), "l"(src),
+                 "r"(bytes), "r"(bar)
+                 : "memory");
+}
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_commit(uint32_t bar) {
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
+}
+// D[tmem] (+)= A[smem] * B[smem]^T, u8 x u8 -> s32
+__device__ __forceinline__ void tc_mma_i8(uint32_t d_tmem, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::i8 [%0], %1, %2, %3, p;\n\t}" ::"r"(d_tmem),
+        "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
+        : "memory");
+}
+__device__ __forceinline__ void tc_ld32(uint32_t taddr, uint32_t (&v)[32]) {
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+        "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+        "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+        : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]), "=r"(v[8]),
+          "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15]), "=r"(v[16]),
+          "=r"(v[17]), "=r"(v[18]), "=r"(v[19]), "=r"(v[20]), "=r"(v[21]), "=r"(v[22]), "=r"(v[23]), "=r"(v[24]),
+          "=r"(v[25]), "=r"(v[26]), "=r"(v[27]), "=r"(v[28]), "=r"(v[29]), "=r"(v[30]), "=r"(v[31])
+        : "r"(taddr)
+        : "memory");
+}
+__device__ __forceinline__ void tc_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+
+// Shared-memory matrix descriptor of a K-major [rows][128 B] SWIZZLE_128B tile (8-row groups 1024 B apart);
+// kbytes = offset of this instruction's 32-byte K slice inside the 128-byte swizzle atom.
+__device__ __forceinline__ uint64_t umma_desc_sw128(uint32_t tile_smem_addr, uint32_t kbytes) {
+    const uint64_t start = ((tile_smem_addr + kbytes) & 0x3FFFFu) >> 4;
+    return start | (1ull << 16) /* LBO (unused with swizzle) */ | (64ull << 32) /* SBO = 1024 B */ | (1ull << 46) /* version */ |
+           (2ull << 61) /* SWIZZLE_128B */;
+}
+// Instruction descriptor, kind::i8: D = s32, A = B = unsigned 8-bit, both K-major, M = 128, N = 128.
+constexpr uint32_t kIdesc = (2u << 4) | (0u << 7) | (0u << 10) | ((uint32_t)(kTN >> 3) << 17) | ((uint32_t)(kTM >> 4) << 24);
+
+__device__ __forceinline__ int f32_ordered(float f) {
+    const int b = __float_as_int(f);
+    return b >= 0 ? b : (b ^ 0x7FFFFFFF);
+}
+__device__ __forceinline__ float ordered_f32(int k) { return __int_as_float(k >= 0 ? k : (k ^ 0x7FFFFFFF)); }
+
+// Per-store-row side of the filter.  With (b, b') the row header, S = b' - b, uy = 255*D*b + S*sum(v),
+// Py = S^2*(D*sum(v^2) - sum(v)^2) + uy^2  (= 255^2 * D * |y|^2):
+//   bp = sqrt(Py)/S,  cp = uy/S,  Bp = 255*D*b/S.
+// A row whose header makes the identity unusable (S <= 0, non-finite, Py <= 0) gets Bp = +inf: it passes every
+// filter (the certified score decides) and is left out of the group maxima.
+struct GemmRowConst {
+    float bp, cp, Bp, inv_bp;
+    int usable;
+};
+__device__ __forceinline__ GemmRowConst gemm_row_const(float mn, float mx, uint32_t s1, uint32_t s2, int D, bool in_range) {
+    GemmRowConst r;
+    const double b = (double)mn, S = (double)mx - b;
+    const double uy = (double)D * 255.0 * b + S * (double)s1;
+    const long long I = (long long)D * (long long)s2 - (long long)s1 * (long long)s1;
+    const double P = S * S * (double)I + uy * uy;
+    const bool ok = in_range && (S > 0.0) && (P > 0.0) && (P < 1.0e300) && (S < 1.0e300);
+    if (ok) {
+        const double sp = sqrt(P);
+        r.bp = (float)(sp / S);
+        r.cp = (float)(uy / S);
+        r.Bp = (float)((double)D * 255.0 * b / S);
+        r.inv_bp = (float)(S / sp);
+        r.usable = 1;
+    } else {
+        r.bp = 0.0f;
+        r.cp = 0.0f;
+        r.Bp = in_range ? __int_as_float(0x7F800000) : __int_as_float(0xFF800000);  // +inf: always passes; -inf: never
+        r.inv_bp = 0.0f;
+        r.usable = 0;
+    }
+    return r;
+}
+
+template <int MODE>
+__global__ void __launch_bounds__(kGemmThreads, 1)
+gemm_kernel(const __grid_constant__ CUtensorMap tm_rows, const __grid_constant__ CUtensorMap tm_queries, const GemmParams p) {
+    extern __shared__ uint8_t smem_raw[];
+    const uint32_t raw = smem_u32(smem_raw);
+    const uint32_t base = (raw + 1023u) & ~1023u;  // SWIZZLE_128B tiles need 1024-byte alignment
+    uint8_t *sm = smem_raw + (base - raw);
+    const int kc = p.kc, ns = p.nstages;
+    const uint32_t sA = base;
+    const uint32_t sB = sA + (uint32_t)kc * kChunkBytes;
+    const uint32_t sQ = sB + (uint32_t)ns * kChunkBytes;
+    const uint32_t sBar = sQ + kAccStages * kTN * 16;
+    float4 *q_consts = reinterpret_cast<float4 *>(sm + (sQ - base));
+    // barrier slots
+    const uint32_t a_full = sBar, a_empty = a_full + 8 * kMaxKC, b_full = a_empty + 8 * kMaxKC, b_empty = b_full + 8 * kMaxStages,
+                   acc_full = b_empty + 8 * kMaxStages, acc_empty = acc_full + 8 * kAccStages, q_full = acc_empty + 8 * kAccStages;
+    volatile uint32_t *tmem_slot = reinterpret_cast<volatile uint32_t *>(sm + (q_full + 8 * kAccStages - base));
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+
+    if (warp == 0 && lane == 0) {
+        asm volatile("prefetch.tensormap [%0];" ::"l"(&tm_rows) : "memory");
+        asm volatile("prefetch.tensormap [%0];" ::"l"(&tm_queries) : "memory");
+    }
+    if (warp == 1 && lane == 0) {
+        for (int i = 0; i < kc; i++) {
+            mbar_init(a_full + 8 * i, 1);
+            mbar_init(a_empty + 8 * i, 1);
+        }
+        for (int i = 0; i < ns; i++) {
+            mbar_init(b_full + 8 * i, 1);
+            mbar_init(b_empty + 8 * i, 1);
+        }
+        for (int i = 0; i < kAccStages; i++) {
+            mbar_init(acc_full + 8 * i, 1);
+            mbar_init(acc_empty + 8 * i, kEpiWarps);
+            mbar_init(q_full + 8 * i, 1);
+        }
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    if (warp == 2) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32((const void *)tmem_slot)),
+                     "r"(kAccStages * kTN)
+                     : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+
+    const uint32_t nqt = p.nq_tiles;
+
+    if (warp == 0) {
+        if (lane == 0) {
+            // ===== TMA producer =====
+            uint32_t it = 0, bit = 0, li = 0;
+            for (uint32_t i = blockIdx.x; i < p.tile_count; i += gridDim.x, li++) {
+                const int row0 = (int)((p.tile_first + i * p.tile_stride) * kTM);
+                for (int c = 0; c < kc; c++) {
+                    mbar_wait(a_empty + 8 * c, (li & 1) ^ 1);
+                    mbar_expect_tx(a_full + 8 * c, kChunkBytes);
+                    tma_load_2d(sA + c * kChunkBytes, &tm_rows, c * kChunkK, row0, a_full + 8 * c);
+                }
+                for (uint32_t qt = 0; qt < nqt; qt++, it++) {
+                    const uint32_t s = it % kAccStages, ph = (it / kAccStages) & 1;
+                    mbar_wait(acc_empty + 8 * s, ph ^ 1);  // the epilogue has finished with this stage's constants
+                    mbar_expect_tx(q_full + 8 * s, kTN * 16);
+                    bulk_load_1d(sQ + s * kTN * 16, p.col_consts + (size_t)qt * kTN, kTN * 16, q_full + 8 * s);
+                    for (int c = 0; c < kc; c++, bit++) {
+                        const uint32_t st = bit % ns, bph = (bit / ns) & 1;
+                        mbar_wait(b_empty + 8 * st, bph ^ 1);
+                        mbar_expect_tx(b_full + 8 * st, kChunkBytes);
+                        tma_load_2d(sB + st * kChunkBytes, &tm_queries, c * kChunkK, (int)(qt * kTN), b_full + 8 * st);
+                    }
+                }
+            }
+        }
+    } else if (warp == 1) {
+        if (lane == 0) {
+            // ===== MMA issuer =====
+            uint32_t it = 0, bit = 0, li = 0;
+            for (uint32_t i = blockIdx.x; i < p.tile_count; i += gridDim.x, li++) {
+                for (uint32_t qt = 0; qt < nqt; qt++, it++) {
+                    const uint32_t s = it % kAccStages, ph = (it / kAccStages) & 1;
+                    mbar_wait(acc_empty + 8 * s, ph ^ 1);
+                    tc_fence_after();
+                    const uint32_t d_tmem = tmem_base + s * kTN;
+                    for (int c = 0; c < kc; c++, bit++) {
+                        const uint32_t st = bit % ns, bph = (bit / ns) & 1;
+                        if (qt == 0) mbar_wait(a_full + 8 * c, li & 1);
+                        mbar_wait(b_full + 8 * st, bph);
+                        tc_fence_after();
+#pragma unroll
+                        for (int k = 0; k < kChunkK / 32; k++) {
+                            tc_mma_i8(d_tmem, umma_desc_sw128(sA + c * kChunkBytes, k * 32), umma_desc_sw128(sB + st * kChunkBytes, k * 32),
+                                      kIdesc, (c | k) != 0 ? 1u : 0u);
+                        }
+                        tc_commit(b_empty + 8 * st);
+                        if (qt == nqt - 1) tc_commit(a_empty + 8 * c);
+                    }
+                    tc_commit(acc_full + 8 * s);
+                }
+            }
+        }
+    } else if (warp >= 4) {
+        // ===== epilogue =====
+        const int e = warp - 4;
+        const int qd = e & 3;   // TMEM lane quadrant this warp may read
+        const int half = e >> 2;  // which 64 query columns
+        uint32_t it = 0;
+        for (uint32_t i = blockIdx.x; i < p.tile_count; i += gridDim.x) {
+            const uint32_t tile = p.tile_first + i * p.tile_stride;
+            const uint32_t row = tile * kTM + qd * 32 + lane;
+            const bool in_range = row < p.n;
+            float2 h = make_float2(0.f, 0.f);
+            uint2 sm2 = make_uint2(0u, 0u);
+            if (in_range) {
+                h = p.row_hdr[row];
+                sm2 = p.row_sums[row];
+            }
+            const GemmRowConst rc = gemm_row_const(h.x, h.y, sm2.x, sm2.y, p.D, in_range);
+            for (uint32_t qt = 0; qt < nqt; qt++, it++) {
+                const uint32_t s = it % kAccStages, ph = (it / kAccStages) & 1;
+                mbar_wait(q_full + 8 * s, ph);
+                mbar_wait(acc_full + 8 * s, ph);
+                tc_fence_after();
+                const float4 *qc = q_consts + s * kTN + half * 64;
+                const uint32_t taddr = tmem_base + ((uint32_t)(qd * 32) << 16) + s * kTN + half * 64;
+#pragma unroll 1
+                for (int cb = 0; cb < 2; cb++) {
+                    uint32_t v[32];
+                    tc_ld32(taddr + cb * 32, v);
+                    tc_ld_wait();
+                    if constexpr (MODE == MODE_FILTER) {
+#pragma unroll
+                        for (int j = 0; j < 32; j++) {
+                            const float4 c4 = qc[cb * 32 + j];  // (tau', -A', -e', -m): warp-uniform address, broadcast
+                            const float T = fmaf(c4.x, rc.bp, fmaf(c4.y, rc.cp, fmaf(c4.z, rc.Bp, c4.w)));
+                            if ((float)v[j] >= T) {
+                                const unsigned int pos = atomicAdd(p.cand_count, 1u);
+                                if (pos < p.cand_cap) {
+                                    p.cand_q[pos] = qt * kTN + half * 64 + cb * 32 + j;
+                                    p.cand_rowdot[pos] = make_uint2(row, v[j]);
+                                }
+                            }
+                        }
+                    } else {
+                        int keep = (int)0x80000000;
+#pragma unroll
+                        for (int j = 0; j < 32; j++) {
+                            const float4 c4 = qc[cb * 32 + j];  // (aq, A', e', -)
+                            float sc = fmaf(c4.y, rc.cp, fmaf(c4.z, rc.Bp, (float)v[j])) * (c4.x * rc.inv_bp);
+                            if (!rc.usable || !(sc == sc)) sc = __int_as_float(0xFF800000);
+                            const int mx = __reduce_max_sync(0xFFFFFFFFu, f32_ordered(sc));
+                            if (lane == j) keep = mx;
+                        }
+                        const uint32_t q = qt * kTN + half * 64 + cb * 32 + lane;
+                        p.gmax[(size_t)q * p.G + (size_t)i * 4 + qd] = ordered_f32(keep);
+                    }
+                }
+                tc_fence_before();
+                __syncwarp();
+                if (lane == 0) mbar_arrive(acc_empty + 8 * s);
+            }
+        }
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 2) {
+        tc_fence_after();
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(kAccStages * kTN) : "memory");
+    }
+}
+
+// ---- per-matrix bounds: max over usable rows of |bp|, |cp|, |Bp| (for the filter margin) ----------------------
+__global__ void row_bounds_kernel(const float2 *hdr, const uint2 *sums, uint32_t n, int D, unsigned int *bounds) {
+    float mb = 0.f, mc = 0.f, mB = 0.f;
+    for (uint32_t r = blockIdx.x * blockDim.x + threadIdx.x; r < n; r += gridDim.x * blockDim.x) {
+        const float2 h = hdr[r];
+        const uint2 s = sums[r];
+        const GemmRowConst rc = gemm_row_const(h.x, h.y, s.x, s.y, D, true);
+        if (rc.usable) {
+            mb = fmaxf(mb, fabsf(rc.bp));
+            mc = fmaxf(mc, fabsf(rc.cp));
+            mB = fmaxf(mB, fabsf(rc.Bp));
+        }
+    }
+    for (int o = 16; o; o >>= 1) {
+        mb = fmaxf(mb, __shfl_xor_sync(0xFFFFFFFFu, mb, o));
+        mc = fmaxf(mc, __shfl_xor_sync(0xFFFFFFFFu, mc, o));
+        mB = fmaxf(mB, __shfl_xor_sync(0xFFFFFFFFu, mB, o));
+    }
+    if ((threadIdx.x & 31) == 0) {  // non-negative floats order like their bit patterns
+        atomicMax(bounds + 0, __float_as_uint(mb));
+        atomicMax(bounds + 1, __float_as_uint(mc));
+        atomicMax(bounds + 2, __float_as_uint(mB));
+    }
+}
+
+// ---- per-query side ------------------------------------------------------------------------------------------
+// With (a, a') the query header, R = a' - a, ux = 255*D*a + R*sum(q), Px = R^2*(D*sum(q^2) - sum(q)^2) + ux^2:
+//   aq = R*D/sqrt(Px)   (cos = aq * (1/bp) * (dot - T0)),   Ap = 255*a/R,   ep = sum(q)/D
+//   cos >= tau  <=>  dot >= T = tau/aq * bp - Ap * cp - ep * Bp
+struct QuerySide {
+    double aq, Ap, ep;
+    int usable;
+};
+__device__ __forceinline__ QuerySide query_side(float mn, float mx, uint32_t s1, uint32_t s2, int D) {
+    QuerySide q;
+    const double a = (double)mn, R = (double)mx - a;
+    const double ux = (double)D * 255.0 * a + R * (double)s1;
+    const long long I = (long long)D * (long long)s2 - (long long)s1 * (long long)s1;
+    const double P = R * R * (double)I + ux * ux;
+    q.usable = (R > 0.0) && (P > 0.0) && (P < 1.0e300) && (R < 1.0e300) && (s1 > 0u);
+    if (q.usable) {
+        q.aq = R * (double)D / sqrt(P);
+        q.Ap = 255.0 * a / R;
+        q.ep = (double)s1 / (double)D;
+    } else {
+        q.aq = q.Ap = q.ep = 0.0;
+    }
+    return q;
+}
+
+// Column constants of the pre-pass: (aq, A', e', 0); padding / unusable queries score -inf everywhere (aq = NaN).
+__global__ void query_consts_groupmax_kernel(MatView queries, uint32_t nq_pad, float4 *out) {
+    const uint32_t q = blockIdx.x * blockDim.x + threadIdx.x;
+    if (q >= nq_pad) return;
+    float4 o = make_float4(__int_as_float(0x7FC00000), 0.f, 0.f, 0.f);
+    if (q < queries.n) {
+        const float2 h = queries.hdr[q];
+        const uint2 s = queries.sums[q];
+        const QuerySide qs = query_side(h.x, h.y, s.x, s.y, queries.d);
+        if (qs.usable) o = make_float4((float)qs.aq, (float)qs.Ap, (float)qs.ep, 0.f);
+    }
+    out[q] = o;
+}
+
+// One block per query: tau = (r-th largest group maximum) - slack; writes the filter's column constants
+// (tau', -A', -e', -m), tau itself, and flags unusable queries for the streaming-scan fallback.
+constexpr int kThrThreads = 128;
+__global__ void __launch_bounds__(kThrThreads)
+threshold_kernel(MatView queries, uint32_t nq_pad, const float *gmax, uint32_t G, uint32_t r, const unsigned int *bounds,
+                 float4 *col_consts, float *tau_out, uint32_t *status) {
+    extern __shared__ int s_keys[];
+    __shared__ unsigned int s_cnt;
+    const uint32_t q = blockIdx.x;
+    const float ninf = __int_as_float(0xFF800000), pinf = __int_as_float(0x7F800000);
+    if (q >= queries.n) {  // padding columns never pass
+        if (threadIdx.x == 0) col_consts[q] = make_float4(0.f, 0.f, 0.f, pinf);
+        return;
+    }
+    for (uint32_t g = threadIdx.x; g < G; g += kThrThreads) s_keys[g] = f32_ordered(gmax[(size_t)q * G + g]);
+    __syncthreads();
+    // r-th largest key by bisection over the ordered-int domain (largest x with count(key >= x) >= r)
+    long long lo = (long long)(int)0x80000000, hi = 0x7FFFFFFFll;
+    while (lo < hi) {
+        const long long mid = lo + (hi - lo + 1) / 2;
+        if (threadIdx.x == 0) s_cnt = 0;
+        __syncthreads();
+        unsigned int c = 0;
+        for (uint32_t g = threadIdx.x; g < G; g += kThrThreads) c += (long long)s_keys[g] >= mid;
+        for (int o = 16; o; o >>= 1) c += __shfl_xor_sync(0xFFFFFFFFu, c, o);
+        if ((threadIdx.x & 31) == 0 && c) atomicAdd(&s_cnt, c);
+        __syncthreads();
+        if (s_cnt >= r) lo = mid;
+        else hi = mid - 1;
+        __syncthreads();
+    }
+    if (threadIdx.x != 0) return;
+    float kth = ordered_f32((int)lo);
+    if (G < r || !(kth == kth)) kth = ninf;
+    const float2 h = queries.hdr[q];
+    const uint2 s = queries.sums[q];
+    const QuerySide qs = query_side(h.x, h.y, s.x, s.y, queries.d);
+    if (!qs.usable) {
+        col_consts[q] = make_float4(0.f, 0.f, 0.f, pinf);
+        tau_out[q] = pinf;
+        status[q] = kStatusNeedMore;
+        return;
+    }
+    status[q] = 0;
+    // the group maxima are float32 evaluations: back off by more than their error
+    const float tau = (kth == ninf) ? ninf : kth - 2.0e-5f * fmaxf(1.0f, fabsf(kth));
+    tau_out[q] = tau;
+    if (tau == ninf) {  // not enough groups: everything passes (small stores); -e' keeps out-of-range rows out
+        col_consts[q] = make_float4(0.f, 0.f, (float)(-qs.ep), ninf);
+        return;
+    }
+    const double tp = (double)tau / qs.aq;
+    const double Bmax = (double)__uint_as_float(bounds[0]), Cmax = (double)__uint_as_float(bounds[1]),
+                 BBmax = (double)__uint_as_float(bounds[2]);
+    // float32 evaluation error of T (coefficient roundings, three FMAs, int->float of the dot) plus the float32
+    // rounding of the reference's own score: < 2^-20 of the term magnitudes + a few units
+    const double m = ldexp(fabs(tp) * Bmax + fabs(qs.Ap) * Cmax + fabs(qs.ep) * BBmax, -20) + 16.0;
+    col_consts[q] = make_float4((float)tp, (float)(-qs.Ap), (float)(-qs.ep), (float)(-m));
+}
+
+// ---- candidate resolution -------------------------------------------------------------------------------------
+__global__ void segment_offsets_kernel(const uint32_t *sorted_q, unsigned int count, uint32_t nq, uint32_t *seg_off) {
+    const uint32_t q = blockIdx.x * blockDim.x + threadIdx.x;
+    if (q > nq) return;
+    unsigned int lo = 0, hi = count;  // first index with sorted_q[idx] >= q
+    while (lo < hi) {
+        const unsigned int mid = (lo + hi) >> 1;
+        if (sorted_q[mid] < q) lo = mid + 1;
+        else hi = mid;
+    }
+    seg_off[q] = lo;
+}
+
+constexpr int kSelThreads = 256;
+constexpr int kSelCap = 4096;  // candidates per query held in shared memory
+
+struct SelEntry {
+    uint32_t key;   // f32_to_key of the float32 similarity; 0 = removed
+    uint32_t row;   // bit31 = float32 rounding not certified yet
+    uint64_t id;
+};
+
+// One block per query: certified scores of its candidates, literal re-score where needed, then k rounds of
+// "best remaining (similarity desc, id asc), drop every other entry of that document" (search.go:256-270).
+__global__ void __launch_bounds__(kSelThreads)
+select_kernel(MatView rows, const uint64_t *ids, uint64_t id_base, MatView queries, const uint32_t *seg_off, const uint2 *cand_rowdot,
+              const float *tau, int k, uint64_t *out_ids, float *out_sims, int32_t *out_counts, uint32_t *status,
+              unsigned long long *fix_counter) {
+    extern __shared__ __align__(16) unsigned char sel_smem[];
+    SelEntry *ent = reinterpret_cast<SelEntry *>(sel_smem);
+    double *sh_qn = reinterpret_cast<double *>(sel_smem + sizeof(SelEntry) * kSelCap);
+    __shared__ SideConst s_side;
+    __shared__ double s_norm;
+    __shared__ int s_any_flag;
+    __shared__ uint32_t s_wkey[kSelThreads / 32];
+    __shared__ uint64_t s_wid[kSelThreads / 32];
+    __shared__ int s_widx[kSelThreads / 32];
+    __shared__ int s_best;
+
+    const uint32_t q = blockIdx.x;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int D = rows.d, d_pad = rows.d_pad;
+    if (status[q] & kStatusNeedMore) return;  // unusable query: the caller's fallback answers it
+    const uint32_t c0 = seg_off[q], c1 = seg_off[q + 1];
+    const uint32_t cnt = c1 - c0;
+    if (cnt > (uint32_t)kSelCap) {
+        if (threadIdx.x == 0) status[q] = kStatusNeedMore;
+        return;
+    }
+    if (threadIdx.x == 0) {
+        const float2 h = queries.hdr[q];
+        const uint2 s = queries.sums[q];
+        s_side = make_side(h.x, h.y, s.x, s.y, D);
+        s_any_flag = 0;
+    }
+    __syncthreads();
+    const SideConst xq = s_side;
+    for (uint32_t e = threadIdx.x; e < cnt; e += kSelThreads) {
+        const uint2 rd = cand_rowdot[c0 + e];
+        const float2 h = rows.hdr[rd.x];
+        const uint2 s = rows.sums[rd.x];
+        bool flag;
+        const float sim = score_fast(xq, h.x, h.y, s.x, s.y, rd.y, D, &flag);
+        ent[e].key = f32_to_key(sim);
+        ent[e].row = rd.x | (flag ? kFlagBit : 0u);
+        ent[e].id = ids ? ids[rd.x] : id_base + rd.x;
+        if (flag) s_any_flag = 1;
+    }
+    __syncthreads();
+    if (s_any_flag) {
+        // literal path: normalizeVector of the query (compute/cosine.go:26,138-149), then each flagged row
+        const uint8_t *qc = queries.codes + (size_t)q * queries.d_pad;
+        const float2 qh = queries.hdr[q];
+        const double mn = (double)qh.x, range = __dsub_rn((double)qh.y, (double)qh.x);
+        for (int i = threadIdx.x; i < D; i += kSelThreads) sh_qn[i] = ref_dequant_f64(qc[i], mn, range);
+        __syncthreads();
+        if (warp == 0) {
+            const double nsq = warp_ordered_sum(D, lane, [&](int i) { return __dmul_rn(sh_qn[i], sh_qn[i]); });
+            if (lane == 0) s_norm = __dsqrt_rn(nsq);
+        }
+        __syncthreads();
+        const double norm = s_norm;
+        if (norm != 0.0)
+            for (int i = threadIdx.x; i < D; i += kSelThreads) sh_qn[i] = __ddiv_rn(sh_qn[i], norm);
+        __syncthreads();
+        for (uint32_t e = warp; e < cnt; e += kSelThreads / 32) {
+            const uint32_t r = ent[e].row;
+            if (r & kFlagBit) {
+                const uint32_t row = r & ~kFlagBit;
+                const float2 h = rows.hdr[row];
+                const double dot = warp_ref_cosine_row_f64(rows.codes + (size_t)row * d_pad, h.x, h.y, sh_qn, D, lane);
+                if (lane == 0) {
+                    ent[e].key = f32_to_key(__double2float_rn(dot));
+                    ent[e].row = row;
+                    if (fix_counter) atomicAdd(fix_counter, 1ull);
+                }
+            }
+        }
+        __syncthreads();
+    }
+    const uint32_t tau_key = f32_to_key(tau[q]);
+    int emitted = 0, emitted_above = 0;
+    for (int round = 0; round < k; round++) {
+        uint32_t bk = 0;
+        uint64_t bid = kEmptyId;
+        int bidx = -1;
+        for (uint32_t e = threadIdx.x; e < cnt; e += kSelThreads) {
+            const uint32_t ek = ent[e].key;
+            if (ek != 0 && (bidx < 0 || cand_better(ek, ent[e].id, bk, bid))) {
+                bk = ek;
+                bid = ent[e].id;
+                bidx = (int)e;
+            }
+        }
+        for (int o = 16; o; o >>= 1) {
+            const uint32_t ok = __shfl_xor_sync(0xFFFFFFFFu, bk, o);
+            const uint64_t oid = __shfl_xor_sync(0xFFFFFFFFu, bid, o);
+            const int oidx = __shfl_xor_sync(0xFFFFFFFFu, bidx, o);
+            if (oidx >= 0 && (bidx < 0 || cand_better(ok, oid, bk, bid) || (ok == bk && oid == bid && oidx < bidx))) {
+                bk = ok;
+                bid = oid;
+                bidx = oidx;
+            }
+        }
+        if (lane == 0) {
+            s_wkey[warp] = bk;
+            s_wid[warp] = bid;
+            s_widx[warp] = bidx;
+        }
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            int best = -1;
+            uint32_t k0 = 0;
+            uint64_t i0 = kEmptyId;
+            for (int w = 0; w < kSelThreads / 32; w++) {
+                if (s_widx[w] >= 0 && (best < 0 || cand_better(s_wkey[w], s_wid[w], k0, i0) ||
+                                       (s_wkey[w] == k0 && s_wid[w] == i0 && s_widx[w] < best))) {
+                    best = s_widx[w];
+                    k0 = s_wkey[w];
+                    i0 = s_wid[w];
+                }
+            }
+            s_best = best;
+            if (best >= 0) {
+                out_ids[(size_t)q * k + round] = i0;
+                out_sims[(size_t)q * k + round] = key_to_f32(k0);
+            }
+        }
+        __syncthreads();
+        const int best = s_best;
+        if (best < 0) break;
+        const uint64_t win_id = ent[best].id;
+        const uint32_t win_key = ent[best].key;
+        emitted++;
+        if (win_key >= tau_key && win_key != 1u) emitted_above++;
+        __syncthreads();
+        for (uint32_t e = threadIdx.x; e < cnt; e += kSelThreads)
+            if (ent[e].id == win_id) ent[e].key = 0;  // one hit per document
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) {
+        out_counts[q] = emitted;
+        // complete only if k distinct documents at or above tau were found: then no row outside the candidate
+        // list (all of which score below tau) can belong to the top k
+        if (emitted_above < k) status[q] = kStatusNeedMore;
+    }
+}
+
+typedef CUresult (*EncodeTiledFn)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *, const cuuint64_t *, const cuuint64_t *,
+                                  const cuuint32_t *, const cuuint32_t *, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+EncodeTiledFn encode_fn() {
+    static EncodeTiledFn fn = nullptr;
+    if (fn) return fn;
+    void *p = nullptr;
+    cudaDriverEntryPointQueryResult qres;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &qres) != cudaSuccess ||
+        qres != cudaDriverEntryPointSuccess)
+        return nullptr;
+    fn = reinterpret_cast<EncodeTiledFn>(p);
+    return fn;
+}
+
+// [n][d_pad] uint8 codes, box = 128 rows x 128 bytes, SWIZZLE_128B; out-of-range rows / columns read as zero.
+bool make_codes_map(CUtensorMap *tm, const MatView &m) {
+    EncodeTiledFn fn = encode_fn();
+    if (!fn) return false;
+    cuuint64_t dims[2] = {(cuuint64_t)m.d_pad, (cuuint64_t)m.n};
+    cuuint64_t strides[1] = {(cuuint64_t)m.d_pad};
+    cuuint32_t box[2] = {(cuuint32_t)kChunkK, (cuuint32_t)kTM};
+    cuuint32_t estr[2] = {1, 1};
+    return fn(tm, CU_TENSOR_MAP_DATA_TYPE_UINT8, 2, const_cast<uint8_t *>(m.codes), dims, strides, box, estr,
+              CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+              CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
+}
+
+size_t gemm_smem_bytes(int kc, int ns) {
+    return 1024 + (size_t)(kc + ns) * kChunkBytes + kAccStages * kTN * 16 + 8 * (2 * kMaxKC + 2 * kMaxStages + 3 * kAccStages) + 64;
+}
+
+}  // namespace
+
+bool gemm_supported(const MatView &rows, size_t nq) {
+    return rows.d_pad <= kMaxKC * kChunkK && rows.n >= 1 && rows.n < 0x7FFFFF00ull && nq >= 1 && nq <= (size_t)kMaxStageQueries &&
+           (reinterpret_cast<uintptr_t>(rows.codes) & 15) == 0;
+}
+
+GemmPlan gemm_plan(const MatView &rows, size_t nq, size_t k, bool unique_ids, int sm_count) {
+    GemmPlan pl{};
+    pl.nq_pad = (uint32_t)((nq + kTN - 1) / kTN * kTN);
+    pl.tiles = (uint32_t)((rows.n + kTM - 1) / kTM);
+    pl.rank = (uint32_t)(unique_ids ? k : 2 * k);
+    // sample about 1/64 of the store, at least 4 groups per wanted rank and one tile per SM, at most all of it
+    uint32_t want = pl.tiles / 64;
+    if (want < pl.rank) want = pl.rank;
+    if (want < (uint32_t)sm_count) want = (uint32_t)sm_count;
+    if (want > pl.tiles) want = pl.tiles;
+    pl.sample_stride = pl.tiles / want;
+    if (pl.sample_stride < 1) pl.sample_stride = 1;
+    pl.sample_tiles = (pl.tiles + pl.sample_stride - 1) / pl.sample_stride;
+    pl.G = pl.sample_tiles * 4;
+    size_t cap = nq * (size_t)4096;
+    if (cap < (1u << 20)) cap = 1u << 20;
+    if (cap > (64u << 20)) cap = 64u << 20;
+    pl.cand_cap = (unsigned int)cap;
+    size_t sort_tmp = 0;
+    cub::DeviceRadixSort::SortPairs(nullptr, sort_tmp, (const uint32_t *)nullptr, (uint32_t *)nullptr, (const uint2 *)nullptr,
+                                    (uint2 *)nullptr, (int64_t)cap, 0, 13);
+    pl.sort_tmp_bytes = sort_tmp;
+    return pl;
+}
+
+size_t gemm_scratch_bytes(const GemmPlan &pl, size_t nq) {
+    auto pad = [](size_t b) { return (b + 255) & ~size_t(255); };
+    return pad((size_t)pl.nq_pad * 16) + pad((size_t)pl.nq_pad * pl.G * 4) + pad(nq * 4) + pad(64) + pad((nq + 2) * 4) +
+           2 * pad((size_t)pl.cand_cap * 4) + 2 * pad((size_t)pl.cand_cap * 8) + pad(pl.sort_tmp_bytes) + 4096;
+}
+
+void gemm_take(char *base, const GemmPlan &pl, size_t nq, GemmBufs *b) {
+    size_t off = 0;
+    auto take = [&](size_t bytes) {
+        off = (off + 255) & ~size_t(255);
+        char *p = base + off;
+        off += bytes;
+        return p;
+    };
+    b->col_consts = reinterpret_cast<float4 *>(take((size_t)pl.nq_pad * 16));
+    b->gmax = reinterpret_cast<float *>(take((size_t)pl.nq_pad * pl.G * 4));
+    b->tau = reinterpret_cast<float *>(take(nq * 4));
+    b->bounds = reinterpret_cast<unsigned int *>(take(64));  // [0..2] bounds, [4] candidate count
+    b->seg_off = reinterpret_cast<uint32_t *>(take((nq + 2) * 4));
+    b->cand_q = reinterpret_cast<uint32_t *>(take((size_t)pl.cand_cap * 4));
+    b->cand_q_sorted = reinterpret_cast<uint32_t *>(take((size_t)pl.cand_cap * 4));
+    b->cand_rowdot = reinterpret_cast<uint2 *>(take((size_t)pl.cand_cap * 8));
+    b->cand_rowdot_sorted = reinterpret_cast<uint2 *>(take((size_t)pl.cand_cap * 8));
+    b->sort_tmp = take(pl.sort_tmp_bytes);
+}
+
+static cudaError_t launch_gemm(int mode, const CUtensorMap &tm_rows, const CUtensorMap &tm_q, const GemmParams &p, int sm_count,
+                               cudaStream_t st) {
+    const size_t smem = gemm_smem_bytes(p.kc, p.nstages);
+    unsigned grid = p.tile_count < (uint32_t)sm_count ? p.tile_count : (unsigned)sm_count;
+    if (grid == 0) return cudaSuccess;
+    cudaError_t e;
+    if (mode == MODE_FILTER) {
+        e = cudaFuncSetAttribute(gemm_kernel<MODE_FILTER>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (e != cudaSuccess) return e;
+        gemm_kernel<MODE_FILTER><<<grid, kGemmThreads, smem, st>>>(tm_rows, tm_q, p);
+    } else {
+        e = cudaFuncSetAttribute(gemm_kernel<MODE_GROUPMAX>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (e != cudaSuccess) return e;
+        gemm_kernel<MODE_GROUPMAX><<<grid, kGemmThreads, smem, st>>>(tm_rows, tm_q, p);
+    }
+    return cudaGetLastError();
+}
+
+// Phase 1: thresholds from the sampled pre-pass, then the filtering GEMM over the whole store.  Asynchronous; the
+// candidate count lands in b.bounds[4].
+cudaError_t gemm_enqueue_filter(const MatView &rows, const MatView &queries, const GemmPlan &pl, const GemmBufs &b, uint32_t *d_status,
+                                int sm_count, cudaStream_t st, uint64_t *launches) {
+    CUtensorMap tm_rows, tm_q;
+    if (!make_codes_map(&tm_rows, rows) || !make_codes_map(&tm_q, queries)) return cudaErrorNotSupported;
+    const uint32_t nq = (uint32_t)queries.n;
+    cudaError_t e = cudaMemsetAsync(b.bounds, 0, 64, st);
+    if (e != cudaSuccess) return e;
+    row_bounds_kernel<<<sm_count * 4, 256, 0, st>>>(rows.hdr, rows.sums, (uint32_t)rows.n, rows.d, b.bounds);
+    query_consts_groupmax_kernel<<<(pl.nq_pad + 127) / 128, 128, 0, st>>>(queries, pl.nq_pad, b.col_consts);
+    GemmParams p{};
+    p.row_hdr = rows.hdr;
+    p.row_sums = rows.sums;
+    p.n = (uint32_t)rows.n;
+    p.D = rows.d;
+    p.kc = (rows.d_pad + kChunkK - 1) / kChunkK;
+    p.nstages = 13 - p.kc < 6 ? 13 - p.kc : 6;  // (kc + stages) * 16 KB + 10 KB <= 227 KB
+    p.nq_tiles = pl.nq_pad / kTN;
+    p.col_consts = b.col_consts;
+    p.cand_count = b.bounds + 4;
+    p.cand_q = b.cand_q;
+    p.cand_rowdot = b.cand_rowdot;
+    p.cand_cap = pl.cand_cap;
+    p.gmax = b.gmax;
+    p.G = pl.G;
+    p.tile_first = 0;
+    p.tile_stride = pl.sample_stride;
+    p.tile_count = pl.sample_tiles;
+    e = launch_gemm(MODE_GROUPMAX, tm_rows, tm_q, p, sm_count, st);
+    if (e != cudaSuccess) return e;
+    threshold_kernel<<<pl.nq_pad, kThrThreads, pl.G * sizeof(int), st>>>(queries, pl.nq_pad, b.gmax, pl.G, pl.rank, b.bounds,
+                                                                         b.col_consts, b.tau, d_status);
+    p.tile_first = 0;
+    p.tile_stride = 1;
+    p.tile_count = pl.tiles;
+    e = launch_gemm(MODE_FILTER, tm_rows, tm_q, p, sm_count, st);
+    if (e != cudaSuccess) return e;
+    (void)nq;
+    if (launches) *launches += 5;
+    return cudaGetLastError();
+}
+
+// Phase 2 (after the host has read the candidate count): group the candidates by query, finish them.
+cudaError_t gemm_enqueue_select(const MatView &rows, const uint64_t *ids, uint64_t id_base, const MatView &queries, const GemmPlan &pl,
+                                const GemmBufs &b, unsigned int cand_count, int k, uint64_t *d_ids, float *d_sims, int32_t *d_counts,
+                                uint32_t *d_status, unsigned long long *fix_counter, cudaStream_t st, uint64_t *launches) {
+    const uint32_t nq = (uint32_t)queries.n;
+    size_t tmp = pl.sort_tmp_bytes;
+    int bits = 1;
+    while ((1u << bits) < nq + 1 && bits < 13) bits++;
+    cudaError_t e = cudaSuccess;
+    if (cand_count)
+        e = cub::DeviceRadixSort::SortPairs(b.sort_tmp, tmp, b.cand_q, b.cand_q_sorted, b.cand_rowdot, b.cand_rowdot_sorted,
+                                            (int64_t)cand_count, 0, bits, st);
+    if (e != cudaSuccess) return e;
+    segment_offsets_kernel<<<(nq + 1 + 127) / 128, 128, 0, st>>>(b.cand_q_sorted, cand_count, nq, b.seg_off);
+    const size_t smem = sizeof(SelEntry) * kSelCap + (size_t)rows.d * 8;
+    e = cudaFuncSetAttribute(select_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return e;
+    select_kernel<<<nq, kSelThreads, smem, st>>>(rows, ids, id_base, queries, b.seg_off, b.cand_rowdot_sorted, b.tau, k, d_ids, d_sims,
+                                                 d_counts, d_status, fix_counter);
+    if (launches) *launches += cand_count ? 4 : 2;
+    return cudaGetLastError();
+}
+
+cudaError_t gemm_set_certify_scale(float scale) { return cudaMemcpyToSymbol(c_certify_scale, &scale, sizeof(float)); }
+
+}  // namespace vs

@@ -149,6 +149,31 @@ def SearchFlat(matrix, queries, k, ctx=None):
     return ids, sims, counts
 
 
+def SearchFlatBatch(matrix, queries, k, doc_ids_dev=None, ctx=None):
+    """Query batch over the whole store as a tensor-core GEMM (BASELINE config 3); same contract and bits as
+    SearchFlat. doc_ids_dev: optional device pointer (int) to uint64 document ids per row."""
+    ctx = ctx or default_context()
+    q = _rows_array(queries if np.asarray(queries).ndim == 2 else np.asarray(queries, np.uint8)[None, :])
+    nq = q.shape[0]
+    ids = np.zeros((nq, k), np.uint64)
+    sims = np.zeros((nq, k), np.float32)
+    counts = np.zeros(nq, np.int32)
+    dp = C.c_void_p(int(doc_ids_dev)) if doc_ids_dev else None
+    _check(matrix._L.vs_search_flat_gemm(ctx.handle, matrix.handle, dp, _p(q), nq, int(k), _p(ids), _p(sims), _p(counts)))
+    return ids, sims, counts
+
+
+def SearchBatchDev(matrix, queries_matrix, k, d_ids, d_sims, d_counts, doc_ids_dev=None, id_base=0, ctx=None):
+    """Device-resident form: results stay in device buffers (raw pointers). Returns the stats tuple
+    (candidates, queries finished by the scan, store tiles, sampled tiles)."""
+    ctx = ctx or default_context()
+    stats = np.zeros(4, np.uint64)
+    vp = lambda x: C.c_void_p(int(x)) if x else None
+    _check(matrix._L.vs_search_batch_dev(ctx.handle, matrix.handle, vp(doc_ids_dev), int(id_base), queries_matrix.handle, int(k),
+                                         vp(d_ids), vp(d_sims), vp(d_counts), _p(stats)))
+    return tuple(int(x) for x in stats)
+
+
 def TopKMergeDev(d_ids_in, d_sims_in, d_counts_in, G, nq, k, d_ids_out, d_sims_out, d_counts_out, ctx=None):
     """Merge G gathered shard-local hit lists per query ([G][nq][k] device arrays) into the global top-k."""
     L = _lib.init()

@@ -157,6 +157,18 @@ VS_API int vs_search(vs_ctx *ctx, const vs_index *ix, const uint8_t *queries_pac
 /* Brute force over a matrix (BASELINE config 1): same contract, ids = doc_ids[row] or row index. */
 VS_API int vs_search_flat(vs_ctx *ctx, const vs_matrix *m, const uint64_t *d_doc_ids, const uint8_t *queries_packed,
                    size_t nq, size_t k, uint64_t *ids_out, float *sims_out, int32_t *counts_out);
+/* Query batches over the whole store as an int8 tensor-core GEMM (tcgen05.mma kind::i8) with a fused per-pair
+ * filter (BASELINE config 3): the loop of per-query scans of search.go:241-273 for nq queries at once.  Same
+ * contract and the same bits as vs_search_flat.  d <= 1024, nq <= 4096, k <= 128.  Queries the filter cannot
+ * answer (degenerate header, fewer than k documents above its threshold) are finished by the streaming scan. */
+VS_API int vs_search_flat_gemm(vs_ctx *ctx, const vs_matrix *m, const uint64_t *d_doc_ids, const uint8_t *queries_packed,
+                        size_t nq, size_t k, uint64_t *ids_out, float *sims_out, int32_t *counts_out);
+/* Device-resident form: queries are a device matrix, results stay in device buffers (d_ids[nq*k], d_sims[nq*k],
+ * d_counts[nq]); ids = d_doc_ids[row] or id_base + row.  Synchronizes the ctx stream internally (candidate count).
+ * stats_out (nullable, host uint64[4]): candidates emitted, queries finished by the scan, store tiles, sampled tiles. */
+VS_API int vs_search_batch_dev(vs_ctx *ctx, const vs_matrix *m, const uint64_t *d_doc_ids, uint64_t id_base,
+                        const vs_matrix *queries, size_t k, uint64_t *d_ids, float *d_sims, int32_t *d_counts,
+                        uint64_t *stats_out);
 /* Device-resident search: queries already a device matrix; results stay in device buffers
  * (d_ids[nq*k], d_sims[nq*k], d_counts[nq], d_status[nq]); asynchronous on the ctx stream.
  * d_status bit0/bit1 = a float32 rounding could not be certified in the probe/list stage, bit2 =
