@@ -121,6 +121,8 @@ extern "C" void vs_ctx_destroy(vs_ctx *c) {
     if (c->d_tickets) cudaFree(c->d_tickets);
     if (c->d_trace) cudaFree(c->d_trace);
     for (cudaEvent_t e : c->prof_events) cudaEventDestroy(e);
+    for (cudaEvent_t e : c->phase_ev)
+        if (e) cudaEventDestroy(e);
     cudaEventDestroy(c->ev0);
     cudaEventDestroy(c->ev1);
     if (c->owns_stream) cudaStreamDestroy(c->stream);
@@ -1133,7 +1135,21 @@ static int gemm_search_core(vs_ctx *c, Arena &a, const vs_index *ix, const MatVi
     GemmBufs gb;
     gemm_take(a.take<char>(gemm_scratch_bytes(pl, nq)), pl, nq, &gb);
     const MatView rows = ix->data->view();
-    CU(gemm_enqueue_filter(rows, qv, pl, gb, d_status, g_sm_count, c->stream, &c->launches));
+    auto phase = [&](int i) -> cudaError_t {
+        if (!stats) return cudaSuccess;
+        if (!c->phase_ev[i]) {
+            const cudaError_t e = cudaEventCreate(&c->phase_ev[i]);
+            if (e != cudaSuccess) return e;
+        }
+        return cudaEventRecord(c->phase_ev[i], c->stream);
+    };
+    CU(phase(0));
+    CU(gemm_enqueue_prepass(rows, qv, pl, gb, d_status, g_sm_count, c->stream, &c->launches));
+    CU(phase(1));
+    VS(prof_mark(c));
+    CU(gemm_enqueue_filter(rows, qv, pl, gb, g_sm_count, c->stream, &c->launches));
+    VS(prof_mark(c));
+    CU(phase(2));
     VS(pinned_reserve(c, nq * 4 + 64));
     uint32_t *h_status = static_cast<uint32_t *>(c->pinned);
     unsigned int *h_count = reinterpret_cast<unsigned int *>(h_status + nq);
@@ -1151,11 +1167,18 @@ static int gemm_search_core(vs_ctx *c, Arena &a, const vs_index *ix, const MatVi
         for (size_t i = 0; i < nq; i++)
             if (h_status[i] & kStatusNeedMore) sel.push_back((uint32_t)i);
     }
+    CU(phase(3));
     if (stats) {
+        CU(cudaEventSynchronize(c->phase_ev[3]));
         stats[0] = cand;
         stats[1] = sel.size();
         stats[2] = pl.tiles;
         stats[3] = pl.sample_tiles;
+        for (int i = 0; i < 3; i++) {  // microseconds: pre-pass, filtering GEMM, candidate resolution
+            float ms = 0.f;
+            CU(cudaEventElapsedTime(&ms, c->phase_ev[i], c->phase_ev[i + 1]));
+            stats[4 + i] = (uint64_t)(ms * 1000.0f);
+        }
     }
     if (sel.empty()) return VS_OK;
     // queries the filter could not answer (unusable header, fewer than k documents above the threshold, overflow):

@@ -27,6 +27,7 @@
 #include <cuda_runtime.h>
 #include <math.h>
 #include <stdint.h>
+#include <stdlib.h>
 
 #include <cub/device/device_radix_sort.cuh>
 
@@ -36,10 +37,15 @@ namespace vs {
 namespace {
 
 constexpr int kTM = 128;                 // store rows per tile (TMEM lanes)
-constexpr int kTN = 128;                 // queries per tile (accumulator columns)
+#ifndef VS_GEMM_TN
+#define VS_GEMM_TN 256
+#endif
+constexpr int kTN = VS_GEMM_TN;          // queries per tile (accumulator columns)
 constexpr int kChunkK = 128;             // K bytes per shared-memory chunk (one 128-byte swizzle atom)
-constexpr int kChunkBytes = kTM * kChunkK;  // 16 KB
-constexpr int kAccStages = 4;
+constexpr int kChunkBytes = kTM * kChunkK;  // 16 KB: one K chunk of the resident store tile
+constexpr int kStageBytes = kTN * kChunkK;  // one K chunk of a streamed query tile
+constexpr int kAccStages = 512 / kTN;    // TMEM accumulator stages (512 columns in all)
+constexpr int kColsPerWarp = kTN / 2;    // the two epilogue warps of a lane quadrant split the columns
 constexpr int kEpiWarps = 8;
 constexpr int kGemmThreads = (4 + kEpiWarps) * 32;
 constexpr int kMaxKC = 8;                // d_pad <= 1024
@@ -66,6 +72,7 @@ struct GemmParams {
     // MODE_GROUPMAX
     float *gmax;               // [nq_pad][G]
     uint32_t G;
+    int dbg;                   // profiling aid (VS_GEMM_DBG): 1 = epilogue skips the filter math, 2 = also skips tcgen05.ld
 };
 
 // ---- PTX wrappers -------------------------------------------------------------------------------
@@ -108,6 +115,15 @@ __device__ __forceinline__ void bulk_load_1d(uint32_t dst, const void *src, uint
     asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(dst), "l"(src),
                  "r"(bytes), "r"(bar)
                  : "memory");
+}
+__device__ __forceinline__ bool elect_one() {  // one lane of a converged warp
+    uint32_t pred;
+    asm volatile(
+        "{\n\t.reg .pred P1;\n\t"
+        "elect.sync _|P1, 0xFFFFFFFF;\n\t"
+        "selp.u32 %0, 1, 0, P1;\n\t}"
+        : "=r"(pred));
+    return pred != 0;
 }
 __device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
@@ -196,7 +212,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tm_rows, const __grid_constant__
     const int kc = p.kc, ns = p.nstages;
     const uint32_t sA = base;
     const uint32_t sB = sA + (uint32_t)kc * kChunkBytes;
-    const uint32_t sQ = sB + (uint32_t)ns * kChunkBytes;
+    const uint32_t sQ = sB + (uint32_t)ns * kStageBytes;
     const uint32_t sBar = sQ + kAccStages * kTN * 16;
     float4 *q_consts = reinterpret_cast<float4 *>(sm + (sQ - base));
     // barrier slots
@@ -239,64 +255,89 @@ gemm_kernel(const __grid_constant__ CUtensorMap tm_rows, const __grid_constant__
 
     const uint32_t nqt = p.nq_tiles;
 
+    // Every role loop is executed by its whole warp (waits are warp-convergent); the single-thread instructions
+    // (TMA, tcgen05.mma, tcgen05.commit) are issued by one elected lane.  Ring positions are advanced
+    // incrementally: no division on the issue path.
     if (warp == 0) {
-        if (lane == 0) {
-            // ===== TMA producer =====
-            uint32_t it = 0, bit = 0, li = 0;
-            for (uint32_t i = blockIdx.x; i < p.tile_count; i += gridDim.x, li++) {
-                const int row0 = (int)((p.tile_first + i * p.tile_stride) * kTM);
-                for (int c = 0; c < kc; c++) {
-                    mbar_wait(a_empty + 8 * c, (li & 1) ^ 1);
+        // ===== TMA producer =====
+        const bool leader = elect_one();
+        uint32_t acc_s = 0, acc_ph = 0, st = 0, bph = 0, li = 0;
+        for (uint32_t i = blockIdx.x; i < p.tile_count; i += gridDim.x, li++) {
+            const int row0 = (int)((p.tile_first + i * p.tile_stride) * kTM);
+            for (int c = 0; c < kc; c++) {
+                mbar_wait(a_empty + 8 * c, (li & 1) ^ 1);
+                if (leader) {
                     mbar_expect_tx(a_full + 8 * c, kChunkBytes);
                     tma_load_2d(sA + c * kChunkBytes, &tm_rows, c * kChunkK, row0, a_full + 8 * c);
                 }
-                for (uint32_t qt = 0; qt < nqt; qt++, it++) {
-                    const uint32_t s = it % kAccStages, ph = (it / kAccStages) & 1;
-                    mbar_wait(acc_empty + 8 * s, ph ^ 1);  // the epilogue has finished with this stage's constants
-                    mbar_expect_tx(q_full + 8 * s, kTN * 16);
-                    bulk_load_1d(sQ + s * kTN * 16, p.col_consts + (size_t)qt * kTN, kTN * 16, q_full + 8 * s);
-                    for (int c = 0; c < kc; c++, bit++) {
-                        const uint32_t st = bit % ns, bph = (bit / ns) & 1;
-                        mbar_wait(b_empty + 8 * st, bph ^ 1);
-                        mbar_expect_tx(b_full + 8 * st, kChunkBytes);
-                        tma_load_2d(sB + st * kChunkBytes, &tm_queries, c * kChunkK, (int)(qt * kTN), b_full + 8 * st);
+            }
+            for (uint32_t qt = 0; qt < nqt; qt++) {
+                mbar_wait(acc_empty + 8 * acc_s, acc_ph ^ 1);  // the epilogue has finished with this stage's constants
+                if (leader) {
+                    mbar_expect_tx(q_full + 8 * acc_s, kTN * 16);
+                    bulk_load_1d(sQ + acc_s * kTN * 16, p.col_consts + (size_t)qt * kTN, kTN * 16, q_full + 8 * acc_s);
+                }
+                if (++acc_s == kAccStages) {
+                    acc_s = 0;
+                    acc_ph ^= 1;
+                }
+                for (int c = 0; c < kc; c++) {
+                    mbar_wait(b_empty + 8 * st, bph ^ 1);
+                    if (leader) {
+                        mbar_expect_tx(b_full + 8 * st, kStageBytes);
+                        tma_load_2d(sB + st * kStageBytes, &tm_queries, c * kChunkK, (int)(qt * kTN), b_full + 8 * st);
+                    }
+                    if (++st == (uint32_t)ns) {
+                        st = 0;
+                        bph ^= 1;
                     }
                 }
             }
         }
     } else if (warp == 1) {
-        if (lane == 0) {
-            // ===== MMA issuer =====
-            uint32_t it = 0, bit = 0, li = 0;
-            for (uint32_t i = blockIdx.x; i < p.tile_count; i += gridDim.x, li++) {
-                for (uint32_t qt = 0; qt < nqt; qt++, it++) {
-                    const uint32_t s = it % kAccStages, ph = (it / kAccStages) & 1;
-                    mbar_wait(acc_empty + 8 * s, ph ^ 1);
+        // ===== MMA issuer =====
+        const bool leader = elect_one();
+        const uint64_t desc_hi = (64ull << 32) | (1ull << 46) | (2ull << 61);  // SBO = 1024 B, version 1, SWIZZLE_128B
+        const uint64_t a_desc0 = desc_hi | (1ull << 16) | (uint64_t)((sA & 0x3FFFFu) >> 4);
+        const uint64_t b_desc0 = desc_hi | (1ull << 16) | (uint64_t)((sB & 0x3FFFFu) >> 4);
+        uint32_t acc_s = 0, acc_ph = 0, st = 0, bph = 0, li = 0;
+        for (uint32_t i = blockIdx.x; i < p.tile_count; i += gridDim.x, li++) {
+            for (uint32_t qt = 0; qt < nqt; qt++) {
+                mbar_wait(acc_empty + 8 * acc_s, acc_ph ^ 1);
+                tc_fence_after();
+                const uint32_t d_tmem = tmem_base + acc_s * kTN;
+                for (int c = 0; c < kc; c++) {
+                    if (qt == 0) mbar_wait(a_full + 8 * c, li & 1);
+                    mbar_wait(b_full + 8 * st, bph);
                     tc_fence_after();
-                    const uint32_t d_tmem = tmem_base + s * kTN;
-                    for (int c = 0; c < kc; c++, bit++) {
-                        const uint32_t st = bit % ns, bph = (bit / ns) & 1;
-                        if (qt == 0) mbar_wait(a_full + 8 * c, li & 1);
-                        mbar_wait(b_full + 8 * st, bph);
-                        tc_fence_after();
+                    if (leader) {
+                        const uint64_t ad = a_desc0 + (uint64_t)(c * (kChunkBytes >> 4));
+                        const uint64_t bd = b_desc0 + (uint64_t)(st * (kStageBytes >> 4));
 #pragma unroll
-                        for (int k = 0; k < kChunkK / 32; k++) {
-                            tc_mma_i8(d_tmem, umma_desc_sw128(sA + c * kChunkBytes, k * 32), umma_desc_sw128(sB + st * kChunkBytes, k * 32),
-                                      kIdesc, (c | k) != 0 ? 1u : 0u);
-                        }
+                        for (int k = 0; k < kChunkK / 32; k++)  // +32 bytes of K inside the swizzle atom = +2 encoded
+                            tc_mma_i8(d_tmem, ad + 2 * k, bd + 2 * k, kIdesc, (c | k) != 0 ? 1u : 0u);
                         tc_commit(b_empty + 8 * st);
                         if (qt == nqt - 1) tc_commit(a_empty + 8 * c);
+                        if (c == kc - 1) tc_commit(acc_full + 8 * acc_s);
                     }
-                    tc_commit(acc_full + 8 * s);
+                    __syncwarp();
+                    if (++st == (uint32_t)ns) {
+                        st = 0;
+                        bph ^= 1;
+                    }
+                }
+                if (++acc_s == kAccStages) {
+                    acc_s = 0;
+                    acc_ph ^= 1;
                 }
             }
         }
     } else if (warp >= 4) {
         // ===== epilogue =====
         const int e = warp - 4;
-        const int qd = e & 3;   // TMEM lane quadrant this warp may read
-        const int half = e >> 2;  // which 64 query columns
-        uint32_t it = 0;
+        const int qd = e & 3;     // TMEM lane quadrant this warp may read
+        const int half = e >> 2;  // which half of the query columns
+        uint32_t acc_s = 0, acc_ph = 0;
         for (uint32_t i = blockIdx.x; i < p.tile_count; i += gridDim.x) {
             const uint32_t tile = p.tile_first + i * p.tile_stride;
             const uint32_t row = tile * kTM + qd * 32 + lane;
@@ -308,28 +349,42 @@ gemm_kernel(const __grid_constant__ CUtensorMap tm_rows, const __grid_constant__
                 sm2 = p.row_sums[row];
             }
             const GemmRowConst rc = gemm_row_const(h.x, h.y, sm2.x, sm2.y, p.D, in_range);
-            for (uint32_t qt = 0; qt < nqt; qt++, it++) {
-                const uint32_t s = it % kAccStages, ph = (it / kAccStages) & 1;
-                mbar_wait(q_full + 8 * s, ph);
-                mbar_wait(acc_full + 8 * s, ph);
+            for (uint32_t qt = 0; qt < nqt; qt++) {
+                mbar_wait(q_full + 8 * acc_s, acc_ph);
+                mbar_wait(acc_full + 8 * acc_s, acc_ph);
                 tc_fence_after();
-                const float4 *qc = q_consts + s * kTN + half * 64;
-                const uint32_t taddr = tmem_base + ((uint32_t)(qd * 32) << 16) + s * kTN + half * 64;
+                const float4 *qc = q_consts + acc_s * kTN + half * kColsPerWarp;
+                const uint32_t taddr = tmem_base + ((uint32_t)(qd * 32) << 16) + acc_s * kTN + half * kColsPerWarp;
 #pragma unroll 1
-                for (int cb = 0; cb < 2; cb++) {
+                for (int cb = 0; cb < kColsPerWarp / 32; cb++) {
+                    if (p.dbg >= 2) break;
                     uint32_t v[32];
                     tc_ld32(taddr + cb * 32, v);
                     tc_ld_wait();
+                    if (p.dbg == 1) {
+                        if (v[0] == 0xFFFFFFFFu && v[31] == 0xFFFFFFFEu) p.cand_q[0] = 0;
+                        continue;
+                    }
                     if constexpr (MODE == MODE_FILTER) {
+                        // fast path: no side effects, so the 32 broadcast loads and FMA chains overlap freely
+                        bool any = false;
 #pragma unroll
                         for (int j = 0; j < 32; j++) {
                             const float4 c4 = qc[cb * 32 + j];  // (tau', -A', -e', -m): warp-uniform address, broadcast
                             const float T = fmaf(c4.x, rc.bp, fmaf(c4.y, rc.cp, fmaf(c4.z, rc.Bp, c4.w)));
-                            if ((float)v[j] >= T) {
-                                const unsigned int pos = atomicAdd(p.cand_count, 1u);
-                                if (pos < p.cand_cap) {
-                                    p.cand_q[pos] = qt * kTN + half * 64 + cb * 32 + j;
-                                    p.cand_rowdot[pos] = make_uint2(row, v[j]);
+                            any = any || ((float)v[j] >= T);
+                        }
+                        if (__any_sync(0xFFFFFFFFu, any)) {  // rare (a few percent of the 32x32 blocks)
+#pragma unroll
+                            for (int j = 0; j < 32; j++) {
+                                const float4 c4 = qc[cb * 32 + j];
+                                const float T = fmaf(c4.x, rc.bp, fmaf(c4.y, rc.cp, fmaf(c4.z, rc.Bp, c4.w)));
+                                if ((float)v[j] >= T) {
+                                    const unsigned int pos = atomicAdd(p.cand_count, 1u);
+                                    if (pos < p.cand_cap) {
+                                        p.cand_q[pos] = qt * kTN + half * kColsPerWarp + cb * 32 + j;
+                                        p.cand_rowdot[pos] = make_uint2(row, v[j]);
+                                    }
                                 }
                             }
                         }
@@ -343,13 +398,17 @@ gemm_kernel(const __grid_constant__ CUtensorMap tm_rows, const __grid_constant__
                             const int mx = __reduce_max_sync(0xFFFFFFFFu, f32_ordered(sc));
                             if (lane == j) keep = mx;
                         }
-                        const uint32_t q = qt * kTN + half * 64 + cb * 32 + lane;
+                        const uint32_t q = qt * kTN + half * kColsPerWarp + cb * 32 + lane;
                         p.gmax[(size_t)q * p.G + (size_t)i * 4 + qd] = ordered_f32(keep);
                     }
                 }
                 tc_fence_before();
                 __syncwarp();
-                if (lane == 0) mbar_arrive(acc_empty + 8 * s);
+                if (lane == 0) mbar_arrive(acc_empty + 8 * acc_s);
+                if (++acc_s == kAccStages) {
+                    acc_s = 0;
+                    acc_ph ^= 1;
+                }
             }
         }
     }
@@ -670,12 +729,12 @@ EncodeTiledFn encode_fn() {
 }
 
 // [n][d_pad] uint8 codes, box = 128 rows x 128 bytes, SWIZZLE_128B; out-of-range rows / columns read as zero.
-bool make_codes_map(CUtensorMap *tm, const MatView &m) {
+bool make_codes_map(CUtensorMap *tm, const MatView &m, int box_rows) {
     EncodeTiledFn fn = encode_fn();
     if (!fn) return false;
     cuuint64_t dims[2] = {(cuuint64_t)m.d_pad, (cuuint64_t)m.n};
     cuuint64_t strides[1] = {(cuuint64_t)m.d_pad};
-    cuuint32_t box[2] = {(cuuint32_t)kChunkK, (cuuint32_t)kTM};
+    cuuint32_t box[2] = {(cuuint32_t)kChunkK, (cuuint32_t)box_rows};
     cuuint32_t estr[2] = {1, 1};
     return fn(tm, CU_TENSOR_MAP_DATA_TYPE_UINT8, 2, const_cast<uint8_t *>(m.codes), dims, strides, box, estr,
               CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
@@ -683,7 +742,8 @@ bool make_codes_map(CUtensorMap *tm, const MatView &m) {
 }
 
 size_t gemm_smem_bytes(int kc, int ns) {
-    return 1024 + (size_t)(kc + ns) * kChunkBytes + kAccStages * kTN * 16 + 8 * (2 * kMaxKC + 2 * kMaxStages + 3 * kAccStages) + 64;
+    return 1024 + (size_t)kc * kChunkBytes + (size_t)ns * kStageBytes + kAccStages * kTN * 16 +
+           8 * (2 * kMaxKC + 2 * kMaxStages + 3 * kAccStages) + 64;
 }
 
 }  // namespace
@@ -762,24 +822,17 @@ static cudaError_t launch_gemm(int mode, const CUtensorMap &tm_rows, const CUten
     return cudaGetLastError();
 }
 
-// Phase 1: thresholds from the sampled pre-pass, then the filtering GEMM over the whole store.  Asynchronous; the
-// candidate count lands in b.bounds[4].
-cudaError_t gemm_enqueue_filter(const MatView &rows, const MatView &queries, const GemmPlan &pl, const GemmBufs &b, uint32_t *d_status,
-                                int sm_count, cudaStream_t st, uint64_t *launches) {
-    CUtensorMap tm_rows, tm_q;
-    if (!make_codes_map(&tm_rows, rows) || !make_codes_map(&tm_q, queries)) return cudaErrorNotSupported;
-    const uint32_t nq = (uint32_t)queries.n;
-    cudaError_t e = cudaMemsetAsync(b.bounds, 0, 64, st);
-    if (e != cudaSuccess) return e;
-    row_bounds_kernel<<<sm_count * 4, 256, 0, st>>>(rows.hdr, rows.sums, (uint32_t)rows.n, rows.d, b.bounds);
-    query_consts_groupmax_kernel<<<(pl.nq_pad + 127) / 128, 128, 0, st>>>(queries, pl.nq_pad, b.col_consts);
+static GemmParams gemm_params(const MatView &rows, const GemmPlan &pl, const GemmBufs &b) {
     GemmParams p{};
     p.row_hdr = rows.hdr;
     p.row_sums = rows.sums;
     p.n = (uint32_t)rows.n;
     p.D = rows.d;
     p.kc = (rows.d_pad + kChunkK - 1) / kChunkK;
-    p.nstages = 13 - p.kc < 6 ? 13 - p.kc : 6;  // (kc + stages) * 16 KB + 10 KB <= 227 KB
+    {   // kc * 16 KB + stages * kStageBytes + ~10 KB <= 227 KB
+        const int room = (227 * 1024 - 10 * 1024 - p.kc * kChunkBytes) / kStageBytes;
+        p.nstages = room < 6 ? room : 6;
+    }
     p.nq_tiles = pl.nq_pad / kTN;
     p.col_consts = b.col_consts;
     p.cand_count = b.bounds + 4;
@@ -788,6 +841,21 @@ cudaError_t gemm_enqueue_filter(const MatView &rows, const MatView &queries, con
     p.cand_cap = pl.cand_cap;
     p.gmax = b.gmax;
     p.G = pl.G;
+    const char *dbg = getenv("VS_GEMM_DBG");
+    p.dbg = dbg ? atoi(dbg) : 0;
+    return p;
+}
+
+// Phase 1a: thresholds from the sampled pre-pass (same GEMM, group maxima instead of the filter).
+cudaError_t gemm_enqueue_prepass(const MatView &rows, const MatView &queries, const GemmPlan &pl, const GemmBufs &b, uint32_t *d_status,
+                                 int sm_count, cudaStream_t st, uint64_t *launches) {
+    CUtensorMap tm_rows, tm_q;
+    if (!make_codes_map(&tm_rows, rows, kTM) || !make_codes_map(&tm_q, queries, kTN)) return cudaErrorNotSupported;
+    cudaError_t e = cudaMemsetAsync(b.bounds, 0, 64, st);
+    if (e != cudaSuccess) return e;
+    row_bounds_kernel<<<sm_count * 4, 256, 0, st>>>(rows.hdr, rows.sums, (uint32_t)rows.n, rows.d, b.bounds);
+    query_consts_groupmax_kernel<<<(pl.nq_pad + 127) / 128, 128, 0, st>>>(queries, pl.nq_pad, b.col_consts);
+    GemmParams p = gemm_params(rows, pl, b);
     p.tile_first = 0;
     p.tile_stride = pl.sample_stride;
     p.tile_count = pl.sample_tiles;
@@ -795,13 +863,22 @@ cudaError_t gemm_enqueue_filter(const MatView &rows, const MatView &queries, con
     if (e != cudaSuccess) return e;
     threshold_kernel<<<pl.nq_pad, kThrThreads, pl.G * sizeof(int), st>>>(queries, pl.nq_pad, b.gmax, pl.G, pl.rank, b.bounds,
                                                                          b.col_consts, b.tau, d_status);
+    if (launches) *launches += 4;
+    return cudaGetLastError();
+}
+
+// Phase 1b: the filtering GEMM over the whole store.  Asynchronous; the candidate count lands in b.bounds[4].
+cudaError_t gemm_enqueue_filter(const MatView &rows, const MatView &queries, const GemmPlan &pl, const GemmBufs &b, int sm_count,
+                                cudaStream_t st, uint64_t *launches) {
+    CUtensorMap tm_rows, tm_q;
+    if (!make_codes_map(&tm_rows, rows, kTM) || !make_codes_map(&tm_q, queries, kTN)) return cudaErrorNotSupported;
+    GemmParams p = gemm_params(rows, pl, b);
     p.tile_first = 0;
     p.tile_stride = 1;
     p.tile_count = pl.tiles;
-    e = launch_gemm(MODE_FILTER, tm_rows, tm_q, p, sm_count, st);
+    const cudaError_t e = launch_gemm(MODE_FILTER, tm_rows, tm_q, p, sm_count, st);
     if (e != cudaSuccess) return e;
-    (void)nq;
-    if (launches) *launches += 5;
+    if (launches) *launches += 1;
     return cudaGetLastError();
 }
 

@@ -28,6 +28,7 @@ struct vs_ctx {
     bool profile = false;
     std::vector<cudaEvent_t> prof_events;  // pairs (start, stop), recycled
     size_t prof_used = 0;
+    cudaEvent_t phase_ev[6] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};  // batch-search phase boundaries
 };
 
 struct vs_matrix {
@@ -142,8 +143,10 @@ bool gemm_supported(const MatView &rows, size_t nq);
 GemmPlan gemm_plan(const MatView &rows, size_t nq, size_t k, bool unique_ids, int sm_count);
 size_t gemm_scratch_bytes(const GemmPlan &pl, size_t nq);
 void gemm_take(char *base, const GemmPlan &pl, size_t nq, GemmBufs *b);
-cudaError_t gemm_enqueue_filter(const MatView &rows, const MatView &queries, const GemmPlan &pl, const GemmBufs &b, uint32_t *d_status,
-                                int sm_count, cudaStream_t st, uint64_t *launches);
+cudaError_t gemm_enqueue_prepass(const MatView &rows, const MatView &queries, const GemmPlan &pl, const GemmBufs &b, uint32_t *d_status,
+                                 int sm_count, cudaStream_t st, uint64_t *launches);
+cudaError_t gemm_enqueue_filter(const MatView &rows, const MatView &queries, const GemmPlan &pl, const GemmBufs &b, int sm_count,
+                                cudaStream_t st, uint64_t *launches);
 cudaError_t gemm_enqueue_select(const MatView &rows, const uint64_t *ids, uint64_t id_base, const MatView &queries, const GemmPlan &pl,
                                 const GemmBufs &b, unsigned int cand_count, int k, uint64_t *d_ids, float *d_sims, int32_t *d_counts,
                                 uint32_t *d_status, unsigned long long *fix_counter, cudaStream_t st, uint64_t *launches);

@@ -165,9 +165,9 @@ def SearchFlatBatch(matrix, queries, k, doc_ids_dev=None, ctx=None):
 
 def SearchBatchDev(matrix, queries_matrix, k, d_ids, d_sims, d_counts, doc_ids_dev=None, id_base=0, ctx=None):
     """Device-resident form: results stay in device buffers (raw pointers). Returns the stats tuple
-    (candidates, queries finished by the scan, store tiles, sampled tiles)."""
+    (candidates, queries finished by the scan, store tiles, sampled tiles, us pre-pass, us GEMM, us resolution, 0)."""
     ctx = ctx or default_context()
-    stats = np.zeros(4, np.uint64)
+    stats = np.zeros(8, np.uint64)
     vp = lambda x: C.c_void_p(int(x)) if x else None
     _check(matrix._L.vs_search_batch_dev(ctx.handle, matrix.handle, vp(doc_ids_dev), int(id_base), queries_matrix.handle, int(k),
                                          vp(d_ids), vp(d_sims), vp(d_counts), _p(stats)))

@@ -165,7 +165,9 @@ VS_API int vs_search_flat_gemm(vs_ctx *ctx, const vs_matrix *m, const uint64_t *
                         size_t nq, size_t k, uint64_t *ids_out, float *sims_out, int32_t *counts_out);
 /* Device-resident form: queries are a device matrix, results stay in device buffers (d_ids[nq*k], d_sims[nq*k],
  * d_counts[nq]); ids = d_doc_ids[row] or id_base + row.  Synchronizes the ctx stream internally (candidate count).
- * stats_out (nullable, host uint64[4]): candidates emitted, queries finished by the scan, store tiles, sampled tiles. */
+ * stats_out (nullable, host uint64[8]): candidates emitted, queries finished by the scan, store tiles, sampled tiles,
+ * then microseconds of the pre-pass, the filtering GEMM and the candidate resolution (CUDA events); [7] unused.
+ * With vs_ctx_profile_enable the filtering GEMM launch is the kernel vs_ctx_profile_read reports. */
 VS_API int vs_search_batch_dev(vs_ctx *ctx, const vs_matrix *m, const uint64_t *d_doc_ids, uint64_t id_base,
                         const vs_matrix *queries, size_t k, uint64_t *d_ids, float *d_sims, int32_t *d_counts,
                         uint64_t *stats_out);
