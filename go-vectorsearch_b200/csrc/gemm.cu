@@ -10,7 +10,7 @@
 // float32 rounding cannot be certified), so the emitted float32 similarities and ids are the reference's bits.
 //
 // tau_q comes from a pre-pass of the same GEMM over a strided sample of the store (MODE_GROUPMAX): the r-th largest of
-// the per-32-row-group maxima is a lower bound of the r-th best score.  The result of a query is accepted only if k
+// the per-16-row-group maxima is a lower bound of the r-th best score.  The result of a query is accepted only if k
 // distinct documents at or above tau_q were found (then nothing outside the candidate list can belong to the top k);
 // otherwise the query is flagged and the caller finishes it with the streaming scan.  Correctness therefore never
 // depends on how good tau_q is -- only the amount of work does.
@@ -151,6 +151,20 @@ __device__ __forceinline__ void tc_ld32(uint32_t taddr, uint32_t (&v)[32]) {
         : "r"(taddr)
         : "memory");
 }
+// 16 lanes x (8 x 256 bits): thread 4*r + c receives, for n = 0..7, columns 8n + 2c, 8n + 2c + 1 of lane r (registers
+// 4n, 4n + 1) and of lane r + 8 (registers 4n + 2, 4n + 3).
+__device__ __forceinline__ void tc_ld_16x256b_x8(uint32_t taddr, uint32_t (&v)[32]) {
+    asm volatile(
+        "tcgen05.ld.sync.aligned.16x256b.x8.b32 "
+        "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+        "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+        : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]), "=r"(v[8]),
+          "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15]), "=r"(v[16]),
+          "=r"(v[17]), "=r"(v[18]), "=r"(v[19]), "=r"(v[20]), "=r"(v[21]), "=r"(v[22]), "=r"(v[23]), "=r"(v[24]),
+          "=r"(v[25]), "=r"(v[26]), "=r"(v[27]), "=r"(v[28]), "=r"(v[29]), "=r"(v[30]), "=r"(v[31])
+        : "r"(taddr)
+        : "memory");
+}
 __device__ __forceinline__ void tc_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
 
 // Shared-memory matrix descriptor of a K-major [rows][128 B] SWIZZLE_128B tile (8-row groups 1024 B apart);
@@ -162,6 +176,12 @@ __device__ __forceinline__ uint64_t umma_desc_sw128(uint32_t tile_smem_addr, uin
 }
 // Instruction descriptor, kind::i8: D = s32, A = B = unsigned 8-bit, both K-major, M = 128, N = 128.
 constexpr uint32_t kIdesc = (2u << 4) | (0u << 7) | (0u << 10) | ((uint32_t)(kTN >> 3) << 17) | ((uint32_t)(kTM >> 4) << 24);
+
+// The integer dot product as a float without the (slow, XU-pipe) int->float conversion: 2^23 + (dot >> 3), exact
+// because dot < 2^26.  The filter compares it with (T - margin) / 8 + 2^23.
+__device__ __forceinline__ float dot_as_f8(uint32_t dot) { return __uint_as_float(0x4B000000u + (dot >> 3)); }
+// dot rounded down to a multiple of 8, as a float (pre-pass: an approximate score is enough)
+__device__ __forceinline__ float dot_approx(uint32_t dot) { return fmaf(dot_as_f8(dot), 8.0f, -67108864.0f); }
 
 __device__ __forceinline__ int f32_ordered(float f) {
     const int b = __float_as_int(f);
@@ -334,72 +354,126 @@ gemm_kernel(const __grid_constant__ CUtensorMap tm_rows, const __grid_constant__
         }
     } else if (warp >= 4) {
         // ===== epilogue =====
+        // tcgen05.ld 16x256b hands every thread a few query columns of several store rows (the layout of an mma C
+        // fragment: lane = 4*r + c holds columns 8n + 2c, 8n + 2c + 1 of rows r and r + 8), so a thread keeps the
+        // constants of its 16 columns in registers for a whole 64-column pass: 16 shared-memory loads per pass
+        // instead of one per column -- the shared-memory port belongs to the tensor cores and TMA.
         const int e = warp - 4;
         const int qd = e & 3;     // TMEM lane quadrant this warp may read
         const int half = e >> 2;  // which half of the query columns
+        const int tc = lane & 3, tr = lane >> 2;
         uint32_t acc_s = 0, acc_ph = 0;
         for (uint32_t i = blockIdx.x; i < p.tile_count; i += gridDim.x) {
             const uint32_t tile = p.tile_first + i * p.tile_stride;
-            const uint32_t row = tile * kTM + qd * 32 + lane;
-            const bool in_range = row < p.n;
+            const uint32_t row_own = tile * kTM + qd * 32 + lane;
+            const bool in_range = row_own < p.n;
             float2 h = make_float2(0.f, 0.f);
             uint2 sm2 = make_uint2(0u, 0u);
             if (in_range) {
-                h = p.row_hdr[row];
-                sm2 = p.row_sums[row];
+                h = p.row_hdr[row_own];
+                sm2 = p.row_sums[row_own];
             }
-            const GemmRowConst rc = gemm_row_const(h.x, h.y, sm2.x, sm2.y, p.D, in_range);
+            const GemmRowConst own = gemm_row_const(h.x, h.y, sm2.x, sm2.y, p.D, in_range);
+            // this thread's four rows: tr + 8k of the quadrant
+            float r_bp[4], r_cp[4], r_Bp[4], r_ib[4];
+            int r_ok[4];
+#pragma unroll
+            for (int k = 0; k < 4; k++) {
+                r_bp[k] = __shfl_sync(0xFFFFFFFFu, own.bp, tr + 8 * k);
+                r_cp[k] = __shfl_sync(0xFFFFFFFFu, own.cp, tr + 8 * k);
+                r_Bp[k] = __shfl_sync(0xFFFFFFFFu, own.Bp, tr + 8 * k);
+                r_ib[k] = __shfl_sync(0xFFFFFFFFu, own.inv_bp, tr + 8 * k);
+                r_ok[k] = __shfl_sync(0xFFFFFFFFu, own.usable, tr + 8 * k);
+            }
+            const uint32_t row_base = tile * kTM + qd * 32 + tr;
             for (uint32_t qt = 0; qt < nqt; qt++) {
                 mbar_wait(q_full + 8 * acc_s, acc_ph);
                 mbar_wait(acc_full + 8 * acc_s, acc_ph);
                 tc_fence_after();
-                const float4 *qc = q_consts + acc_s * kTN + half * kColsPerWarp;
-                const uint32_t taddr = tmem_base + ((uint32_t)(qd * 32) << 16) + acc_s * kTN + half * kColsPerWarp;
 #pragma unroll 1
-                for (int cb = 0; cb < kColsPerWarp / 32; cb++) {
+                for (int pass = 0; pass < kColsPerWarp / 64; pass++) {
                     if (p.dbg >= 2) break;
-                    uint32_t v[32];
-                    tc_ld32(taddr + cb * 32, v);
-                    tc_ld_wait();
-                    if (p.dbg == 1) {
-                        if (v[0] == 0xFFFFFFFFu && v[31] == 0xFFFFFFFEu) p.cand_q[0] = 0;
-                        continue;
+                    const int colbase = half * kColsPerWarp + pass * 64;
+                    const float4 *qc = q_consts + acc_s * kTN + colbase + 2 * tc;
+                    float4 cc[16];
+#pragma unroll
+                    for (int n = 0; n < 8; n++) {
+                        cc[2 * n] = qc[8 * n];
+                        cc[2 * n + 1] = qc[8 * n + 1];
                     }
-                    if constexpr (MODE == MODE_FILTER) {
-                        // fast path: no side effects, so the 32 broadcast loads and FMA chains overlap freely
-                        bool any = false;
-#pragma unroll
-                        for (int j = 0; j < 32; j++) {
-                            const float4 c4 = qc[cb * 32 + j];  // (tau', -A', -e', -m): warp-uniform address, broadcast
-                            const float T = fmaf(c4.x, rc.bp, fmaf(c4.y, rc.cp, fmaf(c4.z, rc.Bp, c4.w)));
-                            any = any || ((float)v[j] >= T);
+#pragma unroll 1
+                    for (int lh = 0; lh < 2; lh++) {
+                        uint32_t v[32];
+                        tc_ld_16x256b_x8(tmem_base + ((uint32_t)(qd * 32 + lh * 16) << 16) + acc_s * kTN + colbase, v);
+                        tc_ld_wait();
+                        if (p.dbg == 1) {
+                            if (v[0] == 0xFFFFFFFFu && v[31] == 0xFFFFFFFEu) p.cand_q[0] = 0;
+                            continue;
                         }
-                        if (__any_sync(0xFFFFFFFFu, any)) {  // rare (a few percent of the 32x32 blocks)
+                        // registers 4n + {0,1}: row tr + 16 lh, columns 8n + 2 tc + {0,1}; 4n + {2,3}: row + 8
+                        const float bpA = lh ? r_bp[2] : r_bp[0], cpA = lh ? r_cp[2] : r_cp[0], BpA = lh ? r_Bp[2] : r_Bp[0];
+                        const float bpB = lh ? r_bp[3] : r_bp[1], cpB = lh ? r_cp[3] : r_cp[1], BpB = lh ? r_Bp[3] : r_Bp[1];
+                        if constexpr (MODE == MODE_FILTER) {
+                            // four groups of 8 pairs: a side-effect-free test first; the (rare) emission code runs only
+                            // for a group with a hit, and only in the threads that have it
 #pragma unroll
-                            for (int j = 0; j < 32; j++) {
-                                const float4 c4 = qc[cb * 32 + j];
-                                const float T = fmaf(c4.x, rc.bp, fmaf(c4.y, rc.cp, fmaf(c4.z, rc.Bp, c4.w)));
-                                if ((float)v[j] >= T) {
-                                    const unsigned int pos = atomicAdd(p.cand_count, 1u);
-                                    if (pos < p.cand_cap) {
-                                        p.cand_q[pos] = qt * kTN + half * kColsPerWarp + cb * 32 + j;
-                                        p.cand_rowdot[pos] = make_uint2(row, v[j]);
+                            for (int g = 0; g < 4; g++) {
+                                bool any = false;
+#pragma unroll
+                                for (int n = 2 * g; n < 2 * g + 2; n++) {
+#pragma unroll
+                                    for (int c = 0; c < 2; c++) {
+                                        const float4 c4 = cc[2 * n + c];  // (tau', -A', -e', 2^23 - m) / 8
+                                        const float TA = fmaf(c4.x, bpA, fmaf(c4.y, cpA, fmaf(c4.z, BpA, c4.w)));
+                                        const float TB = fmaf(c4.x, bpB, fmaf(c4.y, cpB, fmaf(c4.z, BpB, c4.w)));
+                                        any = any || (dot_as_f8(v[4 * n + c]) >= TA) || (dot_as_f8(v[4 * n + 2 + c]) >= TB);
+                                    }
+                                }
+                                if (any) {
+#pragma unroll
+                                    for (int n = 2 * g; n < 2 * g + 2; n++) {
+#pragma unroll
+                                        for (int c = 0; c < 4; c++) {
+                                            const float4 c4 = cc[2 * n + (c & 1)];
+                                            const bool second = (c & 2) != 0;
+                                            const float T = fmaf(c4.x, second ? bpB : bpA,
+                                                                 fmaf(c4.y, second ? cpB : cpA, fmaf(c4.z, second ? BpB : BpA, c4.w)));
+                                            if (dot_as_f8(v[4 * n + c]) >= T) {
+                                                const unsigned int pos = atomicAdd(p.cand_count, 1u);
+                                                if (pos < p.cand_cap) {
+                                                    p.cand_q[pos] = qt * kTN + colbase + 8 * n + 2 * tc + (c & 1);
+                                                    p.cand_rowdot[pos] = make_uint2(row_base + 16 * lh + (second ? 8 : 0), v[4 * n + c]);
+                                                }
+                                            }
+                                        }
+                                    }
+                                }
+                            }
+                        } else {
+                            // group maximum per query column over the 16 rows of this load (4 groups per... 8 per tile)
+                            const float ibA = lh ? r_ib[2] : r_ib[0], ibB = lh ? r_ib[3] : r_ib[1];
+                            const int okA = lh ? r_ok[2] : r_ok[0], okB = lh ? r_ok[3] : r_ok[1];
+                            const float ninf = __int_as_float(0xFF800000);
+#pragma unroll
+                            for (int n = 0; n < 8; n++) {
+#pragma unroll
+                                for (int c = 0; c < 2; c++) {
+                                    const float4 c4 = cc[2 * n + c];  // (aq, A', e', -)
+                                    float sa = fmaf(c4.y, cpA, fmaf(c4.z, BpA, dot_approx(v[4 * n + c]))) * (c4.x * ibA);
+                                    float sb = fmaf(c4.y, cpB, fmaf(c4.z, BpB, dot_approx(v[4 * n + 2 + c]))) * (c4.x * ibB);
+                                    if (!okA || !(sa == sa)) sa = ninf;
+                                    if (!okB || !(sb == sb)) sb = ninf;
+                                    float mx = fmaxf(sa, sb);
+                                    mx = fmaxf(mx, __shfl_xor_sync(0xFFFFFFFFu, mx, 4));
+                                    mx = fmaxf(mx, __shfl_xor_sync(0xFFFFFFFFu, mx, 8));
+                                    mx = fmaxf(mx, __shfl_xor_sync(0xFFFFFFFFu, mx, 16));
+                                    if (tr == 0) {
+                                        const uint32_t q = qt * kTN + colbase + 8 * n + 2 * tc + c;
+                                        p.gmax[(size_t)q * p.G + (size_t)i * 8 + qd * 2 + lh] = mx;
                                     }
                                 }
                             }
                         }
-                    } else {
-                        int keep = (int)0x80000000;
-#pragma unroll
-                        for (int j = 0; j < 32; j++) {
-                            const float4 c4 = qc[cb * 32 + j];  // (aq, A', e', -)
-                            float sc = fmaf(c4.y, rc.cp, fmaf(c4.z, rc.Bp, (float)v[j])) * (c4.x * rc.inv_bp);
-                            if (!rc.usable || !(sc == sc)) sc = __int_as_float(0xFF800000);
-                            const int mx = __reduce_max_sync(0xFFFFFFFFu, f32_ordered(sc));
-                            if (lane == j) keep = mx;
-                        }
-                        const uint32_t q = qt * kTN + half * kColsPerWarp + cb * 32 + lane;
-                        p.gmax[(size_t)q * p.G + (size_t)i * 4 + qd] = ordered_f32(keep);
                     }
                 }
                 tc_fence_before();
@@ -485,7 +559,7 @@ __global__ void query_consts_groupmax_kernel(MatView queries, uint32_t nq_pad, f
 }
 
 // One block per query: tau = (r-th largest group maximum) - slack; writes the filter's column constants
-// (tau', -A', -e', -m), tau itself, and flags unusable queries for the streaming-scan fallback.
+// (tau', -A', -e', 2^23*8 - m) / 8, tau itself, and flags unusable queries for the streaming-scan fallback.
 constexpr int kThrThreads = 128;
 __global__ void __launch_bounds__(kThrThreads)
 threshold_kernel(MatView queries, uint32_t nq_pad, const float *gmax, uint32_t G, uint32_t r, const unsigned int *bounds,
@@ -532,7 +606,7 @@ threshold_kernel(MatView queries, uint32_t nq_pad, const float *gmax, uint32_t G
     const float tau = (kth == ninf) ? ninf : kth - 2.0e-5f * fmaxf(1.0f, fabsf(kth));
     tau_out[q] = tau;
     if (tau == ninf) {  // not enough groups: everything passes (small stores); -e' keeps out-of-range rows out
-        col_consts[q] = make_float4(0.f, 0.f, (float)(-qs.ep), ninf);
+        col_consts[q] = make_float4(0.f, 0.f, (float)(-qs.ep * 0.125), ninf);
         return;
     }
     const double tp = (double)tau / qs.aq;
@@ -540,8 +614,10 @@ threshold_kernel(MatView queries, uint32_t nq_pad, const float *gmax, uint32_t G
                  BBmax = (double)__uint_as_float(bounds[2]);
     // float32 evaluation error of T (coefficient roundings, three FMAs, int->float of the dot) plus the float32
     // rounding of the reference's own score: < 2^-20 of the term magnitudes + a few units
-    const double m = ldexp(fabs(tp) * Bmax + fabs(qs.Ap) * Cmax + fabs(qs.ep) * BBmax, -20) + 16.0;
-    col_consts[q] = make_float4((float)tp, (float)(-qs.Ap), (float)(-qs.ep), (float)(-m));
+    // plus the epilogue's own representation: the dot is compared as 2^23 + (dot >> 3) (up to 7 units low, so T
+    // drops by 8) against T/8 + 2^23 accumulated at float32 ulp 1 there (three roundings: 12 units, take 24)
+    const double m = ldexp(fabs(tp) * Bmax + fabs(qs.Ap) * Cmax + fabs(qs.ep) * BBmax, -20) + 16.0 + 8.0 + 24.0;
+    col_consts[q] = make_float4((float)(tp * 0.125), (float)(-qs.Ap * 0.125), (float)(-qs.ep * 0.125), (float)(8388608.0 - m * 0.125));
 }
 
 // ---- candidate resolution -------------------------------------------------------------------------------------
@@ -766,7 +842,7 @@ GemmPlan gemm_plan(const MatView &rows, size_t nq, size_t k, bool unique_ids, in
     pl.sample_stride = pl.tiles / want;
     if (pl.sample_stride < 1) pl.sample_stride = 1;
     pl.sample_tiles = (pl.tiles + pl.sample_stride - 1) / pl.sample_stride;
-    pl.G = pl.sample_tiles * 4;
+    pl.G = pl.sample_tiles * 8;  // one group maximum per 16 store rows
     size_t cap = nq * (size_t)4096;
     if (cap < (1u << 20)) cap = 1u << 20;
     if (cap > (64u << 20)) cap = 64u << 20;

@@ -125,7 +125,7 @@ struct GemmPlan {
     uint32_t nq_pad;        // queries rounded up to the 128-column tile
     uint32_t tiles;         // 128-row store tiles
     uint32_t rank;          // the threshold is the rank-th largest group maximum of the sample
-    uint32_t sample_stride, sample_tiles, G;  // pre-pass sample: every sample_stride-th tile; G = 4 groups per tile
+    uint32_t sample_stride, sample_tiles, G;  // pre-pass sample: every sample_stride-th tile; G = 8 groups per tile
     unsigned int cand_cap;  // candidate list capacity
     size_t sort_tmp_bytes;
 };
