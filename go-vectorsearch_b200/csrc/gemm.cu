@@ -45,8 +45,8 @@ constexpr int kChunkK = 128;             // K bytes per shared-memory chunk (one
 constexpr int kChunkBytes = kTM * kChunkK;  // 16 KB: one K chunk of the resident store tile
 constexpr int kStageBytes = kTN * kChunkK;  // one K chunk of a streamed query tile
 constexpr int kAccStages = 512 / kTN;    // TMEM accumulator stages (512 columns in all)
-constexpr int kColsPerWarp = kTN / 2;    // the two epilogue warps of a lane quadrant split the columns
-constexpr int kEpiWarps = 8;
+constexpr int kEpiWarps = 16;
+constexpr int kColsPerWarp = kTN / (kEpiWarps / 4);  // the epilogue warps of a lane quadrant split the columns
 constexpr int kGemmThreads = (4 + kEpiWarps) * 32;
 constexpr int kMaxKC = 8;                // d_pad <= 1024
 constexpr int kMaxStages = 8;
@@ -162,6 +162,15 @@ __device__ __forceinline__ void tc_ld_16x256b_x8(uint32_t taddr, uint32_t (&v)[3
           "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15]), "=r"(v[16]),
           "=r"(v[17]), "=r"(v[18]), "=r"(v[19]), "=r"(v[20]), "=r"(v[21]), "=r"(v[22]), "=r"(v[23]), "=r"(v[24]),
           "=r"(v[25]), "=r"(v[26]), "=r"(v[27]), "=r"(v[28]), "=r"(v[29]), "=r"(v[30]), "=r"(v[31])
+        : "r"(taddr)
+        : "memory");
+}
+__device__ __forceinline__ void tc_ld_16x256b_x4(uint32_t taddr, uint32_t (&v)[16]) {  // same, n = 0..3
+    asm volatile(
+        "tcgen05.ld.sync.aligned.16x256b.x4.b32 "
+        "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
+        : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]), "=r"(v[8]),
+          "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15])
         : "r"(taddr)
         : "memory");
 }
@@ -356,11 +365,12 @@ gemm_kernel(const __grid_constant__ CUtensorMap tm_rows, const __grid_constant__
         // ===== epilogue =====
         // tcgen05.ld 16x256b hands every thread a few query columns of several store rows (the layout of an mma C
         // fragment: lane = 4*r + c holds columns 8n + 2c, 8n + 2c + 1 of rows r and r + 8), so a thread keeps the
-        // constants of its 16 columns in registers for a whole 64-column pass: 16 shared-memory loads per pass
-        // instead of one per column -- the shared-memory port belongs to the tensor cores and TMA.
+        // constants of its 8 columns in registers for a whole 32-column pass: 8 shared-memory loads per pass instead
+        // of one per column -- the shared-memory port belongs to the tensor cores and TMA.  Sixteen warps (four per
+        // scheduler) at <= 96 registers hide the TMEM-load and FMA-chain latencies.
         const int e = warp - 4;
-        const int qd = e & 3;     // TMEM lane quadrant this warp may read
-        const int half = e >> 2;  // which half of the query columns
+        const int qd = e & 3;       // TMEM lane quadrant this warp may read
+        const int part = e >> 2;    // which slice of the query columns
         const int tc = lane & 3, tr = lane >> 2;
         uint32_t acc_s = 0, acc_ph = 0;
         for (uint32_t i = blockIdx.x; i < p.tile_count; i += gridDim.x) {
@@ -375,15 +385,20 @@ gemm_kernel(const __grid_constant__ CUtensorMap tm_rows, const __grid_constant__
             }
             const GemmRowConst own = gemm_row_const(h.x, h.y, sm2.x, sm2.y, p.D, in_range);
             // this thread's four rows: tr + 8k of the quadrant
-            float r_bp[4], r_cp[4], r_Bp[4], r_ib[4];
-            int r_ok[4];
+            float r_bp[4], r_cp[4], r_Bp[4];
 #pragma unroll
             for (int k = 0; k < 4; k++) {
                 r_bp[k] = __shfl_sync(0xFFFFFFFFu, own.bp, tr + 8 * k);
                 r_cp[k] = __shfl_sync(0xFFFFFFFFu, own.cp, tr + 8 * k);
                 r_Bp[k] = __shfl_sync(0xFFFFFFFFu, own.Bp, tr + 8 * k);
-                r_ib[k] = __shfl_sync(0xFFFFFFFFu, own.inv_bp, tr + 8 * k);
-                r_ok[k] = __shfl_sync(0xFFFFFFFFu, own.usable, tr + 8 * k);
+            }
+            if constexpr (MODE == MODE_GROUPMAX) {  // the pre-pass scores with 1/bp and must skip unusable rows
+#pragma unroll
+                for (int k = 0; k < 4; k++) {
+                    const float ib = __shfl_sync(0xFFFFFFFFu, own.inv_bp, tr + 8 * k);
+                    const int ok = __shfl_sync(0xFFFFFFFFu, own.usable, tr + 8 * k);
+                    r_bp[k] = ok ? ib : __int_as_float(0x7FC00000);  // NaN marks the row
+                }
             }
             const uint32_t row_base = tile * kTM + qd * 32 + tr;
             for (uint32_t qt = 0; qt < nqt; qt++) {
@@ -391,78 +406,75 @@ gemm_kernel(const __grid_constant__ CUtensorMap tm_rows, const __grid_constant__
                 mbar_wait(acc_full + 8 * acc_s, acc_ph);
                 tc_fence_after();
 #pragma unroll 1
-                for (int pass = 0; pass < kColsPerWarp / 64; pass++) {
+                for (int pass = 0; pass < kColsPerWarp / 32; pass++) {
                     if (p.dbg >= 2) break;
-                    const int colbase = half * kColsPerWarp + pass * 64;
+                    const int colbase = part * kColsPerWarp + pass * 32;
                     const float4 *qc = q_consts + acc_s * kTN + colbase + 2 * tc;
-                    float4 cc[16];
+                    float4 cc[8];
 #pragma unroll
-                    for (int n = 0; n < 8; n++) {
+                    for (int n = 0; n < 4; n++) {
                         cc[2 * n] = qc[8 * n];
                         cc[2 * n + 1] = qc[8 * n + 1];
                     }
-#pragma unroll 1
+#pragma unroll
                     for (int lh = 0; lh < 2; lh++) {
-                        uint32_t v[32];
-                        tc_ld_16x256b_x8(tmem_base + ((uint32_t)(qd * 32 + lh * 16) << 16) + acc_s * kTN + colbase, v);
+                        uint32_t v[16];
+                        tc_ld_16x256b_x4(tmem_base + ((uint32_t)(qd * 32 + lh * 16) << 16) + acc_s * kTN + colbase, v);
                         tc_ld_wait();
                         if (p.dbg == 1) {
-                            if (v[0] == 0xFFFFFFFFu && v[31] == 0xFFFFFFFEu) p.cand_q[0] = 0;
+                            if (v[0] == 0xFFFFFFFFu && v[15] == 0xFFFFFFFEu) p.cand_q[0] = 0;
                             continue;
                         }
                         // registers 4n + {0,1}: row tr + 16 lh, columns 8n + 2 tc + {0,1}; 4n + {2,3}: row + 8
-                        const float bpA = lh ? r_bp[2] : r_bp[0], cpA = lh ? r_cp[2] : r_cp[0], BpA = lh ? r_Bp[2] : r_Bp[0];
-                        const float bpB = lh ? r_bp[3] : r_bp[1], cpB = lh ? r_cp[3] : r_cp[1], BpB = lh ? r_Bp[3] : r_Bp[1];
+                        const float bpA = r_bp[2 * lh], cpA = r_cp[2 * lh], BpA = r_Bp[2 * lh];
+                        const float bpB = r_bp[2 * lh + 1], cpB = r_cp[2 * lh + 1], BpB = r_Bp[2 * lh + 1];
                         if constexpr (MODE == MODE_FILTER) {
-                            // four groups of 8 pairs: a side-effect-free test first; the (rare) emission code runs only
-                            // for a group with a hit, and only in the threads that have it
+                            // a side-effect-free test first (four independent predicate chains); the rare emission code
+                            // runs only in the threads that have a hit
+                            bool any0 = false, any1 = false, any2 = false, any3 = false;
 #pragma unroll
-                            for (int g = 0; g < 4; g++) {
-                                bool any = false;
+                            for (int n = 0; n < 4; n++) {
+                                const float4 c0 = cc[2 * n], c1 = cc[2 * n + 1];  // (tau', -A', -e', 2^23*8 - m) / 8
+                                const float TA0 = fmaf(c0.x, bpA, fmaf(c0.y, cpA, fmaf(c0.z, BpA, c0.w)));
+                                const float TA1 = fmaf(c1.x, bpA, fmaf(c1.y, cpA, fmaf(c1.z, BpA, c1.w)));
+                                const float TB0 = fmaf(c0.x, bpB, fmaf(c0.y, cpB, fmaf(c0.z, BpB, c0.w)));
+                                const float TB1 = fmaf(c1.x, bpB, fmaf(c1.y, cpB, fmaf(c1.z, BpB, c1.w)));
+                                any0 = any0 || (dot_as_f8(v[4 * n + 0]) >= TA0);
+                                any1 = any1 || (dot_as_f8(v[4 * n + 1]) >= TA1);
+                                any2 = any2 || (dot_as_f8(v[4 * n + 2]) >= TB0);
+                                any3 = any3 || (dot_as_f8(v[4 * n + 3]) >= TB1);
+                            }
+                            if (any0 || any1 || any2 || any3) {
 #pragma unroll
-                                for (int n = 2 * g; n < 2 * g + 2; n++) {
+                                for (int n = 0; n < 4; n++) {
 #pragma unroll
-                                    for (int c = 0; c < 2; c++) {
-                                        const float4 c4 = cc[2 * n + c];  // (tau', -A', -e', 2^23 - m) / 8
-                                        const float TA = fmaf(c4.x, bpA, fmaf(c4.y, cpA, fmaf(c4.z, BpA, c4.w)));
-                                        const float TB = fmaf(c4.x, bpB, fmaf(c4.y, cpB, fmaf(c4.z, BpB, c4.w)));
-                                        any = any || (dot_as_f8(v[4 * n + c]) >= TA) || (dot_as_f8(v[4 * n + 2 + c]) >= TB);
-                                    }
-                                }
-                                if (any) {
-#pragma unroll
-                                    for (int n = 2 * g; n < 2 * g + 2; n++) {
-#pragma unroll
-                                        for (int c = 0; c < 4; c++) {
-                                            const float4 c4 = cc[2 * n + (c & 1)];
-                                            const bool second = (c & 2) != 0;
-                                            const float T = fmaf(c4.x, second ? bpB : bpA,
-                                                                 fmaf(c4.y, second ? cpB : cpA, fmaf(c4.z, second ? BpB : BpA, c4.w)));
-                                            if (dot_as_f8(v[4 * n + c]) >= T) {
-                                                const unsigned int pos = atomicAdd(p.cand_count, 1u);
-                                                if (pos < p.cand_cap) {
-                                                    p.cand_q[pos] = qt * kTN + colbase + 8 * n + 2 * tc + (c & 1);
-                                                    p.cand_rowdot[pos] = make_uint2(row_base + 16 * lh + (second ? 8 : 0), v[4 * n + c]);
-                                                }
+                                    for (int c = 0; c < 4; c++) {
+                                        const float4 c4 = cc[2 * n + (c & 1)];
+                                        const bool second = (c & 2) != 0;
+                                        const float T = fmaf(c4.x, second ? bpB : bpA,
+                                                             fmaf(c4.y, second ? cpB : cpA, fmaf(c4.z, second ? BpB : BpA, c4.w)));
+                                        if (dot_as_f8(v[4 * n + c]) >= T) {
+                                            const unsigned int pos = atomicAdd(p.cand_count, 1u);
+                                            if (pos < p.cand_cap) {
+                                                p.cand_q[pos] = qt * kTN + colbase + 8 * n + 2 * tc + (c & 1);
+                                                p.cand_rowdot[pos] = make_uint2(row_base + 16 * lh + (second ? 8 : 0), v[4 * n + c]);
                                             }
                                         }
                                     }
                                 }
                             }
                         } else {
-                            // group maximum per query column over the 16 rows of this load (4 groups per... 8 per tile)
-                            const float ibA = lh ? r_ib[2] : r_ib[0], ibB = lh ? r_ib[3] : r_ib[1];
-                            const int okA = lh ? r_ok[2] : r_ok[0], okB = lh ? r_ok[3] : r_ok[1];
+                            // maximum per query column over the 16 rows of this load (8 groups per store tile)
                             const float ninf = __int_as_float(0xFF800000);
 #pragma unroll
-                            for (int n = 0; n < 8; n++) {
+                            for (int n = 0; n < 4; n++) {
 #pragma unroll
                                 for (int c = 0; c < 2; c++) {
-                                    const float4 c4 = cc[2 * n + c];  // (aq, A', e', -)
-                                    float sa = fmaf(c4.y, cpA, fmaf(c4.z, BpA, dot_approx(v[4 * n + c]))) * (c4.x * ibA);
-                                    float sb = fmaf(c4.y, cpB, fmaf(c4.z, BpB, dot_approx(v[4 * n + 2 + c]))) * (c4.x * ibB);
-                                    if (!okA || !(sa == sa)) sa = ninf;
-                                    if (!okB || !(sb == sb)) sb = ninf;
+                                    const float4 c4 = cc[2 * n + c];  // (aq, A', e', -); r_bp holds 1/bp (NaN: skip the row)
+                                    float sa = fmaf(c4.y, cpA, fmaf(c4.z, BpA, dot_approx(v[4 * n + c]))) * (c4.x * bpA);
+                                    float sb = fmaf(c4.y, cpB, fmaf(c4.z, BpB, dot_approx(v[4 * n + 2 + c]))) * (c4.x * bpB);
+                                    if (!(sa == sa)) sa = ninf;
+                                    if (!(sb == sb)) sb = ninf;
                                     float mx = fmaxf(sa, sb);
                                     mx = fmaxf(mx, __shfl_xor_sync(0xFFFFFFFFu, mx, 4));
                                     mx = fmaxf(mx, __shfl_xor_sync(0xFFFFFFFFu, mx, 8));
