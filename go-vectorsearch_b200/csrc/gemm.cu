@@ -192,6 +192,23 @@ __device__ __forceinline__ float dot_as_f8(uint32_t dot) { return __uint_as_floa
 // dot rounded down to a multiple of 8, as a float (pre-pass: an approximate score is enough)
 __device__ __forceinline__ float dot_approx(uint32_t dot) { return fmaf(dot_as_f8(dot), 8.0f, -67108864.0f); }
 
+// Packed float32 pairs (Blackwell fma.rn.f32x2): one instruction evaluates the filter of two adjacent query columns.
+__device__ __forceinline__ uint64_t pack2(float lo, float hi) {
+    uint64_t r;
+    asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(lo), "f"(hi));
+    return r;
+}
+__device__ __forceinline__ void unpack2(uint64_t v, float &lo, float &hi) { asm("mov.b64 {%0, %1}, %2;" : "=f"(lo), "=f"(hi) : "l"(v)); }
+__device__ __forceinline__ uint64_t fma2(uint64_t a, uint64_t b, uint64_t c) {
+    uint64_t d;
+    asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(d) : "l"(a), "l"(b), "l"(c));
+    return d;
+}
+// Column constants are stored per pair of adjacent queries as (x0, x1, y0, y1, z0, z1, w0, w1).
+__host__ __device__ __forceinline__ size_t col_const_index(uint32_t q, int component) {
+    return (size_t)(q >> 1) * 8 + (size_t)component * 2 + (q & 1);
+}
+
 __device__ __forceinline__ int f32_ordered(float f) {
     const int b = __float_as_int(f);
     return b >= 0 ? b : (b ^ 0x7FFFFFFF);
@@ -344,6 +361,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tm_rows, const __grid_constant__
                         const uint64_t bd = b_desc0 + (uint64_t)(st * (kStageBytes >> 4));
 #pragma unroll
                         for (int k = 0; k < kChunkK / 32; k++)  // +32 bytes of K inside the swizzle atom = +2 encoded
+                            if (p.dbg != 5 || (c | k) == 0)  // profiling aid 5: one MMA per tile (epilogue-only timing)
                             tc_mma_i8(d_tmem, ad + 2 * k, bd + 2 * k, kIdesc, (c | k) != 0 ? 1u : 0u);
                         tc_commit(b_empty + 8 * st);
                         if (qt == nqt - 1) tc_commit(a_empty + 8 * c);
@@ -409,12 +427,16 @@ gemm_kernel(const __grid_constant__ CUtensorMap tm_rows, const __grid_constant__
                 for (int pass = 0; pass < kColsPerWarp / 32; pass++) {
                     if (p.dbg >= 2) break;
                     const int colbase = part * kColsPerWarp + pass * 32;
-                    const float4 *qc = q_consts + acc_s * kTN + colbase + 2 * tc;
-                    float4 cc[8];
+                    // this thread's column pairs 4n + tc of the pass: (x0,x1), (y0,y1), (z0,z1), (w0,w1) each
+                    const ulonglong2 *qc = reinterpret_cast<const ulonglong2 *>(q_consts + acc_s * kTN + colbase + 2 * tc);
+                    uint64_t cx[4], cy[4], cz[4], cw[4];
 #pragma unroll
                     for (int n = 0; n < 4; n++) {
-                        cc[2 * n] = qc[8 * n];
-                        cc[2 * n + 1] = qc[8 * n + 1];
+                        const ulonglong2 lo = qc[8 * n], hi = qc[8 * n + 1];
+                        cx[n] = lo.x;
+                        cy[n] = lo.y;
+                        cz[n] = hi.x;
+                        cw[n] = hi.y;
                     }
 #pragma unroll
                     for (int lh = 0; lh < 2; lh++) {
@@ -432,13 +454,13 @@ gemm_kernel(const __grid_constant__ CUtensorMap tm_rows, const __grid_constant__
                             // a side-effect-free test first (four independent predicate chains); the rare emission code
                             // runs only in the threads that have a hit
                             bool any0 = false, any1 = false, any2 = false, any3 = false;
+                            const uint64_t bpA2 = pack2(bpA, bpA), cpA2 = pack2(cpA, cpA), BpA2 = pack2(BpA, BpA);
+                            const uint64_t bpB2 = pack2(bpB, bpB), cpB2 = pack2(cpB, cpB), BpB2 = pack2(BpB, BpB);
 #pragma unroll
-                            for (int n = 0; n < 4; n++) {
-                                const float4 c0 = cc[2 * n], c1 = cc[2 * n + 1];  // (tau', -A', -e', 2^23*8 - m) / 8
-                                const float TA0 = fmaf(c0.x, bpA, fmaf(c0.y, cpA, fmaf(c0.z, BpA, c0.w)));
-                                const float TA1 = fmaf(c1.x, bpA, fmaf(c1.y, cpA, fmaf(c1.z, BpA, c1.w)));
-                                const float TB0 = fmaf(c0.x, bpB, fmaf(c0.y, cpB, fmaf(c0.z, BpB, c0.w)));
-                                const float TB1 = fmaf(c1.x, bpB, fmaf(c1.y, cpB, fmaf(c1.z, BpB, c1.w)));
+                            for (int n = 0; n < 4; n++) {  // columns (tau', -A', -e', 2^23*8 - m) / 8, two at a time
+                                float TA0, TA1, TB0, TB1;
+                                unpack2(fma2(cx[n], bpA2, fma2(cy[n], cpA2, fma2(cz[n], BpA2, cw[n]))), TA0, TA1);
+                                unpack2(fma2(cx[n], bpB2, fma2(cy[n], cpB2, fma2(cz[n], BpB2, cw[n]))), TB0, TB1);
                                 any0 = any0 || (dot_as_f8(v[4 * n + 0]) >= TA0);
                                 any1 = any1 || (dot_as_f8(v[4 * n + 1]) >= TA1);
                                 any2 = any2 || (dot_as_f8(v[4 * n + 2]) >= TB0);
@@ -447,17 +469,16 @@ gemm_kernel(const __grid_constant__ CUtensorMap tm_rows, const __grid_constant__
                             if (any0 || any1 || any2 || any3) {
 #pragma unroll
                                 for (int n = 0; n < 4; n++) {
+                                    float T[4];
+                                    unpack2(fma2(cx[n], bpA2, fma2(cy[n], cpA2, fma2(cz[n], BpA2, cw[n]))), T[0], T[1]);
+                                    unpack2(fma2(cx[n], bpB2, fma2(cy[n], cpB2, fma2(cz[n], BpB2, cw[n]))), T[2], T[3]);
 #pragma unroll
                                     for (int c = 0; c < 4; c++) {
-                                        const float4 c4 = cc[2 * n + (c & 1)];
-                                        const bool second = (c & 2) != 0;
-                                        const float T = fmaf(c4.x, second ? bpB : bpA,
-                                                             fmaf(c4.y, second ? cpB : cpA, fmaf(c4.z, second ? BpB : BpA, c4.w)));
-                                        if (dot_as_f8(v[4 * n + c]) >= T) {
+                                        if (dot_as_f8(v[4 * n + c]) >= T[c]) {
                                             const unsigned int pos = atomicAdd(p.cand_count, 1u);
                                             if (pos < p.cand_cap) {
                                                 p.cand_q[pos] = qt * kTN + colbase + 8 * n + 2 * tc + (c & 1);
-                                                p.cand_rowdot[pos] = make_uint2(row_base + 16 * lh + (second ? 8 : 0), v[4 * n + c]);
+                                                p.cand_rowdot[pos] = make_uint2(row_base + 16 * lh + ((c & 2) ? 8 : 0), v[4 * n + c]);
                                             }
                                         }
                                     }
@@ -470,9 +491,12 @@ gemm_kernel(const __grid_constant__ CUtensorMap tm_rows, const __grid_constant__
                             for (int n = 0; n < 4; n++) {
 #pragma unroll
                                 for (int c = 0; c < 2; c++) {
-                                    const float4 c4 = cc[2 * n + c];  // (aq, A', e', -); r_bp holds 1/bp (NaN: skip the row)
-                                    float sa = fmaf(c4.y, cpA, fmaf(c4.z, BpA, dot_approx(v[4 * n + c]))) * (c4.x * bpA);
-                                    float sb = fmaf(c4.y, cpB, fmaf(c4.z, BpB, dot_approx(v[4 * n + 2 + c]))) * (c4.x * bpB);
+                                    float xs[2], ys[2], zs[2];  // (aq, A', e'); r_bp holds 1/bp (NaN: skip the row)
+                                    unpack2(cx[n], xs[0], xs[1]);
+                                    unpack2(cy[n], ys[0], ys[1]);
+                                    unpack2(cz[n], zs[0], zs[1]);
+                                    float sa = fmaf(ys[c], cpA, fmaf(zs[c], BpA, dot_approx(v[4 * n + c]))) * (xs[c] * bpA);
+                                    float sb = fmaf(ys[c], cpB, fmaf(zs[c], BpB, dot_approx(v[4 * n + 2 + c]))) * (xs[c] * bpB);
                                     if (!(sa == sa)) sa = ninf;
                                     if (!(sb == sb)) sb = ninf;
                                     float mx = fmaxf(sa, sb);
@@ -556,6 +580,14 @@ __device__ __forceinline__ QuerySide query_side(float mn, float mx, uint32_t s1,
     return q;
 }
 
+__device__ __forceinline__ void store_col_const(float4 *base, uint32_t q, float4 v) {
+    float *f = reinterpret_cast<float *>(base);
+    f[col_const_index(q, 0)] = v.x;
+    f[col_const_index(q, 1)] = v.y;
+    f[col_const_index(q, 2)] = v.z;
+    f[col_const_index(q, 3)] = v.w;
+}
+
 // Column constants of the pre-pass: (aq, A', e', 0); padding / unusable queries score -inf everywhere (aq = NaN).
 __global__ void query_consts_groupmax_kernel(MatView queries, uint32_t nq_pad, float4 *out) {
     const uint32_t q = blockIdx.x * blockDim.x + threadIdx.x;
@@ -567,7 +599,7 @@ __global__ void query_consts_groupmax_kernel(MatView queries, uint32_t nq_pad, f
         const QuerySide qs = query_side(h.x, h.y, s.x, s.y, queries.d);
         if (qs.usable) o = make_float4((float)qs.aq, (float)qs.Ap, (float)qs.ep, 0.f);
     }
-    out[q] = o;
+    store_col_const(out, q, o);
 }
 
 // One block per query: tau = (r-th largest group maximum) - slack; writes the filter's column constants
@@ -581,7 +613,7 @@ threshold_kernel(MatView queries, uint32_t nq_pad, const float *gmax, uint32_t G
     const uint32_t q = blockIdx.x;
     const float ninf = __int_as_float(0xFF800000), pinf = __int_as_float(0x7F800000);
     if (q >= queries.n) {  // padding columns never pass
-        if (threadIdx.x == 0) col_consts[q] = make_float4(0.f, 0.f, 0.f, pinf);
+        if (threadIdx.x == 0) store_col_const(col_consts, q, make_float4(0.f, 0.f, 0.f, pinf));
         return;
     }
     for (uint32_t g = threadIdx.x; g < G; g += kThrThreads) s_keys[g] = f32_ordered(gmax[(size_t)q * G + g]);
@@ -608,7 +640,7 @@ threshold_kernel(MatView queries, uint32_t nq_pad, const float *gmax, uint32_t G
     const uint2 s = queries.sums[q];
     const QuerySide qs = query_side(h.x, h.y, s.x, s.y, queries.d);
     if (!qs.usable) {
-        col_consts[q] = make_float4(0.f, 0.f, 0.f, pinf);
+        store_col_const(col_consts, q, make_float4(0.f, 0.f, 0.f, pinf));
         tau_out[q] = pinf;
         status[q] = kStatusNeedMore;
         return;
@@ -618,7 +650,7 @@ threshold_kernel(MatView queries, uint32_t nq_pad, const float *gmax, uint32_t G
     const float tau = (kth == ninf) ? ninf : kth - 2.0e-5f * fmaxf(1.0f, fabsf(kth));
     tau_out[q] = tau;
     if (tau == ninf) {  // not enough groups: everything passes (small stores); -e' keeps out-of-range rows out
-        col_consts[q] = make_float4(0.f, 0.f, (float)(-qs.ep * 0.125), ninf);
+        store_col_const(col_consts, q, make_float4(0.f, 0.f, (float)(-qs.ep * 0.125), ninf));
         return;
     }
     const double tp = (double)tau / qs.aq;
@@ -629,7 +661,7 @@ threshold_kernel(MatView queries, uint32_t nq_pad, const float *gmax, uint32_t G
     // plus the epilogue's own representation: the dot is compared as 2^23 + (dot >> 3) (up to 7 units low, so T
     // drops by 8) against T/8 + 2^23 accumulated at float32 ulp 1 there (three roundings: 12 units, take 24)
     const double m = ldexp(fabs(tp) * Bmax + fabs(qs.Ap) * Cmax + fabs(qs.ep) * BBmax, -20) + 16.0 + 8.0 + 24.0;
-    col_consts[q] = make_float4((float)(tp * 0.125), (float)(-qs.Ap * 0.125), (float)(-qs.ep * 0.125), (float)(8388608.0 - m * 0.125));
+    store_col_const(col_consts, q, make_float4((float)(tp * 0.125), (float)(-qs.Ap * 0.125), (float)(-qs.ep * 0.125), (float)(8388608.0 - m * 0.125)));
 }
 
 // ---- candidate resolution -------------------------------------------------------------------------------------

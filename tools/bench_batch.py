@@ -52,12 +52,15 @@ def main():
     ctx.sync()
     ctx.profile_enable(True)
     torch.cuda.synchronize()
+    sampler = B.ClockSampler(0)
+    sampler.start()
     t0 = time.perf_counter()
     ctx.timer_start()
     for s in range(a.warmup, a.warmup + a.steps):
         stats.append(pkg.ivf.SearchBatchDev(data, qms[s], a.k, d_ids.data_ptr(), d_sims.data_ptr(), d_counts.data_ptr(), ctx=ctx))
     ms = ctx.timer_stop()
     wall = time.perf_counter() - t0
+    clocks = sampler.stop()
     gemm_ms, gemm_launches = ctx.profile_read()
     ctx.profile_enable(False)
     ops = 2.0 * a.nq * a.rows * B.D
@@ -80,6 +83,7 @@ def main():
         "candidates_per_batch": int(np.mean([st[0] for st in stats])), "queries_finished_by_scan": int(np.sum([st[1] for st in stats])),
         "tiles": stats[-1][2], "sample_tiles": stats[-1][3],
         "parity_vs_scan_path": {"queries_checked": int(nchk), "match": match},
+        "clocks": clocks,
     }
     print(json.dumps(out), flush=True)
 
