@@ -19,7 +19,7 @@ SYMBOLS = [
     "vs_matrix_release", "vs_matrix_rows", "vs_matrix_cols", "vs_matrix_read_rows",
     "vs_cosine_1xN", "vs_dot_1xN", "vs_argmax_MxN", "vs_argmax_MxN_dev",
     "vs_index_build", "vs_index_build_assigned", "vs_index_build_dev", "vs_index_release",
-    "vs_index_rows", "vs_index_lists", "vs_index_list_offsets", "vs_index_read_rows", "vs_search", "vs_search_flat", "vs_search_flat_gemm", "vs_search_batch_dev", "vs_search_dev",
+    "vs_index_rows", "vs_index_lists", "vs_index_list_offsets", "vs_index_read_rows", "vs_search", "vs_search_flat", "vs_search_flat_gemm", "vs_search_batch_dev", "vs_index_search_batch_dev", "vs_search_dev",
     "vs_search_resolve", "vs_select_probes", "vs_topk_merge_dev", "vs_topk_merge_packed_dev",
     "vs_kmeans_step", "vs_recenter",
 ]
@@ -103,6 +103,7 @@ def load():
         L.vs_search_flat.argtypes = [vp, vp, vp, vp, sz, sz, vp, vp, vp]
         L.vs_search_flat_gemm.argtypes = [vp, vp, vp, vp, sz, sz, vp, vp, vp]
         L.vs_search_batch_dev.argtypes = [vp, vp, vp, u64, vp, sz, vp, vp, vp, vp]
+        L.vs_index_search_batch_dev.argtypes = [vp, vp, vp, sz, vp, vp, vp, vp]
         L.vs_search_dev.argtypes = [vp, vp, vp, sz, sz, vp, vp, vp, vp]
         L.vs_search_resolve.argtypes = [vp, vp, vp, sz, sz, vp, vp, vp, vp, C.POINTER(C.c_int)]
         L.vs_select_probes.argtypes = [vp, vp, vp, sz, sz, vp, vp]

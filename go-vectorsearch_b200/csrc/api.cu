@@ -1049,11 +1049,20 @@ extern "C" int vs_search_resolve(vs_ctx *c, const vs_index *ix, const vs_matrix 
                                   false, n_resolved_out);
 }
 
+constexpr size_t kGemmMinQueries = 64;    // below this the per-query scans (HBM-bound) are faster
+constexpr size_t kGemmMinRows = 1u << 16;
+static int gemm_search_host(vs_ctx *c, const vs_index *ix, const uint8_t *queries, size_t nq, size_t k, uint64_t *ids_out,
+                            float *sims_out, int32_t *counts_out);
+
 static int search_host(vs_ctx *c, const vs_index *ix, const uint8_t *queries, size_t nq, size_t nprobe, size_t k,
                        uint64_t *ids_out, float *sims_out, int32_t *counts_out, uint32_t *probe_out, float *probe_sims_out,
                        bool stage1_only) {
     VS(search_check(c, ix));
     if (!queries) return fail(VS_EINVAL, "queries is null");
+    // a query batch over the whole store is a dense contraction: tensor cores (gemm.cu) instead of nq scans
+    if (!stage1_only && nprobe >= ix->C && nq >= kGemmMinQueries && ix->n >= kGemmMinRows && k <= 128 &&
+        gemm_supported(ix->data->view(), nq))
+        return gemm_search_host(c, ix, queries, nq, k, ids_out, sims_out, counts_out);
     const size_t row_bytes = 8 + (size_t)ix->data->d;
     Arena a(c);
     SearchSetup s;
@@ -1209,63 +1218,78 @@ static int gemm_check(vs_ctx *c, const vs_matrix *m, size_t nq, size_t d, size_t
     return VS_OK;
 }
 
-extern "C" int vs_search_batch_dev(vs_ctx *c, const vs_matrix *m, const uint64_t *d_doc_ids, uint64_t id_base,
-                                   const vs_matrix *queries, size_t k, uint64_t *d_ids, float *d_sims, int32_t *d_counts,
-                                   uint64_t *stats_out) {
+static int gemm_search_dev(vs_ctx *c, const vs_index *ix, const vs_matrix *queries, size_t k, uint64_t *d_ids, float *d_sims,
+                           int32_t *d_counts, uint64_t *stats_out) {
     if (!queries || !d_ids || !d_sims || !d_counts) return fail(VS_EINVAL, "null argument");
-    VS(gemm_check(c, m, queries->n, (size_t)queries->d, k));
+    VS(gemm_check(c, ix->data, queries->n, (size_t)queries->d, k));
     const size_t nq = queries->n;
+    const GemmPlan pl = gemm_plan(ix->data->view(), nq, k, ix->doc_ids == nullptr, g_sm_count);
+    Arena a(c);
+    SearchSetup s;
+    VS(search_setup(c, a, ix, nq, ix->C, k, gemm_scratch_bytes(pl, nq) + Arena::pad(nq * 4) + 4096, &s));
+    search_take(a, ix, nq, &s);
+    uint32_t *d_status = a.take<uint32_t>(nq);
+    return gemm_search_core(c, a, ix, queries->view(), k, s, pl, d_ids, d_sims, d_counts, d_status, stats_out);
+}
+
+static int gemm_search_host(vs_ctx *c, const vs_index *ix, const uint8_t *queries, size_t nq, size_t k, uint64_t *ids_out,
+                            float *sims_out, int32_t *counts_out) {
+    if (!queries || !ids_out || !sims_out || !counts_out) return fail(VS_EINVAL, "null argument");
+    VS(gemm_check(c, ix->data, nq, (size_t)ix->data->d, k));
+    const size_t row_bytes = 8 + (size_t)ix->data->d;
+    const GemmPlan pl = gemm_plan(ix->data->view(), nq, k, ix->doc_ids == nullptr, g_sm_count);
+    Arena a(c);
+    SearchSetup s;
+    const size_t out_bytes = Arena::pad(nq * k * 8) + Arena::pad(nq * k * 4) + 2 * Arena::pad(nq * 4) + 4096;
+    VS(search_setup(c, a, ix, nq, ix->C, k, gemm_scratch_bytes(pl, nq) + temp_matrix_bytes(nq, row_bytes) + out_bytes, &s));
+    MatView qv;
+    VS(temp_matrix(c, a, queries, nq, row_bytes, &qv));
+    search_take(a, ix, nq, &s);
+    uint64_t *d_ids = a.take<uint64_t>(nq * k);
+    float *d_sims = a.take<float>(nq * k);
+    int32_t *d_counts = a.take<int32_t>(nq);
+    uint32_t *d_status = a.take<uint32_t>(nq);
+    VS(gemm_search_core(c, a, ix, qv, k, s, pl, d_ids, d_sims, d_counts, d_status, nullptr));
+    CU(cudaMemcpyAsync(ids_out, d_ids, nq * k * 8, cudaMemcpyDeviceToHost, c->stream));
+    CU(cudaMemcpyAsync(sims_out, d_sims, nq * k * 4, cudaMemcpyDeviceToHost, c->stream));
+    CU(cudaMemcpyAsync(counts_out, d_counts, nq * 4, cudaMemcpyDeviceToHost, c->stream));
+    CU(cudaStreamSynchronize(c->stream));
+    return VS_OK;
+}
+
+// a matrix as an index with one list and no centroid stage
+static vs_index flat_view(const vs_matrix *m, const uint64_t *d_doc_ids, uint64_t id_base) {
     vs_index ix;
     ix.data = const_cast<vs_matrix *>(m);
+    ix.centroids = nullptr;
     ix.doc_ids = const_cast<uint64_t *>(d_doc_ids);
     ix.id_base = id_base;
     ix.n = m->n;
     ix.C = 1;
-    const GemmPlan pl = gemm_plan(m->view(), nq, k, d_doc_ids == nullptr, g_sm_count);
-    Arena a(c);
-    SearchSetup s;
-    VS(search_setup(c, a, &ix, nq, 1, k, gemm_scratch_bytes(pl, nq) + Arena::pad(nq * 4) + 4096, &s));
-    search_take(a, &ix, nq, &s);
-    uint32_t *d_status = a.take<uint32_t>(nq);
-    const int rc = gemm_search_core(c, a, &ix, queries->view(), k, s, pl, d_ids, d_sims, d_counts, d_status, stats_out);
-    ix.data = nullptr;
-    return rc;
+    return ix;
+}
+
+extern "C" int vs_search_batch_dev(vs_ctx *c, const vs_matrix *m, const uint64_t *d_doc_ids, uint64_t id_base,
+                                   const vs_matrix *queries, size_t k, uint64_t *d_ids, float *d_sims, int32_t *d_counts,
+                                   uint64_t *stats_out) {
+    VS(need_dev());
+    if (!c || !m) return fail(VS_EINVAL, "null argument");
+    const vs_index ix = flat_view(m, d_doc_ids, id_base);
+    return gemm_search_dev(c, &ix, queries, k, d_ids, d_sims, d_counts, stats_out);
+}
+
+extern "C" int vs_index_search_batch_dev(vs_ctx *c, const vs_index *ix, const vs_matrix *queries, size_t k, uint64_t *d_ids,
+                                         float *d_sims, int32_t *d_counts, uint64_t *stats_out) {
+    VS(search_check(c, ix));
+    return gemm_search_dev(c, ix, queries, k, d_ids, d_sims, d_counts, stats_out);
 }
 
 extern "C" int vs_search_flat_gemm(vs_ctx *c, const vs_matrix *m, const uint64_t *d_doc_ids, const uint8_t *queries, size_t nq,
                                    size_t k, uint64_t *ids_out, float *sims_out, int32_t *counts_out) {
-    if (!queries || !ids_out || !sims_out || !counts_out) return fail(VS_EINVAL, "null argument");
-    VS(gemm_check(c, m, nq, m ? (size_t)m->d : 0, k));
-    vs_index ix;
-    ix.data = const_cast<vs_matrix *>(m);
-    ix.doc_ids = const_cast<uint64_t *>(d_doc_ids);
-    ix.n = m->n;
-    ix.C = 1;
-    const size_t row_bytes = 8 + (size_t)m->d;
-    const GemmPlan pl = gemm_plan(m->view(), nq, k, d_doc_ids == nullptr, g_sm_count);
-    Arena a(c);
-    SearchSetup s;
-    const size_t out_bytes = Arena::pad(nq * k * 8) + Arena::pad(nq * k * 4) + 2 * Arena::pad(nq * 4) + 4096;
-    VS(search_setup(c, a, &ix, nq, 1, k, gemm_scratch_bytes(pl, nq) + temp_matrix_bytes(nq, row_bytes) + out_bytes, &s));
-    MatView qv;
-    int rc = temp_matrix(c, a, queries, nq, row_bytes, &qv);
-    if (rc == VS_OK) {
-        search_take(a, &ix, nq, &s);
-        uint64_t *d_ids = a.take<uint64_t>(nq * k);
-        float *d_sims = a.take<float>(nq * k);
-        int32_t *d_counts = a.take<int32_t>(nq);
-        uint32_t *d_status = a.take<uint32_t>(nq);
-        rc = gemm_search_core(c, a, &ix, qv, k, s, pl, d_ids, d_sims, d_counts, d_status, nullptr);
-        if (rc == VS_OK) {
-            cudaMemcpyAsync(ids_out, d_ids, nq * k * 8, cudaMemcpyDeviceToHost, c->stream);
-            cudaMemcpyAsync(sims_out, d_sims, nq * k * 4, cudaMemcpyDeviceToHost, c->stream);
-            cudaMemcpyAsync(counts_out, d_counts, nq * 4, cudaMemcpyDeviceToHost, c->stream);
-            const cudaError_t e = cudaStreamSynchronize(c->stream);
-            if (e != cudaSuccess) rc = fail(VS_ECUDA, "batched search: %s", cudaGetErrorString(e));
-        }
-    }
-    ix.data = nullptr;
-    return rc;
+    VS(need_dev());
+    if (!c || !m) return fail(VS_EINVAL, "null argument");
+    const vs_index ix = flat_view(m, d_doc_ids, 0);
+    return gemm_search_host(c, &ix, queries, nq, k, ids_out, sims_out, counts_out);
 }
 
 extern "C" int vs_topk_merge_dev(vs_ctx *c, const uint64_t *d_ids_in, const float *d_sims_in, const int32_t *d_counts_in,

@@ -89,6 +89,15 @@ class Index:
         _check(self._L.vs_search_dev(ctx.handle, self._h, queries.handle, int(nprobe), int(k), C.c_void_p(int(d_ids)),
                                      C.c_void_p(int(d_sims)), C.c_void_p(int(d_counts)), C.c_void_p(int(d_status))))
 
+    def SearchBatchDev(self, queries, k, d_ids, d_sims, d_counts, ctx=None):
+        """Query batch over the whole store (all lists) as a tensor-core GEMM; device-resident outputs (raw pointers).
+        Returns (candidates, queries finished by the scan, store tiles, sampled tiles, us pre-pass, us GEMM, us resolve, 0)."""
+        ctx = ctx or default_context()
+        stats = np.zeros(8, np.uint64)
+        _check(self._L.vs_index_search_batch_dev(ctx.handle, self._h, queries.handle, int(k), C.c_void_p(int(d_ids)),
+                                                 C.c_void_p(int(d_sims)), C.c_void_p(int(d_counts)), _p(stats)))
+        return tuple(int(x) for x in stats)
+
     def Resolve(self, queries, nprobe, k, d_ids, d_sims, d_counts, d_status, ctx=None):
         """Finish queries whose float32 roundings could not be certified (reads the status: synchronizes)."""
         ctx = ctx or default_context()

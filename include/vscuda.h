@@ -155,6 +155,8 @@ VS_API int vs_index_read_rows(vs_ctx *ctx, const vs_index *ix, size_t first, siz
 VS_API int vs_search(vs_ctx *ctx, const vs_index *ix, const uint8_t *queries_packed, size_t nq, size_t nprobe, size_t k,
               uint64_t *ids_out, float *sims_out, int32_t *counts_out);
 /* Brute force over a matrix (BASELINE config 1): same contract, ids = doc_ids[row] or row index. */
+/* (vs_search with nprobe >= lists and vs_search_flat hand batches of >= 64 queries over >= 65536 rows to the GEMM
+ * path below; smaller calls run one streaming scan per query.) */
 VS_API int vs_search_flat(vs_ctx *ctx, const vs_matrix *m, const uint64_t *d_doc_ids, const uint8_t *queries_packed,
                    size_t nq, size_t k, uint64_t *ids_out, float *sims_out, int32_t *counts_out);
 /* Query batches over the whole store as an int8 tensor-core GEMM (tcgen05.mma kind::i8) with a fused per-pair
@@ -171,6 +173,9 @@ VS_API int vs_search_flat_gemm(vs_ctx *ctx, const vs_matrix *m, const uint64_t *
 VS_API int vs_search_batch_dev(vs_ctx *ctx, const vs_matrix *m, const uint64_t *d_doc_ids, uint64_t id_base,
                         const vs_matrix *queries, size_t k, uint64_t *d_ids, float *d_sims, int32_t *d_counts,
                         uint64_t *stats_out);
+/* The same over the whole store of an index (nprobe = "all lists"), ids = the index's document ids. */
+VS_API int vs_index_search_batch_dev(vs_ctx *ctx, const vs_index *ix, const vs_matrix *queries, size_t k, uint64_t *d_ids,
+                              float *d_sims, int32_t *d_counts, uint64_t *stats_out);
 /* Device-resident search: queries already a device matrix; results stay in device buffers
  * (d_ids[nq*k], d_sims[nq*k], d_counts[nq], d_status[nq]); asynchronous on the ctx stream.
  * d_status bit0/bit1 = a float32 rounding could not be certified in the probe/list stage, bit2 =

@@ -104,3 +104,31 @@ def test_batch_gemm_literal_path(vs, oracle):
     assert ctx.slowpath_count() > 0
     _check_vs_oracle(oracle, rows, qs, ids, sims, counts, k)
     ctx.close()
+
+
+def test_index_all_lists_batch_dispatch_matches_scan(vs):
+    """vs_search with nprobe >= lists and a large batch is handed to the GEMM path (grouped store, document ids with
+    duplicates); it must return what the per-query scans return."""
+    import torch
+    n, d, C, nq, k = 70000, 768, 32, 70, 10
+    rows = noop_rows(n, d, 81)
+    lists = (np.arange(n) % C).astype(np.uint32)
+    doc = np.random.default_rng(5).integers(0, n // 2, n).astype(np.uint64)
+    ix = vs.ivf.Index.build_assigned(rows, doc, lists, rows[:C])
+    qs = noop_rows(nq, d, 82)
+    ids, sims, counts = ix.Search(qs, C, k)                      # >= 64 queries, all lists: GEMM path
+    parts = [ix.Search(qs[i:i + 16], C, k) for i in range(0, nq, 16)]   # small calls: streaming scans
+    ids2 = np.concatenate([p[0] for p in parts]); sims2 = np.concatenate([p[1] for p in parts])
+    counts2 = np.concatenate([p[2] for p in parts])
+    assert (counts == counts2).all() and (ids == ids2).all() and (f32_bits(sims) == f32_bits(sims2)).all()
+    # device-resident form over the index
+    qm = vs.compute.NewMatrix(qs)
+    dev = torch.device("cuda", 0)
+    d_ids = torch.zeros((nq, k), dtype=torch.int64, device=dev)
+    d_sims = torch.zeros((nq, k), dtype=torch.float32, device=dev)
+    d_counts = torch.zeros(nq, dtype=torch.int32, device=dev)
+    stats = ix.SearchBatchDev(qm, k, d_ids.data_ptr(), d_sims.data_ptr(), d_counts.data_ptr())
+    vs.compute.default_context().sync()
+    assert stats[2] == (n + 127) // 128
+    assert (d_ids.cpu().numpy().view(np.uint64) == ids2).all()
+    assert (f32_bits(d_sims.cpu().numpy()) == f32_bits(sims2)).all()
