@@ -54,6 +54,11 @@ def debug_set_certify_scale(scale):
     _check(_lib.init().vs_debug_set_certify_scale(C.c_float(scale)))
 
 
+def debug_set_argmax_gemm_min(min_centroids):
+    """Test hook: centroid count from which nearest-centroid assignment runs on the tensor cores."""
+    _check(_lib.init().vs_debug_set_argmax_gemm_min(int(min_centroids)))
+
+
 class Context:
     """One CUDA stream + scratch arena (vs_ctx). One per closure / goroutine (dnc/dnc.go:349)."""
 

@@ -63,6 +63,7 @@ struct GemmParams {
     int nstages;               // streamed-operand stages
     uint32_t tile_first, tile_stride, tile_count;  // store tiles of this launch: tile_first + i * tile_stride
     uint32_t nq_tiles;         // query tiles
+    uint32_t qsplit, qt_per;   // a work item = (store tile, range of qt_per query tiles); qsplit ranges per store tile
     const float4 *col_consts;  // [nq_tiles * 128]
     // MODE_FILTER
     unsigned int *cand_count;
@@ -300,6 +301,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tm_rows, const __grid_constant__
     const uint32_t tmem_base = *tmem_slot;
 
     const uint32_t nqt = p.nq_tiles;
+    const uint32_t n_items = p.tile_count * p.qsplit;
 
     // Every role loop is executed by its whole warp (waits are warp-convergent); the single-thread instructions
     // (TMA, tcgen05.mma, tcgen05.commit) are issued by one elected lane.  Ring positions are advanced
@@ -308,7 +310,8 @@ gemm_kernel(const __grid_constant__ CUtensorMap tm_rows, const __grid_constant__
         // ===== TMA producer =====
         const bool leader = elect_one();
         uint32_t acc_s = 0, acc_ph = 0, st = 0, bph = 0, li = 0;
-        for (uint32_t i = blockIdx.x; i < p.tile_count; i += gridDim.x, li++) {
+        for (uint32_t w = blockIdx.x; w < n_items; w += gridDim.x, li++) {
+            const uint32_t i = w / p.qsplit, qt0 = (w % p.qsplit) * p.qt_per, qt1 = min(nqt, qt0 + p.qt_per);
             const int row0 = (int)((p.tile_first + i * p.tile_stride) * kTM);
             for (int c = 0; c < kc; c++) {
                 mbar_wait(a_empty + 8 * c, (li & 1) ^ 1);
@@ -317,7 +320,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tm_rows, const __grid_constant__
                     tma_load_2d(sA + c * kChunkBytes, &tm_rows, c * kChunkK, row0, a_full + 8 * c);
                 }
             }
-            for (uint32_t qt = 0; qt < nqt; qt++) {
+            for (uint32_t qt = qt0; qt < qt1; qt++) {
                 mbar_wait(acc_empty + 8 * acc_s, acc_ph ^ 1);  // the epilogue has finished with this stage's constants
                 if (leader) {
                     mbar_expect_tx(q_full + 8 * acc_s, kTN * 16);
@@ -347,13 +350,14 @@ gemm_kernel(const __grid_constant__ CUtensorMap tm_rows, const __grid_constant__
         const uint64_t a_desc0 = desc_hi | (1ull << 16) | (uint64_t)((sA & 0x3FFFFu) >> 4);
         const uint64_t b_desc0 = desc_hi | (1ull << 16) | (uint64_t)((sB & 0x3FFFFu) >> 4);
         uint32_t acc_s = 0, acc_ph = 0, st = 0, bph = 0, li = 0;
-        for (uint32_t i = blockIdx.x; i < p.tile_count; i += gridDim.x, li++) {
-            for (uint32_t qt = 0; qt < nqt; qt++) {
+        for (uint32_t w = blockIdx.x; w < n_items; w += gridDim.x, li++) {
+            const uint32_t qt0 = (w % p.qsplit) * p.qt_per, qt1 = min(nqt, qt0 + p.qt_per);
+            for (uint32_t qt = qt0; qt < qt1; qt++) {
                 mbar_wait(acc_empty + 8 * acc_s, acc_ph ^ 1);
                 tc_fence_after();
                 const uint32_t d_tmem = tmem_base + acc_s * kTN;
                 for (int c = 0; c < kc; c++) {
-                    if (qt == 0) mbar_wait(a_full + 8 * c, li & 1);
+                    if (qt == qt0) mbar_wait(a_full + 8 * c, li & 1);
                     mbar_wait(b_full + 8 * st, bph);
                     tc_fence_after();
                     if (leader) {
@@ -364,7 +368,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tm_rows, const __grid_constant__
                             if (p.dbg != 5 || (c | k) == 0)  // profiling aid 5: one MMA per tile (epilogue-only timing)
                             tc_mma_i8(d_tmem, ad + 2 * k, bd + 2 * k, kIdesc, (c | k) != 0 ? 1u : 0u);
                         tc_commit(b_empty + 8 * st);
-                        if (qt == nqt - 1) tc_commit(a_empty + 8 * c);
+                        if (qt == qt1 - 1) tc_commit(a_empty + 8 * c);
                         if (c == kc - 1) tc_commit(acc_full + 8 * acc_s);
                     }
                     __syncwarp();
@@ -391,7 +395,8 @@ gemm_kernel(const __grid_constant__ CUtensorMap tm_rows, const __grid_constant__
         const int part = e >> 2;    // which slice of the query columns
         const int tc = lane & 3, tr = lane >> 2;
         uint32_t acc_s = 0, acc_ph = 0;
-        for (uint32_t i = blockIdx.x; i < p.tile_count; i += gridDim.x) {
+        for (uint32_t w = blockIdx.x; w < n_items; w += gridDim.x) {
+            const uint32_t i = w / p.qsplit, qt0 = (w % p.qsplit) * p.qt_per, qt1 = min(nqt, qt0 + p.qt_per);
             const uint32_t tile = p.tile_first + i * p.tile_stride;
             const uint32_t row_own = tile * kTM + qd * 32 + lane;
             const bool in_range = row_own < p.n;
@@ -419,7 +424,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tm_rows, const __grid_constant__
                 }
             }
             const uint32_t row_base = tile * kTM + qd * 32 + tr;
-            for (uint32_t qt = 0; qt < nqt; qt++) {
+            for (uint32_t qt = qt0; qt < qt1; qt++) {
                 mbar_wait(q_full + 8 * acc_s, acc_ph);
                 mbar_wait(acc_full + 8 * acc_s, acc_ph);
                 tc_fence_after();
@@ -868,32 +873,34 @@ size_t gemm_smem_bytes(int kc, int ns) {
 
 }  // namespace
 
-bool gemm_supported(const MatView &rows, size_t nq) {
-    return rows.d_pad <= kMaxKC * kChunkK && rows.n >= 1 && rows.n < 0x7FFFFF00ull && nq >= 1 && nq <= (size_t)kMaxStageQueries &&
-           (reinterpret_cast<uintptr_t>(rows.codes) & 15) == 0;
+bool gemm_store_supported(const MatView &rows) {
+    return rows.d_pad <= kMaxKC * kChunkK && rows.n >= 1 && rows.n < 0x7FFFFF00ull && (reinterpret_cast<uintptr_t>(rows.codes) & 15) == 0;
 }
+bool gemm_supported(const MatView &rows, size_t nq) { return gemm_store_supported(rows) && nq >= 1 && nq <= (size_t)kMaxStageQueries; }
 
-GemmPlan gemm_plan(const MatView &rows, size_t nq, size_t k, bool unique_ids, int sm_count) {
+GemmPlan gemm_plan(const MatView &rows, size_t nq, size_t k, bool unique_ids, uint32_t sample_div, uint32_t min_sample_tiles,
+                   size_t cand_per_query) {
     GemmPlan pl{};
     pl.nq_pad = (uint32_t)((nq + kTN - 1) / kTN * kTN);
     pl.tiles = (uint32_t)((rows.n + kTM - 1) / kTM);
     pl.rank = (uint32_t)(unique_ids ? k : 2 * k);
-    // sample about 1/64 of the store, at least 4 groups per wanted rank and one tile per SM, at most all of it
-    uint32_t want = pl.tiles / 64;
+    // sample about 1/sample_div of the store, at least one tile (8 groups) per wanted rank and min_sample_tiles, at most
+    // all of it
+    uint32_t want = pl.tiles / sample_div;
     if (want < pl.rank) want = pl.rank;
-    if (want < (uint32_t)sm_count) want = (uint32_t)sm_count;
+    if (want < min_sample_tiles) want = min_sample_tiles;
     if (want > pl.tiles) want = pl.tiles;
     pl.sample_stride = pl.tiles / want;
     if (pl.sample_stride < 1) pl.sample_stride = 1;
     pl.sample_tiles = (pl.tiles + pl.sample_stride - 1) / pl.sample_stride;
     pl.G = pl.sample_tiles * 8;  // one group maximum per 16 store rows
-    size_t cap = nq * (size_t)4096;
+    size_t cap = nq * cand_per_query;
     if (cap < (1u << 20)) cap = 1u << 20;
     if (cap > (64u << 20)) cap = 64u << 20;
     pl.cand_cap = (unsigned int)cap;
     size_t sort_tmp = 0;
     cub::DeviceRadixSort::SortPairs(nullptr, sort_tmp, (const uint32_t *)nullptr, (uint32_t *)nullptr, (const uint2 *)nullptr,
-                                    (uint2 *)nullptr, (int64_t)cap, 0, 13);
+                                    (uint2 *)nullptr, (int64_t)cap, 0, 20);
     pl.sort_tmp_bytes = sort_tmp;
     return pl;
 }
@@ -927,7 +934,8 @@ void gemm_take(char *base, const GemmPlan &pl, size_t nq, GemmBufs *b) {
 static cudaError_t launch_gemm(int mode, const CUtensorMap &tm_rows, const CUtensorMap &tm_q, const GemmParams &p, int sm_count,
                                cudaStream_t st) {
     const size_t smem = gemm_smem_bytes(p.kc, p.nstages);
-    unsigned grid = p.tile_count < (uint32_t)sm_count ? p.tile_count : (unsigned)sm_count;
+    const uint32_t n_items = p.tile_count * p.qsplit;
+    unsigned grid = n_items < (uint32_t)sm_count ? n_items : (unsigned)sm_count;
     if (grid == 0) return cudaSuccess;
     cudaError_t e;
     if (mode == MODE_FILTER) {
@@ -940,6 +948,19 @@ static cudaError_t launch_gemm(int mode, const CUtensorMap &tm_rows, const CUten
         gemm_kernel<MODE_GROUPMAX><<<grid, kGemmThreads, smem, st>>>(tm_rows, tm_q, p);
     }
     return cudaGetLastError();
+}
+
+// A store with few tiles is cut into (store tile, query-tile range) work items so that every SM has several; a range keeps
+// at least 4 query tiles so that reloading the resident store tile stays amortized.  Every range is non-empty.
+static void gemm_split(GemmParams &p, int sm_count) {
+    uint32_t qs = 1;
+    if (p.tile_count < 4u * (uint32_t)sm_count && p.tile_count > 0) {
+        qs = (4u * (uint32_t)sm_count + p.tile_count - 1) / p.tile_count;
+        const uint32_t max_qs = p.nq_tiles / 4 > 1 ? p.nq_tiles / 4 : 1;
+        if (qs > max_qs) qs = max_qs;
+    }
+    p.qt_per = (p.nq_tiles + qs - 1) / qs;
+    p.qsplit = (p.nq_tiles + p.qt_per - 1) / p.qt_per;
 }
 
 static GemmParams gemm_params(const MatView &rows, const GemmPlan &pl, const GemmBufs &b) {
@@ -979,6 +1000,7 @@ cudaError_t gemm_enqueue_prepass(const MatView &rows, const MatView &queries, co
     p.tile_first = 0;
     p.tile_stride = pl.sample_stride;
     p.tile_count = pl.sample_tiles;
+    gemm_split(p, sm_count);
     e = launch_gemm(MODE_GROUPMAX, tm_rows, tm_q, p, sm_count, st);
     if (e != cudaSuccess) return e;
     threshold_kernel<<<pl.nq_pad, kThrThreads, pl.G * sizeof(int), st>>>(queries, pl.nq_pad, b.gmax, pl.G, pl.rank, b.bounds,
@@ -996,6 +1018,7 @@ cudaError_t gemm_enqueue_filter(const MatView &rows, const MatView &queries, con
     p.tile_first = 0;
     p.tile_stride = 1;
     p.tile_count = pl.tiles;
+    gemm_split(p, sm_count);
     const cudaError_t e = launch_gemm(MODE_FILTER, tm_rows, tm_q, p, sm_count, st);
     if (e != cudaSuccess) return e;
     if (launches) *launches += 1;
@@ -1009,7 +1032,7 @@ cudaError_t gemm_enqueue_select(const MatView &rows, const uint64_t *ids, uint64
     const uint32_t nq = (uint32_t)queries.n;
     size_t tmp = pl.sort_tmp_bytes;
     int bits = 1;
-    while ((1u << bits) < nq + 1 && bits < 13) bits++;
+    while ((1u << bits) < nq + 1 && bits < 20) bits++;
     cudaError_t e = cudaSuccess;
     if (cand_count)
         e = cub::DeviceRadixSort::SortPairs(b.sort_tmp, tmp, b.cand_q, b.cand_q_sorted, b.cand_rowdot, b.cand_rowdot_sorted,

@@ -20,6 +20,8 @@ struct vs_ctx {
     void *pinned = nullptr;
     size_t pinned_cap = 0;
     bool owns_stream = true;
+    void *aux = nullptr;      // second device buffer (tensor-core assignment): lives beside the arena, grown on demand
+    size_t aux_cap = 0;
     unsigned long long *d_fix_counter = nullptr;  // in-kernel literal re-scores (device)
     unsigned int *d_tickets = nullptr;            // [kMaxStageQueries] zeroed once; every launch re-arms them
     unsigned long long *d_trace = nullptr;        // phase stamps of the last list-scan launch (when enabled)
@@ -139,8 +141,10 @@ struct GemmBufs {
     uint2 *cand_rowdot, *cand_rowdot_sorted;
     void *sort_tmp;
 };
+bool gemm_store_supported(const MatView &rows);
 bool gemm_supported(const MatView &rows, size_t nq);
-GemmPlan gemm_plan(const MatView &rows, size_t nq, size_t k, bool unique_ids, int sm_count);
+GemmPlan gemm_plan(const MatView &rows, size_t nq, size_t k, bool unique_ids, uint32_t sample_div, uint32_t min_sample_tiles,
+                   size_t cand_per_query);
 size_t gemm_scratch_bytes(const GemmPlan &pl, size_t nq);
 void gemm_take(char *base, const GemmPlan &pl, size_t nq, GemmBufs *b);
 cudaError_t gemm_enqueue_prepass(const MatView &rows, const MatView &queries, const GemmPlan &pl, const GemmBufs &b, uint32_t *d_status,

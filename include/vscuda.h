@@ -62,6 +62,9 @@ VS_API uint64_t vs_ctx_slowpath_count(const vs_ctx *ctx);/* rows / queries that 
 /* Test hook: multiply every certification half-width by scale >= 1 so that rows are sent
  * through the literal reference-arithmetic paths; results must not change.  Process-wide; 1.0 = production. */
 VS_API int vs_debug_set_certify_scale(float scale);
+/* Test hook: from how many centroids on vs_argmax_MxN / vs_kmeans_step assign through the tensor-core GEMM
+ * (default 256; below that the HBM-bound dp4a scan of the data rows is faster). */
+VS_API int vs_debug_set_argmax_gemm_min(size_t min_centroids);
 /* CUDA-event timing on the ctx stream (bench.py): start/stop bracket, elapsed in ms after sync. */
 VS_API int vs_ctx_timer_start(vs_ctx *ctx);
 VS_API int vs_ctx_timer_stop(vs_ctx *ctx, float *ms_out);
