@@ -1169,27 +1169,22 @@ static int gemm_search_core(vs_ctx *c, Arena &a, const vs_index *ix, const MatVi
     CU(gemm_enqueue_filter(rows, qv, pl, gb, g_sm_count, c->stream, &c->launches));
     VS(prof_mark(c));
     CU(phase(2));
-    VS(pinned_reserve(c, nq * 4 + 64));
+    VS(pinned_reserve(c, nq * 8 + 64));
     uint32_t *h_status = static_cast<uint32_t *>(c->pinned);
-    unsigned int *h_count = reinterpret_cast<unsigned int *>(h_status + nq);
-    CU(cudaMemcpyAsync(h_count, gb.bounds + 4, sizeof(unsigned int), cudaMemcpyDeviceToHost, c->stream));
-    CU(cudaStreamSynchronize(c->stream));
-    const unsigned int cand = *h_count;
+    unsigned int *h_cnt = reinterpret_cast<unsigned int *>(h_status + nq);
     std::vector<uint32_t> sel;
-    if (cand > pl.cand_cap) {  // thresholds too loose for the candidate list: the scan answers everything
-        for (size_t i = 0; i < nq; i++) sel.push_back((uint32_t)i);
-    } else {
-        CU(gemm_enqueue_select(rows, ix->doc_ids, ix->id_base, qv, pl, gb, cand, (int)k, d_ids, d_sims, d_counts, d_status,
-                               c->d_fix_counter, c->stream, &c->launches));
-        CU(cudaMemcpyAsync(h_status, d_status, nq * 4, cudaMemcpyDeviceToHost, c->stream));
-        CU(cudaStreamSynchronize(c->stream));
-        for (size_t i = 0; i < nq; i++)
-            if (h_status[i] & kStatusNeedMore) sel.push_back((uint32_t)i);
-    }
+    CU(gemm_enqueue_select(rows, ix->doc_ids, ix->id_base, ix->doc_ids == nullptr, qv, pl, gb, (int)k, d_ids, d_sims, d_counts, d_status, c->d_fix_counter,
+                           g_sm_count, c->stream, &c->launches));
+    CU(cudaMemcpyAsync(h_status, d_status, nq * 4, cudaMemcpyDeviceToHost, c->stream));
+    if (stats) CU(cudaMemcpyAsync(h_cnt, gb.cand_cnt, nq * 4, cudaMemcpyDeviceToHost, c->stream));
+    CU(cudaStreamSynchronize(c->stream));
+    for (size_t i = 0; i < nq; i++)
+        if (h_status[i] & kStatusNeedMore) sel.push_back((uint32_t)i);
     CU(phase(3));
     if (stats) {
         CU(cudaEventSynchronize(c->phase_ev[3]));
-        stats[0] = cand;
+        stats[0] = 0;
+        for (size_t i = 0; i < nq; i++) stats[0] += h_cnt[i];
         stats[1] = sel.size();
         stats[2] = pl.tiles;
         stats[3] = pl.sample_tiles;
@@ -1333,6 +1328,14 @@ __global__ void argmax_from_top2_kernel(const uint64_t *ids, const float *sims, 
     }
 }
 
+__global__ void scatter_assign_kernel(const uint32_t *work, unsigned int cnt, const int32_t *w_idx, const float *w_sims,
+                                      int32_t *idx_out, float *sims_out) {
+    const unsigned int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= cnt) return;
+    idx_out[work[i]] = w_idx[i];
+    if (sims_out) sims_out[work[i]] = w_sims[i];
+}
+
 static int aux_reserve(vs_ctx *c, size_t bytes) {
     if (bytes <= c->aux_cap) return VS_OK;
     CU(cudaStreamSynchronize(c->stream));
@@ -1353,7 +1356,7 @@ static int argmax_gemm_dev(vs_ctx *c, const MatView &cent, const MatView &data, 
     const size_t nb_max = n < kArgmaxGemmBatch ? n : kArgmaxGemmBatch;
     const int k = 2;
     // plan for the largest batch; the store may shrink below when duplicates are dropped (only fewer tiles)
-    GemmPlan pl = gemm_plan(cent, nb_max, k, true, 16, 1, 256);
+    GemmPlan pl = gemm_plan(cent, nb_max, k, true, 16, 1, 1024);
     auto pad = [](size_t b) { return (b + 255) & ~size_t(255); };
     const size_t store_bytes = pad(M * (size_t)cent.d_pad) + pad(M * 8) * 2 + pad(M * 8);
     const size_t bytes = pad(M * 4) * 2 + store_bytes + gemm_scratch_bytes(pl, nb_max) + pad(nb_max * k * 8) + pad(nb_max * k * 4) +
@@ -1403,25 +1406,16 @@ static int argmax_gemm_dev(vs_ctx *c, const MatView &cent, const MatView &data, 
     for (size_t r0 = 0; r0 < n; r0 += kArgmaxGemmBatch) {
         const size_t nb = n - r0 < kArgmaxGemmBatch ? n - r0 : kArgmaxGemmBatch;
         const MatView q{data.codes + r0 * (size_t)data.d_pad, data.hdr + r0, data.sums + r0, nb, data.d, data.d_pad};
-        GemmPlan plb = gemm_plan(store, nb, k, true, 16, 1, 256);
-        plb.sort_tmp_bytes = pl.sort_tmp_bytes;
-        if (plb.cand_cap > pl.cand_cap || plb.G > pl.G) return fail(VS_EINVAL, "assignment plan grew");
+        GemmPlan plb = gemm_plan(store, nb, k, true, 16, 1, 1024);
+        if (plb.cand_per_q > pl.cand_per_q || plb.G > pl.G || plb.nq_pad > pl.nq_pad) return fail(VS_EINVAL, "assignment plan grew");
         GemmBufs gb;
         gemm_take(g_scratch, plb, nb, &gb);
         CU(gemm_enqueue_prepass(store, q, plb, gb, t_status, g_sm_count, c->stream, &c->launches));
         VS(prof_mark(c));
         CU(gemm_enqueue_filter(store, q, plb, gb, g_sm_count, c->stream, &c->launches));
         VS(prof_mark(c));
-        CU(cudaMemcpyAsync(h_count, gb.bounds + 4, sizeof(unsigned int), cudaMemcpyDeviceToHost, c->stream));
-        CU(cudaStreamSynchronize(c->stream));
-        const unsigned int cand = *h_count;
-        if (cand > plb.cand_cap) {  // thresholds too loose (degenerate data): every row of the batch takes the literal path
-            CU(cudaMemsetAsync(t_status, 0xFF, nb * 4, c->stream));
-            CU(cudaMemsetAsync(t_counts, 0, nb * 4, c->stream));
-        } else {
-            CU(gemm_enqueue_select(store, store_ids, 0, q, plb, gb, cand, k, t_ids, t_sims, t_counts, t_status, c->d_fix_counter,
-                                   c->stream, &c->launches));
-        }
+        CU(gemm_enqueue_select(store, store_ids, 0, true, q, plb, gb, k, t_ids, t_sims, t_counts, t_status, c->d_fix_counter, g_sm_count,
+                               c->stream, &c->launches));
         argmax_from_top2_kernel<<<(unsigned)((nb + 255) / 256), 256, 0, c->stream>>>(t_ids, t_sims, t_counts, t_status, (uint32_t)nb,
                                                                                     (uint32_t)r0, k, d_idx, d_sims, d_work, d_wcount);
         c->launches++;
@@ -1430,15 +1424,49 @@ static int argmax_gemm_dev(vs_ctx *c, const MatView &cent, const MatView &data, 
     CU(cudaStreamSynchronize(c->stream));
     const unsigned int cnt = *h_count;
     if (cnt > 0) {
-        double *d_cn = nullptr;
-        CU(cudaMalloc(&d_cn, M * (size_t)cent.d * sizeof(double)));
-        cudaError_t e = launch_query_normalize(cent, d_cn, c->stream);
-        if (e == cudaSuccess) e = launch_argmax_fix(cent, data, d_cn, d_idx, d_sims, d_work, d_wcount, g_sm_count, c->stream);
+        // Rows the float32 top-2 could not decide: the scan form on just those rows (float64 intervals separate almost
+        // all of them), then literal arithmetic for what is left (true ties).  Rare, so plain allocations.
+        char *tmp = nullptr;
+        const size_t wb = pad((size_t)cnt * data.d_pad) + pad((size_t)cnt * 8) * 2 + pad((size_t)cnt * 4) * 3 + 256;
+        CU(cudaMalloc(&tmp, wb));
+        size_t o = 0;
+        auto sub = [&](size_t bts) {
+            char *p = tmp + o;
+            o += pad(bts);
+            return p;
+        };
+        uint8_t *w_codes = reinterpret_cast<uint8_t *>(sub((size_t)cnt * data.d_pad));
+        float2 *w_hdr = reinterpret_cast<float2 *>(sub((size_t)cnt * 8));
+        uint2 *w_sums = reinterpret_cast<uint2 *>(sub((size_t)cnt * 8));
+        int32_t *w_idx = reinterpret_cast<int32_t *>(sub((size_t)cnt * 4));
+        float *w_sims = reinterpret_cast<float *>(sub((size_t)cnt * 4));
+        uint32_t *w_work = reinterpret_cast<uint32_t *>(sub((size_t)cnt * 4));
+        unsigned int *w_count = reinterpret_cast<unsigned int *>(sub(64));
+        const MatView wdata{w_codes, w_hdr, w_sums, cnt, data.d, data.d_pad};
+        cudaError_t e = launch_gather_rows(data, d_work, cnt, w_codes, w_hdr, w_sums, nullptr, 0, nullptr, c->stream);
+        if (e == cudaSuccess) e = cudaMemsetAsync(w_count, 0, sizeof(unsigned int), c->stream);
+        if (e == cudaSuccess) e = launch_argmax(cent, wdata, d_canon, w_idx, d_sims ? w_sims : nullptr, w_work, w_count, g_sm_count, c->stream);
+        if (e == cudaSuccess) e = cudaMemcpyAsync(h_count, w_count, sizeof(unsigned int), cudaMemcpyDeviceToHost, c->stream);
         if (e == cudaSuccess) e = cudaStreamSynchronize(c->stream);
-        cudaFree(d_cn);
-        if (e != cudaSuccess) return fail(VS_ECUDA, "argmax fix: %s", cudaGetErrorString(e));
         c->launches += 2;
-        c->slowpath += cnt;
+        const unsigned int cnt2 = e == cudaSuccess ? *h_count : 0;
+        if (e == cudaSuccess && cnt2 > 0) {
+            double *d_cn = nullptr;
+            e = cudaMalloc(&d_cn, M * (size_t)cent.d * sizeof(double));
+            if (e == cudaSuccess) e = launch_query_normalize(cent, d_cn, c->stream);
+            if (e == cudaSuccess) e = launch_argmax_fix(cent, wdata, d_cn, w_idx, d_sims ? w_sims : nullptr, w_work, w_count, g_sm_count, c->stream);
+            if (e == cudaSuccess) e = cudaStreamSynchronize(c->stream);
+            if (d_cn) cudaFree(d_cn);
+            c->launches += 2;
+            c->slowpath += cnt2;
+        }
+        if (e == cudaSuccess) {
+            scatter_assign_kernel<<<(cnt + 255) / 256, 256, 0, c->stream>>>(d_work, cnt, w_idx, w_sims, d_idx, d_sims);
+            c->launches++;
+            e = cudaStreamSynchronize(c->stream);
+        }
+        cudaFree(tmp);
+        if (e != cudaSuccess) return fail(VS_ECUDA, "assignment fallback: %s", cudaGetErrorString(e));
     }
     *done = true;
     return VS_OK;

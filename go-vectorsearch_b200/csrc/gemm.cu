@@ -29,8 +29,6 @@
 #include <stdint.h>
 #include <stdlib.h>
 
-#include <cub/device/device_radix_sort.cuh>
-
 #include "internal.h"
 
 namespace vs {
@@ -65,11 +63,10 @@ struct GemmParams {
     uint32_t nq_tiles;         // query tiles
     uint32_t qsplit, qt_per;   // a work item = (store tile, range of qt_per query tiles); qsplit ranges per store tile
     const float4 *col_consts;  // [nq_tiles * 128]
-    // MODE_FILTER
-    unsigned int *cand_count;
-    uint32_t *cand_q;
-    uint2 *cand_rowdot;
-    unsigned int cand_cap;
+    // MODE_FILTER: one bucket of cand_per_q (row, dot) pairs per query, filled through a per-query counter
+    unsigned int *cand_cnt;    // [nq_pad]
+    uint2 *cand_rowdot;        // [nq_pad][cand_per_q]
+    uint32_t cand_per_q;
     // MODE_GROUPMAX
     float *gmax;               // [nq_pad][G]
     uint32_t G;
@@ -449,7 +446,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tm_rows, const __grid_constant__
                         tc_ld_16x256b_x4(tmem_base + ((uint32_t)(qd * 32 + lh * 16) << 16) + acc_s * kTN + colbase, v);
                         tc_ld_wait();
                         if (p.dbg == 1) {
-                            if (v[0] == 0xFFFFFFFFu && v[15] == 0xFFFFFFFEu) p.cand_q[0] = 0;
+                            if (v[0] == 0xFFFFFFFFu && v[15] == 0xFFFFFFFEu) p.cand_cnt[0] = 0;
                             continue;
                         }
                         // registers 4n + {0,1}: row tr + 16 lh, columns 8n + 2 tc + {0,1}; 4n + {2,3}: row + 8
@@ -480,11 +477,11 @@ gemm_kernel(const __grid_constant__ CUtensorMap tm_rows, const __grid_constant__
 #pragma unroll
                                     for (int c = 0; c < 4; c++) {
                                         if (dot_as_f8(v[4 * n + c]) >= T[c]) {
-                                            const unsigned int pos = atomicAdd(p.cand_count, 1u);
-                                            if (pos < p.cand_cap) {
-                                                p.cand_q[pos] = qt * kTN + colbase + 8 * n + 2 * tc + (c & 1);
-                                                p.cand_rowdot[pos] = make_uint2(row_base + 16 * lh + ((c & 2) ? 8 : 0), v[4 * n + c]);
-                                            }
+                                            const uint32_t q = qt * kTN + colbase + 8 * n + 2 * tc + (c & 1);
+                                            const unsigned int pos = atomicAdd(p.cand_cnt + q, 1u);
+                                            if (pos < p.cand_per_q)
+                                                p.cand_rowdot[(size_t)q * p.cand_per_q + pos] =
+                                                    make_uint2(row_base + 16 * lh + ((c & 2) ? 8 : 0), v[4 * n + c]);
                                         }
                                     }
                                 }
@@ -607,39 +604,12 @@ __global__ void query_consts_groupmax_kernel(MatView queries, uint32_t nq_pad, f
     store_col_const(out, q, o);
 }
 
-// One block per query: tau = (r-th largest group maximum) - slack; writes the filter's column constants
-// (tau', -A', -e', 2^23*8 - m) / 8, tau itself, and flags unusable queries for the streaming-scan fallback.
-constexpr int kThrThreads = 128;
-__global__ void __launch_bounds__(kThrThreads)
-threshold_kernel(MatView queries, uint32_t nq_pad, const float *gmax, uint32_t G, uint32_t r, const unsigned int *bounds,
-                 float4 *col_consts, float *tau_out, uint32_t *status) {
-    extern __shared__ int s_keys[];
-    __shared__ unsigned int s_cnt;
-    const uint32_t q = blockIdx.x;
+// tau = (r-th largest group maximum) - slack; writes the filter's column constants (tau', -A', -e', 2^23*8 - m) / 8,
+// tau itself, and flags unusable queries for the caller's fallback.  kth_key = ordered-int image of the r-th largest.
+__device__ __forceinline__ void threshold_finish(const MatView &queries, uint32_t q, int kth_key, uint32_t G, uint32_t r,
+                                                 const unsigned int *bounds, float4 *col_consts, float *tau_out, uint32_t *status) {
     const float ninf = __int_as_float(0xFF800000), pinf = __int_as_float(0x7F800000);
-    if (q >= queries.n) {  // padding columns never pass
-        if (threadIdx.x == 0) store_col_const(col_consts, q, make_float4(0.f, 0.f, 0.f, pinf));
-        return;
-    }
-    for (uint32_t g = threadIdx.x; g < G; g += kThrThreads) s_keys[g] = f32_ordered(gmax[(size_t)q * G + g]);
-    __syncthreads();
-    // r-th largest key by bisection over the ordered-int domain (largest x with count(key >= x) >= r)
-    long long lo = (long long)(int)0x80000000, hi = 0x7FFFFFFFll;
-    while (lo < hi) {
-        const long long mid = lo + (hi - lo + 1) / 2;
-        if (threadIdx.x == 0) s_cnt = 0;
-        __syncthreads();
-        unsigned int c = 0;
-        for (uint32_t g = threadIdx.x; g < G; g += kThrThreads) c += (long long)s_keys[g] >= mid;
-        for (int o = 16; o; o >>= 1) c += __shfl_xor_sync(0xFFFFFFFFu, c, o);
-        if ((threadIdx.x & 31) == 0 && c) atomicAdd(&s_cnt, c);
-        __syncthreads();
-        if (s_cnt >= r) lo = mid;
-        else hi = mid - 1;
-        __syncthreads();
-    }
-    if (threadIdx.x != 0) return;
-    float kth = ordered_f32((int)lo);
+    float kth = ordered_f32(kth_key);
     if (G < r || !(kth == kth)) kth = ninf;
     const float2 h = queries.hdr[q];
     const uint2 s = queries.sums[q];
@@ -669,21 +639,76 @@ threshold_kernel(MatView queries, uint32_t nq_pad, const float *gmax, uint32_t G
     store_col_const(col_consts, q, make_float4((float)(tp * 0.125), (float)(-qs.Ap * 0.125), (float)(-qs.ep * 0.125), (float)(8388608.0 - m * 0.125)));
 }
 
-// ---- candidate resolution -------------------------------------------------------------------------------------
-__global__ void segment_offsets_kernel(const uint32_t *sorted_q, unsigned int count, uint32_t nq, uint32_t *seg_off) {
-    const uint32_t q = blockIdx.x * blockDim.x + threadIdx.x;
-    if (q > nq) return;
-    unsigned int lo = 0, hi = count;  // first index with sorted_q[idx] >= q
-    while (lo < hi) {
-        const unsigned int mid = (lo + hi) >> 1;
-        if (sorted_q[mid] < q) lo = mid + 1;
-        else hi = mid;
+// One block per query (many groups: large stores).  The r-th largest key by bisection over the ordered-int domain.
+constexpr int kThrThreads = 128;
+__global__ void __launch_bounds__(kThrThreads)
+threshold_kernel(MatView queries, uint32_t nq_pad, const float *gmax, uint32_t G, uint32_t r, const unsigned int *bounds,
+                 float4 *col_consts, float *tau_out, uint32_t *status) {
+    extern __shared__ int s_keys[];
+    __shared__ unsigned int s_cnt;
+    const uint32_t q = blockIdx.x;
+    if (q >= queries.n) {  // padding columns never pass
+        if (threadIdx.x == 0) store_col_const(col_consts, q, make_float4(0.f, 0.f, 0.f, __int_as_float(0x7F800000)));
+        return;
     }
-    seg_off[q] = lo;
+    for (uint32_t g = threadIdx.x; g < G; g += kThrThreads) s_keys[g] = f32_ordered(gmax[(size_t)q * G + g]);
+    __syncthreads();
+    long long lo = (long long)(int)0x80000000, hi = 0x7FFFFFFFll;  // largest x with count(key >= x) >= r
+    while (lo < hi) {
+        const long long mid = lo + (hi - lo + 1) / 2;
+        if (threadIdx.x == 0) s_cnt = 0;
+        __syncthreads();
+        unsigned int c = 0;
+        for (uint32_t g = threadIdx.x; g < G; g += kThrThreads) c += (long long)s_keys[g] >= mid;
+        for (int o = 16; o; o >>= 1) c += __shfl_xor_sync(0xFFFFFFFFu, c, o);
+        if ((threadIdx.x & 31) == 0 && c) atomicAdd(&s_cnt, c);
+        __syncthreads();
+        if (s_cnt >= r) lo = mid;
+        else hi = mid - 1;
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) threshold_finish(queries, q, (int)lo, G, r, bounds, col_consts, tau_out, status);
 }
 
+// One warp per query (few groups: many queries against a small store, the assignment shape): the same bisection with
+// the keys in registers (KPL per lane) and warp reductions, no block barriers.
+template <int KPL>
+__global__ void __launch_bounds__(128)
+threshold_warp_kernel(MatView queries, uint32_t nq_pad, const float *gmax, uint32_t G, uint32_t r, const unsigned int *bounds,
+                      float4 *col_consts, float *tau_out, uint32_t *status) {
+    const int lane = threadIdx.x & 31;
+    const uint32_t nwarps = gridDim.x * (blockDim.x >> 5);
+    for (uint32_t q = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5); q < nq_pad; q += nwarps) {
+        if (q >= queries.n) {
+            if (lane == 0) store_col_const(col_consts, q, make_float4(0.f, 0.f, 0.f, __int_as_float(0x7F800000)));
+            continue;
+        }
+        int keys[KPL];
+#pragma unroll
+        for (int j = 0; j < KPL; j++) {
+            const uint32_t g = (uint32_t)j * 32 + lane;
+            keys[j] = g < G ? f32_ordered(gmax[(size_t)q * G + g]) : (int)0x80000000;
+        }
+        // padding keys are the domain minimum: they only matter when fewer than r real keys exist (handled by G < r)
+        long long lo = (long long)(int)0x80000000, hi = 0x7FFFFFFFll;
+        while (lo < hi) {
+            const int mid = (int)(lo + (hi - lo + 1) / 2);  // lo < mid <= hi: inside the int domain
+            unsigned int c = 0;
+#pragma unroll
+            for (int j = 0; j < KPL; j++) c += keys[j] >= mid;
+            c = __reduce_add_sync(0xFFFFFFFFu, c);
+            if (c >= r) lo = mid;
+            else hi = (long long)mid - 1;
+        }
+        if (lane == 0) threshold_finish(queries, q, (int)lo, G, r, bounds, col_consts, tau_out, status);
+    }
+}
+
+// ---- candidate resolution -------------------------------------------------------------------------------------
 constexpr int kSelThreads = 256;
-constexpr int kSelCap = 4096;  // candidates per query held in shared memory
+constexpr int kSelCap = 4096;      // candidates per query the block kernel holds in shared memory (= the largest bucket)
+constexpr int kSelWarpCap = 128;   // candidates per query the warp kernel holds in registers (4 per lane)
+constexpr uint32_t kStatusDeferred = 0x100u;  // internal: the warp kernel hands a query with uncertified candidates on
 
 struct SelEntry {
     uint32_t key;   // f32_to_key of the float32 similarity; 0 = removed
@@ -691,12 +716,119 @@ struct SelEntry {
     uint64_t id;
 };
 
-// One block per query: certified scores of its candidates, literal re-score where needed, then k rounds of
-// "best remaining (similarity desc, id asc), drop every other entry of that document" (search.go:256-270).
+// One warp per query with at most kSelWarpCap candidates (the assignment shape: tens of candidates for each of many
+// queries): certified scores in registers, then k rounds of "best remaining (similarity desc, id asc), drop every other
+// entry of that document" (search.go:256-270) by warp reductions.  A query with a candidate whose float32 rounding is
+// not certified is left to select_kernel (literal arithmetic needs the normalized query in shared memory).
+// Lower bound of the key of an entry whose float32 rounding is not certified: the true similarity is the float32 just
+// below the stored (upper) one -- two keys down at most, the key of -0 being unused -- or unknown (stored 2.0).
+__device__ __forceinline__ uint32_t key_lower_bound(uint32_t key, bool flagged) {
+    if (!flagged) return key;
+    return (key == f32_to_key(2.0f) || key < 4u) ? 1u : key - 2u;
+}
+
 __global__ void __launch_bounds__(kSelThreads)
-select_kernel(MatView rows, const uint64_t *ids, uint64_t id_base, MatView queries, const uint32_t *seg_off, const uint2 *cand_rowdot,
-              const float *tau, int k, uint64_t *out_ids, float *out_sims, int32_t *out_counts, uint32_t *status,
-              unsigned long long *fix_counter) {
+select_warp_kernel(MatView rows, const uint64_t *ids, uint64_t id_base, int unique_ids, MatView queries, const unsigned int *cand_cnt,
+                   const uint2 *cand_rowdot, uint32_t cand_per_q, const float *tau, int k, uint64_t *out_ids, float *out_sims,
+                   int32_t *out_counts, uint32_t *status) {
+    const int lane = threadIdx.x & 31;
+    const uint32_t nwarps = gridDim.x * (kSelThreads / 32);
+    const int D = rows.d;
+    for (uint32_t q = blockIdx.x * (kSelThreads / 32) + (threadIdx.x >> 5); q < (uint32_t)queries.n; q += nwarps) {
+        const uint32_t st = status[q];
+        if (st & kStatusNeedMore) continue;
+        const uint32_t cnt = cand_cnt[q];
+        if (cnt > (uint32_t)kSelWarpCap || cnt > cand_per_q) continue;  // the block kernel's
+        const float2 qh = queries.hdr[q];
+        const uint2 qs = queries.sums[q];
+        const SideConst xq = make_side(qh.x, qh.y, qs.x, qs.y, D);
+        uint32_t key[kSelWarpCap / 32];
+        uint64_t id[kSelWarpCap / 32];
+        uint32_t flags = 0;
+        bool any_flag = false;
+#pragma unroll
+        for (int s = 0; s < kSelWarpCap / 32; s++) {
+            const uint32_t e = (uint32_t)s * 32 + lane;
+            key[s] = 0;
+            id[s] = kEmptyId;
+            if (e < cnt) {
+                const uint2 rd = cand_rowdot[(size_t)q * cand_per_q + e];
+                const float2 h = rows.hdr[rd.x];
+                const uint2 sm = rows.sums[rd.x];
+                bool flag;
+                const float sim = score_fast(xq, h.x, h.y, sm.x, sm.y, rd.y, D, &flag);
+                key[s] = f32_to_key(sim);
+                id[s] = ids ? ids[rd.x] : id_base + rd.x;
+                any_flag |= flag;
+                flags |= flag ? (1u << s) : 0u;
+            }
+        }
+        any_flag = __any_sync(0xFFFFFFFFu, any_flag);
+        if (any_flag && unique_ids && cnt >= (uint32_t)k) {
+            // With one entry per document the k-th largest lower bound L is a floor of the k-th best similarity: an
+            // uncertified entry whose upper value is below L cannot be among the top k and needs no literal re-score.
+            uint32_t lo = 0, hi = 0xFFFFFFFFu;  // largest x with count(lower bound >= x) >= k
+            while (lo < hi) {
+                const uint32_t mid = lo + (hi - lo) / 2 + 1;
+                unsigned int c = 0;
+#pragma unroll
+                for (int s = 0; s < kSelWarpCap / 32; s++) c += key[s] != 0 && key_lower_bound(key[s], (flags >> s) & 1u) >= mid;
+                c = __reduce_add_sync(0xFFFFFFFFu, c);
+                if (c >= (unsigned int)k) lo = mid;
+                else hi = mid - 1;
+            }
+            bool need = false;
+#pragma unroll
+            for (int s = 0; s < kSelWarpCap / 32; s++) need |= ((flags >> s) & 1u) && key[s] >= lo;
+            any_flag = __any_sync(0xFFFFFFFFu, need);
+        }
+        if (any_flag) {
+            if (lane == 0) status[q] = st | kStatusDeferred;
+            continue;
+        }
+        const uint32_t tau_key = f32_to_key(tau[q]);
+        int emitted = 0, emitted_above = 0;
+        for (int round = 0; round < k; round++) {
+            uint32_t bk = 0;
+            uint64_t bid = kEmptyId;
+#pragma unroll
+            for (int s = 0; s < kSelWarpCap / 32; s++)
+                if (key[s] != 0 && (bk == 0 || cand_better(key[s], id[s], bk, bid))) {
+                    bk = key[s];
+                    bid = id[s];
+                }
+            for (int o = 16; o; o >>= 1) {
+                const uint32_t ok = __shfl_xor_sync(0xFFFFFFFFu, bk, o);
+                const uint64_t oid = __shfl_xor_sync(0xFFFFFFFFu, bid, o);
+                if (ok != 0 && (bk == 0 || cand_better(ok, oid, bk, bid))) {
+                    bk = ok;
+                    bid = oid;
+                }
+            }
+            if (bk == 0) break;
+            if (lane == 0) {
+                out_ids[(size_t)q * k + round] = bid;
+                out_sims[(size_t)q * k + round] = key_to_f32(bk);
+            }
+            emitted++;
+            if (bk >= tau_key && bk != 1u) emitted_above++;
+#pragma unroll
+            for (int s = 0; s < kSelWarpCap / 32; s++)
+                if (id[s] == bid) key[s] = 0;  // one hit per document
+        }
+        if (lane == 0) {
+            out_counts[q] = emitted;
+            if (emitted_above < k) status[q] = st | kStatusNeedMore;
+        }
+    }
+}
+
+// Blocks walk the queries the warp kernel left (more than kSelWarpCap candidates, or uncertified candidates; with
+// all = 1 every query): certified scores of the candidates, literal re-score where needed, then the same k rounds.
+__global__ void __launch_bounds__(kSelThreads)
+select_kernel(MatView rows, const uint64_t *ids, uint64_t id_base, int unique_ids, MatView queries, const unsigned int *cand_cnt,
+              const uint2 *cand_rowdot, uint32_t cand_per_q, int all, const float *tau, int k, uint64_t *out_ids, float *out_sims,
+              int32_t *out_counts, uint32_t *status, unsigned long long *fix_counter) {
     extern __shared__ __align__(16) unsigned char sel_smem[];
     SelEntry *ent = reinterpret_cast<SelEntry *>(sel_smem);
     double *sh_qn = reinterpret_cast<double *>(sel_smem + sizeof(SelEntry) * kSelCap);
@@ -708,132 +840,158 @@ select_kernel(MatView rows, const uint64_t *ids, uint64_t id_base, MatView queri
     __shared__ int s_widx[kSelThreads / 32];
     __shared__ int s_best;
 
-    const uint32_t q = blockIdx.x;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int D = rows.d, d_pad = rows.d_pad;
-    if (status[q] & kStatusNeedMore) return;  // unusable query: the caller's fallback answers it
-    const uint32_t c0 = seg_off[q], c1 = seg_off[q + 1];
-    const uint32_t cnt = c1 - c0;
-    if (cnt > (uint32_t)kSelCap) {
-        if (threadIdx.x == 0) status[q] = kStatusNeedMore;
-        return;
-    }
-    if (threadIdx.x == 0) {
-        const float2 h = queries.hdr[q];
-        const uint2 s = queries.sums[q];
-        s_side = make_side(h.x, h.y, s.x, s.y, D);
-        s_any_flag = 0;
-    }
-    __syncthreads();
-    const SideConst xq = s_side;
-    for (uint32_t e = threadIdx.x; e < cnt; e += kSelThreads) {
-        const uint2 rd = cand_rowdot[c0 + e];
-        const float2 h = rows.hdr[rd.x];
-        const uint2 s = rows.sums[rd.x];
-        bool flag;
-        const float sim = score_fast(xq, h.x, h.y, s.x, s.y, rd.y, D, &flag);
-        ent[e].key = f32_to_key(sim);
-        ent[e].row = rd.x | (flag ? kFlagBit : 0u);
-        ent[e].id = ids ? ids[rd.x] : id_base + rd.x;
-        if (flag) s_any_flag = 1;
-    }
-    __syncthreads();
-    if (s_any_flag) {
-        // literal path: normalizeVector of the query (compute/cosine.go:26,138-149), then each flagged row
-        const uint8_t *qc = queries.codes + (size_t)q * queries.d_pad;
-        const float2 qh = queries.hdr[q];
-        const double mn = (double)qh.x, range = __dsub_rn((double)qh.y, (double)qh.x);
-        for (int i = threadIdx.x; i < D; i += kSelThreads) sh_qn[i] = ref_dequant_f64(qc[i], mn, range);
-        __syncthreads();
-        if (warp == 0) {
-            const double nsq = warp_ordered_sum(D, lane, [&](int i) { return __dmul_rn(sh_qn[i], sh_qn[i]); });
-            if (lane == 0) s_norm = __dsqrt_rn(nsq);
+    for (uint32_t q = blockIdx.x; q < (uint32_t)queries.n; q += gridDim.x) {
+        const uint32_t st = status[q];
+        if (st & kStatusNeedMore) continue;  // unusable query: the caller's fallback answers it
+        const uint32_t cnt = cand_cnt[q];
+        if (!all && cnt <= (uint32_t)kSelWarpCap && cnt <= cand_per_q && !(st & kStatusDeferred)) continue;  // the warp kernel answered it
+        __syncthreads();  // everyone has read status[q]; the previous query's shared state is dead
+        if (cnt > (uint32_t)kSelCap || cnt > cand_per_q) {
+            if (threadIdx.x == 0) status[q] = kStatusNeedMore;
+            continue;
         }
-        __syncthreads();
-        const double norm = s_norm;
-        if (norm != 0.0)
-            for (int i = threadIdx.x; i < D; i += kSelThreads) sh_qn[i] = __ddiv_rn(sh_qn[i], norm);
-        __syncthreads();
-        for (uint32_t e = warp; e < cnt; e += kSelThreads / 32) {
-            const uint32_t r = ent[e].row;
-            if (r & kFlagBit) {
-                const uint32_t row = r & ~kFlagBit;
-                const float2 h = rows.hdr[row];
-                const double dot = warp_ref_cosine_row_f64(rows.codes + (size_t)row * d_pad, h.x, h.y, sh_qn, D, lane);
-                if (lane == 0) {
-                    ent[e].key = f32_to_key(__double2float_rn(dot));
-                    ent[e].row = row;
-                    if (fix_counter) atomicAdd(fix_counter, 1ull);
-                }
-            }
-        }
-        __syncthreads();
-    }
-    const uint32_t tau_key = f32_to_key(tau[q]);
-    int emitted = 0, emitted_above = 0;
-    for (int round = 0; round < k; round++) {
-        uint32_t bk = 0;
-        uint64_t bid = kEmptyId;
-        int bidx = -1;
-        for (uint32_t e = threadIdx.x; e < cnt; e += kSelThreads) {
-            const uint32_t ek = ent[e].key;
-            if (ek != 0 && (bidx < 0 || cand_better(ek, ent[e].id, bk, bid))) {
-                bk = ek;
-                bid = ent[e].id;
-                bidx = (int)e;
-            }
-        }
-        for (int o = 16; o; o >>= 1) {
-            const uint32_t ok = __shfl_xor_sync(0xFFFFFFFFu, bk, o);
-            const uint64_t oid = __shfl_xor_sync(0xFFFFFFFFu, bid, o);
-            const int oidx = __shfl_xor_sync(0xFFFFFFFFu, bidx, o);
-            if (oidx >= 0 && (bidx < 0 || cand_better(ok, oid, bk, bid) || (ok == bk && oid == bid && oidx < bidx))) {
-                bk = ok;
-                bid = oid;
-                bidx = oidx;
-            }
-        }
-        if (lane == 0) {
-            s_wkey[warp] = bk;
-            s_wid[warp] = bid;
-            s_widx[warp] = bidx;
-        }
-        __syncthreads();
         if (threadIdx.x == 0) {
-            int best = -1;
-            uint32_t k0 = 0;
-            uint64_t i0 = kEmptyId;
-            for (int w = 0; w < kSelThreads / 32; w++) {
-                if (s_widx[w] >= 0 && (best < 0 || cand_better(s_wkey[w], s_wid[w], k0, i0) ||
-                                       (s_wkey[w] == k0 && s_wid[w] == i0 && s_widx[w] < best))) {
-                    best = s_widx[w];
-                    k0 = s_wkey[w];
-                    i0 = s_wid[w];
-                }
-            }
-            s_best = best;
-            if (best >= 0) {
-                out_ids[(size_t)q * k + round] = i0;
-                out_sims[(size_t)q * k + round] = key_to_f32(k0);
-            }
+            const float2 h = queries.hdr[q];
+            const uint2 s = queries.sums[q];
+            s_side = make_side(h.x, h.y, s.x, s.y, D);
+            s_any_flag = 0;
         }
         __syncthreads();
-        const int best = s_best;
-        if (best < 0) break;
-        const uint64_t win_id = ent[best].id;
-        const uint32_t win_key = ent[best].key;
-        emitted++;
-        if (win_key >= tau_key && win_key != 1u) emitted_above++;
+        const SideConst xq = s_side;
+        for (uint32_t e = threadIdx.x; e < cnt; e += kSelThreads) {
+            const uint2 rd = cand_rowdot[(size_t)q * cand_per_q + e];
+            const float2 h = rows.hdr[rd.x];
+            const uint2 s = rows.sums[rd.x];
+            bool flag;
+            const float sim = score_fast(xq, h.x, h.y, s.x, s.y, rd.y, D, &flag);
+            ent[e].key = f32_to_key(sim);
+            ent[e].row = rd.x | (flag ? kFlagBit : 0u);
+            ent[e].id = ids ? ids[rd.x] : id_base + rd.x;
+            if (flag) s_any_flag = 1;
+        }
         __syncthreads();
-        for (uint32_t e = threadIdx.x; e < cnt; e += kSelThreads)
-            if (ent[e].id == win_id) ent[e].key = 0;  // one hit per document
-        __syncthreads();
-    }
-    if (threadIdx.x == 0) {
-        out_counts[q] = emitted;
-        // complete only if k distinct documents at or above tau were found: then no row outside the candidate
-        // list (all of which score below tau) can belong to the top k
-        if (emitted_above < k) status[q] = kStatusNeedMore;
+        uint32_t floor_key = 0;  // uncertified entries below it cannot reach the top k (see select_warp_kernel)
+        if (s_any_flag && unique_ids && cnt >= (uint32_t)k) {
+            uint32_t lo = 0, hi = 0xFFFFFFFFu;
+            while (lo < hi) {
+                const uint32_t mid = lo + (hi - lo) / 2 + 1;
+                int c = 0;
+                for (uint32_t e = threadIdx.x; e < cnt; e += kSelThreads)
+                    c += key_lower_bound(ent[e].key, (ent[e].row & kFlagBit) != 0) >= mid;
+                for (int o = 16; o; o >>= 1) c += __shfl_xor_sync(0xFFFFFFFFu, c, o);
+                if (lane == 0) s_widx[warp] = c;
+                __syncthreads();
+                int sum = 0;
+                for (int w = 0; w < kSelThreads / 32; w++) sum += s_widx[w];
+                __syncthreads();
+                if (sum >= k) lo = mid;
+                else hi = mid - 1;
+            }
+            floor_key = lo;
+            int need = 0;
+            for (uint32_t e = threadIdx.x; e < cnt; e += kSelThreads) need |= (ent[e].row & kFlagBit) && ent[e].key >= floor_key;
+            if (__syncthreads_or(need) == 0 && threadIdx.x == 0) s_any_flag = 0;
+            __syncthreads();
+        }
+        if (s_any_flag) {
+            // literal path: normalizeVector of the query (compute/cosine.go:26,138-149), then each flagged row
+            const uint8_t *qc = queries.codes + (size_t)q * queries.d_pad;
+            const float2 qh = queries.hdr[q];
+            const double mn = (double)qh.x, range = __dsub_rn((double)qh.y, (double)qh.x);
+            for (int i = threadIdx.x; i < D; i += kSelThreads) sh_qn[i] = ref_dequant_f64(qc[i], mn, range);
+            __syncthreads();
+            if (warp == 0) {
+                const double nsq = warp_ordered_sum(D, lane, [&](int i) { return __dmul_rn(sh_qn[i], sh_qn[i]); });
+                if (lane == 0) s_norm = __dsqrt_rn(nsq);
+            }
+            __syncthreads();
+            const double norm = s_norm;
+            if (norm != 0.0)
+                for (int i = threadIdx.x; i < D; i += kSelThreads) sh_qn[i] = __ddiv_rn(sh_qn[i], norm);
+            __syncthreads();
+            for (uint32_t e = warp; e < cnt; e += kSelThreads / 32) {
+                const uint32_t r = ent[e].row;
+                if ((r & kFlagBit) && ent[e].key >= floor_key) {
+                    const uint32_t row = r & ~kFlagBit;
+                    const float2 h = rows.hdr[row];
+                    const double dot = warp_ref_cosine_row_f64(rows.codes + (size_t)row * d_pad, h.x, h.y, sh_qn, D, lane);
+                    if (lane == 0) {
+                        ent[e].key = f32_to_key(__double2float_rn(dot));
+                        ent[e].row = row;
+                        if (fix_counter) atomicAdd(fix_counter, 1ull);
+                    }
+                }
+            }
+            __syncthreads();
+        }
+        const uint32_t tau_key = f32_to_key(tau[q]);
+        int emitted = 0, emitted_above = 0;
+        for (int round = 0; round < k; round++) {
+            uint32_t bk = 0;
+            uint64_t bid = kEmptyId;
+            int bidx = -1;
+            for (uint32_t e = threadIdx.x; e < cnt; e += kSelThreads) {
+                const uint32_t ek = ent[e].key;
+                if (ek != 0 && (bidx < 0 || cand_better(ek, ent[e].id, bk, bid))) {
+                    bk = ek;
+                    bid = ent[e].id;
+                    bidx = (int)e;
+                }
+            }
+            for (int o = 16; o; o >>= 1) {
+                const uint32_t ok = __shfl_xor_sync(0xFFFFFFFFu, bk, o);
+                const uint64_t oid = __shfl_xor_sync(0xFFFFFFFFu, bid, o);
+                const int oidx = __shfl_xor_sync(0xFFFFFFFFu, bidx, o);
+                if (oidx >= 0 && (bidx < 0 || cand_better(ok, oid, bk, bid) || (ok == bk && oid == bid && oidx < bidx))) {
+                    bk = ok;
+                    bid = oid;
+                    bidx = oidx;
+                }
+            }
+            if (lane == 0) {
+                s_wkey[warp] = bk;
+                s_wid[warp] = bid;
+                s_widx[warp] = bidx;
+            }
+            __syncthreads();
+            if (threadIdx.x == 0) {
+                int best = -1;
+                uint32_t k0 = 0;
+                uint64_t i0 = kEmptyId;
+                for (int w = 0; w < kSelThreads / 32; w++) {
+                    if (s_widx[w] >= 0 && (best < 0 || cand_better(s_wkey[w], s_wid[w], k0, i0) ||
+                                           (s_wkey[w] == k0 && s_wid[w] == i0 && s_widx[w] < best))) {
+                        best = s_widx[w];
+                        k0 = s_wkey[w];
+                        i0 = s_wid[w];
+                    }
+                }
+                s_best = best;
+                if (best >= 0) {
+                    out_ids[(size_t)q * k + round] = i0;
+                    out_sims[(size_t)q * k + round] = key_to_f32(k0);
+                }
+            }
+            __syncthreads();
+            const int best = s_best;
+            if (best < 0) break;
+            const uint64_t win_id = ent[best].id;
+            const uint32_t win_key = ent[best].key;
+            emitted++;
+            if (win_key >= tau_key && win_key != 1u) emitted_above++;
+            __syncthreads();
+            for (uint32_t e = threadIdx.x; e < cnt; e += kSelThreads)
+                if (ent[e].id == win_id) ent[e].key = 0;  // one hit per document
+            __syncthreads();
+        }
+        if (threadIdx.x == 0) {
+            out_counts[q] = emitted;
+            // complete only if k distinct documents at or above tau were found: then no row outside the candidate
+            // list (all of which score below tau) can belong to the top k
+            status[q] = (emitted_above < k) ? kStatusNeedMore : 0u;
+        }
     }
 }
 
@@ -894,21 +1052,16 @@ GemmPlan gemm_plan(const MatView &rows, size_t nq, size_t k, bool unique_ids, ui
     if (pl.sample_stride < 1) pl.sample_stride = 1;
     pl.sample_tiles = (pl.tiles + pl.sample_stride - 1) / pl.sample_stride;
     pl.G = pl.sample_tiles * 8;  // one group maximum per 16 store rows
-    size_t cap = nq * cand_per_query;
-    if (cap < (1u << 20)) cap = 1u << 20;
-    if (cap > (64u << 20)) cap = 64u << 20;
-    pl.cand_cap = (unsigned int)cap;
-    size_t sort_tmp = 0;
-    cub::DeviceRadixSort::SortPairs(nullptr, sort_tmp, (const uint32_t *)nullptr, (uint32_t *)nullptr, (const uint2 *)nullptr,
-                                    (uint2 *)nullptr, (int64_t)cap, 0, 20);
-    pl.sort_tmp_bytes = sort_tmp;
+    if (cand_per_query > (size_t)kSelCap) cand_per_query = kSelCap;
+    if (cand_per_query < 32) cand_per_query = 32;
+    pl.cand_per_q = (uint32_t)cand_per_query;
     return pl;
 }
 
 size_t gemm_scratch_bytes(const GemmPlan &pl, size_t nq) {
     auto pad = [](size_t b) { return (b + 255) & ~size_t(255); };
-    return pad((size_t)pl.nq_pad * 16) + pad((size_t)pl.nq_pad * pl.G * 4) + pad(nq * 4) + pad(64) + pad((nq + 2) * 4) +
-           2 * pad((size_t)pl.cand_cap * 4) + 2 * pad((size_t)pl.cand_cap * 8) + pad(pl.sort_tmp_bytes) + 4096;
+    return pad((size_t)pl.nq_pad * 16) + pad((size_t)pl.nq_pad * pl.G * 4) + pad(nq * 4) + pad(64) + pad((size_t)pl.nq_pad * 4) +
+           pad((size_t)pl.nq_pad * pl.cand_per_q * 8) + 4096;
 }
 
 void gemm_take(char *base, const GemmPlan &pl, size_t nq, GemmBufs *b) {
@@ -922,13 +1075,9 @@ void gemm_take(char *base, const GemmPlan &pl, size_t nq, GemmBufs *b) {
     b->col_consts = reinterpret_cast<float4 *>(take((size_t)pl.nq_pad * 16));
     b->gmax = reinterpret_cast<float *>(take((size_t)pl.nq_pad * pl.G * 4));
     b->tau = reinterpret_cast<float *>(take(nq * 4));
-    b->bounds = reinterpret_cast<unsigned int *>(take(64));  // [0..2] bounds, [4] candidate count
-    b->seg_off = reinterpret_cast<uint32_t *>(take((nq + 2) * 4));
-    b->cand_q = reinterpret_cast<uint32_t *>(take((size_t)pl.cand_cap * 4));
-    b->cand_q_sorted = reinterpret_cast<uint32_t *>(take((size_t)pl.cand_cap * 4));
-    b->cand_rowdot = reinterpret_cast<uint2 *>(take((size_t)pl.cand_cap * 8));
-    b->cand_rowdot_sorted = reinterpret_cast<uint2 *>(take((size_t)pl.cand_cap * 8));
-    b->sort_tmp = take(pl.sort_tmp_bytes);
+    b->bounds = reinterpret_cast<unsigned int *>(take(64));
+    b->cand_cnt = reinterpret_cast<unsigned int *>(take((size_t)pl.nq_pad * 4));
+    b->cand_rowdot = reinterpret_cast<uint2 *>(take((size_t)pl.nq_pad * pl.cand_per_q * 8));
 }
 
 static cudaError_t launch_gemm(int mode, const CUtensorMap &tm_rows, const CUtensorMap &tm_q, const GemmParams &p, int sm_count,
@@ -976,10 +1125,9 @@ static GemmParams gemm_params(const MatView &rows, const GemmPlan &pl, const Gem
     }
     p.nq_tiles = pl.nq_pad / kTN;
     p.col_consts = b.col_consts;
-    p.cand_count = b.bounds + 4;
-    p.cand_q = b.cand_q;
+    p.cand_cnt = b.cand_cnt;
     p.cand_rowdot = b.cand_rowdot;
-    p.cand_cap = pl.cand_cap;
+    p.cand_per_q = pl.cand_per_q;
     p.gmax = b.gmax;
     p.G = pl.G;
     const char *dbg = getenv("VS_GEMM_DBG");
@@ -1003,8 +1151,20 @@ cudaError_t gemm_enqueue_prepass(const MatView &rows, const MatView &queries, co
     gemm_split(p, sm_count);
     e = launch_gemm(MODE_GROUPMAX, tm_rows, tm_q, p, sm_count, st);
     if (e != cudaSuccess) return e;
-    threshold_kernel<<<pl.nq_pad, kThrThreads, pl.G * sizeof(int), st>>>(queries, pl.nq_pad, b.gmax, pl.G, pl.rank, b.bounds,
-                                                                         b.col_consts, b.tau, d_status);
+    if (pl.G <= 1024u) {
+        const unsigned blocks = (pl.nq_pad + 3) / 4 < (unsigned)sm_count * 16 ? (pl.nq_pad + 3) / 4 : (unsigned)sm_count * 16;
+        if (pl.G <= 256u)
+            threshold_warp_kernel<8><<<blocks, 128, 0, st>>>(queries, pl.nq_pad, b.gmax, pl.G, pl.rank, b.bounds, b.col_consts, b.tau,
+                                                             d_status);
+        else
+            threshold_warp_kernel<32><<<blocks, 128, 0, st>>>(queries, pl.nq_pad, b.gmax, pl.G, pl.rank, b.bounds, b.col_consts,
+                                                              b.tau, d_status);
+    } else {
+        threshold_kernel<<<pl.nq_pad, kThrThreads, pl.G * sizeof(int), st>>>(queries, pl.nq_pad, b.gmax, pl.G, pl.rank, b.bounds,
+                                                                             b.col_consts, b.tau, d_status);
+    }
+    e = cudaMemsetAsync(b.cand_cnt, 0, (size_t)pl.nq_pad * 4, st);
+    if (e != cudaSuccess) return e;
     if (launches) *launches += 4;
     return cudaGetLastError();
 }
@@ -1025,26 +1185,26 @@ cudaError_t gemm_enqueue_filter(const MatView &rows, const MatView &queries, con
     return cudaGetLastError();
 }
 
-// Phase 2 (after the host has read the candidate count): group the candidates by query, finish them.
-cudaError_t gemm_enqueue_select(const MatView &rows, const uint64_t *ids, uint64_t id_base, const MatView &queries, const GemmPlan &pl,
-                                const GemmBufs &b, unsigned int cand_count, int k, uint64_t *d_ids, float *d_sims, int32_t *d_counts,
-                                uint32_t *d_status, unsigned long long *fix_counter, cudaStream_t st, uint64_t *launches) {
+// Phase 2: finish the candidates of every query (no host involvement: the buckets are already grouped by query).
+cudaError_t gemm_enqueue_select(const MatView &rows, const uint64_t *ids, uint64_t id_base, bool unique_ids, const MatView &queries, const GemmPlan &pl,
+                                const GemmBufs &b, int k, uint64_t *d_ids, float *d_sims, int32_t *d_counts, uint32_t *d_status,
+                                unsigned long long *fix_counter, int sm_count, cudaStream_t st, uint64_t *launches) {
     const uint32_t nq = (uint32_t)queries.n;
-    size_t tmp = pl.sort_tmp_bytes;
-    int bits = 1;
-    while ((1u << bits) < nq + 1 && bits < 20) bits++;
-    cudaError_t e = cudaSuccess;
-    if (cand_count)
-        e = cub::DeviceRadixSort::SortPairs(b.sort_tmp, tmp, b.cand_q, b.cand_q_sorted, b.cand_rowdot, b.cand_rowdot_sorted,
-                                            (int64_t)cand_count, 0, bits, st);
-    if (e != cudaSuccess) return e;
-    segment_offsets_kernel<<<(nq + 1 + 127) / 128, 128, 0, st>>>(b.cand_q_sorted, cand_count, nq, b.seg_off);
+    // many queries with few candidates each (assignment): the warp kernel takes them, the block kernel the rest
+    const bool two_level = k <= 32 && nq >= 4u * (uint32_t)sm_count;
+    if (two_level) {
+        const unsigned wb = (nq + 7) / 8 < (unsigned)sm_count * 8 ? (nq + 7) / 8 : (unsigned)sm_count * 8;
+        select_warp_kernel<<<wb, kSelThreads, 0, st>>>(rows, ids, id_base, unique_ids ? 1 : 0, queries, b.cand_cnt, b.cand_rowdot, pl.cand_per_q, b.tau, k,
+                                                       d_ids, d_sims, d_counts, d_status);
+        if (launches) *launches += 1;
+    }
     const size_t smem = sizeof(SelEntry) * kSelCap + (size_t)rows.d * 8;
-    e = cudaFuncSetAttribute(select_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    cudaError_t e = cudaFuncSetAttribute(select_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return e;
-    select_kernel<<<nq, kSelThreads, smem, st>>>(rows, ids, id_base, queries, b.seg_off, b.cand_rowdot_sorted, b.tau, k, d_ids, d_sims,
-                                                 d_counts, d_status, fix_counter);
-    if (launches) *launches += cand_count ? 4 : 2;
+    const unsigned grid = nq < (unsigned)sm_count * 3 ? nq : (unsigned)sm_count * 3;
+    select_kernel<<<grid, kSelThreads, smem, st>>>(rows, ids, id_base, unique_ids ? 1 : 0, queries, b.cand_cnt, b.cand_rowdot, pl.cand_per_q,
+                                                   two_level ? 0 : 1, b.tau, k, d_ids, d_sims, d_counts, d_status, fix_counter);
+    if (launches) *launches += 1;
     return cudaGetLastError();
 }
 

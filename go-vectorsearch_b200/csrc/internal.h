@@ -124,22 +124,19 @@ cudaError_t gemm_set_certify_scale(float scale);
 
 // gemm.cu: query batches as a tcgen05 int8 GEMM with a fused filter (BASELINE config 3)
 struct GemmPlan {
-    uint32_t nq_pad;        // queries rounded up to the 128-column tile
+    uint32_t nq_pad;        // queries rounded up to the query tile
     uint32_t tiles;         // 128-row store tiles
     uint32_t rank;          // the threshold is the rank-th largest group maximum of the sample
     uint32_t sample_stride, sample_tiles, G;  // pre-pass sample: every sample_stride-th tile; G = 8 groups per tile
-    unsigned int cand_cap;  // candidate list capacity
-    size_t sort_tmp_bytes;
+    uint32_t cand_per_q;    // candidate bucket capacity per query
 };
 struct GemmBufs {
     float4 *col_consts;
     float *gmax;
     float *tau;
-    unsigned int *bounds;   // [0..2] row-side bounds, [4] candidate count
-    uint32_t *seg_off;
-    uint32_t *cand_q, *cand_q_sorted;
-    uint2 *cand_rowdot, *cand_rowdot_sorted;
-    void *sort_tmp;
+    unsigned int *bounds;   // [0..2] row-side bounds
+    unsigned int *cand_cnt; // [nq_pad] candidates emitted per query (may exceed the bucket: then the query needs more)
+    uint2 *cand_rowdot;     // [nq_pad][cand_per_q] (store row, integer dot)
 };
 bool gemm_store_supported(const MatView &rows);
 bool gemm_supported(const MatView &rows, size_t nq);
@@ -151,9 +148,10 @@ cudaError_t gemm_enqueue_prepass(const MatView &rows, const MatView &queries, co
                                  int sm_count, cudaStream_t st, uint64_t *launches);
 cudaError_t gemm_enqueue_filter(const MatView &rows, const MatView &queries, const GemmPlan &pl, const GemmBufs &b, int sm_count,
                                 cudaStream_t st, uint64_t *launches);
-cudaError_t gemm_enqueue_select(const MatView &rows, const uint64_t *ids, uint64_t id_base, const MatView &queries, const GemmPlan &pl,
-                                const GemmBufs &b, unsigned int cand_count, int k, uint64_t *d_ids, float *d_sims, int32_t *d_counts,
-                                uint32_t *d_status, unsigned long long *fix_counter, cudaStream_t st, uint64_t *launches);
+cudaError_t gemm_enqueue_select(const MatView &rows, const uint64_t *ids, uint64_t id_base, bool unique_ids, const MatView &queries,
+                                const GemmPlan &pl,
+                                const GemmBufs &b, int k, uint64_t *d_ids, float *d_sims, int32_t *d_counts, uint32_t *d_status,
+                                unsigned long long *fix_counter, int sm_count, cudaStream_t st, uint64_t *launches);
 
 // quantize.cu
 cudaError_t launch_quantize_f32(const float *in, size_t n, int d, uint8_t *out_rows, cudaStream_t st);
