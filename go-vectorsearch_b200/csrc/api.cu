@@ -664,23 +664,32 @@ __global__ void lower_bound_kernel(const uint32_t *keys, size_t n, uint64_t *off
 }
 
 // Stable sort of rows by key: d_order[i] = source row of sorted position i; d_sorted_keys optional.
-static int sort_rows_by_key(vs_ctx *c, const uint32_t *d_keys, size_t n, int key_bits, uint32_t *d_order,
-                            uint32_t *d_keys_sorted) {
-    uint32_t *d_iota = nullptr;
-    void *d_temp = nullptr;
+// ws/ws_bytes: optional caller workspace of at least sort_rows_ws_bytes(n) (else allocated here).
+static size_t sort_rows_ws_bytes(size_t n) {
     size_t temp_bytes = 0;
-    CU(cudaMalloc(&d_iota, n * 4 + 4));
+    cub::DeviceRadixSort::SortPairs(nullptr, temp_bytes, (const uint32_t *)nullptr, (uint32_t *)nullptr, (const uint32_t *)nullptr,
+                                    (uint32_t *)nullptr, (int64_t)n, 0, 32);
+    return Arena::pad(n * 4 + 4) + Arena::pad(temp_bytes + 16);
+}
+static int sort_rows_by_key(vs_ctx *c, const uint32_t *d_keys, size_t n, int key_bits, uint32_t *d_order,
+                            uint32_t *d_keys_sorted, void *ws = nullptr, size_t ws_bytes = 0) {
+    const size_t need = sort_rows_ws_bytes(n);
+    char *own = nullptr;
+    if (!ws || ws_bytes < need) {
+        CU(cudaMalloc(&own, need));
+        ws = own;
+    }
+    uint32_t *d_iota = static_cast<uint32_t *>(ws);
+    void *d_temp = static_cast<char *>(ws) + Arena::pad(n * 4 + 4);
+    size_t temp_bytes = need - Arena::pad(n * 4 + 4);
     iota_kernel<<<g_sm_count * 4, 256, 0, c->stream>>>(d_iota, n);
     c->launches++;
-    cudaError_t e = cub::DeviceRadixSort::SortPairs(nullptr, temp_bytes, d_keys, d_keys_sorted, d_iota, d_order, (int64_t)n, 0,
-                                                    key_bits, c->stream);
-    if (e == cudaSuccess) e = cudaMalloc(&d_temp, temp_bytes + 16);
-    if (e == cudaSuccess)
-        e = cub::DeviceRadixSort::SortPairs(d_temp, temp_bytes, d_keys, d_keys_sorted, d_iota, d_order, (int64_t)n, 0, key_bits,
-                                            c->stream);
-    if (e == cudaSuccess) e = cudaStreamSynchronize(c->stream);
-    cudaFree(d_iota);
-    if (d_temp) cudaFree(d_temp);
+    cudaError_t e = cub::DeviceRadixSort::SortPairs(d_temp, temp_bytes, d_keys, d_keys_sorted, d_iota, d_order, (int64_t)n, 0, key_bits,
+                                                    c->stream);
+    if (own) {
+        if (e == cudaSuccess) e = cudaStreamSynchronize(c->stream);
+        cudaFree(own);
+    }
     if (e != cudaSuccess) return fail(VS_ECUDA, "radix sort: %s", cudaGetErrorString(e));
     c->launches += 4;
     return VS_OK;
@@ -1549,6 +1558,116 @@ extern "C" int vs_kmeans_step(vs_ctx *c, const vs_matrix *data, const uint8_t *c
         for (size_t j = 0; j < k && conv; j++)
             if (memcmp(new_centroids_out + j * rb + 8, centroids + j * rb + 8, d) != 0) conv = 0;
         *converged_out = conv;
+    }
+    return VS_OK;
+}
+
+// The whole kMeans of dnc/k_means.go:19-212 with every iteration on the device.  The random superset draw (:35-44) is the
+// caller's (superset_rows); the superset phase iterates ks centroids until the code bytes stop changing (:67-117), the set
+// phase keeps the first k (the sort at :132 compares counts that :111-113 already zeroed; Go's pdqsort leaves an
+// all-equal slice untouched) together with their float32 means (:153-154) and iterates again (:157-207).
+__global__ void codes_differ_kernel(const uint8_t *a, const uint8_t *b, size_t rows, int d, int d_pad, int *flag) {
+    const size_t total = rows * (size_t)d;
+    int diff = 0;
+    for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < total && !diff; i += (size_t)gridDim.x * blockDim.x) {
+        const size_t r = i / d, j = i % d;
+        diff = a[r * d_pad + j] != b[r * d_pad + j];
+    }
+    if (diff) *flag = 1;
+}
+
+extern "C" int vs_kmeans(vs_ctx *c, const vs_matrix *data, size_t k, const uint64_t *superset_rows, size_t ks, size_t iter_limit,
+                         uint8_t *centroids_out, int64_t *stats_out) {
+    VS(need_dev());
+    if (!c || !data || !superset_rows || !centroids_out) return fail(VS_EINVAL, "null argument");
+    const size_t n = data->n, d = data->d, rb = 8 + d, d_pad = data->d_pad;
+    if (k == 0) return fail(VS_EEMPTY, "matrix rows are empty");
+    if (ks < k || ks > n) return fail(VS_EINVAL, "superset of %zu rows for k=%zu, n=%zu", ks, k, n);
+    if (n > 0xFFFFFFF0ull) return fail(VS_ERANGE, "n=%zu rows", n);
+    std::vector<uint32_t> rows32(ks);
+    for (size_t i = 0; i < ks; i++) {
+        if (superset_rows[i] >= n) return fail(VS_EINVAL, "superset row %llu >= n", (unsigned long long)superset_rows[i]);
+        rows32[i] = (uint32_t)superset_rows[i];
+    }
+    Arena a(c);
+    const size_t soa = Arena::pad(ks * d_pad) + 2 * Arena::pad(ks * 8);
+    VS(a.reserve(2 * soa + Arena::pad(ks * 4) + argmax_bytes(ks, n) + 3 * Arena::pad(n * 4) + Arena::pad((ks + 1) * 4) +
+                 Arena::pad(ks * d * 4) + Arena::pad(ks * 8) + Arena::pad(k * rb) + sort_rows_ws_bytes(n) + 8192));
+    struct Soa {
+        uint8_t *codes;
+        float2 *hdr;
+        uint2 *sums;
+    } cur, nxt;
+    cur.codes = a.take<uint8_t>(ks * d_pad);
+    cur.hdr = a.take<float2>(ks);
+    cur.sums = a.take<uint2>(ks);
+    nxt.codes = a.take<uint8_t>(ks * d_pad);
+    nxt.hdr = a.take<float2>(ks);
+    nxt.sums = a.take<uint2>(ks);
+    uint32_t *d_rows = a.take<uint32_t>(ks);
+    int32_t *d_assign = a.take<int32_t>(n);
+    uint32_t *d_order = a.take<uint32_t>(n);
+    uint32_t *d_sorted = a.take<uint32_t>(n);
+    uint32_t *d_segoff = a.take<uint32_t>(ks + 1);
+    float *d_means = a.take<float>(ks * d);
+    int64_t *d_counts = a.take<int64_t>(ks);
+    uint8_t *d_out = a.take<uint8_t>(k * rb);
+    int *d_flag = a.take<int>(16);
+    const size_t sort_ws_bytes = sort_rows_ws_bytes(n);
+    char *d_sort_ws = a.take<char>(sort_ws_bytes);
+    CU(cudaMemcpyAsync(d_rows, rows32.data(), ks * 4, cudaMemcpyHostToDevice, c->stream));
+    CU(cudaMemsetAsync(nxt.codes, 0, ks * d_pad, c->stream));  // the padding columns stay zero
+    LAUNCH(c, launch_gather_rows(data->view(), d_rows, ks, cur.codes, cur.hdr, cur.sums, nullptr, 0, nullptr, c->stream));
+    CU(cudaMemsetAsync(d_means, 0, ks * d * 4, c->stream));     // k_means.go:60-65
+    VS(pinned_reserve(c, 64));
+    for (int i = 0; i < 4; i++)
+        if (!c->phase_ev[i]) CU(cudaEventCreate(&c->phase_ev[i]));
+    int64_t iters[2] = {0, 0};
+    double ms_assign = 0, ms_update = 0;
+    for (int phase = 0; phase < 2; phase++) {
+        const size_t m = phase == 0 ? ks : k;
+        bool conv = false;
+        for (size_t it = 0; it < iter_limit && !conv; it++) {
+            const MatView cv{cur.codes, cur.hdr, cur.sums, m, (int)d, (int)d_pad};
+            CU(cudaEventRecord(c->phase_ev[0], c->stream));
+            const size_t mark = a.off;
+            VS(argmax_dev(c, a, cv, data->view(), d_assign, nullptr));  // :73-77
+            a.off = mark;
+            CU(cudaEventRecord(c->phase_ev[1], c->stream));
+            VS(sort_rows_by_key(c, reinterpret_cast<const uint32_t *>(d_assign), n, bits_for(m), d_order, d_sorted, d_sort_ws,
+                                sort_ws_bytes));
+            lower_bound_kernel<<<(unsigned)((m + 1 + 255) / 256), 256, 0, c->stream>>>(d_sorted, n, nullptr, d_segoff, m);
+            c->launches++;
+            LAUNCH(c, launch_kmeans_accumulate(data->view(), d_order, d_segoff, (int)m, d_means, d_counts, c->stream));  // :80-96
+            LAUNCH(c, launch_quantize_f32_soa(d_means, m, (int)d, nxt.codes, (int)d_pad, nxt.hdr, nxt.sums, c->stream));  // :99
+            CU(cudaMemsetAsync(d_flag, 0, sizeof(int), c->stream));
+            codes_differ_kernel<<<g_sm_count * 4, 256, 0, c->stream>>>(cur.codes, nxt.codes, m, (int)d, (int)d_pad, d_flag);  // :102-108
+            c->launches++;
+            CU(cudaEventRecord(c->phase_ev[2], c->stream));
+            int *h_flag = static_cast<int *>(c->pinned);
+            CU(cudaMemcpyAsync(h_flag, d_flag, sizeof(int), cudaMemcpyDeviceToHost, c->stream));
+            CU(cudaStreamSynchronize(c->stream));
+            conv = *h_flag == 0;
+            float t0 = 0.f, t1 = 0.f;
+            CU(cudaEventElapsedTime(&t0, c->phase_ev[0], c->phase_ev[1]));
+            CU(cudaEventElapsedTime(&t1, c->phase_ev[1], c->phase_ev[2]));
+            ms_assign += t0;
+            ms_update += t1;
+            const Soa t = cur;
+            cur = nxt;
+            nxt = t;
+            iters[phase]++;
+        }
+    }
+    const MatView fin{cur.codes, cur.hdr, cur.sums, k, (int)d, (int)d_pad};
+    LAUNCH(c, launch_export(fin, 0, k, d_out, c->stream));
+    CU(cudaMemcpyAsync(centroids_out, d_out, k * rb, cudaMemcpyDeviceToHost, c->stream));
+    CU(cudaStreamSynchronize(c->stream));
+    if (stats_out) {
+        stats_out[0] = iters[0];
+        stats_out[1] = iters[1];
+        stats_out[2] = (int64_t)(ms_assign * 1000.0);
+        stats_out[3] = (int64_t)(ms_update * 1000.0);
     }
     return VS_OK;
 }

@@ -5,38 +5,75 @@
 // (float64 sum of a cluster's rows in row order, divided by the count).  Float addition is not
 // associative, so to reproduce the reference's bytes each (centroid, dimension) pair is one
 // sequential chain over the member rows in ascending row order; parallelism comes from the
-// k x D independent chains.  HBM-bound: every member row is read once (776 B per row).
+// k x D independent chains (four per thread, a 32-bit word of codes per row) and from the unrolled
+// row loop, whose loads do not depend on the additions.  HBM-bound: every member row is read once.
 #include "internal.h"
 
 namespace vs {
 
-constexpr int kDimsPerBlock = 64;
+constexpr int kAccThreads = 192;  // four adjacent dimensions per thread: one block covers 768 columns of a centroid
+constexpr int kAccChunk = 64;     // member rows staged per round (row index + header in shared memory)
+
+// float32(q) / 255.0f, correctly rounded like the reference's `float32(quantized) / 255.0` (quantization.go:56), without
+// the division sequence: q as a float by a byte permute into 2^23's mantissa, one multiply by float32(1/255) and one
+// Newton correction (exact for every q in 0..255: checked exhaustively against IEEE division).
+__device__ __forceinline__ float byte_over_255(uint32_t word, int k) {
+    const float x = __uint_as_float(__byte_perm(word, 0x4B000000u, 0x7650u + (uint32_t)k)) - 8388608.0f;
+    const float rcp = 0x1.010102p-8f;
+    const float r = __fmul_rn(x, rcp);
+    const float e = __fmaf_rn(-r, 255.0f, x);
+    return __fmaf_rn(e, rcp, r);
+}
 
 // order[seg_off[c] .. seg_off[c+1]) = rows assigned to centroid c, ascending.
-__global__ void __launch_bounds__(kDimsPerBlock)
+__global__ void __launch_bounds__(kAccThreads)
 kmeans_accumulate_kernel(MatView data, const uint32_t *__restrict__ order, const uint32_t *__restrict__ seg_off,
                          float *__restrict__ means, int64_t *__restrict__ counts) {
+    __shared__ uint32_t s_row[kAccChunk];
+    __shared__ float2 s_hdr[kAccChunk];
     const int c = blockIdx.x;
-    const int j = blockIdx.y * kDimsPerBlock + threadIdx.x;
+    const int j0 = (blockIdx.y * kAccThreads + threadIdx.x) * 4;
     const uint32_t beg = seg_off[c], end = seg_off[c + 1];
     if (blockIdx.y == 0 && threadIdx.x == 0) counts[c] = (int64_t)(end - beg);
-    if (j >= data.d) return;
-    float sum = 0.0f;  // k_means.go:60-65 zero-initialised sumVectors
-#pragma unroll 4
-    for (uint32_t i = beg; i < end; i++) {
-        const uint32_t row = order[i];
-        const float2 h = data.hdr[row];
-        const uint32_t q = data.codes[(size_t)row * data.d_pad + j];
-        // compute.DequantizeVectorFloat32(data[i]) then sumVectors[c][j] += val  (k_means.go:81-84)
-        sum = __fadd_rn(sum, ref_dequant_f32(q, h.x, __fsub_rn(h.y, h.x)));
+    const bool live = j0 < data.d_pad;  // d_pad is a multiple of 16: the 4-byte word stays inside the padded row
+    float s0 = 0.0f, s1 = 0.0f, s2 = 0.0f, s3 = 0.0f;  // k_means.go:60-65 zero-initialised sumVectors
+    for (uint32_t base = beg; base < end; base += kAccChunk) {
+        const int cnt = (int)min((uint32_t)kAccChunk, end - base);
+        __syncthreads();
+        if ((int)threadIdx.x < cnt) {
+            const uint32_t r = order[base + threadIdx.x];
+            s_row[threadIdx.x] = r;
+            s_hdr[threadIdx.x] = data.hdr[r];
+        }
+        __syncthreads();
+        if (live) {
+#pragma unroll 8
+            for (int i = 0; i < cnt; i++) {
+                const uint32_t w = *reinterpret_cast<const uint32_t *>(data.codes + (size_t)s_row[i] * data.d_pad + j0);
+                const float2 h = s_hdr[i];
+                const float range = __fsub_rn(h.y, h.x);
+                // compute.DequantizeVectorFloat32(data[i]) then sumVectors[c][j] += val  (k_means.go:81-84)
+                s0 = __fadd_rn(s0, __fadd_rn(h.x, __fmul_rn(byte_over_255(w, 0), range)));
+                s1 = __fadd_rn(s1, __fadd_rn(h.x, __fmul_rn(byte_over_255(w, 1), range)));
+                s2 = __fadd_rn(s2, __fadd_rn(h.x, __fmul_rn(byte_over_255(w, 2), range)));
+                s3 = __fadd_rn(s3, __fadd_rn(h.x, __fmul_rn(byte_over_255(w, 3), range)));
+            }
+        }
     }
-    if (end > beg) means[(size_t)c * data.d + j] = __fdiv_rn(sum, (float)(int64_t)(end - beg));  // :89-96
+    if (end > beg && live) {  // :89-96 (an empty cluster keeps its previous mean)
+        const float n = (float)(int64_t)(end - beg);
+        float *m = means + (size_t)c * data.d;
+        if (j0 + 0 < data.d) m[j0 + 0] = __fdiv_rn(s0, n);
+        if (j0 + 1 < data.d) m[j0 + 1] = __fdiv_rn(s1, n);
+        if (j0 + 2 < data.d) m[j0 + 2] = __fdiv_rn(s2, n);
+        if (j0 + 3 < data.d) m[j0 + 3] = __fdiv_rn(s3, n);
+    }
 }
 
 cudaError_t launch_kmeans_accumulate(const MatView &data, const uint32_t *order, const uint32_t *seg_off, int k,
                                      float *means, int64_t *counts, cudaStream_t st) {
-    dim3 grid(k, (data.d + kDimsPerBlock - 1) / kDimsPerBlock);
-    kmeans_accumulate_kernel<<<grid, kDimsPerBlock, 0, st>>>(data, order, seg_off, means, counts);
+    dim3 grid(k, (data.d_pad + kAccThreads * 4 - 1) / (kAccThreads * 4));
+    kmeans_accumulate_kernel<<<grid, kAccThreads, 0, st>>>(data, order, seg_off, means, counts);
     return cudaGetLastError();
 }
 

@@ -27,6 +27,38 @@ def KMeansStep(data_matrix, centroids, means, ctx=None, want_assign=True):
     return assign, counts, newc, bool(conv.value)
 
 
+SUPERSET_MUL = 5                 # config/constants.go:11
+KMEANS_ITTERATION_LIMIT = 1000   # config/constants.go:12
+
+
+def KMeans(data_matrix, k, superset_rows=None, rng=None, iter_limit=KMEANS_ITTERATION_LIMIT, ctx=None, want_stats=False):
+    """kMeans (dnc/k_means.go:19-212): the k centroids ((k, 8+d) uint8) of the rows of `data_matrix` (compute.Matrix).
+
+    k <= 0 returns None (:20-22); a matrix with at most k rows is returned unchanged as rows (:24-26).  The reference
+    seeds its superset from the wall clock (:29); pass `superset_rows` (min(n, 5k) distinct row indices) or an `rng`
+    (numpy Generator) to make a build reproducible.
+    """
+    ctx = ctx or default_context()
+    if k <= 0:
+        return None
+    n = data_matrix.rows
+    if n == 0 or n <= k:
+        return data_matrix.ReadRows()
+    ks = min(n, k * SUPERSET_MUL)
+    if superset_rows is None:
+        rng = rng or np.random.default_rng()
+        superset_rows = rng.choice(n, ks, replace=False)
+    rows = np.ascontiguousarray(superset_rows, dtype=np.uint64)
+    assert rows.shape == (ks,) and len(set(rows.tolist())) == ks, "superset rows must be min(n, 5k) distinct indices"
+    out = np.empty((k, 8 + data_matrix.cols), np.uint8)
+    stats = np.zeros(4, np.int64)
+    _check(data_matrix._L.vs_kmeans(ctx.handle, data_matrix.handle, int(k), _p(rows), ks, int(iter_limit), _p(out), _p(stats)))
+    if want_stats:
+        return out, {"superset_iterations": int(stats[0]), "set_iterations": int(stats[1]),
+                     "assign_us": int(stats[2]), "update_us": int(stats[3])}
+    return out
+
+
 def Recenter(matrix, ctx=None):
     """recenterDbCentroid's arithmetic (dnc.go:417-449) over all rows of `matrix` -> row776."""
     ctx = ctx or default_context()

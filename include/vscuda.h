@@ -209,6 +209,14 @@ VS_API int vs_topk_merge_packed_dev(vs_ctx *ctx, const void *d_packed, size_t ra
  * Outputs (host): assign_out[n] (nullable), counts_out[k], new_centroids_out[k*(8+D)], *converged_out. */
 VS_API int vs_kmeans_step(vs_ctx *ctx, const vs_matrix *data, const uint8_t *centroids_packed, size_t k, float *means,
                    int64_t *assign_out, int64_t *counts_out, uint8_t *new_centroids_out, int *converged_out);
+/* kMeans (dnc/k_means.go:19-212) with every iteration on the device.  superset_rows[ks] = the distinct random data rows
+ * the reference draws at :35-44 (ks = min(n, 5k)); the superset is iterated until the centroids' code bytes stop
+ * changing or iter_limit iterations (:67-117), its first k centroids and their float32 means are kept (:125-154), and
+ * the set is iterated the same way (:157-207).  centroids_out: k rows of 8+D bytes (host).
+ * stats_out (nullable, [4]): iterations of the superset phase, of the set phase, microseconds spent assigning, updating.
+ * The early returns of :20-26 (k <= 0, n <= k) are the binding's: they need no device work. */
+VS_API int vs_kmeans(vs_ctx *ctx, const vs_matrix *data, size_t k, const uint64_t *superset_rows, size_t ks, size_t iter_limit,
+              uint8_t *centroids_out, int64_t *stats_out);
 /* recenterDbCentroid (dnc.go:417-449): float64 mean of all rows of m in row order -> row776. */
 VS_API int vs_recenter(vs_ctx *ctx, const vs_matrix *m, uint8_t *out_row);
 

@@ -219,3 +219,29 @@ def recenter(rows):
     out = np.empty(rb, np.uint8)
     lib().ora_recenter(_p(rows), C.c_size_t(n), C.c_size_t(rb), _p(out))
     return out
+
+
+def kmeans(data, k, superset_rows, limit=1000):
+    """kMeans (dnc/k_means.go:19-212) with the random superset draw (:35-44) supplied by the caller: iterate the
+    superset until the code bytes stop changing (:67-117), keep the first k (the sort at :132 compares counts that
+    :111-113 have already zeroed, so Go's pattern-defeating quicksort leaves the all-equal slice as it is), iterate the
+    set (:157-207).  The float32 means survive from iteration to iteration and from the superset to the set (:153-154).
+    Returns (centroids, iterations of the superset phase, iterations of the set phase)."""
+    data = _u8(data)
+    if k <= 0:
+        return None, 0, 0                      # :20-22
+    if data.shape[0] == 0 or data.shape[0] <= k:
+        return data, 0, 0                      # :24-26
+    cent = data[np.asarray(superset_rows, np.int64)].copy()
+    means = np.zeros((cent.shape[0], data.shape[1] - 8), np.float32)
+    iters = []
+    for phase in range(2):
+        if phase == 1:
+            cent = np.ascontiguousarray(cent[:k])
+            means = np.ascontiguousarray(means[:k])
+        n, conv = 0, False
+        while n < limit and not conv:
+            _, _, cent, conv = kmeans_step(data, cent, means)
+            n += 1
+        iters.append(n)
+    return cent, iters[0], iters[1]

@@ -33,3 +33,37 @@ def test_kmeans_steps_parity(vs, oracle, d, n, k):
 def test_recenter_parity(vs, oracle, d, n):
     rows = oracle.quantize_matrix_f32(unit_rows(n, d, 5))
     assert (vs.dnc.Recenter(vs.compute.NewMatrix(rows)) == oracle.recenter(rows)).all()
+
+
+@pytest.mark.parametrize("d,n,k", [(768, 4000, 5), (256, 3000, 3), (64, 1500, 8)])
+def test_kmeans_full_loop_parity(vs, oracle, d, n, k):
+    """The whole kMeans (k_means.go:19-212) given the superset draw: superset phase, truncation to the first k, set phase."""
+    data = oracle.quantize_matrix_f32(unit_rows(n, d, 70 + k))
+    rows = np.random.default_rng(k).choice(n, min(n, 5 * k), replace=False)
+    want, it1, it2 = oracle.kmeans(data, k, rows, limit=12)
+    got, st = vs.dnc.KMeans(vs.compute.NewMatrix(data), k, superset_rows=rows, iter_limit=12, want_stats=True)
+    assert (st["superset_iterations"], st["set_iterations"]) == (it1, it2)
+    assert (got == want).all()
+
+
+def test_kmeans_full_loop_tensor_core_assign(vs, oracle):
+    """Same, with the centroid counts of both phases above the tensor-core assignment threshold."""
+    d, n, k = 512, 5000, 20
+    data = oracle.quantize_matrix_f32(unit_rows(n, d, 91))
+    rows = np.random.default_rng(9).choice(n, 5 * k, replace=False)
+    want, it1, it2 = oracle.kmeans(data, k, rows, limit=4)
+    vs.compute.debug_set_argmax_gemm_min(16)
+    try:
+        got, st = vs.dnc.KMeans(vs.compute.NewMatrix(data), k, superset_rows=rows, iter_limit=4, want_stats=True)
+    finally:
+        vs.compute.debug_set_argmax_gemm_min(256)
+    assert (st["superset_iterations"], st["set_iterations"]) == (it1, it2)
+    assert (got == want).all()
+
+
+def test_kmeans_early_returns(vs):
+    """k <= 0 -> nil; len(data) <= k -> data unchanged (k_means.go:20-26)."""
+    data = vs.compute.QuantizeMatrixFloat32(unit_rows(4, 64, 1))
+    m = vs.compute.NewMatrix(data)
+    assert vs.dnc.KMeans(m, 0) is None
+    assert (vs.dnc.KMeans(m, 4) == data).all() and (vs.dnc.KMeans(m, 9) == data).all()
