@@ -46,6 +46,7 @@ def parse():
     ap.add_argument("--k", type=int, default=10)
     ap.add_argument("--batch", type=int, default=int(os.environ.get("VS_BENCH_BATCH", 64)))
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-extra", action="store_true", help="skip the config-3 / config-4 side measurements")
     return ap.parse_args()
 
 
@@ -370,6 +371,8 @@ def run_b200(a):
         "clocks": clocks,
     }
 
+    if world == 1 and not a.no_extra:
+        out["other_configs"] = other_configs(pkg, torch, ctx, ix, a, device, peaks)
     if world == 1 and not a.no_cpu_baseline:
         out["cpu_baseline"] = cpu_baseline(pkg, ctx, ix, cent, a, qhost[W + K - 1], result_ids, result_sims, offsets)
     print(json.dumps(out), flush=True)
@@ -378,13 +381,113 @@ def run_b200(a):
         dist.destroy_process_group()
 
 
+def other_configs(pkg, torch, ctx, ix, a, device, peaks):
+    """Side measurements on the same store (not the headline): BASELINE config 3 (a batch of 4096 queries over every row
+    as a tcgen05 int8 GEMM with fused filter) and a slice of config 4 (nearest of 65536 centroids for 1M rows, the
+    k-means assign step).  Tensor-bound: achieved integer TOPS against the measured cuBLASLt int8 peak of this pool
+    (profiles/r01_tensor_peaks.json; MEASURED_PEAKS.json carries no int8 figure) and the 4.5 POPS nominal."""
+    cp = pkg.compute
+    out = {}
+    try:
+        tp = json.load(open(os.path.join(ROOT, "profiles", "r01_tensor_peaks.json")))
+        int8_peak, src = float(tp["int8_tops_8192"]), "measured cuBLASLt int8 8192^3 (profiles/r01_tensor_peaks.json)"
+    except Exception:  # noqa: BLE001
+        int8_peak, src = 4500.0, "nominal dense int8"
+    try:
+        nq, k, reps = 4096, a.k, 3
+        qms = []
+        for s in range(reps + 1):
+            x = gen_unit_rows(torch, SEED_QUERY, 5000 + s, nq, device)
+            torch.cuda.synchronize()
+            m = cp.EmptyMatrix(nq, D, ctx=ctx)
+            m.FillFloat32Dev(0, x.data_ptr(), nq, ctx=ctx)
+            ctx.sync()
+            qms.append(m)
+            del x
+        d_ids = torch.zeros((nq, k), dtype=torch.int64, device=device)
+        d_sims = torch.zeros((nq, k), dtype=torch.float32, device=device)
+        d_counts = torch.zeros(nq, dtype=torch.int32, device=device)
+        ix.SearchBatchDev(qms[0], k, d_ids.data_ptr(), d_sims.data_ptr(), d_counts.data_ptr(), ctx=ctx)
+        ctx.sync()
+        ctx.profile_enable(True)
+        ctx.timer_start()
+        stats = [ix.SearchBatchDev(qms[1 + s], k, d_ids.data_ptr(), d_sims.data_ptr(), d_counts.data_ptr(), ctx=ctx)
+                 for s in range(reps)]
+        ms = ctx.timer_stop() / reps
+        gemm_ms, gemm_launches = ctx.profile_read()
+        ctx.profile_enable(False)
+        ops = 2.0 * nq * a.rows * D
+        tops = ops / (gemm_ms / max(1, gemm_launches) * 1e-3) / 1e12
+        # parity of a few queries against the streaming-scan path (itself checked against the oracle in cpu_baseline)
+        nchk = 16
+        qh = qms[reps].ReadRows()[:nchk]
+        s_ids, s_sims, _ = ix.Search(qh, a.centroids, k, ctx=ctx)
+        match = bool((d_ids[:nchk].cpu().numpy().view(np.uint64) == s_ids).all() and
+                     (d_sims[:nchk].cpu().numpy().view(np.uint32) == s_sims.view(np.uint32)).all())
+        out["batch_search_config3"] = {
+            "workload": f"{nq} queries x {a.rows} x {D}-d uint8 rows, top-{k}, int8 tensor-core GEMM + fused filter",
+            "queries_per_s": round(nq / (ms * 1e-3), 1), "ms_per_batch": round(ms, 3),
+            "roofline": {"bound": "tensor", "kernel": "gemm_kernel<MODE_FILTER> (tcgen05.mma kind::i8)",
+                         "achieved": round(tops, 1), "peak": int8_peak, "peak_source": src, "unit": "TOP/s",
+                         "frac": round(tops / int8_peak, 4), "frac_of_nominal_4500": round(tops / 4500.0, 4),
+                         "int_ops_per_launch": ops, "ms_per_launch": round(gemm_ms / max(1, gemm_launches), 3),
+                         "launches_timed": gemm_launches},
+            "whole_batch_tops": round(ops / (ms * 1e-3) / 1e12, 1),
+            "candidates_per_batch": int(np.mean([st[0] for st in stats])),
+            "queries_finished_by_scan": int(sum(st[1] for st in stats)),
+            "parity_vs_scan_path": {"queries_checked": nchk, "match": match}}
+        del qms, d_ids, d_sims, d_counts
+    except Exception as e:  # noqa: BLE001
+        out["batch_search_config3"] = {"error": repr(e)[:300]}
+    try:
+        n4, k4 = min(1_000_000, a.rows), 65536
+        cent4 = cp.EmptyMatrix(k4, D, ctx=ctx)
+        x = gen_unit_rows(torch, SEED_CENT, 1, k4, device)
+        torch.cuda.synchronize()
+        cent4.FillFloat32Dev(0, x.data_ptr(), k4, ctx=ctx)
+        ctx.sync()
+        del x
+        data4 = cp.EmptyMatrix(n4, D, ctx=ctx)
+        for ci, r0 in enumerate(range(0, n4, CHUNK)):
+            cnt = min(CHUNK, n4 - r0)
+            x = gen_unit_rows(torch, SEED_DATA, ci, cnt, device)
+            torch.cuda.synchronize()
+            data4.FillFloat32Dev(r0, x.data_ptr(), cnt, ctx=ctx)
+            ctx.sync()
+            del x
+        assign = torch.empty(n4, device=device, dtype=torch.int32)
+        cent4.ArgmaxDev(data4, assign.data_ptr(), ctx=ctx)
+        ctx.sync()
+        ctx.timer_start()
+        cent4.ArgmaxDev(data4, assign.data_ptr(), ctx=ctx)
+        ms = ctx.timer_stop()
+        ops = 2.0 * n4 * k4 * D
+        nchk = 2048
+        sample = cp.NewMatrix(data4.ReadRows(0, nchk))
+        cp.debug_set_argmax_gemm_min(1 << 30)
+        _, want = cent4.MatrixCosineSimilarity(sample, ctx=ctx, want_sims=False)
+        cp.debug_set_argmax_gemm_min(256)
+        out["kmeans_assign_config4_slice"] = {
+            "workload": f"nearest of {k4} centroids for {n4} x {D}-d uint8 rows (one k-means assign step; config 4 is 100x "
+                        f"these rows: profiles/r01_kmeans_100m.json)",
+            "rows_per_s": round(n4 / (ms * 1e-3), 1), "ms": round(ms, 3),
+            "roofline": {"bound": "tensor", "achieved": round(ops / (ms * 1e-3) / 1e12, 1), "peak": int8_peak, "peak_source": src,
+                         "unit": "TOP/s", "frac": round(ops / (ms * 1e-3) / 1e12 / int8_peak, 4),
+                         "note": "whole call: sampled pre-pass + filter GEMM + candidate resolution, 2*n*k*768 integer ops"},
+            "parity_vs_scan_form": {"rows_checked": nchk, "match": bool((assign[:nchk].cpu().numpy() == want).all())}}
+        del data4, cent4, assign
+    except Exception as e:  # noqa: BLE001
+        out["kmeans_assign_config4_slice"] = {"error": repr(e)[:300]}
+    torch.cuda.empty_cache()
+    return out
+
+
 def cpu_baseline(pkg, ctx, ix, cent, a, queries, gpu_ids, gpu_sims, offsets):
     """The oracle on the host cores, on a bounded sample: the first `nq` queries of the last timed step, each doing the
     full per-query work (all centroids + its probed lists). Doubles as a parity check of the timed GPU results."""
     import oracle
     cores = os.cpu_count() or 1
     centroids = cent.ReadRows()
-    nq_max = min(queries.shape[0], max(8, 2 * cores))
 
     def host_index(qs):
         lists = set()
@@ -401,21 +504,24 @@ def cpu_baseline(pkg, ctx, ix, cent, a, queries, gpu_ids, gpu_sims, offsets):
         order = np.argsort(ids, kind="stable")   # the reference streams rows in primary-key order
         return rows[order], ids[order], lor[order]
 
-    t0 = time.perf_counter()
     rows1, ids1, lor1 = host_index(queries[:1])
     t0 = time.perf_counter()
     oracle.search_many(queries[:1], centroids, rows1, lor1, ids1, a.nprobe, a.k, threads=1)
     t1 = time.perf_counter() - t0
-    nq = int(max(1, min(nq_max, round(15.0 * cores / max(t1, 1e-3)))))
+    nq = int(min(queries.shape[0], 32))
     rows, ids, lor = host_index(queries[:nq])
+    # about 12 s of CPU work: the sample is repeated (every repetition redoes the full per-query work: ~54 MB of rows per
+    # query, far beyond the host caches)
+    reps = int(max(1, min(50, round(12.0 * cores / max(t1 * nq, 1e-3)))))
     t0 = time.perf_counter()
-    o_ids, o_sims, o_counts = oracle.search_many(queries[:nq], centroids, rows, lor, ids, a.nprobe, a.k, threads=cores)
+    for _ in range(reps):
+        o_ids, o_sims, o_counts = oracle.search_many(queries[:nq], centroids, rows, lor, ids, a.nprobe, a.k, threads=cores)
     dt = time.perf_counter() - t0
     parity = bool((o_ids == gpu_ids[:nq]).all() and (o_sims.view(np.uint32) == gpu_sims[:nq].view(np.uint32)).all())
-    return {"value": round(nq / dt, 3), "unit": "queries/s", "cores": cores, "kind": "port",
-            "sample": f"{nq} queries of the last timed step, full per-query work (4096 centroids + {a.nprobe} probed lists "
-                      f"~{int(rows.shape[0] / max(1, nq))} rows/query incl. overlap), oracle (default-backend restatement) on "
-                      f"{cores} threads; single-thread {round(1.0 / t1, 3)} q/s",
+    return {"value": round(nq * reps / dt, 3), "unit": "queries/s", "cores": cores, "kind": "port",
+            "sample": f"{nq} queries of the last timed step x {reps} repetitions, full per-query work (4096 centroids + "
+                      f"{a.nprobe} probed lists ~{int(rows.shape[0] / max(1, nq))} rows/query incl. overlap), oracle "
+                      f"(default-backend restatement) on {cores} threads; single-thread {round(1.0 / t1, 3)} q/s",
             "seconds": round(dt, 2), "parity_vs_gpu_topk": parity}
 
 
