@@ -208,6 +208,7 @@ extern "C" int vs_debug_set_certify_scale(float scale) {
     CU(vs::scan_set_certify_scale(scale));
     CU(vs::argmax_set_certify_scale(scale));
     CU(vs::gemm_set_certify_scale(scale));
+    CU(vs::probe_set_certify_scale(scale));
     return VS_OK;
 }
 
@@ -859,6 +860,9 @@ struct SearchBufs {
     unsigned int *tickets;  // [nq]
     double *qnorm;          // exact only
     uint32_t *q_select;     // exact only
+    uint32_t *probe_keys;   // batched probe selection (probe.cu): [nq][C] similarity keys, or null
+    unsigned int *flag_cnt; // [nq]
+    uint32_t *flag_list;    // [nq][kProbeFlagCap]
     int grid;               // blocks per stage launch
     int iters1, iters2;     // rows per lane group (tile height) of each stage
     int tile_rows1, tile_rows2;
@@ -890,6 +894,14 @@ static int search_plan(const vs_index *ix, size_t nq, size_t npe, bool flat, Sea
     return VS_OK;
 }
 
+constexpr size_t kProbeBatchMin = 8;  // from this many queries on the probe stage reads the centroid table once (probe.cu)
+static bool use_probe_batch(const vs_index *ix, size_t nq, size_t npe, bool flat) {
+    return !flat && nq >= kProbeBatchMin && ix->centroids && probe_batch_supported(ix->centroids->view(), nq, npe);
+}
+static size_t probe_batch_bytes(size_t nq, size_t C) {
+    return Arena::pad(nq * C * 4) + Arena::pad(nq * 4) + Arena::pad(nq * (size_t)kProbeFlagCap * 4);
+}
+
 static size_t search_bytes(size_t nq, size_t npe, int kpl1, int kpl2, int grid, size_t d) {
     return Arena::pad(nq * npe * 4) + Arena::pad((nq + grid) * (size_t)32 * kpl1 * sizeof(Cand)) +
            Arena::pad((nq + grid) * (size_t)32 * kpl2 * sizeof(Cand)) + 3 * Arena::pad(nq * 4) + Arena::pad(nq * d * 8) + 4096;
@@ -909,7 +921,14 @@ static int search_enqueue(vs_ctx *c, const vs_index *ix, const MatView &qv, size
     p.out_status = d_status;
     p.fix_counter = c->d_fix_counter;
     const uint32_t tr1 = exact ? 32 : b.tile_rows1, tr2 = exact ? 32 : b.tile_rows2;
-    if (!flat) {
+    if (!flat && !exact && !d_select && b.probe_keys && nq_launch == qv.n) {
+        // a batch: score every (query, centroid) pair with the table read once, then select per query (probe.cu)
+        LAUNCH(c, launch_probe_batch(ix->centroids->view(), qv, (int)npe, b.probe_keys, b.flag_cnt, b.flag_list, b.probe,
+                                     d_probe_sims, b.qtiles, ix->list_off, tr2, d_status, kStatusProbeAmbiguous, 1, c->d_fix_counter,
+                                     g_sm_count, c->stream));
+        c->launches++;
+        if (stage1_only) return VS_OK;
+    } else if (!flat) {
         p.rows = ix->centroids->view();
         p.ids = nullptr;
         p.id_base = 0;
@@ -994,7 +1013,8 @@ static int search_setup(vs_ctx *c, Arena &a, const vs_index *ix, size_t nq, size
     if (!s->kpl2) return fail(VS_ERANGE, "k=%zu: at most 128 hits (Count+Offset) per query", k);
     if (!s->kpl1) return fail(VS_ERANGE, "nprobe=%zu: at most 128 probed lists unless nprobe >= number of lists", nprobe);
     VS(search_plan(ix, nq, s->npe, s->flat, &s->b));
-    VS(a.reserve(a.off + extra_bytes + search_bytes(nq, s->npe, s->kpl1, s->kpl2, s->b.grid, ix->data->d)));
+    VS(a.reserve(a.off + extra_bytes + search_bytes(nq, s->npe, s->kpl1, s->kpl2, s->b.grid, ix->data->d) +
+                 (use_probe_batch(ix, nq, s->npe, s->flat) ? probe_batch_bytes(nq, ix->C) : 0)));
     return VS_OK;
 }
 
@@ -1006,6 +1026,12 @@ static void search_take(Arena &a, const vs_index *ix, size_t nq, SearchSetup *s)
     s->b.tickets = a.take<unsigned int>(nq);
     s->b.qnorm = a.take<double>(nq * (size_t)ix->data->d);
     s->b.q_select = a.take<uint32_t>(nq);
+    s->b.probe_keys = nullptr;
+    if (use_probe_batch(ix, nq, s->npe, s->flat)) {
+        s->b.probe_keys = a.take<uint32_t>(nq * ix->C);
+        s->b.flag_cnt = a.take<unsigned int>(nq);
+        s->b.flag_list = a.take<uint32_t>(nq * (size_t)kProbeFlagCap);
+    }
 }
 
 // Finish the queries whose status is non-zero with literal arithmetic. h_status: host copy of d_status.

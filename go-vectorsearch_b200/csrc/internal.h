@@ -153,6 +153,15 @@ cudaError_t gemm_enqueue_select(const MatView &rows, const uint64_t *ids, uint64
                                 const GemmBufs &b, int k, uint64_t *d_ids, float *d_sims, int32_t *d_counts, uint32_t *d_status,
                                 unsigned long long *fix_counter, int sm_count, cudaStream_t st, uint64_t *launches);
 
+// probe.cu: probe selection for a batch of queries (the centroid table is read once, not once per query)
+constexpr int kProbeFlagCap = 64;   // uncertified (query, centroid) pairs listed per query
+bool probe_batch_supported(const MatView &cent, size_t nq, size_t k);
+cudaError_t launch_probe_batch(const MatView &cent, const MatView &queries, int k, uint32_t *keys, unsigned int *flag_cnt,
+                               uint32_t *flag_list, uint32_t *out_probe, float *out_sims, uint32_t *out_qtiles,
+                               const uint64_t *next_list_off, uint32_t next_tile_rows, uint32_t *out_status, uint32_t status_bit,
+                               int status_init, unsigned long long *fix_counter, int sm_count, cudaStream_t st);
+cudaError_t probe_set_certify_scale(float scale);
+
 // quantize.cu
 cudaError_t launch_quantize_f32(const float *in, size_t n, int d, uint8_t *out_rows, cudaStream_t st);
 cudaError_t launch_quantize_f64(const double *in, size_t n, int d, uint8_t *out_rows, cudaStream_t st);

@@ -1,0 +1,370 @@
+// probe.cu -- probe selection for a batch of queries (server/search.go:202-227 for nq queries at once).
+//
+// The streaming stage kernel (scan.cu) re-reads the centroid table once per query; for a batch that is nq x C x 776 B
+// of L2 traffic (203 MB at 64 queries x 4096 centroids) for a table of 3 MB.  Here the table is read once: a warp keeps
+// eight centroid rows in registers and takes u8 dot products (dp4a) against every query of a shared-memory chunk, the
+// certified float32 similarity (common.cuh) of every (query, centroid) pair is written as an order-preserving key, and
+// a second kernel selects each query's nprobe best keys (similarity desc, centroid index asc) with a radix select.
+// Pairs whose float32 rounding could not be certified are listed per query; the few of them that can reach the probe
+// window are re-scored with literal reference arithmetic before the selection is accepted.
+#include "internal.h"
+
+namespace vs {
+namespace {
+
+#define FULL 0xFFFFFFFFu
+constexpr int kPsWarps = 4;                          // warps per block of the score kernel
+constexpr int kPsRows = kPsWarps * 8;                // centroid rows per work item (2 half-warps x 4 rows per warp)
+constexpr int kPsQueries = 32;                       // queries staged in shared memory per work item
+constexpr int kSelThreadsP = 256;
+constexpr int kMaxProbe = 128;
+
+// CPL = 16-byte chunks per lane; 16 lanes stream one row: d_pad = 256 * CPL bytes.
+template <int CPL>
+__global__ void __launch_bounds__(kPsWarps * 32)
+probe_score_kernel(MatView cent, MatView queries, uint32_t *__restrict__ keys, size_t key_stride,
+                   unsigned int *__restrict__ flag_cnt, uint32_t *__restrict__ flag_list) {
+    extern __shared__ __align__(16) unsigned char ps_smem[];
+    constexpr int CH = 16 * CPL;  // 16-byte chunks per row
+    uint4 *sh_q = reinterpret_cast<uint4 *>(ps_smem);                                       // [kPsQueries][CH]
+    SideConst *sh_side = reinterpret_cast<SideConst *>(ps_smem + (size_t)kPsQueries * CH * 16);  // [kPsQueries]
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int hw = lane >> 4, l = lane & 15;
+    const int D = cent.d, d_pad = cent.d_pad;
+    const uint32_t C = (uint32_t)cent.n, nq = (uint32_t)queries.n;
+    const uint32_t row_tiles = (C + kPsRows - 1) / kPsRows, q_chunks = (nq + kPsQueries - 1) / kPsQueries;
+    for (uint32_t item = blockIdx.x; item < row_tiles * q_chunks; item += gridDim.x) {
+        const uint32_t rt = item % row_tiles, qc = item / row_tiles;
+        const uint32_t q0 = qc * kPsQueries;
+        const int nqc = (int)min((uint32_t)kPsQueries, nq - q0);
+        __syncthreads();  // the previous item's shared reads are done
+        {
+            const uint4 *src = reinterpret_cast<const uint4 *>(queries.codes + (size_t)q0 * d_pad);
+            for (int i = threadIdx.x; i < nqc * CH; i += blockDim.x) sh_q[i] = src[i];
+            for (int j = threadIdx.x; j < nqc; j += blockDim.x) {
+                const float2 h = queries.hdr[q0 + j];
+                const uint2 s = queries.sums[q0 + j];
+                sh_side[j] = make_side(h.x, h.y, s.x, s.y, D);
+            }
+        }
+        __syncthreads();
+        const uint32_t row_base = rt * kPsRows + warp * 8 + hw * 4;
+        uint4 r[4][CPL];
+#pragma unroll
+        for (int i = 0; i < 4; i++) {
+            const uint32_t row = row_base + i;
+#pragma unroll
+            for (int j = 0; j < CPL; j++)
+                r[i][j] = row < C ? ld_stream_u4(cent.codes + (size_t)row * d_pad + (size_t)(l + 16 * j) * 16) : make_uint4(0, 0, 0, 0);
+        }
+        // after the reduction lane l of a half-warp holds the dot of (query qg + l/4, row row_base + l%4)
+        const uint32_t row_my = row_base + (l & 3);
+        float2 h_my = make_float2(0.f, 0.f);
+        uint2 s_my = make_uint2(0u, 0u);
+        if (row_my < C) {
+            h_my = cent.hdr[row_my];
+            s_my = cent.sums[row_my];
+        }
+        for (int qg = 0; qg < nqc; qg += 4) {
+            uint32_t v[16];
+#pragma unroll
+            for (int t = 0; t < 16; t++) v[t] = 0;
+#pragma unroll
+            for (int qq = 0; qq < 4; qq++) {
+                const int q = min(qg + qq, nqc - 1);
+#pragma unroll
+                for (int j = 0; j < CPL; j++) {
+                    const uint4 qv = sh_q[q * CH + l + 16 * j];
+#pragma unroll
+                    for (int i = 0; i < 4; i++) v[qq * 4 + i] = dot16(r[i][j], qv, v[qq * 4 + i]);
+                }
+            }
+            // transpose-reduce 16 values over the 16 lanes of the half-warp: lane l ends with the total of value l
+#pragma unroll
+            for (int t = 0; t < 8; t++) {
+                const uint32_t send = (l & 8) ? v[t] : v[t + 8], keep = (l & 8) ? v[t + 8] : v[t];
+                v[t] = keep + __shfl_xor_sync(FULL, send, 8);
+            }
+#pragma unroll
+            for (int t = 0; t < 4; t++) {
+                const uint32_t send = (l & 4) ? v[t] : v[t + 4], keep = (l & 4) ? v[t + 4] : v[t];
+                v[t] = keep + __shfl_xor_sync(FULL, send, 4);
+            }
+#pragma unroll
+            for (int t = 0; t < 2; t++) {
+                const uint32_t send = (l & 2) ? v[t] : v[t + 2], keep = (l & 2) ? v[t + 2] : v[t];
+                v[t] = keep + __shfl_xor_sync(FULL, send, 2);
+            }
+            {
+                const uint32_t send = (l & 1) ? v[0] : v[1], keep = (l & 1) ? v[1] : v[0];
+                v[0] = keep + __shfl_xor_sync(FULL, send, 1);
+            }
+            const int q = qg + (l >> 2);
+            if (q < nqc && row_my < C) {
+                bool flag;
+                const float sim = score_fast(sh_side[q], h_my.x, h_my.y, s_my.x, s_my.y, v[0], D, &flag);
+                keys[(size_t)(q0 + q) * key_stride + row_my] = f32_to_key(sim);
+                if (flag) {
+                    const unsigned int pos = atomicAdd(flag_cnt + q0 + q, 1u);
+                    if (pos < (unsigned int)kProbeFlagCap) flag_list[(size_t)(q0 + q) * kProbeFlagCap + pos] = row_my;
+                }
+            }
+        }
+    }
+}
+
+// One block per query: the k largest keys (ties by lowest centroid index) by an 8-bit radix select over the key row, a
+// rank sort of the k survivors, literal re-scores where an uncertified pair could be among them, emission.
+// REG: the thread's contiguous slice of the key row (<= 32 keys) lives in registers.
+template <bool REG>
+__global__ void __launch_bounds__(kSelThreadsP)
+probe_select_kernel(MatView cent, MatView queries, uint32_t *__restrict__ keys, size_t key_stride,
+                    const unsigned int *__restrict__ flag_cnt, const uint32_t *__restrict__ flag_list, int k,
+                    uint32_t *__restrict__ out_probe, float *__restrict__ out_sims, uint32_t *__restrict__ out_qtiles,
+                    const uint64_t *__restrict__ next_list_off, uint32_t next_tile_rows, uint32_t *__restrict__ out_status,
+                    uint32_t status_bit, int status_init, unsigned long long *fix_counter) {
+    extern __shared__ __align__(16) unsigned char sel_smem[];
+    double *sh_qn = reinterpret_cast<double *>(sel_smem);  // [D] normalized query (literal path only)
+    __shared__ unsigned int hist[256];
+    __shared__ uint32_t s_prefix, s_remaining;
+    __shared__ uint32_t s_key[kMaxProbe], s_id[kMaxProbe], o_key[kMaxProbe], o_id[kMaxProbe];
+    __shared__ unsigned int s_nsel, s_wties[kSelThreadsP / 32], s_tiles;
+    __shared__ int s_need_fix;
+    __shared__ double s_norm;
+    __shared__ unsigned char s_fstate[kProbeFlagCap];  // 0 = uncertified, 1 = re-scored, 2 = to re-score now
+
+    const uint32_t q = blockIdx.x;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const uint32_t C = (uint32_t)cent.n;
+    const int D = cent.d, d_pad = cent.d_pad;
+    const uint32_t per = (C + kSelThreadsP - 1) / kSelThreadsP;
+    const uint32_t lo = min(C, (uint32_t)tid * per), hi = min(C, lo + per);
+    uint32_t *kq = keys + (size_t)q * key_stride;
+    const unsigned int nflag_all = flag_cnt[q];
+    const int nflag = (int)min(nflag_all, (unsigned int)kProbeFlagCap);
+    uint32_t status = nflag_all > (unsigned int)kProbeFlagCap ? status_bit : 0u;  // unlisted uncertified pairs: the caller's literal path
+    if (tid < kProbeFlagCap) s_fstate[tid] = 0;
+    if (tid == 0) s_tiles = 0;
+    bool normalized = false;
+    uint32_t rk[REG ? 32 : 1];
+    uint32_t T = 0;
+    for (;;) {
+        if (REG) {
+#pragma unroll
+            for (int j = 0; j < 32; j++) rk[j] = lo + j < hi ? kq[lo + j] : 0u;
+        }
+        // visits the thread's keys in index order (register copies are indexed statically)
+        auto for_keys = [&](auto &&body) {
+            if (REG) {
+#pragma unroll
+                for (int j = 0; j < 32; j++)
+                    if (lo + j < hi) body(rk[j], lo + j);
+            } else {
+                for (uint32_t i = lo; i < hi; i++) body(kq[i], i);
+            }
+        };
+        // ---- k-th largest key: four 8-bit passes from the top byte ----
+        uint32_t prefix = 0, remaining = (uint32_t)k;
+        for (int pass = 0; pass < 4; pass++) {
+            const int shift = 24 - 8 * pass;
+            hist[tid] = 0;
+            __syncthreads();
+            for_keys([&](uint32_t kk, uint32_t) {
+                if (pass == 0 || (kk >> (shift + 8)) == prefix) atomicAdd(&hist[(kk >> shift) & 255u], 1u);
+            });
+            __syncthreads();
+            if (warp == 0) {  // lane L owns bins 8L .. 8L+7; walk from the top bin down
+                unsigned int c[8], tot = 0;
+#pragma unroll
+                for (int b = 0; b < 8; b++) {
+                    c[b] = hist[8 * lane + b];
+                    tot += c[b];
+                }
+                unsigned int above = tot;  // inclusive suffix sum over lanes, then made exclusive
+                for (int o = 1; o < 32; o <<= 1) {
+                    const unsigned int x = __shfl_down_sync(FULL, above, o);
+                    if (lane + o < 32) above += x;
+                }
+                above -= tot;
+                if (above < remaining && above + tot >= remaining) {
+                    unsigned int run = above;
+#pragma unroll
+                    for (int b = 7; b >= 0; b--) {
+                        if (run < remaining && run + c[b] >= remaining) {
+                            s_prefix = (prefix << 8) | (uint32_t)(8 * lane + b);
+                            s_remaining = remaining - run;
+                        }
+                        run += c[b];
+                    }
+                }
+            }
+            __syncthreads();
+            prefix = s_prefix;
+            remaining = s_remaining;
+        }
+        T = prefix;                          // the k-th largest key
+        const uint32_t need_ties = remaining;  // how many of the keys equal to T belong to the k (lowest indices first)
+        // ---- collect: keys above T in any order, then the first need_ties ties in index order ----
+        if (tid == 0) s_nsel = 0;
+        __syncthreads();
+        unsigned int my_ties = 0;
+        for_keys([&](uint32_t kk, uint32_t idx) {
+            if (kk > T) {
+                const unsigned int pos = atomicAdd(&s_nsel, 1u);
+                s_key[pos] = kk;
+                s_id[pos] = idx;
+            } else if (kk == T) {
+                my_ties++;
+            }
+        });
+        unsigned int incl = my_ties;
+        for (int o = 1; o < 32; o <<= 1) {
+            const unsigned int x = __shfl_up_sync(FULL, incl, o);
+            if (lane >= o) incl += x;
+        }
+        if (lane == 31) s_wties[warp] = incl;
+        __syncthreads();
+        unsigned int rank = incl - my_ties;
+        for (int w = 0; w < warp; w++) rank += s_wties[w];
+        const unsigned int base = s_nsel;  // = k - need_ties
+        if (my_ties && rank < need_ties) {
+            for_keys([&](uint32_t kk, uint32_t idx) {
+                if (kk == T && rank < need_ties) {
+                    s_key[base + rank] = T;
+                    s_id[base + rank] = idx;
+                    rank++;
+                }
+            });
+        }
+        if (tid == 0) s_need_fix = 0;
+        __syncthreads();
+        // ---- an uncertified pair matters iff its stored (upper) key reaches T: below T its true key is below T too ----
+        if (tid < nflag && s_fstate[tid] == 0) {
+            const uint32_t c = flag_list[(size_t)q * kProbeFlagCap + tid];
+            if (kq[c] >= T) {
+                s_fstate[tid] = 2;
+                s_need_fix = 1;
+            }
+        }
+        __syncthreads();
+        if (!s_need_fix) break;
+        if (!normalized) {  // normalizeVector of the query (compute/cosine.go:26,138-149), literal
+            const uint8_t *qc = queries.codes + (size_t)q * d_pad;
+            const float2 qh = queries.hdr[q];
+            const double mn = (double)qh.x, range = __dsub_rn((double)qh.y, (double)qh.x);
+            for (int i = tid; i < D; i += kSelThreadsP) sh_qn[i] = ref_dequant_f64(qc[i], mn, range);
+            __syncthreads();
+            if (warp == 0) {
+                const double nsq = warp_ordered_sum(D, lane, [&](int i) { return __dmul_rn(sh_qn[i], sh_qn[i]); });
+                if (lane == 0) s_norm = __dsqrt_rn(nsq);
+            }
+            __syncthreads();
+            const double norm = s_norm;
+            if (norm != 0.0)
+                for (int i = tid; i < D; i += kSelThreadsP) sh_qn[i] = __ddiv_rn(sh_qn[i], norm);
+            __syncthreads();
+            normalized = true;
+        }
+        for (int f = warp; f < nflag; f += kSelThreadsP / 32) {
+            if (s_fstate[f] == 2) {
+                const uint32_t c = flag_list[(size_t)q * kProbeFlagCap + f];
+                const float2 h = cent.hdr[c];
+                const double dot = warp_ref_cosine_row_f64(cent.codes + (size_t)c * d_pad, h.x, h.y, sh_qn, D, lane);
+                if (lane == 0) {
+                    kq[c] = f32_to_key(__double2float_rn(dot));
+                    s_fstate[f] = 1;
+                    if (fix_counter) atomicAdd(fix_counter, 1ull);
+                }
+            }
+        }
+        __syncthreads();  // the rewritten keys are visible to the whole block; select again
+    }
+    // ---- order the k survivors (similarity desc, centroid index asc) and emit ----
+    if (tid < k) {
+        const uint32_t mk = s_key[tid], mi = s_id[tid];
+        int rnk = 0;
+        for (int j = 0; j < k; j++) rnk += cand_better(s_key[j], (uint64_t)s_id[j], mk, (uint64_t)mi) ? 1 : 0;
+        o_key[rnk] = mk;
+        o_id[rnk] = mi;
+    }
+    __syncthreads();
+    uint32_t mytiles = 0;
+    if (tid < k) {
+        const uint32_t L = o_id[tid];
+        out_probe[(size_t)q * k + tid] = L;
+        if (out_sims) out_sims[(size_t)q * k + tid] = key_to_f32(o_key[tid]);
+        if (out_qtiles) {
+            const uint32_t len = (uint32_t)(next_list_off[L + 1] - next_list_off[L]);
+            mytiles = (len + next_tile_rows - 1) / next_tile_rows;
+        }
+    }
+    if (out_qtiles) {
+        for (int o = 16; o > 0; o >>= 1) mytiles += __shfl_xor_sync(FULL, mytiles, o);
+        if (lane == 0 && mytiles) atomicAdd(&s_tiles, mytiles);
+        __syncthreads();
+        if (tid == 0) out_qtiles[q] = s_tiles ? s_tiles : 1u;
+    }
+    if (tid == 0 && out_status) out_status[q] = status_init ? status : (out_status[q] | status);
+}
+
+}  // namespace
+
+cudaError_t probe_set_certify_scale(float scale) { return cudaMemcpyToSymbol(c_certify_scale, &scale, sizeof(float)); }
+
+bool probe_batch_supported(const MatView &cent, size_t nq, size_t k) {
+    const int cpl = cent.d_pad / 256;
+    return cent.d_pad % 256 == 0 && (cpl == 1 || cpl == 2 || cpl == 3 || cpl == 4 || cpl == 6) && k >= 1 && k <= (size_t)kMaxProbe &&
+           k <= cent.n && cent.n < 0x7FFFFFFFull && nq * cent.n <= ((size_t)32 << 20);
+}
+
+cudaError_t launch_probe_batch(const MatView &cent, const MatView &queries, int k, uint32_t *keys, unsigned int *flag_cnt,
+                               uint32_t *flag_list, uint32_t *out_probe, float *out_sims, uint32_t *out_qtiles,
+                               const uint64_t *next_list_off, uint32_t next_tile_rows, uint32_t *out_status, uint32_t status_bit,
+                               int status_init, unsigned long long *fix_counter, int sm_count, cudaStream_t st) {
+    const size_t nq = queries.n, C = cent.n;
+    cudaError_t e = cudaMemsetAsync(flag_cnt, 0, nq * sizeof(unsigned int), st);
+    if (e != cudaSuccess) return e;
+    const size_t items = ((C + kPsRows - 1) / kPsRows) * ((nq + kPsQueries - 1) / kPsQueries);
+    const unsigned grid = (unsigned)(items < (size_t)sm_count * 4 ? items : (size_t)sm_count * 4);
+    const size_t smem = (size_t)kPsQueries * cent.d_pad + kPsQueries * sizeof(SideConst);
+#define VS_PROBE_SCORE(CPL)                                                                                                   \
+    do {                                                                                                                      \
+        if (smem > 48 * 1024) {                                                                                               \
+            e = cudaFuncSetAttribute(probe_score_kernel<CPL>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);       \
+            if (e != cudaSuccess) return e;                                                                                   \
+        }                                                                                                                     \
+        probe_score_kernel<CPL><<<grid, kPsWarps * 32, smem, st>>>(cent, queries, keys, C, flag_cnt, flag_list);             \
+    } while (0)
+    switch (cent.d_pad / 256) {
+        case 1: VS_PROBE_SCORE(1); break;
+        case 2: VS_PROBE_SCORE(2); break;
+        case 3: VS_PROBE_SCORE(3); break;
+        case 4: VS_PROBE_SCORE(4); break;
+        case 6: VS_PROBE_SCORE(6); break;
+        default: return cudaErrorInvalidValue;
+    }
+#undef VS_PROBE_SCORE
+    e = cudaGetLastError();
+    if (e != cudaSuccess) return e;
+    const size_t smem2 = (size_t)cent.d * sizeof(double);
+    if (C <= (size_t)kSelThreadsP * 32) {
+        if (smem2 > 40 * 1024) {
+            e = cudaFuncSetAttribute(probe_select_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem2);
+            if (e != cudaSuccess) return e;
+        }
+        probe_select_kernel<true><<<(unsigned)nq, kSelThreadsP, smem2, st>>>(cent, queries, keys, C, flag_cnt, flag_list, k, out_probe,
+                                                                             out_sims, out_qtiles, next_list_off, next_tile_rows,
+                                                                             out_status, status_bit, status_init, fix_counter);
+    } else {
+        if (smem2 > 40 * 1024) {
+            e = cudaFuncSetAttribute(probe_select_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem2);
+            if (e != cudaSuccess) return e;
+        }
+        probe_select_kernel<false><<<(unsigned)nq, kSelThreadsP, smem2, st>>>(cent, queries, keys, C, flag_cnt, flag_list, k, out_probe,
+                                                                              out_sims, out_qtiles, next_list_off, next_tile_rows,
+                                                                              out_status, status_bit, status_init, fix_counter);
+    }
+    return cudaGetLastError();
+}
+
+}  // namespace vs

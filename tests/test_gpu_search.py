@@ -232,3 +232,86 @@ def test_striped_shards_merge_matches_full(vs, oracle, G):
         assert counts[i] == len(wi)
         assert ids[i, :counts[i]].tolist() == wi.tolist()
         assert (f32_bits(sims[i, :counts[i]]) == f32_bits(ws)).all()
+
+
+# ---- batches of >= 8 queries: the probe stage reads the centroid table once (probe.cu) -------------------------
+@pytest.mark.parametrize("d,C,nq,nprobe", [(768, 300, 40, 32), (768, 96, 9, 1), (512, 1000, 70, 100), (256, 64, 33, 64),
+                                           (1024, 40, 8, 7)])
+def test_batched_probe_selection_parity(vs, oracle, d, C, nq, nprobe):
+    n = 4000
+    rows, cent, lists, doc = _index_inputs(oracle, n, d, C, 40 + C)
+    cent[5] = cent[2]                       # identical centroids: equal similarities, lower index first
+    cent[7, :] = 0                          # zero centroid
+    ix = vs.ivf.Index.build_assigned(rows, doc, lists, cent)
+    q = unit_rows(nq, d, 7)
+    q[3] = 0
+    qs = oracle.quantize_matrix_f32(q)
+    qs[4] = cent[2]
+    probes, sims = ix.SelectProbes(qs, nprobe)
+    for i in range(nq):
+        wp, ws = oracle.select_probes(qs[i], cent, nprobe)
+        assert probes[i].tolist() == wp.tolist(), f"query {i}"
+        assert (f32_bits(sims[i]) == f32_bits(ws)).all(), f"query {i}"
+
+
+def test_batched_probe_many_centroids(vs, oracle):
+    """More than 8192 centroids: the select kernel reads its key slice from memory instead of registers."""
+    n, d, C, nq, nprobe = 2000, 256, 9000, 12, 48
+    rows = oracle.quantize_matrix_f32(unit_rows(n, d, 1))
+    cent = oracle.quantize_matrix_f32(unit_rows(C, d, 2))
+    cent[8000:8100] = cent[100]             # a run of ties far apart in index
+    lists = (np.arange(n) % C).astype(np.uint32)
+    doc = np.arange(n, dtype=np.uint64)
+    ix = vs.ivf.Index.build_assigned(rows, doc, lists, cent)
+    qs = oracle.quantize_matrix_f32(unit_rows(nq, d, 3))
+    qs[0] = cent[100]
+    probes, sims = ix.SelectProbes(qs, nprobe)
+    for i in range(nq):
+        wp, ws = oracle.select_probes(qs[i], cent, nprobe)
+        assert probes[i].tolist() == wp.tolist(), f"query {i}"
+        assert (f32_bits(sims[i]) == f32_bits(ws)).all()
+
+
+def test_batched_search_parity_and_small_call_agreement(vs, oracle):
+    n, d, C, nq, nprobe, k = 30000, 768, 128, 24, 16, 10
+    rows, cent, lists, doc = _index_inputs(oracle, n, d, C, 61, docs_per=2)
+    ix = vs.ivf.Index.build_assigned(rows, doc, lists, cent)
+    qs = oracle.quantize_matrix_f32(unit_rows(nq, d, 62))
+    _check(oracle, ix, qs, cent, rows, lists, doc, nprobe, k)
+    ids, sims, counts = ix.Search(qs, nprobe, k)                           # batched probe stage
+    parts = [ix.Search(qs[i:i + 4], nprobe, k) for i in range(0, nq, 4)]   # per-query streaming probe stage
+    assert (ids == np.concatenate([p[0] for p in parts])).all()
+    assert (f32_bits(sims) == f32_bits(np.concatenate([p[1] for p in parts]))).all()
+
+
+def test_batched_probe_literal_paths(vs, oracle):
+    """Adversarial centroids (tiny norms: many uncertified pairs, re-scored inside the select kernel) and the
+    certification disabled altogether (more uncertified pairs than the per-query list holds: the caller's path)."""
+    d, n, C, nq = 768, 3000, 200, 16
+    rng = np.random.default_rng(5)
+    rows = noop_rows(n, d, 5)
+    rows[:, 8:] = rng.integers(126, 130, (n, d), dtype=np.uint8)
+    cent = rows[:C].copy()
+    cent[::3] = noop_rows((C + 2) // 3, d, 6)      # a mix of well- and ill-conditioned centroids
+    _, lists = oracle.argmax_MxN(cent, rows)
+    lists = lists.astype(np.uint32)
+    doc = np.arange(n, dtype=np.uint64)
+    ctx = vs.compute.Context()
+    ix = vs.ivf.Index.build_assigned(rows, doc, lists, cent, ctx=ctx)
+    qs = np.concatenate([rows[10:10 + nq // 2], noop_rows(nq // 2, d, 8)])
+    for scale in (1.0, 1.0e7):
+        vs.compute.debug_set_certify_scale(scale)
+        try:
+            probes, sims = ix.SelectProbes(qs, 20, ctx=ctx)
+            ids, hs, counts = ix.Search(qs, 20, 10, ctx=ctx)
+        finally:
+            vs.compute.debug_set_certify_scale(1.0)
+        for i in range(nq):
+            wp, ws = oracle.select_probes(qs[i], cent, 20)
+            assert probes[i].tolist() == wp.tolist(), f"scale {scale} query {i}"
+            assert (f32_bits(sims[i]) == f32_bits(ws)).all()
+            want_ids, want_sims = oracle.search(qs[i], cent, rows, lists, doc, 20, 10)
+            assert ids[i, :counts[i]].tolist() == want_ids.tolist()
+            assert (f32_bits(hs[i, :counts[i]]) == f32_bits(want_sims)).all()
+    assert ctx.slowpath_count() > 0
+    ctx.close()
