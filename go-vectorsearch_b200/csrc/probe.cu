@@ -15,7 +15,8 @@ namespace {
 #define FULL 0xFFFFFFFFu
 constexpr int kPsWarps = 4;                          // warps per block of the score kernel
 constexpr int kPsRows = kPsWarps * 8;                // centroid rows per work item (2 half-warps x 4 rows per warp)
-constexpr int kPsQueries = 32;                       // queries staged in shared memory per work item
+constexpr int kPsQueries = 8;                        // queries staged in shared memory per work item (small items: the
+                                                     // whole stage is a few microseconds of work, spread it over every SM)
 constexpr int kSelThreadsP = 256;
 constexpr int kMaxProbe = 128;
 
@@ -37,6 +38,23 @@ probe_score_kernel(MatView cent, MatView queries, uint32_t *__restrict__ keys, s
         const uint32_t rt = item % row_tiles, qc = item / row_tiles;
         const uint32_t q0 = qc * kPsQueries;
         const int nqc = (int)min((uint32_t)kPsQueries, nq - q0);
+        // the centroid rows do not depend on the staged queries: their loads fly while the chunk is staged
+        const uint32_t row_base = rt * kPsRows + warp * 8 + hw * 4;
+        uint4 r[4][CPL];
+#pragma unroll
+        for (int i = 0; i < 4; i++) {
+            const uint32_t row = row_base + i;
+#pragma unroll
+            for (int j = 0; j < CPL; j++)
+                r[i][j] = row < C ? ld_stream_u4(cent.codes + (size_t)row * d_pad + (size_t)(l + 16 * j) * 16) : make_uint4(0, 0, 0, 0);
+        }
+        const uint32_t row_my = row_base + (l & 3);  // after the reduction lane l holds (query qg + l/4, row row_base + l%4)
+        float2 h_my = make_float2(0.f, 0.f);
+        uint2 s_my = make_uint2(0u, 0u);
+        if (row_my < C) {
+            h_my = cent.hdr[row_my];
+            s_my = cent.sums[row_my];
+        }
         __syncthreads();  // the previous item's shared reads are done
         {
             const uint4 *src = reinterpret_cast<const uint4 *>(queries.codes + (size_t)q0 * d_pad);
@@ -48,23 +66,6 @@ probe_score_kernel(MatView cent, MatView queries, uint32_t *__restrict__ keys, s
             }
         }
         __syncthreads();
-        const uint32_t row_base = rt * kPsRows + warp * 8 + hw * 4;
-        uint4 r[4][CPL];
-#pragma unroll
-        for (int i = 0; i < 4; i++) {
-            const uint32_t row = row_base + i;
-#pragma unroll
-            for (int j = 0; j < CPL; j++)
-                r[i][j] = row < C ? ld_stream_u4(cent.codes + (size_t)row * d_pad + (size_t)(l + 16 * j) * 16) : make_uint4(0, 0, 0, 0);
-        }
-        // after the reduction lane l of a half-warp holds the dot of (query qg + l/4, row row_base + l%4)
-        const uint32_t row_my = row_base + (l & 3);
-        float2 h_my = make_float2(0.f, 0.f);
-        uint2 s_my = make_uint2(0u, 0u);
-        if (row_my < C) {
-            h_my = cent.hdr[row_my];
-            s_my = cent.sums[row_my];
-        }
         for (int qg = 0; qg < nqc; qg += 4) {
             uint32_t v[16];
 #pragma unroll
@@ -113,10 +114,10 @@ probe_score_kernel(MatView cent, MatView queries, uint32_t *__restrict__ keys, s
     }
 }
 
-// One block per query: the k largest keys (ties by lowest centroid index) by an 8-bit radix select over the key row, a
+// One block per query: the k largest keys (ties by lowest centroid index) by bisection over the key row, a
 // rank sort of the k survivors, literal re-scores where an uncertified pair could be among them, emission.
-// REG: the thread's contiguous slice of the key row (<= 32 keys) lives in registers.
-template <bool REG>
+// KPT > 0: the thread's contiguous slice of the key row (<= KPT keys) lives in registers; KPT = 0: it is read from memory.
+template <int KPT>
 __global__ void __launch_bounds__(kSelThreadsP)
 probe_select_kernel(MatView cent, MatView queries, uint32_t *__restrict__ keys, size_t key_stride,
                     const unsigned int *__restrict__ flag_cnt, const uint32_t *__restrict__ flag_list, int k,
@@ -125,8 +126,7 @@ probe_select_kernel(MatView cent, MatView queries, uint32_t *__restrict__ keys, 
                     uint32_t status_bit, int status_init, unsigned long long *fix_counter) {
     extern __shared__ __align__(16) unsigned char sel_smem[];
     double *sh_qn = reinterpret_cast<double *>(sel_smem);  // [D] normalized query (literal path only)
-    __shared__ unsigned int hist[256];
-    __shared__ uint32_t s_prefix, s_remaining;
+    __shared__ unsigned int s_wcount[2][kSelThreadsP / 32];
     __shared__ uint32_t s_key[kMaxProbe], s_id[kMaxProbe], o_key[kMaxProbe], o_id[kMaxProbe];
     __shared__ unsigned int s_nsel, s_wties[kSelThreadsP / 32], s_tiles;
     __shared__ int s_need_fix;
@@ -146,69 +146,62 @@ probe_select_kernel(MatView cent, MatView queries, uint32_t *__restrict__ keys, 
     if (tid < kProbeFlagCap) s_fstate[tid] = 0;
     if (tid == 0) s_tiles = 0;
     bool normalized = false;
-    uint32_t rk[REG ? 32 : 1];
+    constexpr bool REG = KPT > 0;
+    uint32_t rk[REG ? KPT : 1];
     uint32_t T = 0;
     for (;;) {
-        if (REG) {
+        if (REG) {  // key 0 = no entry: below every valid key
 #pragma unroll
-            for (int j = 0; j < 32; j++) rk[j] = lo + j < hi ? kq[lo + j] : 0u;
+            for (int j = 0; j < (REG ? KPT : 1); j++) rk[j] = lo + j < hi ? kq[lo + j] : 0u;
         }
-        // visits the thread's keys in index order (register copies are indexed statically)
+        // visits the thread's keys in index order (register copies are indexed statically); warp-uniform trip count
         auto for_keys = [&](auto &&body) {
             if (REG) {
 #pragma unroll
-                for (int j = 0; j < 32; j++)
-                    if (lo + j < hi) body(rk[j], lo + j);
+                for (int j = 0; j < (REG ? KPT : 1); j++) body(rk[j], lo + j, lo + j < hi);
             } else {
-                for (uint32_t i = lo; i < hi; i++) body(kq[i], i);
+                for (uint32_t j = 0; j < per; j++) body(lo + j < hi ? kq[lo + j] : 0u, lo + j, lo + j < hi);
             }
         };
-        // ---- k-th largest key: four 8-bit passes from the top byte ----
-        uint32_t prefix = 0, remaining = (uint32_t)k;
-        for (int pass = 0; pass < 4; pass++) {
-            const int shift = 24 - 8 * pass;
-            hist[tid] = 0;
-            __syncthreads();
-            for_keys([&](uint32_t kk, uint32_t) {
-                if (pass == 0 || (kk >> (shift + 8)) == prefix) atomicAdd(&hist[(kk >> shift) & 255u], 1u);
-            });
-            __syncthreads();
-            if (warp == 0) {  // lane L owns bins 8L .. 8L+7; walk from the top bin down
-                unsigned int c[8], tot = 0;
+        // ---- k-th largest key: bisection over the 32-bit key domain (largest x with count(key >= x) >= k).  A radix
+        // select would be fewer passes, but similarities crowd into a handful of top-byte bins and its shared-memory
+        // atomics serialize; counting needs no atomics at all.
+        auto block_count = [&](uint32_t x, int buf) -> unsigned int {  // keys >= x in the whole row (x >= 1: padding is 0)
+            unsigned int c = 0;
+            if (REG) {
+                unsigned int c4[4] = {0u, 0u, 0u, 0u};  // independent chains
 #pragma unroll
-                for (int b = 0; b < 8; b++) {
-                    c[b] = hist[8 * lane + b];
-                    tot += c[b];
-                }
-                unsigned int above = tot;  // inclusive suffix sum over lanes, then made exclusive
-                for (int o = 1; o < 32; o <<= 1) {
-                    const unsigned int x = __shfl_down_sync(FULL, above, o);
-                    if (lane + o < 32) above += x;
-                }
-                above -= tot;
-                if (above < remaining && above + tot >= remaining) {
-                    unsigned int run = above;
-#pragma unroll
-                    for (int b = 7; b >= 0; b--) {
-                        if (run < remaining && run + c[b] >= remaining) {
-                            s_prefix = (prefix << 8) | (uint32_t)(8 * lane + b);
-                            s_remaining = remaining - run;
-                        }
-                        run += c[b];
-                    }
-                }
+                for (int j = 0; j < (REG ? KPT : 1); j++) c4[j & 3] += rk[j] >= x ? 1u : 0u;
+                c = (c4[0] + c4[1]) + (c4[2] + c4[3]);
+            } else {
+                for_keys([&](uint32_t kk, uint32_t, bool valid) { c += (valid && kk >= x) ? 1u : 0u; });
             }
+            c = __reduce_add_sync(FULL, c);
+            if (lane == 0) s_wcount[buf][warp] = c;
             __syncthreads();
-            prefix = s_prefix;
-            remaining = s_remaining;
+            unsigned int tot = 0;
+#pragma unroll
+            for (int w = 0; w < kSelThreadsP / 32; w++) tot += s_wcount[buf][w];
+            return tot;
+        };
+        uint32_t klo = 1u, khi = 0xFFFFFFFFu;  // every valid key is >= 1 and k <= C: count(key >= 1) >= k
+        int buf = 0;
+        while (klo < khi) {
+            const uint32_t mid = klo + (khi - klo) / 2 + 1;
+            if (block_count(mid, buf) >= (unsigned int)k) klo = mid;
+            else khi = mid - 1;
+            buf ^= 1;
         }
-        T = prefix;                          // the k-th largest key
-        const uint32_t need_ties = remaining;  // how many of the keys equal to T belong to the k (lowest indices first)
+        T = klo;  // the k-th largest key
+        // how many of the keys equal to T belong to the k (lowest indices first)
+        const uint32_t need_ties = (uint32_t)k - (T == 0xFFFFFFFFu ? 0u : block_count(T + 1u, buf));
+        __syncthreads();
         // ---- collect: keys above T in any order, then the first need_ties ties in index order ----
         if (tid == 0) s_nsel = 0;
         __syncthreads();
         unsigned int my_ties = 0;
-        for_keys([&](uint32_t kk, uint32_t idx) {
+        for_keys([&](uint32_t kk, uint32_t idx, bool valid) {
+            if (!valid) return;
             if (kk > T) {
                 const unsigned int pos = atomicAdd(&s_nsel, 1u);
                 s_key[pos] = kk;
@@ -228,8 +221,8 @@ probe_select_kernel(MatView cent, MatView queries, uint32_t *__restrict__ keys, 
         for (int w = 0; w < warp; w++) rank += s_wties[w];
         const unsigned int base = s_nsel;  // = k - need_ties
         if (my_ties && rank < need_ties) {
-            for_keys([&](uint32_t kk, uint32_t idx) {
-                if (kk == T && rank < need_ties) {
+            for_keys([&](uint32_t kk, uint32_t idx, bool valid) {
+                if (valid && kk == T && rank < need_ties) {
                     s_key[base + rank] = T;
                     s_id[base + rank] = idx;
                     rank++;
@@ -347,23 +340,23 @@ cudaError_t launch_probe_batch(const MatView &cent, const MatView &queries, int 
     e = cudaGetLastError();
     if (e != cudaSuccess) return e;
     const size_t smem2 = (size_t)cent.d * sizeof(double);
-    if (C <= (size_t)kSelThreadsP * 32) {
-        if (smem2 > 40 * 1024) {
-            e = cudaFuncSetAttribute(probe_select_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem2);
-            if (e != cudaSuccess) return e;
-        }
-        probe_select_kernel<true><<<(unsigned)nq, kSelThreadsP, smem2, st>>>(cent, queries, keys, C, flag_cnt, flag_list, k, out_probe,
-                                                                             out_sims, out_qtiles, next_list_off, next_tile_rows,
-                                                                             out_status, status_bit, status_init, fix_counter);
-    } else {
-        if (smem2 > 40 * 1024) {
-            e = cudaFuncSetAttribute(probe_select_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem2);
-            if (e != cudaSuccess) return e;
-        }
-        probe_select_kernel<false><<<(unsigned)nq, kSelThreadsP, smem2, st>>>(cent, queries, keys, C, flag_cnt, flag_list, k, out_probe,
-                                                                              out_sims, out_qtiles, next_list_off, next_tile_rows,
-                                                                              out_status, status_bit, status_init, fix_counter);
-    }
+    const size_t per = (C + kSelThreadsP - 1) / kSelThreadsP;
+#define VS_PROBE_SELECT(KPT)                                                                                                  \
+    do {                                                                                                                      \
+        if (smem2 > 40 * 1024) {                                                                                              \
+            e = cudaFuncSetAttribute(probe_select_kernel<KPT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem2);      \
+            if (e != cudaSuccess) return e;                                                                                   \
+        }                                                                                                                     \
+        probe_select_kernel<KPT><<<(unsigned)nq, kSelThreadsP, smem2, st>>>(cent, queries, keys, C, flag_cnt, flag_list, k,   \
+                                                                            out_probe, out_sims, out_qtiles, next_list_off,  \
+                                                                            next_tile_rows, out_status, status_bit,          \
+                                                                            status_init, fix_counter);                       \
+    } while (0)
+    if (per <= 8) VS_PROBE_SELECT(8);
+    else if (per <= 16) VS_PROBE_SELECT(16);
+    else if (per <= 32) VS_PROBE_SELECT(32);
+    else VS_PROBE_SELECT(0);
+#undef VS_PROBE_SELECT
     return cudaGetLastError();
 }
 
