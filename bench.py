@@ -3,7 +3,9 @@
 
 Workload (BASELINE.json configs[1]): IVF-Flat search on 10M synthetic 768-d uint8-quantized vectors,
 4096 centroids, nprobe=32, top-10.  A "step" is one call of the search path over a batch of `--batch`
-independent queries (distinct queries every step; the 7.7 GB store is >> the 126 MB L2).
+independent queries (default 256: what a server at ~100K queries/s has in flight in 2.5 ms; distinct queries every
+step; the 7.7 GB store is >> the 126 MB L2).  The config's single-query latency is reported beside it
+(`latency_us_batch1`).
 
   value   queries/s with the index and the queries resident in HBM (vs_search_dev + status check)
   e2e     queries/s through the host-buffer C ABI call vs_search (H2D of the query rows and D2H of the
@@ -44,7 +46,7 @@ def parse():
     ap.add_argument("--centroids", type=int, default=4096)
     ap.add_argument("--nprobe", type=int, default=32)
     ap.add_argument("--k", type=int, default=10)
-    ap.add_argument("--batch", type=int, default=int(os.environ.get("VS_BENCH_BATCH", 64)))
+    ap.add_argument("--batch", type=int, default=int(os.environ.get("VS_BENCH_BATCH", 256)))
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-extra", action="store_true", help="skip the config-3 / config-4 side measurements")
     return ap.parse_args()
@@ -343,7 +345,8 @@ def run_b200(a):
     achieved = bytes_per_launch / (scan_ms_avg * 1e-3) / 1e9 if scan_ms_avg > 0 else 0.0
     traffic = None
     try:
-        traffic = json.load(open(os.path.join(ROOT, "profiles", "scan_traffic.json"))).get("dram_bytes_per_launch")
+        tj = json.load(open(os.path.join(ROOT, "profiles", "scan_traffic.json")))
+        traffic = tj.get(f"dram_bytes_per_launch_batch{B}", tj.get("dram_bytes_per_launch") if B == 64 else None)
     except Exception:  # noqa: BLE001
         pass
     scan_gbs_step = (float(np.mean(scored)) + B * a.centroids) * ROW_BYTES / (ms_per_step * 1e-3) / 1e9
@@ -363,7 +366,11 @@ def run_b200(a):
         "roofline": {"bound": "hbm", "kernel": "stage_kernel (list scan + fused top-k)", "achieved": round(achieved, 1),
                      "peak": peak, "peak_source": peak_src, "unit": "GB/s", "frac": round(achieved / peak, 4),
                      "traffic": traffic, "bytes_per_launch": round(bytes_per_launch), "ms_per_launch": round(scan_ms_avg, 5),
-                     "launches_timed": scan_launches},
+                     "launches_timed": scan_launches,
+                     "note": "achieved = rows scored x 776 B / launch time (algorithmic bytes); traffic = ncu dram bytes of one "
+                             "launch at this batch size (= algorithmic: L2 hit rate 1 %). peak is the driver's read+write copy "
+                             "figure; a read-only stream goes higher on this part (ncu: 7.07 TB/s, 86 % of its 8.17 TB/s "
+                             "ceiling, profiles/r01_scan_b256_summary.txt), so frac can pass 1"},
         "e2e": {"value": round(e2e_qps, 1), "unit": "queries/s", "h2d_bytes_per_step": B * ROW_BYTES,
                 "d2h_bytes_per_step": B * k * 12 + B * 4 + B * 4, "results_match_device_path": e2e_match},
         "gpu_launches": int(launches),
