@@ -14,6 +14,7 @@ Inputs are never mutated (the reference normalizes in place, which is why its ca
 here Clone() is a reference-count bump on an immutable device matrix).
 """
 import ctypes as C
+import os
 
 import numpy as np
 
@@ -204,6 +205,12 @@ class Matrix:
         ctx = ctx or default_context()
         _check(self._L.vs_argmax_MxN_dev(ctx.handle, self._h, data._h, C.c_void_p(int(d_idx_ptr))))
 
+    def SaveSpool(self, path, first=0, count=None, append=False, ctx=None):
+        """Write rows as a D&C row spool (createDataset.WriteRow, dnc/dataset.go:53-56, for many rows at once)."""
+        ctx = ctx or default_context()
+        count = self.rows - first if count is None else count
+        _check(self._L.vs_matrix_save_spool(ctx.handle, self._h, int(first), int(count), os.fsencode(path), 1 if append else 0))
+
     def ReadRows(self, first=0, count=None):
         count = self.rows - first if count is None else count
         out = np.empty((count, 8 + self.cols), np.uint8)
@@ -264,6 +271,16 @@ def NewMatrix(matrixQuantized, ctx=None):
     ctx = ctx or default_context()
     h = C.c_void_p()
     _check(L.vs_matrix_create(ctx.handle, _p(rows), rows.shape[0], rows.shape[1], C.byref(h)))
+    return Matrix(h, L)
+
+
+def LoadSpool(path, d, first_row=0, count=0, ctx=None):
+    """A device matrix from rows [first_row, first_row+count) (count 0 = to the end) of a D&C row spool: a flat file of
+    8+d-byte rows (dnc/dataset.go:19-56,122-146)."""
+    L = _lib.init()
+    ctx = ctx or default_context()
+    h = C.c_void_p()
+    _check(L.vs_matrix_load_spool(ctx.handle, os.fsencode(path), 8 + int(d), int(first_row), int(count), C.byref(h)))
     return Matrix(h, L)
 
 

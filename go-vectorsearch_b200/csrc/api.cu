@@ -2,6 +2,11 @@
 // No torch types, no CPU fallback: every compute entry point needs a CUDA device.
 #include <cub/device/device_radix_sort.cuh>
 
+#include <fcntl.h>
+#include <sys/stat.h>
+#include <unistd.h>
+
+#include <cerrno>
 #include <cstdarg>
 #include <cstdio>
 #include <cstring>
@@ -510,6 +515,126 @@ extern "C" int vs_matrix_read_rows(vs_ctx *c, const vs_matrix *m, size_t first, 
     return VS_OK;
 }
 
+// ---- the D&C row spool (dnc/dataset.go:19-56,122-146): a flat file of 8+D-byte rows, no header -----------------
+// Loader: the file is read with pread into two pinned staging halves; while one half is on its way to the device
+// (H2D + ingest kernel on the ctx stream) the next chunk is read into the other.  Replaces the per-row
+// `make([]uint8) + io.ReadFull` of dataset.ReadRow and the [][]uint8 -> NewMatrix re-pack of chunkData (k_means.go:214-221).
+constexpr size_t kSpoolChunkBytes = size_t(64) << 20;
+
+extern "C" int vs_matrix_load_spool(vs_ctx *c, const char *path, size_t row_bytes, size_t first_row, size_t count,
+                                    vs_matrix **out) {
+    VS(need_dev());
+    if (!c || !path || !out) return fail(VS_EINVAL, "null argument");
+    if (row_bytes <= 8) return fail(VS_EEMPTY, "matrix columns are empty");  // compute.go:29-31
+    const int fd = open(path, O_RDONLY);
+    if (fd < 0) return fail(VS_EINVAL, "open %s: %s", path, strerror(errno));
+    struct stat st;
+    if (fstat(fd, &st) != 0) {
+        close(fd);
+        return fail(VS_EINVAL, "stat %s: %s", path, strerror(errno));
+    }
+    const size_t fsize = (size_t)st.st_size;
+    if (fsize % row_bytes != 0) {  // dataset.ReadRow: io.ReadFull fails on a short row (dataset.go:131-136)
+        close(fd);
+        return fail(VS_EINVAL, "%s: %zu bytes is not a whole number of %zu-byte rows", path, fsize, row_bytes);
+    }
+    const size_t total = fsize / row_bytes;
+    if (first_row > total) first_row = total;
+    const size_t n = (count == 0 || first_row + count > total) ? total - first_row : count;
+    if (n == 0) {
+        close(fd);
+        return fail(VS_EEMPTY, "matrix rows are empty");  // compute.go:25-27
+    }
+    vs_matrix *m = nullptr;
+    int rc = matrix_alloc(n, row_bytes - 8, &m);
+    size_t chunk = kSpoolChunkBytes / row_bytes;
+    if (chunk < 1) chunk = 1;
+    if (chunk > n) chunk = n;
+    Arena a(c);
+    if (rc == VS_OK) rc = a.reserve(2 * Arena::pad(chunk * row_bytes) + 1024);
+    if (rc == VS_OK) rc = pinned_reserve(c, 2 * chunk * row_bytes);
+    for (int i = 4; i < 6 && rc == VS_OK; i++)
+        if (!c->phase_ev[i] && cudaEventCreateWithFlags(&c->phase_ev[i], cudaEventDisableTiming) != cudaSuccess)
+            rc = fail(VS_ECUDA, "event create");
+    if (rc != VS_OK) {
+        close(fd);
+        if (m) vs_matrix_release(m);
+        return rc;
+    }
+    uint8_t *d_stage[2] = {a.take<uint8_t>(chunk * row_bytes), a.take<uint8_t>(chunk * row_bytes)};
+    uint8_t *h_stage[2] = {static_cast<uint8_t *>(c->pinned), static_cast<uint8_t *>(c->pinned) + chunk * row_bytes};
+    bool used[2] = {false, false};
+    int b = 0;
+    for (size_t r0 = 0; r0 < n && rc == VS_OK; r0 += chunk, b ^= 1) {
+        const size_t cnt = n - r0 < chunk ? n - r0 : chunk;
+        if (used[b] && cudaEventSynchronize(c->phase_ev[4 + b]) != cudaSuccess) rc = fail(VS_ECUDA, "spool: event sync");
+        size_t got = 0;
+        const size_t want = cnt * row_bytes;
+        const off_t base = (off_t)((first_row + r0) * row_bytes);
+        while (got < want && rc == VS_OK) {
+            const ssize_t r = pread(fd, h_stage[b] + got, want - got, base + (off_t)got);
+            if (r < 0 && errno == EINTR) continue;
+            if (r <= 0) rc = fail(VS_EINVAL, "read %s: %s", path, r < 0 ? strerror(errno) : "unexpected end of file");
+            else got += (size_t)r;
+        }
+        if (rc != VS_OK) break;
+        cudaError_t e = cudaMemcpyAsync(d_stage[b], h_stage[b], want, cudaMemcpyHostToDevice, c->stream);
+        if (e == cudaSuccess)
+            e = launch_ingest(d_stage[b], cnt, (int)row_bytes, m->codes + r0 * (size_t)m->d_pad, m->d_pad, m->hdr + r0, m->sums + r0,
+                              c->stream);
+        if (e == cudaSuccess) e = cudaEventRecord(c->phase_ev[4 + b], c->stream);
+        if (e != cudaSuccess) rc = fail(VS_ECUDA, "spool upload: %s", cudaGetErrorString(e));
+        used[b] = true;
+        c->launches++;
+    }
+    close(fd);
+    if (cudaStreamSynchronize(c->stream) != cudaSuccess && rc == VS_OK) rc = fail(VS_ECUDA, "spool upload: stream sync");
+    if (rc != VS_OK) {
+        vs_matrix_release(m);
+        return rc;
+    }
+    *out = m;
+    return VS_OK;
+}
+
+// Writer: rows [first, first+count) of a device matrix as 8+D-byte rows, appended to (or replacing) a spool file --
+// createDataset.WriteRow (dataset.go:53-56) for a whole child cluster at once.
+extern "C" int vs_matrix_save_spool(vs_ctx *c, const vs_matrix *m, size_t first, size_t count, const char *path, int append) {
+    VS(need_dev());
+    if (!c || !m || !path) return fail(VS_EINVAL, "null argument");
+    if (first + count > m->n) return fail(VS_EINVAL, "row range out of bounds");
+    const size_t rb = 8 + (size_t)m->d;
+    const int fd = open(path, O_WRONLY | O_CREAT | (append ? O_APPEND : O_TRUNC), 0644);
+    if (fd < 0) return fail(VS_EINVAL, "open %s: %s", path, strerror(errno));
+    size_t chunk = kSpoolChunkBytes / rb;
+    if (chunk < 1) chunk = 1;
+    if (chunk > count) chunk = count ? count : 1;
+    Arena a(c);
+    int rc = a.reserve(Arena::pad(chunk * rb) + 1024);
+    if (rc == VS_OK) rc = pinned_reserve(c, chunk * rb);
+    uint8_t *d_buf = rc == VS_OK ? a.take<uint8_t>(chunk * rb) : nullptr;
+    for (size_t r0 = 0; r0 < count && rc == VS_OK; r0 += chunk) {
+        const size_t cnt = count - r0 < chunk ? count - r0 : chunk;
+        cudaError_t e = launch_export(m->view(), first + r0, cnt, d_buf, c->stream);
+        if (e == cudaSuccess) e = cudaMemcpyAsync(c->pinned, d_buf, cnt * rb, cudaMemcpyDeviceToHost, c->stream);
+        if (e == cudaSuccess) e = cudaStreamSynchronize(c->stream);
+        if (e != cudaSuccess) {
+            rc = fail(VS_ECUDA, "spool download: %s", cudaGetErrorString(e));
+            break;
+        }
+        c->launches++;
+        size_t put = 0;
+        while (put < cnt * rb && rc == VS_OK) {
+            const ssize_t w = write(fd, static_cast<uint8_t *>(c->pinned) + put, cnt * rb - put);
+            if (w < 0 && errno == EINTR) continue;
+            if (w <= 0) rc = fail(VS_EINVAL, "write %s: %s", path, strerror(errno));
+            else put += (size_t)w;
+        }
+    }
+    if (close(fd) != 0 && rc == VS_OK) rc = fail(VS_EINVAL, "close %s: %s", path, strerror(errno));
+    return rc;
+}
+
 // A temporary (arena-resident) matrix built from host rows: queries, centroids.
 static int temp_matrix(vs_ctx *c, Arena &a, const uint8_t *rows, size_t n, size_t row_bytes, MatView *out) {
     const size_t d = row_bytes - 8, d_pad = (d + 15) & ~size_t(15);
@@ -899,7 +1024,7 @@ static bool use_probe_batch(const vs_index *ix, size_t nq, size_t npe, bool flat
     return !flat && nq >= kProbeBatchMin && ix->centroids && probe_batch_supported(ix->centroids->view(), nq, npe);
 }
 static size_t probe_batch_bytes(size_t nq, size_t C) {
-    return Arena::pad(nq * C * 4) + Arena::pad(nq * 4) + Arena::pad(nq * (size_t)kProbeFlagCap * 4);
+    return Arena::pad(nq * C * 4) + Arena::pad(nq * 4) + Arena::pad(nq * (size_t)probe_flag_cap(C) * 4);
 }
 
 static size_t search_bytes(size_t nq, size_t npe, int kpl1, int kpl2, int grid, size_t d) {
@@ -923,7 +1048,7 @@ static int search_enqueue(vs_ctx *c, const vs_index *ix, const MatView &qv, size
     const uint32_t tr1 = exact ? 32 : b.tile_rows1, tr2 = exact ? 32 : b.tile_rows2;
     if (!flat && !exact && !d_select && b.probe_keys && nq_launch == qv.n) {
         // a batch: score every (query, centroid) pair with the table read once, then select per query (probe.cu)
-        LAUNCH(c, launch_probe_batch(ix->centroids->view(), qv, (int)npe, b.probe_keys, b.flag_cnt, b.flag_list, b.probe,
+        LAUNCH(c, launch_probe_batch(ix->centroids->view(), qv, (int)npe, b.probe_keys, b.flag_cnt, b.flag_list, probe_flag_cap(ix->C), b.probe,
                                      d_probe_sims, b.qtiles, ix->list_off, tr2, d_status, kStatusProbeAmbiguous, 1, c->d_fix_counter,
                                      g_sm_count, c->stream));
         c->launches++;
@@ -1030,7 +1155,7 @@ static void search_take(Arena &a, const vs_index *ix, size_t nq, SearchSetup *s)
     if (use_probe_batch(ix, nq, s->npe, s->flat)) {
         s->b.probe_keys = a.take<uint32_t>(nq * ix->C);
         s->b.flag_cnt = a.take<unsigned int>(nq);
-        s->b.flag_list = a.take<uint32_t>(nq * (size_t)kProbeFlagCap);
+        s->b.flag_list = a.take<uint32_t>(nq * (size_t)probe_flag_cap(ix->C));
     }
 }
 

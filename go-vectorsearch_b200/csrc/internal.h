@@ -154,10 +154,14 @@ cudaError_t gemm_enqueue_select(const MatView &rows, const uint64_t *ids, uint64
                                 unsigned long long *fix_counter, int sm_count, cudaStream_t st, uint64_t *launches);
 
 // probe.cu: probe selection for a batch of queries (the centroid table is read once, not once per query)
-constexpr int kProbeFlagCap = 64;   // uncertified (query, centroid) pairs listed per query
+constexpr int kProbeFlagCapMax = 4096;  // uncertified (query, centroid) pairs listed per query: about 1 in 10^3 pairs is
+inline uint32_t probe_flag_cap(size_t C) {  // uncertified (more where |cos| is small), only those near the top matter
+    const size_t c = C / 16;
+    return (uint32_t)(c < 64 ? 64 : (c > (size_t)kProbeFlagCapMax ? (size_t)kProbeFlagCapMax : c));
+}
 bool probe_batch_supported(const MatView &cent, size_t nq, size_t k);
 cudaError_t launch_probe_batch(const MatView &cent, const MatView &queries, int k, uint32_t *keys, unsigned int *flag_cnt,
-                               uint32_t *flag_list, uint32_t *out_probe, float *out_sims, uint32_t *out_qtiles,
+                               uint32_t *flag_list, uint32_t flag_cap, uint32_t *out_probe, float *out_sims, uint32_t *out_qtiles,
                                const uint64_t *next_list_off, uint32_t next_tile_rows, uint32_t *out_status, uint32_t status_bit,
                                int status_init, unsigned long long *fix_counter, int sm_count, cudaStream_t st);
 cudaError_t probe_set_certify_scale(float scale);

@@ -24,7 +24,7 @@ constexpr int kMaxProbe = 128;
 template <int CPL>
 __global__ void __launch_bounds__(kPsWarps * 32)
 probe_score_kernel(MatView cent, MatView queries, uint32_t *__restrict__ keys, size_t key_stride,
-                   unsigned int *__restrict__ flag_cnt, uint32_t *__restrict__ flag_list) {
+                   unsigned int *__restrict__ flag_cnt, uint32_t *__restrict__ flag_list, uint32_t flag_cap) {
     extern __shared__ __align__(16) unsigned char ps_smem[];
     constexpr int CH = 16 * CPL;  // 16-byte chunks per row
     uint4 *sh_q = reinterpret_cast<uint4 *>(ps_smem);                                       // [kPsQueries][CH]
@@ -107,7 +107,7 @@ probe_score_kernel(MatView cent, MatView queries, uint32_t *__restrict__ keys, s
                 keys[(size_t)(q0 + q) * key_stride + row_my] = f32_to_key(sim);
                 if (flag) {
                     const unsigned int pos = atomicAdd(flag_cnt + q0 + q, 1u);
-                    if (pos < (unsigned int)kProbeFlagCap) flag_list[(size_t)(q0 + q) * kProbeFlagCap + pos] = row_my;
+                    if (pos < flag_cap) flag_list[(size_t)(q0 + q) * flag_cap + pos] = row_my;
                 }
             }
         }
@@ -120,7 +120,7 @@ probe_score_kernel(MatView cent, MatView queries, uint32_t *__restrict__ keys, s
 template <int KPT>
 __global__ void __launch_bounds__(kSelThreadsP)
 probe_select_kernel(MatView cent, MatView queries, uint32_t *__restrict__ keys, size_t key_stride,
-                    const unsigned int *__restrict__ flag_cnt, const uint32_t *__restrict__ flag_list, int k,
+                    const unsigned int *__restrict__ flag_cnt, const uint32_t *__restrict__ flag_list, uint32_t flag_cap, int k,
                     uint32_t *__restrict__ out_probe, float *__restrict__ out_sims, uint32_t *__restrict__ out_qtiles,
                     const uint64_t *__restrict__ next_list_off, uint32_t next_tile_rows, uint32_t *__restrict__ out_status,
                     uint32_t status_bit, int status_init, unsigned long long *fix_counter) {
@@ -131,7 +131,7 @@ probe_select_kernel(MatView cent, MatView queries, uint32_t *__restrict__ keys, 
     __shared__ unsigned int s_nsel, s_wties[kSelThreadsP / 32], s_tiles;
     __shared__ int s_need_fix;
     __shared__ double s_norm;
-    __shared__ unsigned char s_fstate[kProbeFlagCap];  // 0 = uncertified, 1 = re-scored, 2 = to re-score now
+    __shared__ unsigned char s_fstate[kProbeFlagCapMax];  // 0 = uncertified, 1 = re-scored, 2 = to re-score now
 
     const uint32_t q = blockIdx.x;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -141,9 +141,9 @@ probe_select_kernel(MatView cent, MatView queries, uint32_t *__restrict__ keys, 
     const uint32_t lo = min(C, (uint32_t)tid * per), hi = min(C, lo + per);
     uint32_t *kq = keys + (size_t)q * key_stride;
     const unsigned int nflag_all = flag_cnt[q];
-    const int nflag = (int)min(nflag_all, (unsigned int)kProbeFlagCap);
-    uint32_t status = nflag_all > (unsigned int)kProbeFlagCap ? status_bit : 0u;  // unlisted uncertified pairs: the caller's literal path
-    if (tid < kProbeFlagCap) s_fstate[tid] = 0;
+    const int nflag = (int)min(nflag_all, flag_cap);
+    uint32_t status = nflag_all > flag_cap ? status_bit : 0u;  // unlisted uncertified pairs: the caller's literal path
+    for (int f = tid; f < nflag; f += kSelThreadsP) s_fstate[f] = 0;
     if (tid == 0) s_tiles = 0;
     bool normalized = false;
     constexpr bool REG = KPT > 0;
@@ -232,10 +232,9 @@ probe_select_kernel(MatView cent, MatView queries, uint32_t *__restrict__ keys, 
         if (tid == 0) s_need_fix = 0;
         __syncthreads();
         // ---- an uncertified pair matters iff its stored (upper) key reaches T: below T its true key is below T too ----
-        if (tid < nflag && s_fstate[tid] == 0) {
-            const uint32_t c = flag_list[(size_t)q * kProbeFlagCap + tid];
-            if (kq[c] >= T) {
-                s_fstate[tid] = 2;
+        for (int f = tid; f < nflag; f += kSelThreadsP) {
+            if (s_fstate[f] == 0 && kq[flag_list[(size_t)q * flag_cap + f]] >= T) {
+                s_fstate[f] = 2;
                 s_need_fix = 1;
             }
         }
@@ -260,7 +259,7 @@ probe_select_kernel(MatView cent, MatView queries, uint32_t *__restrict__ keys, 
         }
         for (int f = warp; f < nflag; f += kSelThreadsP / 32) {
             if (s_fstate[f] == 2) {
-                const uint32_t c = flag_list[(size_t)q * kProbeFlagCap + f];
+                const uint32_t c = flag_list[(size_t)q * flag_cap + f];
                 const float2 h = cent.hdr[c];
                 const double dot = warp_ref_cosine_row_f64(cent.codes + (size_t)c * d_pad, h.x, h.y, sh_qn, D, lane);
                 if (lane == 0) {
@@ -311,7 +310,7 @@ bool probe_batch_supported(const MatView &cent, size_t nq, size_t k) {
 }
 
 cudaError_t launch_probe_batch(const MatView &cent, const MatView &queries, int k, uint32_t *keys, unsigned int *flag_cnt,
-                               uint32_t *flag_list, uint32_t *out_probe, float *out_sims, uint32_t *out_qtiles,
+                               uint32_t *flag_list, uint32_t flag_cap, uint32_t *out_probe, float *out_sims, uint32_t *out_qtiles,
                                const uint64_t *next_list_off, uint32_t next_tile_rows, uint32_t *out_status, uint32_t status_bit,
                                int status_init, unsigned long long *fix_counter, int sm_count, cudaStream_t st) {
     const size_t nq = queries.n, C = cent.n;
@@ -326,7 +325,7 @@ cudaError_t launch_probe_batch(const MatView &cent, const MatView &queries, int 
             e = cudaFuncSetAttribute(probe_score_kernel<CPL>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);       \
             if (e != cudaSuccess) return e;                                                                                   \
         }                                                                                                                     \
-        probe_score_kernel<CPL><<<grid, kPsWarps * 32, smem, st>>>(cent, queries, keys, C, flag_cnt, flag_list);             \
+        probe_score_kernel<CPL><<<grid, kPsWarps * 32, smem, st>>>(cent, queries, keys, C, flag_cnt, flag_list, flag_cap);            \
     } while (0)
     switch (cent.d_pad / 256) {
         case 1: VS_PROBE_SCORE(1); break;
@@ -347,7 +346,7 @@ cudaError_t launch_probe_batch(const MatView &cent, const MatView &queries, int 
             e = cudaFuncSetAttribute(probe_select_kernel<KPT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem2);      \
             if (e != cudaSuccess) return e;                                                                                   \
         }                                                                                                                     \
-        probe_select_kernel<KPT><<<(unsigned)nq, kSelThreadsP, smem2, st>>>(cent, queries, keys, C, flag_cnt, flag_list, k,   \
+        probe_select_kernel<KPT><<<(unsigned)nq, kSelThreadsP, smem2, st>>>(cent, queries, keys, C, flag_cnt, flag_list, flag_cap, k, \
                                                                             out_probe, out_sims, out_qtiles, next_list_off,  \
                                                                             next_tile_rows, out_status, status_bit,          \
                                                                             status_init, fix_counter);                       \

@@ -116,6 +116,13 @@ VS_API size_t vs_matrix_rows(const vs_matrix *m);
 VS_API size_t vs_matrix_cols(const vs_matrix *m);
 /* Read rows back in row776 format (host out: count*(8+D) bytes). */
 VS_API int vs_matrix_read_rows(vs_ctx *ctx, const vs_matrix *m, size_t first, size_t count, uint8_t *out);
+/* The D&C row spool of the reference (dnc/dataset.go:19-56,122-146): a flat file of 8+D-byte rows, no header.
+ * vs_matrix_load_spool builds a device matrix from rows [first_row, first_row+count) of the file (count 0 = to the end)
+ * with double-buffered pinned reads overlapping the upload; a file that is not a whole number of rows is an error
+ * (dataset.go:131-136).  vs_matrix_save_spool writes rows of a device matrix in the same format (append != 0: at the
+ * end of an existing file, like createDataset.WriteRow). */
+VS_API int vs_matrix_load_spool(vs_ctx *ctx, const char *path, size_t row_bytes, size_t first_row, size_t count, vs_matrix **out);
+VS_API int vs_matrix_save_spool(vs_ctx *ctx, const vs_matrix *m, size_t first, size_t count, const char *path, int append);
 
 /* ---- compute/cosine.go ------------------------------------------------------------- */
 /* (*vectorContainer).MatrixCosineSimilarity (cosine.go:13-57): sims_out[i] = float32 cosine of the

@@ -178,3 +178,32 @@ def test_closures_concurrent(vs, oracle):
     [t.start() for t in ts]
     [t.join() for t in ts]
     assert not errs, errs
+
+
+def test_row_spool_load_and_save(vs, oracle, tmp_path):
+    """dnc/dataset.go's cache file: a flat file of 8+D-byte rows.  Load (whole file, ranges), save, append."""
+    d, n = 768, 200_000                     # 155 MB: several 64 MB staging chunks
+    rows = noop_rows(n, d, 9)
+    rows[:, 0:8] = np.random.default_rng(1).integers(0, 256, (n, 8), dtype=np.uint8)   # arbitrary header bytes survive
+    path = tmp_path / "1234.cache"
+    rows.tofile(path)
+    m = vs.compute.LoadSpool(path, d)
+    assert m.rows == n and m.cols == d
+    assert (m.ReadRows() == rows).all()
+    part = vs.compute.LoadSpool(path, d, first_row=1000, count=5000)
+    assert (part.ReadRows() == rows[1000:6000]).all()
+    tail = vs.compute.LoadSpool(path, d, first_row=n - 10)
+    assert (tail.ReadRows() == rows[n - 10:]).all()
+    # the loaded matrix scores like one built from the rows
+    q = vs.compute.NewVector(rows[7])
+    assert (f32_bits(q.MatrixCosineSimilarity(part)) == f32_bits(oracle.cosine_1xN(rows[7], rows[1000:6000]))).all()
+    out = tmp_path / "child.cache"
+    m.SaveSpool(out, first=0, count=90_000)
+    m.SaveSpool(out, first=90_000, append=True)
+    assert (np.fromfile(out, np.uint8).reshape(n, 8 + d) == rows).all()
+    with open(path, "ab") as f:
+        f.write(b"\x00" * 5)                # a torn last row: dataset.ReadRow's io.ReadFull would fail
+    with pytest.raises(vs.compute.ComputeError):
+        vs.compute.LoadSpool(path, d)
+    with pytest.raises(vs.compute.ComputePanic):
+        vs.compute.LoadSpool(out, d, first_row=n)   # no rows: compute.go:25-27
