@@ -987,7 +987,8 @@ struct SearchBufs {
     uint32_t *q_select;     // exact only
     uint32_t *probe_keys;   // batched probe selection (probe.cu): [nq][C] similarity keys, or null
     unsigned int *flag_cnt; // [nq]
-    uint32_t *flag_list;    // [nq][kProbeFlagCap]
+    uint32_t *flag_list;    // [nq][probe_flag_cap(C)]
+    uint32_t *cand_keys, *cand_ids;  // [nq][segments][npe] segment survivors (many centroids only)
     int grid;               // blocks per stage launch
     int iters1, iters2;     // rows per lane group (tile height) of each stage
     int tile_rows1, tile_rows2;
@@ -1023,8 +1024,9 @@ constexpr size_t kProbeBatchMin = 8;  // from this many queries on the probe sta
 static bool use_probe_batch(const vs_index *ix, size_t nq, size_t npe, bool flat) {
     return !flat && nq >= kProbeBatchMin && ix->centroids && probe_batch_supported(ix->centroids->view(), nq, npe);
 }
-static size_t probe_batch_bytes(size_t nq, size_t C) {
-    return Arena::pad(nq * C * 4) + Arena::pad(nq * 4) + Arena::pad(nq * (size_t)probe_flag_cap(C) * 4);
+static size_t probe_batch_bytes(size_t nq, size_t C, size_t npe) {
+    return Arena::pad(nq * C * 4) + Arena::pad(nq * 4) + Arena::pad(nq * (size_t)probe_flag_cap(C) * 4) +
+           2 * Arena::pad(nq * probe_segments(C) * npe * 4);
 }
 
 static size_t search_bytes(size_t nq, size_t npe, int kpl1, int kpl2, int grid, size_t d) {
@@ -1048,7 +1050,7 @@ static int search_enqueue(vs_ctx *c, const vs_index *ix, const MatView &qv, size
     const uint32_t tr1 = exact ? 32 : b.tile_rows1, tr2 = exact ? 32 : b.tile_rows2;
     if (!flat && !exact && !d_select && b.probe_keys && nq_launch == qv.n) {
         // a batch: score every (query, centroid) pair with the table read once, then select per query (probe.cu)
-        LAUNCH(c, launch_probe_batch(ix->centroids->view(), qv, (int)npe, b.probe_keys, b.flag_cnt, b.flag_list, probe_flag_cap(ix->C), b.probe,
+        LAUNCH(c, launch_probe_batch(ix->centroids->view(), qv, (int)npe, b.probe_keys, b.flag_cnt, b.flag_list, probe_flag_cap(ix->C), b.cand_keys, b.cand_ids, b.probe,
                                      d_probe_sims, b.qtiles, ix->list_off, tr2, d_status, kStatusProbeAmbiguous, 1, c->d_fix_counter,
                                      g_sm_count, c->stream));
         c->launches++;
@@ -1139,7 +1141,7 @@ static int search_setup(vs_ctx *c, Arena &a, const vs_index *ix, size_t nq, size
     if (!s->kpl1) return fail(VS_ERANGE, "nprobe=%zu: at most 128 probed lists unless nprobe >= number of lists", nprobe);
     VS(search_plan(ix, nq, s->npe, s->flat, &s->b));
     VS(a.reserve(a.off + extra_bytes + search_bytes(nq, s->npe, s->kpl1, s->kpl2, s->b.grid, ix->data->d) +
-                 (use_probe_batch(ix, nq, s->npe, s->flat) ? probe_batch_bytes(nq, ix->C) : 0)));
+                 (use_probe_batch(ix, nq, s->npe, s->flat) ? probe_batch_bytes(nq, ix->C, s->npe) : 0)));
     return VS_OK;
 }
 
@@ -1156,6 +1158,8 @@ static void search_take(Arena &a, const vs_index *ix, size_t nq, SearchSetup *s)
         s->b.probe_keys = a.take<uint32_t>(nq * ix->C);
         s->b.flag_cnt = a.take<unsigned int>(nq);
         s->b.flag_list = a.take<uint32_t>(nq * (size_t)probe_flag_cap(ix->C));
+        s->b.cand_keys = a.take<uint32_t>(nq * probe_segments(ix->C) * s->npe);
+        s->b.cand_ids = a.take<uint32_t>(nq * probe_segments(ix->C) * s->npe);
     }
 }
 

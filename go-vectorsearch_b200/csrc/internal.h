@@ -160,8 +160,10 @@ inline uint32_t probe_flag_cap(size_t C) {  // uncertified (more where |cos| is 
     return (uint32_t)(c < 64 ? 64 : (c > (size_t)kProbeFlagCapMax ? (size_t)kProbeFlagCapMax : c));
 }
 bool probe_batch_supported(const MatView &cent, size_t nq, size_t k);
+uint32_t probe_segments(size_t C);  // the select stage cuts a key row into this many segments (1: no final pass)
 cudaError_t launch_probe_batch(const MatView &cent, const MatView &queries, int k, uint32_t *keys, unsigned int *flag_cnt,
-                               uint32_t *flag_list, uint32_t flag_cap, uint32_t *out_probe, float *out_sims, uint32_t *out_qtiles,
+                               uint32_t *flag_list, uint32_t flag_cap, uint32_t *cand_keys, uint32_t *cand_ids, uint32_t *out_probe,
+                               float *out_sims, uint32_t *out_qtiles,
                                const uint64_t *next_list_off, uint32_t next_tile_rows, uint32_t *out_status, uint32_t status_bit,
                                int status_init, unsigned long long *fix_counter, int sm_count, cudaStream_t st);
 cudaError_t probe_set_certify_scale(float scale);

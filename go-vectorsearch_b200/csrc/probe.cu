@@ -123,7 +123,8 @@ probe_select_kernel(MatView cent, MatView queries, uint32_t *__restrict__ keys, 
                     const unsigned int *__restrict__ flag_cnt, const uint32_t *__restrict__ flag_list, uint32_t flag_cap, int k,
                     uint32_t *__restrict__ out_probe, float *__restrict__ out_sims, uint32_t *__restrict__ out_qtiles,
                     const uint64_t *__restrict__ next_list_off, uint32_t next_tile_rows, uint32_t *__restrict__ out_status,
-                    uint32_t status_bit, int status_init, unsigned long long *fix_counter) {
+                    uint32_t status_bit, int status_init, unsigned long long *fix_counter, uint32_t nseg, uint32_t seg_len,
+                    uint32_t *__restrict__ cand_keys, uint32_t *__restrict__ cand_ids) {
     extern __shared__ __align__(16) unsigned char sel_smem[];
     double *sh_qn = reinterpret_cast<double *>(sel_smem);  // [D] normalized query (literal path only)
     __shared__ unsigned int s_wcount[2][kSelThreadsP / 32];
@@ -133,12 +134,17 @@ probe_select_kernel(MatView cent, MatView queries, uint32_t *__restrict__ keys, 
     __shared__ double s_norm;
     __shared__ unsigned char s_fstate[kProbeFlagCapMax];  // 0 = uncertified, 1 = re-scored, 2 = to re-score now
 
-    const uint32_t q = blockIdx.x;
+    // nseg > 1: the key row is cut into segments of seg_len keys, one block each; a block leaves its segment's k best
+    // (exact after its own literal re-scores) in cand_keys / cand_ids and probe_final_kernel selects among them.
+    const uint32_t q = blockIdx.x / nseg, seg = blockIdx.x % nseg;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const uint32_t C = (uint32_t)cent.n;
     const int D = cent.d, d_pad = cent.d_pad;
-    const uint32_t per = (C + kSelThreadsP - 1) / kSelThreadsP;
-    const uint32_t lo = min(C, (uint32_t)tid * per), hi = min(C, lo + per);
+    const uint32_t seg_lo = min(C, seg * seg_len), seg_hi = min(C, seg_lo + seg_len);
+    const uint32_t per = (seg_hi - seg_lo + kSelThreadsP - 1) / kSelThreadsP;
+    const uint32_t lo = min(seg_hi, seg_lo + (uint32_t)tid * per), hi = min(seg_hi, lo + per);
+    const int k_full = k;
+    k = (int)min((uint32_t)k, seg_hi - seg_lo);  // a short segment keeps everything it has
     uint32_t *kq = keys + (size_t)q * key_stride;
     const unsigned int nflag_all = flag_cnt[q];
     const int nflag = (int)min(nflag_all, flag_cap);
@@ -188,7 +194,7 @@ probe_select_kernel(MatView cent, MatView queries, uint32_t *__restrict__ keys, 
         int buf = 0;
         while (klo < khi) {
             const uint32_t mid = klo + (khi - klo) / 2 + 1;
-            if (block_count(mid, buf) >= (unsigned int)k) klo = mid;
+            if (k > 0 && block_count(mid, buf) >= (unsigned int)k) klo = mid;
             else khi = mid - 1;
             buf ^= 1;
         }
@@ -233,7 +239,8 @@ probe_select_kernel(MatView cent, MatView queries, uint32_t *__restrict__ keys, 
         __syncthreads();
         // ---- an uncertified pair matters iff its stored (upper) key reaches T: below T its true key is below T too ----
         for (int f = tid; f < nflag; f += kSelThreadsP) {
-            if (s_fstate[f] == 0 && kq[flag_list[(size_t)q * flag_cap + f]] >= T) {
+            const uint32_t c = flag_list[(size_t)q * flag_cap + f];
+            if (s_fstate[f] == 0 && c >= seg_lo && c < seg_hi && kq[c] >= T) {
                 s_fstate[f] = 2;
                 s_need_fix = 1;
             }
@@ -280,6 +287,13 @@ probe_select_kernel(MatView cent, MatView queries, uint32_t *__restrict__ keys, 
         o_id[rnk] = mi;
     }
     __syncthreads();
+    if (nseg > 1) {  // hand the segment's survivors to the final selection (key 0 = no entry)
+        for (int r = tid; r < k_full; r += kSelThreadsP) {
+            cand_keys[((size_t)q * nseg + seg) * k_full + r] = r < k ? o_key[r] : 0u;
+            cand_ids[((size_t)q * nseg + seg) * k_full + r] = r < k ? o_id[r] : 0u;
+        }
+        return;
+    }
     uint32_t mytiles = 0;
     if (tid < k) {
         const uint32_t L = o_id[tid];
@@ -299,18 +313,110 @@ probe_select_kernel(MatView cent, MatView queries, uint32_t *__restrict__ keys, 
     if (tid == 0 && out_status) out_status[q] = status_init ? status : (out_status[q] | status);
 }
 
+// Final selection among the nseg x k segment survivors of one query (all exact): the k best by (similarity desc,
+// centroid index asc), found by bisection over the 64-bit composite (key, ~index), which is unique per entry.
+__global__ void __launch_bounds__(kSelThreadsP)
+probe_final_kernel(const uint32_t *__restrict__ cand_keys, const uint32_t *__restrict__ cand_ids, uint32_t ncand, uint32_t C,
+                   const unsigned int *__restrict__ flag_cnt, uint32_t flag_cap, int k, uint32_t *__restrict__ out_probe,
+                   float *__restrict__ out_sims, uint32_t *__restrict__ out_qtiles, const uint64_t *__restrict__ next_list_off,
+                   uint32_t next_tile_rows, uint32_t *__restrict__ out_status, uint32_t status_bit, int status_init) {
+    __shared__ unsigned int s_wcount[2][kSelThreadsP / 32];
+    __shared__ uint32_t s_key[kMaxProbe], s_id[kMaxProbe], o_key[kMaxProbe], o_id[kMaxProbe];
+    __shared__ unsigned int s_nsel, s_tiles;
+    const uint32_t q = blockIdx.x;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    constexpr int PER = 16;  // ncand <= 32 segments x 128
+    unsigned long long comp[PER];
+#pragma unroll
+    for (int j = 0; j < PER; j++) {
+        const uint32_t i = (uint32_t)j * kSelThreadsP + tid;
+        comp[j] = 0ull;
+        if (i < ncand) {
+            const uint32_t kk = cand_keys[(size_t)q * ncand + i];
+            if (kk != 0) comp[j] = ((unsigned long long)kk << 32) | (unsigned long long)(0xFFFFFFFFu - cand_ids[(size_t)q * ncand + i]);
+        }
+    }
+    if (tid == 0) {
+        s_nsel = 0;
+        s_tiles = 0;
+    }
+    k = (int)min((uint32_t)k, C);
+    unsigned long long lo = 1ull, hi = ~0ull;  // largest x with count(comp >= x) >= k
+    int buf = 0;
+    while (lo < hi) {
+        const unsigned long long mid = lo + (hi - lo) / 2 + 1;
+        unsigned int c = 0;
+#pragma unroll
+        for (int j = 0; j < PER; j++) c += comp[j] >= mid ? 1u : 0u;
+        c = __reduce_add_sync(FULL, c);
+        if (lane == 0) s_wcount[buf][warp] = c;
+        __syncthreads();
+        unsigned int tot = 0;
+#pragma unroll
+        for (int w = 0; w < kSelThreadsP / 32; w++) tot += s_wcount[buf][w];
+        if (tot >= (unsigned int)k) lo = mid;
+        else hi = mid - 1;
+        buf ^= 1;
+    }
+#pragma unroll
+    for (int j = 0; j < PER; j++) {
+        if (comp[j] >= lo && comp[j] != 0ull) {
+            const unsigned int pos = atomicAdd(&s_nsel, 1u);
+            if (pos < (unsigned int)kMaxProbe) {
+                s_key[pos] = (uint32_t)(comp[j] >> 32);
+                s_id[pos] = 0xFFFFFFFFu - (uint32_t)comp[j];
+            }
+        }
+    }
+    __syncthreads();
+    if (tid < k) {
+        const uint32_t mk = s_key[tid], mi = s_id[tid];
+        int rnk = 0;
+        for (int j = 0; j < k; j++) rnk += cand_better(s_key[j], (uint64_t)s_id[j], mk, (uint64_t)mi) ? 1 : 0;
+        o_key[rnk] = mk;
+        o_id[rnk] = mi;
+    }
+    __syncthreads();
+    uint32_t mytiles = 0;
+    if (tid < k) {
+        const uint32_t L = o_id[tid];
+        out_probe[(size_t)q * k + tid] = L;
+        if (out_sims) out_sims[(size_t)q * k + tid] = key_to_f32(o_key[tid]);
+        if (out_qtiles) {
+            const uint32_t len = (uint32_t)(next_list_off[L + 1] - next_list_off[L]);
+            mytiles = (len + next_tile_rows - 1) / next_tile_rows;
+        }
+    }
+    if (out_qtiles) {
+        for (int o = 16; o > 0; o >>= 1) mytiles += __shfl_xor_sync(FULL, mytiles, o);
+        if (lane == 0 && mytiles) atomicAdd(&s_tiles, mytiles);
+        __syncthreads();
+        if (tid == 0) out_qtiles[q] = s_tiles ? s_tiles : 1u;
+    }
+    if (tid == 0 && out_status) {
+        const uint32_t status = flag_cnt[q] > flag_cap ? status_bit : 0u;  // unlisted uncertified pairs: the caller's literal path
+        out_status[q] = status_init ? status : (out_status[q] | status);
+    }
+}
+
 }  // namespace
 
 cudaError_t probe_set_certify_scale(float scale) { return cudaMemcpyToSymbol(c_certify_scale, &scale, sizeof(float)); }
 
+uint32_t probe_segments(size_t C) {  // key-row segments of at most 8192 keys (32 register-resident keys per thread)
+    const size_t s = (C + 8191) / 8192;
+    return (uint32_t)(s < 1 ? 1 : s);
+}
+
 bool probe_batch_supported(const MatView &cent, size_t nq, size_t k) {
     const int cpl = cent.d_pad / 256;
     return cent.d_pad % 256 == 0 && (cpl == 1 || cpl == 2 || cpl == 3 || cpl == 4 || cpl == 6) && k >= 1 && k <= (size_t)kMaxProbe &&
-           k <= cent.n && cent.n < 0x7FFFFFFFull && nq * cent.n <= ((size_t)32 << 20);
+           k <= cent.n && probe_segments(cent.n) <= 32 && nq * cent.n <= ((size_t)32 << 20);
 }
 
 cudaError_t launch_probe_batch(const MatView &cent, const MatView &queries, int k, uint32_t *keys, unsigned int *flag_cnt,
-                               uint32_t *flag_list, uint32_t flag_cap, uint32_t *out_probe, float *out_sims, uint32_t *out_qtiles,
+                               uint32_t *flag_list, uint32_t flag_cap, uint32_t *cand_keys, uint32_t *cand_ids, uint32_t *out_probe,
+                               float *out_sims, uint32_t *out_qtiles,
                                const uint64_t *next_list_off, uint32_t next_tile_rows, uint32_t *out_status, uint32_t status_bit,
                                int status_init, unsigned long long *fix_counter, int sm_count, cudaStream_t st) {
     const size_t nq = queries.n, C = cent.n;
@@ -339,23 +445,28 @@ cudaError_t launch_probe_batch(const MatView &cent, const MatView &queries, int 
     e = cudaGetLastError();
     if (e != cudaSuccess) return e;
     const size_t smem2 = (size_t)cent.d * sizeof(double);
-    const size_t per = (C + kSelThreadsP - 1) / kSelThreadsP;
+    const uint32_t nseg = probe_segments(C);
+    const uint32_t seg_len = (uint32_t)((C + nseg - 1) / nseg);
+    const size_t per = ((size_t)seg_len + kSelThreadsP - 1) / kSelThreadsP;
 #define VS_PROBE_SELECT(KPT)                                                                                                  \
     do {                                                                                                                      \
         if (smem2 > 40 * 1024) {                                                                                              \
             e = cudaFuncSetAttribute(probe_select_kernel<KPT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem2);      \
             if (e != cudaSuccess) return e;                                                                                   \
         }                                                                                                                     \
-        probe_select_kernel<KPT><<<(unsigned)nq, kSelThreadsP, smem2, st>>>(cent, queries, keys, C, flag_cnt, flag_list, flag_cap, k, \
-                                                                            out_probe, out_sims, out_qtiles, next_list_off,  \
-                                                                            next_tile_rows, out_status, status_bit,          \
-                                                                            status_init, fix_counter);                       \
+        probe_select_kernel<KPT><<<(unsigned)(nq * nseg), kSelThreadsP, smem2, st>>>(                                         \
+            cent, queries, keys, C, flag_cnt, flag_list, flag_cap, k, out_probe, out_sims, out_qtiles, next_list_off,         \
+            next_tile_rows, out_status, status_bit, status_init, fix_counter, nseg, seg_len, cand_keys, cand_ids);            \
     } while (0)
     if (per <= 8) VS_PROBE_SELECT(8);
     else if (per <= 16) VS_PROBE_SELECT(16);
-    else if (per <= 32) VS_PROBE_SELECT(32);
-    else VS_PROBE_SELECT(0);
+    else VS_PROBE_SELECT(32);
 #undef VS_PROBE_SELECT
+    e = cudaGetLastError();
+    if (e != cudaSuccess || nseg == 1) return e;
+    probe_final_kernel<<<(unsigned)nq, kSelThreadsP, 0, st>>>(cand_keys, cand_ids, nseg * (uint32_t)k, (uint32_t)C, flag_cnt, flag_cap, k,
+                                                             out_probe, out_sims, out_qtiles, next_list_off, next_tile_rows, out_status,
+                                                             status_bit, status_init);
     return cudaGetLastError();
 }
 

@@ -69,3 +69,56 @@ func KMeansStep(data Matrix, centroids [][]uint8, means []float32) (counts []int
 	}
 	return counts, newCentroids, conv != 0
 }
+
+// KMeans is the whole kMeans of dnc/k_means.go:19-212 on the device. supersetRows are the distinct random row indices
+// the reference draws at k_means.go:35-44 (min(len(data), k*config.SUPERSET_MUL) of them); the two convergence loops,
+// the truncation to the first k centroids and the float32 means all stay in HBM. iterLimit = config.KMEANS_ITTERATION_LIMIT.
+func KMeans(data Matrix, k int, supersetRows []uint64, iterLimit int) (centroids [][]uint8) {
+	m := data.(*matrixContainer)
+	rowBytes := m.cols + 8
+	out := make([]uint8, k*rowBytes)
+	withDefaultCtx(func(c *ctx) {
+		check(C.vs_kmeans(c.h, m.h, C.size_t(k), (*C.uint64_t)(unsafe.Pointer(&supersetRows[0])), C.size_t(len(supersetRows)),
+			C.size_t(iterLimit), (*C.uint8_t)(unsafe.Pointer(&out[0])), nil))
+	})
+	centroids = make([][]uint8, k)
+	for i := range centroids {
+		centroids[i] = out[i*rowBytes : (i+1)*rowBytes]
+	}
+	return centroids
+}
+
+// LoadSpool builds a device matrix straight from a D&C cache file (dnc/dataset.go: a flat file of 8+vectorSize-byte
+// rows), replacing the ReadRow loop + NewMatrix re-pack of chunkData (k_means.go:214-221). count 0 = to the end.
+func LoadSpool(path string, vectorSize int, firstRow, count uint64) Matrix {
+	cpath := C.CString(path)
+	defer C.free(unsafe.Pointer(cpath))
+	m := &matrixContainer{cols: vectorSize}
+	withDefaultCtx(func(c *ctx) {
+		check(C.vs_matrix_load_spool(c.h, cpath, C.size_t(8+vectorSize), C.size_t(firstRow), C.size_t(count), &m.h))
+	})
+	m.rows = int(C.vs_matrix_rows(m.h))
+	runtime.SetFinalizer(m, func(m *matrixContainer) { C.vs_matrix_release(m.h) })
+	return m
+}
+
+// SearchBatch answers many queries at once (queries as packed 8+D-byte rows). With nprobe >= the number of lists and
+// 64 or more queries the library scores the batch on the tensor cores (tcgen05 int8 GEMM + fused filter).
+func (ix *Index) SearchBatch(queries [][]uint8, nprobe int, k int) (documentIDs [][]uint64, similarities [][]float32) {
+	qbuf, nq, _ := pack(queries)
+	defer C.free(qbuf)
+	ids := make([]uint64, nq*k)
+	sims := make([]float32, nq*k)
+	counts := make([]int32, nq)
+	withDefaultCtx(func(c *ctx) {
+		check(C.vs_search(c.h, ix.h, (*C.uint8_t)(qbuf), C.size_t(nq), C.size_t(nprobe), C.size_t(k),
+			(*C.uint64_t)(unsafe.Pointer(&ids[0])), (*C.float)(unsafe.Pointer(&sims[0])), (*C.int32_t)(unsafe.Pointer(&counts[0]))))
+	})
+	documentIDs = make([][]uint64, nq)
+	similarities = make([][]float32, nq)
+	for i := 0; i < nq; i++ {
+		documentIDs[i] = ids[i*k : i*k+int(counts[i])]
+		similarities[i] = sims[i*k : i*k+int(counts[i])]
+	}
+	return documentIDs, similarities
+}
