@@ -21,7 +21,7 @@ SYMBOLS = [
     "vs_index_build", "vs_index_build_assigned", "vs_index_build_dev", "vs_index_release",
     "vs_index_rows", "vs_index_lists", "vs_index_list_offsets", "vs_index_read_rows", "vs_search", "vs_search_flat", "vs_search_flat_gemm", "vs_search_batch_dev", "vs_index_search_batch_dev", "vs_search_dev",
     "vs_search_resolve", "vs_select_probes", "vs_topk_merge_dev", "vs_topk_merge_packed_dev",
-    "vs_kmeans_step", "vs_kmeans", "vs_recenter", "vs_debug_set_argmax_gemm_min",
+    "vs_kmeans_step", "vs_kmeans", "vs_kmeans_accumulate_dev", "vs_kmeans_finish_dev", "vs_recenter", "vs_debug_set_argmax_gemm_min",
 ]
 
 
@@ -107,6 +107,8 @@ def load():
         L.vs_matrix_load_spool.argtypes = [vp, C.c_char_p, sz, sz, sz, C.POINTER(vp)]
         L.vs_matrix_save_spool.argtypes = [vp, vp, sz, sz, C.c_char_p, C.c_int]
         L.vs_kmeans.argtypes = [vp, vp, sz, vp, sz, sz, vp, vp]
+        L.vs_kmeans_accumulate_dev.argtypes = [vp, vp, sz, vp, vp, vp]
+        L.vs_kmeans_finish_dev.argtypes = [vp, vp, vp, vp, vp, C.POINTER(vp), C.POINTER(C.c_int)]
         L.vs_index_search_batch_dev.argtypes = [vp, vp, vp, sz, vp, vp, vp, vp]
         L.vs_search_dev.argtypes = [vp, vp, vp, sz, sz, vp, vp, vp, vp]
         L.vs_search_resolve.argtypes = [vp, vp, vp, sz, sz, vp, vp, vp, vp, C.POINTER(C.c_int)]

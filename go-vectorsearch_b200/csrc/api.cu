@@ -1827,6 +1827,68 @@ extern "C" int vs_kmeans(vs_ctx *c, const vs_matrix *data, size_t k, const uint6
     return VS_OK;
 }
 
+// ---- one Lloyd iteration over a store cut into contiguous row blocks (one block per GPU) --------------------------
+// Every rank assigns its own rows (vs_argmax_MxN_dev; k_means.go:73-77) at the same time.  vs_kmeans_accumulate_dev then
+// continues the per-centroid float32 sums and counts from the values the previous block left in d_sums / d_counts
+// (zeros for the first block).  Blocks are accumulated in row order, so the additions run in the reference's order
+// (k_means.go:80-86) and the result is the same bits as on one device; the running sums travel from rank to rank
+// (NCCL send/recv, shard.py).
+extern "C" int vs_kmeans_accumulate_dev(vs_ctx *c, const vs_matrix *data, size_t k, const int32_t *d_assign, float *d_sums,
+                                        int64_t *d_counts) {
+    VS(need_dev());
+    if (!c || !data || !d_assign || !d_sums || !d_counts) return fail(VS_EINVAL, "null argument");
+    if (k == 0) return fail(VS_EEMPTY, "matrix rows are empty");
+    const size_t n = data->n;
+    if (n > 0xFFFFFFF0ull) return fail(VS_ERANGE, "n=%zu rows", n);
+    Arena a(c);
+    VS(a.reserve(2 * Arena::pad(n * 4) + Arena::pad((k + 1) * 4) + sort_rows_ws_bytes(n) + 4096));
+    uint32_t *d_order = a.take<uint32_t>(n);
+    uint32_t *d_sorted = a.take<uint32_t>(n);
+    uint32_t *d_segoff = a.take<uint32_t>(k + 1);
+    const size_t ws_bytes = sort_rows_ws_bytes(n);
+    char *d_ws = a.take<char>(ws_bytes);
+    VS(sort_rows_by_key(c, reinterpret_cast<const uint32_t *>(d_assign), n, bits_for(k), d_order, d_sorted, d_ws, ws_bytes));
+    lower_bound_kernel<<<(unsigned)((k + 1 + 255) / 256), 256, 0, c->stream>>>(d_sorted, n, nullptr, d_segoff, k);
+    c->launches++;
+    LAUNCH(c, launch_kmeans_accumulate_relay(data->view(), d_order, d_segoff, (int)k, d_sums, d_counts, c->stream));
+    return VS_OK;
+}
+
+// vs_kmeans_finish_dev (after the last block): means = sums / float32(count) where a cluster has members, else the
+// previous mean (k_means.go:89-96); new centroids = QuantizeMatrixFloat32(means) (:99) as a new device matrix;
+// *converged_out = every centroid's code bytes unchanged (:102-108).  d_means: [k][D] float32 state, in/out.
+extern "C" int vs_kmeans_finish_dev(vs_ctx *c, const vs_matrix *centroids, const float *d_sums, const int64_t *d_counts,
+                                    float *d_means, vs_matrix **new_centroids_out, int *converged_out) {
+    VS(need_dev());
+    if (!c || !centroids || !d_sums || !d_counts || !d_means || !new_centroids_out) return fail(VS_EINVAL, "null argument");
+    const size_t k = centroids->n, d = centroids->d;
+    vs_matrix *m = nullptr;
+    VS(matrix_alloc(k, d, &m));
+    Arena a(c);
+    int rc = a.reserve(1024);
+    int *d_flag = rc == VS_OK ? a.take<int>(16) : nullptr;
+    cudaError_t e = rc == VS_OK ? launch_kmeans_finalize(d_sums, d_counts, k, (int)d, d_means, c->stream) : cudaSuccess;
+    if (rc == VS_OK && e == cudaSuccess) e = cudaMemsetAsync(m->codes, 0, k * (size_t)m->d_pad, c->stream);
+    if (rc == VS_OK && e == cudaSuccess) e = launch_quantize_f32_soa(d_means, k, (int)d, m->codes, m->d_pad, m->hdr, m->sums, c->stream);
+    if (rc == VS_OK && e == cudaSuccess) e = cudaMemsetAsync(d_flag, 0, sizeof(int), c->stream);
+    if (rc == VS_OK && e == cudaSuccess) {
+        codes_differ_kernel<<<g_sm_count * 4, 256, 0, c->stream>>>(centroids->codes, m->codes, k, (int)d, m->d_pad, d_flag);
+        e = cudaGetLastError();
+    }
+    int h_flag = 0;
+    if (rc == VS_OK && e == cudaSuccess) e = cudaMemcpyAsync(&h_flag, d_flag, sizeof(int), cudaMemcpyDeviceToHost, c->stream);
+    if (rc == VS_OK && e == cudaSuccess) e = cudaStreamSynchronize(c->stream);
+    if (rc == VS_OK && e != cudaSuccess) rc = fail(VS_ECUDA, "k-means finish: %s", cudaGetErrorString(e));
+    if (rc != VS_OK) {
+        vs_matrix_release(m);
+        return rc;
+    }
+    c->launches += 3;
+    if (converged_out) *converged_out = h_flag == 0;
+    *new_centroids_out = m;
+    return VS_OK;
+}
+
 extern "C" int vs_recenter(vs_ctx *c, const vs_matrix *m, uint8_t *out_row) {
     VS(need_dev());
     if (!c || !m || !out_row) return fail(VS_EINVAL, "null argument");

@@ -26,6 +26,11 @@ __device__ __forceinline__ float byte_over_255(uint32_t word, int k) {
 }
 
 // order[seg_off[c] .. seg_off[c+1]) = rows assigned to centroid c, ascending.
+// RELAY = false: sums start at zero and the mean is written (one device holds every row).
+// RELAY = true: the chains continue from sums[] and the running sums are written back, counts are added to: the rows
+// of a store cut into contiguous blocks are accumulated block after block (device after device) in row order, which
+// is the reference's single left-to-right chain, bit for bit; kmeans_finalize_kernel divides at the end.
+template <bool RELAY>
 __global__ void __launch_bounds__(kAccThreads)
 kmeans_accumulate_kernel(MatView data, const uint32_t *__restrict__ order, const uint32_t *__restrict__ seg_off,
                          float *__restrict__ means, int64_t *__restrict__ counts) {
@@ -34,9 +39,16 @@ kmeans_accumulate_kernel(MatView data, const uint32_t *__restrict__ order, const
     const int c = blockIdx.x;
     const int j0 = (blockIdx.y * kAccThreads + threadIdx.x) * 4;
     const uint32_t beg = seg_off[c], end = seg_off[c + 1];
-    if (blockIdx.y == 0 && threadIdx.x == 0) counts[c] = (int64_t)(end - beg);
+    if (blockIdx.y == 0 && threadIdx.x == 0) counts[c] = (RELAY ? counts[c] : 0) + (int64_t)(end - beg);
     const bool live = j0 < data.d_pad;  // d_pad is a multiple of 16: the 4-byte word stays inside the padded row
     float s0 = 0.0f, s1 = 0.0f, s2 = 0.0f, s3 = 0.0f;  // k_means.go:60-65 zero-initialised sumVectors
+    if (RELAY && live) {
+        const float *m = means + (size_t)c * data.d;
+        if (j0 + 0 < data.d) s0 = m[j0 + 0];
+        if (j0 + 1 < data.d) s1 = m[j0 + 1];
+        if (j0 + 2 < data.d) s2 = m[j0 + 2];
+        if (j0 + 3 < data.d) s3 = m[j0 + 3];
+    }
     for (uint32_t base = beg; base < end; base += kAccChunk) {
         const int cnt = (int)min((uint32_t)kAccChunk, end - base);
         __syncthreads();
@@ -61,19 +73,41 @@ kmeans_accumulate_kernel(MatView data, const uint32_t *__restrict__ order, const
         }
     }
     if (end > beg && live) {  // :89-96 (an empty cluster keeps its previous mean)
-        const float n = (float)(int64_t)(end - beg);
+        const float n = RELAY ? 1.0f : (float)(int64_t)(end - beg);
         float *m = means + (size_t)c * data.d;
-        if (j0 + 0 < data.d) m[j0 + 0] = __fdiv_rn(s0, n);
-        if (j0 + 1 < data.d) m[j0 + 1] = __fdiv_rn(s1, n);
-        if (j0 + 2 < data.d) m[j0 + 2] = __fdiv_rn(s2, n);
-        if (j0 + 3 < data.d) m[j0 + 3] = __fdiv_rn(s3, n);
+        if (j0 + 0 < data.d) m[j0 + 0] = RELAY ? s0 : __fdiv_rn(s0, n);
+        if (j0 + 1 < data.d) m[j0 + 1] = RELAY ? s1 : __fdiv_rn(s1, n);
+        if (j0 + 2 < data.d) m[j0 + 2] = RELAY ? s2 : __fdiv_rn(s2, n);
+        if (j0 + 3 < data.d) m[j0 + 3] = RELAY ? s3 : __fdiv_rn(s3, n);
+    }
+}
+
+// means[c][j] = sums[c][j] / float32(counts[c]) where the cluster has members (k_means.go:89-96)
+__global__ void kmeans_finalize_kernel(const float *__restrict__ sums, const int64_t *__restrict__ counts, size_t k, int d,
+                                       float *__restrict__ means) {
+    const size_t total = k * (size_t)d;
+    for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
+        const int64_t n = counts[i / d];
+        if (n > 0) means[i] = __fdiv_rn(sums[i], (float)n);
     }
 }
 
 cudaError_t launch_kmeans_accumulate(const MatView &data, const uint32_t *order, const uint32_t *seg_off, int k,
                                      float *means, int64_t *counts, cudaStream_t st) {
     dim3 grid(k, (data.d_pad + kAccThreads * 4 - 1) / (kAccThreads * 4));
-    kmeans_accumulate_kernel<<<grid, kAccThreads, 0, st>>>(data, order, seg_off, means, counts);
+    kmeans_accumulate_kernel<false><<<grid, kAccThreads, 0, st>>>(data, order, seg_off, means, counts);
+    return cudaGetLastError();
+}
+
+cudaError_t launch_kmeans_accumulate_relay(const MatView &data, const uint32_t *order, const uint32_t *seg_off, int k,
+                                           float *sums, int64_t *counts, cudaStream_t st) {
+    dim3 grid(k, (data.d_pad + kAccThreads * 4 - 1) / (kAccThreads * 4));
+    kmeans_accumulate_kernel<true><<<grid, kAccThreads, 0, st>>>(data, order, seg_off, sums, counts);
+    return cudaGetLastError();
+}
+
+cudaError_t launch_kmeans_finalize(const float *sums, const int64_t *counts, size_t k, int d, float *means, cudaStream_t st) {
+    kmeans_finalize_kernel<<<1024, 256, 0, st>>>(sums, counts, k, d, means);
     return cudaGetLastError();
 }
 

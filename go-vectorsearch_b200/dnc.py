@@ -59,6 +59,27 @@ def KMeans(data_matrix, k, superset_rows=None, rng=None, iter_limit=KMEANS_ITTER
     return out
 
 
+def KMeansAccumulateDev(data_matrix, k, d_assign, d_sums, d_counts, ctx=None):
+    """One block of rows of a Lloyd iteration (vs_kmeans_accumulate_dev): given the rows' nearest-centroid indices (int32,
+    raw device pointer d_assign, from Matrix.ArgmaxDev) continue the float32 sums [k][d] / int64 counts [k] (raw device
+    pointers) that the previous block of rows left -- zeros for the first block.  Asynchronous on the ctx stream."""
+    ctx = ctx or default_context()
+    _check(data_matrix._L.vs_kmeans_accumulate_dev(ctx.handle, data_matrix.handle, int(k), C.c_void_p(int(d_assign)),
+                                                   C.c_void_p(int(d_sums)), C.c_void_p(int(d_counts))))
+
+
+def KMeansFinishDev(centroid_matrix, d_sums, d_counts, d_means, ctx=None):
+    """After the last block (vs_kmeans_finish_dev): new means (raw device pointer d_means, [k][d] float32, in/out), the new
+    centroid matrix and the convergence flag of k_means.go:102-108.  Returns (compute.Matrix, converged)."""
+    from .compute import Matrix
+    ctx = ctx or default_context()
+    h = C.c_void_p()
+    conv = C.c_int(0)
+    _check(centroid_matrix._L.vs_kmeans_finish_dev(ctx.handle, centroid_matrix.handle, C.c_void_p(int(d_sums)),
+                                                   C.c_void_p(int(d_counts)), C.c_void_p(int(d_means)), C.byref(h), C.byref(conv)))
+    return Matrix(h, centroid_matrix._L), bool(conv.value)
+
+
 def Recenter(matrix, ctx=None):
     """recenterDbCentroid's arithmetic (dnc.go:417-449) over all rows of `matrix` -> row776."""
     ctx = ctx or default_context()

@@ -75,3 +75,47 @@ class PackedHits:
         _check(L.vs_topk_merge_packed_dev(ctx.handle, vp(self.gathered), self.nbytes, self.ids_off, self.sims_off,
                                           self.counts_off, self.world, self.nq, self.k, vp(self.out_ids), vp(self.out_sims),
                                           vp(self.out_counts)))
+
+
+# ---- k-means over a store cut into contiguous row blocks -------------------------------------------
+def block_range(n_total, rank, world):
+    """Rows [lo, hi) of rank `rank` when the store is cut into `world` contiguous blocks (row order = rank order, which is
+    what lets the float32 sums of k_means.go:80-86 be continued from rank to rank in the reference's order)."""
+    base, rem = divmod(n_total, world)
+    lo = rank * base + min(rank, rem)
+    return lo, lo + base + (1 if rank < rem else 0)
+
+
+def kmeans_step_relay(assign, accumulate, finish, sums, counts, centroid_rows, group=None):
+    """One Lloyd iteration (dnc/k_means.go:67-117) across ranks, bit-identical to one device.
+
+    Every rank first assigns its own block of rows (`assign()`; at many centroids this is the whole cost and it runs on
+    all ranks at once).  The running float32 sums / int64 counts (torch tensors) are then relayed rank 0 -> 1 -> ... in
+    row order: a rank receives them (zeros on rank 0), continues them over its rows (`accumulate(sums, counts)`) and
+    sends them on; the last rank calls `finish(sums, counts) -> (new centroid rows uint8 tensor [k, 8+d], converged)`
+    and broadcasts both.  An all-reduce would be one collective instead of a relay, but float32 addition is not
+    associative: the reference's bytes need its order.  `centroid_rows`: uint8 tensor [k, 8+d] that receives the
+    broadcast.  Returns converged (bool).
+    """
+    import torch
+    import torch.distributed as dist
+    rank, world = dist.get_rank(group), dist.get_world_size(group)
+    assign()
+    if rank > 0:
+        dist.recv(sums, src=rank - 1, group=group)
+        dist.recv(counts, src=rank - 1, group=group)
+    else:
+        sums.zero_()
+        counts.zero_()
+    accumulate(sums, counts)
+    flag = torch.zeros(1, dtype=torch.int32, device=centroid_rows.device)
+    if rank < world - 1:
+        dist.send(sums, dst=rank + 1, group=group)
+        dist.send(counts, dst=rank + 1, group=group)
+    else:
+        rows, conv = finish(sums, counts)
+        centroid_rows.copy_(rows)
+        flag.fill_(1 if conv else 0)
+    dist.broadcast(centroid_rows, src=world - 1, group=group)
+    dist.broadcast(flag, src=world - 1, group=group)
+    return bool(int(flag.item()))

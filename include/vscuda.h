@@ -224,6 +224,16 @@ VS_API int vs_kmeans_step(vs_ctx *ctx, const vs_matrix *data, const uint8_t *cen
  * The early returns of :20-26 (k <= 0, n <= k) are the binding's: they need no device work. */
 VS_API int vs_kmeans(vs_ctx *ctx, const vs_matrix *data, size_t k, const uint64_t *superset_rows, size_t ks, size_t iter_limit,
               uint8_t *centroids_out, int64_t *stats_out);
+/* One Lloyd iteration over a store cut into contiguous row blocks, one per GPU, bit-identical to one
+ * device.  Every rank assigns its rows with vs_argmax_MxN_dev at the same time; vs_kmeans_accumulate_dev then continues
+ * the per-centroid float32 sums [k][D] and int64 counts [k] (device buffers; zeros before the first block) over this
+ * block's rows in row order, and the buffers travel to the next rank (NCCL send/recv).  After the last block
+ * vs_kmeans_finish_dev turns them into the new float32 means (d_means in/out; an empty cluster keeps its previous
+ * mean), the new centroid matrix and the convergence flag of k_means.go:102-108. */
+VS_API int vs_kmeans_accumulate_dev(vs_ctx *ctx, const vs_matrix *data, size_t k, const int32_t *d_assign, float *d_sums,
+                             int64_t *d_counts);
+VS_API int vs_kmeans_finish_dev(vs_ctx *ctx, const vs_matrix *centroids, const float *d_sums, const int64_t *d_counts,
+                         float *d_means, vs_matrix **new_centroids_out, int *converged_out);
 /* recenterDbCentroid (dnc.go:417-449): float64 mean of all rows of m in row order -> row776. */
 VS_API int vs_recenter(vs_ctx *ctx, const vs_matrix *m, uint8_t *out_row);
 

@@ -67,3 +67,40 @@ def test_kmeans_early_returns(vs):
     m = vs.compute.NewMatrix(data)
     assert vs.dnc.KMeans(m, 0) is None
     assert (vs.dnc.KMeans(m, 4) == data).all() and (vs.dnc.KMeans(m, 9) == data).all()
+
+
+@pytest.mark.parametrize("d,n,k,blocks", [(768, 9000, 7, 3), (256, 5000, 40, 4), (768, 2500, 300, 2)])
+def test_kmeans_row_blocks_relay_matches_one_device(vs, oracle, d, n, k, blocks):
+    """The store cut into contiguous row blocks (one per GPU in production, shard.kmeans_step_relay): assigning block by
+    block and continuing the float32 sums in row order gives the oracle's single-device bits (here the blocks are
+    separate matrices on one GPU, processed in order)."""
+    import torch
+    data = oracle.quantize_matrix_f32(unit_rows(n, d, 30 + k))
+    cent = data[np.random.default_rng(k).choice(n, k, replace=False)].copy()
+    cent[1] = cent[0]                                  # an empty cluster keeps its previous mean
+    means_o = np.full((k, d), 0.25, np.float32)
+    dev = torch.device("cuda", 0)
+    ctx = vs.compute.default_context()
+    d_means = torch.from_numpy(means_o.copy()).to(dev)
+    cmat = vs.compute.NewMatrix(cent)
+    cent_o = cent
+    bounds = [vs.shard.block_range(n, r, blocks) for r in range(blocks)]
+    mats = [vs.compute.NewMatrix(data[lo:hi]) for lo, hi in bounds]
+    for it in range(2):
+        a_o, c_o, new_o, conv_o = oracle.kmeans_step(data, cent_o, means_o)
+        sums = torch.zeros(k * d, dtype=torch.float32, device=dev)
+        counts = torch.zeros(k, dtype=torch.int64, device=dev)
+        assigns = []
+        for (lo, hi), m in zip(bounds, mats):
+            a = torch.empty(hi - lo, dtype=torch.int32, device=dev)
+            torch.cuda.synchronize()
+            cmat.ArgmaxDev(m, a.data_ptr(), ctx=ctx)
+            vs.dnc.KMeansAccumulateDev(m, k, a.data_ptr(), sums.data_ptr(), counts.data_ptr(), ctx=ctx)
+            ctx.sync()
+            assigns.append(a.cpu().numpy())
+        cmat, conv = vs.dnc.KMeansFinishDev(cmat, sums.data_ptr(), counts.data_ptr(), d_means.data_ptr(), ctx=ctx)
+        assert (np.concatenate(assigns) == a_o).all(), f"assign differs at iteration {it}"
+        assert (counts.cpu().numpy() == c_o).all()
+        assert (f32_bits(d_means.cpu().numpy()) == f32_bits(means_o)).all()
+        assert (cmat.ReadRows() == new_o).all() and conv == conv_o
+        cent_o = new_o

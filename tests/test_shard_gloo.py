@@ -110,3 +110,91 @@ def test_stripe_partition():
             parts = [pkg.shard.stripe(n, r, world) for r in range(world)]
             assert sorted(np.concatenate(parts).tolist()) == list(range(n))
             assert [len(p) for p in parts] == [pkg.shard.local_count(n, r, world) for r in range(world)]
+
+
+# ---- k-means over contiguous row blocks: the relay of shard.kmeans_step_relay ------------------------------------------
+def _kmeans_worker(rank, world, port, q):
+    """On the GPU box assign / accumulate / finish are libvscuda calls (vs_argmax_MxN_dev, vs_kmeans_accumulate_dev,
+    vs_kmeans_finish_dev); here numpy stand-ins restate them (float32 sums continued in row order, k_means.go:80-99) so
+    that the relay's control flow -- who waits for whom, what is broadcast -- is checked on CPU against the oracle's
+    single-process iteration."""
+    try:
+        os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world))
+        import torch
+        import torch.distributed as dist
+        import oracle
+        from conftest import load_pkg
+        from _util import unit_rows
+        pkg = load_pkg()
+        dist.init_process_group("gloo", rank=rank, world_size=world)
+        n, d, k = 1501, 32, 6
+        data = oracle.quantize_matrix_f32(unit_rows(n, d, 11))
+        cent = data[np.random.default_rng(3).choice(n, k, replace=False)].copy()
+        cent[4] = cent[2]                                   # an empty cluster keeps its previous mean
+        lo, hi = pkg.shard.block_range(n, rank, world)
+        mine = data[lo:hi]
+        means = np.full((k, d), 0.5, np.float32)            # state of the finishing rank
+        means_o = means.copy()
+        cent_o = cent.copy()
+        cent_t = torch.from_numpy(cent.copy())
+        sums = torch.zeros(k * d, dtype=torch.float32)
+        counts = torch.zeros(k, dtype=torch.int64)
+        state = {}
+        for it in range(3):
+            a_o, c_o, new_o, conv_o = oracle.kmeans_step(data, cent_o, means_o)
+            cur = cent_t.numpy().copy()
+
+            def assign():
+                state["a"] = oracle.argmax_MxN(cur, mine)[1]
+
+            def accumulate(s, c):
+                sv = s.numpy().reshape(k, d)
+                x = oracle.dequantize_matrix_f32(mine)
+                for i, j in enumerate(state["a"]):           # row order; float32 additions (k_means.go:81-86)
+                    sv[j] += x[i]
+                    c[j] += 1
+
+            def finish(s, c):
+                sv = s.numpy().reshape(k, d)
+                for j in range(k):
+                    if int(c[j]) > 0:
+                        means[j] = sv[j] / np.float32(int(c[j]))
+                newc = oracle.quantize_matrix_f32(means)
+                conv = bool((newc[:, 8:] == cur[:, 8:]).all())
+                return torch.from_numpy(newc), conv
+
+            conv = pkg.shard.kmeans_step_relay(assign, accumulate, finish, sums, counts, cent_t)
+            assert (state["a"] == a_o[lo:hi]).all()
+            assert (cent_t.numpy() == new_o).all(), f"rank {rank} iteration {it}"
+            assert conv == conv_o
+            if rank == world - 1:
+                assert (counts.numpy() == c_o).all()
+                assert (means.view(np.uint32) == means_o.view(np.uint32)).all()
+            cent_o = new_o
+        dist.destroy_process_group()
+        q.put((rank, "ok"))
+    except Exception as e:  # noqa: BLE001
+        import traceback
+        q.put((rank, "error: " + repr(e) + "\n" + traceback.format_exc()))
+
+
+def test_kmeans_relay_world2_gloo():
+    import torch.multiprocessing as mp
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_kmeans_worker, args=(r, 2, port, q)) for r in range(2)]
+    [p.start() for p in procs]
+    res = [q.get(timeout=180) for _ in procs]
+    [p.join(timeout=60) for p in procs]
+    assert all(r[1] == "ok" for r in res), res
+
+
+def test_block_partition():
+    from conftest import load_pkg
+    pkg = load_pkg()
+    for n in (0, 1, 7, 1000, 1501):
+        for world in (1, 2, 3, 8):
+            r = [pkg.shard.block_range(n, i, world) for i in range(world)]
+            assert r[0][0] == 0 and r[-1][1] == n and all(r[i][1] == r[i + 1][0] for i in range(world - 1))
+            assert max(b - a for a, b in r) - min(b - a for a, b in r) <= 1
