@@ -16,7 +16,7 @@ SYMBOLS = [
     "vs_quantize_f32", "vs_quantize_f64", "vs_dequantize_f32", "vs_dequantize_f64",
     "vs_quantize_f32_dev", "vs_quantize_f64_dev",
     "vs_matrix_create", "vs_matrix_create_empty", "vs_matrix_fill_f32_dev", "vs_matrix_load_rows", "vs_matrix_create_dev", "vs_matrix_from_f32_dev", "vs_matrix_retain",
-    "vs_matrix_release", "vs_matrix_rows", "vs_matrix_cols", "vs_matrix_read_rows", "vs_matrix_load_spool", "vs_matrix_save_spool",
+    "vs_matrix_release", "vs_matrix_rows", "vs_matrix_cols", "vs_matrix_read_rows", "vs_matrix_load_spool", "vs_matrix_save_spool", "vs_matrix_gather", "vs_matrix_split_dev", "vs_matrix_split", "vs_reassign_recenter", "vs_recenter_clusters_dev",
     "vs_cosine_1xN", "vs_dot_1xN", "vs_argmax_MxN", "vs_argmax_MxN_dev",
     "vs_index_build", "vs_index_build_assigned", "vs_index_build_dev", "vs_index_release",
     "vs_index_rows", "vs_index_lists", "vs_index_list_offsets", "vs_index_read_rows", "vs_search", "vs_search_flat", "vs_search_flat_gemm", "vs_search_batch_dev", "vs_index_search_batch_dev", "vs_search_dev",
@@ -104,6 +104,11 @@ def load():
         L.vs_search_flat_gemm.argtypes = [vp, vp, vp, vp, sz, sz, vp, vp, vp]
         L.vs_search_batch_dev.argtypes = [vp, vp, vp, u64, vp, sz, vp, vp, vp, vp]
         L.vs_debug_set_argmax_gemm_min.argtypes = [sz]
+        L.vs_matrix_gather.argtypes = [vp, vp, vp, sz, C.POINTER(vp)]
+        L.vs_matrix_split_dev.argtypes = [vp, vp, vp, sz, vp, vp]
+        L.vs_matrix_split.argtypes = [vp, vp, vp, sz, vp, vp]
+        L.vs_reassign_recenter.argtypes = [vp, vp, vp, sz, vp, vp, vp, vp]
+        L.vs_recenter_clusters_dev.argtypes = [vp, vp, vp, sz, vp, vp]
         L.vs_matrix_load_spool.argtypes = [vp, C.c_char_p, sz, sz, sz, C.POINTER(vp)]
         L.vs_matrix_save_spool.argtypes = [vp, vp, sz, sz, C.c_char_p, C.c_int]
         L.vs_kmeans.argtypes = [vp, vp, sz, vp, sz, sz, vp, vp]

@@ -1889,6 +1889,170 @@ extern "C" int vs_kmeans_finish_dev(vs_ctx *c, const vs_matrix *centroids, const
     return VS_OK;
 }
 
+// ---- device-side pieces of the divide-and-conquer centroid build (dnc/dnc.go:300-400, 402-456) --------------------
+// vs_matrix_gather: a new matrix made of the given rows of src, in the given order (sample(), dnc/sampling.go:12-74).
+extern "C" int vs_matrix_gather(vs_ctx *c, const vs_matrix *src, const uint64_t *rows, size_t n, vs_matrix **out) {
+    VS(need_dev());
+    if (!c || !src || !rows || !out) return fail(VS_EINVAL, "null argument");
+    if (n == 0) return fail(VS_EEMPTY, "matrix rows are empty");
+    std::vector<uint32_t> r32(n);
+    for (size_t i = 0; i < n; i++) {
+        if (rows[i] >= src->n) return fail(VS_EINVAL, "row %llu >= %zu", (unsigned long long)rows[i], src->n);
+        r32[i] = (uint32_t)rows[i];
+    }
+    vs_matrix *m = nullptr;
+    VS(matrix_alloc(n, src->d, &m));
+    Arena a(c);
+    int rc = a.reserve(Arena::pad(n * 4) + 1024);
+    if (rc == VS_OK) {
+        uint32_t *d_rows = a.take<uint32_t>(n);
+        cudaError_t e = cudaMemcpyAsync(d_rows, r32.data(), n * 4, cudaMemcpyHostToDevice, c->stream);
+        if (e == cudaSuccess) e = launch_gather_rows(src->view(), d_rows, n, m->codes, m->hdr, m->sums, nullptr, 0, nullptr, c->stream);
+        if (e == cudaSuccess) e = cudaStreamSynchronize(c->stream);  // r32 is read by the copy
+        if (e != cudaSuccess) rc = fail(VS_ECUDA, "gather: %s", cudaGetErrorString(e));
+        c->launches++;
+    }
+    if (rc != VS_OK) {
+        vs_matrix_release(m);
+        return rc;
+    }
+    *out = m;
+    return VS_OK;
+}
+
+// vs_matrix_split_dev: the split loop of divideNconquer (dnc.go:363-389) once the rows have their nearest-centroid
+// index: child j receives the rows with d_assign[row] == j in their original order (a stable partition; the reference
+// appends rows to the child files in read order).  children_out[j] = null for a child without rows.
+extern "C" int vs_matrix_split_dev(vs_ctx *c, const vs_matrix *src, const int32_t *d_assign, size_t k, vs_matrix **children_out,
+                                   uint64_t *counts_out) {
+    VS(need_dev());
+    if (!c || !src || !d_assign || !children_out || !counts_out) return fail(VS_EINVAL, "null argument");
+    if (k == 0) return fail(VS_EINVAL, "k == 0");
+    const size_t n = src->n;
+    for (size_t j = 0; j < k; j++) children_out[j] = nullptr;
+    Arena a(c);
+    VS(a.reserve(2 * Arena::pad(n * 4) + Arena::pad((k + 1) * 4) + sort_rows_ws_bytes(n) + 4096));
+    uint32_t *d_order = a.take<uint32_t>(n);
+    uint32_t *d_sorted = a.take<uint32_t>(n);
+    uint32_t *d_segoff = a.take<uint32_t>(k + 1);
+    const size_t ws_bytes = sort_rows_ws_bytes(n);
+    char *d_ws = a.take<char>(ws_bytes);
+    VS(sort_rows_by_key(c, reinterpret_cast<const uint32_t *>(d_assign), n, bits_for(k), d_order, d_sorted, d_ws, ws_bytes));
+    lower_bound_kernel<<<(unsigned)((k + 1 + 255) / 256), 256, 0, c->stream>>>(d_sorted, n, nullptr, d_segoff, k);
+    c->launches++;
+    std::vector<uint32_t> off(k + 1);
+    CU(cudaMemcpyAsync(off.data(), d_segoff, (k + 1) * 4, cudaMemcpyDeviceToHost, c->stream));
+    CU(cudaStreamSynchronize(c->stream));
+    int rc = VS_OK;
+    for (size_t j = 0; j < k && rc == VS_OK; j++) {
+        const size_t cnt = off[j + 1] - off[j];
+        counts_out[j] = cnt;
+        if (cnt == 0) continue;
+        vs_matrix *m = nullptr;
+        rc = matrix_alloc(cnt, src->d, &m);
+        if (rc != VS_OK) break;
+        const cudaError_t e = launch_gather_rows(src->view(), d_order + off[j], cnt, m->codes, m->hdr, m->sums, nullptr, 0, nullptr,
+                                                 c->stream);
+        if (e != cudaSuccess) {
+            vs_matrix_release(m);
+            rc = fail(VS_ECUDA, "split: %s", cudaGetErrorString(e));
+            break;
+        }
+        c->launches++;
+        children_out[j] = m;
+    }
+    if (rc == VS_OK && cudaStreamSynchronize(c->stream) != cudaSuccess) rc = fail(VS_ECUDA, "split: stream sync");
+    if (rc != VS_OK)
+        for (size_t j = 0; j < k; j++)
+            if (children_out[j]) {
+                vs_matrix_release(children_out[j]);
+                children_out[j] = nullptr;
+            }
+    return rc;
+}
+
+// vs_recenter_clusters_dev: recenterDbCentroid (dnc.go:402-456) for all k clusters of an assignment at once: the float64
+// mean of each cluster's rows in row order, quantized with QuantizeVectorFloat64.  centroids_out: k rows (host).
+extern "C" int vs_recenter_clusters_dev(vs_ctx *c, const vs_matrix *data, const int32_t *d_assign, size_t k, uint8_t *centroids_out,
+                                        int64_t *counts_out) {
+    VS(need_dev());
+    if (!c || !data || !d_assign || !centroids_out) return fail(VS_EINVAL, "null argument");
+    if (k == 0) return fail(VS_EINVAL, "k == 0");
+    const size_t n = data->n, d = data->d, rb = 8 + d;
+    Arena a(c);
+    VS(a.reserve(2 * Arena::pad(n * 4) + Arena::pad((k + 1) * 4) + sort_rows_ws_bytes(n) + Arena::pad(k * d * 8) + Arena::pad(k * 8) +
+                 Arena::pad(k * rb) + 4096));
+    uint32_t *d_order = a.take<uint32_t>(n);
+    uint32_t *d_sorted = a.take<uint32_t>(n);
+    uint32_t *d_segoff = a.take<uint32_t>(k + 1);
+    const size_t ws_bytes = sort_rows_ws_bytes(n);
+    char *d_ws = a.take<char>(ws_bytes);
+    double *d_means = a.take<double>(k * d);
+    int64_t *d_counts = a.take<int64_t>(k);
+    uint8_t *d_rows = a.take<uint8_t>(k * rb);
+    VS(sort_rows_by_key(c, reinterpret_cast<const uint32_t *>(d_assign), n, bits_for(k), d_order, d_sorted, d_ws, ws_bytes));
+    lower_bound_kernel<<<(unsigned)((k + 1 + 255) / 256), 256, 0, c->stream>>>(d_sorted, n, nullptr, d_segoff, k);
+    c->launches++;
+    LAUNCH(c, launch_recenter_clusters(data->view(), d_order, d_segoff, (int)k, d_means, d_counts, c->stream));
+    LAUNCH(c, launch_quantize_f64(d_means, k, (int)d, d_rows, c->stream));
+    CU(cudaMemcpyAsync(centroids_out, d_rows, k * rb, cudaMemcpyDeviceToHost, c->stream));
+    if (counts_out) CU(cudaMemcpyAsync(counts_out, d_counts, k * 8, cudaMemcpyDeviceToHost, c->stream));
+    CU(cudaStreamSynchronize(c->stream));
+    return VS_OK;
+}
+
+// Host-pointer forms for the D&C driver: the centroids arrive as packed rows, the assignment stays on the device.
+// vs_matrix_split = the split loop of divideNconquer (dnc.go:363-389): nearest of the k centroids for every row of src
+// (cosine.go:70-125), then the stable partition above.
+extern "C" int vs_matrix_split(vs_ctx *c, const vs_matrix *src, const uint8_t *centroids, size_t k, vs_matrix **children_out,
+                               uint64_t *counts_out) {
+    VS(need_dev());
+    if (!c || !src || !centroids || !children_out || !counts_out) return fail(VS_EINVAL, "null argument");
+    if (k == 0) return fail(VS_EEMPTY, "matrix rows are empty");
+    const size_t n = src->n, rb = 8 + (size_t)src->d;
+    int32_t *d_assign = nullptr;
+    CU(cudaMalloc(&d_assign, n * 4 + 4));
+    int rc;
+    {
+        Arena a(c);
+        rc = a.reserve(temp_matrix_bytes(k, rb) + argmax_bytes(k, n) + 4096);
+        MatView cv;
+        if (rc == VS_OK) rc = temp_matrix(c, a, centroids, k, rb, &cv);
+        if (rc == VS_OK) rc = argmax_dev(c, a, cv, src->view(), d_assign, nullptr);
+    }
+    if (rc == VS_OK) rc = vs_matrix_split_dev(c, src, d_assign, k, children_out, counts_out);
+    cudaFree(d_assign);
+    return rc;
+}
+
+// The tail of KMeansDivideAndConquer (dnc.go:177-291): every row to its nearest of the k new centroids, then every
+// centroid re-centred on its members (recenterDbCentroid).  assign_out (host int32, nullable) / d_assign_out (device
+// int32, nullable) receive the assignment; centroids_out the k re-centred rows; counts_out the cluster sizes.
+extern "C" int vs_reassign_recenter(vs_ctx *c, const vs_matrix *data, const uint8_t *centroids, size_t k, int32_t *assign_out,
+                                    int32_t *d_assign_out, uint8_t *centroids_out, int64_t *counts_out) {
+    VS(need_dev());
+    if (!c || !data || !centroids || !centroids_out) return fail(VS_EINVAL, "null argument");
+    if (k == 0) return fail(VS_EEMPTY, "matrix rows are empty");
+    const size_t n = data->n, rb = 8 + (size_t)data->d;
+    int32_t *d_assign = d_assign_out;
+    if (!d_assign) CU(cudaMalloc(&d_assign, n * 4 + 4));
+    int rc;
+    {
+        Arena a(c);
+        rc = a.reserve(temp_matrix_bytes(k, rb) + argmax_bytes(k, n) + 4096);
+        MatView cv;
+        if (rc == VS_OK) rc = temp_matrix(c, a, centroids, k, rb, &cv);
+        if (rc == VS_OK) rc = argmax_dev(c, a, cv, data->view(), d_assign, nullptr);
+    }
+    if (rc == VS_OK) rc = vs_recenter_clusters_dev(c, data, d_assign, k, centroids_out, counts_out);
+    if (rc == VS_OK && assign_out) {
+        const cudaError_t e = cudaMemcpy(assign_out, d_assign, n * 4, cudaMemcpyDeviceToHost);
+        if (e != cudaSuccess) rc = fail(VS_ECUDA, "assignment download: %s", cudaGetErrorString(e));
+    }
+    if (!d_assign_out) cudaFree(d_assign);
+    return rc;
+}
+
 extern "C" int vs_recenter(vs_ctx *c, const vs_matrix *m, uint8_t *out_row) {
     VS(need_dev());
     if (!c || !m || !out_row) return fail(VS_EINVAL, "null argument");

@@ -197,6 +197,8 @@ cudaError_t launch_kmeans_accumulate(const MatView &data, const uint32_t *order,
 cudaError_t launch_kmeans_accumulate_relay(const MatView &data, const uint32_t *order, const uint32_t *seg_off, int k,
                                            float *sums, int64_t *counts, cudaStream_t st);
 cudaError_t launch_kmeans_finalize(const float *sums, const int64_t *counts, size_t k, int d, float *means, cudaStream_t st);
+cudaError_t launch_recenter_clusters(const MatView &data, const uint32_t *order, const uint32_t *seg_off, int k, double *means,
+                                     int64_t *counts, cudaStream_t st);
 cudaError_t launch_recenter(const MatView &data, double *mean_out, cudaStream_t st);
 
 }  // namespace vs

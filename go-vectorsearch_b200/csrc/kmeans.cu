@@ -127,6 +127,55 @@ __global__ void __launch_bounds__(32) recenter_kernel(MatView data, double *__re
     mean_out[j] = __ddiv_rn(sum, (double)(unsigned long long)data.n);
 }
 
+// recenterDbCentroid for every cluster at once: order[seg_off[c] .. seg_off[c+1]) = member rows of cluster c, ascending
+// (the reference reads a cluster's embeddings in primary-key order); one float64 chain per (cluster, dimension).
+// float64(q) / 255.0 comes from a 256-entry shared-memory table built with IEEE division (quantization.go:64).
+// A cluster without members divides 0 by 0: NaN, which QuantizeVectorFloat64 turns into all-zero codes (dnc.go:437-441).
+constexpr int kRecThreads = 128;
+__global__ void __launch_bounds__(kRecThreads)
+recenter_clusters_kernel(MatView data, const uint32_t *__restrict__ order, const uint32_t *__restrict__ seg_off,
+                         double *__restrict__ means, int64_t *__restrict__ counts) {
+    __shared__ double s_div[256];
+    __shared__ uint32_t s_row[kAccChunk];
+    __shared__ float2 s_hdr[kAccChunk];
+    for (int q = threadIdx.x; q < 256; q += kRecThreads) s_div[q] = __ddiv_rn((double)q, 255.0);
+    const int c = blockIdx.x;
+    const int j = blockIdx.y * kRecThreads + threadIdx.x;
+    const uint32_t beg = seg_off[c], end = seg_off[c + 1];
+    if (blockIdx.y == 0 && threadIdx.x == 0) counts[c] = (int64_t)(end - beg);
+    const bool live = j < data.d;
+    double sum = 0.0;
+    for (uint32_t base = beg; base < end; base += kAccChunk) {
+        const int cnt = (int)min((uint32_t)kAccChunk, end - base);
+        __syncthreads();
+        if ((int)threadIdx.x < cnt) {
+            const uint32_t r = order[base + threadIdx.x];
+            s_row[threadIdx.x] = r;
+            s_hdr[threadIdx.x] = data.hdr[r];
+        }
+        __syncthreads();
+        if (live) {
+#pragma unroll 8
+            for (int i = 0; i < cnt; i++) {
+                const uint32_t q = data.codes[(size_t)s_row[i] * data.d_pad + j];
+                const float2 h = s_hdr[i];
+                const double mn = (double)h.x;
+                // DequantizeVectorFloat64 (quantization.go:63-69,124-132), then dataSum[idx] += val (dnc.go:431-433)
+                sum = __dadd_rn(sum, __dadd_rn(mn, __dmul_rn(s_div[q], __dsub_rn((double)h.y, mn))));
+            }
+        }
+    }
+    __syncthreads();
+    if (live) means[(size_t)c * data.d + j] = __ddiv_rn(sum, (double)(unsigned long long)(end - beg));  // dnc.go:437-439
+}
+
+cudaError_t launch_recenter_clusters(const MatView &data, const uint32_t *order, const uint32_t *seg_off, int k, double *means,
+                                     int64_t *counts, cudaStream_t st) {
+    dim3 grid(k, (data.d + kRecThreads - 1) / kRecThreads);
+    recenter_clusters_kernel<<<grid, kRecThreads, 0, st>>>(data, order, seg_off, means, counts);
+    return cudaGetLastError();
+}
+
 cudaError_t launch_recenter(const MatView &data, double *mean_out, cudaStream_t st) {
     recenter_kernel<<<(data.d + 31) / 32, 32, 0, st>>>(data, mean_out);
     return cudaGetLastError();

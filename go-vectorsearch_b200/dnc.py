@@ -27,6 +27,9 @@ def KMeansStep(data_matrix, centroids, means, ctx=None, want_assign=True):
     return assign, counts, newc, bool(conv.value)
 
 
+CENTROID_SIZE = 10000            # config/constants.go:8
+SAMPLE_SIZE = 50000              # config/constants.go:9
+SPLIT_SIZE = 5                   # config/constants.go:10
 SUPERSET_MUL = 5                 # config/constants.go:11
 KMEANS_ITTERATION_LIMIT = 1000   # config/constants.go:12
 
@@ -86,3 +89,75 @@ def Recenter(matrix, ctx=None):
     out = np.empty(8 + matrix.cols, np.uint8)
     _check(matrix._L.vs_recenter(ctx.handle, matrix.handle, _p(out)))
     return out
+
+
+def _sample(X, sample_size, rng, ctx):
+    """sample() (dnc/sampling.go:12-74): all rows when there are at most sample_size, else sample_size distinct random rows
+    in ascending order."""
+    if X.rows <= sample_size:
+        return X
+    rows = np.sort(rng.choice(X.rows, sample_size, replace=False)).astype(np.uint64)
+    from .compute import Matrix
+    h = C.c_void_p()
+    _check(X._L.vs_matrix_gather(ctx.handle, X.handle, _p(rows), rows.shape[0], C.byref(h)))
+    return Matrix(h, X._L)
+
+
+def Split(X, centroids, ctx=None):
+    """The split loop of divideNconquer (dnc.go:363-389): child j = the rows of X nearest to centroid j, in X's order.
+    Returns a list of compute.Matrix (None for a child without rows)."""
+    from .compute import Matrix
+    ctx = ctx or default_context()
+    cent = _rows_array(centroids)
+    k = cent.shape[0]
+    handles = (C.c_void_p * k)()
+    counts = np.zeros(k, np.uint64)
+    _check(X._L.vs_matrix_split(ctx.handle, X.handle, _p(cent), k, C.cast(handles, C.c_void_p), _p(counts)))
+    return [Matrix(C.c_void_p(handles[j]), X._L) if handles[j] else None for j in range(k)]
+
+
+def DivideAndConquer(data_matrix, target_size=CENTROID_SIZE, sample_size=SAMPLE_SIZE, split_size=SPLIT_SIZE, rng=None,
+                     iter_limit=KMEANS_ITTERATION_LIMIT, ctx=None):
+    """divideNconquer (dnc/dnc.go:300-400) with every dataset resident in HBM instead of a temp file: a set of at most
+    target_size rows yields one centroid, kMeans(sample, 1)[0] (dataset.go:93-98); a larger one is split by the
+    min(split_size, max(2, rows / target_size)) centroids of kMeans(sample) and its children are treated the same way.
+    The reference runs the children concurrently and seeds every draw from the clock; here the order is depth-first with
+    children in index order and every draw comes from `rng`, so a build is reproducible.  A child that receives no row
+    is skipped (the reference would index an empty slice).  Returns the leaf centroids, (m, 8+d) uint8.
+    """
+    ctx = ctx or default_context()
+    rng = rng or np.random.default_rng()
+    out = []
+    stack = [data_matrix]
+    while stack:
+        X = stack.pop()
+        S = _sample(X, sample_size, rng, ctx)
+        if X.rows <= target_size:                                          # dnc.go:316-319
+            out.append(KMeans(S, 1, rng=rng, iter_limit=iter_limit, ctx=ctx)[0])
+            continue
+        k = min(split_size, max(2, X.rows // target_size))                 # dnc.go:330-339
+        cents = KMeans(S, k, rng=rng, iter_limit=iter_limit, ctx=ctx)
+        del S
+        children = [ch for ch in Split(X, cents, ctx=ctx) if ch is not None]
+        del X
+        stack.extend(reversed(children))                                    # child 0 first
+    return np.stack(out)
+
+
+def ReassignRecenter(data_matrix, centroids, d_assign=None, want_assign=True, ctx=None):
+    """The tail of KMeansDivideAndConquer (dnc.go:177-291): every row to its nearest new centroid, then every centroid
+    re-centred on its members (float64 mean in row order, QuantizeVectorFloat64).  dropSmallCentroids (dnc.go:458-574)
+    sits between the two upstream and never drops anything: its list is sorted ascending and its loop stops at the
+    first cluster below CENTROID_SIZE/10, which can only be index 0, so `oldCentroids = results[:0]` is always empty.
+    Returns (assign int32[n] or None, recentred centroids (k, 8+d) uint8, counts int64[k]); d_assign: optional raw device
+    pointer that also receives the assignment (for vs_index_build_dev)."""
+    ctx = ctx or default_context()
+    cent = _rows_array(centroids)
+    k, rb = cent.shape
+    n = data_matrix.rows
+    assign = np.empty(n, np.int32) if want_assign else None
+    out = np.empty((k, rb), np.uint8)
+    counts = np.empty(k, np.int64)
+    _check(data_matrix._L.vs_reassign_recenter(ctx.handle, data_matrix.handle, _p(cent), k, _p(assign) if want_assign else None,
+                                               C.c_void_p(int(d_assign)) if d_assign else None, _p(out), _p(counts)))
+    return assign, out, counts

@@ -234,6 +234,25 @@ VS_API int vs_kmeans_accumulate_dev(vs_ctx *ctx, const vs_matrix *data, size_t k
                              int64_t *d_counts);
 VS_API int vs_kmeans_finish_dev(vs_ctx *ctx, const vs_matrix *centroids, const float *d_sums, const int64_t *d_counts,
                          float *d_means, vs_matrix **new_centroids_out, int *converged_out);
+/* Device-side pieces of the divide-and-conquer centroid build (dnc/dnc.go:300-400; the recursion itself is host logic,
+ * see go-vectorsearch_b200/dnc.py DivideAndConquer).
+ * vs_matrix_gather: a new matrix of the given rows of src in the given order (sample(), dnc/sampling.go:12-74).
+ * vs_matrix_split_dev: stable partition of src by a device int32 assignment (dnc.go:363-389): children_out[j] gets the
+ *   rows assigned to j in their original order (null when none), counts_out[j] their number.
+ * vs_recenter_clusters_dev: recenterDbCentroid (dnc.go:402-456) for all k clusters of an assignment at once. */
+VS_API int vs_matrix_gather(vs_ctx *ctx, const vs_matrix *src, const uint64_t *rows, size_t n, vs_matrix **out);
+VS_API int vs_matrix_split_dev(vs_ctx *ctx, const vs_matrix *src, const int32_t *d_assign, size_t k, vs_matrix **children_out,
+                        uint64_t *counts_out);
+/* Host-pointer forms: vs_matrix_split = nearest of the k packed centroids for every row of src, then the stable
+ * partition (the whole split loop of dnc.go:363-389); vs_reassign_recenter = the tail of KMeansDivideAndConquer
+ * (dnc.go:177-291): every row to its nearest of the k new centroids (assignment to assign_out on the host and/or
+ * d_assign_out on the device, both nullable), every centroid re-centred on its members. */
+VS_API int vs_matrix_split(vs_ctx *ctx, const vs_matrix *src, const uint8_t *centroids_packed, size_t k, vs_matrix **children_out,
+                    uint64_t *counts_out);
+VS_API int vs_reassign_recenter(vs_ctx *ctx, const vs_matrix *data, const uint8_t *centroids_packed, size_t k, int32_t *assign_out,
+                         int32_t *d_assign_out, uint8_t *centroids_out, int64_t *counts_out);
+VS_API int vs_recenter_clusters_dev(vs_ctx *ctx, const vs_matrix *data, const int32_t *d_assign, size_t k, uint8_t *centroids_out,
+                             int64_t *counts_out);
 /* recenterDbCentroid (dnc.go:417-449): float64 mean of all rows of m in row order -> row776. */
 VS_API int vs_recenter(vs_ctx *ctx, const vs_matrix *m, uint8_t *out_row);
 

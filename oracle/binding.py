@@ -245,3 +245,57 @@ def kmeans(data, k, superset_rows, limit=1000):
             n += 1
         iters.append(n)
     return cent, iters[0], iters[1]
+
+
+def divide_and_conquer(rows, target_size, sample_size, split_size, rng, limit=1000):
+    """divideNconquer (dnc/dnc.go:300-400) on host arrays, depth-first with children in index order, every draw from `rng`
+    in the order the device driver makes them (the reference seeds each draw from the clock and runs children
+    concurrently, so only a restatement with shared draws can be compared): sample() (sampling.go:12-74) = all rows or
+    sample_size sorted distinct rows; a set of at most target_size rows yields kMeans(sample, 1)[0] (dataset.go:93-98);
+    a larger one is split by nearest centroid of kMeans(sample, min(split, max(2, rows/target))) (dnc.go:330-389)."""
+    rows = _u8(rows)
+
+    def sample(x):
+        if x.shape[0] <= sample_size:
+            return x
+        return x[np.sort(rng.choice(x.shape[0], sample_size, replace=False))]
+
+    def km(x, k):
+        if x.shape[0] == 0 or x.shape[0] <= k:
+            return x
+        ks = min(x.shape[0], 5 * k)
+        return kmeans(x, k, rng.choice(x.shape[0], ks, replace=False), limit)[0]
+
+    out, stack = [], [rows]
+    while stack:
+        x = stack.pop()
+        s = sample(x)
+        if x.shape[0] <= target_size:
+            out.append(km(s, 1)[0])
+            continue
+        cents = km(s, min(split_size, max(2, x.shape[0] // target_size)))
+        _, idx = argmax_MxN(cents, x)
+        children = [x[idx == j] for j in range(cents.shape[0])]
+        stack.extend(reversed([c for c in children if c.shape[0]]))
+    return np.stack(out)
+
+
+def reassign_recenter(rows, centroids):
+    """The tail of KMeansDivideAndConquer: nearest new centroid for every row (dnc.go:194-208), dropSmallCentroids (a no-op
+    upstream, see dnc.py), recenterDbCentroid for every centroid (dnc.go:402-456; a cluster without members divides by
+    zero: NaN -> all-zero codes)."""
+    rows = _u8(rows)
+    centroids = _u8(centroids)
+    _, idx = argmax_MxN(centroids, rows)
+    out = np.empty_like(centroids)
+    counts = np.zeros(centroids.shape[0], np.int64)
+    for j in range(centroids.shape[0]):
+        members = rows[idx == j]
+        counts[j] = members.shape[0]
+        if members.shape[0]:
+            out[j] = recenter(members)
+        else:
+            d = rows.shape[1] - 8
+            with np.errstate(invalid="ignore"):
+                out[j] = quantize_vector_f64(np.full(d, np.nan))
+    return idx.astype(np.int32), out, counts
