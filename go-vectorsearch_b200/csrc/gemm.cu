@@ -172,7 +172,22 @@ __device__ __forceinline__ void tc_ld_16x256b_x4(uint32_t taddr, uint32_t (&v)[1
         : "r"(taddr)
         : "memory");
 }
+__device__ __forceinline__ void tc_ld_16x256b_x2(uint32_t taddr, uint32_t (&v)[8]) {  // same, n = 0..1
+    asm volatile(
+        "tcgen05.ld.sync.aligned.16x256b.x2.b32 "
+        "{%0, %1, %2, %3, %4, %5, %6, %7}, [%8];"
+        : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7])
+        : "r"(taddr)
+        : "memory");
+}
 __device__ __forceinline__ void tc_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+// The wait names the destination registers of the load it completes, so no use of them can be scheduled above it.
+__device__ __forceinline__ void tc_ld_wait8(uint32_t (&v)[8]) {
+    asm volatile("tcgen05.wait::ld.sync.aligned;"
+                 : "+r"(v[0]), "+r"(v[1]), "+r"(v[2]), "+r"(v[3]), "+r"(v[4]), "+r"(v[5]), "+r"(v[6]), "+r"(v[7])
+                 :
+                 : "memory");
+}
 
 // Shared-memory matrix descriptor of a K-major [rows][128 B] SWIZZLE_128B tile (8-row groups 1024 B apart);
 // kbytes = offset of this instruction's 32-byte K slice inside the 128-byte swizzle atom.
@@ -425,93 +440,103 @@ gemm_kernel(const __grid_constant__ CUtensorMap tm_rows, const __grid_constant__
                 mbar_wait(q_full + 8 * acc_s, acc_ph);
                 mbar_wait(acc_full + 8 * acc_s, acc_ph);
                 tc_fence_after();
-#pragma unroll 1
-                for (int pass = 0; pass < kColsPerWarp / 32; pass++) {
-                    if (p.dbg >= 2) break;
-                    const int colbase = part * kColsPerWarp + pass * 32;
-                    // this thread's column pairs 4n + tc of the pass: (x0,x1), (y0,y1), (z0,z1), (w0,w1) each
-                    const ulonglong2 *qc = reinterpret_cast<const ulonglong2 *>(q_consts + acc_s * kTN + colbase + 2 * tc);
-                    uint64_t cx[4], cy[4], cz[4], cw[4];
-#pragma unroll
-                    for (int n = 0; n < 4; n++) {
-                        const ulonglong2 lo = qc[8 * n], hi = qc[8 * n + 1];
-                        cx[n] = lo.x;
-                        cy[n] = lo.y;
-                        cz[n] = hi.x;
-                        cw[n] = hi.y;
+                // Units of 16 TMEM lanes x 16 query columns (tcgen05.ld 16x256b.x2: 8 registers).  The load of the next
+                // unit is in flight while the current one is filtered: the TMEM read latency, which bounded the 32-column
+                // version, hides behind the arithmetic.  Registers 4n + {0,1}: row tr + 16 lh, columns 8n + 2 tc + {0,1};
+                // 4n + {2,3}: the row 8 further down.
+                constexpr int kUnits = (kColsPerWarp / 16) * 2;
+                const uint32_t taddr0 = tmem_base + ((uint32_t)(qd * 32) << 16) + acc_s * kTN + part * kColsPerWarp;
+                uint64_t cx[2], cy[2], cz[2], cw[2];
+                auto process = [&](const uint32_t (&v)[8], const int lh, const int colbase) {
+                    if (p.dbg == 1) {
+                        if (v[0] == 0xFFFFFFFFu && v[7] == 0xFFFFFFFEu) p.cand_cnt[0] = 0;
+                        return;
                     }
+                    const float bpA = r_bp[2 * lh], cpA = r_cp[2 * lh], BpA = r_Bp[2 * lh];
+                    const float bpB = r_bp[2 * lh + 1], cpB = r_cp[2 * lh + 1], BpB = r_Bp[2 * lh + 1];
+                    if constexpr (MODE == MODE_FILTER) {
+                        // a side-effect-free test first (four independent predicate chains); the rare emission code
+                        // runs only in the threads that have a hit
+                        bool any0 = false, any1 = false, any2 = false, any3 = false;
+                        const uint64_t bpA2 = pack2(bpA, bpA), cpA2 = pack2(cpA, cpA), BpA2 = pack2(BpA, BpA);
+                        const uint64_t bpB2 = pack2(bpB, bpB), cpB2 = pack2(cpB, cpB), BpB2 = pack2(BpB, BpB);
 #pragma unroll
-                    for (int lh = 0; lh < 2; lh++) {
-                        uint32_t v[16];
-                        tc_ld_16x256b_x4(tmem_base + ((uint32_t)(qd * 32 + lh * 16) << 16) + acc_s * kTN + colbase, v);
-                        tc_ld_wait();
-                        if (p.dbg == 1) {
-                            if (v[0] == 0xFFFFFFFFu && v[15] == 0xFFFFFFFEu) p.cand_cnt[0] = 0;
-                            continue;
+                        for (int n = 0; n < 2; n++) {  // columns (tau', -A', -e', 2^23*8 - m) / 8, two at a time
+                            float TA0, TA1, TB0, TB1;
+                            unpack2(fma2(cx[n], bpA2, fma2(cy[n], cpA2, fma2(cz[n], BpA2, cw[n]))), TA0, TA1);
+                            unpack2(fma2(cx[n], bpB2, fma2(cy[n], cpB2, fma2(cz[n], BpB2, cw[n]))), TB0, TB1);
+                            any0 = any0 || (dot_as_f8(v[4 * n + 0]) >= TA0);
+                            any1 = any1 || (dot_as_f8(v[4 * n + 1]) >= TA1);
+                            any2 = any2 || (dot_as_f8(v[4 * n + 2]) >= TB0);
+                            any3 = any3 || (dot_as_f8(v[4 * n + 3]) >= TB1);
                         }
-                        // registers 4n + {0,1}: row tr + 16 lh, columns 8n + 2 tc + {0,1}; 4n + {2,3}: row + 8
-                        const float bpA = r_bp[2 * lh], cpA = r_cp[2 * lh], BpA = r_Bp[2 * lh];
-                        const float bpB = r_bp[2 * lh + 1], cpB = r_cp[2 * lh + 1], BpB = r_Bp[2 * lh + 1];
-                        if constexpr (MODE == MODE_FILTER) {
-                            // a side-effect-free test first (four independent predicate chains); the rare emission code
-                            // runs only in the threads that have a hit
-                            bool any0 = false, any1 = false, any2 = false, any3 = false;
-                            const uint64_t bpA2 = pack2(bpA, bpA), cpA2 = pack2(cpA, cpA), BpA2 = pack2(BpA, BpA);
-                            const uint64_t bpB2 = pack2(bpB, bpB), cpB2 = pack2(cpB, cpB), BpB2 = pack2(BpB, BpB);
+                        if (any0 || any1 || any2 || any3) {
 #pragma unroll
-                            for (int n = 0; n < 4; n++) {  // columns (tau', -A', -e', 2^23*8 - m) / 8, two at a time
-                                float TA0, TA1, TB0, TB1;
-                                unpack2(fma2(cx[n], bpA2, fma2(cy[n], cpA2, fma2(cz[n], BpA2, cw[n]))), TA0, TA1);
-                                unpack2(fma2(cx[n], bpB2, fma2(cy[n], cpB2, fma2(cz[n], BpB2, cw[n]))), TB0, TB1);
-                                any0 = any0 || (dot_as_f8(v[4 * n + 0]) >= TA0);
-                                any1 = any1 || (dot_as_f8(v[4 * n + 1]) >= TA1);
-                                any2 = any2 || (dot_as_f8(v[4 * n + 2]) >= TB0);
-                                any3 = any3 || (dot_as_f8(v[4 * n + 3]) >= TB1);
-                            }
-                            if (any0 || any1 || any2 || any3) {
+                            for (int n = 0; n < 2; n++) {
+                                float T[4];
+                                unpack2(fma2(cx[n], bpA2, fma2(cy[n], cpA2, fma2(cz[n], BpA2, cw[n]))), T[0], T[1]);
+                                unpack2(fma2(cx[n], bpB2, fma2(cy[n], cpB2, fma2(cz[n], BpB2, cw[n]))), T[2], T[3]);
 #pragma unroll
-                                for (int n = 0; n < 4; n++) {
-                                    float T[4];
-                                    unpack2(fma2(cx[n], bpA2, fma2(cy[n], cpA2, fma2(cz[n], BpA2, cw[n]))), T[0], T[1]);
-                                    unpack2(fma2(cx[n], bpB2, fma2(cy[n], cpB2, fma2(cz[n], BpB2, cw[n]))), T[2], T[3]);
-#pragma unroll
-                                    for (int c = 0; c < 4; c++) {
-                                        if (dot_as_f8(v[4 * n + c]) >= T[c]) {
-                                            const uint32_t q = qt * kTN + colbase + 8 * n + 2 * tc + (c & 1);
-                                            const unsigned int pos = atomicAdd(p.cand_cnt + q, 1u);
-                                            if (pos < p.cand_per_q)
-                                                p.cand_rowdot[(size_t)q * p.cand_per_q + pos] =
-                                                    make_uint2(row_base + 16 * lh + ((c & 2) ? 8 : 0), v[4 * n + c]);
-                                        }
-                                    }
-                                }
-                            }
-                        } else {
-                            // maximum per query column over the 16 rows of this load (8 groups per store tile)
-                            const float ninf = __int_as_float(0xFF800000);
-#pragma unroll
-                            for (int n = 0; n < 4; n++) {
-#pragma unroll
-                                for (int c = 0; c < 2; c++) {
-                                    float xs[2], ys[2], zs[2];  // (aq, A', e'); r_bp holds 1/bp (NaN: skip the row)
-                                    unpack2(cx[n], xs[0], xs[1]);
-                                    unpack2(cy[n], ys[0], ys[1]);
-                                    unpack2(cz[n], zs[0], zs[1]);
-                                    float sa = fmaf(ys[c], cpA, fmaf(zs[c], BpA, dot_approx(v[4 * n + c]))) * (xs[c] * bpA);
-                                    float sb = fmaf(ys[c], cpB, fmaf(zs[c], BpB, dot_approx(v[4 * n + 2 + c]))) * (xs[c] * bpB);
-                                    if (!(sa == sa)) sa = ninf;
-                                    if (!(sb == sb)) sb = ninf;
-                                    float mx = fmaxf(sa, sb);
-                                    mx = fmaxf(mx, __shfl_xor_sync(0xFFFFFFFFu, mx, 4));
-                                    mx = fmaxf(mx, __shfl_xor_sync(0xFFFFFFFFu, mx, 8));
-                                    mx = fmaxf(mx, __shfl_xor_sync(0xFFFFFFFFu, mx, 16));
-                                    if (tr == 0) {
-                                        const uint32_t q = qt * kTN + colbase + 8 * n + 2 * tc + c;
-                                        p.gmax[(size_t)q * p.G + (size_t)i * 8 + qd * 2 + lh] = mx;
+                                for (int c = 0; c < 4; c++) {
+                                    if (dot_as_f8(v[4 * n + c]) >= T[c]) {
+                                        const uint32_t q = qt * kTN + colbase + 8 * n + 2 * tc + (c & 1);
+                                        const unsigned int pos = atomicAdd(p.cand_cnt + q, 1u);
+                                        if (pos < p.cand_per_q)
+                                            p.cand_rowdot[(size_t)q * p.cand_per_q + pos] =
+                                                make_uint2(row_base + 16 * lh + ((c & 2) ? 8 : 0), v[4 * n + c]);
                                     }
                                 }
                             }
                         }
+                    } else {
+                        // maximum per query column over the 16 rows of this unit (8 groups per store tile)
+                        const float ninf = __int_as_float(0xFF800000);
+#pragma unroll
+                        for (int n = 0; n < 2; n++) {
+#pragma unroll
+                            for (int c = 0; c < 2; c++) {
+                                float xs[2], ys[2], zs[2];  // (aq, A', e'); r_bp holds 1/bp (NaN: skip the row)
+                                unpack2(cx[n], xs[0], xs[1]);
+                                unpack2(cy[n], ys[0], ys[1]);
+                                unpack2(cz[n], zs[0], zs[1]);
+                                float sa = fmaf(ys[c], cpA, fmaf(zs[c], BpA, dot_approx(v[4 * n + c]))) * (xs[c] * bpA);
+                                float sb = fmaf(ys[c], cpB, fmaf(zs[c], BpB, dot_approx(v[4 * n + 2 + c]))) * (xs[c] * bpB);
+                                if (!(sa == sa)) sa = ninf;
+                                if (!(sb == sb)) sb = ninf;
+                                float mx = fmaxf(sa, sb);
+                                mx = fmaxf(mx, __shfl_xor_sync(0xFFFFFFFFu, mx, 4));
+                                mx = fmaxf(mx, __shfl_xor_sync(0xFFFFFFFFu, mx, 8));
+                                mx = fmaxf(mx, __shfl_xor_sync(0xFFFFFFFFu, mx, 16));
+                                if (tr == 0) {
+                                    const uint32_t q = qt * kTN + colbase + 8 * n + 2 * tc + c;
+                                    p.gmax[(size_t)q * p.G + (size_t)i * 8 + qd * 2 + lh] = mx;
+                                }
+                            }
+                        }
+                    }
+                };
+                if (p.dbg < 2) {
+                    uint32_t va[8], vb[8];
+                    tc_ld_16x256b_x2(taddr0, va);
+#pragma unroll 1
+                    for (int g = 0; g < kUnits / 2; g++) {  // a group = 16 columns: unit 2g (lanes 0-15), 2g+1 (16-31)
+                        const int colbase = part * kColsPerWarp + g * 16;
+                        // this thread's column pairs 4n + tc of the group: (x0,x1), (y0,y1), (z0,z1), (w0,w1) each
+                        const ulonglong2 *qc = reinterpret_cast<const ulonglong2 *>(q_consts + acc_s * kTN + colbase + 2 * tc);
+#pragma unroll
+                        for (int n = 0; n < 2; n++) {
+                            const ulonglong2 lo = qc[8 * n], hi = qc[8 * n + 1];
+                            cx[n] = lo.x;
+                            cy[n] = lo.y;
+                            cz[n] = hi.x;
+                            cw[n] = hi.y;
+                        }
+                        tc_ld_wait8(va);
+                        tc_ld_16x256b_x2(taddr0 + (16u << 16) + (uint32_t)(g * 16), vb);
+                        process(va, 0, colbase);
+                        tc_ld_wait8(vb);
+                        if (g + 1 < kUnits / 2) tc_ld_16x256b_x2(taddr0 + (uint32_t)((g + 1) * 16), va);
+                        process(vb, 1, colbase);
                     }
                 }
                 tc_fence_before();
