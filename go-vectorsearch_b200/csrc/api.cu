@@ -126,6 +126,7 @@ extern "C" void vs_ctx_destroy(vs_ctx *c) {
     if (c->d_tickets) cudaFree(c->d_tickets);
     if (c->d_trace) cudaFree(c->d_trace);
     if (c->aux) cudaFree(c->aux);
+    if (c->h_flags) cudaFreeHost(c->h_flags);
     for (cudaEvent_t e : c->prof_events) cudaEventDestroy(e);
     for (cudaEvent_t e : c->phase_ev)
         if (e) cudaEventDestroy(e);
@@ -703,6 +704,8 @@ extern "C" int vs_dot_1xN(vs_ctx *c, const uint8_t *q, size_t q_bytes, const vs_
 // argmax MxN
 static size_t g_argmax_gemm_min_centroids = 256;  // from here on the tensor cores beat the dp4a scan (vs_debug_set_argmax_gemm_min)
 constexpr size_t kArgmaxGemmMinRows = 1024;
+constexpr size_t kKMeansScanCentroids = 64;        // up to here the centroid update walks the assignment instead of sorting it
+constexpr size_t kArgmaxInlineFixCentroids = 64;  // up to here the literal-arithmetic kernel is enqueued without asking the host
 static int argmax_gemm_dev(vs_ctx *c, const MatView &cent, const MatView &data, int32_t *d_idx, float *d_sims, bool *done);
 
 static int argmax_dev(vs_ctx *c, Arena &a, const MatView &cent, const MatView &data, int32_t *d_idx, float *d_sims) {
@@ -718,6 +721,15 @@ static int argmax_dev(vs_ctx *c, Arena &a, const MatView &cent, const MatView &d
     CU(cudaMemsetAsync(d_count, 0, sizeof(unsigned int), c->stream));
     LAUNCH(c, launch_canonical_rows(cent, d_canon, c->stream));
     LAUNCH(c, launch_argmax(cent, data, d_canon, d_idx, d_sims, d_work, d_count, g_sm_count, c->stream));
+    if (M <= kArgmaxInlineFixCentroids) {
+        // few centroids (the reference's own shapes): the literal-arithmetic kernel is enqueued unconditionally -- it
+        // reads the worklist length on the device and does nothing when it is zero -- so the call never waits for the
+        // host (k-means iterations stay back to back on the stream)
+        double *d_cn = a.take<double>(M * (size_t)cent.d);
+        LAUNCH(c, launch_query_normalize(cent, d_cn, c->stream, d_count));
+        LAUNCH(c, launch_argmax_fix(cent, data, d_cn, d_idx, d_sims, d_work, d_count, g_sm_count, c->stream));
+        return VS_OK;
+    }
     unsigned int cnt = 0;
     CU(cudaMemcpyAsync(&cnt, d_count, sizeof(cnt), cudaMemcpyDeviceToHost, c->stream));
     CU(cudaStreamSynchronize(c->stream));
@@ -734,7 +746,9 @@ static int argmax_dev(vs_ctx *c, Arena &a, const MatView &cent, const MatView &d
     }
     return VS_OK;
 }
-static size_t argmax_bytes(size_t M, size_t n) { return Arena::pad(M * 4) + Arena::pad(n * 4) + 1024; }
+static size_t argmax_bytes(size_t M, size_t n, size_t d) {
+    return Arena::pad(M * 4) + Arena::pad(n * 4) + (M <= kArgmaxInlineFixCentroids ? Arena::pad(M * d * 8) : 0) + 1024;
+}
 
 static int argmax_check(const vs_matrix *cent, const vs_matrix *data) {
     if (!cent || !data) return fail(VS_EINVAL, "null matrix");
@@ -748,7 +762,7 @@ extern "C" int vs_argmax_MxN_dev(vs_ctx *c, const vs_matrix *cent, const vs_matr
     if (!c || !d_idx_out) return fail(VS_EINVAL, "null argument");
     VS(argmax_check(cent, data));
     Arena a(c);
-    VS(a.reserve(argmax_bytes(cent->n, data->n)));
+    VS(a.reserve(argmax_bytes(cent->n, data->n, (size_t)cent->d)));
     return argmax_dev(c, a, cent->view(), data->view(), d_idx_out, nullptr);
 }
 
@@ -758,7 +772,7 @@ extern "C" int vs_argmax_MxN(vs_ctx *c, const vs_matrix *cent, const vs_matrix *
     VS(argmax_check(cent, data));
     const size_t n = data->n;
     Arena a(c);
-    VS(a.reserve(argmax_bytes(cent->n, n) + 2 * Arena::pad(n * 4) + 1024));
+    VS(a.reserve(argmax_bytes(cent->n, n, (size_t)cent->d) + 2 * Arena::pad(n * 4) + 1024));
     int32_t *d_idx = a.take<int32_t>(n);
     float *d_sims = sims_out ? a.take<float>(n) : nullptr;
     VS(argmax_dev(c, a, cent->view(), data->view(), d_idx, d_sims));
@@ -1676,7 +1690,7 @@ extern "C" int vs_kmeans_step(vs_ctx *c, const vs_matrix *data, const uint8_t *c
     if (k == 0) return fail(VS_EEMPTY, "matrix rows are empty");
     const size_t n = data->n, d = data->d, rb = 8 + d;
     Arena a(c);
-    VS(a.reserve(temp_matrix_bytes(k, rb) + argmax_bytes(k, n) + 4 * Arena::pad(n * 4) + Arena::pad((k + 1) * 4) +
+    VS(a.reserve(temp_matrix_bytes(k, rb) + argmax_bytes(k, n, d) + 4 * Arena::pad(n * 4) + Arena::pad((k + 1) * 4) +
                  Arena::pad(k * d * 4) + Arena::pad(k * 8) + Arena::pad(k * rb) + 8192));
     MatView cv;
     VS(temp_matrix(c, a, centroids, k, rb, &cv));
@@ -1689,13 +1703,17 @@ extern "C" int vs_kmeans_step(vs_ctx *c, const vs_matrix *data, const uint8_t *c
     uint8_t *d_newc = a.take<uint8_t>(k * rb);
     // k_means.go:73-77: nearest centroid of every row
     VS(argmax_dev(c, a, cv, data->view(), d_assign, nullptr));
-    // member lists in ascending row order (stable sort by centroid index)
-    VS(sort_rows_by_key(c, reinterpret_cast<const uint32_t *>(d_assign), n, bits_for(k), d_order, d_sorted));
-    lower_bound_kernel<<<(unsigned)((k + 1 + 255) / 256), 256, 0, c->stream>>>(d_sorted, n, nullptr, d_segoff, k);
-    c->launches++;
     CU(cudaMemcpyAsync(d_means, means, k * d * 4, cudaMemcpyHostToDevice, c->stream));
     // k_means.go:80-96 accumulate + mean, :99 requantize
-    LAUNCH(c, launch_kmeans_accumulate(data->view(), d_order, d_segoff, (int)k, d_means, d_counts, c->stream));
+    if (k <= kKMeansScanCentroids) {
+        LAUNCH(c, launch_kmeans_accumulate_scan(data->view(), d_assign, (int)k, d_means, d_counts, c->stream));
+    } else {
+        // member lists in ascending row order (stable sort by centroid index)
+        VS(sort_rows_by_key(c, reinterpret_cast<const uint32_t *>(d_assign), n, bits_for(k), d_order, d_sorted));
+        lower_bound_kernel<<<(unsigned)((k + 1 + 255) / 256), 256, 0, c->stream>>>(d_sorted, n, nullptr, d_segoff, k);
+        c->launches++;
+        LAUNCH(c, launch_kmeans_accumulate(data->view(), d_order, d_segoff, (int)k, d_means, d_counts, c->stream));
+    }
     LAUNCH(c, launch_quantize_f32(d_means, k, (int)d, d_newc, c->stream));
     std::vector<int32_t> tmp;
     if (assign_out) {
@@ -1744,76 +1762,121 @@ extern "C" int vs_kmeans(vs_ctx *c, const vs_matrix *data, size_t k, const uint6
         if (superset_rows[i] >= n) return fail(VS_EINVAL, "superset row %llu >= n", (unsigned long long)superset_rows[i]);
         rows32[i] = (uint32_t)superset_rows[i];
     }
+    // few centroids over a store small enough to copy once per iteration (the reference's sampled shapes)
+    const bool use_ring = ks <= kKMeansScanCentroids && kmeans_ring_supported((int)d_pad) && n * d_pad <= (size_t(512) << 20);
     Arena a(c);
     const size_t soa = Arena::pad(ks * d_pad) + 2 * Arena::pad(ks * 8);
-    VS(a.reserve(2 * soa + Arena::pad(ks * 4) + argmax_bytes(ks, n) + 3 * Arena::pad(n * 4) + Arena::pad((ks + 1) * 4) +
-                 Arena::pad(ks * d * 4) + Arena::pad(ks * 8) + Arena::pad(k * rb) + sort_rows_ws_bytes(n) + 8192));
+    VS(a.reserve(2 * soa + Arena::pad(ks * 4) + argmax_bytes(ks, n, d) + 3 * Arena::pad(n * 4) + Arena::pad((ks + 1) * 4) +
+                 2 * Arena::pad(ks * d * 4) + Arena::pad(ks * 8) + Arena::pad(k * rb) + sort_rows_ws_bytes(n) +
+                 (use_ring ? kmeans_ring_scratch_bytes(n, (int)ks, (int)d_pad) : 0) + soa + 8192));
     struct Soa {
         uint8_t *codes;
         float2 *hdr;
         uint2 *sums;
-    } cur, nxt;
-    cur.codes = a.take<uint8_t>(ks * d_pad);
-    cur.hdr = a.take<float2>(ks);
-    cur.sums = a.take<uint2>(ks);
-    nxt.codes = a.take<uint8_t>(ks * d_pad);
-    nxt.hdr = a.take<float2>(ks);
-    nxt.sums = a.take<uint2>(ks);
+    } buf[3];
+    for (int i = 0; i < 3; i++) {
+        buf[i].codes = a.take<uint8_t>(ks * d_pad);
+        buf[i].hdr = a.take<float2>(ks);
+        buf[i].sums = a.take<uint2>(ks);
+    }
     uint32_t *d_rows = a.take<uint32_t>(ks);
     int32_t *d_assign = a.take<int32_t>(n);
     uint32_t *d_order = a.take<uint32_t>(n);
     uint32_t *d_sorted = a.take<uint32_t>(n);
     uint32_t *d_segoff = a.take<uint32_t>(ks + 1);
-    float *d_means = a.take<float>(ks * d);
+    float *d_means2[2] = {a.take<float>(ks * d), a.take<float>(ks * d)};
     int64_t *d_counts = a.take<int64_t>(ks);
     uint8_t *d_out = a.take<uint8_t>(k * rb);
     int *d_flag = a.take<int>(16);
     const size_t sort_ws_bytes = sort_rows_ws_bytes(n);
     char *d_sort_ws = a.take<char>(sort_ws_bytes);
+    char *d_ring = use_ring ? a.take<char>(kmeans_ring_scratch_bytes(n, (int)ks, (int)d_pad)) : nullptr;
     CU(cudaMemcpyAsync(d_rows, rows32.data(), ks * 4, cudaMemcpyHostToDevice, c->stream));
-    CU(cudaMemsetAsync(nxt.codes, 0, ks * d_pad, c->stream));  // the padding columns stay zero
-    LAUNCH(c, launch_gather_rows(data->view(), d_rows, ks, cur.codes, cur.hdr, cur.sums, nullptr, 0, nullptr, c->stream));
-    CU(cudaMemsetAsync(d_means, 0, ks * d * 4, c->stream));     // k_means.go:60-65
-    VS(pinned_reserve(c, 64));
-    for (int i = 0; i < 4; i++)
-        if (!c->phase_ev[i]) CU(cudaEventCreate(&c->phase_ev[i]));
+    for (int i = 0; i < 3; i++) CU(cudaMemsetAsync(buf[i].codes, 0, ks * d_pad, c->stream));  // the padding columns stay zero
+    LAUNCH(c, launch_gather_rows(data->view(), d_rows, ks, buf[0].codes, buf[0].hdr, buf[0].sums, nullptr, 0, nullptr, c->stream));
+    CU(cudaMemsetAsync(d_means2[0], 0, ks * d * 4, c->stream));  // k_means.go:60-65
+    CU(cudaMemsetAsync(d_means2[1], 0, ks * d * 4, c->stream));
+    if (!c->h_flags) CU(cudaMallocHost(&c->h_flags, 64));  // not c->pinned: the assignment inside an iteration uses that
+    volatile int *h_flag = c->h_flags;
+    // per-slot events: start, assign done, iteration done (the flag of that iteration is on the host)
+    cudaEvent_t ev[2][3];
+    for (int sl = 0; sl < 2; sl++)
+        for (int j = 0; j < 3; j++) CU(cudaEventCreate(&ev[sl][j]));
     int64_t iters[2] = {0, 0};
     double ms_assign = 0, ms_update = 0;
-    for (int phase = 0; phase < 2; phase++) {
-        const size_t m = phase == 0 ? ks : k;
-        bool conv = false;
-        for (size_t it = 0; it < iter_limit && !conv; it++) {
-            const MatView cv{cur.codes, cur.hdr, cur.sums, m, (int)d, (int)d_pad};
-            CU(cudaEventRecord(c->phase_ev[0], c->stream));
-            const size_t mark = a.off;
-            VS(argmax_dev(c, a, cv, data->view(), d_assign, nullptr));  // :73-77
-            a.off = mark;
-            CU(cudaEventRecord(c->phase_ev[1], c->stream));
+    // One Lloyd iteration, fully asynchronous: in -> out, means mi -> mo, convergence flag to h_flag[slot].
+    auto enqueue = [&](const Soa &in, const Soa &out, const float *mi, float *mo, size_t m, int slot) -> int {
+        const MatView cv{in.codes, in.hdr, in.sums, m, (int)d, (int)d_pad};
+        CU(cudaEventRecord(ev[slot][0], c->stream));
+        const size_t mark = a.off;
+        VS(argmax_dev(c, a, cv, data->view(), d_assign, nullptr));  // :73-77
+        a.off = mark;
+        CU(cudaEventRecord(ev[slot][1], c->stream));
+        if (use_ring) {  // few centroids: member rows made contiguous, then streamed through a shared-memory ring
+            LAUNCH(c, launch_kmeans_accumulate_ring(data->view(), d_assign, (int)m, mo, d_counts, mi, d_ring, c->stream));  // :80-96
+            c->launches += 3;
+        } else if (m <= kKMeansScanCentroids) {  // (rows too many to copy) members found by walking the assignment
+            LAUNCH(c, launch_kmeans_accumulate_scan(data->view(), d_assign, (int)m, mo, d_counts, c->stream, mi));
+        } else {
             VS(sort_rows_by_key(c, reinterpret_cast<const uint32_t *>(d_assign), n, bits_for(m), d_order, d_sorted, d_sort_ws,
                                 sort_ws_bytes));
             lower_bound_kernel<<<(unsigned)((m + 1 + 255) / 256), 256, 0, c->stream>>>(d_sorted, n, nullptr, d_segoff, m);
             c->launches++;
-            LAUNCH(c, launch_kmeans_accumulate(data->view(), d_order, d_segoff, (int)m, d_means, d_counts, c->stream));  // :80-96
-            LAUNCH(c, launch_quantize_f32_soa(d_means, m, (int)d, nxt.codes, (int)d_pad, nxt.hdr, nxt.sums, c->stream));  // :99
-            CU(cudaMemsetAsync(d_flag, 0, sizeof(int), c->stream));
-            codes_differ_kernel<<<g_sm_count * 4, 256, 0, c->stream>>>(cur.codes, nxt.codes, m, (int)d, (int)d_pad, d_flag);  // :102-108
-            c->launches++;
-            CU(cudaEventRecord(c->phase_ev[2], c->stream));
-            int *h_flag = static_cast<int *>(c->pinned);
-            CU(cudaMemcpyAsync(h_flag, d_flag, sizeof(int), cudaMemcpyDeviceToHost, c->stream));
-            CU(cudaStreamSynchronize(c->stream));
-            conv = *h_flag == 0;
+            LAUNCH(c, launch_kmeans_accumulate(data->view(), d_order, d_segoff, (int)m, mo, d_counts, c->stream, mi));  // :80-96
+        }
+        LAUNCH(c, launch_quantize_f32_soa(mo, m, (int)d, out.codes, (int)d_pad, out.hdr, out.sums, c->stream));     // :99
+        CU(cudaMemsetAsync(d_flag + slot, 0, sizeof(int), c->stream));
+        codes_differ_kernel<<<g_sm_count * 4, 256, 0, c->stream>>>(in.codes, out.codes, m, (int)d, (int)d_pad, d_flag + slot);  // :102-108
+        c->launches++;
+        CU(cudaMemcpyAsync(const_cast<int *>(h_flag) + slot, d_flag + slot, sizeof(int), cudaMemcpyDeviceToHost, c->stream));
+        CU(cudaEventRecord(ev[slot][2], c->stream));
+        return VS_OK;
+    };
+    // The loop of k_means.go:67-117 / :157-207.  Whether iteration i converged is known only on the host; iteration i+1
+    // is enqueued before that answer arrives (its inputs are iteration i's outputs either way) so the device never waits
+    // for the round trip.  Three centroid buffers and two mean buffers keep iteration i's results intact when the
+    // speculative iteration turns out to be one too many: it is simply ignored.
+    Soa in = buf[0], out = buf[1], spare = buf[2];
+    float *mi = d_means2[0], *mo = d_means2[1];
+    int rc = VS_OK;
+    for (int phase = 0; phase < 2 && rc == VS_OK; phase++) {
+        const size_t m = phase == 0 ? ks : k;
+        if (iter_limit == 0) break;
+        int slot = 0;
+        rc = enqueue(in, out, mi, mo, m, slot);
+        for (size_t it = 0; rc == VS_OK; it++) {
+            const bool can_next = it + 1 < iter_limit;
+            if (can_next) rc = enqueue(out, spare, mo, mi, m, slot ^ 1);
+            if (rc != VS_OK) break;
+            if (cudaEventSynchronize(ev[slot][2]) != cudaSuccess) {
+                rc = fail(VS_ECUDA, "k-means: event sync");
+                break;
+            }
+            const bool conv = h_flag[slot] == 0;
             float t0 = 0.f, t1 = 0.f;
-            CU(cudaEventElapsedTime(&t0, c->phase_ev[0], c->phase_ev[1]));
-            CU(cudaEventElapsedTime(&t1, c->phase_ev[1], c->phase_ev[2]));
+            cudaEventElapsedTime(&t0, ev[slot][0], ev[slot][1]);
+            cudaEventElapsedTime(&t1, ev[slot][1], ev[slot][2]);
             ms_assign += t0;
             ms_update += t1;
-            const Soa t = cur;
-            cur = nxt;
-            nxt = t;
             iters[phase]++;
+            // this iteration's output becomes the next input (or the result)
+            const Soa done_in = in;
+            in = out;
+            out = spare;
+            spare = done_in;
+            float *t = mi;
+            mi = mo;
+            mo = t;
+            slot ^= 1;
+            if (conv || !can_next) break;
         }
+        // `in` / `mi` now hold the phase's result; a speculative iteration may still be writing `out` / `mo`, in stream
+        // order before anything enqueued below
     }
+    for (int sl = 0; sl < 2; sl++)
+        for (int j = 0; j < 3; j++) cudaEventDestroy(ev[sl][j]);
+    VS(rc);
+    const Soa cur = in;
     const MatView fin{cur.codes, cur.hdr, cur.sums, k, (int)d, (int)d_pad};
     LAUNCH(c, launch_export(fin, 0, k, d_out, c->stream));
     CU(cudaMemcpyAsync(centroids_out, d_out, k * rb, cudaMemcpyDeviceToHost, c->stream));
@@ -2015,7 +2078,7 @@ extern "C" int vs_matrix_split(vs_ctx *c, const vs_matrix *src, const uint8_t *c
     int rc;
     {
         Arena a(c);
-        rc = a.reserve(temp_matrix_bytes(k, rb) + argmax_bytes(k, n) + 4096);
+        rc = a.reserve(temp_matrix_bytes(k, rb) + argmax_bytes(k, n, rb - 8) + 4096);
         MatView cv;
         if (rc == VS_OK) rc = temp_matrix(c, a, centroids, k, rb, &cv);
         if (rc == VS_OK) rc = argmax_dev(c, a, cv, src->view(), d_assign, nullptr);
@@ -2039,7 +2102,7 @@ extern "C" int vs_reassign_recenter(vs_ctx *c, const vs_matrix *data, const uint
     int rc;
     {
         Arena a(c);
-        rc = a.reserve(temp_matrix_bytes(k, rb) + argmax_bytes(k, n) + 4096);
+        rc = a.reserve(temp_matrix_bytes(k, rb) + argmax_bytes(k, n, rb - 8) + 4096);
         MatView cv;
         if (rc == VS_OK) rc = temp_matrix(c, a, centroids, k, rb, &cv);
         if (rc == VS_OK) rc = argmax_dev(c, a, cv, data->view(), d_assign, nullptr);

@@ -20,6 +20,7 @@ struct vs_ctx {
     void *pinned = nullptr;
     size_t pinned_cap = 0;
     bool owns_stream = true;
+    int *h_flags = nullptr;   // small pinned block of its own for flags read while other calls use `pinned`
     void *aux = nullptr;      // second device buffer (tensor-core assignment): lives beside the arena, grown on demand
     size_t aux_cap = 0;
     unsigned long long *d_fix_counter = nullptr;  // in-kernel literal re-scores (device)
@@ -109,7 +110,8 @@ constexpr uint32_t kStatusNeedMore = 4u;
 cudaError_t launch_stage(const StageParams &p, int kpl, bool exact, int grid_blocks, cudaStream_t st);
 int stage_lanes_per_row(int d_pad);
 int stage_cap(int kpl);
-cudaError_t launch_query_normalize(const MatView &queries, double *qnorm, cudaStream_t st);
+cudaError_t launch_query_normalize(const MatView &queries, double *qnorm, cudaStream_t st,
+                                   const unsigned int *only_if_nonzero = nullptr);
 cudaError_t launch_cosine_1xN(const MatView &rows, const MatView &query, float *sims, uint32_t *dots,
                               uint32_t *worklist, unsigned int *work_count, int sm_count, cudaStream_t st);
 cudaError_t launch_cosine_fix(const MatView &rows, const double *qnorm, float *sims, const uint32_t *worklist,
@@ -193,7 +195,13 @@ cudaError_t launch_canonical_rows(const MatView &m, uint32_t *canon, cudaStream_
 
 // kmeans.cu
 cudaError_t launch_kmeans_accumulate(const MatView &data, const uint32_t *order, const uint32_t *seg_off, int k,
-                                     float *means, int64_t *counts, cudaStream_t st);
+                                     float *means, int64_t *counts, cudaStream_t st, const float *means_prev = nullptr);
+cudaError_t launch_kmeans_accumulate_scan(const MatView &data, const int32_t *assign, int k, float *means, int64_t *counts,
+                                          cudaStream_t st, const float *means_prev = nullptr);
+bool kmeans_ring_supported(int d_pad);
+size_t kmeans_ring_scratch_bytes(size_t n, int k, int d_pad);
+cudaError_t launch_kmeans_accumulate_ring(const MatView &data, const int32_t *assign, int k, float *means, int64_t *counts,
+                                          const float *means_prev, void *scratch, cudaStream_t st);
 cudaError_t launch_kmeans_accumulate_relay(const MatView &data, const uint32_t *order, const uint32_t *seg_off, int k,
                                            float *sums, int64_t *counts, cudaStream_t st);
 cudaError_t launch_kmeans_finalize(const float *sums, const int64_t *counts, size_t k, int d, float *means, cudaStream_t st);

@@ -25,6 +25,48 @@ __device__ __forceinline__ float byte_over_255(uint32_t word, int k) {
     return __fmaf_rn(e, rcp, r);
 }
 
+// Two codes at a time with Blackwell's packed float32 pairs (add/mul/fma .rn.f32x2: IEEE per half, so the bits are those
+// of the scalar sequence): (lo, hi) = dequantized values of bytes k and k+1 of `word`, added onto the running pair.
+__device__ __forceinline__ uint64_t km_pack(float lo, float hi) {
+    uint64_t r;
+    asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(lo), "f"(hi));
+    return r;
+}
+__device__ __forceinline__ uint64_t km_add2(uint64_t a, uint64_t b) {
+    uint64_t d;
+    asm("add.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b));
+    return d;
+}
+__device__ __forceinline__ uint64_t km_mul2(uint64_t a, uint64_t b) {
+    uint64_t d;
+    asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b));
+    return d;
+}
+__device__ __forceinline__ uint64_t km_fma2(uint64_t a, uint64_t b, uint64_t c) {
+    uint64_t d;
+    asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(d) : "l"(a), "l"(b), "l"(c));
+    return d;
+}
+// sum2 += mn + (float32(q)/255) * range for the byte pair (k, k+1) of word; constants pre-packed by the caller
+__device__ __forceinline__ uint64_t km_accumulate_pair(uint64_t sum2, uint32_t word, int k, uint64_t mn2, uint64_t range2,
+                                                       uint64_t neg2p23, uint64_t rcp2, uint64_t neg255, uint64_t one2) {
+    const uint64_t bits = ((uint64_t)__byte_perm(word, 0x4B000000u, 0x7650u + (uint32_t)k + 1u) << 32) |
+                          (uint64_t)__byte_perm(word, 0x4B000000u, 0x7650u + (uint32_t)k);
+    const uint64_t x = km_add2(bits, neg2p23);       // float32(q), exact
+    const uint64_t r = km_mul2(x, rcp2);
+    const uint64_t e = km_fma2(r, neg255, x);        // fma(-r, 255, x) = fma(r, -255, x)
+    const uint64_t q = km_fma2(e, rcp2, r);          // float32(q) / 255.0f, correctly rounded
+    // mn + q*range with the product rounded on its own, as the reference does.  In packed form ptxas contracts the
+    // multiply into the addition (mul.rn.f32x2 + add.rn.f32x2 -> FFMA2, even through fma(product, 1, mn): seen in the
+    // SASS), which changes the bits, so this step stays scalar: mul.rn.f32 / add.rn.f32 are never contracted.
+    float q_lo, q_hi, mn, range, mn_hi, range_hi;
+    asm("mov.b64 {%0, %1}, %2;" : "=f"(q_lo), "=f"(q_hi) : "l"(q));
+    asm("mov.b64 {%0, %1}, %2;" : "=f"(mn), "=f"(mn_hi) : "l"(mn2));
+    asm("mov.b64 {%0, %1}, %2;" : "=f"(range), "=f"(range_hi) : "l"(range2));
+    const uint64_t val = km_pack(__fadd_rn(mn, __fmul_rn(q_lo, range)), __fadd_rn(mn_hi, __fmul_rn(q_hi, range_hi)));
+    return km_add2(sum2, val);
+}
+
 // order[seg_off[c] .. seg_off[c+1]) = rows assigned to centroid c, ascending.
 // RELAY = false: sums start at zero and the mean is written (one device holds every row).
 // RELAY = true: the chains continue from sums[] and the running sums are written back, counts are added to: the rows
@@ -33,7 +75,7 @@ __device__ __forceinline__ float byte_over_255(uint32_t word, int k) {
 template <bool RELAY>
 __global__ void __launch_bounds__(kAccThreads)
 kmeans_accumulate_kernel(MatView data, const uint32_t *__restrict__ order, const uint32_t *__restrict__ seg_off,
-                         float *__restrict__ means, int64_t *__restrict__ counts) {
+                         float *means, int64_t *__restrict__ counts, const float *means_prev) {
     __shared__ uint32_t s_row[kAccChunk];
     __shared__ float2 s_hdr[kAccChunk];
     const int c = blockIdx.x;
@@ -79,6 +121,11 @@ kmeans_accumulate_kernel(MatView data, const uint32_t *__restrict__ order, const
         if (j0 + 1 < data.d) m[j0 + 1] = RELAY ? s1 : __fdiv_rn(s1, n);
         if (j0 + 2 < data.d) m[j0 + 2] = RELAY ? s2 : __fdiv_rn(s2, n);
         if (j0 + 3 < data.d) m[j0 + 3] = RELAY ? s3 : __fdiv_rn(s3, n);
+    } else if (!RELAY && live && means_prev != means) {  // the previous mean carries over into the other buffer
+        float *m = means + (size_t)c * data.d;
+        const float *mp = means_prev + (size_t)c * data.d;
+        for (int t = 0; t < 4; t++)
+            if (j0 + t < data.d) m[j0 + t] = mp[j0 + t];
     }
 }
 
@@ -92,17 +139,313 @@ __global__ void kmeans_finalize_kernel(const float *__restrict__ sums, const int
     }
 }
 
-cudaError_t launch_kmeans_accumulate(const MatView &data, const uint32_t *order, const uint32_t *seg_off, int k,
-                                     float *means, int64_t *counts, cudaStream_t st) {
+// Few centroids (the reference's own shapes: k <= 25): no sort at all.  Block (c, slice) walks the assignment in row
+// order, compacts the rows of centroid c of every 768-row window into shared memory (order kept: a thread owns four
+// consecutive rows, positions come from a block prefix sum) and continues its chains over them.  Reading the whole
+// assignment once per centroid (k x n x 4 B) is nothing next to what a radix sort's launches cost at these sizes.
+constexpr int kScanRowsPerThread = 4;
+constexpr int kScanWindow = kAccThreads * kScanRowsPerThread;
+__global__ void __launch_bounds__(kAccThreads)
+kmeans_accumulate_scan_kernel(MatView data, const int32_t *__restrict__ assign, float *means, int64_t *__restrict__ counts,
+                              const float *means_prev) {
+    __shared__ uint32_t s_row[kScanWindow];
+    __shared__ float2 s_hdr[kScanWindow];
+    __shared__ uint32_t s_wsum[kAccThreads / 32];
+    const int c = blockIdx.x;
+    const int j0 = (blockIdx.y * kAccThreads + threadIdx.x) * 4;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const bool live = j0 < data.d_pad;
+    const size_t n = data.n;
+    float s0 = 0.0f, s1 = 0.0f, s2 = 0.0f, s3 = 0.0f;
+    uint64_t total = 0;
+    for (size_t base = 0; base < n; base += kScanWindow) {
+        const size_t r0 = base + (size_t)threadIdx.x * kScanRowsPerThread;
+        bool hit[kScanRowsPerThread];
+        uint32_t mine = 0;
+#pragma unroll
+        for (int t = 0; t < kScanRowsPerThread; t++) {
+            hit[t] = r0 + t < n && assign[r0 + t] == c;
+            mine += hit[t] ? 1u : 0u;
+        }
+        uint32_t incl = mine;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            const uint32_t x = __shfl_up_sync(0xFFFFFFFFu, incl, o);
+            if (lane >= o) incl += x;
+        }
+        __syncthreads();  // the previous window's rows are consumed
+        if (lane == 31) s_wsum[warp] = incl;
+        __syncthreads();
+        uint32_t pos = incl - mine, cnt = 0;
+#pragma unroll
+        for (int w = 0; w < kAccThreads / 32; w++) {
+            if (w < warp) pos += s_wsum[w];
+            cnt += s_wsum[w];
+        }
+#pragma unroll
+        for (int t = 0; t < kScanRowsPerThread; t++) {
+            if (hit[t]) {
+                s_row[pos] = (uint32_t)(r0 + t);
+                s_hdr[pos] = data.hdr[r0 + t];
+                pos++;
+            }
+        }
+        __syncthreads();
+        total += cnt;
+        if (live) {
+#pragma unroll 8
+            for (uint32_t i = 0; i < cnt; i++) {
+                const uint32_t w = *reinterpret_cast<const uint32_t *>(data.codes + (size_t)s_row[i] * data.d_pad + j0);
+                const float2 h = s_hdr[i];
+                const float range = __fsub_rn(h.y, h.x);
+                s0 = __fadd_rn(s0, __fadd_rn(h.x, __fmul_rn(byte_over_255(w, 0), range)));
+                s1 = __fadd_rn(s1, __fadd_rn(h.x, __fmul_rn(byte_over_255(w, 1), range)));
+                s2 = __fadd_rn(s2, __fadd_rn(h.x, __fmul_rn(byte_over_255(w, 2), range)));
+                s3 = __fadd_rn(s3, __fadd_rn(h.x, __fmul_rn(byte_over_255(w, 3), range)));
+            }
+        }
+    }
+    if (blockIdx.y == 0 && threadIdx.x == 0) counts[c] = (int64_t)total;
+    if (!live) return;
+    float *m = means + (size_t)c * data.d;
+    if (total > 0) {  // :89-96
+        const float nf = (float)(int64_t)total;
+        if (j0 + 0 < data.d) m[j0 + 0] = __fdiv_rn(s0, nf);
+        if (j0 + 1 < data.d) m[j0 + 1] = __fdiv_rn(s1, nf);
+        if (j0 + 2 < data.d) m[j0 + 2] = __fdiv_rn(s2, nf);
+        if (j0 + 3 < data.d) m[j0 + 3] = __fdiv_rn(s3, nf);
+    } else if (means_prev != means) {  // an empty cluster keeps its previous mean
+        const float *mp = means_prev + (size_t)c * data.d;
+        for (int t = 0; t < 4; t++)
+            if (j0 + t < data.d) m[j0 + t] = mp[j0 + t];
+    }
+}
+
+cudaError_t launch_kmeans_accumulate_scan(const MatView &data, const int32_t *assign, int k, float *means, int64_t *counts,
+                                          cudaStream_t st, const float *means_prev) {
     dim3 grid(k, (data.d_pad + kAccThreads * 4 - 1) / (kAccThreads * 4));
-    kmeans_accumulate_kernel<false><<<grid, kAccThreads, 0, st>>>(data, order, seg_off, means, counts);
+    kmeans_accumulate_scan_kernel<<<grid, kAccThreads, 0, st>>>(data, assign, means, counts, means_prev ? means_prev : means);
+    return cudaGetLastError();
+}
+
+// ---- few centroids, many rows each (the reference's shapes: k <= 25 over <= 50 000 sampled rows) -------------------
+// A (centroid, dimension) sum is one dependent chain over ~n/k rows, and with a handful of centroids there are only a
+// handful of blocks: direct loads leave each chain waiting ~1 us of HBM latency for every few rows (measured 1.2 ms per
+// update at 50 000 x 768, 30 GB/s).  So the member rows are first made contiguous per centroid (ordered member lists by
+// walking the assignment, then a row gather at copy speed) and then streamed through a deep shared-memory ring by TMA
+// bulk copies: one block per centroid, a producer thread keeps ~200 KB (8 stages x 32 rows) in flight, the consumer
+// threads run their chains out of shared memory.
+__global__ void kmeans_histogram_kernel(const int32_t *__restrict__ assign, size_t n, int k, uint32_t *__restrict__ counts) {
+    extern __shared__ uint32_t s_cnt[];
+    for (int i = threadIdx.x; i < k; i += blockDim.x) s_cnt[i] = 0;
+    __syncthreads();
+    for (size_t r = blockIdx.x * (size_t)blockDim.x + threadIdx.x; r < n; r += (size_t)gridDim.x * blockDim.x)
+        atomicAdd(&s_cnt[assign[r]], 1u);
+    __syncthreads();
+    for (int i = threadIdx.x; i < k; i += blockDim.x)
+        if (s_cnt[i]) atomicAdd(&counts[i], s_cnt[i]);
+}
+
+// Block c: the rows assigned to centroid c, ascending, written at order[seg_off[c] ..); seg_off from the histogram.
+constexpr int kListThreads = 1024;
+__global__ void __launch_bounds__(kListThreads)
+kmeans_member_lists_kernel(const int32_t *__restrict__ assign, size_t n, int k, const uint32_t *__restrict__ counts,
+                           uint32_t *__restrict__ order, uint32_t *__restrict__ seg_off) {
+    __shared__ uint32_t s_wsum[kListThreads / 32];
+    __shared__ uint32_t s_base;
+    const int c = blockIdx.x;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    if (threadIdx.x == 0) {
+        uint32_t off = 0;
+        for (int i = 0; i < c; i++) off += counts[i];
+        s_base = off;
+        seg_off[c] = off;
+        if (c == k - 1) seg_off[k] = off + counts[c];
+    }
+    __syncthreads();
+    uint32_t base = s_base;
+    for (size_t w0 = 0; w0 < n; w0 += kListThreads) {
+        const size_t r = w0 + threadIdx.x;
+        const bool hit = r < n && assign[r] == c;
+        const unsigned int m = __ballot_sync(0xFFFFFFFFu, hit);
+        __syncthreads();
+        if (lane == 0) s_wsum[warp] = (uint32_t)__popc(m);
+        __syncthreads();
+        uint32_t pos = base + (uint32_t)__popc(m & ((1u << lane) - 1u)), tot = 0;
+        for (int w = 0; w < kListThreads / 32; w++) {
+            if (w < warp) pos += s_wsum[w];
+            tot += s_wsum[w];
+        }
+        if (hit) order[pos] = (uint32_t)r;
+        base += tot;
+    }
+}
+
+constexpr int kRingRows = 32;       // rows per stage
+constexpr int kRingMaxStages = 8;   // as many as fit in ~200 KB of shared memory
+__device__ __forceinline__ uint32_t km_smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void km_mbar_wait(uint32_t bar, uint32_t parity) {
+    uint32_t done;
+    do {
+        asm volatile(
+            "{\n\t.reg .pred p;\n\t"
+            "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+            "selp.u32 %0, 1, 0, p;\n\t}"
+            : "=r"(done)
+            : "r"(bar), "r"(parity)
+            : "memory");
+    } while (!done);
+}
+
+// codes / hdr: the member rows of all centroids, contiguous per centroid in row order (gathered), seg_off[k+1].
+// blockDim = 32 * (consumer warps + 1): thread t < d_pad/4 owns dimensions 4t..4t+3; the last warp is the producer.
+__global__ void __launch_bounds__(288)
+kmeans_accumulate_ring_kernel(const uint8_t *__restrict__ codes, const float2 *__restrict__ hdr, int d, int d_pad,
+                              const uint32_t *__restrict__ seg_off, float *means, int64_t *__restrict__ counts,
+                              const float *means_prev, int consumer_warps, int kRingStages) {
+    extern __shared__ __align__(128) unsigned char ring[];
+    const uint32_t stage_bytes = (uint32_t)kRingRows * d_pad;
+    const uint32_t hdr_stage = (kRingRows + 2) * 8;  // 16-byte aligned source: up to 8 bytes of lead-in
+    unsigned char *s_codes = ring;
+    unsigned char *s_hdr = ring + (size_t)kRingStages * stage_bytes;
+    uint64_t *bars = reinterpret_cast<uint64_t *>(s_hdr + (size_t)kRingStages * hdr_stage);  // full[S], empty[S]
+    const int c = blockIdx.x;
+    const uint32_t beg = seg_off[c], end = seg_off[c + 1];
+    const uint32_t rows = end - beg, groups = (rows + kRingRows - 1) / kRingRows;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    if (threadIdx.x == 0) {
+        for (int i = 0; i < kRingStages; i++) {
+            asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(km_smem_u32(&bars[i])), "r"(1) : "memory");
+            asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(km_smem_u32(&bars[kRingStages + i])), "r"(consumer_warps)
+                         : "memory");
+        }
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        counts[c] = (int64_t)rows;
+    }
+    __syncthreads();
+    if (warp == consumer_warps) {
+        if (lane == 0) {  // producer: keeps kRingStages groups of rows in flight
+            for (uint32_t g = 0; g < groups; g++) {
+                const uint32_t st = g % kRingStages, ph = (g / kRingStages) & 1u;
+                if (g >= (uint32_t)kRingStages) km_mbar_wait(km_smem_u32(&bars[kRingStages + st]), ph ^ 1u);
+                const uint32_t r0 = beg + g * kRingRows, nr = min((uint32_t)kRingRows, end - r0);
+                const uint32_t cb = nr * (uint32_t)d_pad;
+                const uintptr_t hsrc = reinterpret_cast<uintptr_t>(hdr + r0);
+                const uintptr_t hal = hsrc & ~uintptr_t(15);
+                const uint32_t hb = (uint32_t)(((hsrc - hal) + (uintptr_t)nr * 8 + 15) & ~uintptr_t(15));
+                const uint32_t full = km_smem_u32(&bars[st]);
+                asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(full), "r"(cb + hb) : "memory");
+                asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+                                 km_smem_u32(s_codes + (size_t)st * stage_bytes)),
+                             "l"(codes + (size_t)r0 * d_pad), "r"(cb), "r"(full)
+                             : "memory");
+                asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+                                 km_smem_u32(s_hdr + (size_t)st * hdr_stage)),
+                             "l"(reinterpret_cast<const void *>(hal)), "r"(hb), "r"(full)
+                             : "memory");
+            }
+        }
+        return;
+    }
+    const int j0 = threadIdx.x * 4;
+    const bool live = j0 < d_pad;
+    uint64_t s01 = km_pack(0.0f, 0.0f), s23 = km_pack(0.0f, 0.0f);  // k_means.go:60-65 zero-initialised sumVectors
+    const uint64_t neg2p23 = km_pack(-8388608.0f, -8388608.0f), rcp2 = km_pack(0x1.010102p-8f, 0x1.010102p-8f),
+                   neg255 = km_pack(-255.0f, -255.0f), one2 = km_pack(1.0f, 1.0f);
+    for (uint32_t g = 0; g < groups; g++) {
+        const uint32_t st = g % kRingStages, ph = (g / kRingStages) & 1u;
+        km_mbar_wait(km_smem_u32(&bars[st]), ph);
+        const uint32_t r0 = beg + g * kRingRows, nr = min((uint32_t)kRingRows, end - r0);
+        const unsigned char *cs = s_codes + (size_t)st * stage_bytes;
+        const float2 *hs = reinterpret_cast<const float2 *>(s_hdr + (size_t)st * hdr_stage + (reinterpret_cast<uintptr_t>(hdr + r0) & 15));
+        if (live) {
+#pragma unroll 8
+            for (uint32_t i = 0; i < nr; i++) {
+                const uint32_t w = *reinterpret_cast<const uint32_t *>(cs + (size_t)i * d_pad + j0);
+                const float2 h = hs[i];
+                const float range = __fsub_rn(h.y, h.x);
+                const uint64_t mn2 = km_pack(h.x, h.x), range2 = km_pack(range, range);
+                // compute.DequantizeVectorFloat32(data[i]) then sumVectors[c][j] += val  (k_means.go:81-84)
+                s01 = km_accumulate_pair(s01, w, 0, mn2, range2, neg2p23, rcp2, neg255, one2);
+                s23 = km_accumulate_pair(s23, w, 2, mn2, range2, neg2p23, rcp2, neg255, one2);
+            }
+        }
+        __syncwarp();
+        if (lane == 0) asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(km_smem_u32(&bars[kRingStages + st])) : "memory");
+    }
+    if (!live) return;
+    float s0, s1, s2, s3;
+    asm("mov.b64 {%0, %1}, %2;" : "=f"(s0), "=f"(s1) : "l"(s01));
+    asm("mov.b64 {%0, %1}, %2;" : "=f"(s2), "=f"(s3) : "l"(s23));
+    float *m = means + (size_t)c * d;
+    if (rows > 0) {  // :89-96
+        const float nf = (float)(int64_t)rows;
+        if (j0 + 0 < d) m[j0 + 0] = __fdiv_rn(s0, nf);
+        if (j0 + 1 < d) m[j0 + 1] = __fdiv_rn(s1, nf);
+        if (j0 + 2 < d) m[j0 + 2] = __fdiv_rn(s2, nf);
+        if (j0 + 3 < d) m[j0 + 3] = __fdiv_rn(s3, nf);
+    } else if (means_prev != means) {  // an empty cluster keeps its previous mean
+        const float *mp = means_prev + (size_t)c * d;
+        for (int t = 0; t < 4; t++)
+            if (j0 + t < d) m[j0 + t] = mp[j0 + t];
+    }
+}
+
+bool kmeans_ring_supported(int d_pad) { return d_pad >= 16 && d_pad <= 1024 && d_pad % 16 == 0; }
+size_t kmeans_ring_scratch_bytes(size_t n, int k, int d_pad) {
+    auto pad = [](size_t b) { return (b + 255) & ~size_t(255); };
+    return pad((size_t)(k + 1) * 4) * 2 + pad(n * 4) + pad(n * (size_t)d_pad) + pad(n * 8) + pad(n * 8) + 1024;
+}
+
+// assign -> means (and counts) for few centroids: histogram, ordered member lists, gather, ring accumulate.
+cudaError_t launch_kmeans_accumulate_ring(const MatView &data, const int32_t *assign, int k, float *means, int64_t *counts,
+                                          const float *means_prev, void *scratch, cudaStream_t st) {
+    auto pad = [](size_t b) { return (b + 255) & ~size_t(255); };
+    const size_t n = data.n;
+    char *p = static_cast<char *>(scratch);
+    uint32_t *hist = reinterpret_cast<uint32_t *>(p);
+    p += pad((size_t)(k + 1) * 4);
+    uint32_t *seg_off = reinterpret_cast<uint32_t *>(p);
+    p += pad((size_t)(k + 1) * 4);
+    uint32_t *order = reinterpret_cast<uint32_t *>(p);
+    p += pad(n * 4);
+    uint8_t *g_codes = reinterpret_cast<uint8_t *>(p);
+    p += pad(n * (size_t)data.d_pad);
+    float2 *g_hdr = reinterpret_cast<float2 *>(p);
+    p += pad(n * 8);
+    uint2 *g_sums = reinterpret_cast<uint2 *>(p);
+    cudaError_t e = cudaMemsetAsync(hist, 0, (size_t)(k + 1) * 4, st);
+    if (e != cudaSuccess) return e;
+    const unsigned hb = (unsigned)((n + 1023) / 1024 < 592 ? (n + 1023) / 1024 : 592);
+    kmeans_histogram_kernel<<<hb ? hb : 1, 256, (size_t)k * 4, st>>>(assign, n, k, hist);
+    kmeans_member_lists_kernel<<<k, kListThreads, 0, st>>>(assign, n, k, hist, order, seg_off);
+    e = launch_gather_rows(data, order, n, g_codes, g_hdr, g_sums, nullptr, 0, nullptr, st);
+    if (e != cudaSuccess) return e;
+    const int consumer_warps = (data.d_pad / 4 + 31) / 32;
+    const size_t per_stage = (size_t)kRingRows * data.d_pad + (kRingRows + 2) * 8;
+    int stages = (int)((200 * 1024) / per_stage);
+    if (stages > kRingMaxStages) stages = kRingMaxStages;
+    if (stages < 2) return cudaErrorInvalidValue;
+    const size_t smem = (size_t)stages * per_stage + 2 * (size_t)stages * 8 + 128;
+    e = cudaFuncSetAttribute(kmeans_accumulate_ring_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return e;
+    kmeans_accumulate_ring_kernel<<<k, 32 * (consumer_warps + 1), smem, st>>>(g_codes, g_hdr, data.d, data.d_pad, seg_off, means, counts,
+                                                                             means_prev ? means_prev : means, consumer_warps, stages);
+    return cudaGetLastError();
+}
+
+// means_prev: the means before this iteration (an empty cluster keeps its previous mean); may be `means` itself.
+cudaError_t launch_kmeans_accumulate(const MatView &data, const uint32_t *order, const uint32_t *seg_off, int k,
+                                     float *means, int64_t *counts, cudaStream_t st, const float *means_prev) {
+    dim3 grid(k, (data.d_pad + kAccThreads * 4 - 1) / (kAccThreads * 4));
+    kmeans_accumulate_kernel<false><<<grid, kAccThreads, 0, st>>>(data, order, seg_off, means, counts, means_prev ? means_prev : means);
     return cudaGetLastError();
 }
 
 cudaError_t launch_kmeans_accumulate_relay(const MatView &data, const uint32_t *order, const uint32_t *seg_off, int k,
                                            float *sums, int64_t *counts, cudaStream_t st) {
     dim3 grid(k, (data.d_pad + kAccThreads * 4 - 1) / (kAccThreads * 4));
-    kmeans_accumulate_kernel<true><<<grid, kAccThreads, 0, st>>>(data, order, seg_off, sums, counts);
+    kmeans_accumulate_kernel<true><<<grid, kAccThreads, 0, st>>>(data, order, seg_off, sums, counts, sums);
     return cudaGetLastError();
 }
 

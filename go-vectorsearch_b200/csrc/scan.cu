@@ -859,8 +859,9 @@ cudaError_t launch_stage(const StageParams &p, int kpl, bool exact, int grid_blo
 // ---------------------------------------------------------------------------------------------------
 // normalizeVector of each query (compute/cosine.go:26,138-149) in literal float64: one thread sums
 // sequentially, then the block divides.
-__global__ void query_normalize_kernel(MatView q, double *qnorm) {
+__global__ void query_normalize_kernel(MatView q, double *qnorm, const unsigned int *only_if_nonzero) {
     __shared__ double s_norm;
+    if (only_if_nonzero && *only_if_nonzero == 0) return;  // nothing will read the result (empty literal-path worklist)
     const int qi = blockIdx.x;
     const int D = q.d;
     const uint8_t *codes = q.codes + (size_t)qi * q.d_pad;
@@ -883,8 +884,8 @@ __global__ void query_normalize_kernel(MatView q, double *qnorm) {
     }
 }
 
-cudaError_t launch_query_normalize(const MatView &queries, double *qnorm, cudaStream_t st) {
-    query_normalize_kernel<<<(unsigned)queries.n, 128, 0, st>>>(queries, qnorm);
+cudaError_t launch_query_normalize(const MatView &queries, double *qnorm, cudaStream_t st, const unsigned int *only_if_nonzero) {
+    query_normalize_kernel<<<(unsigned)queries.n, 128, 0, st>>>(queries, qnorm, only_if_nonzero);
     return cudaGetLastError();
 }
 
