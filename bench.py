@@ -245,6 +245,19 @@ def run_b200(a):
         step(s)
     finish(list(range(W)))
     barrier()
+    # ---- single-query latency (batch 1), device resident; measured before the sustained throughput run, whose power
+    # draw lowers the clocks for what follows ----
+    lat = []
+    one = cp.EmptyMatrix(1, D, ctx=ctx)
+    for i in range(min(64, B)):
+        one.LoadRows(0, qhost[0][i:i + 1], ctx=ctx)
+        ctx.sync()
+        ctx.timer_start()
+        ix.SearchDev(one, a.nprobe, k, d_ids.data_ptr(), d_sims.data_ptr(), d_counts.data_ptr(), d_status_all[0].data_ptr(), ctx=ctx)
+        lat.append(ctx.timer_stop() * 1e3)
+    lat = sorted(lat[4:]) if len(lat) > 8 else sorted(lat)
+
+    barrier()
     ctx.profile_enable(True)
     launches0 = ctx.launch_count()
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
@@ -270,17 +283,6 @@ def run_b200(a):
     qps = B * K / (ms_total / 1e3)
     result_ids = (f_ids if world > 1 else d_ids).cpu().numpy().view(np.uint64).copy()
     result_sims = (f_sims if world > 1 else d_sims).cpu().numpy().copy()
-
-    # ---- single-query latency (batch 1), device resident ----
-    lat = []
-    one = cp.EmptyMatrix(1, D, ctx=ctx)
-    for i in range(min(64, B)):
-        one.LoadRows(0, qhost[0][i:i + 1], ctx=ctx)
-        ctx.sync()
-        ctx.timer_start()
-        ix.SearchDev(one, a.nprobe, k, d_ids.data_ptr(), d_sims.data_ptr(), d_counts.data_ptr(), d_status_all[0].data_ptr(), ctx=ctx)
-        lat.append(ctx.timer_stop() * 1e3)
-    lat = sorted(lat[4:]) if len(lat) > 8 else sorted(lat)
 
     # ---- e2e: host query rows in pinned memory -> vs_search -> hits in pinned host memory ----
     hq = torch.empty((B, ROW_BYTES), dtype=torch.uint8).pin_memory()

@@ -535,13 +535,22 @@ gemm_kernel(const __grid_constant__ CUtensorMap tm_rows, const __grid_constant__
                         tc_ld_16x256b_x2(taddr0 + (16u << 16) + (uint32_t)(g * 16), vb);
                         process(va, 0, colbase);
                         tc_ld_wait8(vb);
-                        if (g + 1 < kUnits / 2) tc_ld_16x256b_x2(taddr0 + (uint32_t)((g + 1) * 16), va);
+                        if (g + 1 < kUnits / 2) {
+                            tc_ld_16x256b_x2(taddr0 + (uint32_t)((g + 1) * 16), va);
+                        } else {
+                            // the last TMEM read of this accumulator stage has landed in registers: hand the stage back
+                            // to the MMA warp before filtering the last unit
+                            tc_fence_before();
+                            __syncwarp();
+                            if (lane == 0) mbar_arrive(acc_empty + 8 * acc_s);
+                        }
                         process(vb, 1, colbase);
                     }
+                } else {
+                    tc_fence_before();
+                    __syncwarp();
+                    if (lane == 0) mbar_arrive(acc_empty + 8 * acc_s);
                 }
-                tc_fence_before();
-                __syncwarp();
-                if (lane == 0) mbar_arrive(acc_empty + 8 * acc_s);
                 if (++acc_s == kAccStages) {
                     acc_s = 0;
                     acc_ph ^= 1;
