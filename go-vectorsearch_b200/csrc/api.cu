@@ -1054,6 +1054,7 @@ static int search_enqueue(vs_ctx *c, const vs_index *ix, const MatView &qv, size
                           uint64_t *d_ids, float *d_sims, int32_t *d_counts, uint32_t *d_status, float *d_probe_sims,
                           bool stage1_only) {
     StageParams p{};
+    bool chained = false;
     p.queries = qv;
     p.qnorm = b.qnorm;
     p.q_select = d_select;
@@ -1092,6 +1093,9 @@ static int search_enqueue(vs_ctx *c, const vs_index *ix, const MatView &qv, size
         p.status_init = 1;
         p.trace = c->trace ? c->d_trace : nullptr;
         if (p.trace) CU(cudaMemsetAsync(p.trace, 0, kTraceBlocks * 16 * sizeof(unsigned long long), c->stream));
+        // the list stage follows immediately on the stream: let its blocks be scheduled while this stage drains
+        chained = !stage1_only && !c->trace && !c->profile;
+        p.pdl = chained ? 1 : 0;
         LAUNCH(c, launch_stage(p, kpl1, exact, b.grid, c->stream));
         if (stage1_only) return VS_OK;
     }
@@ -1125,6 +1129,7 @@ static int search_enqueue(vs_ctx *c, const vs_index *ix, const MatView &qv, size
     p.out_qtiles = nullptr;
     p.status_bit = kStatusListAmbiguous;
     p.status_init = flat ? 1 : 0;
+    p.pdl = chained ? 2 : 0;
     p.trace = c->trace ? c->d_trace + kTraceBlocks * 16 : nullptr;
     if (p.trace) CU(cudaMemsetAsync(p.trace, 0, kTraceBlocks * 16 * sizeof(unsigned long long), c->stream));
     VS(prof_mark(c));

@@ -1058,6 +1058,25 @@ bool make_codes_map(CUtensorMap *tm, const MatView &m, int box_rows) {
               CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
 }
 
+}  // namespace
+
+// A plain (unswizzled) 2-D tile map over a [rows][row_stride] byte matrix: box = box_cols bytes x box_rows rows.
+// Out-of-range elements read as zero and still count towards the transaction bytes.  tm_out: CUtensorMap*.
+bool make_u8_tile_map(void *tm_out, const uint8_t *base, uint64_t cols, uint64_t rows, uint64_t row_stride, uint32_t box_cols,
+                      uint32_t box_rows) {
+    EncodeTiledFn fn = encode_fn();
+    if (!fn) return false;
+    cuuint64_t dims[2] = {(cuuint64_t)cols, (cuuint64_t)rows};
+    cuuint64_t strides[1] = {(cuuint64_t)row_stride};
+    cuuint32_t box[2] = {(cuuint32_t)box_cols, (cuuint32_t)box_rows};
+    cuuint32_t estr[2] = {1, 1};
+    return fn(static_cast<CUtensorMap *>(tm_out), CU_TENSOR_MAP_DATA_TYPE_UINT8, 2, const_cast<uint8_t *>(base), dims, strides, box,
+              estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+              CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
+}
+
+namespace {
+
 size_t gemm_smem_bytes(int kc, int ns) {
     return 1024 + (size_t)kc * kChunkBytes + (size_t)ns * kStageBytes + kAccStages * kTN * 16 +
            8 * (2 * kMaxKC + 2 * kMaxStages + 3 * kAccStages) + 64;

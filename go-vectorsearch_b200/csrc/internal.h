@@ -100,6 +100,8 @@ struct StageParams {
     uint32_t *out_status;         // [q], OR-ed with status_bit / need-more bit
     uint32_t status_bit;
     int status_init;              // 1: this stage stores the query's status word, 0: it ORs into it
+    int pdl;                      // programmatic dependent launch: 1 = let the next stage's blocks be scheduled while
+                                  // this one drains, 2 = launched that way: wait for the previous stage before reading
 };
 
 constexpr uint32_t kStatusProbeAmbiguous = 1u;
@@ -169,6 +171,10 @@ cudaError_t launch_probe_batch(const MatView &cent, const MatView &queries, int 
                                const uint64_t *next_list_off, uint32_t next_tile_rows, uint32_t *out_status, uint32_t status_bit,
                                int status_init, unsigned long long *fix_counter, int sm_count, cudaStream_t st);
 cudaError_t probe_set_certify_scale(float scale);
+
+// gemm.cu: a plain 2-D TMA tile map over a byte matrix (tm_out: CUtensorMap*)
+bool make_u8_tile_map(void *tm_out, const uint8_t *base, uint64_t cols, uint64_t rows, uint64_t row_stride, uint32_t box_cols,
+                      uint32_t box_rows);
 
 // quantize.cu
 cudaError_t launch_quantize_f32(const float *in, size_t n, int d, uint8_t *out_rows, cudaStream_t st);

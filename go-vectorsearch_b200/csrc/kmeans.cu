@@ -7,6 +7,9 @@
 // sequential chain over the member rows in ascending row order; parallelism comes from the
 // k x D independent chains (four per thread, a 32-bit word of codes per row) and from the unrolled
 // row loop, whose loads do not depend on the additions.  HBM-bound: every member row is read once.
+#include <cuda.h>
+#include <stdlib.h>
+
 #include "internal.h"
 
 namespace vs {
@@ -247,7 +250,9 @@ __global__ void kmeans_histogram_kernel(const int32_t *__restrict__ assign, size
 }
 
 // Block c: the rows assigned to centroid c, ascending, written at order[seg_off[c] ..); seg_off from the histogram.
+// A thread owns eight consecutive rows of every window (their loads fly together), positions come from a block scan.
 constexpr int kListThreads = 1024;
+constexpr int kListRowsPerThread = 8;
 __global__ void __launch_bounds__(kListThreads)
 kmeans_member_lists_kernel(const int32_t *__restrict__ assign, size_t n, int k, const uint32_t *__restrict__ counts,
                            uint32_t *__restrict__ order, uint32_t *__restrict__ seg_off) {
@@ -264,19 +269,32 @@ kmeans_member_lists_kernel(const int32_t *__restrict__ assign, size_t n, int k, 
     }
     __syncthreads();
     uint32_t base = s_base;
-    for (size_t w0 = 0; w0 < n; w0 += kListThreads) {
-        const size_t r = w0 + threadIdx.x;
-        const bool hit = r < n && assign[r] == c;
-        const unsigned int m = __ballot_sync(0xFFFFFFFFu, hit);
+    for (size_t w0 = 0; w0 < n; w0 += (size_t)kListThreads * kListRowsPerThread) {
+        const size_t r0 = w0 + (size_t)threadIdx.x * kListRowsPerThread;
+        uint32_t hits = 0, mine = 0;
+#pragma unroll
+        for (int t = 0; t < kListRowsPerThread; t++) {
+            const bool hit = r0 + t < n && assign[r0 + t] == c;
+            hits |= hit ? (1u << t) : 0u;
+            mine += hit ? 1u : 0u;
+        }
+        uint32_t incl = mine;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            const uint32_t x = __shfl_up_sync(0xFFFFFFFFu, incl, o);
+            if (lane >= o) incl += x;
+        }
         __syncthreads();
-        if (lane == 0) s_wsum[warp] = (uint32_t)__popc(m);
+        if (lane == 31) s_wsum[warp] = incl;
         __syncthreads();
-        uint32_t pos = base + (uint32_t)__popc(m & ((1u << lane) - 1u)), tot = 0;
+        uint32_t pos = base + incl - mine, tot = 0;
         for (int w = 0; w < kListThreads / 32; w++) {
             if (w < warp) pos += s_wsum[w];
             tot += s_wsum[w];
         }
-        if (hit) order[pos] = (uint32_t)r;
+#pragma unroll
+        for (int t = 0; t < kListRowsPerThread; t++)
+            if (hits & (1u << t)) order[pos++] = (uint32_t)(r0 + t);
         base += tot;
     }
 }
@@ -391,6 +409,167 @@ kmeans_accumulate_ring_kernel(const uint8_t *__restrict__ codes, const float2 *_
     }
 }
 
+// Two warp roles instead of one.  In kmeans_accumulate_ring_kernel every consumer thread both dequantizes and adds, ~22
+// instructions per row and thread, and a centroid's 768 dimensions sit on one SM: issue-bound at ~33 cycles per row.
+// Here a block owns a 128-dimension slice of one centroid (6 blocks per centroid at 768-d): eight warps dequantize rows
+// from the byte ring into a float32 ring (any order: 4 rows per warp), and one warp runs the 128 x 1 chains over the
+// float32 rows with two packed additions per row.  Same operations on the same values in the same order per chain.
+constexpr int kR2Slice = 128;        // bytes (= dimensions) of a row per block
+constexpr int kR2Rows = 64;          // rows per stage (an mbarrier hand-off costs a few hundred cycles: amortize it)
+constexpr int kR2ByteStages = 12, kR2FloatStages = 3;  // 96 KB of row bytes in flight per block; 96 KB of float32 rows
+constexpr int kR2DequantWarps = 8;
+constexpr int kR2Threads = 32 * (1 + kR2DequantWarps + 1);  // chain warp, dequant warps, producer warp
+struct R2Smem {
+    float f32[kR2FloatStages][kR2Rows][kR2Slice];               // 96 KB
+    unsigned char u8[kR2ByteStages][kR2Rows][kR2Slice];         // 96 KB
+    unsigned char hdr[kR2ByteStages][(kR2Rows + 2) * 8];        // row headers (with up to 8 bytes of lead-in)
+    uint64_t u_full[kR2ByteStages], u_empty[kR2ByteStages], f_full[kR2FloatStages], f_empty[kR2FloatStages];
+};
+__device__ __forceinline__ void km_mbar_init(uint64_t *bar, int count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(km_smem_u32(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void km_mbar_arrive(uint64_t *bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(km_smem_u32(bar)) : "memory");
+}
+// dequantized values of bytes k, k+1 of word as a packed pair: mn + (float32(q)/255) * range
+__device__ __forceinline__ uint64_t km_dequant_pair(uint32_t word, int k, float mn, float range, uint64_t neg2p23, uint64_t rcp2,
+                                                    uint64_t neg255) {
+    const uint64_t bits = ((uint64_t)__byte_perm(word, 0x4B000000u, 0x7650u + (uint32_t)k + 1u) << 32) |
+                          (uint64_t)__byte_perm(word, 0x4B000000u, 0x7650u + (uint32_t)k);
+    const uint64_t x = km_add2(bits, neg2p23);
+    const uint64_t r = km_mul2(x, rcp2);
+    const uint64_t e = km_fma2(r, neg255, x);
+    const uint64_t q = km_fma2(e, rcp2, r);
+    float q_lo, q_hi;  // the product is rounded on its own (scalar: ptxas would contract the packed form)
+    asm("mov.b64 {%0, %1}, %2;" : "=f"(q_lo), "=f"(q_hi) : "l"(q));
+    return km_pack(__fadd_rn(mn, __fmul_rn(q_lo, range)), __fadd_rn(mn, __fmul_rn(q_hi, range)));
+}
+
+__global__ void __launch_bounds__(kR2Threads)
+kmeans_accumulate_ring2_kernel(const __grid_constant__ CUtensorMap tm_codes, const float2 *__restrict__ hdr, int d, int d_pad,
+                               const uint32_t *__restrict__ seg_off, float *means, int64_t *__restrict__ counts,
+                               const float *means_prev, int dbg) {
+    extern __shared__ __align__(128) unsigned char r2_raw[];
+    R2Smem &sm = *reinterpret_cast<R2Smem *>(r2_raw);
+    const int c = blockIdx.x, slice = blockIdx.y;
+    const int col0 = slice * kR2Slice;                       // first byte / dimension of this slice
+    const int width = min(kR2Slice, d_pad - col0);           // bytes of a row in this slice (multiple of 16)
+    const uint32_t beg = seg_off[c], end = seg_off[c + 1];
+    const uint32_t rows = end - beg, groups = (rows + kR2Rows - 1) / kR2Rows;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    if (threadIdx.x == 0) {
+        for (int i = 0; i < kR2ByteStages; i++) {
+            km_mbar_init(&sm.u_full[i], 1);
+            km_mbar_init(&sm.u_empty[i], kR2DequantWarps);
+        }
+        for (int i = 0; i < kR2FloatStages; i++) {
+            km_mbar_init(&sm.f_full[i], kR2DequantWarps);
+            km_mbar_init(&sm.f_empty[i], 1);
+        }
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        if (slice == 0) counts[c] = (int64_t)rows;
+    }
+    __syncthreads();
+    if (warp == 1 + kR2DequantWarps) {
+        // ===== producer: one 2-D TMA tile (32 rows x this slice) and the group's headers per stage =====
+        // (one bulk copy per 128-byte row slice was tried first: 32 tiny copies per stage cost ~2000 cycles)
+        if (lane == 0) {
+            for (uint32_t g = 0; g < groups; g++) {
+                const uint32_t st = g % kR2ByteStages, ph = (g / kR2ByteStages) & 1u;
+                if (g >= (uint32_t)kR2ByteStages) km_mbar_wait(km_smem_u32(&sm.u_empty[st]), ph ^ 1u);
+                const uint32_t r0 = beg + g * kR2Rows, nr = min((uint32_t)kR2Rows, end - r0);
+                const uintptr_t hsrc = reinterpret_cast<uintptr_t>(hdr + r0);
+                const uintptr_t hal = hsrc & ~uintptr_t(15);
+                const uint32_t hb = (uint32_t)(((hsrc - hal) + (uintptr_t)nr * 8 + 15) & ~uintptr_t(15));
+                const uint32_t full = km_smem_u32(&sm.u_full[st]);
+                // the tile always delivers the whole box (rows past the store read as zero and are not used)
+                asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(full),
+                             "r"((uint32_t)(kR2Rows * kR2Slice) + hb)
+                             : "memory");
+                asm volatile(
+                    "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3}], [%4];" ::"r"(
+                        km_smem_u32(&sm.u8[st][0][0])),
+                    "l"(&tm_codes), "r"(col0), "r"((int)r0), "r"(full)
+                    : "memory");
+                asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+                                 km_smem_u32(&sm.hdr[st][0])),
+                             "l"(reinterpret_cast<const void *>(hal)), "r"(hb), "r"(full)
+                             : "memory");
+            }
+        }
+        return;
+    }
+    if (warp >= 1) {
+        // ===== dequantize: warp w takes rows 4w .. 4w+3 of every group; lane l bytes 4l .. 4l+3 of the slice =====
+        const int w = warp - 1;
+        const uint64_t neg2p23 = km_pack(-8388608.0f, -8388608.0f), rcp2 = km_pack(0x1.010102p-8f, 0x1.010102p-8f),
+                       neg255 = km_pack(-255.0f, -255.0f);
+        const bool live = lane * 4 < width;
+        for (uint32_t g = 0; g < groups; g++) {
+            const uint32_t su = g % kR2ByteStages, pu = (g / kR2ByteStages) & 1u;
+            const uint32_t sf = g % kR2FloatStages, pf = (g / kR2FloatStages) & 1u;
+            const uint32_t r0 = beg + g * kR2Rows, nr = min((uint32_t)kR2Rows, end - r0);
+            km_mbar_wait(km_smem_u32(&sm.u_full[su]), pu);
+            if (g >= (uint32_t)kR2FloatStages) km_mbar_wait(km_smem_u32(&sm.f_empty[sf]), pf ^ 1u);
+            const float2 *hs = reinterpret_cast<const float2 *>(&sm.hdr[su][reinterpret_cast<uintptr_t>(hdr + r0) & 15]);
+#pragma unroll
+            for (int t = 0; t < kR2Rows / kR2DequantWarps; t++) {
+                const uint32_t i = (uint32_t)(w * (kR2Rows / kR2DequantWarps) + t);
+                if (i < nr && live && !(dbg & 2)) {
+                    const uint32_t word = *reinterpret_cast<const uint32_t *>(&sm.u8[su][i][lane * 4]);
+                    const float2 h = hs[i];
+                    const float range = __fsub_rn(h.y, h.x);
+                    // compute.DequantizeVectorFloat32(data[i]) (k_means.go:81)
+                    const uint64_t v01 = km_dequant_pair(word, 0, h.x, range, neg2p23, rcp2, neg255);
+                    const uint64_t v23 = km_dequant_pair(word, 2, h.x, range, neg2p23, rcp2, neg255);
+                    *reinterpret_cast<ulonglong2 *>(&sm.f32[sf][i][lane * 4]) = make_ulonglong2(v01, v23);
+                }
+            }
+            __syncwarp();
+            if (lane == 0) {
+                km_mbar_arrive(&sm.u_empty[su]);
+                km_mbar_arrive(&sm.f_full[sf]);  // (release: the stores above are ordered before the arrive)
+            }
+        }
+        return;
+    }
+    // ===== chain warp: thread t owns dimensions col0 + 4t .. 4t+3; sumVectors[c][j] += val in row order (k_means.go:82-84) =====
+    const bool live = lane * 4 < width;
+    float s0 = 0.0f, s1 = 0.0f, s2 = 0.0f, s3 = 0.0f;  // scalar adds: four independent 4-cycle chains (a dependent FADD2
+                                                       // chain measured ~8x slower per row)
+    for (uint32_t g = 0; g < groups; g++) {
+        const uint32_t sf = g % kR2FloatStages, pf = (g / kR2FloatStages) & 1u;
+        const uint32_t r0 = beg + g * kR2Rows, nr = min((uint32_t)kR2Rows, end - r0);
+        km_mbar_wait(km_smem_u32(&sm.f_full[sf]), pf);
+        if (live && !(dbg & 1)) {
+#pragma unroll 8
+            for (uint32_t i = 0; i < nr; i++) {
+                const float4 v = *reinterpret_cast<const float4 *>(&sm.f32[sf][i][lane * 4]);
+                s0 = __fadd_rn(s0, v.x);
+                s1 = __fadd_rn(s1, v.y);
+                s2 = __fadd_rn(s2, v.z);
+                s3 = __fadd_rn(s3, v.w);
+            }
+        }
+        __syncwarp();
+        if (lane == 0) km_mbar_arrive(&sm.f_empty[sf]);
+    }
+    if (!live) return;
+    const int j0 = col0 + lane * 4;
+    float *m = means + (size_t)c * d;
+    if (rows > 0) {  // :89-96
+        const float nf = (float)(int64_t)rows;
+        if (j0 + 0 < d) m[j0 + 0] = __fdiv_rn(s0, nf);
+        if (j0 + 1 < d) m[j0 + 1] = __fdiv_rn(s1, nf);
+        if (j0 + 2 < d) m[j0 + 2] = __fdiv_rn(s2, nf);
+        if (j0 + 3 < d) m[j0 + 3] = __fdiv_rn(s3, nf);
+    } else if (means_prev != means) {  // an empty cluster keeps its previous mean
+        const float *mp = means_prev + (size_t)c * d;
+        for (int t = 0; t < 4; t++)
+            if (j0 + t < d) m[j0 + t] = mp[j0 + t];
+    }
+}
+
 bool kmeans_ring_supported(int d_pad) { return d_pad >= 16 && d_pad <= 1024 && d_pad % 16 == 0; }
 size_t kmeans_ring_scratch_bytes(size_t n, int k, int d_pad) {
     auto pad = [](size_t b) { return (b + 255) & ~size_t(255); };
@@ -421,6 +600,19 @@ cudaError_t launch_kmeans_accumulate_ring(const MatView &data, const int32_t *as
     kmeans_member_lists_kernel<<<k, kListThreads, 0, st>>>(assign, n, k, hist, order, seg_off);
     e = launch_gather_rows(data, order, n, g_codes, g_hdr, g_sums, nullptr, 0, nullptr, st);
     if (e != cudaSuccess) return e;
+    if (!getenv("VS_KMEANS_RING1")) {  // (the one-role ring stays selectable for A/B timing)
+        const size_t smem2 = sizeof(R2Smem) + 128;
+        e = cudaFuncSetAttribute(kmeans_accumulate_ring2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem2);
+        if (e != cudaSuccess) return e;
+        CUtensorMap tm;
+        if (!make_u8_tile_map(&tm, g_codes, (uint64_t)data.d_pad, (uint64_t)n, (uint64_t)data.d_pad, kR2Slice, kR2Rows))
+            return cudaErrorNotSupported;
+        dim3 grid2(k, (data.d_pad + kR2Slice - 1) / kR2Slice);
+        const char *dbg = getenv("VS_KMEANS_DBG");  // profiling aid: 1 = chain warp skips its additions, 2 = no dequantize
+        kmeans_accumulate_ring2_kernel<<<grid2, kR2Threads, smem2, st>>>(tm, g_hdr, data.d, data.d_pad, seg_off, means, counts,
+                                                                        means_prev ? means_prev : means, dbg ? atoi(dbg) : 0);
+        return cudaGetLastError();
+    }
     const int consumer_warps = (data.d_pad / 4 + 31) / 32;
     const size_t per_stage = (size_t)kRingRows * data.d_pad + (kRingRows + 2) * 8;
     int stages = (int)((200 * 1024) / per_stage);

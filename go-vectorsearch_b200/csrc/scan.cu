@@ -350,6 +350,11 @@ stage_kernel(const StageParams p) {
 
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int D = p.rows.d, d_pad = p.rows.d_pad;
+    // Probe stage -> list stage of one search: the list stage is launched with programmatic stream serialization, so
+    // its blocks are scheduled as the probe stage's blocks retire (while the last one still merges) and wait here
+    // until that grid has completed and its writes (probe list, tile counts) are visible.
+    if (p.pdl == 1) asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+    if (p.pdl == 2) asm volatile("griddepcontrol.wait;" ::: "memory");
     constexpr int GG = (G == 0) ? 32 : G;
     const int iters = (G == 0 || EXACT) ? 32 : p.iters;  // rows per lane group in a tile
     const int tile_rows = (G == 0 || EXACT) ? 32 : (32 / GG) * iters;
@@ -817,6 +822,19 @@ static cudaError_t launch_stage_t(const StageParams &p, int grid_blocks, cudaStr
     if (smem > 48 * 1024) {
         cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         if (e != cudaSuccess) return e;
+    }
+    if (p.pdl == 2) {
+        cudaLaunchConfig_t cfg = {};
+        cfg.gridDim = dim3((unsigned)grid_blocks);
+        cfg.blockDim = dim3(kStageWarps * 32);
+        cfg.dynamicSmemBytes = smem;
+        cfg.stream = st;
+        cudaLaunchAttribute attr[1];
+        attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+        attr[0].val.programmaticStreamSerializationAllowed = 1;
+        cfg.attrs = attr;
+        cfg.numAttrs = 1;
+        return cudaLaunchKernelEx(&cfg, kern, p);
     }
     kern<<<grid_blocks, kStageWarps * 32, smem, st>>>(p);
     return cudaGetLastError();
