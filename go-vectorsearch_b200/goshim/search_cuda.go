@@ -122,3 +122,58 @@ func (ix *Index) SearchBatch(queries [][]uint8, nprobe int, k int) (documentIDs 
 	}
 	return documentIDs, similarities
 }
+
+// Split is the split loop of dnc.divideNconquer (dnc/dnc.go:363-389) on a device matrix: child j receives the rows of X
+// nearest to centroids[j], in X's order (nil for a child without rows).  Together with KMeans and a sample taken with
+// Gather this is all divideNconquer needs; see go-vectorsearch_b200/dnc.py:DivideAndConquer for the recursion.
+func Split(X Matrix, centroids [][]uint8) []Matrix {
+	m := X.(*matrixContainer)
+	cbuf, k, _ := pack(centroids)
+	defer C.free(cbuf)
+	handles := make([]*C.vs_matrix, k)
+	counts := make([]C.uint64_t, k)
+	withDefaultCtx(func(c *ctx) {
+		check(C.vs_matrix_split(c.h, m.h, (*C.uint8_t)(cbuf), C.size_t(k), &handles[0], &counts[0]))
+	})
+	out := make([]Matrix, k)
+	for j, h := range handles {
+		if h == nil {
+			continue
+		}
+		child := &matrixContainer{h: h, rows: int(counts[j]), cols: m.cols}
+		runtime.SetFinalizer(child, func(m *matrixContainer) { C.vs_matrix_release(m.h) })
+		out[j] = child
+	}
+	return out
+}
+
+// Gather is sample() (dnc/sampling.go:12-74) once the sorted row indices are drawn: a new device matrix of those rows.
+func Gather(X Matrix, rows []uint64) Matrix {
+	m := X.(*matrixContainer)
+	g := &matrixContainer{rows: len(rows), cols: m.cols}
+	withDefaultCtx(func(c *ctx) {
+		check(C.vs_matrix_gather(c.h, m.h, (*C.uint64_t)(unsafe.Pointer(&rows[0])), C.size_t(len(rows)), &g.h))
+	})
+	runtime.SetFinalizer(g, func(m *matrixContainer) { C.vs_matrix_release(m.h) })
+	return g
+}
+
+// ReassignRecenter is the tail of KMeansDivideAndConquer (dnc/dnc.go:177-291): the index of the nearest new centroid for
+// every row, and every centroid re-centred on its members (recenterDbCentroid, dnc.go:402-456).
+func ReassignRecenter(X Matrix, centroids [][]uint8) (assign []int32, recentred [][]uint8, counts []int64) {
+	m := X.(*matrixContainer)
+	cbuf, k, rowBytes := pack(centroids)
+	defer C.free(cbuf)
+	assign = make([]int32, m.rows)
+	out := make([]uint8, k*rowBytes)
+	counts = make([]int64, k)
+	withDefaultCtx(func(c *ctx) {
+		check(C.vs_reassign_recenter(c.h, m.h, (*C.uint8_t)(cbuf), C.size_t(k), (*C.int32_t)(unsafe.Pointer(&assign[0])), nil,
+			(*C.uint8_t)(unsafe.Pointer(&out[0])), (*C.int64_t)(unsafe.Pointer(&counts[0]))))
+	})
+	recentred = make([][]uint8, k)
+	for i := range recentred {
+		recentred[i] = out[i*rowBytes : (i+1)*rowBytes]
+	}
+	return assign, recentred, counts
+}
