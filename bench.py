@@ -487,6 +487,54 @@ def other_configs(pkg, torch, ctx, ix, a, device, peaks):
         del data4, cent4, assign
     except Exception as e:  # noqa: BLE001
         out["kmeans_assign_config4_slice"] = {"error": repr(e)[:300]}
+    try:
+        # BASELINE config 1 (the reference's own CPU-runnable case): brute-force cosine over 100k rows, 1 query, top-10.
+        # Timed through the host-buffer C ABI call (vs_search_flat), one query per call, distinct queries; the oracle
+        # answers the same queries on one host thread (compute/cosine.go:13-57 + sort, what search.go does per batch).
+        import oracle
+        n1 = min(100_000, a.rows)
+        x = gen_unit_rows(torch, SEED_DATA, 0, n1, device) if n1 <= CHUNK else None
+        m1 = cp.EmptyMatrix(n1, D, ctx=ctx)
+        if x is None:
+            raise RuntimeError("config 1 needs rows <= one generator chunk")
+        torch.cuda.synchronize()
+        m1.FillFloat32Dev(0, x.data_ptr(), n1, ctx=ctx)
+        ctx.sync()
+        del x
+        xq = gen_unit_rows(torch, SEED_QUERY, 9000, 72, device)
+        torch.cuda.synchronize()
+        qm = cp.EmptyMatrix(72, D, ctx=ctx)
+        qm.FillFloat32Dev(0, xq.data_ptr(), 72, ctx=ctx)
+        ctx.sync()
+        qh = qm.ReadRows()
+        for i in range(8):
+            pkg.ivf.SearchFlat(m1, qh[i], a.k, ctx=ctx)
+        lat, res = [], []
+        for i in range(8, 72):
+            t0 = time.perf_counter()
+            res.append(pkg.ivf.SearchFlat(m1, qh[i], a.k, ctx=ctx))
+            lat.append((time.perf_counter() - t0) * 1e6)
+        lat.sort()
+        rows1 = m1.ReadRows()
+        t0 = time.perf_counter()
+        nchk = 4
+        ok = True
+        for i in range(nchk):
+            w_ids, w_sims = oracle.search_flat(qh[8 + i], rows1, None, a.k)
+            g_ids, g_sims, g_cnt = res[i]
+            ok = ok and g_ids[0, :g_cnt[0]].tolist() == w_ids.tolist() and \
+                (g_sims[0, :g_cnt[0]].view(np.uint32) == w_sims.view(np.uint32)).all()
+        cpu_s = (time.perf_counter() - t0) / nchk
+        p50 = lat[len(lat) // 2]
+        out["brute_force_config1"] = {
+            "workload": f"brute-force cosine over {n1} x {D}-d uint8 rows, 1 query per call, top-{a.k}, host buffers in and out",
+            "latency_us": {"p50": round(p50, 1), "p99": round(lat[int(len(lat) * 0.99)], 1), "n": len(lat)},
+            "queries_per_s": round(1e6 / p50, 1), "scan_gbs": round(n1 * ROW_BYTES / (p50 * 1e-6) / 1e9, 1),
+            "cpu_oracle_one_thread_s_per_query": round(cpu_s, 4),
+            "parity_vs_oracle": {"queries_checked": nchk, "match": bool(ok)}}
+        del m1, qm
+    except Exception as e:  # noqa: BLE001
+        out["brute_force_config1"] = {"error": repr(e)[:300]}
     torch.cuda.empty_cache()
     return out
 
