@@ -15,13 +15,13 @@ namespace {
 #define FULL 0xFFFFFFFFu
 constexpr int kPsWarps = 4;                          // warps per block of the score kernel
 constexpr int kPsRows = kPsWarps * 8;                // centroid rows per work item (2 half-warps x 4 rows per warp)
-constexpr int kPsQueries = 8;                        // queries staged in shared memory per work item (small items: the
-                                                     // whole stage is a few microseconds of work, spread it over every SM)
+// queries staged in shared memory per work item: 8 for small batches (the whole stage is a few microseconds of work,
+// spread it over every SM), 32 for large ones (a row tile is loaded once per 32 queries instead of once per 8)
 constexpr int kSelThreadsP = 256;
 constexpr int kMaxProbe = 128;
 
 // CPL = 16-byte chunks per lane; 16 lanes stream one row: d_pad = 256 * CPL bytes.
-template <int CPL>
+template <int CPL, int kPsQueries>
 __global__ void __launch_bounds__(kPsWarps * 32)
 probe_score_kernel(MatView cent, MatView queries, uint32_t *__restrict__ keys, size_t key_stride,
                    unsigned int *__restrict__ flag_cnt, uint32_t *__restrict__ flag_list, uint32_t flag_cap) {
@@ -422,16 +422,22 @@ cudaError_t launch_probe_batch(const MatView &cent, const MatView &queries, int 
     const size_t nq = queries.n, C = cent.n;
     cudaError_t e = cudaMemsetAsync(flag_cnt, 0, nq * sizeof(unsigned int), st);
     if (e != cudaSuccess) return e;
-    const size_t items = ((C + kPsRows - 1) / kPsRows) * ((nq + kPsQueries - 1) / kPsQueries);
+    const int qc = nq >= 128 ? 32 : 8;
+    const size_t items = ((C + kPsRows - 1) / kPsRows) * ((nq + qc - 1) / qc);
     const unsigned grid = (unsigned)(items < (size_t)sm_count * 4 ? items : (size_t)sm_count * 4);
-    const size_t smem = (size_t)kPsQueries * cent.d_pad + kPsQueries * sizeof(SideConst);
-#define VS_PROBE_SCORE(CPL)                                                                                                   \
+    const size_t smem = (size_t)qc * cent.d_pad + qc * sizeof(SideConst);
+#define VS_PROBE_SCORE2(CPL, QC)                                                                                              \
     do {                                                                                                                      \
         if (smem > 48 * 1024) {                                                                                               \
-            e = cudaFuncSetAttribute(probe_score_kernel<CPL>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);       \
+            e = cudaFuncSetAttribute(probe_score_kernel<CPL, QC>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);   \
             if (e != cudaSuccess) return e;                                                                                   \
         }                                                                                                                     \
-        probe_score_kernel<CPL><<<grid, kPsWarps * 32, smem, st>>>(cent, queries, keys, C, flag_cnt, flag_list, flag_cap);            \
+        probe_score_kernel<CPL, QC><<<grid, kPsWarps * 32, smem, st>>>(cent, queries, keys, C, flag_cnt, flag_list, flag_cap); \
+    } while (0)
+#define VS_PROBE_SCORE(CPL)               \
+    do {                                  \
+        if (qc == 32) VS_PROBE_SCORE2(CPL, 32); \
+        else VS_PROBE_SCORE2(CPL, 8);     \
     } while (0)
     switch (cent.d_pad / 256) {
         case 1: VS_PROBE_SCORE(1); break;
@@ -441,6 +447,7 @@ cudaError_t launch_probe_batch(const MatView &cent, const MatView &queries, int 
         case 6: VS_PROBE_SCORE(6); break;
         default: return cudaErrorInvalidValue;
     }
+#undef VS_PROBE_SCORE2
 #undef VS_PROBE_SCORE
     e = cudaGetLastError();
     if (e != cudaSuccess) return e;
