@@ -1003,6 +1003,14 @@ struct SearchBufs {
     unsigned int *flag_cnt; // [nq]
     uint32_t *flag_list;    // [nq][probe_flag_cap(C)]
     uint32_t *cand_keys, *cand_ids;  // [nq][segments][npe] segment survivors (many centroids only)
+    // probe selection on the tensor cores (very many centroids, large batches): the GEMM pipeline with k = nprobe
+    bool gemm_probe;
+    GemmPlan gp;
+    char *gp_scratch;
+    uint64_t *gp_ids;       // [nq][npe]
+    float *gp_sims;         // [nq][npe]
+    int32_t *gp_counts;     // [nq]
+    uint32_t *gp_status;    // [nq]
     int grid;               // blocks per stage launch
     int iters1, iters2;     // rows per lane group (tile height) of each stage
     int tile_rows1, tile_rows2;
@@ -1035,6 +1043,20 @@ static int search_plan(const vs_index *ix, size_t nq, size_t npe, bool flat, Sea
 }
 
 constexpr size_t kProbeBatchMin = 8;  // from this many queries on the probe stage reads the centroid table once (probe.cu)
+// Very many centroids x a large batch is a dense contraction (256 x 65 536 x 768 at config 5): the tensor-core pipeline
+// of gemm.cu with k = nprobe (sampled thresholds, fused filter, certified selection) replaces the dp4a score kernel.
+constexpr size_t kProbeGemmMinCentroids = 16384, kProbeGemmMinQueries = 64;
+static bool use_probe_gemm(const vs_index *ix, size_t nq, size_t npe, bool flat) {
+    return !flat && ix->centroids && nq >= kProbeGemmMinQueries && ix->C >= kProbeGemmMinCentroids && npe <= 128 &&
+           gemm_supported(ix->centroids->view(), nq);
+}
+static GemmPlan probe_gemm_plan(const vs_index *ix, size_t nq, size_t npe) {
+    return gemm_plan(ix->centroids->view(), nq, npe, true, 16, 1, 2048);
+}
+static size_t probe_gemm_bytes(const vs_index *ix, size_t nq, size_t npe) {
+    const GemmPlan pl = probe_gemm_plan(ix, nq, npe);
+    return gemm_scratch_bytes(pl, nq) + Arena::pad(nq * npe * 8) + Arena::pad(nq * npe * 4) + 2 * Arena::pad(nq * 4) + 1024;
+}
 static bool use_probe_batch(const vs_index *ix, size_t nq, size_t npe, bool flat) {
     return !flat && nq >= kProbeBatchMin && ix->centroids && probe_batch_supported(ix->centroids->view(), nq, npe);
 }
@@ -1046,6 +1068,33 @@ static size_t probe_batch_bytes(size_t nq, size_t C, size_t npe) {
 static size_t search_bytes(size_t nq, size_t npe, int kpl1, int kpl2, int grid, size_t d) {
     return Arena::pad(nq * npe * 4) + Arena::pad((nq + grid) * (size_t)32 * kpl1 * sizeof(Cand)) +
            Arena::pad((nq + grid) * (size_t)32 * kpl2 * sizeof(Cand)) + 3 * Arena::pad(nq * 4) + Arena::pad(nq * d * 8) + 4096;
+}
+
+// Probe list, next-stage tile count and status of one query from its certified top-npe centroids (tensor-core probe
+// selection).  A query the filter could not answer (unusable header, fewer than npe centroids above its threshold) gets
+// a valid placeholder list and the ambiguous bit: the caller's literal path redoes it.
+__global__ void probe_from_topk_kernel(const uint64_t *ids, const float *sims, const int32_t *counts, const uint32_t *gstatus, int npe,
+                                       uint32_t *out_probe, float *out_sims, uint32_t *out_qtiles, const uint64_t *list_off,
+                                       uint32_t tile_rows, uint32_t *out_status) {
+    __shared__ uint32_t s_tiles;
+    const uint32_t q = blockIdx.x;
+    const bool ok = !(gstatus[q] & kStatusNeedMore) && counts[q] == npe;
+    if (threadIdx.x == 0) s_tiles = 0;
+    __syncthreads();
+    uint32_t mytiles = 0;
+    for (int r = threadIdx.x; r < npe; r += blockDim.x) {
+        const uint32_t L = ok ? (uint32_t)ids[(size_t)q * npe + r] : (uint32_t)r;
+        out_probe[(size_t)q * npe + r] = L;
+        if (out_sims) out_sims[(size_t)q * npe + r] = ok ? sims[(size_t)q * npe + r] : 0.0f;
+        mytiles += (uint32_t)((list_off[L + 1] - list_off[L] + tile_rows - 1) / tile_rows);
+    }
+    for (int o = 16; o > 0; o >>= 1) mytiles += __shfl_xor_sync(0xFFFFFFFFu, mytiles, o);
+    if ((threadIdx.x & 31) == 0 && mytiles) atomicAdd(&s_tiles, mytiles);
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        out_qtiles[q] = s_tiles ? s_tiles : 1u;
+        out_status[q] = ok ? 0u : kStatusProbeAmbiguous;
+    }
 }
 
 // Enqueue the two stages for nq_launch queries (all, or those listed in d_select).
@@ -1063,7 +1112,19 @@ static int search_enqueue(vs_ctx *c, const vs_index *ix, const MatView &qv, size
     p.out_status = d_status;
     p.fix_counter = c->d_fix_counter;
     const uint32_t tr1 = exact ? 32 : b.tile_rows1, tr2 = exact ? 32 : b.tile_rows2;
-    if (!flat && !exact && !d_select && b.probe_keys && nq_launch == qv.n) {
+    if (!flat && !exact && !d_select && b.gemm_probe && nq_launch == qv.n) {
+        const MatView cent = ix->centroids->view();
+        GemmBufs gb;
+        gemm_take(b.gp_scratch, b.gp, qv.n, &gb);
+        CU(gemm_enqueue_prepass(cent, qv, b.gp, gb, b.gp_status, g_sm_count, c->stream, &c->launches));
+        CU(gemm_enqueue_filter(cent, qv, b.gp, gb, g_sm_count, c->stream, &c->launches));
+        CU(gemm_enqueue_select(cent, nullptr, 0, true, qv, b.gp, gb, (int)npe, b.gp_ids, b.gp_sims, b.gp_counts, b.gp_status,
+                               c->d_fix_counter, g_sm_count, c->stream, &c->launches));
+        probe_from_topk_kernel<<<(unsigned)qv.n, 128, 0, c->stream>>>(b.gp_ids, b.gp_sims, b.gp_counts, b.gp_status, (int)npe, b.probe,
+                                                                     d_probe_sims, b.qtiles, ix->list_off, tr2, d_status);
+        c->launches++;
+        if (stage1_only) return VS_OK;
+    } else if (!flat && !exact && !d_select && b.probe_keys && nq_launch == qv.n) {
         // a batch: score every (query, centroid) pair with the table read once, then select per query (probe.cu)
         LAUNCH(c, launch_probe_batch(ix->centroids->view(), qv, (int)npe, b.probe_keys, b.flag_cnt, b.flag_list, probe_flag_cap(ix->C), b.cand_keys, b.cand_ids, b.probe,
                                      d_probe_sims, b.qtiles, ix->list_off, tr2, d_status, kStatusProbeAmbiguous, 1, c->d_fix_counter,
@@ -1160,7 +1221,8 @@ static int search_setup(vs_ctx *c, Arena &a, const vs_index *ix, size_t nq, size
     if (!s->kpl1) return fail(VS_ERANGE, "nprobe=%zu: at most 128 probed lists unless nprobe >= number of lists", nprobe);
     VS(search_plan(ix, nq, s->npe, s->flat, &s->b));
     VS(a.reserve(a.off + extra_bytes + search_bytes(nq, s->npe, s->kpl1, s->kpl2, s->b.grid, ix->data->d) +
-                 (use_probe_batch(ix, nq, s->npe, s->flat) ? probe_batch_bytes(nq, ix->C, s->npe) : 0)));
+                 (use_probe_gemm(ix, nq, s->npe, s->flat) ? probe_gemm_bytes(ix, nq, s->npe)
+                  : use_probe_batch(ix, nq, s->npe, s->flat) ? probe_batch_bytes(nq, ix->C, s->npe) : 0)));
     return VS_OK;
 }
 
@@ -1173,7 +1235,15 @@ static void search_take(Arena &a, const vs_index *ix, size_t nq, SearchSetup *s)
     s->b.qnorm = a.take<double>(nq * (size_t)ix->data->d);
     s->b.q_select = a.take<uint32_t>(nq);
     s->b.probe_keys = nullptr;
-    if (use_probe_batch(ix, nq, s->npe, s->flat)) {
+    s->b.gemm_probe = use_probe_gemm(ix, nq, s->npe, s->flat);
+    if (s->b.gemm_probe) {
+        s->b.gp = probe_gemm_plan(ix, nq, s->npe);
+        s->b.gp_scratch = a.take<char>(gemm_scratch_bytes(s->b.gp, nq));
+        s->b.gp_ids = a.take<uint64_t>(nq * s->npe);
+        s->b.gp_sims = a.take<float>(nq * s->npe);
+        s->b.gp_counts = a.take<int32_t>(nq);
+        s->b.gp_status = a.take<uint32_t>(nq);
+    } else if (use_probe_batch(ix, nq, s->npe, s->flat)) {
         s->b.probe_keys = a.take<uint32_t>(nq * ix->C);
         s->b.flag_cnt = a.take<unsigned int>(nq);
         s->b.flag_list = a.take<uint32_t>(nq * (size_t)probe_flag_cap(ix->C));

@@ -315,3 +315,30 @@ def test_batched_probe_literal_paths(vs, oracle):
             assert (f32_bits(hs[i, :counts[i]]) == f32_bits(want_sims)).all()
     assert ctx.slowpath_count() > 0
     ctx.close()
+
+
+def test_probe_selection_on_tensor_cores(vs, oracle):
+    """>= 16384 centroids and >= 64 queries: the probe stage runs through the int8 GEMM pipeline with k = nprobe
+    (sampled thresholds, fused filter, certified selection); same probe lists, similarities and hits as the oracle."""
+    n, d, C, nq, nprobe, k = 30000, 128, 16500, 70, 40, 10
+    rows = oracle.quantize_matrix_f32(unit_rows(n, d, 71))
+    cent = oracle.quantize_matrix_f32(unit_rows(C, d, 72))
+    cent[9000:9040] = cent[77]               # a run of identical centroids: ties by index
+    cent[123, :] = 0                          # zero centroid
+    lists = (np.arange(n) % C).astype(np.uint32)
+    doc = np.arange(n, dtype=np.uint64)
+    ix = vs.ivf.Index.build_assigned(rows, doc, lists, cent)
+    q = unit_rows(nq, d, 73)
+    q[5] = 0                                  # zero query: unusable for the filter -> the literal path
+    qs = oracle.quantize_matrix_f32(q)
+    qs[6] = cent[77]
+    probes, sims = ix.SelectProbes(qs, nprobe)
+    for i in range(nq):
+        wp, ws = oracle.select_probes(qs[i], cent, nprobe)
+        assert probes[i].tolist() == wp.tolist(), f"query {i}"
+        assert (f32_bits(sims[i]) == f32_bits(ws)).all(), f"query {i}"
+    ids, hs, counts = ix.Search(qs, nprobe, k)
+    for i in (0, 5, 6, 33, 69):
+        want_ids, want_sims = oracle.search(qs[i], cent, rows, lists, doc, nprobe, k)
+        assert ids[i, :counts[i]].tolist() == want_ids.tolist(), f"query {i}"
+        assert (f32_bits(hs[i, :counts[i]]) == f32_bits(want_sims)).all()
