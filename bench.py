@@ -14,7 +14,9 @@ step; the 7.7 GB store is >> the 126 MB L2).  The config's single-query latency 
   cpu_baseline  the oracle (CPU restatement of the reference's default backend) on the host cores
 
 N > 1 (torchrun): strong scaling -- the same 10M-row store striped across the ranks by row id, the
-centroid table replicated, shard-local top-k all-gathered over NCCL and merged on device.
+centroid table replicated, shard-local top-k all-gathered over NCCL and merged on device.  On several GPUs four
+search contexts (one CUDA stream each, the reference's one-closure-per-goroutine model) take the steps in turn, so
+one batch's exchange and probe selection overlap another batch's list scan.
 
 `--impl reference` times the reference's own CPU algorithm (the oracle port; Go is not in this image).
 """
@@ -49,9 +51,9 @@ def parse():
     ap.add_argument("--batch", type=int, default=int(os.environ.get("VS_BENCH_BATCH", 256)))
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-extra", action="store_true", help="skip the config-3 / config-4 side measurements")
-    ap.add_argument("--contexts", type=int, default=0, choices=[0, 1, 2],
+    ap.add_argument("--contexts", type=int, default=0, choices=[0, 1, 2, 3, 4],
                     help="search contexts (one CUDA stream each) that take the steps in turn, like the reference's "
-                         "one-closure-per-goroutine searches running side by side (0 = 1 on one GPU, 2 on several, where "
+                         "one-closure-per-goroutine searches running side by side (0 = 1 on one GPU, 4 on several, where "
                          "the per-step exchange is worth hiding behind the other context's list scan)")
     return ap.parse_args()
 
@@ -206,7 +208,7 @@ def run_b200(a):
     # (search.go:230); a closure is a vs_ctx = one CUDA stream + scratch.  Steps are handed to the contexts in turn, so
     # the small latency-bound kernels of one batch (probe selection, all-gather, merge) overlap the HBM-bound list scan
     # of the other.  Context 0 shares the stream the index was built on.
-    NC = a.contexts if a.contexts else (1 if world == 1 else 2)
+    NC = a.contexts if a.contexts else (1 if world == 1 else 4)
     streams = [stream] + [torch.cuda.Stream(device=device) for _ in range(NC - 1)]
     ctxs = [ctx] + [cp.Context(cuda_stream=st.cuda_stream) for st in streams[1:]]
     hits_all = [pkg.shard.PackedHits(B, k, device, world) for _ in range(NC)]   # local hits (+ gathered / merged for N > 1)
