@@ -961,6 +961,33 @@ select_kernel(MatView rows, const uint64_t *ids, uint64_t id_base, int unique_id
             __syncthreads();
         }
         const uint32_t tau_key = f32_to_key(tau[q]);
+        if (unique_ids && k > 16 && cnt <= 1024u) {
+            // Many hits wanted from few candidates, one entry per document (the probe stage: k = nprobe up to 128): no
+            // rounds.  Every candidate counts the candidates that rank before it -- (similarity desc, id asc) is a
+            // strict total order here -- and the first k write themselves to their rank.
+            int above = 0;
+            for (uint32_t e = threadIdx.x; e < cnt; e += kSelThreads) {
+                const uint32_t mk = ent[e].key;
+                const uint64_t mi = ent[e].id;
+                uint32_t rnk = 0;
+                for (uint32_t j = 0; j < cnt; j++) rnk += cand_better(ent[j].key, ent[j].id, mk, mi) ? 1u : 0u;
+                if (rnk < (uint32_t)k) {
+                    out_ids[(size_t)q * k + rnk] = mi;
+                    out_sims[(size_t)q * k + rnk] = key_to_f32(mk);
+                    above += (mk >= tau_key && mk != 1u) ? 1 : 0;
+                }
+            }
+            for (int o = 16; o; o >>= 1) above += __shfl_xor_sync(0xFFFFFFFFu, above, o);
+            if (lane == 0) s_widx[warp] = above;
+            __syncthreads();
+            if (threadIdx.x == 0) {
+                int sum = 0;
+                for (int w = 0; w < kSelThreads / 32; w++) sum += s_widx[w];
+                out_counts[q] = (int)min(cnt, (uint32_t)k);
+                status[q] = (sum < k) ? kStatusNeedMore : 0u;
+            }
+            continue;
+        }
         int emitted = 0, emitted_above = 0;
         for (int round = 0; round < k; round++) {
             uint32_t bk = 0;
