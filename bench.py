@@ -157,7 +157,6 @@ def build_index(pkg, torch, ctx, a, rank, world, device):
     ctx.sync()
     t2 = time.time()
     ix = pkg.ivf.Index.build_dev(data, assign.data_ptr(), ids.data_ptr(), cent, ctx=ctx)
-    ix._d = D
     ctx.sync()
     del data, assign, ids
     torch.cuda.empty_cache()
@@ -584,6 +583,73 @@ def other_configs(pkg, torch, ctx, ix, a, device, peaks):
         del m1, qm
     except Exception as e:  # noqa: BLE001
         out["brute_force_config1"] = {"error": repr(e)[:300]}
+    try:
+        # One query against every row of the store (nprobe = all lists): the streaming scan the single-query path is made
+        # of, at a size where launch and merge latency no longer hide it.  776 B per row scored, device-timed.
+        peak = float(peaks.get("hbm_gbs", 6650.0))
+        xq = gen_unit_rows(torch, SEED_QUERY, 9100, 12, device)
+        torch.cuda.synchronize()
+        qm = cp.EmptyMatrix(12, D, ctx=ctx)
+        qm.FillFloat32Dev(0, xq.data_ptr(), 12, ctx=ctx)
+        ctx.sync()
+        qh = qm.ReadRows()
+        one = cp.EmptyMatrix(1, D, ctx=ctx)
+        d_ids = torch.zeros((1, a.k), dtype=torch.int64, device=device)
+        d_sims = torch.zeros((1, a.k), dtype=torch.float32, device=device)
+        d_counts = torch.zeros(1, dtype=torch.int32, device=device)
+        d_status = torch.zeros(1, dtype=torch.int32, device=device)
+        times = []
+        for i in range(12):
+            one.LoadRows(0, qh[i:i + 1], ctx=ctx)
+            ctx.sync()
+            ctx.timer_start()
+            ix.SearchDev(one, a.centroids, a.k, d_ids.data_ptr(), d_sims.data_ptr(), d_counts.data_ptr(), d_status.data_ptr(), ctx=ctx)
+            times.append(ctx.timer_stop())
+        times = sorted(times[2:])
+        ms = times[len(times) // 2]
+        gbs = a.rows * ROW_BYTES / (ms * 1e-3) / 1e9
+        # the same query through the probed path must agree on the hits both return when every list is probed
+        ix.Resolve(one, a.centroids, a.k, d_ids.data_ptr(), d_sims.data_ptr(), d_counts.data_ptr(), d_status.data_ptr(), ctx=ctx)
+        h_ids, h_sims, h_cnt = ix.Search(qh[11:12], a.centroids, a.k, ctx=ctx)
+        match = bool((d_ids.cpu().numpy().view(np.uint64)[0, :h_cnt[0]] == h_ids[0, :h_cnt[0]]).all())
+        out["single_query_full_scan"] = {
+            "workload": f"1 query x all {a.rows} rows ({a.rows * ROW_BYTES / 1e9:.2f} GB), top-{a.k}, device-resident, whole call "
+                        f"(scan + merges + emit)",
+            "ms_p50": round(ms, 4), "queries_per_s": round(1e3 / ms, 1),
+            "roofline": {"bound": "hbm", "kernel": "stage_kernel (flat scan + fused top-k)", "achieved": round(gbs, 1), "peak": peak,
+                         "unit": "GB/s", "frac": round(gbs / peak, 4), "bytes_per_launch": a.rows * ROW_BYTES, "launches_timed": len(times)},
+            "matches_host_call": match}
+        del one, qm
+    except Exception as e:  # noqa: BLE001
+        out["single_query_full_scan"] = {"error": repr(e)[:300]}
+    try:
+        # Upload (server/upload.go:239-279): new rows assigned to their nearest centroid and merged into the device index.
+        nu = min(100_000, a.rows)
+        xu = gen_unit_rows(torch, SEED_DATA, 7777, nu, device)
+        torch.cuda.synchronize()
+        um = cp.EmptyMatrix(nu, D, ctx=ctx)
+        um.FillFloat32Dev(0, xu.data_ptr(), nu, ctx=ctx)
+        ctx.sync()
+        new_rows = um.ReadRows()
+        del um, xu
+        new_ids = np.arange(a.rows, a.rows + nu, dtype=np.uint64)
+        t0 = time.perf_counter()
+        ix2, assign = ix.Upload(new_rows, new_ids, ctx=ctx)
+        dt = time.perf_counter() - t0
+        probe = [0, nu // 2, nu - 1]
+        h_ids, h_sims, h_cnt = ix2.Search(new_rows[probe], a.nprobe, a.k, ctx=ctx)
+        found = bool(all(int(new_ids[r]) in h_ids[j, :h_cnt[j]].tolist() for j, r in enumerate(probe)))
+        off2 = ix2.ListOffsets(ctx=ctx).astype(np.int64)
+        grew = bool((np.diff(off2) - np.diff(ix.ListOffsets(ctx=ctx).astype(np.int64)) == np.bincount(assign, minlength=a.centroids)).all())
+        out["upload"] = {
+            "workload": f"{nu} new rows (host buffers) into the {a.rows}-row index: nearest of {a.centroids} centroids, then one "
+                        f"merge pass of the store into the new list order",
+            "seconds": round(dt, 4), "rows_per_s": round(nu / dt, 1),
+            "store_copy_gbs": round(2.0 * (a.rows + nu) * ROW_BYTES / dt / 1e9, 1),
+            "uploaded_rows_found_by_search": found, "lists_grew_by_assignment": grew}
+        del ix2
+    except Exception as e:  # noqa: BLE001
+        out["upload"] = {"error": repr(e)[:300]}
     torch.cuda.empty_cache()
     return out
 

@@ -19,7 +19,7 @@ SYMBOLS = [
     "vs_matrix_release", "vs_matrix_rows", "vs_matrix_cols", "vs_matrix_read_rows", "vs_matrix_load_spool", "vs_matrix_save_spool", "vs_matrix_gather", "vs_matrix_split_dev", "vs_matrix_split", "vs_reassign_recenter", "vs_recenter_clusters_dev",
     "vs_cosine_1xN", "vs_dot_1xN", "vs_argmax_MxN", "vs_argmax_MxN_dev",
     "vs_index_build", "vs_index_build_assigned", "vs_index_build_dev", "vs_index_release",
-    "vs_index_rows", "vs_index_lists", "vs_index_list_offsets", "vs_index_read_rows", "vs_search", "vs_search_flat", "vs_search_flat_gemm", "vs_search_batch_dev", "vs_index_search_batch_dev", "vs_search_dev",
+    "vs_index_rows", "vs_index_lists", "vs_index_cols", "vs_index_list_offsets", "vs_index_read_rows", "vs_index_upload", "vs_search", "vs_search_flat", "vs_search_flat_gemm", "vs_search_batch_dev", "vs_index_search_batch_dev", "vs_search_dev",
     "vs_search_resolve", "vs_select_probes", "vs_topk_merge_dev", "vs_topk_merge_packed_dev",
     "vs_kmeans_step", "vs_kmeans", "vs_kmeans_accumulate_dev", "vs_kmeans_finish_dev", "vs_recenter", "vs_debug_set_argmax_gemm_min",
 ]
@@ -58,6 +58,7 @@ def load():
         L.vs_matrix_cols.restype = sz
         L.vs_index_rows.restype = sz
         L.vs_index_lists.restype = sz
+        L.vs_index_cols.restype = sz
         L.vs_matrix_retain.restype = None
         L.vs_matrix_release.restype = None
         L.vs_index_release.restype = None
@@ -65,7 +66,7 @@ def load():
         L.vs_shutdown.restype = None
         for name in ("vs_ctx_stream", "vs_ctx_launch_count", "vs_ctx_slowpath_count", "vs_ctx_destroy", "vs_ctx_sync",
                      "vs_ctx_timer_start", "vs_matrix_retain", "vs_matrix_release", "vs_matrix_rows", "vs_matrix_cols",
-                     "vs_index_release", "vs_index_rows", "vs_index_lists"):
+                     "vs_index_release", "vs_index_rows", "vs_index_lists", "vs_index_cols"):
             getattr(L, name).argtypes = [vp]
         L.vs_init.argtypes = [C.c_int]
         L.vs_debug_set_certify_scale.argtypes = [C.c_float]
@@ -80,6 +81,7 @@ def load():
         L.vs_matrix_load_rows.argtypes = [vp, vp, sz, vp, sz]
         L.vs_index_list_offsets.argtypes = [vp, vp, vp]
         L.vs_index_read_rows.argtypes = [vp, vp, sz, sz, vp, vp]
+        L.vs_index_upload.argtypes = [vp, vp, vp, sz, sz, vp, vp, C.POINTER(vp)]
         L.vs_ctx_timer_stop.argtypes = [vp, C.POINTER(C.c_float)]
         L.vs_device_info.argtypes = [C.c_char_p, sz, C.POINTER(C.c_int), C.POINTER(sz)]
         L.vs_quantize_f32.argtypes = [vp, vp, sz, sz, vp]

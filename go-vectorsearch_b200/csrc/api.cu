@@ -852,6 +852,7 @@ extern "C" void vs_index_release(vs_index *ix) {
 }
 extern "C" size_t vs_index_rows(const vs_index *ix) { return ix ? ix->n : 0; }
 extern "C" size_t vs_index_lists(const vs_index *ix) { return ix ? ix->C : 0; }
+extern "C" size_t vs_index_cols(const vs_index *ix) { return ix && ix->centroids ? (size_t)ix->centroids->d : 0; }
 
 extern "C" int vs_index_list_offsets(vs_ctx *c, const vs_index *ix, uint64_t *out) {
     VS(need_dev());
@@ -886,7 +887,10 @@ extern "C" int vs_index_build_dev(vs_ctx *c, const vs_matrix *data, const int32_
     const size_t n = data->n, C = centroids->n;
     uint32_t *d_order = nullptr, *d_keys_sorted = nullptr;
     CU(cudaMalloc(&d_order, n * 4 + 4));
-    CU(cudaMalloc(&d_keys_sorted, n * 4 + 4));
+    if (cudaMalloc(&d_keys_sorted, n * 4 + 4) != cudaSuccess) {
+        cudaFree(d_order);
+        return fail(VS_ENOMEM, "cudaMalloc for the sorted list keys of %zu rows", n);
+    }
     int rc = sort_rows_by_key(c, reinterpret_cast<const uint32_t *>(d_list_of_row), n, bits_for(C), d_order, d_keys_sorted);
     vs_index *ix = nullptr;
     vs_matrix *g = nullptr;
@@ -898,6 +902,8 @@ extern "C" int vs_index_build_dev(vs_ctx *c, const vs_matrix *data, const int32_
         ix->data = g;
         ix->centroids = const_cast<vs_matrix *>(centroids);
         vs_matrix_retain(ix->centroids);
+        ix->id_base = id_base;
+        ix->implicit_ids = d_doc_ids == nullptr;
         cudaError_t e = cudaMalloc(&ix->doc_ids, n * 8 + 8);
         if (e == cudaSuccess) e = cudaMalloc(&ix->list_off, (C + 1) * 8);
         if (e == cudaSuccess)
@@ -979,6 +985,100 @@ extern "C" int vs_index_build(vs_ctx *c, const uint8_t *rows, size_t n, size_t r
         return rc;
     }
     *out = ix;
+    return VS_OK;
+}
+
+// ---- Upload: new rows into an existing index (server/upload.go:239-279) ----
+// list_off of the merged store: every list keeps its rows and gets the uploaded rows assigned to it after them.
+__global__ void merged_offsets_kernel(const uint64_t *old_off, const uint32_t *add_off, size_t C, uint64_t *new_off) {
+    const size_t c = blockIdx.x * (size_t)blockDim.x + threadIdx.x;
+    if (c <= C) new_off[c] = old_off[c] + add_off[c];
+}
+// order[i] = source of merged row i: a row of the old store, or (bit 31) an uploaded row, in upload order within a list.
+__global__ void merge_order_kernel(const uint64_t *old_off, const uint32_t *add_off, const uint64_t *new_off,
+                                   const uint32_t *add_order, size_t C, size_t n_total, uint32_t *order) {
+    for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n_total; i += (size_t)gridDim.x * blockDim.x) {
+        size_t lo = 0, hi = C;  // first list boundary beyond i; new_off[0] = 0 <= i < new_off[C] = n_total
+        while (lo < hi) {
+            const size_t mid = (lo + hi) >> 1;
+            if (new_off[mid] <= i) lo = mid + 1;
+            else hi = mid;
+        }
+        const size_t l = lo - 1;
+        const uint64_t p = i - new_off[l], old_len = old_off[l + 1] - old_off[l];
+        order[i] = p < old_len ? (uint32_t)(old_off[l] + p) : (0x80000000u | add_order[add_off[l] + (p - old_len)]);
+    }
+}
+
+static int index_upload_core(vs_ctx *c, const vs_index *ix, const vs_matrix *nm, const uint64_t *doc_ids, int64_t *assign_out,
+                             vs_index *nx) {
+    const size_t n = nm->n, C = ix->C, n_total = ix->n + n, d = (size_t)nm->d;
+    const size_t sort_ws = sort_rows_ws_bytes(n);
+    Arena a(c);
+    VS(a.reserve(argmax_bytes(C, n, d) + 3 * Arena::pad(n * 4) + sort_ws + Arena::pad((C + 1) * 4) + Arena::pad(n_total * 4) +
+                 Arena::pad(n * 8) + 4096));
+    int32_t *d_assign = a.take<int32_t>(n);
+    uint32_t *d_add_order = a.take<uint32_t>(n);
+    uint32_t *d_keys_sorted = a.take<uint32_t>(n);
+    char *ws = a.take<char>(sort_ws);
+    uint32_t *d_add_off = a.take<uint32_t>(C + 1);
+    uint32_t *d_order = a.take<uint32_t>(n_total);
+    uint64_t *d_new_ids = doc_ids ? a.take<uint64_t>(n) : nullptr;
+    // upload.go:245: centroids.MatrixCosineSimilarity(embeddings) -> nearest centroid of every new row, lowest index on ties
+    VS(argmax_dev(c, a, ix->centroids->view(), nm->view(), d_assign, nullptr));
+    VS(sort_rows_by_key(c, reinterpret_cast<const uint32_t *>(d_assign), n, bits_for(C), d_add_order, d_keys_sorted, ws, sort_ws));
+    const unsigned cb = (unsigned)((C + 1 + 255) / 256);
+    lower_bound_kernel<<<cb, 256, 0, c->stream>>>(d_keys_sorted, n, nullptr, d_add_off, C);
+    CU(cudaGetLastError());
+    merged_offsets_kernel<<<cb, 256, 0, c->stream>>>(ix->list_off, d_add_off, C, nx->list_off);
+    CU(cudaGetLastError());
+    merge_order_kernel<<<g_sm_count * 4, 256, 0, c->stream>>>(ix->list_off, d_add_off, nx->list_off, d_add_order, C, n_total, d_order);
+    CU(cudaGetLastError());
+    c->launches += 3;
+    if (doc_ids) CU(cudaMemcpyAsync(d_new_ids, doc_ids, n * 8, cudaMemcpyHostToDevice, c->stream));
+    LAUNCH(c, launch_merge_rows(ix->data->view(), ix->doc_ids, ix->id_base, nm->view(), d_new_ids, ix->id_base + ix->n, d_order, n_total,
+                                nx->data->codes, nx->data->hdr, nx->data->sums, nx->doc_ids, c->stream));
+    std::vector<int32_t> tmp;
+    if (assign_out) {
+        tmp.resize(n);
+        CU(cudaMemcpyAsync(tmp.data(), d_assign, n * 4, cudaMemcpyDeviceToHost, c->stream));
+    }
+    CU(cudaStreamSynchronize(c->stream));
+    for (size_t i = 0; i < tmp.size(); i++) assign_out[i] = tmp[i];
+    return VS_OK;
+}
+
+extern "C" int vs_index_upload(vs_ctx *c, const vs_index *ix, const uint8_t *rows, size_t n, size_t row_bytes, const uint64_t *doc_ids,
+                               int64_t *assign_out, vs_index **out) {
+    VS(need_dev());
+    if (!c || !ix || !rows || !out) return fail(VS_EINVAL, "null argument");
+    VS(check_rows(n, row_bytes));
+    if (ix->C == 0) return fail(VS_EINVAL, "the index has no centroids");  // compute.go:26: NewMatrix panics on 0 rows
+    if ((size_t)ix->centroids->d != row_bytes - 8)                          // cosine.go:77-79
+        return fail(VS_EDIM, "matrix/matrix column size does not match: %d != %zu", ix->centroids->d, row_bytes - 8);
+    const bool implicit = ix->implicit_ids || !ix->doc_ids;
+    if (!implicit && !doc_ids) return fail(VS_EINVAL, "the index holds explicit document ids: doc_ids is required");
+    if (ix->n + n > 0x7FFFFFFFull) return fail(VS_ERANGE, "n=%zu: a device matrix holds < 2^31 rows", ix->n + n);
+    vs_matrix *nm = nullptr;
+    VS(vs_matrix_create(c, rows, n, row_bytes, &nm));
+    vs_index *nx = new vs_index();
+    nx->n = ix->n + n;
+    nx->C = ix->C;
+    nx->centroids = ix->centroids;
+    vs_matrix_retain(nx->centroids);
+    nx->id_base = ix->id_base;
+    nx->implicit_ids = implicit && !doc_ids;
+    int rc = matrix_alloc(nx->n, (size_t)nm->d, &nx->data);
+    if (rc == VS_OK && cudaMalloc(&nx->list_off, (nx->C + 1) * 8) != cudaSuccess) rc = fail(VS_ENOMEM, "cudaMalloc list offsets");
+    if (rc == VS_OK && cudaMalloc(&nx->doc_ids, nx->n * 8 + 8) != cudaSuccess) rc = fail(VS_ENOMEM, "cudaMalloc document ids");
+    if (rc == VS_OK) rc = index_upload_core(c, ix, nm, doc_ids, assign_out, nx);
+    if (rc != VS_OK) cudaStreamSynchronize(c->stream);  // nothing may still read nm / nx when they are freed
+    vs_matrix_release(nm);
+    if (rc != VS_OK) {
+        vs_index_release(nx);
+        return rc;
+    }
+    *out = nx;
     return VS_OK;
 }
 

@@ -52,6 +52,7 @@ struct vs_index {
     vs_matrix *centroids = nullptr;  // C rows
     uint64_t *doc_ids = nullptr;     // [n] device (may be null -> id = id_base + row)
     uint64_t id_base = 0;
+    bool implicit_ids = false;       // built without document ids: rows are numbered id_base + primary-key order
     uint64_t *list_off = nullptr;    // [C+1] device
     size_t n = 0, C = 0;
 };
@@ -189,6 +190,9 @@ cudaError_t launch_export(const MatView &m, size_t first, size_t count, uint8_t 
 cudaError_t launch_gather_rows(const MatView &src, const uint32_t *order, size_t n, uint8_t *codes, float2 *hdr,
                                uint2 *sums, const uint64_t *ids_in, uint64_t id_base, uint64_t *ids_out,
                                cudaStream_t st);
+cudaError_t launch_merge_rows(const MatView &a, const uint64_t *a_ids, uint64_t a_id_base, const MatView &b, const uint64_t *b_ids,
+                              uint64_t b_id_base, const uint32_t *order, size_t n, uint8_t *codes, float2 *hdr, uint2 *sums,
+                              uint64_t *ids_out, cudaStream_t st);
 
 // argmax.cu
 cudaError_t launch_argmax(const MatView &cent, const MatView &data, const uint32_t *canon, int32_t *idx_out,

@@ -261,4 +261,40 @@ cudaError_t launch_gather_rows(const MatView &src, const uint32_t *order, size_t
     return cudaGetLastError();
 }
 
+// dst row i <- row (order[i] & 0x7fffffff) of `a`, or of `b` when bit 31 of order[i] is set: the rows of an index and a batch
+// of uploaded rows interleaved into the new list order (vs_index_upload).  Same copy shape as gather_rows_kernel: a warp per
+// row, 128-bit loads and stores, 776+ B read and written once per row.
+__global__ void __launch_bounds__(kRowWarps * 32) merge_rows_kernel(MatView a, const uint64_t *__restrict__ a_ids, uint64_t a_id_base,
+                                                                    MatView b, const uint64_t *__restrict__ b_ids, uint64_t b_id_base,
+                                                                    const uint32_t *__restrict__ order, size_t n,
+                                                                    uint8_t *__restrict__ codes, float2 *__restrict__ hdr,
+                                                                    uint2 *__restrict__ sums, uint64_t *__restrict__ ids_out) {
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int CH = a.d_pad >> 4;
+    for (size_t i = (size_t)blockIdx.x * kRowWarps + warp; i < n; i += (size_t)gridDim.x * kRowWarps) {
+        const uint32_t o = order[i];
+        const bool from_b = (o >> 31) != 0;
+        const size_t s = o & 0x7fffffffu;
+        const uint8_t *sc = from_b ? b.codes : a.codes;   // both matrices have the same d_pad
+        const uint4 *sp = reinterpret_cast<const uint4 *>(sc + s * (size_t)a.d_pad);
+        uint4 *dp = reinterpret_cast<uint4 *>(codes + i * (size_t)a.d_pad);
+        for (int c = lane; c < CH; c += 32) dp[c] = sp[c];
+        if (lane == 0) {
+            hdr[i] = (from_b ? b.hdr : a.hdr)[s];
+            sums[i] = (from_b ? b.sums : a.sums)[s];
+            const uint64_t *ids = from_b ? b_ids : a_ids;
+            ids_out[i] = ids ? ids[s] : (from_b ? b_id_base : a_id_base) + s;
+        }
+    }
+}
+
+cudaError_t launch_merge_rows(const MatView &a, const uint64_t *a_ids, uint64_t a_id_base, const MatView &b, const uint64_t *b_ids,
+                              uint64_t b_id_base, const uint32_t *order, size_t n, uint8_t *codes, float2 *hdr, uint2 *sums,
+                              uint64_t *ids_out, cudaStream_t st) {
+    if (n == 0) return cudaSuccess;
+    merge_rows_kernel<<<row_grid(n), kRowWarps * 32, 0, st>>>(a, a_ids, a_id_base, b, b_ids, b_id_base, order, n, codes, hdr, sums,
+                                                             ids_out);
+    return cudaGetLastError();
+}
+
 }  // namespace vs

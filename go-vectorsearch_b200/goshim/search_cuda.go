@@ -50,6 +50,23 @@ func (ix *Index) Search(query []uint8, nprobe int, k int) (documentIDs []uint64,
 	return ids[:count], sims[:count]
 }
 
+// Upload is the assignment of server/upload.go:239-279 plus the insert into the device store: every new embedding goes to
+// its nearest centroid (upload.go:245) and joins that posting list behind the rows already there.  centroidIndex[i] is
+// what upload.go:268-271 turns into Embedding.CentroidID (centroids[centroidIndex[i]].ID).  The receiver stays valid for
+// searches in flight; the server swaps its category's *Index for the returned one.
+func (ix *Index) Upload(rows [][]uint8, documentIDs []uint64) (next *Index, centroidIndex []int64) {
+	rbuf, n, rowBytes := pack(rows)
+	defer C.free(rbuf)
+	centroidIndex = make([]int64, n)
+	next = &Index{}
+	withDefaultCtx(func(c *ctx) {
+		check(C.vs_index_upload(c.h, ix.h, (*C.uint8_t)(rbuf), C.size_t(n), C.size_t(rowBytes),
+			(*C.uint64_t)(unsafe.Pointer(&documentIDs[0])), (*C.int64_t)(unsafe.Pointer(&centroidIndex[0])), &next.h))
+	})
+	runtime.SetFinalizer(next, func(ix *Index) { C.vs_index_release(ix.h) })
+	return next, centroidIndex
+}
+
 // KMeansStep is one iteration of dnc/k_means.go:67-117 on a device matrix. means is the [k][d] float32 state the
 // reference carries between iterations (flattened); it is updated in place.
 func KMeansStep(data Matrix, centroids [][]uint8, means []float32) (counts []int64, newCentroids [][]uint8, converged bool) {

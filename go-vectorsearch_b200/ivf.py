@@ -63,6 +63,19 @@ class Index:
                                     centroids.handle, C.byref(h)))
         return cls(h, L)
 
+    def Upload(self, rows, doc_ids=None, ctx=None):
+        """Upload's assignment and insert (server/upload.go:239-279): every new row joins the list of its nearest centroid
+        (upload.go:245) behind the rows already there.  Returns (new Index, assign int64[n]); this Index stays valid."""
+        ctx = ctx or default_context()
+        rows = _rows_array(rows)
+        ids = None if doc_ids is None else np.ascontiguousarray(doc_ids, dtype=np.uint64)
+        assert ids is None or ids.shape == (rows.shape[0],)
+        assign = np.empty(rows.shape[0], np.int64)
+        h = C.c_void_p()
+        _check(self._L.vs_index_upload(ctx.handle, self._h, _p(rows), rows.shape[0], rows.shape[1],
+                                       _p(ids) if ids is not None else None, _p(assign), C.byref(h)))
+        return Index(h, self._L), assign
+
     def ListOffsets(self, ctx=None):
         ctx = ctx or default_context()
         out = np.empty(self.lists + 1, np.uint64)
@@ -72,16 +85,11 @@ class Index:
     def ReadRows(self, first, count, ctx=None):
         """(rows776, ids) of the grouped store."""
         ctx = ctx or default_context()
-        width = 8 + self._cols(ctx)
+        width = 8 + self.cols
         rows = np.empty((count, width), np.uint8)
         ids = np.empty(count, np.uint64)
         _check(self._L.vs_index_read_rows(ctx.handle, self._h, int(first), int(count), _p(rows), _p(ids)))
         return rows, ids
-
-    def _cols(self, ctx):
-        if not hasattr(self, "_d"):
-            raise RuntimeError("set index._d (dimension) before ReadRows")
-        return self._d
 
     def SearchDev(self, queries, nprobe, k, d_ids, d_sims, d_counts, d_status, ctx=None):
         """Asynchronous device-resident search: queries is a compute.Matrix, outputs are raw device pointers."""
@@ -110,6 +118,10 @@ class Index:
     @property
     def rows(self):
         return int(self._L.vs_index_rows(self._h))
+
+    @property
+    def cols(self):
+        return int(self._L.vs_index_cols(self._h))
 
     @property
     def lists(self):

@@ -155,9 +155,20 @@ VS_API int vs_index_build_dev(vs_ctx *ctx, const vs_matrix *data, const int32_t 
 VS_API void vs_index_release(vs_index *ix);
 VS_API size_t vs_index_rows(const vs_index *ix);
 VS_API size_t vs_index_lists(const vs_index *ix);
+VS_API size_t vs_index_cols(const vs_index *ix);   /* vector size of the rows (row776 is 8 + this many bytes) */
 /* Read back the CSR offsets (C+1 values) and rows [first, first+count) of the grouped store with their ids. */
 VS_API int vs_index_list_offsets(vs_ctx *ctx, const vs_index *ix, uint64_t *offsets_out);
 VS_API int vs_index_read_rows(vs_ctx *ctx, const vs_index *ix, size_t first, size_t count, uint8_t *rows_out, uint64_t *ids_out);
+/* Upload's assignment and insert (server/upload.go:239-279): every new row (row776, host) goes to its nearest centroid
+ * (centroids.MatrixCosineSimilarity(embeddings), upload.go:245; lowest index wins ties, cosine.go:114) and joins that
+ * list behind the rows already there -- new embeddings get larger primary keys and search.go:241-243 streams a list in
+ * primary-key order.  *out is a NEW index holding the old and the new rows (one pass at copy bandwidth: no re-sort of
+ * the store, no host round trip); the old handle stays valid for the searches in flight and is released by the caller.
+ * doc_ids[n] = Embedding.DocumentID of the new rows: required when the index was built with explicit ids, else NULL
+ * continues the implicit numbering (id_base + row).  assign_out[n] (nullable) = the list index of every new row, what
+ * upload.go:268-271 turns into Embedding.CentroidID.  Errors as NewMatrix / MatrixCosineSimilarity: VS_EEMPTY, VS_EDIM. */
+VS_API int vs_index_upload(vs_ctx *ctx, const vs_index *ix, const uint8_t *rows_packed, size_t n, size_t row_bytes,
+                    const uint64_t *doc_ids, int64_t *assign_out, vs_index **out);
 /* Search (search.go:115-273 minus embedding/DB hops): nq query rows (row776, host), nprobe =
  * SearchRequest.Centroids (>= number of lists means "all"), k = Count+Offset.  Outputs (host):
  * ids_out[nq*k] document IDs, sims_out[nq*k] float32 similarities, counts_out[nq] valid entries.

@@ -134,6 +134,18 @@ def argmax_MxN(cent, rows):
     return sims, idx
 
 
+def upload(centroids, new_rows, list_of_row, rows=None, doc_ids=None, new_doc_ids=None):
+    """The state of the embeddings table after Upload (server/upload.go:239-279): the new rows are appended (larger
+    primary keys, upload.go:284-287) with CentroidID = the nearest centroid (centroids.MatrixCosineSimilarity(new rows),
+    upload.go:245).  Returns (assign of the new rows, list_of_row of old + new, rows, doc_ids); the last two are None
+    when not given."""
+    _, assign = argmax_MxN(centroids, new_rows)
+    lists = np.concatenate([np.asarray(list_of_row, dtype=np.uint32), assign.astype(np.uint32)])
+    all_rows = None if rows is None else np.concatenate([_u8(rows), _u8(new_rows)])
+    all_ids = None if doc_ids is None else np.concatenate([np.asarray(doc_ids, np.uint64), np.asarray(new_doc_ids, np.uint64)])
+    return assign, lists, all_rows, all_ids
+
+
 def select_probes(q, centroids, nprobe):
     q = _u8(q)
     centroids = _u8(centroids)
