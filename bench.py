@@ -129,38 +129,58 @@ def gen_unit_rows(torch, seed, chunk_index, count, device):
 def build_index(pkg, torch, ctx, a, rank, world, device):
     """Synthetic store, generated and quantized on device, assigned to its nearest centroid, grouped into lists."""
     cp = pkg.compute
-    t0 = time.time()
     cent = cp.EmptyMatrix(a.centroids, D, ctx=ctx)
     x = gen_unit_rows(torch, SEED_CENT, 0, a.centroids, device)
     torch.cuda.synchronize()
     cent.FillFloat32Dev(0, x.data_ptr(), a.centroids, ctx=ctx)
     ctx.sync()
     n_local = pkg.shard.local_count(a.rows, rank, world)
-    data = cp.EmptyMatrix(n_local, D, ctx=ctx)
-    filled = 0
-    for ci, r0 in enumerate(range(0, a.rows, CHUNK)):
-        cnt = min(CHUNK, a.rows - r0)
-        x = gen_unit_rows(torch, SEED_DATA, ci, cnt, device)
-        first = (rank - r0) % world          # first row of this chunk owned by this rank
-        xs = x[first::world].contiguous()
-        torch.cuda.synchronize()
-        data.FillFloat32Dev(filled, xs.data_ptr(), xs.shape[0], ctx=ctx)
-        ctx.sync()
-        filled += xs.shape[0]
-        del x, xs
-    assert filled == n_local, (filled, n_local)
-    ids = torch.arange(rank, a.rows, world, device=device, dtype=torch.int64)
+    # The store goes through the streaming loader (vs_index_create_empty / vs_index_fill_dev), so HBM holds it once plus
+    # one chunk.  Pass 1: nearest centroid of every row (compute/cosine.go:70-125), kept as int32, and the per-list row
+    # counts; pass 2: the same chunks again (the generator is keyed by chunk), each placed straight into its lists.
     assign = torch.empty(n_local, device=device, dtype=torch.int32)
-    torch.cuda.synchronize()
-    t1 = time.time()
-    cent.ArgmaxDev(data, assign.data_ptr(), ctx=ctx)   # nearest centroid of every row (compute/cosine.go:70-125)
-    ctx.sync()
-    t2 = time.time()
-    ix = pkg.ivf.Index.build_dev(data, assign.data_ptr(), ids.data_ptr(), cent, ctx=ctx)
-    ctx.sync()
-    del data, assign, ids
+    gen_s = assign_s = fill_s = 0.0
+
+    def chunks():
+        filled = 0
+        for ci, r0 in enumerate(range(0, a.rows, CHUNK)):
+            cnt = min(CHUNK, a.rows - r0)
+            first = (rank - r0) % world          # first row of this chunk owned by this rank
+            if first >= cnt:
+                continue
+            t = time.time()
+            x = gen_unit_rows(torch, SEED_DATA, ci, cnt, device)
+            xs = x[first::world].contiguous()
+            torch.cuda.synchronize()
+            m = cp.EmptyMatrix(xs.shape[0], D, ctx=ctx)
+            m.FillFloat32Dev(0, xs.data_ptr(), xs.shape[0], ctx=ctx)
+            ctx.sync()
+            del x, xs
+            yield m, filled, r0 + first, time.time() - t
+            filled += m.rows
+        assert filled == n_local, (filled, n_local)
+
+    for m, at, _, dt in chunks():
+        gen_s += dt
+        t = time.time()
+        cent.ArgmaxDev(m, assign[at:at + m.rows].data_ptr(), ctx=ctx)
+        ctx.sync()
+        assign_s += time.time() - t
+    counts = torch.bincount(assign, minlength=a.centroids).cpu().numpy().astype(np.uint64)
+    ix = pkg.ivf.Index.create_empty(cent, counts, ctx=ctx)
+    for m, at, key0, dt in chunks():
+        gen_s += dt
+        t = time.time()
+        ids = torch.arange(key0, key0 + m.rows * world, world, device=device, dtype=torch.int64)
+        torch.cuda.synchronize()
+        ix.FillDev(m, assign[at:at + m.rows].data_ptr(), ids.data_ptr(), ctx=ctx)
+        ctx.sync()
+        fill_s += time.time() - t
+        del ids
+    del assign
     torch.cuda.empty_cache()
-    return ix, cent, {"gen_quantize_s": round(t1 - t0, 2), "assign_s": round(t2 - t1, 2), "group_s": round(time.time() - t2, 2)}
+    return ix, cent, {"gen_quantize_s": round(gen_s, 2), "assign_s": round(assign_s, 2), "group_s": round(fill_s, 2),
+                      "loader": "streaming (two passes over the generator; the store is held once)"}
 
 
 def run_b200(a):

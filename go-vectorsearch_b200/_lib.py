@@ -18,7 +18,7 @@ SYMBOLS = [
     "vs_matrix_create", "vs_matrix_create_empty", "vs_matrix_fill_f32_dev", "vs_matrix_load_rows", "vs_matrix_create_dev", "vs_matrix_from_f32_dev", "vs_matrix_retain",
     "vs_matrix_release", "vs_matrix_rows", "vs_matrix_cols", "vs_matrix_read_rows", "vs_matrix_load_spool", "vs_matrix_save_spool", "vs_matrix_gather", "vs_matrix_split_dev", "vs_matrix_split", "vs_reassign_recenter", "vs_recenter_clusters_dev",
     "vs_cosine_1xN", "vs_dot_1xN", "vs_argmax_MxN", "vs_argmax_MxN_dev",
-    "vs_index_build", "vs_index_build_assigned", "vs_index_build_dev", "vs_index_release",
+    "vs_index_build", "vs_index_build_assigned", "vs_index_build_dev", "vs_index_create_empty", "vs_index_fill_dev", "vs_index_fill", "vs_index_release",
     "vs_index_rows", "vs_index_lists", "vs_index_cols", "vs_index_list_offsets", "vs_index_read_rows", "vs_index_upload", "vs_search", "vs_search_flat", "vs_search_flat_gemm", "vs_search_batch_dev", "vs_index_search_batch_dev", "vs_search_dev",
     "vs_search_resolve", "vs_select_probes", "vs_topk_merge_dev", "vs_topk_merge_packed_dev",
     "vs_kmeans_step", "vs_kmeans", "vs_kmeans_accumulate_dev", "vs_kmeans_finish_dev", "vs_recenter", "vs_debug_set_argmax_gemm_min",
@@ -82,6 +82,9 @@ def load():
         L.vs_index_list_offsets.argtypes = [vp, vp, vp]
         L.vs_index_read_rows.argtypes = [vp, vp, sz, sz, vp, vp]
         L.vs_index_upload.argtypes = [vp, vp, vp, sz, sz, vp, vp, C.POINTER(vp)]
+        L.vs_index_create_empty.argtypes = [vp, vp, vp, C.POINTER(vp)]
+        L.vs_index_fill_dev.argtypes = [vp, vp, vp, vp, vp, u64]
+        L.vs_index_fill.argtypes = [vp, vp, vp, sz, sz, vp, vp, u64]
         L.vs_ctx_timer_stop.argtypes = [vp, C.POINTER(C.c_float)]
         L.vs_device_info.argtypes = [C.c_char_p, sz, C.POINTER(C.c_int), C.POINTER(sz)]
         L.vs_quantize_f32.argtypes = [vp, vp, sz, sz, vp]

@@ -846,6 +846,7 @@ extern "C" void vs_index_release(vs_index *ix) {
     if (ix->data) cudaSetDevice(ix->data->device);
     if (ix->doc_ids) cudaFree(ix->doc_ids);
     if (ix->list_off) cudaFree(ix->list_off);
+    if (ix->fill_cursor) cudaFree(ix->fill_cursor);
     vs_matrix_release(ix->data);
     vs_matrix_release(ix->centroids);
     delete ix;
@@ -988,6 +989,109 @@ extern "C" int vs_index_build(vs_ctx *c, const uint8_t *rows, size_t n, size_t r
     return VS_OK;
 }
 
+// ---- Streaming loader: database -> HBM with centroid_id grouping (database/model.go:9-18; search.go:241-243) ----
+__global__ void advance_cursor_kernel(const uint32_t *chunk_off, size_t C, uint64_t *cursor) {
+    const size_t c = blockIdx.x * (size_t)blockDim.x + threadIdx.x;
+    if (c < C) cursor[c] += chunk_off[c + 1] - chunk_off[c];
+}
+
+extern "C" int vs_index_create_empty(vs_ctx *c, const vs_matrix *centroids, const uint64_t *list_counts, vs_index **out) {
+    VS(need_dev());
+    if (!c || !centroids || !list_counts || !out) return fail(VS_EINVAL, "null argument");
+    const size_t C = centroids->n;
+    if (C == 0) return fail(VS_EEMPTY, "matrix rows are empty");  // compute.go:25-27
+    std::vector<uint64_t> off(C + 1, 0);
+    for (size_t l = 0; l < C; l++) off[l + 1] = off[l] + list_counts[l];
+    const size_t n = off[C];
+    vs_index *ix = new vs_index();
+    ix->n = n;
+    ix->C = C;
+    ix->centroids = const_cast<vs_matrix *>(centroids);
+    vs_matrix_retain(ix->centroids);
+    int rc = matrix_alloc(n, (size_t)centroids->d, &ix->data);
+    if (rc == VS_OK) {
+        cudaError_t e = cudaMalloc(&ix->doc_ids, n * 8 + 8);
+        if (e == cudaSuccess) e = cudaMalloc(&ix->list_off, (C + 1) * 8);
+        if (e == cudaSuccess) e = cudaMalloc(&ix->fill_cursor, (C + 1) * 8);  // [C] cursors + the overflow flag
+        if (e == cudaSuccess) e = cudaMemcpyAsync(ix->list_off, off.data(), (C + 1) * 8, cudaMemcpyHostToDevice, c->stream);
+        if (e == cudaSuccess) e = cudaMemsetAsync(ix->fill_cursor, 0, (C + 1) * 8, c->stream);
+        if (e == cudaSuccess) e = cudaStreamSynchronize(c->stream);
+        if (e != cudaSuccess) rc = fail(VS_ECUDA, "empty index of %zu rows: %s", n, cudaGetErrorString(e));
+    }
+    if (rc != VS_OK) {
+        vs_index_release(ix);
+        return rc;
+    }
+    *out = ix;
+    return VS_OK;
+}
+
+extern "C" int vs_index_fill_dev(vs_ctx *c, vs_index *ix, const vs_matrix *chunk, const int32_t *d_list_of_row, const uint64_t *d_doc_ids,
+                                 uint64_t id_base) {
+    VS(need_dev());
+    if (!c || !ix || !chunk || !d_list_of_row) return fail(VS_EINVAL, "null argument");
+    if (!ix->fill_cursor) return fail(VS_EINVAL, "the index was not created by vs_index_create_empty");
+    if (chunk->d != ix->data->d) return fail(VS_EDIM, "data/centroid column size does not match: %d != %d", chunk->d, ix->data->d);
+    const size_t m = chunk->n, C = ix->C;
+    if (m == 0) return VS_OK;
+    if (ix->filled + m > ix->n) return fail(VS_EINVAL, "%zu rows do not fit: %zu of %zu already placed", m, ix->filled, ix->n);
+    const size_t sort_ws = sort_rows_ws_bytes(m);
+    Arena a(c);
+    VS(a.reserve(2 * Arena::pad(m * 4) + sort_ws + Arena::pad((C + 1) * 4) + 4096));
+    uint32_t *d_order = a.take<uint32_t>(m);
+    uint32_t *d_keys_sorted = a.take<uint32_t>(m);
+    char *ws = a.take<char>(sort_ws);
+    uint32_t *d_chunk_off = a.take<uint32_t>(C + 1);
+    unsigned int *d_overflow = reinterpret_cast<unsigned int *>(ix->fill_cursor + C);
+    // a list index >= C sorts behind every list and is caught by the row count below
+    VS(sort_rows_by_key(c, reinterpret_cast<const uint32_t *>(d_list_of_row), m, 32, d_order, d_keys_sorted, ws, sort_ws));
+    const unsigned cb = (unsigned)((C + 1 + 255) / 256);
+    lower_bound_kernel<<<cb, 256, 0, c->stream>>>(d_keys_sorted, m, nullptr, d_chunk_off, C);
+    CU(cudaGetLastError());
+    c->launches++;
+    VS(pinned_reserve(c, 64));
+    unsigned int *h = static_cast<unsigned int *>(c->pinned);
+    CU(cudaMemcpyAsync(h, d_chunk_off + C, 4, cudaMemcpyDeviceToHost, c->stream));
+    CU(cudaStreamSynchronize(c->stream));
+    if (h[0] != m) return fail(VS_EINVAL, "%zu row(s) of the chunk name a list >= %zu", m - (size_t)h[0], C);
+    LAUNCH(c, launch_scatter_rows(chunk->view(), d_order, d_keys_sorted, d_chunk_off, ix->list_off, ix->fill_cursor, ix->data->codes,
+                                  ix->data->hdr, ix->data->sums, d_doc_ids, id_base, ix->doc_ids, d_overflow, c->stream));
+    advance_cursor_kernel<<<cb, 256, 0, c->stream>>>(d_chunk_off, C, ix->fill_cursor);
+    CU(cudaGetLastError());
+    c->launches++;
+    CU(cudaMemcpyAsync(h, d_overflow, 4, cudaMemcpyDeviceToHost, c->stream));
+    CU(cudaStreamSynchronize(c->stream));
+    if (h[0] != 0) return fail(VS_EINVAL, "a list received more rows than vs_index_create_empty reserved for it");
+    ix->filled += m;
+    return VS_OK;
+}
+
+extern "C" int vs_index_fill(vs_ctx *c, vs_index *ix, const uint8_t *rows, size_t n, size_t row_bytes, const uint32_t *list_of_row,
+                             const uint64_t *doc_ids, uint64_t id_base) {
+    VS(need_dev());
+    if (!c || !ix || !rows || !list_of_row) return fail(VS_EINVAL, "null argument");
+    VS(check_rows(n, row_bytes));
+    vs_matrix *chunk = nullptr;
+    VS(vs_matrix_create(c, rows, n, row_bytes, &chunk));
+    int32_t *d_list = nullptr;
+    uint64_t *d_ids = nullptr;
+    int rc = VS_OK;
+    if (cudaMalloc(&d_list, n * 4 + 4) != cudaSuccess) rc = fail(VS_ENOMEM, "cudaMalloc list_of_row");
+    if (rc == VS_OK && doc_ids && cudaMalloc(&d_ids, n * 8 + 8) != cudaSuccess) rc = fail(VS_ENOMEM, "cudaMalloc doc_ids");
+    if (rc == VS_OK) {
+        cudaError_t e = cudaMemcpyAsync(d_list, list_of_row, n * 4, cudaMemcpyHostToDevice, c->stream);
+        if (e == cudaSuccess && doc_ids) e = cudaMemcpyAsync(d_ids, doc_ids, n * 8, cudaMemcpyHostToDevice, c->stream);
+        if (e == cudaSuccess) e = cudaStreamSynchronize(c->stream);
+        if (e != cudaSuccess) rc = fail(VS_ECUDA, "chunk upload: %s", cudaGetErrorString(e));
+    }
+    if (rc == VS_OK) rc = vs_index_fill_dev(c, ix, chunk, d_list, d_ids, id_base);
+    cudaStreamSynchronize(c->stream);
+    if (d_list) cudaFree(d_list);
+    if (d_ids) cudaFree(d_ids);
+    vs_matrix_release(chunk);
+    return rc;
+}
+
 // ---- Upload: new rows into an existing index (server/upload.go:239-279) ----
 // list_off of the merged store: every list keeps its rows and gets the uploaded rows assigned to it after them.
 __global__ void merged_offsets_kernel(const uint64_t *old_off, const uint32_t *add_off, size_t C, uint64_t *new_off) {
@@ -1053,6 +1157,7 @@ extern "C" int vs_index_upload(vs_ctx *c, const vs_index *ix, const uint8_t *row
     VS(need_dev());
     if (!c || !ix || !rows || !out) return fail(VS_EINVAL, "null argument");
     VS(check_rows(n, row_bytes));
+    if (ix->fill_cursor && ix->filled != ix->n) return fail(VS_EINVAL, "the index is still loading");
     if (ix->C == 0) return fail(VS_EINVAL, "the index has no centroids");  // compute.go:26: NewMatrix panics on 0 rows
     if ((size_t)ix->centroids->d != row_bytes - 8)                          // cosine.go:77-79
         return fail(VS_EDIM, "matrix/matrix column size does not match: %d != %zu", ix->centroids->d, row_bytes - 8);
@@ -1373,6 +1478,8 @@ static int search_resolve_flagged(vs_ctx *c, const vs_index *ix, const MatView &
 static int search_check(vs_ctx *c, const vs_index *ix) {
     VS(need_dev());
     if (!c || !ix) return fail(VS_EINVAL, "null argument");
+    if (ix->fill_cursor && ix->filled != ix->n)
+        return fail(VS_EINVAL, "the index is still loading: %zu of %zu rows placed", ix->filled, ix->n);
     return VS_OK;
 }
 

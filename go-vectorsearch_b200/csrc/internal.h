@@ -55,6 +55,10 @@ struct vs_index {
     bool implicit_ids = false;       // built without document ids: rows are numbered id_base + primary-key order
     uint64_t *list_off = nullptr;    // [C+1] device
     size_t n = 0, C = 0;
+    // streaming load (vs_index_create_empty / vs_index_fill*): rows placed so far per list (device, [C] + overflow flag) and
+    // in total; null once the index was built in one piece.  Searches are refused until filled == n.
+    uint64_t *fill_cursor = nullptr;
+    size_t filled = 0;
 };
 
 namespace vs {
@@ -193,6 +197,9 @@ cudaError_t launch_gather_rows(const MatView &src, const uint32_t *order, size_t
 cudaError_t launch_merge_rows(const MatView &a, const uint64_t *a_ids, uint64_t a_id_base, const MatView &b, const uint64_t *b_ids,
                               uint64_t b_id_base, const uint32_t *order, size_t n, uint8_t *codes, float2 *hdr, uint2 *sums,
                               uint64_t *ids_out, cudaStream_t st);
+cudaError_t launch_scatter_rows(const MatView &src, const uint32_t *order, const uint32_t *keys, const uint32_t *chunk_off,
+                                const uint64_t *list_off, const uint64_t *cursor, uint8_t *codes, float2 *hdr, uint2 *sums,
+                                const uint64_t *ids_in, uint64_t id_base, uint64_t *ids_out, unsigned int *overflow, cudaStream_t st);
 
 // argmax.cu
 cudaError_t launch_argmax(const MatView &cent, const MatView &data, const uint32_t *canon, int32_t *idx_out,

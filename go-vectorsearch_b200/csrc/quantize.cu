@@ -297,4 +297,47 @@ cudaError_t launch_merge_rows(const MatView &a, const uint64_t *a_ids, uint64_t 
     return cudaGetLastError();
 }
 
+// Streaming loader (vs_index_fill*): the rows of one chunk, already ordered by list (order[j] = chunk row of sorted position j,
+// keys[j] = its list), go straight to their final place in the grouped store: list_off[l] + rows the list already holds
+// (cursor[l]) + position among this chunk's rows of the list.  A list that would overflow its reserved length raises *overflow
+// and its surplus rows are dropped.  Same copy shape as gather_rows_kernel.
+__global__ void __launch_bounds__(kRowWarps * 32) scatter_rows_kernel(MatView src, const uint32_t *__restrict__ order,
+                                                                      const uint32_t *__restrict__ keys,
+                                                                      const uint32_t *__restrict__ chunk_off,
+                                                                      const uint64_t *__restrict__ list_off,
+                                                                      const uint64_t *__restrict__ cursor, size_t n,
+                                                                      uint8_t *__restrict__ codes, float2 *__restrict__ hdr,
+                                                                      uint2 *__restrict__ sums, const uint64_t *__restrict__ ids_in,
+                                                                      uint64_t id_base, uint64_t *__restrict__ ids_out,
+                                                                      unsigned int *__restrict__ overflow) {
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int CH = src.d_pad >> 4;
+    for (size_t j = (size_t)blockIdx.x * kRowWarps + warp; j < n; j += (size_t)gridDim.x * kRowWarps) {
+        const uint32_t l = keys[j];
+        const uint64_t at = cursor[l] + (j - chunk_off[l]);
+        if (at >= list_off[l + 1] - list_off[l]) {
+            if (lane == 0) *overflow = 1u;
+            continue;
+        }
+        const size_t s = order[j], i = list_off[l] + at;
+        const uint4 *sp = reinterpret_cast<const uint4 *>(src.codes + s * (size_t)src.d_pad);
+        uint4 *dp = reinterpret_cast<uint4 *>(codes + i * (size_t)src.d_pad);
+        for (int c = lane; c < CH; c += 32) dp[c] = sp[c];
+        if (lane == 0) {
+            hdr[i] = src.hdr[s];
+            sums[i] = src.sums[s];
+            ids_out[i] = ids_in ? ids_in[s] : id_base + s;
+        }
+    }
+}
+
+cudaError_t launch_scatter_rows(const MatView &src, const uint32_t *order, const uint32_t *keys, const uint32_t *chunk_off,
+                                const uint64_t *list_off, const uint64_t *cursor, uint8_t *codes, float2 *hdr, uint2 *sums,
+                                const uint64_t *ids_in, uint64_t id_base, uint64_t *ids_out, unsigned int *overflow, cudaStream_t st) {
+    if (src.n == 0) return cudaSuccess;
+    scatter_rows_kernel<<<row_grid(src.n), kRowWarps * 32, 0, st>>>(src, order, keys, chunk_off, list_off, cursor, src.n, codes, hdr, sums,
+                                                                  ids_in, id_base, ids_out, overflow);
+    return cudaGetLastError();
+}
+
 }  // namespace vs

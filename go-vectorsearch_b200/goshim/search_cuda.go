@@ -50,6 +50,30 @@ func (ix *Index) Search(query []uint8, nprobe int, k int) (documentIDs []uint64,
 	return ids[:count], sims[:count]
 }
 
+// NewIndexLoader reserves the device store of a category from its per-centroid embedding counts (the GROUP BY of
+// dnc.go:465-470); Fill then streams the embeddings table into it in primary-key order, FindInBatches chunk by chunk
+// (search.go:241-243's own read order), without ever holding a second copy of the rows in HBM.  The index answers
+// searches once every counted row has been placed.
+func NewIndexLoader(centroids Matrix, rowsPerCentroid []uint64) *Index {
+	m := centroids.(*matrixContainer)
+	ix := &Index{}
+	withDefaultCtx(func(c *ctx) {
+		check(C.vs_index_create_empty(c.h, m.h, (*C.uint64_t)(unsafe.Pointer(&rowsPerCentroid[0])), &ix.h))
+	})
+	runtime.SetFinalizer(ix, func(ix *Index) { C.vs_index_release(ix.h) })
+	return ix
+}
+
+// Fill places one chunk of embeddings (Embedding.Vector, DocumentID, position of CentroidID in the centroid table).
+func (ix *Index) Fill(rows [][]uint8, documentIDs []uint64, centroidIndex []uint32) {
+	rbuf, n, rowBytes := pack(rows)
+	defer C.free(rbuf)
+	withDefaultCtx(func(c *ctx) {
+		check(C.vs_index_fill(c.h, ix.h, (*C.uint8_t)(rbuf), C.size_t(n), C.size_t(rowBytes),
+			(*C.uint32_t)(unsafe.Pointer(&centroidIndex[0])), (*C.uint64_t)(unsafe.Pointer(&documentIDs[0])), 0))
+	})
+}
+
 // Upload is the assignment of server/upload.go:239-279 plus the insert into the device store: every new embedding goes to
 // its nearest centroid (upload.go:245) and joins that posting list behind the rows already there.  centroidIndex[i] is
 // what upload.go:268-271 turns into Embedding.CentroidID (centroids[centroidIndex[i]].ID).  The receiver stays valid for

@@ -63,6 +63,34 @@ class Index:
                                     centroids.handle, C.byref(h)))
         return cls(h, L)
 
+    @classmethod
+    def create_empty(cls, centroids, list_counts, ctx=None):
+        """Streaming loader, step 1: reserve the grouped store from the per-list row counts (centroids: compute.Matrix).
+        Fill it with Fill / FillDev in primary-key order; searches are refused until every row is placed."""
+        L = _lib.init()
+        ctx = ctx or default_context()
+        counts = np.ascontiguousarray(list_counts, dtype=np.uint64)
+        assert counts.shape == (centroids.rows,)
+        h = C.c_void_p()
+        _check(L.vs_index_create_empty(ctx.handle, centroids.handle, _p(counts), C.byref(h)))
+        return cls(h, L)
+
+    def FillDev(self, chunk, d_list_of_row_ptr, d_doc_ids_ptr=None, id_base=0, ctx=None):
+        """Place a device chunk (compute.Matrix; int32 list index per row and optional uint64 ids as raw device pointers)."""
+        ctx = ctx or default_context()
+        _check(self._L.vs_index_fill_dev(ctx.handle, self._h, chunk.handle, C.c_void_p(int(d_list_of_row_ptr)),
+                                         C.c_void_p(int(d_doc_ids_ptr)) if d_doc_ids_ptr else None, int(id_base)))
+
+    def Fill(self, rows, list_of_row, doc_ids=None, id_base=0, ctx=None):
+        """Place a chunk of host rows (row776) with their list index and ids (None: id_base + row index in the chunk)."""
+        ctx = ctx or default_context()
+        rows = _rows_array(rows)
+        lor = np.ascontiguousarray(list_of_row, dtype=np.uint32)
+        ids = None if doc_ids is None else np.ascontiguousarray(doc_ids, dtype=np.uint64)
+        assert lor.shape == (rows.shape[0],) and (ids is None or ids.shape == lor.shape)
+        _check(self._L.vs_index_fill(ctx.handle, self._h, _p(rows), rows.shape[0], rows.shape[1], _p(lor),
+                                     _p(ids) if ids is not None else None, int(id_base)))
+
     def Upload(self, rows, doc_ids=None, ctx=None):
         """Upload's assignment and insert (server/upload.go:239-279): every new row joins the list of its nearest centroid
         (upload.go:245) behind the rows already there.  Returns (new Index, assign int64[n]); this Index stays valid."""

@@ -152,6 +152,20 @@ VS_API int vs_index_build_assigned(vs_ctx *ctx, const uint8_t *rows_packed, size
  * (d_doc_ids may be NULL -> id = id_base + row index). */
 VS_API int vs_index_build_dev(vs_ctx *ctx, const vs_matrix *data, const int32_t *d_list_of_row, const uint64_t *d_doc_ids,
                        uint64_t id_base, const vs_matrix *centroids, vs_index **out);
+/* Streaming loader: the database as a one-time loader (database/model.go:9-18: id, vector, document_id, centroid_id;
+ * search.go:241-243 reads a list in primary-key order).  vs_index_create_empty reserves the grouped store at its final
+ * size from the per-list row counts (host, [C] -- SELECT centroid_id, COUNT(*) ... GROUP BY centroid_id, the query of
+ * dnc.go:465-470); vs_index_fill* then places chunks of rows, handed over in primary-key order, straight into their
+ * lists.  HBM holds the store once plus one chunk, so a shard can be sized for nearly all of the 180 GB (the one-piece
+ * builds above hold the ungrouped rows and the grouped copy at the same time).  Searches are refused (VS_EINVAL) until
+ * every reserved row is placed; the result is identical to vs_index_build_assigned over the same rows.
+ * vs_index_fill_dev: chunk = device matrix, d_list_of_row[m] int32 list index per row (e.g. from vs_argmax_MxN_dev),
+ * d_doc_ids[m] or NULL (id = id_base + row index in the chunk); vs_index_fill: the same from host buffers. */
+VS_API int vs_index_create_empty(vs_ctx *ctx, const vs_matrix *centroids, const uint64_t *list_counts, vs_index **out);
+VS_API int vs_index_fill_dev(vs_ctx *ctx, vs_index *ix, const vs_matrix *chunk, const int32_t *d_list_of_row,
+                      const uint64_t *d_doc_ids, uint64_t id_base);
+VS_API int vs_index_fill(vs_ctx *ctx, vs_index *ix, const uint8_t *rows_packed, size_t n, size_t row_bytes,
+                  const uint32_t *list_of_row, const uint64_t *doc_ids, uint64_t id_base);
 VS_API void vs_index_release(vs_index *ix);
 VS_API size_t vs_index_rows(const vs_index *ix);
 VS_API size_t vs_index_lists(const vs_index *ix);
