@@ -7,6 +7,7 @@
 //   compute/cosine.go:60-66     VectorMatrixCosineSimilarity() -> {calculate, done}
 //   compute/cosine.go:129-135   MatrixCosineSimilarity()       -> {calculate, done}
 //   compute/quantization.go     Quantize{Vector,Matrix}Float{32,64}, Dequantize...
+//   server/search.go:202-273, server/upload.go:239-279 -> Index { Search, Upload, Fill } (device-resident extension)
 // logger.Sugar().Fatalf (process exit in Go, cosine.go:19-21,77-79) surfaces as compute::Fatal.
 // The Go shim a maintainer adds is goshim/*.go; this header is what the C++ self-test and any C++ caller use.
 #pragma once
@@ -140,6 +141,74 @@ inline MatrixMatrixClosure MatrixCosineSimilarity() {                           
     auto ctx = std::make_shared<Context>();
     return {[ctx](const Matrix &a, const Matrix &b) { return a.MatrixCosineSimilarity(b, ctx.get()); },
             [ctx]() { ctx->Close(); }};
+}
+
+// ---- device-resident IVF-Flat store of one category (server/search.go:202-273, server/upload.go:239-279) ----
+// The same extension beyond the reference's compute API as goshim/search_cuda.go: the database only loads.
+struct Hits {
+    std::vector<uint64_t> documentIDs;   // similarity desc (float32), then document id asc; one entry per document
+    std::vector<float> similarities;
+};
+
+class Index {
+  public:
+    explicit Index(vs_index *h) : h_(h, [](vs_index *p) { vs_index_release(p); }) {}
+    size_t rows() const { return vs_index_rows(h_.get()); }
+    size_t lists() const { return vs_index_lists(h_.get()); }
+    size_t cols() const { return vs_index_cols(h_.get()); }
+    vs_index *handle() const { return h_.get(); }
+    // search.go:214-273: nprobe = req.Centroids, k = req.Count + req.Offset
+    Hits Search(const Row &query, size_t nprobe, size_t k, Context *ctx = nullptr) const {
+        Context &c = ctx ? *ctx : DefaultContext();
+        Hits out;
+        out.documentIDs.resize(k);
+        out.similarities.resize(k);
+        int32_t count = 0;
+        check(vs_search(c.handle(), h_.get(), query.data(), 1, nprobe, k, out.documentIDs.data(), out.similarities.data(), &count));
+        out.documentIDs.resize((size_t)count);
+        out.similarities.resize((size_t)count);
+        return out;
+    }
+    // upload.go:239-279: nearest centroid of every new row (upload.go:245), rows appended to their lists; returns the
+    // index to swap in and the centroid index of every row (-> Embedding.CentroidID, upload.go:268-271)
+    std::pair<Index, std::vector<int64_t>> Upload(const Rows &rows, const std::vector<uint64_t> &documentIDs, Context *ctx = nullptr) const {
+        Context &c = ctx ? *ctx : DefaultContext();
+        std::vector<uint8_t> buf = Pack(rows);
+        if (documentIDs.size() != rows.size()) throw Error("one document id per row");
+        std::vector<int64_t> assign(rows.size());
+        vs_index *h = nullptr;
+        check(vs_index_upload(c.handle(), h_.get(), buf.data(), rows.size(), rows[0].size(), documentIDs.data(), assign.data(), &h));
+        return {Index(h), std::move(assign)};
+    }
+    // streaming loader, step 2: one chunk of the embeddings table in primary-key order
+    void Fill(const Rows &rows, const std::vector<uint64_t> &documentIDs, const std::vector<uint32_t> &centroidIndex, Context *ctx = nullptr) {
+        Context &c = ctx ? *ctx : DefaultContext();
+        std::vector<uint8_t> buf = Pack(rows);
+        if (documentIDs.size() != rows.size() || centroidIndex.size() != rows.size()) throw Error("one id and one list per row");
+        check(vs_index_fill(c.handle(), h_.get(), buf.data(), rows.size(), rows[0].size(), centroidIndex.data(), documentIDs.data(), 0));
+    }
+  private:
+    std::shared_ptr<vs_index> h_;
+};
+
+// rows = Embedding.Vector in primary-key order, documentIDs = Embedding.DocumentID, centroidIndex = position of
+// Embedding.CentroidID in `centroids` (database/model.go:9-18,35-37)
+inline Index NewIndex(const Rows &rows, const std::vector<uint64_t> &documentIDs, const std::vector<uint32_t> &centroidIndex,
+                      const Rows &centroids) {
+    std::vector<uint8_t> rbuf = Pack(rows), cbuf = Pack(centroids);
+    if (documentIDs.size() != rows.size() || centroidIndex.size() != rows.size()) throw Error("one id and one list per row");
+    vs_index *h = nullptr;
+    check(vs_index_build_assigned(DefaultContext().handle(), rbuf.data(), rows.size(), rows[0].size(), documentIDs.data(),
+                                  centroidIndex.data(), cbuf.data(), centroids.size(), &h));
+    return Index(h);
+}
+
+// streaming loader, step 1: the store reserved from the per-centroid embedding counts (the GROUP BY of dnc.go:465-470)
+inline Index NewIndexLoader(const Matrix &centroids, const std::vector<uint64_t> &rowsPerCentroid) {
+    if (rowsPerCentroid.size() != centroids.rows()) throw Error("one count per centroid");
+    vs_index *h = nullptr;
+    check(vs_index_create_empty(DefaultContext().handle(), centroids.handle(), rowsPerCentroid.data(), &h));
+    return Index(h);
 }
 
 // ---- compute/quantization.go ----

@@ -51,6 +51,33 @@ int main() {
         auto res = mm.calculate(cent.Clone(), data.Clone());
         mm.done();
         EXPECT((res.second == std::vector<int64_t>{0, 1, 0, 0, 1}), "argmax known answers");
+        // search.go:202-273 + upload.go:239-279 -- the five data rows above behind the first two centroids; by hand: lists
+        // {1,0,0,0,1} (row 1 ties -> lowest index; the zero row scores 0 > -1 against centroid 0), query (1,0)
+        const Rows cents = {row(0.f, 1.f, {255, 0}), row(0.f, 1.f, {0, 255})};
+        const Rows drows = {row(0.f, 1.f, {0, 255}), row(0.f, 1.f, {255, 255}), row(0.f, 1.f, {255, 0}), row(0.f, 0.f, {0, 0}),
+                            row(-1.f, 0.f, {0, 255})};
+        const Row query = row(0.f, 1.f, {255, 0});
+        Index ix = NewIndex(drows, {100, 101, 102, 103, 104}, {1, 0, 0, 0, 1}, cents);
+        Hits h1 = ix.Search(query, 1, 10);
+        EXPECT((h1.documentIDs == std::vector<uint64_t>{102, 101, 103}), "ivf search nprobe=1 ids");
+        EXPECT(h1.similarities.size() == 3 && h1.similarities[0] == 1.f && h1.similarities[1] == s1 && h1.similarities[2] == 0.f,
+               "ivf search nprobe=1 similarities");
+        Hits h2 = ix.Search(query, 2, 10);
+        EXPECT((h2.documentIDs == std::vector<uint64_t>{102, 101, 100, 103, 104}), "ivf search all lists: ties by document id");
+        Index first3 = NewIndex({drows[0], drows[1], drows[2]}, {100, 101, 102}, {1, 0, 0}, cents);
+        auto up = first3.Upload({drows[3], drows[4]}, {103, 104});
+        EXPECT((up.second == std::vector<int64_t>{0, 1}), "upload assignment (upload.go:245)");
+        Hits h3 = up.first.Search(query, 2, 10);
+        EXPECT(h3.documentIDs == h2.documentIDs && h3.similarities == h2.similarities, "index after upload == index built from all rows");
+        EXPECT(first3.rows() == 3 && up.first.rows() == 5, "upload leaves the old index untouched");
+        Index ld = NewIndexLoader(NewMatrix(cents), {3, 2});
+        bool refused = false;
+        try { ld.Search(query, 2, 10); } catch (const Error &) { refused = true; }
+        EXPECT(refused, "a loading index refuses searches");
+        ld.Fill({drows[0], drows[1]}, {100, 101}, {1, 0});
+        ld.Fill({drows[2], drows[3], drows[4]}, {102, 103, 104}, {0, 0, 1});
+        Hits h4 = ld.Search(query, 2, 10);
+        EXPECT(h4.documentIDs == h2.documentIDs && h4.similarities == h2.similarities, "streamed index == index built in one piece");
         // error behaviour
         bool panicked = false;
         try { NewVector(compute::Row(8, 0)); } catch (const Panic &) { panicked = true; }
