@@ -124,8 +124,34 @@ argmax_cases = dict(
          "zero row: every dot is +0 > -1.0 -> index 0", "tie 0.7071 between 0 and 1 -> lowest index",
          "(-1,0): dots are -1,0,-1 -> centroid 1"])
 
+# server/search.go:202-273 and server/upload.go:239-279 on five rows behind two centroids, by hand.
+# Centroid of each row (cosine.go:70-125): (0,1) -> 1; (1,1) ties 0.7071 -> lowest index 0; (1,0) -> 0; the zero row scores
+# +0 > -1.0 against centroid 0 -> 0; (-1,0) scores -1 and 0 -> 1.  Query (1,0): centroid sims 1 and 0.
+s_cent = [row(0.0, 1.0, [255, 0]), row(0.0, 1.0, [0, 255])]
+s_rows = [row(0.0, 1.0, [0, 255]), row(0.0, 1.0, [255, 255]), row(0.0, 1.0, [255, 0]), row(0.0, 0.0, [0, 0]),
+          row(-1.0, 0.0, [0, 255])]
+s_doc = [100, 101, 102, 103, 104]
+s_lists = [1, 0, 0, 0, 1]
+s_sim = {d: f32_hex(cosine(q, r)) for d, r in zip(s_doc, s_rows)}
+search_cases = dict(
+    centroids=s_cent, rows=s_rows, doc_ids=s_doc, lists=s_lists, query=q,
+    searches=[
+        dict(nprobe=1, k=10, ids=[102, 101, 103], sims_f32=[s_sim[102], s_sim[101], s_sim[103]],
+             why="only list 0 is probed (centroid sims 1 > 0): its rows score 0.7071, 1, +0 -> sorted by similarity desc"),
+        dict(nprobe=2, k=10, ids=[102, 101, 100, 103, 104], sims_f32=[s_sim[i] for i in (102, 101, 100, 103, 104)],
+             why="every list: 1, 0.7071, then documents 100 and 103 tie at +0 -> lower id first, then -1"),
+        dict(nprobe=2, k=2, ids=[102, 101], sims_f32=[s_sim[102], s_sim[101]], why="truncated to Count+Offset = 2"),
+    ],
+    upload=dict(first=3, assign=[0, 1],
+                why="the index holds rows 0-2; rows 3 and 4 are uploaded: the zero row goes to centroid 0, (-1,0) to centroid 1 "
+                    "(upload.go:245); the index then answers like the one built from all five rows"))
+same_doc = dict(doc_ids=[7, 8, 7, 9, 8], nprobe=2, k=10, ids=[7, 8, 9], sims_f32=[s_sim[102], s_sim[101], s_sim[103]],
+                why="search.go:260-268: one hit per document keeping its best embedding: document 7 (rows 0, 2) keeps 1, "
+                    "document 8 (rows 1, 4) keeps 0.7071, document 9 has +0")
+search_cases["dedup"] = same_doc
+
 out = dict(quantize_f32=quantize_f32, quantize_f64=quantize_f64, dequantize=dequantize, cosine=cosine_cases,
-           argmax=argmax_cases)
+           argmax=argmax_cases, search=search_cases)
 
 
 def clean(o):

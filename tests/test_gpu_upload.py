@@ -76,6 +76,36 @@ def test_uploads_in_sequence_and_empty_lists(vs, oracle):
     _search_parity(oracle, ix, qs, cent, cur_rows, cur_lists, cur_doc, nprobe=5, k=20)
 
 
+def test_search_and_upload_kat(vs):
+    """The hand-derived five-row store of tests/golden/kat.json (no oracle involved): search, dedup, upload, loader."""
+    import json
+    import os
+    import struct
+    c = json.load(open(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "kat.json")))["search"]
+    cent = np.array(c["centroids"], np.uint8)
+    rows = np.array(c["rows"], np.uint8)
+    doc = np.array(c["doc_ids"], np.uint64)
+    lists = np.array(c["lists"], np.uint32)
+    q = np.array(c["query"], np.uint8)[None, :]
+
+    def check(ix, cases):
+        for s in cases:
+            ids, sims, counts = ix.Search(q, s["nprobe"], s["k"])
+            assert ids[0, :counts[0]].tolist() == s["ids"], s["why"]
+            assert [struct.pack(">f", x).hex() for x in sims[0, :counts[0]]] == s["sims_f32"], s["why"]
+
+    check(vs.ivf.Index.build_assigned(rows, doc, lists, cent), c["searches"])
+    check(vs.ivf.Index.build_assigned(rows, np.array(c["dedup"]["doc_ids"], np.uint64), lists, cent), [c["dedup"]])
+    n0 = c["upload"]["first"]
+    ix1, assign = vs.ivf.Index.build_assigned(rows[:n0], doc[:n0], lists[:n0], cent).Upload(rows[n0:], doc[n0:])
+    assert assign.tolist() == c["upload"]["assign"], c["upload"]["why"]
+    check(ix1, c["searches"])
+    ld = vs.ivf.Index.create_empty(vs.compute.NewMatrix(cent), np.bincount(lists, minlength=2))
+    ld.Fill(rows[:2], lists[:2], doc[:2])
+    ld.Fill(rows[2:], lists[2:], doc[2:])
+    check(ld, c["searches"])
+
+
 def test_upload_implicit_ids(vs, oracle):
     """An index built without document ids numbers its rows; uploaded rows continue the numbering."""
     d, C, n0, n1 = 128, 5, 700, 90

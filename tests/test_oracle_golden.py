@@ -67,6 +67,29 @@ def test_argmax_kat(oracle):
     assert onp.argmax_MxN(cent, data)[1].tolist() == c["argmax"]
 
 
+def test_search_and_upload_kat(oracle):
+    """server/search.go:202-273 and server/upload.go:239-279 on the hand-derived five-row store."""
+    c = KAT["search"]
+    cent = np.array(c["centroids"], np.uint8)
+    rows = np.array(c["rows"], np.uint8)
+    doc = np.array(c["doc_ids"], np.uint64)
+    lists = np.array(c["lists"], np.uint32)
+    q = np.array(c["query"], np.uint8)
+    assert oracle.argmax_MxN(cent, rows)[1].tolist() == c["lists"]
+    for s in c["searches"]:
+        ids, sims = oracle.search(q, cent, rows, lists, doc, s["nprobe"], s["k"])
+        assert ids.tolist() == s["ids"], s["why"]
+        assert [struct.pack(">f", x).hex() for x in sims] == s["sims_f32"], s["why"]
+    dd = c["dedup"]
+    ids, sims = oracle.search(q, cent, rows, lists, np.array(dd["doc_ids"], np.uint64), dd["nprobe"], dd["k"])
+    assert ids.tolist() == dd["ids"] and [struct.pack(">f", x).hex() for x in sims] == dd["sims_f32"], dd["why"]
+    u = c["upload"]
+    n0 = u["first"]
+    assign, all_lists, all_rows, all_doc = oracle.upload(cent, rows[n0:], lists[:n0], rows[:n0], doc[:n0], doc[n0:])
+    assert assign.tolist() == u["assign"], u["why"]
+    assert all_lists.tolist() == c["lists"] and (all_rows == rows).all() and (all_doc == doc).all()
+
+
 def test_reference_panics(oracle):
     q = np.zeros(8, np.uint8)
     rows = np.zeros((2, 10), np.uint8)
