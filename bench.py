@@ -126,6 +126,36 @@ def gen_unit_rows(torch, seed, chunk_index, count, device):
     return x
 
 
+STORE_LANES = 8  # a store chunk is 8 interleaved lanes, each with its own generator key (CHUNK is a multiple of 8)
+
+
+def store_chunk_rows(torch, chunk_index, r0, count, rank, world, device):
+    """The rows of store chunk `chunk_index` (global rows r0 .. r0+count) that rank `rank` of `world` owns (global row
+    index mod world == rank), in row order.  Row r0+i of the chunk is element i // 8 of lane i % 8, and lane j is
+    gen_unit_rows(SEED_DATA, chunk_index * 8 + j): the store is the same for every world size, and when world divides 8
+    a rank generates only the lanes it owns instead of the whole chunk.  Returns (rows [m, D] float32, first) with
+    first = chunk-local index of the rank's first row (first >= count: the rank owns nothing here)."""
+    first = (rank - r0) % world
+    if first >= count:
+        return None, first
+
+    def lane(j):
+        return gen_unit_rows(torch, SEED_DATA, chunk_index * STORE_LANES + j, (count - j + STORE_LANES - 1) // STORE_LANES, device)
+
+    def interleave(lanes, total):
+        out = torch.empty((total, D), device=device, dtype=torch.float32)
+        for t, x in enumerate(lanes):
+            out[t::len(lanes)] = x
+        return out
+
+    if STORE_LANES % world == 0 and r0 % STORE_LANES == 0:
+        mine = [j for j in range(first, min(STORE_LANES, count), world)]   # first == rank here
+        lanes = [lane(j) for j in mine]
+        return interleave(lanes, sum(x.shape[0] for x in lanes)), first
+    full = interleave([lane(j) for j in range(min(STORE_LANES, count))], count)
+    return full[first::world].contiguous(), first
+
+
 def build_index(pkg, torch, ctx, a, rank, world, device):
     """Synthetic store, generated and quantized on device, assigned to its nearest centroid, grouped into lists."""
     cp = pkg.compute
@@ -145,17 +175,15 @@ def build_index(pkg, torch, ctx, a, rank, world, device):
         filled = 0
         for ci, r0 in enumerate(range(0, a.rows, CHUNK)):
             cnt = min(CHUNK, a.rows - r0)
-            first = (rank - r0) % world          # first row of this chunk owned by this rank
-            if first >= cnt:
-                continue
             t = time.time()
-            x = gen_unit_rows(torch, SEED_DATA, ci, cnt, device)
-            xs = x[first::world].contiguous()
+            xs, first = store_chunk_rows(torch, ci, r0, cnt, rank, world, device)   # this rank's rows of the chunk
+            if xs is None:
+                continue
             torch.cuda.synchronize()
             m = cp.EmptyMatrix(xs.shape[0], D, ctx=ctx)
             m.FillFloat32Dev(0, xs.data_ptr(), xs.shape[0], ctx=ctx)
             ctx.sync()
-            del x, xs
+            del xs
             yield m, filled, r0 + first, time.time() - t
             filled += m.rows
         assert filled == n_local, (filled, n_local)
