@@ -150,8 +150,87 @@ same_doc = dict(doc_ids=[7, 8, 7, 9, 8], nprobe=2, k=10, ids=[7, 8, 9], sims_f32
                     "document 8 (rows 1, 4) keeps 0.7071, document 9 has +0")
 search_cases["dedup"] = same_doc
 
+
+
+# ---- dnc/k_means.go:67-117 (one Lloyd iteration) and dnc/dnc.go:417-449 (recenter), in plain Python arithmetic ----
+def f32(x):
+    return struct.unpack("<f", struct.pack("<f", x))[0]
+
+
+def quantize32(vec):
+    """quantization.go:21-45,82-91,194-216 in float32: range seeded at 0, clamp, ((v-min)/(max-min))*255 truncated."""
+    mn = mx = 0.0
+    for v in vec:
+        if v < mn:
+            mn = v
+        if v > mx:
+            mx = v
+    codes = []
+    for v in vec:
+        v = min(max(v, mn), mx)
+        if mx == mn:
+            codes.append(0)          # 0/0 = NaN -> uint8(NaN) = 0 on amd64
+            continue
+        normalized = f32(f32(v - mn) / f32(mx - mn))
+        codes.append(int(f32(normalized * 255.0)) & 0xFF)
+    return row(mn, mx, codes)
+
+
+def quantize64(vec):
+    """quantization.go:8-19,93-102 in float64; the header stores float32(min), float32(max)."""
+    mn = mx = 0.0
+    for v in vec:
+        if v < mn:
+            mn = v
+        if v > mx:
+            mx = v
+    codes = []
+    for v in vec:
+        v = min(max(v, mn), mx)
+        codes.append(0 if mx == mn else int(((v - mn) / (mx - mn)) * 255.0) & 0xFF)
+    return row(mn, mx, codes)
+
+
+def dequantize_row(r, fn):
+    mn, mx = struct.unpack("<ff", bytes(r[:8]))
+    return [fn(c, mn, mx) for c in r[8:]]
+
+
+km_cent = [row(0.0, 1.0, [255, 0]), row(0.0, 1.0, [0, 255]), row(-1.0, 0.0, [0, 255])]
+km_data = [row(0.0, 1.0, [255, 0]), row(0.0, 1.0, [200, 100]), row(0.0, 1.0, [0, 255]), row(0.0, 1.0, [100, 100]),
+           row(0.0, 0.0, [9, 9])]
+km_assign = [0, 0, 1, 0, 0]   # (1,0); cos .894 vs .447; (0,1); tie .7071 -> lowest index; zero row: +0 > -1.0 -> index 0
+km_prev_means = [[0.5, 0.5], [0.125, 0.0], [0.25, 0.5]]
+km_sums = [[0.0, 0.0] for _ in km_cent]
+km_counts = [0, 0, 0]
+for i, c in enumerate(km_assign):                       # k_means.go:80-86: float32 sums in row order
+    vec = dequantize_row(km_data[i], deq32)
+    for j, val in enumerate(vec):
+        km_sums[c][j] = f32(km_sums[c][j] + val)
+    km_counts[c] += 1
+km_means = [list(m) for m in km_prev_means]
+for c in range(len(km_cent)):                            # k_means.go:89-96: an empty cluster keeps its previous mean
+    if km_counts[c] > 0:
+        km_means[c] = [f32(sv / f32(float(km_counts[c]))) for sv in km_sums[c]]
+km_new = [quantize32(m) for m in km_means]              # k_means.go:99
+kmeans_case = dict(
+    centroids=km_cent, data=km_data, prev_means=km_prev_means, assign=km_assign, counts=km_counts,
+    means_f32=[[f32_hex(v) for v in m] for m in km_means], new_centroids=km_new,
+    converged=all(n[8:] == c[8:] for n, c in zip(km_new, km_cent)),
+    why="cluster 0 = rows 0,1,3,4 (the zero row adds +0 but counts), cluster 1 = row 2, cluster 2 empty: it keeps the mean it "
+        "had, (0.25, 0.5), and is requantized from it; sums and means in float32, row order")
+
+rc_rows = [row(0.0, 1.0, [255, 0]), row(0.0, 1.0, [0, 255]), row(-1.0, 0.0, [0, 255])]
+rc_sum = [0.0, 0.0]
+for r in rc_rows:                                        # dnc.go:417-436: float64 sums in row order
+    for j, val in enumerate(dequantize_row(r, deq64)):
+        rc_sum[j] += val
+rc_mean = [v / float(len(rc_rows)) for v in rc_sum]      # dnc.go:446-448
+recenter_case = dict(rows=rc_rows, expect=quantize64(rc_mean),
+                     why="(1,0) + (0,1) + (-1,0) = (0,1); / 3 = (0, 0.333..): range [0, 1/3] (header float32(1/3)), codes 0 and 255")
+
 out = dict(quantize_f32=quantize_f32, quantize_f64=quantize_f64, dequantize=dequantize, cosine=cosine_cases,
-           argmax=argmax_cases, search=search_cases)
+           argmax=argmax_cases, search=search_cases, kmeans_step=kmeans_case, recenter=recenter_case)
 
 
 def clean(o):

@@ -90,6 +90,26 @@ def test_search_and_upload_kat(oracle):
     assert all_lists.tolist() == c["lists"] and (all_rows == rows).all() and (all_doc == doc).all()
 
 
+def test_kmeans_step_and_recenter_kat(oracle):
+    """dnc/k_means.go:67-117 and dnc/dnc.go:417-449 on the hand-derived cases (plain Python arithmetic in make_golden.py)."""
+    from oracle import oracle_np as onp
+    c = KAT["kmeans_step"]
+    cent = np.array(c["centroids"], np.uint8)
+    data = np.array(c["data"], np.uint8)
+    means = np.array(c["prev_means"], np.float32)
+    assign, counts, newc, conv = oracle.kmeans_step(data, cent, means)
+    assert assign.tolist() == c["assign"] and counts.tolist() == c["counts"], c["why"]
+    assert [[struct.pack(">f", v).hex() for v in m] for m in means] == c["means_f32"], c["why"]
+    assert newc.tolist() == c["new_centroids"] and conv == c["converged"], c["why"]
+    counts2, means2, newc2 = onp.kmeans_update(data, np.array(c["assign"]), len(cent), np.array(c["prev_means"], np.float32))
+    assert counts2.tolist() == c["counts"] and newc2.tolist() == c["new_centroids"]
+    assert [[struct.pack(">f", v).hex() for v in m] for m in means2] == c["means_f32"]
+    r = KAT["recenter"]
+    rows = np.array(r["rows"], np.uint8)
+    assert oracle.recenter(rows).tolist() == r["expect"], r["why"]
+    assert onp.recenter(rows).tolist() == r["expect"]
+
+
 def test_reference_panics(oracle):
     q = np.zeros(8, np.uint8)
     rows = np.zeros((2, 10), np.uint8)
