@@ -158,7 +158,9 @@ VS_API int vs_index_build_dev(vs_ctx *ctx, const vs_matrix *data, const int32_t 
  * dnc.go:465-470); vs_index_fill* then places chunks of rows, handed over in primary-key order, straight into their
  * lists.  HBM holds the store once plus one chunk, so a shard can be sized for nearly all of the 180 GB (the one-piece
  * builds above hold the ungrouped rows and the grouped copy at the same time).  Searches are refused (VS_EINVAL) until
- * every reserved row is placed; the result is identical to vs_index_build_assigned over the same rows.
+ * every reserved row is placed; the result is identical to vs_index_build_assigned over the same rows.  One loader
+ * thread per index (the fill calls mutate it and are ordered); a fill that fails with VS_EINVAL because a list
+ * overflowed its reservation leaves the index unusable -- release it.
  * vs_index_fill_dev: chunk = device matrix, d_list_of_row[m] int32 list index per row (e.g. from vs_argmax_MxN_dev),
  * d_doc_ids[m] or NULL (id = id_base + row index in the chunk); vs_index_fill: the same from host buffers. */
 VS_API int vs_index_create_empty(vs_ctx *ctx, const vs_matrix *centroids, const uint64_t *list_counts, vs_index **out);
