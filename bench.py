@@ -738,22 +738,23 @@ def cpu_baseline(pkg, ctx, ix, cent, a, queries, gpu_ids, gpu_sims, offsets):
         o_ids, o_sims, o_counts = oracle.search_many(queries[:nq], centroids, rows, lor, ids, a.nprobe, a.k, threads=cores)
     dt = time.perf_counter() - t0
     parity = bool((o_ids == gpu_ids[:nq]).all() and (o_sims.view(np.uint32) == gpu_sims[:nq].view(np.uint32)).all())
-    # The reference's gonum build tag scores with BLAS (Dnrm2 / Dscal / Ddot, cosine_gonum.go): timed here as a PROXY, the same
-    # call sequence through numpy's OpenBLAS (oracle/gonum_proxy.py), one query per host thread.  Never a parity anchor.
+    # The reference's gonum build tag scores with BLAS (Dnrm2 / Dscal / Ddot, cosine_gonum.go; gonum is not in the image): timed
+    # here as a PROXY -- the oracle's own source compiled a second time with the float64 sums free to be reordered and
+    # vectorized (AVX2+FMA clones, run-time dispatch; oracle/Makefile).  Same queries, same threads.  Never a parity anchor.
     try:
-        import concurrent.futures as cf
-        from oracle import gonum_proxy as gp
-        nqp = int(min(nq, cores))
-        gp.search(queries[0], centroids, rows, lor, ids, a.nprobe, a.k)          # warm the BLAS threads
+        reps_p = int(max(1, reps // 2))
+        oracle.search_many(queries[:1], centroids, rows1, lor1, ids1, a.nprobe, a.k, threads=1, blas_proxy=True)
         t0 = time.perf_counter()
-        with cf.ThreadPoolExecutor(cores) as ex:
-            res = list(ex.map(lambda q: gp.search(q, centroids, rows, lor, ids, a.nprobe, a.k), queries[:nqp]))
+        for _ in range(reps_p):
+            p_ids, p_sims, p_counts = oracle.search_many(queries[:nq], centroids, rows, lor, ids, a.nprobe, a.k, threads=cores,
+                                                         blas_proxy=True)
         dtp = time.perf_counter() - t0
-        same = sum(int(r[0].tolist() == o_ids[i, :o_counts[i]].tolist()) for i, r in enumerate(res))
-        proxy = {"value": round(nqp / dtp, 3), "unit": "queries/s", "cores": cores, "kind": "port",
-                 "sample": f"{nqp} of the same queries, one per thread; numpy/OpenBLAS restatement of cosine_gonum.go's BLAS calls "
-                           f"(gonum v0.16.0 itself is not in the image)", "seconds": round(dtp, 2),
-                 "queries_with_the_default_backends_top_k": f"{same}/{nqp}"}
+        same = int(sum(int((p_ids[i] == o_ids[i]).all()) for i in range(nq)))
+        rel = float(np.max(np.abs(p_sims.astype(np.float64) - o_sims) / np.maximum(np.abs(o_sims), 1e-30)))
+        proxy = {"value": round(nq * reps_p / dtp, 3), "unit": "queries/s", "cores": cores, "kind": "port",
+                 "sample": f"the same {nq} queries x {reps_p} repetitions on {cores} threads; the default-backend restatement compiled "
+                           f"with reorderable, vectorized float64 sums (a stand-in for gonum's BLAS kernels, which are not in the image)",
+                 "seconds": round(dtp, 2), "queries_with_the_exact_top_k": f"{same}/{nq}", "max_rel_diff_of_similarities": rel}
     except Exception as e:  # noqa: BLE001
         proxy = {"error": repr(e)[:200]}
     return {"gonum_blas_proxy": proxy,

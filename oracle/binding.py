@@ -7,16 +7,30 @@ import numpy as np
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
 _SO = os.path.join(_HERE, "_build", "liboracle.so")
+# the same source with the float64 sums free to be reordered and vectorized: a TIMING proxy for the reference's BLAS
+# (gonum) backend, never a parity anchor (see the note at the top of oracle.c)
+_SO_PROXY = os.path.join(_HERE, "_build", "liboracle_blas_proxy.so")
 
 
 def build(force=False):
     src = os.path.join(_HERE, "oracle.c")
-    if force or not os.path.exists(_SO) or os.path.getmtime(_SO) < os.path.getmtime(src):
+    stale = any(not os.path.exists(so) or os.path.getmtime(so) < os.path.getmtime(src) for so in (_SO, _SO_PROXY))
+    if force or stale:
         subprocess.check_call(["make", "-s", "-C", _HERE])
     return _SO
 
 
 _lib = None
+_lib_proxy = None
+
+
+def lib_blas_proxy():
+    global _lib_proxy
+    if _lib_proxy is None:
+        if not os.path.exists(_SO_PROXY):
+            build()
+        _lib_proxy = C.CDLL(_SO_PROXY)
+    return _lib_proxy
 
 
 def lib():
@@ -111,12 +125,12 @@ def _check(rc):
         raise OraclePanic("column size does not match")
 
 
-def cosine_1xN(q, rows):
+def cosine_1xN(q, rows, blas_proxy=False):
     q = _u8(q)
     rows = _u8(rows)
     n, rb = rows.shape if rows.ndim == 2 else (0, 0)
     out = np.empty(n, np.float32)
-    rc = lib().ora_cosine_1xN(_p(q), C.c_size_t(q.shape[0]), _p(rows), C.c_size_t(n), C.c_size_t(rb), _p(out))
+    rc = (lib_blas_proxy() if blas_proxy else lib()).ora_cosine_1xN(_p(q), C.c_size_t(q.shape[0]), _p(rows), C.c_size_t(n), C.c_size_t(rb), _p(out))
     _check(rc)
     return out
 
@@ -175,7 +189,7 @@ def search(q, centroids, rows, list_of_row, doc_ids, nprobe, k):
     return ids[:rc], sims[:rc]
 
 
-def search_many(qs, centroids, rows, list_of_row, doc_ids, nprobe, k, threads=1):
+def search_many(qs, centroids, rows, list_of_row, doc_ids, nprobe, k, threads=1, blas_proxy=False):
     qs = _u8(qs)
     centroids = _u8(centroids)
     rows = _u8(rows)
@@ -187,7 +201,7 @@ def search_many(qs, centroids, rows, list_of_row, doc_ids, nprobe, k, threads=1)
     ids = np.zeros((nq, k), np.uint64)
     sims = np.zeros((nq, k), np.float32)
     counts = np.zeros(nq, np.int32)
-    rc = lib().ora_search_many(_p(qs), C.c_size_t(nq), _p(centroids), C.c_size_t(Cn), _p(rows), C.c_size_t(n),
+    rc = (lib_blas_proxy() if blas_proxy else lib()).ora_search_many(_p(qs), C.c_size_t(nq), _p(centroids), C.c_size_t(Cn), _p(rows), C.c_size_t(n),
                                C.c_size_t(rb), _p(list_of_row), _p(doc_ids), C.c_size_t(nprobe), C.c_size_t(k),
                                _p(ids), _p(sims), _p(counts), C.c_int(threads))
     _check(rc)

@@ -25,6 +25,17 @@
 
 #define ORA_API __attribute__((visibility("default")))
 
+/* The same source is compiled a second time as _build/liboracle_blas_proxy.so (oracle/Makefile: -O3 -ffast-math
+ * -DORA_VECTORIZED_PROXY): there the compiler may reorder and vectorize the float64 sums and 1xN scoring is cloned
+ * for AVX2+FMA with run-time dispatch.  That build is a TIMING PROXY for the reference's `gonum` build tag (BLAS
+ * Dnrm2 / Dscal / Ddot, compute/cosine_gonum.go; gonum v0.16.0 is not in the image): a vectorised float64 CPU path
+ * with an unspecified summation order, reported beside the exact build.  No parity claim rests on it. */
+#ifdef ORA_VECTORIZED_PROXY
+#define ORA_HOT __attribute__((target_clones("avx2,fma", "default")))
+#else
+#define ORA_HOT
+#endif
+
 /* Go's uint8(f) on amd64: CVTTSS2SL / CVTTSD2SQ then keep the low byte; NaN and
  * out-of-range inputs produce the "integer indefinite" pattern whose low byte is 0.
  * (compute/quantization.go:30,43: `valueQuantized = uint8(normalized * 255)`) */
@@ -172,7 +183,7 @@ ORA_API void ora_dot_u8_1xN(const uint8_t *q, const uint8_t *rows, size_t n, siz
  * q: 8+d bytes; rows: n packed rows of row_bytes. Returns 0, or -1 for the reference's
  * panic cases (empty vector / empty matrix), -2 for the Fatalf dimension mismatch
  * (q_bytes != row_bytes). */
-ORA_API int ora_cosine_1xN(const uint8_t *q, size_t q_bytes, const uint8_t *rows, size_t n, size_t row_bytes, float *sims) {
+ORA_API ORA_HOT int ora_cosine_1xN(const uint8_t *q, size_t q_bytes, const uint8_t *rows, size_t n, size_t row_bytes, float *sims) {
     if (q_bytes <= 8) return -1;        /* compute.go:12-14 */
     if (n == 0) return -1;              /* compute.go:25-27 */
     if (row_bytes <= 8) return -1;      /* compute.go:29-31 */
