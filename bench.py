@@ -793,16 +793,16 @@ def run_reference(a):
     nq = max(1, min(a.batch, cores))
     queries = oracle.quantize_matrix_f32(unit(nq * (a.steps + a.warmup)))
 
-    def one(q):
+    def one(q, blas_proxy=False):
         probes, _ = oracle.select_probes(q, centroids, a.nprobe)      # untimed relabelling of the pool
         lor = np.repeat(probes.astype(np.uint32), avg)
         t0 = time.perf_counter()
-        oracle.search(q, centroids, rows, lor, doc, a.nprobe, a.k)    # search.go:202-273 for this query
+        oracle.search(q, centroids, rows, lor, doc, a.nprobe, a.k, blas_proxy=blas_proxy)   # search.go:202-273 for this query
         return time.perf_counter() - t0
 
-    def run_step(s):
+    def run_step(s, blas_proxy=False):
         with cf.ThreadPoolExecutor(cores) as ex:
-            return max(ex.map(one, queries[s * nq:(s + 1) * nq]))
+            return max(ex.map(lambda q: one(q, blas_proxy), queries[s * nq:(s + 1) * nq]))
 
     for s in range(a.warmup):
         run_step(s)
@@ -811,6 +811,14 @@ def run_reference(a):
         run_step(s)
     dt = time.perf_counter() - t0
     qps = nq * a.steps / dt
+    # the same steps (a quarter of them) through the oracle's second build -- reorderable, vectorized float64 sums: the labelled
+    # stand-in for the reference's gonum/BLAS build tag, which cannot be built or restated exactly here
+    steps_p = max(1, a.steps // 4)
+    run_step(0, True)
+    t0 = time.perf_counter()
+    for s in range(a.warmup, a.warmup + steps_p):
+        run_step(s, True)
+    qps_proxy = nq * steps_p / (time.perf_counter() - t0)
     out = {
         "impl": "reference",
         "metric": "IVF-Flat search queries/s (768-d uint8, top-10, bit-exact IDs)",
@@ -821,7 +829,10 @@ def run_reference(a):
                    "k": a.k, "batch": a.batch},
         "cpu_baseline": {"value": round(qps, 3), "unit": "queries/s", "cores": cores, "kind": "port",
                          "sample": f"{nq} queries per step (one thread each, {cores} threads), each scoring {a.centroids} centroids "
-                                   f"+ {npe} lists x {avg} rows with the reference's default float64 backend restated in C"},
+                                   f"+ {npe} lists x {avg} rows with the reference's default float64 backend restated in C",
+                         "gonum_blas_proxy": {"value": round(qps_proxy, 3), "unit": "queries/s", "cores": cores, "kind": "port",
+                                              "sample": f"{steps_p} of the same steps; the same source built with reorderable, vectorized "
+                                                        f"float64 sums (stand-in for the gonum build tag's BLAS kernels)"}},
         "e2e": {"value": round(qps, 3), "unit": "queries/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }
     print(json.dumps(out), flush=True)

@@ -173,7 +173,7 @@ def select_probes(q, centroids, nprobe):
     return probes[:rc], sims[:rc]
 
 
-def search(q, centroids, rows, list_of_row, doc_ids, nprobe, k):
+def search(q, centroids, rows, list_of_row, doc_ids, nprobe, k, blas_proxy=False):
     q = _u8(q)
     centroids = _u8(centroids)
     rows = _u8(rows)
@@ -183,7 +183,7 @@ def search(q, centroids, rows, list_of_row, doc_ids, nprobe, k):
     n = rows.shape[0]
     ids = np.empty(k, np.uint64)
     sims = np.empty(k, np.float32)
-    rc = lib().ora_search(_p(q), _p(centroids), C.c_size_t(Cn), _p(rows), C.c_size_t(n), C.c_size_t(rb),
+    rc = (lib_blas_proxy() if blas_proxy else lib()).ora_search(_p(q), _p(centroids), C.c_size_t(Cn), _p(rows), C.c_size_t(n), C.c_size_t(rb),
                           _p(list_of_row), _p(doc_ids), C.c_size_t(nprobe), C.c_size_t(k), _p(ids), _p(sims))
     _check(rc)
     return ids[:rc], sims[:rc]
