@@ -16,6 +16,15 @@ def local_count(n_total, rank, world):
     return (n_total - rank + world - 1) // world if rank < n_total else 0
 
 
+def upload_stripe(first_key, n_new, rank, world):
+    """Upload on a striped store (server/upload.go:239-279): the new embeddings get the primary keys first_key ..
+    first_key + n_new - 1 and the stripe rule is unchanged -- rank r owns the keys with key % world == r.  Returns the
+    indices (into the uploaded batch, ascending) of the rows this rank passes to its own Index.Upload; the ranks need no
+    exchange because the centroid table is replicated, and the next search merges the shards as before."""
+    start = (rank - first_key) % world
+    return np.arange(start, n_new, world, dtype=np.int64)
+
+
 def gather_hits(ids, sims, counts, group=None):
     """all_gather the shard-local results. ids [nq,k] int64 (uint64 bit pattern), sims [nq,k] float32,
     counts [nq] int32 torch tensors (CPU/gloo or CUDA/nccl). Returns ([G,nq,k], [G,nq,k], [G,nq])."""

@@ -112,6 +112,23 @@ def test_stripe_partition():
             assert [len(p) for p in parts] == [pkg.shard.local_count(n, r, world) for r in range(world)]
 
 
+def test_upload_keeps_the_stripe_rule():
+    """After uploads every rank still owns exactly the primary keys with key % world == rank."""
+    from conftest import load_pkg
+    pkg = load_pkg()
+    for world in (1, 2, 3, 8):
+        n = 1003
+        owned = [set(pkg.shard.stripe(n, r, world).tolist()) for r in range(world)]
+        for n_new in (1, 5, 64, 0):
+            parts = [pkg.shard.upload_stripe(n, n_new, r, world) for r in range(world)]
+            assert sorted(np.concatenate(parts).tolist()) == list(range(n_new))
+            for r in range(world):
+                owned[r].update(int(n + i) for i in parts[r])
+            n += n_new
+        for r in range(world):
+            assert owned[r] == set(pkg.shard.stripe(n, r, world).tolist())
+
+
 # ---- k-means over contiguous row blocks: the relay of shard.kmeans_step_relay ------------------------------------------
 def _kmeans_worker(rank, world, port, q):
     """On the GPU box assign / accumulate / finish are libvscuda calls (vs_argmax_MxN_dev, vs_kmeans_accumulate_dev,
