@@ -479,7 +479,10 @@ def run_b200(a):
     if world == 1 and not a.no_extra:
         out["other_configs"] = other_configs(pkg, torch, ctx, ix, a, device, peaks)
     if world == 1 and not a.no_cpu_baseline:
-        out["cpu_baseline"] = cpu_baseline(pkg, ctx, ix, cent, a, qhost[W + K - 1], result_ids, result_sims, offsets)
+        try:
+            out["cpu_baseline"] = cpu_baseline(pkg, ctx, ix, cent, a, qhost[W + K - 1], result_ids, result_sims, offsets)
+        except Exception as e:  # noqa: BLE001 -- the measured line above must still be printed
+            out["cpu_baseline"] = {"error": repr(e)[:300]}
     print(json.dumps(out), flush=True)
     if world > 1:
         dist.barrier()
@@ -622,12 +625,39 @@ def other_configs(pkg, torch, ctx, ix, a, device, peaks):
                 (g_sims[0, :g_cnt[0]].view(np.uint32) == w_sims.view(np.uint32)).all()
         cpu_s = (time.perf_counter() - t0) / nchk
         p50 = lat[len(lat) // 2]
+        # the same call rotating over 4 more stores of the same size (388 MB in all, 3 x the L2): every call finds its rows
+        # in HBM, not in L2.  A separate try: a failure here leaves the figures above standing.
+        cold = None
+        try:
+            stores = []
+            for j in range(4):
+                xj = gen_unit_rows(torch, SEED_DATA, 9200 + j, n1, device)
+                torch.cuda.synchronize()
+                mj = cp.EmptyMatrix(n1, D, ctx=ctx)
+                mj.FillFloat32Dev(0, xj.data_ptr(), n1, ctx=ctx)
+                ctx.sync()
+                stores.append(mj)
+                del xj
+            lat_c = []
+            for i in range(8, 72):
+                t0 = time.perf_counter()
+                pkg.ivf.SearchFlat(stores[i % 4], qh[i], a.k, ctx=ctx)
+                lat_c.append((time.perf_counter() - t0) * 1e6)
+            lat_c = sorted(lat_c[8:])
+            pc = lat_c[len(lat_c) // 2]
+            cold = {"p50": round(pc, 1), "p99": round(lat_c[int(len(lat_c) * 0.99)], 1), "n": len(lat_c),
+                    "scan_gbs": round(n1 * ROW_BYTES / (pc * 1e-6) / 1e9, 1)}
+            del stores
+        except Exception as e:  # noqa: BLE001
+            cold = {"error": repr(e)[:200]}
         out["brute_force_config1"] = {
+            "latency_us_rotating_4_stores": cold,
             "workload": f"brute-force cosine over {n1} x {D}-d uint8 rows, 1 query per call, top-{a.k}, host buffers in and out",
             "latency_us": {"p50": round(p50, 1), "p99": round(lat[int(len(lat) * 0.99)], 1), "n": len(lat)},
             "queries_per_s": round(1e6 / p50, 1), "scan_gbs": round(n1 * ROW_BYTES / (p50 * 1e-6) / 1e9, 1),
-            "l2": "the 77.6 MB store fits the 126 MB L2 and is not flushed between calls (L2-warm); the call is bound by its host "
-                  "round trip and launch latency, not by bandwidth -- the cold, bandwidth-bound form of the same scan is "
+            "l2": "the 77.6 MB store fits the 126 MB L2 and is not flushed between calls (L2-warm) for latency_us; "
+                  "latency_us_rotating_4_stores rotates over 4 other stores (3 x the L2) so every call reads HBM.  Either way the "
+                  "call is bound by its host round trip and launch latency; the bandwidth-bound form of the same scan is "
                   "single_query_full_scan below",
             "cpu_oracle_one_thread_s_per_query": round(cpu_s, 4),
             "parity_vs_oracle": {"queries_checked": nchk, "match": bool(ok)}}
