@@ -60,6 +60,11 @@ def debug_set_argmax_gemm_min(min_centroids):
     _check(_lib.init().vs_debug_set_argmax_gemm_min(int(min_centroids)))
 
 
+def debug_set_fused(on):
+    """Test hook: False sends single-query searches through the two-launch streaming path instead of the fused kernel."""
+    _check(_lib.init().vs_debug_set_fused(1 if on else 0))
+
+
 class Context:
     """One CUDA stream + scratch arena (vs_ctx). One per closure / goroutine (dnc/dnc.go:349)."""
 

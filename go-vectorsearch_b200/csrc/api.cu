@@ -93,8 +93,9 @@ extern "C" int vs_ctx_create(vs_ctx **out) {
     CU(cudaEventCreate(&c->ev1));
     CU(cudaMalloc(&c->d_fix_counter, 8));
     CU(cudaMemset(c->d_fix_counter, 0, 8));
-    CU(cudaMalloc(&c->d_tickets, kMaxStageQueries * sizeof(unsigned int)));
-    CU(cudaMemset(c->d_tickets, 0, kMaxStageQueries * sizeof(unsigned int)));
+    CU(cudaMalloc(&c->d_tickets, (kMaxStageQueries + 8) * sizeof(unsigned int)));
+    CU(cudaMemset(c->d_tickets, 0, (kMaxStageQueries + 8) * sizeof(unsigned int)));
+    c->d_fused_sync = c->d_tickets + kMaxStageQueries;  // [0] grid barrier, [1] tickets, [2] uncertified-pair count
     *out = c;
     return VS_OK;
 }
@@ -110,8 +111,9 @@ extern "C" int vs_ctx_create_on_stream(void *cuda_stream, vs_ctx **out) {
     CU(cudaEventCreate(&c->ev1));
     CU(cudaMalloc(&c->d_fix_counter, 8));
     CU(cudaMemset(c->d_fix_counter, 0, 8));
-    CU(cudaMalloc(&c->d_tickets, kMaxStageQueries * sizeof(unsigned int)));
-    CU(cudaMemset(c->d_tickets, 0, kMaxStageQueries * sizeof(unsigned int)));
+    CU(cudaMalloc(&c->d_tickets, (kMaxStageQueries + 8) * sizeof(unsigned int)));
+    CU(cudaMemset(c->d_tickets, 0, (kMaxStageQueries + 8) * sizeof(unsigned int)));
+    c->d_fused_sync = c->d_tickets + kMaxStageQueries;  // [0] grid barrier, [1] tickets, [2] uncertified-pair count
     *out = c;
     return VS_OK;
 }
@@ -215,6 +217,7 @@ extern "C" int vs_debug_set_certify_scale(float scale) {
     CU(vs::argmax_set_certify_scale(scale));
     CU(vs::gemm_set_certify_scale(scale));
     CU(vs::probe_set_certify_scale(scale));
+    CU(vs::fused_set_certify_scale(scale));
     return VS_OK;
 }
 
@@ -1216,6 +1219,8 @@ struct SearchBufs {
     float *gp_sims;         // [nq][npe]
     int32_t *gp_counts;     // [nq]
     uint32_t *gp_status;    // [nq]
+    uint32_t *fused_keys;   // single query in one launch (fused.cu): [C + 4] centroid keys, [kFusedFlagCap] uncertified centroids
+    uint32_t *fused_flags;
     int grid;               // blocks per stage launch
     int iters1, iters2;     // rows per lane group (tile height) of each stage
     int tile_rows1, tile_rows2;
@@ -1270,8 +1275,8 @@ static size_t probe_batch_bytes(size_t nq, size_t C, size_t npe) {
            2 * Arena::pad(nq * probe_segments(C) * npe * 4);
 }
 
-static size_t search_bytes(size_t nq, size_t npe, int kpl1, int kpl2, int grid, size_t d) {
-    return Arena::pad(nq * npe * 4) + Arena::pad((nq + grid) * (size_t)32 * kpl1 * sizeof(Cand)) +
+static size_t search_bytes(size_t nq, size_t npe, int kpl1, int kpl2, int grid, size_t d, size_t C) {
+    return Arena::pad((C + 4) * 4) + Arena::pad(kFusedFlagCap * 4) + Arena::pad(nq * npe * 4) + Arena::pad((nq + grid) * (size_t)32 * kpl1 * sizeof(Cand)) +
            Arena::pad((nq + grid) * (size_t)32 * kpl2 * sizeof(Cand)) + 3 * Arena::pad(nq * 4) + Arena::pad(nq * d * 8) + 4096;
 }
 
@@ -1302,11 +1307,63 @@ __global__ void probe_from_topk_kernel(const uint64_t *ids, const float *sims, c
     }
 }
 
+// One query: probe stage, selection, list stage and top-k in ONE cooperative launch (fused.cu).  Queries it cannot decide
+// (an uncertified score inside a window) get the usual status bits and are finished by the resolve path.
+static bool g_fused_enabled = true;
+extern "C" int vs_debug_set_fused(int on) {
+    g_fused_enabled = on != 0;
+    return VS_OK;
+}
+static bool fused_eligible(const vs_ctx *c, const vs_index *ix, size_t nq_launch, const uint32_t *d_select, size_t npe, bool flat,
+                           bool exact, bool stage1_only) {
+    if (!g_fused_enabled || nq_launch != 1 || d_select || exact || stage1_only) return false;
+    if (!fused_supported(ix->data->d_pad) || ix->n >= (1ull << 30)) return false;
+    if (flat) return true;
+    return ix->centroids && npe >= 1 && npe <= (size_t)kMaxSeg && npe < ix->C && ix->C < (1ull << 30);
+}
+static int fused_enqueue(vs_ctx *c, const vs_index *ix, const MatView &qv, size_t npe, size_t k, int kpl, bool flat,
+                         const SearchBufs &b, uint64_t *d_ids, float *d_sims, int32_t *d_counts, uint32_t *d_status) {
+    FusedParams p{};
+    p.rows = ix->data->view();
+    p.ids = ix->doc_ids;
+    p.id_base = ix->id_base;
+    if (!flat) {
+        p.cent = ix->centroids->view();
+        p.list_off = ix->list_off;
+        p.npe = (int)npe;
+    } else {
+        p.npe = 0;
+        p.flat_start = 0;
+        p.flat_count = ix->n;
+    }
+    p.query = qv;
+    p.k = (int)k;
+    p.pub = fused_pub((int)k, kpl);
+    p.keys = b.fused_keys;
+    p.flag_list = b.fused_flags;
+    p.flag_cnt = c->d_fused_sync + 2;
+    p.sync = c->d_fused_sync;
+    p.partial = reinterpret_cast<uint4 *>(b.partial2);  // (1 + grid) * 32 * kpl entries of 16 bytes >= grid * pub
+    p.out_ids = d_ids;
+    p.out_sims = d_sims;
+    p.out_counts = d_counts;
+    p.out_status = d_status;
+    p.out_probe = nullptr;
+    p.trace = c->trace ? c->d_trace : nullptr;
+    if (p.trace) CU(cudaMemsetAsync(p.trace, 0, kTraceBlocks * 16 * sizeof(unsigned long long), c->stream));
+    VS(prof_mark(c));
+    LAUNCH(c, launch_fused_search(p, kpl, g_sm_count, c->stream));
+    VS(prof_mark(c));
+    return VS_OK;
+}
+
 // Enqueue the two stages for nq_launch queries (all, or those listed in d_select).
 static int search_enqueue(vs_ctx *c, const vs_index *ix, const MatView &qv, size_t nq_launch, const uint32_t *d_select,
                           size_t npe, size_t k, int kpl1, int kpl2, bool flat, bool exact, const SearchBufs &b,
                           uint64_t *d_ids, float *d_sims, int32_t *d_counts, uint32_t *d_status, float *d_probe_sims,
                           bool stage1_only) {
+    if (fused_eligible(c, ix, nq_launch, d_select, npe, flat, exact, stage1_only))
+        return fused_enqueue(c, ix, qv, npe, k, kpl2, flat, b, d_ids, d_sims, d_counts, d_status);
     StageParams p{};
     bool chained = false;
     p.queries = qv;
@@ -1416,7 +1473,7 @@ static int search_setup(vs_ctx *c, Arena &a, const vs_index *ix, size_t nq, size
     if (nq == 0) return fail(VS_EINVAL, "nq == 0");
     if (nq > (size_t)kMaxStageQueries) return fail(VS_ERANGE, "nq=%zu: at most %d queries per call", nq, kMaxStageQueries);
     if (k == 0) return fail(VS_EINVAL, "k == 0");
-    if (ix->n > 0x7FFFFFFFull) return fail(VS_ERANGE, "a device store holds < 2^31 rows per GPU");
+    if (ix->n > 0x3FFFFFFFull) return fail(VS_ERANGE, "a device store holds < 2^30 rows per GPU");
     if (nprobe == 0) nprobe = 1;  // search.go:118-119
     s->flat = nprobe >= ix->C && !rank_all;  // rank_all: stage 1 only, the caller wants the ranked list itself
     s->npe = nprobe >= ix->C ? ix->C : nprobe;
@@ -1425,7 +1482,7 @@ static int search_setup(vs_ctx *c, Arena &a, const vs_index *ix, size_t nq, size
     if (!s->kpl2) return fail(VS_ERANGE, "k=%zu: at most 128 hits (Count+Offset) per query", k);
     if (!s->kpl1) return fail(VS_ERANGE, "nprobe=%zu: at most 128 probed lists unless nprobe >= number of lists", nprobe);
     VS(search_plan(ix, nq, s->npe, s->flat, &s->b));
-    VS(a.reserve(a.off + extra_bytes + search_bytes(nq, s->npe, s->kpl1, s->kpl2, s->b.grid, ix->data->d) +
+    VS(a.reserve(a.off + extra_bytes + search_bytes(nq, s->npe, s->kpl1, s->kpl2, s->b.grid, ix->data->d, ix->C) +
                  (use_probe_gemm(ix, nq, s->npe, s->flat) ? probe_gemm_bytes(ix, nq, s->npe)
                   : use_probe_batch(ix, nq, s->npe, s->flat) ? probe_batch_bytes(nq, ix->C, s->npe) : 0)));
     return VS_OK;
@@ -1439,6 +1496,8 @@ static void search_take(Arena &a, const vs_index *ix, size_t nq, SearchSetup *s)
     s->b.tickets = a.take<unsigned int>(nq);
     s->b.qnorm = a.take<double>(nq * (size_t)ix->data->d);
     s->b.q_select = a.take<uint32_t>(nq);
+    s->b.fused_keys = a.take<uint32_t>(ix->C + 4);
+    s->b.fused_flags = a.take<uint32_t>(kFusedFlagCap);
     s->b.probe_keys = nullptr;
     s->b.gemm_probe = use_probe_gemm(ix, nq, s->npe, s->flat);
     if (s->b.gemm_probe) {

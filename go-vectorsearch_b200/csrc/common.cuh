@@ -29,6 +29,12 @@ struct Cand {
     uint64_t id;
 };
 constexpr uint32_t kFlagBit = 0x80000000u;
+// meta bit30 (with explicit document ids only): another row of the same document with the same float32 score, equally
+// uncertain, was dropped in favour of this one (one hit per document, server/search.go:260-268).  If the literal
+// re-score moves this row down, the dropped one may have been the document's best: the query is then finished by the
+// literal-arithmetic kernel.  Rows per device store are < 2^30 (a 180 GB GPU holds ~2.3e8 rows of 784 B).
+constexpr uint32_t kSibBit = 0x40000000u;
+constexpr uint32_t kMetaRowMask = 0x3FFFFFFFu;
 constexpr uint64_t kEmptyId = 0xFFFFFFFFFFFFFFFFull;
 
 __host__ __device__ inline uint32_t f32_to_key(float f) {

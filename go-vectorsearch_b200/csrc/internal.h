@@ -25,6 +25,7 @@ struct vs_ctx {
     size_t aux_cap = 0;
     unsigned long long *d_fix_counter = nullptr;  // in-kernel literal re-scores (device)
     unsigned int *d_tickets = nullptr;            // [kMaxStageQueries] zeroed once; every launch re-arms them
+    unsigned int *d_fused_sync = nullptr;         // [3] counters of the single-query kernel (fused.cu), same allocation
     unsigned long long *d_trace = nullptr;        // phase stamps of the last list-scan launch (when enabled)
     bool trace = false;
     // optional per-kernel timing of the list-scan stage
@@ -130,6 +131,36 @@ cudaError_t scan_set_certify_scale(float scale);
 cudaError_t argmax_set_certify_scale(float scale);
 
 cudaError_t gemm_set_certify_scale(float scale);
+
+// fused.cu: one query in one cooperative launch (probe stage, grid barrier, selection, list stage through a TMA ring)
+constexpr int kFusedFlagCap = 256;  // uncertified (query, centroid) pairs listed per launch; more: the caller's literal path
+struct FusedParams {
+    MatView rows;              // the store (rows grouped by list) or a flat matrix
+    const uint64_t *ids;       // per-row document id, or null -> id_base + row (distinct: no de-duplication needed)
+    uint64_t id_base;
+    MatView cent;              // centroid table (npe > 0)
+    const uint64_t *list_off;  // CSR of the lists (npe > 0)
+    MatView query;             // one row
+    int npe;                   // lists to probe (< number of centroids, <= kMaxSeg); 0 = flat scan of [flat_start, +flat_count)
+    uint64_t flat_start, flat_count;
+    int k, pub;                // hits to emit; distinct documents a block publishes (fused_pub)
+    uint32_t *keys;            // [C + 4] similarity keys of the centroids (16-byte aligned)
+    uint32_t *flag_list;       // [kFusedFlagCap] centroids whose float32 rounding could not be certified
+    unsigned int *flag_cnt;    // zero at launch; re-armed by the kernel
+    unsigned int *sync;        // [2] grid barrier counter and ticket counter: zero at launch; re-armed by the kernel
+    uint4 *partial;            // [gridDim][pub] published candidates (key, meta, id lo, id hi)
+    uint64_t *out_ids;         // [k]
+    float *out_sims;           // [k]
+    int32_t *out_counts;       // [1]
+    uint32_t *out_status;      // [1] stored (kStatusProbeAmbiguous / kStatusListAmbiguous / 0)
+    uint32_t *out_probe;       // optional [npe]
+    unsigned long long *trace; // optional [gridDim][16] globaltimer stamps
+    int stage_bytes, stages;   // ring geometry (filled by the launcher)
+};
+bool fused_supported(int d_pad);
+int fused_pub(int k, int kpl);
+cudaError_t launch_fused_search(const FusedParams &p, int kpl, int grid, cudaStream_t st);
+cudaError_t fused_set_certify_scale(float scale);
 
 // gemm.cu: query batches as a tcgen05 int8 GEMM with a fused filter (BASELINE config 3)
 struct GemmPlan {

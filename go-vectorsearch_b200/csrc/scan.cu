@@ -17,128 +17,10 @@
 #include <cstdio>
 
 #include "internal.h"
+#include "topk.cuh"
 
 namespace vs {
 
-#define FULL 0xFFFFFFFFu
-
-// ---------------------------------------------------------------------------------------------------
-// Warp-distributed sorted top list: rank r lives in slot r/32 of lane r%32, best first.
-template <int KPL>
-struct WarpTopK {
-    uint32_t skey[KPL];
-    uint32_t meta[KPL];
-    uint64_t id[KPL];
-    uint32_t thr_key;  // worst kept entry (rank 32*KPL-1), warp-uniform
-    uint64_t thr_id;
-
-    __device__ __forceinline__ void init() {
-#pragma unroll
-        for (int s = 0; s < KPL; s++) {
-            skey[s] = 0;
-            meta[s] = 0;
-            id[s] = kEmptyId;
-        }
-        thr_key = 0;
-        thr_id = kEmptyId;
-    }
-
-    // Insert one (warp-uniform) candidate.
-    __device__ __forceinline__ void insert(uint32_t ck, uint32_t cm, uint64_t cid, int lane) {
-        int pos = 0;
-#pragma unroll
-        for (int s = 0; s < KPL; s++) {
-            bool ahead = !cand_better(ck, cid, skey[s], id[s]);
-            pos += __popc(__ballot_sync(FULL, ahead));
-        }
-        if (pos >= 32 * KPL) return;
-        uint32_t ck_prev = 0, cm_prev = 0;
-        uint64_t cid_prev = 0;
-        const int src = (lane + 31) & 31;
-#pragma unroll
-        for (int s = 0; s < KPL; s++) {
-            uint32_t rk = __shfl_sync(FULL, skey[s], src);
-            uint32_t rm = __shfl_sync(FULL, meta[s], src);
-            uint64_t rid = __shfl_sync(FULL, id[s], src);
-            uint32_t sk = lane == 0 ? ck_prev : rk;
-            uint32_t sm = lane == 0 ? cm_prev : rm;
-            uint64_t sid = lane == 0 ? cid_prev : rid;
-            int r = s * 32 + lane;
-            if (r == pos) {
-                skey[s] = ck;
-                meta[s] = cm;
-                id[s] = cid;
-            } else if (r > pos) {
-                skey[s] = sk;
-                meta[s] = sm;
-                id[s] = sid;
-            }
-            ck_prev = rk;  // on lane 0: the old rank 32*s+31, which moves to rank 32*(s+1)
-            cm_prev = rm;
-            cid_prev = rid;
-        }
-        thr_key = __shfl_sync(FULL, skey[KPL - 1], 31);
-        thr_id = __shfl_sync(FULL, id[KPL - 1], 31);
-    }
-
-    // Offer one candidate per lane.
-    __device__ __forceinline__ void offer(bool valid, uint32_t ck, uint32_t cm, uint64_t cid, int lane) {
-        bool pass = valid && cand_better(ck, cid, thr_key, thr_id);
-        unsigned m = __ballot_sync(FULL, pass);
-        while (m) {
-            int src = __ffs(m) - 1;
-            m &= m - 1;
-            uint32_t bk = __shfl_sync(FULL, ck, src);
-            uint32_t bm = __shfl_sync(FULL, cm, src);
-            uint64_t bid = __shfl_sync(FULL, cid, src);
-            insert(bk, bm, bid, lane);
-        }
-    }
-
-    __device__ __forceinline__ void store(Cand *dst, int lane) const {
-#pragma unroll
-        for (int s = 0; s < KPL; s++) {
-            Cand c;
-            c.skey = skey[s];
-            c.meta = meta[s];
-            c.id = id[s];
-            dst[s * 32 + lane] = c;
-        }
-    }
-
-    template <typename B>
-    __device__ __forceinline__ void store_soa(B &b, int base, int lane) const {
-#pragma unroll
-        for (int s = 0; s < KPL; s++) {
-            b.key[base + s * 32 + lane] = skey[s];
-            b.meta[base + s * 32 + lane] = meta[s];
-            b.id[base + s * 32 + lane] = id[s];
-        }
-    }
-    template <typename B>
-    __device__ __forceinline__ void load_soa(const B &b, int base, int lane) {
-#pragma unroll
-        for (int s = 0; s < KPL; s++) {
-            skey[s] = b.key[base + s * 32 + lane];
-            meta[s] = b.meta[base + s * 32 + lane];
-            id[s] = b.id[base + s * 32 + lane];
-        }
-        thr_key = __shfl_sync(0xFFFFFFFFu, skey[KPL - 1], 31);
-        thr_id = __shfl_sync(0xFFFFFFFFu, id[KPL - 1], 31);
-    }
-
-    // Offer a stored list (32*KPL entries, sorted best-first) from shared memory.
-    __device__ __forceinline__ void merge_from(const Cand *src, int lane) {
-#pragma unroll
-        for (int s = 0; s < KPL; s++) {
-            Cand c = src[s * 32 + lane];
-            // lists are sorted: once a whole chunk fails the threshold the rest fails too
-            bool any = __any_sync(FULL, c.skey != 0 && cand_better(c.skey, c.id, thr_key, thr_id));
-            if (!any) break;
-            offer(c.skey != 0, c.skey, c.meta, c.id, lane);
-        }
-    }
-};
 
 // ---------------------------------------------------------------------------------------------------
 // Tile dot products. A tile is NG*iters consecutive rows (NG = 32/G lane groups, `iters` rows per group):
@@ -187,112 +69,6 @@ __device__ __forceinline__ uint32_t tile_dots_generic(const uint8_t *__restrict_
         if (lane == r) mydot = acc;
     }
     return mydot;
-}
-
-// ---------------------------------------------------------------------------------------------------
-// Block-wide merge machinery.  Candidates live in shared memory as three arrays (key, meta, id).  A
-// warp-shuffle insertion costs ~100 cycles per candidate and a barrier-per-step bitonic sort ~400 cycles
-// per step, so ordering is done by RANK instead: every thread computes the final position of its own
-// candidate (binary searches against the other sorted lists, or a count over an unsorted set) and
-// scatters it -- no barriers inside, one at the end.
-constexpr int kSortCap = 1024;  // input candidates per merge (>= kStageWarps * 128)
-constexpr int kOutCap = 512;    // output / slot-head buffer
-
-struct CandBuf {
-    uint32_t *key;
-    uint32_t *meta;
-    uint64_t *id;
-};
-struct SortSmem {
-    uint64_t id_a[kSortCap];
-    uint64_t id_b[kOutCap];
-    uint32_t key_a[kSortCap];
-    uint32_t meta_a[kSortCap];
-    uint32_t key_b[kOutCap];
-    uint32_t meta_b[kOutCap];
-};
-
-__device__ __forceinline__ void cand_put(const CandBuf &b, int i, uint32_t k, uint32_t m, uint64_t id) {
-    b.key[i] = k;
-    b.meta[i] = m;
-    b.id[i] = id;
-}
-
-// e precedes f in the merged order; equal (key,id) pairs are ordered by (list, position) to keep ranks unique.
-__device__ __forceinline__ bool cand_before(uint32_t ek, uint64_t eid, int eorder, uint32_t fk, uint64_t fid, int forder) {
-    return ek > fk || (ek == fk && (eid < fid || (eid == fid && eorder < forder)));
-}
-
-// Merge nl sorted lists (list l occupies src[l*stride .. l*stride+len[l]) or, when len == nullptr, `stride`
-// entries each) into dst[0..outcap) best-first.  One thread per input entry; ends with a barrier.
-__device__ __forceinline__ void rank_merge(const CandBuf &src, int nl, int stride, const int *len, const CandBuf &dst,
-                                           int outcap) {
-    const int total = nl * stride;
-    for (int e = threadIdx.x; e < total; e += blockDim.x) {
-        const int l = e / stride, pos = e - l * stride;
-        const int mylen = len ? len[l] : stride;
-        if (pos >= mylen) continue;
-        const uint32_t k = src.key[e];
-        const uint64_t id = src.id[e];
-        int rank = pos;
-        for (int o = 0; o < nl && rank < outcap; o++) {
-            if (o == l) continue;
-            const int base = o * stride;
-            int lo = 0, hi = len ? len[o] : stride;
-            while (lo < hi) {  // number of entries of list o that precede (k,id,l)
-                const int mid = (lo + hi) >> 1;
-                if (cand_before(src.key[base + mid], src.id[base + mid], o, k, id, l)) lo = mid + 1;
-                else hi = mid;
-            }
-            rank += lo;
-        }
-        if (rank < outcap) cand_put(dst, rank, k, src.meta[e], id);
-    }
-    __syncthreads();
-}
-
-// Warp bitonic sort of 32 candidates held one per lane (registers + shuffles, no shared memory).
-__device__ __forceinline__ void warp_sort32(uint32_t &k, uint32_t &m, uint64_t &id, int lane) {
-#pragma unroll
-    for (int kk = 2; kk <= 32; kk <<= 1) {
-#pragma unroll
-        for (int j = kk >> 1; j > 0; j >>= 1) {
-            const uint32_t ok = __shfl_xor_sync(FULL, k, j);
-            const uint32_t om = __shfl_xor_sync(FULL, m, j);
-            const uint64_t oid = __shfl_xor_sync(FULL, id, j);
-            const bool up = (lane & kk) == 0;        // this run ends up best-first
-            const bool lower = (lane & j) == 0;      // I hold the lower index of the pair
-            const bool want_better = (up == lower);  // the better of the two belongs here
-            const bool other_better = cand_better(ok, oid, k, id);
-            if (other_better == want_better && !(ok == k && oid == id)) {
-                k = ok;
-                m = om;
-                id = oid;
-            }
-        }
-    }
-}
-
-// Order an unsorted set src[0..n) (n <= kOutCap, src has room for n rounded up to 32) into dst[0..outcap)
-// best-first: every warp sorts 32-entry chunks in registers, then the chunks are rank-merged.  Barriers inside.
-__device__ __forceinline__ void block_sort_small(const CandBuf &src, int n, const CandBuf &dst, int outcap) {
-    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarp = blockDim.x >> 5;
-    const int nch = (n + 31) >> 5;
-    for (int ch = warp; ch < nch; ch += nwarp) {
-        const int e = ch * 32 + lane;
-        uint32_t k = 0, m = 0;
-        uint64_t id = kEmptyId;
-        if (e < n) {
-            k = src.key[e];
-            m = src.meta[e];
-            id = src.id[e];
-        }
-        warp_sort32(k, m, id, lane);
-        cand_put(src, e, k, m, id);
-    }
-    for (int e = threadIdx.x; e < outcap; e += blockDim.x) cand_put(dst, e, 0u, 0u, kEmptyId);
-    __syncthreads();
-    rank_merge(src, nch, 32, nullptr, dst, outcap);
 }
 
 // ---------------------------------------------------------------------------------------------------
@@ -467,6 +243,9 @@ stage_kernel(const StageParams p) {
 
         WarpTopK<KPL> top;
         top.init();
+        // one hit per document (search.go:260-268): removed BEFORE any list is cut to its capacity, at insert time and in
+        // every merge.  Implicit ids (id_base + row) are distinct by construction.
+        const bool dedup = (p.mode == 0) && (p.ids != nullptr);
         VS_TRACE(1);
 
         // ---- main loop: this block's tiles of this query, round-robin over its warps ----
@@ -520,22 +299,20 @@ stage_kernel(const StageParams p) {
             // lazy id: only rows that can still enter the list need their document id
             const bool cand = valid && key >= top.thr_key;
             if (cand && cid == kEmptyId) cid = p.ids ? p.ids[row] : p.id_base + row;
-            top.offer(cand, key, (uint32_t)row | (flag ? kFlagBit : 0u), cid, lane);
+            top.offer(cand, key, (uint32_t)row | (flag ? kFlagBit : 0u), cid, lane, dedup);
             row0 = next_row0;
             nrows = next_nrows;
         }
 
-        // ---- block merge: every warp's (sorted) list -> shared memory -> rank merge -> partial slot (qslot + block) ----
+        // ---- block merge: every warp's (sorted) list -> shared memory -> rank merge (duplicates out) -> partial slot ----
+        CandBuf res = bufB;  // where the block's merged list (and later the query's final list) lives
         {
-            int cnt = 0;
-#pragma unroll
-            for (int s2 = 0; s2 < KPL; s2++) cnt += __popc(__ballot_sync(FULL, top.skey[s2] != 0));
+            const int cnt = top.count();
             if (lane == 0) sh.warp_cnt[warp] = cnt;
             top.store_soa(bufA, warp * CAP, lane);
-            for (int e = threadIdx.x; e < CAP; e += blockDim.x) cand_put(bufB, e, 0u, 0u, kEmptyId);
             __syncthreads();
             VS_TRACE(2);
-            rank_merge(bufA, kStageWarps, CAP, sh.warp_cnt, bufB, CAP);  // top CAP of the block -> bufB
+            res = merge_lists(bufA, kStageWarps, CAP, sh.warp_cnt, bufB, CAP, dedup, ss.scan_tmp);  // top CAP of the block
         }
         VS_TRACE(8);
         const uint32_t blo = block_of_tile(P0, T, Gd), bhi = block_of_tile(P1 - 1, T, Gd);
@@ -543,10 +320,10 @@ stage_kernel(const StageParams p) {
             Cand *slot = p.partial + ((size_t)qslot + blockIdx.x) * CAP;
             for (int e = threadIdx.x; e < CAP; e += blockDim.x) {
                 uint4 v;
-                v.x = bufB.key[e];
-                v.y = bufB.meta[e];
-                v.z = (uint32_t)bufB.id[e];
-                v.w = (uint32_t)(bufB.id[e] >> 32);
+                v.x = res.key[e];
+                v.y = res.meta[e];
+                v.z = (uint32_t)res.id[e];
+                v.w = (uint32_t)(res.id[e] >> 32);
                 *reinterpret_cast<uint4 *>(slot + e) = v;
             }
         }
@@ -576,24 +353,25 @@ stage_kernel(const StageParams p) {
                 id = (uint64_t)v.z | ((uint64_t)v.w << 32);
             };
             if (nslots == 1) {
-                // the block's own sorted list is still in bufB[0..CAP)
+                // the block's own sorted list is still in res[0..CAP)
             } else if (nslots * CAP <= kSortCap) {
                 // few slots: merge them all by rank
+                __syncthreads();
                 for (int e = threadIdx.x; e < nslots * CAP; e += blockDim.x) {
                     uint32_t k, m;
                     uint64_t id;
                     ld_cand(e / CAP, e % CAP, k, m, id);
                     cand_put(bufA, e, k, m, id);
                 }
-                for (int e = threadIdx.x; e < CAP; e += blockDim.x) cand_put(bufB, e, 0u, 0u, kEmptyId);
                 __syncthreads();
-                rank_merge(bufA, nslots, CAP, nullptr, bufB, CAP);
+                res = merge_lists(bufA, nslots, CAP, nullptr, bufB, CAP, dedup, ss.scan_tmp);
             } else {
                 // many slots: the CAP-th best of the slot heads bounds the CAP-th best overall from below, so only
                 // entries at least that good can matter; each slot is sorted, so they form a prefix of it.
                 const int mh = (CAP + nslots - 1) / nslots;  // heads per slot so that at least CAP are gathered
                 const int ng = nslots * mh;
                 bool slow = ng > 2 * (int)blockDim.x;
+                uint32_t tkey = 0;
                 if (!slow) {
                     // each thread holds up to two gathered heads
                     uint32_t hk[2] = {0u, 0u}, hm[2] = {0u, 0u};
@@ -605,7 +383,7 @@ stage_kernel(const StageParams p) {
                     }
                     VS_TRACE(11);
                     // exact CAP-th largest key among the heads, built bit by bit from block-wide counts
-                    uint32_t tkey = 0;
+                    tkey = 0;
                     for (int bit = 31; bit >= 0; bit--) {
                         const uint32_t cand_t = tkey | (1u << bit);
                         int c = __syncthreads_count(hk[0] >= cand_t);
@@ -644,7 +422,19 @@ stage_kernel(const StageParams p) {
                     __syncthreads();
                     VS_TRACE(13);
                     slow = sh.overflow != 0;
-                    if (!slow) block_sort_small(bufA, (int)sh.extra_count, bufB, CAP);  // final list -> bufB[0..CAP)
+                    if (!slow && !dedup) {
+                        block_sort_small(bufA, (int)sh.extra_count, bufB, CAP);  // final list -> bufB[0..CAP)
+                        res = bufB;
+                    } else if (!slow) {
+                        // everything collected in order, then one hit per document, then the cut
+                        const int n = (int)sh.extra_count;
+                        block_sort_small(bufA, n, bufB, n);
+                        const int uniq = block_unique_compact(bufB, n, bufA, CAP, ss.scan_tmp);
+                        res = bufA;
+                        // duplicates across blocks left fewer than CAP documents although entries below the threshold
+                        // were never looked at: take every slot in turn instead (exact)
+                        slow = uniq < CAP && tkey != 0;
+                    }
                 }
                 if (slow) {
                     // degenerate (massive ties or an unusually wide grid): warp 0 inserts every slot in turn
@@ -658,18 +448,19 @@ stage_kernel(const StageParams p) {
                                 ld_cand(sidx, c * 32 + lane, k, m, id);
                                 bool any = __any_sync(FULL, k != 0 && cand_better(k, id, top.thr_key, top.thr_id));
                                 if (!any) break;
-                                top.offer(k != 0, k, m, id, lane);
+                                top.offer(k != 0, k, m, id, lane, dedup);
                             }
                         }
                         top.store_soa(bufB, 0, lane);
                     }
+                    res = bufB;
                     __syncthreads();
                 }
             }
         }
         VS_TRACE(4);
         if (warp == 0) {
-            top.load_soa(bufB, 0, lane);
+            top.load_soa(res, 0, lane);
             if (lane == 0) p.tickets[qslot] = 0;  // re-arm for the next launch
         }
         VS_TRACE(5);
@@ -679,35 +470,18 @@ stage_kernel(const StageParams p) {
         for (int pass = 0; pass < 2; pass++) {
             bool need_fix = false;
             if (warp == 0) {
-                bool dup[KPL];
                 int outpos[KPL];
-#pragma unroll
-                for (int s = 0; s < KPL; s++) dup[s] = false;
-                if (p.mode == 0) {  // dedup by id keeping the best-ranked entry (server/search.go:260-268)
-#pragma unroll
-                    for (int s0 = 0; s0 < KPL; s0++) {
-                        for (int l0 = 0; l0 < 32; l0++) {
-                            uint64_t bid = __shfl_sync(FULL, top.id[s0], l0);
-                            uint32_t bk = __shfl_sync(FULL, top.skey[s0], l0);
-                            if (bk == 0) break;  // rest of the list is empty (warp-uniform)
-#pragma unroll
-                            for (int s = 0; s < KPL; s++) {
-                                int r = s * 32 + lane;
-                                if (r > s0 * 32 + l0 && top.skey[s] != 0 && top.id[s] == bid) dup[s] = true;
-                            }
-                        }
-                    }
-                }
+                // (every list holds distinct documents: search.go:260-268 happened on the way, nothing to remove here)
                 int base = 0;
                 bool anyflag = false;
                 uint32_t kth_key = 0;
                 uint64_t kth_id = kEmptyId;
 #pragma unroll
                 for (int s = 0; s < KPL; s++) {
-                    bool keep = top.skey[s] != 0 && !dup[s];
+                    bool keep = top.skey[s] != 0;
                     unsigned m = __ballot_sync(FULL, keep);
                     outpos[s] = base + __popc(m & ((1u << lane) - 1u));
-                    // every entry (kept or duplicate) ranked before the k-th unique one must be certain
+                    // every entry ranked before the k-th one must be certain
                     anyflag |= __any_sync(FULL, top.skey[s] != 0 && outpos[s] < p.k && (top.meta[s] & kFlagBit));
                     unsigned mk = __ballot_sync(FULL, keep && outpos[s] == p.k - 1);
                     if (mk) {
@@ -721,6 +495,7 @@ stage_kernel(const StageParams p) {
                     need_fix = true;
                     top.store_soa(bufA, 0, lane);
                     if (lane == 0) {
+                        sh.overflow = 0;
                         sh.tail_key = top.thr_key;
                         sh.tail_id = top.thr_id;
                     }
@@ -728,6 +503,7 @@ stage_kernel(const StageParams p) {
                     if (anyflag) status |= p.status_bit;  // (EXACT never flags; defensive)
                     if (pass == 1 && full && kth_key != 0 && cand_better(sh.tail_key, sh.tail_id, kth_key, kth_id))
                         status |= p.status_bit;  // a re-scored entry fell below rows that were not kept
+                    if (pass == 1 && sh.overflow) status |= p.status_bit;
                     if (p.mode == 1) {
                         uint32_t mytiles = 0;
 #pragma unroll
@@ -751,7 +527,7 @@ stage_kernel(const StageParams p) {
                     } else {
 #pragma unroll
                         for (int s = 0; s < KPL; s++) {
-                            bool keep = top.skey[s] != 0 && !dup[s];
+                            bool keep = top.skey[s] != 0;
                             if (keep && outpos[s] < p.k) {
                                 p.out_ids[(size_t)qi * p.k + outpos[s]] = top.id[s];
                                 p.out_sims[(size_t)qi * p.k + outpos[s]] = key_to_f32(top.skey[s]);
@@ -791,12 +567,16 @@ stage_kernel(const StageParams p) {
                 for (int e = warp; e < CAP; e += kStageWarps) {
                     const uint32_t k0 = bufA.key[e], m0 = bufA.meta[e];
                     if (k0 != 0 && (m0 & kFlagBit)) {
-                        const size_t row = m0 & ~kFlagBit;
+                        const size_t row = m0 & kMetaRowMask;
                         const float2 h = p.rows.hdr[row];
                         const double dot = warp_ref_cosine_row_f64(p.rows.codes + row * (size_t)d_pad, h.x, h.y, sh_qn, D, lane);
                         if (lane == 0) {
-                            bufA.key[e] = f32_to_key(__double2float_rn(dot));
-                            bufA.meta[e] = m0 & ~kFlagBit;
+                            const uint32_t k1 = f32_to_key(__double2float_rn(dot));
+                            bufA.key[e] = k1;
+                            bufA.meta[e] = m0 & kMetaRowMask;
+                            // an equally scored, equally uncertain row of the same document was dropped on the way: if this
+                            // one's true score is the lower neighbour, the document's best hit is not known here
+                            if ((m0 & kSibBit) && k1 != k0) sh.overflow = 1;
                             if (p.fix_counter) atomicAdd(p.fix_counter, 1ull);
                         }
                     }
@@ -1020,26 +800,13 @@ __global__ void topk_merge_kernel(const uint64_t *ids_in, const float *sims_in, 
             size_t off = (size_t)qi * k + (valid ? j : 0);
             uint32_t key = valid ? f32_to_key(gs[off]) : 0u;
             uint64_t id = valid ? gi[off] : kEmptyId;
-            top.offer(valid, key, 0u, id, lane);
-        }
-    }
-    bool dup[4] = {false, false, false, false};
-    for (int s0 = 0; s0 < 4; s0++) {
-        for (int l0 = 0; l0 < 32; l0++) {
-            uint64_t bid = __shfl_sync(FULL, top.id[s0], l0);
-            uint32_t bk = __shfl_sync(FULL, top.skey[s0], l0);
-            if (bk == 0) break;
-#pragma unroll
-            for (int s = 0; s < 4; s++) {
-                int r = s * 32 + lane;
-                if (r > s0 * 32 + l0 && top.skey[s] != 0 && top.id[s] == bid) dup[s] = true;
-            }
+            top.offer(valid, key, 0u, id, lane, true);  // one hit per document across shards, before the cut
         }
     }
     int base = 0;
 #pragma unroll
     for (int s = 0; s < 4; s++) {
-        bool keep = top.skey[s] != 0 && !dup[s];
+        bool keep = top.skey[s] != 0;
         unsigned m = __ballot_sync(FULL, keep);
         int outpos = base + __popc(m & ((1u << lane) - 1u));
         if (keep && outpos < k) {

@@ -65,6 +65,10 @@ VS_API int vs_debug_set_certify_scale(float scale);
 /* Test hook: from how many centroids on vs_argmax_MxN / vs_kmeans_step assign through the tensor-core GEMM
  * (default 256; below that the HBM-bound dp4a scan of the data rows is faster). */
 VS_API int vs_debug_set_argmax_gemm_min(size_t min_centroids);
+/* Test hook: 0 sends single-query searches through the two-launch streaming path (scan.cu) instead of the one-launch
+ * fused kernel (fused.cu: probe stage, grid barrier, selection, TMA-ring list scan and top-k in one cooperative
+ * launch; replaces server/search.go:214-273 for one query).  Default 1. */
+VS_API int vs_debug_set_fused(int on);
 /* CUDA-event timing on the ctx stream (bench.py): start/stop bracket, elapsed in ms after sync. */
 VS_API int vs_ctx_timer_start(vs_ctx *ctx);
 VS_API int vs_ctx_timer_stop(vs_ctx *ctx, float *ms_out);

@@ -342,3 +342,80 @@ def test_probe_selection_on_tensor_cores(vs, oracle):
         want_ids, want_sims = oracle.search(qs[i], cent, rows, lists, doc, nprobe, k)
         assert ids[i, :counts[i]].tolist() == want_ids.tolist(), f"query {i}"
         assert (f32_bits(hs[i, :counts[i]]) == f32_bits(want_sims)).all()
+
+
+# ---- one hit per document BEFORE the cut (search.go:259-271): a document whose embeddings crowd the top of the list ----
+def _crowded_inputs(oracle, n, d, C, seed, crowd, ndocs_crowd=1):
+    """`crowd` rows close to the query direction share `ndocs_crowd` document ids; every other row is its own document."""
+    rng = np.random.default_rng(seed)
+    x = unit_rows(n, d, seed)
+    qdir = unit_rows(1, d, seed + 7)[0]
+    hot = rng.choice(n, crowd, replace=False)
+    x[hot] = qdir + 0.05 * rng.standard_normal((crowd, d)).astype(np.float32) / np.sqrt(d) * 4.0
+    x[hot] /= np.linalg.norm(x[hot], axis=1, keepdims=True)
+    rows = oracle.quantize_matrix_f32(x)
+    cent = oracle.quantize_matrix_f32(unit_rows(C, d, seed + 1))
+    _, lists = oracle.argmax_MxN(cent, rows)
+    doc = np.arange(n, dtype=np.uint64) + 10_000
+    doc[hot] = 7 + (np.arange(crowd) % ndocs_crowd)
+    q = oracle.quantize_vector_f32(qdir)
+    return rows, cent, lists.astype(np.uint32), doc, q
+
+
+@pytest.mark.parametrize("k,crowd,ndocs", [(10, 40, 1), (32, 40, 1), (20, 300, 3), (64, 200, 2), (100, 500, 5)])
+def test_document_crowding_the_top(vs, oracle, k, crowd, ndocs):
+    """One document owns more rows at the top than any kept list holds (32 / 64 / 128 entries): the reference still
+    returns k distinct documents (it de-duplicates the whole running list before it truncates)."""
+    n, d, C = 12000, 256, 12
+    rows, cent, lists, doc, q = _crowded_inputs(oracle, n, d, C, 300 + k, crowd, ndocs)
+    ix = vs.ivf.Index.build_assigned(rows, doc, lists, cent)
+    qs = np.stack([q, oracle.quantize_vector_f32(unit_rows(1, d, 5)[0])])
+    for nprobe in (C, 5):      # every list (flat form of the scan) and a probed subset
+        ids, sims, counts = ix.Search(qs, nprobe, k)
+        for i in range(2):
+            want_ids, want_sims = oracle.search(qs[i], cent, rows, lists, doc, nprobe, k)
+            assert counts[i] == len(want_ids) == k, (nprobe, i, counts[i], len(want_ids))
+            assert ids[i, :k].tolist() == want_ids.tolist(), (nprobe, i)
+            assert (f32_bits(sims[i, :k]) == f32_bits(want_sims)).all()
+            assert len(set(ids[i, :k].tolist())) == k
+
+
+def test_merge_removes_cross_shard_duplicates_before_the_cut(vs, oracle):
+    """vs_topk_merge_dev: 8 shards x 20 hits where the same few documents lead every shard's list (a document's
+    embeddings are striped over the ranks): the merged list still has k distinct documents."""
+    import torch
+    G, nq, k = 8, 3, 20
+    dev = torch.device("cuda", 0)
+    rng = np.random.default_rng(3)
+    ids = np.zeros((G, nq, k), np.uint64)
+    sims = np.zeros((G, nq, k), np.float32)
+    for g in range(G):
+        for q in range(nq):
+            s = np.sort(rng.random(k).astype(np.float32))[::-1]
+            i = rng.permutation(1000)[:k].astype(np.uint64) + 100 * (g + 1) * 1000
+            i[:12] = np.arange(12) + q          # the same 12 documents lead on every shard
+            s[:12] = s[:12] + 1.0
+            ids[g, q], sims[g, q] = i, s
+    counts = np.full((G, nq), k, np.int32)
+    t = lambda a, dt: torch.from_numpy(a.view(dt) if a.dtype == np.uint64 else a).to(dev)
+    g_ids, g_sims, g_counts = t(ids, np.int64), t(sims, None), t(counts, None)
+    out_ids = torch.zeros((nq, k), dtype=torch.int64, device=dev)
+    out_sims = torch.zeros((nq, k), dtype=torch.float32, device=dev)
+    out_counts = torch.zeros(nq, dtype=torch.int32, device=dev)
+    torch.cuda.synchronize()
+    ctx = vs.compute.default_context()
+    vs.shard.merge_hits_dev(g_ids, g_sims, g_counts, k, out_ids, out_sims, out_counts, ctx=ctx)
+    ctx.sync()
+    got_ids = out_ids.cpu().numpy().view(np.uint64)
+    got_sims = out_sims.cpu().numpy()
+    for q in range(nq):
+        best = {}
+        for g in range(G):
+            for j in range(k):
+                d_, s_ = int(ids[g, q, j]), float(sims[g, q, j])
+                if d_ not in best or s_ > best[d_]:
+                    best[d_] = s_
+        want = sorted(best.items(), key=lambda kv: (-kv[1], kv[0]))[:k]
+        assert int(out_counts[q]) == k
+        assert got_ids[q].tolist() == [w[0] for w in want]
+        assert got_sims[q].tolist() == [np.float32(w[1]) for w in want]
