@@ -176,9 +176,8 @@ extern "C" int vs_ctx_trace_read(vs_ctx *c, int stage, uint64_t *out, size_t max
     if (!c || !out || !c->d_trace) return fail(VS_EINVAL, "trace not enabled");
     if (stage < 1 || stage > 2) return fail(VS_EINVAL, "stage must be 1 or 2");
     CU(cudaStreamSynchronize(c->stream));
-    size_t nb = (size_t)g_sm_count * 2;
+    size_t nb = kTraceBlocks;  // (blocks that did not run leave zeros)
     if (nb > max_blocks) nb = max_blocks;
-    if (nb > kTraceBlocks) nb = kTraceBlocks;
     CU(cudaMemcpy(out, c->d_trace + (size_t)(stage - 1) * kTraceBlocks * 16, nb * 16 * sizeof(unsigned long long), cudaMemcpyDeviceToHost));
     if (blocks_out) *blocks_out = nb;
     return VS_OK;
@@ -1219,8 +1218,8 @@ struct SearchBufs {
     float *gp_sims;         // [nq][npe]
     int32_t *gp_counts;     // [nq]
     uint32_t *gp_status;    // [nq]
-    uint32_t *fused_keys;   // single query in one launch (fused.cu): [C + 4] centroid keys, [kFusedFlagCap] uncertified centroids
-    uint32_t *fused_flags;
+    uint32_t *fused_keys;   // single query in one launch (fused.cu): [C + 4] centroid keys, [C] list extents + uncertified marks
+    uint4 *fused_seginfo;
     int grid;               // blocks per stage launch
     int iters1, iters2;     // rows per lane group (tile height) of each stage
     int tile_rows1, tile_rows2;
@@ -1276,7 +1275,7 @@ static size_t probe_batch_bytes(size_t nq, size_t C, size_t npe) {
 }
 
 static size_t search_bytes(size_t nq, size_t npe, int kpl1, int kpl2, int grid, size_t d, size_t C) {
-    return Arena::pad((C + 4) * 4) + Arena::pad(kFusedFlagCap * 4) + Arena::pad(nq * npe * 4) + Arena::pad((nq + grid) * (size_t)32 * kpl1 * sizeof(Cand)) +
+    return Arena::pad((C + 4) * 4) + Arena::pad(C * 16) + Arena::pad(nq * npe * 4) + Arena::pad((nq + grid) * (size_t)32 * kpl1 * sizeof(Cand)) +
            Arena::pad((nq + grid) * (size_t)32 * kpl2 * sizeof(Cand)) + 3 * Arena::pad(nq * 4) + Arena::pad(nq * d * 8) + 4096;
 }
 
@@ -1315,9 +1314,9 @@ extern "C" int vs_debug_set_fused(int on) {
     return VS_OK;
 }
 static bool fused_eligible(const vs_ctx *c, const vs_index *ix, size_t nq_launch, const uint32_t *d_select, size_t npe, bool flat,
-                           bool exact, bool stage1_only) {
+                           bool exact, bool stage1_only, int kpl) {
     if (!g_fused_enabled || nq_launch != 1 || d_select || exact || stage1_only) return false;
-    if (!fused_supported(ix->data->d_pad) || ix->n >= (1ull << 30)) return false;
+    if (!fused_supported(ix->data->d_pad, kpl) || ix->n >= (1ull << 30)) return false;
     if (flat) return true;
     return ix->centroids && npe >= 1 && npe <= (size_t)kMaxSeg && npe < ix->C && ix->C < (1ull << 30);
 }
@@ -1340,8 +1339,7 @@ static int fused_enqueue(vs_ctx *c, const vs_index *ix, const MatView &qv, size_
     p.k = (int)k;
     p.pub = fused_pub((int)k, kpl);
     p.keys = b.fused_keys;
-    p.flag_list = b.fused_flags;
-    p.flag_cnt = c->d_fused_sync + 2;
+    p.seginfo = b.fused_seginfo;
     p.sync = c->d_fused_sync;
     p.partial = reinterpret_cast<uint4 *>(b.partial2);  // (1 + grid) * 32 * kpl entries of 16 bytes >= grid * pub
     p.out_ids = d_ids;
@@ -1349,8 +1347,8 @@ static int fused_enqueue(vs_ctx *c, const vs_index *ix, const MatView &qv, size_
     p.out_counts = d_counts;
     p.out_status = d_status;
     p.out_probe = nullptr;
-    p.trace = c->trace ? c->d_trace : nullptr;
-    if (p.trace) CU(cudaMemsetAsync(p.trace, 0, kTraceBlocks * 16 * sizeof(unsigned long long), c->stream));
+    p.trace = c->trace ? c->d_trace : nullptr;  // (both halves: the second holds per-chunk stamps)
+    if (p.trace) CU(cudaMemsetAsync(p.trace, 0, 2 * kTraceBlocks * 16 * sizeof(unsigned long long), c->stream));
     VS(prof_mark(c));
     LAUNCH(c, launch_fused_search(p, kpl, g_sm_count, c->stream));
     VS(prof_mark(c));
@@ -1362,7 +1360,7 @@ static int search_enqueue(vs_ctx *c, const vs_index *ix, const MatView &qv, size
                           size_t npe, size_t k, int kpl1, int kpl2, bool flat, bool exact, const SearchBufs &b,
                           uint64_t *d_ids, float *d_sims, int32_t *d_counts, uint32_t *d_status, float *d_probe_sims,
                           bool stage1_only) {
-    if (fused_eligible(c, ix, nq_launch, d_select, npe, flat, exact, stage1_only))
+    if (fused_eligible(c, ix, nq_launch, d_select, npe, flat, exact, stage1_only, kpl2))
         return fused_enqueue(c, ix, qv, npe, k, kpl2, flat, b, d_ids, d_sims, d_counts, d_status);
     StageParams p{};
     bool chained = false;
@@ -1497,7 +1495,7 @@ static void search_take(Arena &a, const vs_index *ix, size_t nq, SearchSetup *s)
     s->b.qnorm = a.take<double>(nq * (size_t)ix->data->d);
     s->b.q_select = a.take<uint32_t>(nq);
     s->b.fused_keys = a.take<uint32_t>(ix->C + 4);
-    s->b.fused_flags = a.take<uint32_t>(kFusedFlagCap);
+    s->b.fused_seginfo = a.take<uint4>(ix->C);
     s->b.probe_keys = nullptr;
     s->b.gemm_probe = use_probe_gemm(ix, nq, s->npe, s->flat);
     if (s->b.gemm_probe) {

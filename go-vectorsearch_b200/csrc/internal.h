@@ -133,7 +133,6 @@ cudaError_t argmax_set_certify_scale(float scale);
 cudaError_t gemm_set_certify_scale(float scale);
 
 // fused.cu: one query in one cooperative launch (probe stage, grid barrier, selection, list stage through a TMA ring)
-constexpr int kFusedFlagCap = 256;  // uncertified (query, centroid) pairs listed per launch; more: the caller's literal path
 struct FusedParams {
     MatView rows;              // the store (rows grouped by list) or a flat matrix
     const uint64_t *ids;       // per-row document id, or null -> id_base + row (distinct: no de-duplication needed)
@@ -145,8 +144,7 @@ struct FusedParams {
     uint64_t flat_start, flat_count;
     int k, pub;                // hits to emit; distinct documents a block publishes (fused_pub)
     uint32_t *keys;            // [C + 4] similarity keys of the centroids (16-byte aligned)
-    uint32_t *flag_list;       // [kFusedFlagCap] centroids whose float32 rounding could not be certified
-    unsigned int *flag_cnt;    // zero at launch; re-armed by the kernel
+    uint4 *seginfo;            // [C] per centroid: (list start lo, hi, rows in the list, similarity uncertified)
     unsigned int *sync;        // [2] grid barrier counter and ticket counter: zero at launch; re-armed by the kernel
     uint4 *partial;            // [gridDim][pub] published candidates (key, meta, id lo, id hi)
     uint64_t *out_ids;         // [k]
@@ -157,7 +155,7 @@ struct FusedParams {
     unsigned long long *trace; // optional [gridDim][16] globaltimer stamps
     int stage_bytes, stages;   // ring geometry (filled by the launcher)
 };
-bool fused_supported(int d_pad);
+bool fused_supported(int d_pad, int kpl);
 int fused_pub(int k, int kpl);
 cudaError_t launch_fused_search(const FusedParams &p, int kpl, int grid, cudaStream_t st);
 cudaError_t fused_set_certify_scale(float scale);

@@ -23,38 +23,6 @@ namespace vs {
 
 
 // ---------------------------------------------------------------------------------------------------
-// Tile dot products. A tile is NG*iters consecutive rows (NG = 32/G lane groups, `iters` rows per group):
-// group g streams rows g*iters+it. Returns in lane g*G+it (it < iters) the integer dot of that row.
-template <int G, int CPL>
-__device__ __forceinline__ uint32_t tile_dots(const uint8_t *__restrict__ codes, size_t row0, int nrows, int d_pad,
-                                              const uint4 (&q)[CPL], int lane, int iters) {
-    constexpr int U = (CPL <= 3) ? 4 : 2;  // rows in flight per lane group
-    const int g = lane / G, l = lane % G;
-    uint32_t mydot = 0;
-#pragma unroll 1
-    for (int it0 = 0; it0 < iters; it0 += U) {
-        uint4 v[U][CPL];
-#pragma unroll
-        for (int u = 0; u < U; u++) {
-            int r = g * iters + it0 + u;
-            bool ok = (it0 + u < iters) && (r < nrows);
-            const uint8_t *p = codes + (row0 + (size_t)(ok ? r : 0)) * (size_t)d_pad + l * 16;
-#pragma unroll
-            for (int j = 0; j < CPL; j++) v[u][j] = ok ? ld_stream_u4(p + j * G * 16) : make_uint4(0, 0, 0, 0);
-        }
-#pragma unroll
-        for (int u = 0; u < U; u++) {
-            uint32_t acc = 0;
-#pragma unroll
-            for (int j = 0; j < CPL; j++) acc = dot16(v[u][j], q[j], acc);
-#pragma unroll
-            for (int o = G / 2; o > 0; o >>= 1) acc += __shfl_xor_sync(FULL, acc, o);
-            if (l == it0 + u) mydot = acc;
-        }
-    }
-    return mydot;
-}
-
 // Any dimension: whole warp per row (G = 32, NG = 1), query chunks read from shared memory.
 __device__ __forceinline__ uint32_t tile_dots_generic(const uint8_t *__restrict__ codes, size_t row0, int nrows,
                                                       int d_pad, const uint4 *__restrict__ qs, int lane) {

@@ -16,6 +16,39 @@ namespace vs {
 #endif
 
 // ---------------------------------------------------------------------------------------------------
+// Tile dot products. A tile is NG*iters consecutive rows (NG = 32/G lane groups, `iters` rows per group):
+// group g streams rows g*iters+it. Returns in lane g*G+it (it < iters) the integer dot of that row.
+template <int G, int CPL>
+__device__ __forceinline__ uint32_t tile_dots(const uint8_t *__restrict__ codes, size_t row0, int nrows, int d_pad,
+                                              const uint4 (&q)[CPL], int lane, int iters) {
+    constexpr int U = (CPL <= 3) ? 4 : 2;  // rows in flight per lane group
+    const int g = lane / G, l = lane % G;
+    uint32_t mydot = 0;
+#pragma unroll 1
+    for (int it0 = 0; it0 < iters; it0 += U) {
+        uint4 v[U][CPL];
+#pragma unroll
+        for (int u = 0; u < U; u++) {
+            int r = g * iters + it0 + u;
+            bool ok = (it0 + u < iters) && (r < nrows);
+            const uint8_t *p = codes + (row0 + (size_t)(ok ? r : 0)) * (size_t)d_pad + l * 16;
+#pragma unroll
+            for (int j = 0; j < CPL; j++) v[u][j] = ok ? ld_stream_u4(p + j * G * 16) : make_uint4(0, 0, 0, 0);
+        }
+#pragma unroll
+        for (int u = 0; u < U; u++) {
+            uint32_t acc = 0;
+#pragma unroll
+            for (int j = 0; j < CPL; j++) acc = dot16(v[u][j], q[j], acc);
+#pragma unroll
+            for (int o = G / 2; o > 0; o >>= 1) acc += __shfl_xor_sync(FULL, acc, o);
+            if (l == it0 + u) mydot = acc;
+        }
+    }
+    return mydot;
+}
+
+// ---------------------------------------------------------------------------------------------------
 // Warp-distributed sorted top list: rank r lives in slot r/32 of lane r%32, best first.
 template <int KPL>
 struct WarpTopK {
@@ -296,6 +329,64 @@ __device__ __forceinline__ int block_unique_compact(const CandBuf &srt, int n, c
         __syncthreads();
     }
     return scan_tmp[32];
+}
+
+// A small unsorted set (n <= blockDim.x) ordered by COUNTING, with the whole block at work: a lone warp runs a dependent
+// instruction chain at ~5 cycles per instruction, so each candidate gets `tpe` adjacent lanes (as many as the block
+// affords, up to 32); every lane compares the candidate with a strided share of the set, branch-free, and the lanes add
+// their counts with shuffles.  With dedup a first pass finds, the same way, whether a better row of the same document
+// exists (one hit per document, search.go:260-268; equal scores: see kSibBit).
+// src[0..n) -> dst[0..outcap) best-first (empty beyond).  Returns the number of distinct documents.  src's keys of
+// dropped candidates are zeroed.  Barriers inside; all threads call.
+static __device__ __forceinline__ int block_rank_small(CandBuf src, int n, CandBuf dst, int outcap, bool dedup) {
+    int lg = 5;  // tpe = 1 << lg lanes per candidate (shifts, not divisions: a division is ~50 dependent instructions)
+    while (lg > 0 && (n << lg) > (int)blockDim.x) lg--;
+    const int tpe = 1 << lg;
+    const int e = (int)threadIdx.x >> lg, part = (int)threadIdx.x & (tpe - 1);
+    for (int i = threadIdx.x; i < outcap; i += blockDim.x) cand_put(dst, i, 0u, 0u, kEmptyId);
+    const bool mine = e < n;
+    const uint32_t k = mine ? src.key[e] : 0u;
+    const uint64_t id = mine ? src.id[e] : kEmptyId;
+    bool live = k != 0;
+    if (dedup) {
+        // the best row of the same document that precedes this one (score desc, then position), packed for a max-reduce
+        unsigned long long best = 0;
+        for (int f = part; f < n; f += tpe) {
+            const uint32_t fk = src.key[f];
+            const uint64_t fid = src.id[f];
+            const bool hit = live & (fid == id) & ((fk > k) | ((fk == k) & (f < e)));
+            const unsigned long long cand = ((unsigned long long)fk << 32) | (unsigned long long)(0xFFFFFFFFu - (uint32_t)f);
+            best = hit && cand > best ? cand : best;
+        }
+        for (int o = 1; o < tpe; o <<= 1) {
+            const unsigned long long other = __shfl_xor_sync(FULL, best, o);
+            best = other > best ? other : best;
+        }
+        if (best != 0) {
+            live = false;
+            const int f = (int)(0xFFFFFFFFu - (uint32_t)best);
+            if (part == 0 && (uint32_t)(best >> 32) == k) {  // equal float32 scores: the certain row represents the document
+                const uint32_t mf = src.meta[f], me = src.meta[e];
+                if (mf & kFlagBit) {
+                    if (me & kFlagBit) atomicOr(&src.meta[f], kSibBit);
+                    else src.meta[f] = me;
+                }
+            }
+        }
+        __syncthreads();
+        if (mine && !live && part == 0) src.key[e] = 0;  // dropped: out of the ranking below
+    }
+    const int uniq = __syncthreads_count(live && part == 0);
+    int rank = 0;
+    for (int f = part; f < n; f += tpe) {
+        const uint32_t fk = src.key[f];
+        const uint64_t fid = src.id[f];
+        rank += (int)((fk > k) | ((fk == k) & ((fid < id) | ((fid == id) & (f < e)))));
+    }
+    for (int o = 1; o < tpe; o <<= 1) rank += __shfl_xor_sync(FULL, rank, o);
+    if (live && part == 0 && rank < outcap) cand_put(dst, rank, k, src.meta[e], id);
+    __syncthreads();
+    return uniq;
 }
 
 // nl sorted lists (of distinct documents each, when dedup) in src -> the best `outcap` (distinct documents) of their
