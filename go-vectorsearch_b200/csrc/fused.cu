@@ -101,10 +101,6 @@ struct FusedCtl {
     alignas(16) uint4 segbuf[kSegBufCap];  // (list start lo, hi, rows, uncertified) of the probe-stage survivors
 };
 
-#define FUSED_TRACE2(slot)                                                                                  \
-    do {                                                                                                    \
-        if (p.trace) p.trace[(size_t)2048 * 16 + (size_t)blockIdx.x * 96 + (slot)] = fused_timer();           \
-    } while (0)
 #define FUSED_TRACE(slot)                                                                                   \
     do {                                                                                                    \
         if (p.trace && threadIdx.x == 0) p.trace[(size_t)blockIdx.x * 16 + (slot)] = fused_timer();          \
@@ -244,51 +240,62 @@ fused_search_kernel(const FusedParams p) {
     uint4 qreg[CPL];
 #pragma unroll
     for (int j = 0; j < CPL; j++) qreg[j] = *reinterpret_cast<const uint4 *>(p.query.codes + ((lane % G) + G * j) * 16);
+
+    // ================= probe stage: score my share of the centroid table, meet, select =================
+    // A block's share of the table is small (28 rows of 4096 on 148 SMs, L2-resident): plain 128-bit loads issued by every
+    // warp at once beat a ring here.  Tiles are sized so that every warp gets one, and a warp's first tile is loaded and
+    // dotted BEFORE the block waits for thread 0's prologue (the query constants are only needed for the scoring).
+    const uint64_t C = has_probe ? p.cent.n : 0;
+    const uint32_t cq = (uint32_t)C / Gd, cr = (uint32_t)C % Gd;  // block b takes centroids [b*q + min(b,r), ...)
+    const uint64_t c_lo = (uint64_t)blockIdx.x * cq + min(blockIdx.x, cr), c_hi = (uint64_t)(blockIdx.x + 1) * cq + min(blockIdx.x + 1, cr);
+    uint32_t pchunk = (uint32_t)((c_hi - c_lo + kFusedWarps - 1) / kFusedWarps);
+    pchunk = pchunk < (uint32_t)NG ? (uint32_t)NG : (pchunk > 32u ? 32u : pchunk);
+    const uint32_t pnch = (uint32_t)((c_hi - c_lo + pchunk - 1) / pchunk);
+    struct ProbeTile {
+        uint64_t ci, l0, l1;
+        float2 h;
+        uint2 sums;
+        uint32_t dot;
+        bool valid;
+    };
+    auto probe_tile = [&](uint32_t c) {  // loads + integer dots of tile c; the finishing lane's side data beside them
+        ProbeTile t;
+        const uint64_t crow0 = c_lo + (uint64_t)c * pchunk;
+        const int cn = (int)min((uint64_t)pchunk, c_hi - crow0);
+        const int iters = (cn + NG - 1) / NG;
+        const int myr = (lane / G) * iters + (lane % G);
+        t.valid = (lane % G) < iters && myr < cn;
+        t.ci = crow0 + (uint64_t)(t.valid ? myr : 0);
+        t.h = make_float2(0.f, 0.f);
+        t.sums = make_uint2(0, 0);
+        t.l0 = t.l1 = 0;
+        if (t.valid) {
+            t.h = p.cent.hdr[t.ci];
+            t.sums = p.cent.sums[t.ci];
+            t.l0 = __ldg(p.list_off + t.ci);
+            t.l1 = __ldg(p.list_off + t.ci + 1);
+        }
+        t.dot = tile_dots<G, CPL>(p.cent.codes, (size_t)crow0, cn, d_pad, qreg, lane, iters);
+        return t;
+    };
+    ProbeTile first_tile;
+    first_tile.valid = false;
+    if (has_probe && (uint32_t)warp < pnch) first_tile = probe_tile((uint32_t)warp);
     __syncthreads();
     const SideConst xq = ctl.qside;
     FUSED_TRACE(0);
     const long long clk0 = clock64();
-    long long clk_wait = 0, clk_work = 0;
-    unsigned int cs[24];  // cycle stamps of thread 0 (relative to clk0), dumped once at the end when tracing
-#pragma unroll
-    for (int i = 0; i < 24; i++) cs[i] = 0;
-#define CS(i) cs[i] = (unsigned int)(clock64() - clk0)
 
-    // ================= probe stage: score my share of the centroid table, meet, select =================
     if (has_probe) {
-        const uint64_t C = p.cent.n;
-        const uint32_t cq = (uint32_t)C / Gd, cr = (uint32_t)C % Gd;  // block b takes centroids [b*q + min(b,r), ...)
-        const uint64_t c_lo = (uint64_t)blockIdx.x * cq + min(blockIdx.x, cr), c_hi = (uint64_t)(blockIdx.x + 1) * cq + min(blockIdx.x + 1, cr);
-        // A block's share of the table is small (28 rows of 4096 on 148 SMs, L2-resident): plain 128-bit loads issued by
-        // every warp at once beat a ring here.  Tiles are sized so that every warp gets one.
-        uint32_t pchunk = (uint32_t)((c_hi - c_lo + kFusedWarps - 1) / kFusedWarps);
-        pchunk = pchunk < (uint32_t)NG ? (uint32_t)NG : (pchunk > 32u ? 32u : pchunk);
-        const uint32_t nch = (uint32_t)((c_hi - c_lo + pchunk - 1) / pchunk);
-        for (uint32_t c = warp; c < nch; c += kFusedWarps) {
-            const uint64_t crow0 = c_lo + (uint64_t)c * pchunk;
-            const int cn = (int)min((uint64_t)pchunk, c_hi - crow0);
-            const int iters = (cn + NG - 1) / NG;
-            const int myr = (lane / G) * iters + (lane % G);
-            const bool valid = (lane % G) < iters && myr < cn;
-            const uint64_t ci = crow0 + (uint64_t)(valid ? myr : 0);
-            // side data of the row this lane will finish (and its list extent), in flight beside the row bytes
-            float2 h = make_float2(0.f, 0.f);
-            uint2 sm2 = make_uint2(0, 0);
-            uint64_t l0 = 0, l1 = 0;
-            if (valid) {
-                h = p.cent.hdr[ci];
-                sm2 = p.cent.sums[ci];
-                l0 = __ldg(p.list_off + ci);
-                l1 = __ldg(p.list_off + ci + 1);
-            }
-            const uint32_t mydot = tile_dots<G, CPL>(p.cent.codes, (size_t)crow0, cn, d_pad, qreg, lane, iters);
-            if (valid) {
-                bool flag;
-                const float sim = score_fast(xq, h.x, h.y, sm2.x, sm2.y, mydot, D, &flag);
-                p.keys[ci] = f32_to_key(sim);
-                p.seginfo[ci] = make_uint4((uint32_t)l0, (uint32_t)(l0 >> 32), (uint32_t)(l1 - l0), flag ? 1u : 0u);
-            }
-        }
+        auto probe_score = [&](const ProbeTile &t) {
+            if (!t.valid) return;
+            bool flag;
+            const float sim = score_fast(xq, t.h.x, t.h.y, t.sums.x, t.sums.y, t.dot, D, &flag);
+            p.keys[t.ci] = f32_to_key(sim);
+            p.seginfo[t.ci] = make_uint4((uint32_t)t.l0, (uint32_t)(t.l0 >> 32), (uint32_t)(t.l1 - t.l0), flag ? 1u : 0u);
+        };
+        probe_score(first_tile);
+        for (uint32_t c = warp + kFusedWarps; c < pnch; c += kFusedWarps) probe_score(probe_tile(c));
         FUSED_TRACE(1);
         // ---- grid barrier (cooperative launch: every block is resident) ----
         __syncthreads();
@@ -299,7 +306,6 @@ fused_search_kernel(const FusedParams p) {
         }
         __syncthreads();
         FUSED_TRACE(2);
-        CS(0);
         // ---- every block selects the same npe best centroids (search.go:220-223; ties: lower index first) ----
         const uint32_t P = (uint32_t)(((C + kFusedThreads - 1) / kFusedThreads + 3) & ~uint64_t(3));
         uint4 seg_first = make_uint4(0, 0, 0, 0);
@@ -337,9 +343,7 @@ fused_search_kernel(const FusedParams p) {
             uint32_t gm = 0;
 #pragma unroll
             for (int i = 0; i < 16; i++) gm = max(gm, kreg[i]);
-            CS(1);
             const uint32_t thr = block_threshold(gm, p.npe, ctl);
-            CS(2);
             unsigned mask = 0;
 #pragma unroll
             for (int i = 0; i < 16; i++) mask |= (unsigned)((kreg[i] != 0) & (kreg[i] >= thr)) << i;
@@ -385,16 +389,13 @@ fused_search_kernel(const FusedParams p) {
                 keep_all(kk, cnt, thr, k_lo + i);
             }
         }
-        CS(3);
         __syncthreads();
         const int nsurv = (int)min(ctl.cnt, (unsigned)kSegBufCap);
         const bool sel_overflow = ctl.overflow != 0;
         __syncthreads();
-        CS(4);
         block_rank_small(bufA, nsurv, bufB, nsurv, false);  // (nsurv <= kSegBufCap <= blockDim.x)
         if (seg_first_pos >= 0) ctl.segbuf[seg_first_pos] = seg_first;  // (its load was in flight during the ranking)
         __syncthreads();
-        CS(5);
         const int npe = min(p.npe, nsurv);  // (= p.npe: every centroid has a non-zero key and the caller keeps npe < C)
         if (threadIdx.x == 0) {
             ctl.nseg = npe;
@@ -430,7 +431,6 @@ fused_search_kernel(const FusedParams p) {
     // fills; then the buffer is cut to its best CAP distinct documents (sorted insertion, one hit per document) and the
     // CAP-th of them becomes the threshold.  A short scan (one query of BASELINE config 2 gives a warp ~35 rows) never
     // pays for an insertion; a long one cuts a few times (the rate of survivors falls like CAP / rows).
-    CS(6);
     const bool aborted = ctl.abort_status != 0;
     int cnt_w = 0;
     if (!aborted) {
@@ -483,7 +483,6 @@ fused_search_kernel(const FusedParams p) {
         }
         __syncthreads();
         FUSED_TRACE(3);
-        CS(7);
         const uint32_t nch = ctl.nchunks;
         // chunk c of this block: first store row and rows (every lane computes it: warp-uniform)
         auto locate = [&](uint32_t c, uint32_t &row0, uint32_t &nr) {
@@ -543,10 +542,7 @@ fused_search_kernel(const FusedParams p) {
                 if (c >= nch) break;
                 const Pending cur = pend[sl];
                 const uint32_t st = (uint32_t)warp + kFusedWarps * sl;
-                const long long tw0 = clock64();
                 mbar_wait(smem_u32(&ctl.full[st]), (j0 / SPW) & 1u);
-                const long long tw1 = clock64();
-                clk_wait += tw1 - tw0;
                 if (p.trace && c == 0 && lane == 0) ctl.t_first = fused_timer();
                 const int iters = ((int)cur.nr + NG - 1) / NG;
                 const uint32_t mydot = stage_dots<G, CPL>(smem_u32(ring + (size_t)st * stage_bytes), (int)cur.nr, d_pad, qreg, lane, iters);
@@ -591,12 +587,7 @@ fused_search_kernel(const FusedParams p) {
                     wid[slot] = cur.id;
                 }
                 cnt_w += __popc(m);
-                clk_work += clock64() - tw1;
             }
-        }
-        if (p.trace && warp == 0 && lane == 0) {
-            p.trace[(size_t)blockIdx.x * 16 + 14] = (unsigned long long)clk_wait;
-            p.trace[(size_t)blockIdx.x * 16 + 15] = (unsigned long long)clk_work;
         }
         if (lane == 0) {
             ctl.wcnt[warp] = cnt_w;
@@ -604,7 +595,6 @@ fused_search_kernel(const FusedParams p) {
         }
     }
     FUSED_TRACE(4);
-    CS(8);
     __syncthreads();  // every bulk copy of this block has landed and been consumed: the ring is free for the sort buffers
     if (p.trace && threadIdx.x == 0) {
         p.trace[(size_t)blockIdx.x * 16 + 9] = ctl.t_scan_end;
@@ -646,9 +636,7 @@ fused_search_kernel(const FusedParams p) {
             cand_at(e, k, m, id);
             gm = max(gm, k);
         }
-        CS(9);
         const uint32_t thr = block_threshold(gm, pub, ctl);
-        CS(10);
         for (int e = threadIdx.x; e < NS; e += kFusedThreads) {
             uint32_t k, m;
             uint64_t id;
@@ -659,10 +647,8 @@ fused_search_kernel(const FusedParams p) {
                 else ctl.overflow = 1;
             }
         }
-        CS(11);
         bool slow;
         CandBuf res = finish_survivors(bufA, bufB, ctl, CAP, pub, dedup, thr, ss.scan_tmp, &slow);
-        CS(12);
         if (slow) {
             insert_all(cand_at, NS, bufB);
             res = bufB;
@@ -679,7 +665,6 @@ fused_search_kernel(const FusedParams p) {
         }
     }
     FUSED_TRACE(5);
-    CS(13);
     if (p.trace && threadIdx.x == 0) p.trace[(size_t)blockIdx.x * 16 + 13] = (unsigned long long)(clock64() - clk0);
     __syncthreads();
     if (threadIdx.x == 0) {
@@ -690,11 +675,6 @@ fused_search_kernel(const FusedParams p) {
         ctl.overflow = 0;
     }
     __syncthreads();
-    CS(14);
-    if (p.trace && threadIdx.x == 0) {
-#pragma unroll
-        for (int i = 0; i < 15; i++) p.trace[(size_t)2048 * 16 + (size_t)blockIdx.x * 96 + 60 + i] = cs[i];
-    }
     if (!ctl.is_last) return;
     __threadfence();
     if (threadIdx.x == 0) {  // re-arm for the next launch: every block has passed the barrier and taken its ticket
@@ -717,7 +697,6 @@ fused_search_kernel(const FusedParams p) {
         m = v.y;
         id = (uint64_t)v.z | ((uint64_t)v.w << 32);
     };
-    CS(15);
     constexpr int kPer = 4;
     uint32_t tkey = 0;
     if (total <= kPer * kFusedThreads) {  // one round trip: the entries stay in registers between the two passes
@@ -730,9 +709,7 @@ fused_search_kernel(const FusedParams p) {
         }
 #pragma unroll
         for (int u = 0; u < kPer; u++) gm = max(gm, ent[u].x);
-        CS(16);
         tkey = block_threshold(gm, p.k, ctl);
-        CS(17);
 #pragma unroll
         for (int u = 0; u < kPer; u++) {
             if (ent[u].x != 0 && ent[u].x >= tkey) {
@@ -756,10 +733,8 @@ fused_search_kernel(const FusedParams p) {
             }
         }
     }
-    CS(18);
     bool slow;
     CandBuf fin = finish_survivors(bufA, bufB, ctl, CAP, p.k, dedup, tkey, ss.scan_tmp, &slow);
-    CS(19);
     if (slow) {
         insert_all(part_at, total, bufB);
         fin = bufB;
@@ -789,13 +764,6 @@ fused_search_kernel(const FusedParams p) {
         }
     }
     FUSED_TRACE(8);
-    CS(20);
-    if (p.trace && threadIdx.x == 0) {
-#pragma unroll
-        for (int i = 15; i < 21; i++) p.trace[(size_t)2048 * 16 + (size_t)blockIdx.x * 96 + 60 + i] = cs[i];
-        p.trace[(size_t)2048 * 16 + (size_t)blockIdx.x * 96 + 59] = 1;
-    }
-#undef CS
 }
 
 // ---------------------------------------------------------------------------------------------------
