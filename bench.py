@@ -51,6 +51,9 @@ def parse():
     ap.add_argument("--batch", type=int, default=int(os.environ.get("VS_BENCH_BATCH", 256)))
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-extra", action="store_true", help="skip the config-3 / config-4 side measurements")
+    ap.add_argument("--query-major", action="store_true",
+                    help="measurement aid: list stage of the batch through the query-major scan (scan.cu) instead of the "
+                         "list-major one (listmajor.cu)")
     ap.add_argument("--contexts", type=int, default=0, choices=[0, 1, 2, 3, 4],
                     help="search contexts (one CUDA stream each) that take the steps in turn, like the reference's "
                          "one-closure-per-goroutine searches running side by side (0 = 1 on one GPU, 4 on several, where "
@@ -226,6 +229,8 @@ def run_b200(a):
     pkg = load_pkg()
     pkg._lib.init(local_rank)
     cp = pkg.compute
+    if a.query_major:
+        cp.debug_set_list_major(False)
 
     stream = torch.cuda.Stream(device=device)
     ctx = cp.Context(cuda_stream=stream.cuda_stream)   # libvscuda kernels and NCCL share one stream

@@ -21,7 +21,7 @@ SYMBOLS = [
     "vs_index_build", "vs_index_build_assigned", "vs_index_build_dev", "vs_index_create_empty", "vs_index_fill_dev", "vs_index_fill", "vs_index_release",
     "vs_index_rows", "vs_index_lists", "vs_index_cols", "vs_index_list_offsets", "vs_index_read_rows", "vs_index_upload", "vs_search", "vs_search_flat", "vs_search_flat_gemm", "vs_search_batch_dev", "vs_index_search_batch_dev", "vs_search_dev",
     "vs_search_resolve", "vs_select_probes", "vs_topk_merge_dev", "vs_topk_merge_packed_dev",
-    "vs_kmeans_step", "vs_kmeans", "vs_kmeans_accumulate_dev", "vs_kmeans_finish_dev", "vs_recenter", "vs_debug_set_argmax_gemm_min", "vs_debug_set_fused",
+    "vs_kmeans_step", "vs_kmeans", "vs_kmeans_accumulate_dev", "vs_kmeans_finish_dev", "vs_recenter", "vs_debug_set_argmax_gemm_min", "vs_debug_set_fused", "vs_debug_set_list_major",
 ]
 
 
@@ -110,6 +110,7 @@ def load():
         L.vs_search_batch_dev.argtypes = [vp, vp, vp, u64, vp, sz, vp, vp, vp, vp]
         L.vs_debug_set_argmax_gemm_min.argtypes = [sz]
         L.vs_debug_set_fused.argtypes = [C.c_int]
+        L.vs_debug_set_list_major.argtypes = [C.c_int]
         L.vs_matrix_gather.argtypes = [vp, vp, vp, sz, C.POINTER(vp)]
         L.vs_matrix_split_dev.argtypes = [vp, vp, vp, sz, vp, vp]
         L.vs_matrix_split.argtypes = [vp, vp, vp, sz, vp, vp]

@@ -65,6 +65,11 @@ def debug_set_fused(on):
     _check(_lib.init().vs_debug_set_fused(1 if on else 0))
 
 
+def debug_set_list_major(on):
+    """Test hook: False sends the list stage of query batches through the query-major scan instead of the list-major one."""
+    _check(_lib.init().vs_debug_set_list_major(1 if on else 0))
+
+
 class Context:
     """One CUDA stream + scratch arena (vs_ctx). One per closure / goroutine (dnc/dnc.go:349)."""
 

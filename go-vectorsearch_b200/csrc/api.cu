@@ -217,6 +217,7 @@ extern "C" int vs_debug_set_certify_scale(float scale) {
     CU(vs::gemm_set_certify_scale(scale));
     CU(vs::probe_set_certify_scale(scale));
     CU(vs::fused_set_certify_scale(scale));
+    CU(vs::lm_set_certify_scale(scale));
     return VS_OK;
 }
 
@@ -1218,6 +1219,15 @@ struct SearchBufs {
     float *gp_sims;         // [nq][npe]
     int32_t *gp_counts;     // [nq]
     uint32_t *gp_status;    // [nq]
+    // list stage of a batch, list-major (listmajor.cu)
+    bool lm;
+    LmParams lmp;
+    uint32_t *lm_count, *lm_pair_off;
+    uint32_t lm_items_cap;
+    uint64_t *lm_seed_ids;   // exact top k of every query's nearest list (seeds the running bounds)
+    float *lm_seed_sims;
+    int32_t *lm_seed_counts;
+    uint32_t *lm_seed_status;
     uint32_t *fused_keys;   // single query in one launch (fused.cu): [C + 4] centroid keys, [C] list extents + uncertified marks
     uint4 *fused_seginfo;
     int grid;               // blocks per stage launch
@@ -1272,6 +1282,25 @@ static bool use_probe_batch(const vs_index *ix, size_t nq, size_t npe, bool flat
 static size_t probe_batch_bytes(size_t nq, size_t C, size_t npe) {
     return Arena::pad(nq * C * 4) + Arena::pad(nq * 4) + Arena::pad(nq * (size_t)probe_flag_cap(C) * 4) +
            2 * Arena::pad(nq * probe_segments(C) * npe * 4);
+}
+
+// The list stage of a batch goes list-major when lists are shared: with P (query, list) pairs over C lists the expected
+// number of queries per probed list is (P/C) / (1 - exp(-P/C)): 1.27 at P = C/2, 2.3 at P = 2C (256 queries x 32 probes
+// over 4096 lists).  Below that the query-major scan, which has no per-item cost, is as fast.
+static bool g_lm_enabled = true;
+extern "C" int vs_debug_set_list_major(int on) {
+    g_lm_enabled = on != 0;
+    return VS_OK;
+}
+static bool lm_eligible(const vs_index *ix, size_t nq, size_t npe, size_t k, bool flat) {
+    if (!g_lm_enabled || flat || !ix->centroids || nq < 16 || nq > 1024 || nq < kProbeBatchMin) return false;
+    if (nq * npe * 2 < ix->C || ix->n >= (1ull << 30) || ix->C >= (1ull << 30)) return false;
+    return lm_supported(ix->data->d_pad, (int)k);
+}
+static size_t lm_bytes(const vs_index *ix, size_t nq, size_t npe) {
+    return 2 * Arena::pad(ix->C * 4) + Arena::pad(lm_items_cap(ix->n, nq, npe) * sizeof(LmItem)) + Arena::pad(nq * npe * 4) +
+           Arena::pad(nq * sizeof(SideConst)) + 4 * Arena::pad(nq * 4) + Arena::pad(nq * (size_t)kLmGbufCap * 16) + 2 * Arena::pad(8) +
+           Arena::pad(nq * 32 * 8) + Arena::pad(nq * 32 * 4) + 4096;
 }
 
 static size_t search_bytes(size_t nq, size_t npe, int kpl1, int kpl2, int grid, size_t d, size_t C) {
@@ -1415,10 +1444,59 @@ static int search_enqueue(vs_ctx *c, const vs_index *ix, const MatView &qv, size
         p.trace = c->trace ? c->d_trace : nullptr;
         if (p.trace) CU(cudaMemsetAsync(p.trace, 0, kTraceBlocks * 16 * sizeof(unsigned long long), c->stream));
         // the list stage follows immediately on the stream: let its blocks be scheduled while this stage drains
-        chained = !stage1_only && !c->trace && !c->profile;
+        chained = !stage1_only && !c->trace && !c->profile && !(b.lm && !exact && !d_select && nq_launch == qv.n);
         p.pdl = chained ? 1 : 0;
         LAUNCH(c, launch_stage(p, kpl1, exact, b.grid, c->stream));
         if (stage1_only) return VS_OK;
+    }
+    if (b.lm && !flat && !exact && !d_select && nq_launch == qv.n) {
+        // a batch that shares lists: every probed list is read once for all the queries that probe it (listmajor.cu)
+        LmParams lp = b.lmp;
+        lp.rows = ix->data->view();
+        lp.ids = ix->doc_ids;
+        lp.id_base = ix->id_base;
+        lp.queries = qv;
+        lp.k = (int)k;
+        lp.pub = fused_pub((int)k, 1);
+        CU(lm_enqueue_prepare(lp, b.probe, (uint32_t)qv.n, (uint32_t)npe, (uint32_t)ix->C, ix->list_off, b.lm_count, b.lm_pair_off,
+                              b.lm_items_cap, c->stream, &c->launches));
+        {
+            // exact top k of the first 512 rows of every query's nearest list (query-major kernel, first probe only): its k-th
+            // best -- the ~2 % quantile of the query's scores -- seeds the query's running bound, so that the list-major
+            // warps keep almost nothing from their first row on (without it a warp, which sees ~128 rows of an item, keeps
+            // and sorts half of them)
+            StageParams sp{};
+            sp.queries = qv;
+            sp.nq = (int)qv.n;
+            sp.tickets = c->d_tickets;
+            sp.fix_counter = c->d_fix_counter;
+            sp.rows = ix->data->view();
+            sp.ids = ix->doc_ids;
+            sp.id_base = ix->id_base;
+            sp.seg_list = b.probe;
+            sp.seg_stride = (int)npe;
+            sp.list_off = ix->list_off;
+            sp.nseg = 1;
+            sp.seg_cap = 512;
+            sp.qtiles = b.qtiles;  // (tiles of all npe lists: an over-estimate only spreads the same work over fewer blocks)
+            sp.iters = b.iters2;
+            sp.partial = b.partial2;
+            sp.mode = 0;
+            sp.k = (int)k;
+            sp.out_ids = b.lm_seed_ids;
+            sp.out_sims = b.lm_seed_sims;
+            sp.out_counts = b.lm_seed_counts;
+            sp.out_status = b.lm_seed_status;
+            sp.status_bit = kStatusListAmbiguous;
+            sp.status_init = 1;
+            LAUNCH(c, launch_stage(sp, kpl2, false, b.grid, c->stream));
+            CU(lm_enqueue_seed(lp, b.lm_seed_sims, b.lm_seed_counts, (uint32_t)qv.n, c->stream, &c->launches));
+        }
+        VS(prof_mark(c));
+        CU(lm_enqueue_scan(lp, g_sm_count, c->stream, &c->launches));
+        VS(prof_mark(c));
+        CU(lm_enqueue_final(lp, (uint32_t)qv.n, d_ids, d_sims, d_counts, d_status, c->d_fix_counter, c->stream, &c->launches));
+        return VS_OK;
     }
     p.rows = ix->data->view();
     p.ids = ix->doc_ids;
@@ -1460,7 +1538,7 @@ static int search_enqueue(vs_ctx *c, const vs_index *ix, const MatView &qv, size
 }
 
 struct SearchSetup {
-    size_t npe;
+    size_t npe, k;
     bool flat;
     int kpl1, kpl2;
     SearchBufs b;
@@ -1482,7 +1560,9 @@ static int search_setup(vs_ctx *c, Arena &a, const vs_index *ix, size_t nq, size
     VS(search_plan(ix, nq, s->npe, s->flat, &s->b));
     VS(a.reserve(a.off + extra_bytes + search_bytes(nq, s->npe, s->kpl1, s->kpl2, s->b.grid, ix->data->d, ix->C) +
                  (use_probe_gemm(ix, nq, s->npe, s->flat) ? probe_gemm_bytes(ix, nq, s->npe)
-                  : use_probe_batch(ix, nq, s->npe, s->flat) ? probe_batch_bytes(nq, ix->C, s->npe) : 0)));
+                  : use_probe_batch(ix, nq, s->npe, s->flat) ? probe_batch_bytes(nq, ix->C, s->npe) : 0) +
+                 (lm_eligible(ix, nq, s->npe, k, s->flat) ? lm_bytes(ix, nq, s->npe) : 0)));
+    s->k = k;
     return VS_OK;
 }
 
@@ -1494,6 +1574,27 @@ static void search_take(Arena &a, const vs_index *ix, size_t nq, SearchSetup *s)
     s->b.tickets = a.take<unsigned int>(nq);
     s->b.qnorm = a.take<double>(nq * (size_t)ix->data->d);
     s->b.q_select = a.take<uint32_t>(nq);
+    s->b.lm = lm_eligible(ix, nq, s->npe, s->k, s->flat);
+    if (s->b.lm) {
+        LmParams &lp = s->b.lmp;
+        lp = LmParams{};
+        s->b.lm_count = a.take<uint32_t>(ix->C);
+        s->b.lm_pair_off = a.take<uint32_t>(ix->C);
+        s->b.lm_items_cap = (uint32_t)lm_items_cap(ix->n, nq, s->npe);
+        lp.items = a.take<LmItem>(s->b.lm_items_cap);
+        lp.pairs = a.take<uint32_t>(nq * s->npe);
+        lp.sides = a.take<SideConst>(nq);
+        lp.gthr = a.take<uint32_t>(nq);
+        lp.gcnt = a.take<unsigned int>(nq);
+        lp.gbuf = a.take<uint4>(nq * (size_t)kLmGbufCap);
+        lp.nitems = a.take<uint32_t>(2);
+        lp.next_item = a.take<unsigned int>(2);
+        lp.gcap = kLmGbufCap;
+        s->b.lm_seed_ids = a.take<uint64_t>(nq * 32);
+        s->b.lm_seed_sims = a.take<float>(nq * 32);
+        s->b.lm_seed_counts = a.take<int32_t>(nq);
+        s->b.lm_seed_status = a.take<uint32_t>(nq);
+    }
     s->b.fused_keys = a.take<uint32_t>(ix->C + 4);
     s->b.fused_seginfo = a.take<uint4>(ix->C);
     s->b.probe_keys = nullptr;

@@ -84,6 +84,7 @@ struct StageParams {
     const uint64_t *list_off;     // CSR offsets when seg_list != null
     int nseg;
     uint64_t single_start, single_count;
+    uint32_t seg_cap;             // when non-zero: at most this many rows of every segment are scanned (a sample)
     // work decomposition: tiles per query (stage 2: written by stage 1) or a uniform count
     const uint32_t *qtiles;       // [total queries] indexed like the outputs, or null
     uint32_t uniform_tiles;       // used when qtiles == null
@@ -159,6 +160,43 @@ bool fused_supported(int d_pad, int kpl);
 int fused_pub(int k, int kpl);
 cudaError_t launch_fused_search(const FusedParams &p, int kpl, int grid, cudaStream_t st);
 cudaError_t fused_set_certify_scale(float scale);
+
+// listmajor.cu: the list stage of a query batch with every probed list read once for all the queries that probe it
+struct LmItem {
+    uint32_t row0;      // first store row
+    uint32_t nrows;     // <= 1024 (a longer list is cut into several items)
+    uint32_t pair_off;  // the item's queries: pairs[pair_off .. pair_off + m)
+    uint32_t m;
+};
+struct LmParams {
+    MatView rows;              // the store (rows grouped by list)
+    const uint64_t *ids;       // per-row document id, or null -> id_base + row
+    uint64_t id_base;
+    MatView queries;           // the batch
+    SideConst *sides;          // [nq] query side of the score identity
+    uint32_t *pairs;           // [nq * npe] queries grouped by list
+    LmItem *items;
+    uint32_t *nitems;          // device word
+    unsigned int *next_item;   // device word: work queue cursor
+    uint32_t *gthr;            // [nq] running lower bound of the query's k-th best distinct document (score key)
+    unsigned int *gcnt;        // [nq] candidates appended
+    uint4 *gbuf;               // [nq][gcap] candidates (key, meta, id lo, id hi)
+    int gcap;
+    int k, pub;
+    int stage_bytes;           // ring geometry (filled by the launcher)
+};
+constexpr int kLmGbufCap = 4096;   // candidates per query the list-major scan may append (more: the literal path)
+bool lm_supported(int d_pad, int k);
+size_t lm_items_cap(size_t n_rows, size_t nq, size_t npe);
+cudaError_t lm_enqueue_prepare(const LmParams &p, const uint32_t *probe, uint32_t nq, uint32_t npe, uint32_t C,
+                               const uint64_t *list_off, uint32_t *count, uint32_t *pair_off, uint32_t items_cap, cudaStream_t st,
+                               uint64_t *launches);
+cudaError_t lm_enqueue_seed(const LmParams &p, const float *first_list_sims, const int32_t *first_list_counts, uint32_t nq,
+                            cudaStream_t st, uint64_t *launches);
+cudaError_t lm_enqueue_scan(const LmParams &p, int sm_count, cudaStream_t st, uint64_t *launches);
+cudaError_t lm_enqueue_final(const LmParams &p, uint32_t nq, uint64_t *out_ids, float *out_sims, int32_t *out_counts,
+                             uint32_t *out_status, unsigned long long *fix_counter, cudaStream_t st, uint64_t *launches);
+cudaError_t lm_set_certify_scale(float scale);
 
 // gemm.cu: query batches as a tcgen05 int8 GEMM with a fused filter (BASELINE config 3)
 struct GemmPlan {

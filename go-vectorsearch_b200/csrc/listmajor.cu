@@ -1,0 +1,576 @@
+// listmajor.cu -- the posting-list scan of a query BATCH, list-major: every probed list is read from HBM once and
+// scored against all the queries of the batch that probe it.
+//
+// Replaces, for a batch: server/search.go:241-273 (posting-list scan, running sort, one hit per document, truncate)
+// with compute/cosine.go:13-57 inside.  The reference runs one search per goroutine and reads the probed lists of every
+// query separately (search.go:241-243); scan.cu's query-major kernel does the same on the device, and at 256 queries x
+// 32 probes over 4096 lists ~57 % of its HBM traffic is lists read again for another query (8192 (query, list) pairs hit
+// ~3540 distinct lists).  Here
+//
+//   1. the (query, list) pairs are inverted on the device into ITEMS: (list, up to 1024 of its rows, the queries that
+//      probe it) -- lm_count / lm_items / lm_fill;
+//   2. persistent blocks (one per SM) claim items in order.  An item's rows stream through a shared-memory ring of
+//      16-row stages filled by bulk copies (cp.async.bulk, completion on an mbarrier).  With m queries on the item the
+//      16 warps form r = 16 / m phase groups of m warps: the group of phase p takes the chunks p, p + r, p + 2r, ... and
+//      owns its share of the ring stages; inside a group warp j scores the staged rows against query j (its codes live
+//      in the warp's registers), so a row is read from HBM once and from shared memory m times.  The last warp of a
+//      group to drain a stage re-arms it with the group's next chunk (no producer warp);
+//   3. a warp keeps the rows that reach its threshold in its own candidate buffer (the same scheme as fused.cu); the
+//      threshold starts at the query's RUNNING k-th best -- a per-query word in global memory raised (atomicMax) by every
+//      warp that has found k distinct documents -- so after a query's first items almost nothing is kept;
+//   4. what a warp kept is appended to the query's candidate list in global memory; lm_final picks the best k distinct
+//      documents per query (threshold from group maxima, counting rank), emits them and raises the status bits.
+//
+// Exactness: thresholds only ever drop rows whose score is below a proven lower bound of the query's k-th best distinct
+// document, so the emitted top k is the one the query-major path returns; scores are the certified integer-identity
+// scores of common.cuh, and a query with an uncertified score inside its top k (or whose candidate list overflowed) gets
+// the status bit that sends it to the caller's literal-arithmetic path, as everywhere else.
+#include <cstdlib>
+
+#include "internal.h"
+#include "ring.cuh"
+#include "topk.cuh"
+
+namespace vs {
+
+namespace {
+
+constexpr int kLmWarps = 16;
+constexpr int kLmThreads = 32 * kLmWarps;
+constexpr int kLmStages = 16;
+constexpr int kLmSubRows = 1024;   // rows per item (a longer list is cut: more, evener work items)
+constexpr int kLmCap = 32;         // distinct documents a warp's buffer is cut to (k <= 32 on this path)
+constexpr int kLmWB = kLmCap + 32; // candidates a warp can hold
+
+// ---- 1. inversion of the probe lists -------------------------------------------------------------------------------
+__global__ void lm_count_kernel(const uint32_t *__restrict__ probe, uint32_t npairs, uint32_t *__restrict__ count) {
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < npairs) atomicAdd(&count[probe[i]], 1u);
+}
+
+// One block: per list with at least one query, its items (<= kLmSubRows rows each) and the offset of its query list.
+__global__ void __launch_bounds__(1024) lm_items_kernel(const uint32_t *__restrict__ count, const uint64_t *__restrict__ list_off,
+                                                       uint32_t C, uint32_t *__restrict__ pair_off, LmItem *__restrict__ items,
+                                                       uint32_t *__restrict__ nitems, uint32_t items_cap) {
+    __shared__ uint32_t s_items[64], s_pairs[64];
+    const uint32_t per = (C + 1023u) / 1024u;
+    const uint32_t lo = threadIdx.x * per, hi = min(C, lo + per);
+    uint32_t my_items = 0, my_pairs = 0;
+    for (uint32_t L = lo; L < hi; L++) {
+        const uint32_t c = count[L];
+        if (c) {
+            const uint64_t len = list_off[L + 1] - list_off[L];
+            my_items += (uint32_t)((len + kLmSubRows - 1) / kLmSubRows);
+            my_pairs += c;
+        }
+    }
+    // exclusive scans over the 1024 threads: shuffles inside a warp, the 32 warp totals by warp 0
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    uint32_t vi = my_items, vp = my_pairs;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        const uint32_t a = __shfl_up_sync(FULL, vi, o), b = __shfl_up_sync(FULL, vp, o);
+        if (lane >= o) {
+            vi += a;
+            vp += b;
+        }
+    }
+    if (lane == 31) {
+        s_items[warp] = vi;
+        s_pairs[warp] = vp;
+    }
+    __syncthreads();
+    if (warp == 0) {
+        uint32_t wi = s_items[lane], wp = s_pairs[lane];
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            const uint32_t a = __shfl_up_sync(FULL, wi, o), b = __shfl_up_sync(FULL, wp, o);
+            if (lane >= o) {
+                wi += a;
+                wp += b;
+            }
+        }
+        s_items[32 + lane] = wi;  // inclusive totals of warps 0..lane
+        s_pairs[32 + lane] = wp;
+    }
+    __syncthreads();
+    uint32_t it = vi - my_items + (warp ? s_items[32 + warp - 1] : 0u), pr = vp - my_pairs + (warp ? s_pairs[32 + warp - 1] : 0u);
+    for (uint32_t L = lo; L < hi; L++) {
+        const uint32_t c = count[L];
+        pair_off[L] = pr;
+        if (c) {
+            const uint64_t st = list_off[L], len = list_off[L + 1] - st;
+            for (uint64_t o = 0; o < len; o += kLmSubRows) {
+                if (it < items_cap) items[it] = LmItem{(uint32_t)(st + o), (uint32_t)min((uint64_t)kLmSubRows, len - o), pr, c};
+                it++;
+            }
+            pr += c;
+        }
+    }
+    if (threadIdx.x == 1023) *nitems = min(s_items[32 + 31], items_cap);
+}
+
+// count[L] is consumed as a cursor (filled from the end): pairs[pair_off[L] + ...] = query
+__global__ void lm_fill_kernel(const uint32_t *__restrict__ probe, uint32_t npairs, uint32_t npe, uint32_t *__restrict__ count,
+                               const uint32_t *__restrict__ pair_off, uint32_t *__restrict__ pairs) {
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= npairs) return;
+    const uint32_t L = probe[i];
+    const uint32_t pos = atomicSub(&count[L], 1u) - 1u;
+    pairs[pair_off[L] + pos] = i / npe;
+}
+
+// The running bound of every query starts at the k-th best of its NEAREST list (an exact top k from the query-major
+// kernel, ~1/npe of the rows): a lower bound of the k-th best over all its lists, one float32 step lower to be safe
+// against an uncertified last digit.  Fewer than k documents there: no bound.
+__global__ void lm_seed_kernel(const float *__restrict__ sims, const int32_t *__restrict__ counts, uint32_t nq, int k,
+                               uint32_t *__restrict__ gthr) {
+    const uint32_t q = blockIdx.x * blockDim.x + threadIdx.x;
+    if (q >= nq) return;
+    uint32_t t = 0;
+    if (counts[q] >= k) {
+        const uint32_t key = f32_to_key(sims[(size_t)q * k + k - 1]);
+        t = key > 2u ? key - 1u : 0u;
+    }
+    gthr[q] = t;
+}
+
+// The query side of the score identity, once per query and step (compute/cosine.go:26,138-149 folded into integers).
+__global__ void lm_side_kernel(MatView queries, SideConst *__restrict__ sides) {
+    const uint32_t q = blockIdx.x * blockDim.x + threadIdx.x;
+    if (q >= queries.n) return;
+    const float2 h = queries.hdr[q];
+    const uint2 s = queries.sums[q];
+    sides[q] = make_side(h.x, h.y, s.x, s.y, queries.d);
+}
+
+struct LmCtl {
+    uint64_t full[kLmStages];
+    unsigned int done[kLmStages];   // warps of the owning group that have drained the stage
+    unsigned int base[kLmStages];   // completed phases of the stage's barrier before the current pass
+    unsigned int item, next_item;
+};
+
+}  // namespace
+
+// ---- 2./3. the scan ------------------------------------------------------------------------------------------------
+template <int G, int CPL, int TR>
+__global__ void __launch_bounds__(kLmThreads, 1)
+lm_scan_kernel(const LmParams p) {
+    extern __shared__ __align__(128) unsigned char lsm[];
+    constexpr int NG = 32 / G;
+    constexpr int CAP = kLmCap, WB = kLmWB;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int D = p.rows.d, d_pad = p.rows.d_pad;
+    const uint32_t stage_bytes = (uint32_t)p.stage_bytes;
+    unsigned char *ring = lsm;
+    uint64_t *cand_id = reinterpret_cast<uint64_t *>(lsm + (size_t)kLmStages * stage_bytes);
+    uint32_t *cand_key = reinterpret_cast<uint32_t *>(cand_id + kLmWarps * WB);
+    uint32_t *cand_meta = cand_key + kLmWarps * WB;
+    LmCtl &ctl = *reinterpret_cast<LmCtl *>(cand_meta + kLmWarps * WB);
+    const bool dedup = p.ids != nullptr;
+    const uint32_t nitems = *p.nitems;
+
+    if (threadIdx.x == 0) {
+        for (int i = 0; i < kLmStages; i++) {
+            mbar_init(smem_u32(&ctl.full[i]), 1);
+            ctl.done[i] = 0;
+            ctl.base[i] = 0;
+        }
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        ctl.item = atomicAdd(p.next_item, 1u);
+    }
+    __syncthreads();
+    uint64_t *wid = cand_id + warp * WB;
+    uint32_t *wkey = cand_key + warp * WB, *wmeta = cand_meta + warp * WB;
+
+    for (;;) {
+        const uint32_t item = ctl.item;
+        if (item >= nitems) break;
+        const LmItem it = p.items[item];
+        if (threadIdx.x == 0) ctl.next_item = atomicAdd(p.next_item, 1u);  // (its latency hides behind this item)
+        const uint32_t nchunks = (it.nrows + TR - 1) / TR;
+        for (uint32_t pass0 = 0; pass0 < it.m; pass0 += kLmWarps) {
+            const int m = (int)min((uint32_t)kLmWarps, it.m - pass0);  // queries scored in this pass, one warp each per phase
+            const int r = kLmWarps / m;                                 // phase groups
+            const int depth = kLmStages / r;                            // ring stages a group owns
+            const int j = warp % m, ph = warp / m;
+            const bool active = ph < r;
+            // ---- this warp's query ----
+            uint4 qreg[CPL];
+            SideConst xq;
+            uint32_t q = 0, thr_w = 0;
+            int cnt_w = 0;
+            if (active) {
+                q = p.pairs[it.pair_off + pass0 + j];
+                const uint8_t *qc = p.queries.codes + (size_t)q * d_pad;
+#pragma unroll
+                for (int t = 0; t < CPL; t++) qreg[t] = *reinterpret_cast<const uint4 *>(qc + ((lane % G) + G * t) * 16);
+                xq = p.sides[q];
+                thr_w = __ldcg(p.gthr + q);
+            }
+            // chunk i of my group: rows [c * TR, ...) of the item with c = ph + i * r, in stage ph * depth + i % depth
+            struct Pending {
+                uint32_t nr;
+                float2 h;
+                uint2 sums;
+                uint64_t id;
+            };
+            auto arm = [&](uint32_t c, uint32_t st) {  // (one lane)
+                const uint32_t nr = min((uint32_t)TR, it.nrows - c * TR);
+                const uint32_t full = smem_u32(&ctl.full[st]);
+                const uint32_t cb = nr * (uint32_t)d_pad;
+                mbar_expect_tx(full, cb);
+                bulk_g2s(smem_u32(ring + (size_t)st * stage_bytes), p.rows.codes + (uint64_t)(it.row0 + c * TR) * d_pad, cb, full);
+            };
+            auto side = [&](uint32_t c, Pending &pd) {  // per lane: the side data of the row it will finish in chunk c
+                pd.nr = min((uint32_t)TR, it.nrows - c * TR);
+                const int iters = ((int)pd.nr + NG - 1) / NG;
+                const int myr = (lane / G) * iters + (lane % G);
+                pd.h = make_float2(0.f, 0.f);
+                pd.sums = make_uint2(0, 0);
+                pd.id = kEmptyId;
+                if ((lane % G) < iters && myr < (int)pd.nr) {
+                    const uint32_t row = it.row0 + c * TR + (uint32_t)myr;
+                    pd.h = p.rows.hdr[row];
+                    pd.sums = p.rows.sums[row];
+                    pd.id = p.ids ? p.ids[row] : p.id_base + row;
+                }
+            };
+            if (active) {
+                if (j == 0 && lane == 0) {  // the group's first warp arms the group's stages
+                    for (int i = 0; i < depth; i++) {
+                        const uint32_t c = (uint32_t)ph + (uint32_t)i * r;
+                        if (c < nchunks) arm(c, (uint32_t)(ph * depth + i));
+                    }
+                }
+                Pending cur;
+                if ((uint32_t)ph < nchunks) side((uint32_t)ph, cur);
+                for (uint32_t i = 0, c = (uint32_t)ph; c < nchunks; i++, c += r) {
+                    const uint32_t st = (uint32_t)(ph * depth) + i % (uint32_t)depth;
+                    mbar_wait(smem_u32(&ctl.full[st]), (ctl.base[st] + i / (uint32_t)depth) & 1u);
+                    const int iters = ((int)cur.nr + NG - 1) / NG;
+                    const uint32_t mydot = stage_dots<G, CPL>(smem_u32(ring + (size_t)st * stage_bytes), (int)cur.nr, d_pad, qreg, lane, iters);
+                    const int myr = (lane / G) * iters + (lane % G);
+                    const bool valid = (lane % G) < iters && myr < (int)cur.nr;
+                    __syncwarp();
+                    // the last warp of the group to drain the stage re-arms it with the group's chunk `depth` turns ahead
+                    if (lane == 0) {
+                        const unsigned int old = atomicAdd(&ctl.done[st], 1u);
+                        if (old == (unsigned)m - 1u) {
+                            ctl.done[st] = 0;
+                            const uint32_t cn = c + (uint32_t)r * depth;
+                            if (cn < nchunks) arm(cn, st);
+                        }
+                    }
+                    const Pending now = cur;
+                    if (c + r < nchunks) side(c + r, cur);  // next chunk's side data in flight during the scoring
+                    uint32_t key = 0, meta = 0;
+                    if (valid) {
+                        bool flag;
+                        const float sim = score_fast(xq, now.h.x, now.h.y, now.sums.x, now.sums.y, mydot, D, &flag);
+                        key = f32_to_key(sim);
+                        meta = (it.row0 + c * TR + (uint32_t)myr) | (flag ? kFlagBit : 0u);
+                    }
+                    unsigned mk = __ballot_sync(FULL, valid && key >= thr_w);
+                    if (cnt_w + __popc(mk) > WB) {
+                        // cut the buffer to its best CAP distinct documents; the CAP-th becomes the threshold
+                        WarpTopK<1> top;
+                        top.init();
+                        for (int base = 0; base < cnt_w; base += 32) {
+                            const int e = base + lane;
+                            const bool have = e < cnt_w;
+                            top.offer(have, have ? wkey[e] : 0u, have ? wmeta[e] : 0u, have ? wid[e] : kEmptyId, lane, dedup);
+                        }
+                        __syncwarp();
+                        wkey[lane] = top.skey[0];
+                        wmeta[lane] = top.meta[0];
+                        wid[lane] = top.id[0];
+                        cnt_w = top.count();
+                        thr_w = max(thr_w, top.thr_key);
+                        __syncwarp();
+                        mk = __ballot_sync(FULL, valid && key >= thr_w);
+                    }
+                    if (mk & (1u << lane)) {
+                        const int slot = cnt_w + __popc(mk & ((1u << lane) - 1u));
+                        wkey[slot] = key;
+                        wmeta[slot] = meta;
+                        wid[slot] = now.id;
+                    }
+                    cnt_w += __popc(mk);
+                }
+                // ---- what this warp kept goes to the query's candidate list; k distinct documents raise its running bound ----
+                __syncwarp();
+                if (cnt_w >= p.k) {
+                    WarpTopK<1> top;
+                    top.init();
+                    for (int base = 0; base < cnt_w; base += 32) {
+                        const int e = base + lane;
+                        const bool have = e < cnt_w;
+                        top.offer(have, have ? wkey[e] : 0u, have ? wmeta[e] : 0u, have ? wid[e] : kEmptyId, lane, dedup);
+                    }
+                    __syncwarp();
+                    wkey[lane] = top.skey[0];
+                    wmeta[lane] = top.meta[0];
+                    wid[lane] = top.id[0];
+                    const int have = top.count();
+                    cnt_w = min(have, p.pub);  // the best k distinct documents of a union are among the best k of every part
+                    if (have >= p.k) {
+                        const uint32_t kth = __shfl_sync(FULL, top.skey[0], p.k - 1);
+                        if (lane == 0) atomicMax(p.gthr + q, kth);
+                    }
+                    __syncwarp();
+                }
+                if (cnt_w > 0) {
+                    unsigned int at = 0;
+                    if (lane == 0) at = atomicAdd(p.gcnt + q, (unsigned)cnt_w);
+                    at = __shfl_sync(FULL, at, 0);
+                    for (int e = lane; e < cnt_w; e += 32) {
+                        if (at + e < (unsigned)p.gcap) {
+                            uint4 v;
+                            v.x = wkey[e];
+                            v.y = wmeta[e];
+                            v.z = (uint32_t)wid[e];
+                            v.w = (uint32_t)(wid[e] >> 32);
+                            p.gbuf[(size_t)q * p.gcap + at + e] = v;
+                        }
+                    }
+                }
+            }
+            __syncthreads();  // every armed chunk has been drained by its whole group: the ring is idle
+            if (threadIdx.x < kLmStages) {  // completed barrier phases of every stage, for the next pass / item
+                const int st = (int)threadIdx.x, g = st / depth, d = st % depth;
+                unsigned int uses = 0;
+                if (g < r && (uint32_t)g < nchunks) {
+                    const uint32_t n_g = (nchunks - (uint32_t)g + (uint32_t)r - 1u) / (uint32_t)r;  // chunks of group g
+                    if ((uint32_t)d < n_g) uses = (n_g - (uint32_t)d + (uint32_t)depth - 1u) / (uint32_t)depth;
+                }
+                ctl.base[st] += uses;
+            }
+            __syncthreads();
+        }
+        if (threadIdx.x == 0) ctl.item = ctl.next_item;
+        __syncthreads();
+    }
+}
+
+// ---- 4. per query: best k distinct documents of its candidate list ----------------------------------------------------
+constexpr int kLmFinalThreads = 256;
+constexpr int kLmFinalSurv = 256;  // survivors of the threshold cut that are ranked (more: the caller's literal path)
+
+__global__ void __launch_bounds__(kLmFinalThreads)
+lm_final_kernel(const uint4 *__restrict__ gbuf, const unsigned int *__restrict__ gcnt, uint32_t gcap, int k, bool dedup, MatView rows,
+                MatView queries, uint64_t *__restrict__ out_ids, float *__restrict__ out_sims, int32_t *__restrict__ out_counts,
+                uint32_t *__restrict__ out_status, unsigned long long *fix_counter) {
+    extern __shared__ __align__(16) unsigned char lf_raw[];
+    double *sh_qn = reinterpret_cast<double *>(lf_raw);  // [d] normalized query (literal re-score only)
+    __shared__ uint32_t s_gmax[kLmFinalThreads];
+    __shared__ uint32_t s_thr;
+    __shared__ unsigned int s_cnt, s_fix, s_bad;
+    __shared__ double s_norm;
+    __shared__ uint64_t a_id[kLmFinalSurv], b_id[kLmFinalSurv];
+    __shared__ uint32_t a_key[kLmFinalSurv], a_meta[kLmFinalSurv], b_key[kLmFinalSurv], b_meta[kLmFinalSurv];
+    const uint32_t q = blockIdx.x;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const unsigned int total = gcnt[q];
+    const uint32_t n = min(total, gcap);
+    const uint4 *src = gbuf + (size_t)q * gcap;
+    uint32_t status = total > gcap ? kStatusListAmbiguous : 0u;  // candidates were lost: the literal path redoes the query
+    // threshold: the k-th largest of the maxima of 64 groups of 4 threads
+    uint32_t gm = 0;
+    for (uint32_t e = threadIdx.x; e < n; e += kLmFinalThreads) gm = max(gm, __ldcg(&src[e].x));
+    gm = max(gm, __shfl_xor_sync(FULL, gm, 1));
+    gm = max(gm, __shfl_xor_sync(FULL, gm, 2));
+    const int g = (int)threadIdx.x >> 2, part = (int)threadIdx.x & 3;
+    if (threadIdx.x == 0) {
+        s_thr = 0;
+        s_cnt = 0;
+        s_fix = 0;
+        s_bad = 0;
+    }
+    if (part == 0) s_gmax[g] = gm;
+    __syncthreads();
+    {
+        const uint32_t mine = s_gmax[g];
+        int rk = 0;
+        for (int u = part; u < kLmFinalThreads / 4; u += 4) {
+            const uint32_t o = s_gmax[u];
+            rk += (int)((o > mine) | ((o == mine) & (u < g)));
+        }
+        rk += __shfl_xor_sync(FULL, rk, 1);
+        rk += __shfl_xor_sync(FULL, rk, 2);
+        if (part == 0 && rk == k - 1) s_thr = mine;
+    }
+    __syncthreads();
+    const uint32_t thr = s_thr;
+    for (uint32_t e = threadIdx.x; e < n; e += kLmFinalThreads) {
+        const uint4 v = __ldcg(src + e);
+        if (v.x != 0 && v.x >= thr) {
+            const unsigned int pos = atomicAdd(&s_cnt, 1u);
+            if (pos < (unsigned)kLmFinalSurv) {
+                a_key[pos] = v.x;
+                a_meta[pos] = v.y;
+                a_id[pos] = (uint64_t)v.z | ((uint64_t)v.w << 32);
+            }
+        }
+    }
+    __syncthreads();
+    const unsigned int ns = s_cnt;
+    if (ns > (unsigned)kLmFinalSurv) status |= kStatusListAmbiguous;
+    const int nsurv = (int)min(ns, (unsigned)kLmFinalSurv);
+    const CandBuf A{a_key, a_meta, a_id}, B{b_key, b_meta, b_id};
+    int uniq = block_rank_small(A, nsurv, B, 32, dedup);
+    // An uncertified score among the first k: every uncertified survivor is re-scored with the reference's own arithmetic
+    // (compute/cosine.go:26-50, warp_ref_cosine_row_f64) and the survivors are ranked again.  Scores only move down, by at
+    // most one float32 step; everything that was not a survivor lies below `thr`, so the new first k are exact as long as
+    // the k-th of them still reaches `thr` (otherwise: the caller's literal path).
+    {
+        bool flag = false;
+        if ((int)threadIdx.x < min(k, 32)) flag = b_key[threadIdx.x] != 0 && (b_meta[threadIdx.x] & kFlagBit);
+        if (__syncthreads_or(flag)) {
+            const int D = queries.d;
+            const uint8_t *qc = queries.codes + (size_t)q * queries.d_pad;
+            const float2 qh = queries.hdr[q];
+            const double mn = (double)qh.x, range = __dsub_rn((double)qh.y, (double)qh.x);
+            for (int i = threadIdx.x; i < D; i += kLmFinalThreads) sh_qn[i] = ref_dequant_f64(qc[i], mn, range);
+            __syncthreads();
+            if (warp == 0) {
+                const double nsq = warp_ordered_sum(D, lane, [&](int i) { return __dmul_rn(sh_qn[i], sh_qn[i]); });
+                if (lane == 0) s_norm = __dsqrt_rn(nsq);
+            }
+            __syncthreads();
+            const double norm = s_norm;
+            if (norm != 0.0)
+                for (int i = threadIdx.x; i < D; i += kLmFinalThreads) sh_qn[i] = __ddiv_rn(sh_qn[i], norm);
+            __syncthreads();
+            for (int e = warp; e < nsurv; e += kLmFinalThreads / 32) {  // one warp per uncertified survivor (A still holds them)
+                const uint32_t k0 = a_key[e], m0 = a_meta[e];
+                if (k0 != 0 && (m0 & kFlagBit)) {
+                    const size_t row = m0 & kMetaRowMask;
+                    const float2 h = rows.hdr[row];
+                    const double dot = warp_ref_cosine_row_f64(rows.codes + row * (size_t)rows.d_pad, h.x, h.y, sh_qn, D, lane);
+                    if (lane == 0) {
+                        const uint32_t k1 = f32_to_key(__double2float_rn(dot));
+                        a_key[e] = k1;
+                        a_meta[e] = m0 & kMetaRowMask;
+                        if ((m0 & kSibBit) && k1 != k0) s_bad = 1;  // an equally scored row of the same document was dropped
+                        atomicAdd(&s_fix, 1u);
+                    }
+                }
+            }
+            __syncthreads();
+            uniq = block_rank_small(A, nsurv, B, 32, dedup);
+            const uint32_t kth = (k <= 32 && uniq >= k) ? b_key[k - 1] : 0u;
+            if (s_bad || (thr != 0 && n > (uint32_t)nsurv && kth < thr)) status |= kStatusListAmbiguous;
+            if (threadIdx.x == 0 && fix_counter) atomicAdd(fix_counter, (unsigned long long)s_fix);
+        }
+    }
+    // duplicates ate the margin of the cut although candidates below the threshold were left out: not decided here
+    if (dedup && uniq < k && thr != 0 && n > (uint32_t)nsurv) status |= kStatusListAmbiguous;
+    if (threadIdx.x < 32) {
+        const int r = (int)threadIdx.x;
+        const uint32_t kk = b_key[r];
+        const bool have = kk != 0;
+        bool flag = false;
+        if (have && r < k) {
+            out_ids[(size_t)q * k + r] = b_id[r];
+            out_sims[(size_t)q * k + r] = key_to_f32(kk);
+            flag = (b_meta[r] & kFlagBit) != 0;
+        }
+        const int cnt = __popc(__ballot_sync(FULL, have));
+        if (__any_sync(FULL, flag)) status |= kStatusListAmbiguous;
+        if (r == 0) {
+            out_counts[q] = min(cnt, k);
+            out_status[q] |= status;  // (the probe stage stored its own bits)
+        }
+    }
+}
+
+// ---------------------------------------------------------------------------------------------------
+static int lm_tile_rows(int d_pad) { return d_pad <= 768 ? 16 : 8; }
+
+static bool lm_geometry(int d_pad, int *stage_bytes, size_t *smem) {
+    const int sb = (lm_tile_rows(d_pad) * d_pad + 127) & ~127;
+    *stage_bytes = sb;
+    *smem = (size_t)kLmStages * sb + (size_t)kLmWarps * kLmWB * 16 + ((sizeof(LmCtl) + 127) & ~size_t(127));
+    return *smem <= (size_t)227 * 1024;
+}
+
+bool lm_supported(int d_pad, int k) {
+    if (d_pad & 15) return false;
+    switch (d_pad >> 4) {
+        case 48: case 32: case 64: case 96: case 24: break;
+        default: return false;
+    }
+    int sb;
+    size_t smem;
+    return k >= 1 && k <= kLmCap && lm_geometry(d_pad, &sb, &smem);
+}
+
+size_t lm_items_cap(size_t n_rows, size_t nq, size_t npe) { return n_rows / kLmSubRows + nq * npe + 16; }
+
+template <int G, int CPL, int TR>
+static cudaError_t lm_launch_scan(LmParams p, int grid, cudaStream_t st) {
+    size_t smem;
+    if (!lm_geometry(p.rows.d_pad, &p.stage_bytes, &smem)) return cudaErrorInvalidValue;
+    auto kern = lm_scan_kernel<G, CPL, TR>;
+    static bool attr = false;
+    if (!attr) {
+        cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (e != cudaSuccess) return e;
+        attr = true;
+    }
+    kern<<<grid, kLmThreads, smem, st>>>(p);
+    return cudaGetLastError();
+}
+
+// The list stage of a batch, list-major, in three steps (the caller brackets the scan with its profiling marks).
+// probe: [nq][npe] list ids (already selected); the status words already hold the probe stage's bits.
+cudaError_t lm_enqueue_prepare(const LmParams &p, const uint32_t *probe, uint32_t nq, uint32_t npe, uint32_t C,
+                               const uint64_t *list_off, uint32_t *count, uint32_t *pair_off, uint32_t items_cap, cudaStream_t st,
+                               uint64_t *launches) {
+    const uint32_t npairs = nq * npe;
+    cudaError_t e;
+    if ((e = cudaMemsetAsync(count, 0, (size_t)C * 4, st)) != cudaSuccess) return e;
+    if ((e = cudaMemsetAsync(p.gcnt, 0, (size_t)nq * 4, st)) != cudaSuccess) return e;
+    if ((e = cudaMemsetAsync(p.gthr, 0, (size_t)nq * 4, st)) != cudaSuccess) return e;
+    if ((e = cudaMemsetAsync(p.next_item, 0, 4, st)) != cudaSuccess) return e;
+    lm_count_kernel<<<(npairs + 255) / 256, 256, 0, st>>>(probe, npairs, count);
+    lm_items_kernel<<<1, 1024, 0, st>>>(count, list_off, C, pair_off, p.items, p.nitems, items_cap);
+    lm_fill_kernel<<<(npairs + 255) / 256, 256, 0, st>>>(probe, npairs, npe, count, pair_off, p.pairs);
+    lm_side_kernel<<<(nq + 127) / 128, 128, 0, st>>>(p.queries, p.sides);
+    if (launches) *launches += 4;
+    return cudaGetLastError();
+}
+
+cudaError_t lm_enqueue_seed(const LmParams &p, const float *first_list_sims, const int32_t *first_list_counts, uint32_t nq,
+                            cudaStream_t st, uint64_t *launches) {
+    lm_seed_kernel<<<(nq + 127) / 128, 128, 0, st>>>(first_list_sims, first_list_counts, nq, p.k, p.gthr);
+    if (launches) *launches += 1;
+    return cudaGetLastError();
+}
+
+cudaError_t lm_enqueue_scan(const LmParams &p, int sm_count, cudaStream_t st, uint64_t *launches) {
+    if (launches) *launches += 1;
+    switch (p.rows.d_pad >> 4) {
+        case 48: return lm_launch_scan<16, 3, 16>(p, sm_count, st);  // 768-d (nomic-embed-text)
+        case 32: return lm_launch_scan<32, 1, 16>(p, sm_count, st);  // 512-d (noop/ai.go)
+        case 64: return lm_launch_scan<32, 2, 8>(p, sm_count, st);   // 1024-d
+        case 96: return lm_launch_scan<32, 3, 8>(p, sm_count, st);   // 1536-d
+        case 24: return lm_launch_scan<8, 3, 16>(p, sm_count, st);   // 384-d
+        default: return cudaErrorInvalidValue;
+    }
+}
+
+cudaError_t lm_enqueue_final(const LmParams &p, uint32_t nq, uint64_t *out_ids, float *out_sims, int32_t *out_counts,
+                             uint32_t *out_status, unsigned long long *fix_counter, cudaStream_t st, uint64_t *launches) {
+    lm_final_kernel<<<nq, kLmFinalThreads, (size_t)p.rows.d * sizeof(double), st>>>(p.gbuf, p.gcnt, (uint32_t)p.gcap, p.k, p.ids != nullptr,
+                                                                                    p.rows, p.queries, out_ids, out_sims, out_counts,
+                                                                                    out_status, fix_counter);
+    if (launches) *launches += 1;
+    return cudaGetLastError();
+}
+
+cudaError_t lm_set_certify_scale(float scale) { return cudaMemcpyToSymbol(c_certify_scale, &scale, sizeof(float)); }
+
+}  // namespace vs

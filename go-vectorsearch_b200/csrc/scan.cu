@@ -165,6 +165,7 @@ stage_kernel(const StageParams p) {
                 uint32_t L = p.seg_list[(size_t)qi * p.seg_stride + s];
                 st = p.list_off[L];
                 len = p.list_off[L + 1] - st;
+                if (p.seg_cap && len > p.seg_cap) len = p.seg_cap;
             } else {
                 st = p.single_start;
                 len = p.single_count;

@@ -69,6 +69,10 @@ VS_API int vs_debug_set_argmax_gemm_min(size_t min_centroids);
  * fused kernel (fused.cu: probe stage, grid barrier, selection, TMA-ring list scan and top-k in one cooperative
  * launch; replaces server/search.go:214-273 for one query).  Default 1. */
 VS_API int vs_debug_set_fused(int on);
+/* Test hook: 0 sends the list stage of query batches through the query-major streaming scan (scan.cu) instead of the
+ * list-major one (listmajor.cu: every probed list read once for all the queries of the batch that probe it; replaces
+ * server/search.go:241-273 for a batch).  Default 1. */
+VS_API int vs_debug_set_list_major(int on);
 /* CUDA-event timing on the ctx stream (bench.py): start/stop bracket, elapsed in ms after sync. */
 VS_API int vs_ctx_timer_start(vs_ctx *ctx);
 VS_API int vs_ctx_timer_stop(vs_ctx *ctx, float *ms_out);

@@ -1,0 +1,136 @@
+"""GPU parity of the list-major batch scan (csrc/listmajor.cu: every probed list read once for all the queries that probe
+it) against the oracle's restatement of server/search.go:202-273 and against the query-major scan."""
+import numpy as np
+import pytest
+
+from _util import f32_bits, noop_rows, unit_rows
+from test_gpu_search import _check, _crowded_inputs, _index_inputs
+
+pytestmark = pytest.mark.gpu
+
+
+def _same_as_query_major(vs, ix, qs, nprobe, k, ctx=None):
+    a = ix.Search(qs, nprobe, k, ctx=ctx)
+    vs.compute.debug_set_list_major(False)
+    try:
+        b = ix.Search(qs, nprobe, k, ctx=ctx)
+    finally:
+        vs.compute.debug_set_list_major(True)
+    assert (a[2] == b[2]).all()
+    assert (a[0] == b[0]).all()
+    assert (f32_bits(a[1]) == f32_bits(b[1])).all()
+    return a
+
+
+def test_list_major_path_is_taken(vs, oracle):
+    n, d, C = 20000, 768, 64
+    rows, cent, lists, doc = _index_inputs(oracle, n, d, C, 5)
+    ctx = vs.compute.Context()
+    ix = vs.ivf.Index.build_assigned(rows, doc, lists, cent, ctx=ctx)
+    qs = oracle.quantize_matrix_f32(unit_rows(32, d, 9))
+    ix.Search(qs, 8, 10, ctx=ctx)
+    l0 = ctx.launch_count()
+    ix.Search(qs, 8, 10, ctx=ctx)
+    lm = ctx.launch_count() - l0
+    vs.compute.debug_set_list_major(False)
+    try:
+        l0 = ctx.launch_count()
+        ix.Search(qs, 8, 10, ctx=ctx)
+        qm = ctx.launch_count() - l0
+    finally:
+        vs.compute.debug_set_list_major(True)
+    assert lm != qm       # (the list-major pipeline has its inversion and final kernels)
+    ctx.close()
+
+
+@pytest.mark.parametrize("d,C,nq,nprobe,k", [(768, 96, 40, 8, 10), (768, 96, 64, 32, 20), (512, 300, 200, 6, 10), (384, 40, 17, 39, 32),
+                                             (1024, 24, 48, 3, 10), (1536, 16, 32, 5, 7)])
+def test_list_major_parity(vs, oracle, d, C, nq, nprobe, k):
+    n = 30000 if d == 768 else 9000
+    rows, cent, lists, doc = _index_inputs(oracle, n, d, C, 50 + C, docs_per=2)
+    ix = vs.ivf.Index.build_assigned(rows, doc, lists, cent)
+    qs = oracle.quantize_matrix_f32(unit_rows(nq, d, 99))
+    _same_as_query_major(vs, ix, qs, nprobe, k)
+    sel = np.arange(0, nq, max(1, nq // 12))
+    ids, sims, counts = ix.Search(qs, nprobe, k)
+    for i in sel:
+        want_ids, want_sims = oracle.search(qs[i], cent, rows, lists, doc, nprobe, k)
+        c = counts[i]
+        assert c == len(want_ids)
+        assert ids[i, :c].tolist() == want_ids.tolist(), f"query {i}"
+        assert (f32_bits(sims[i, :c]) == f32_bits(want_sims)).all(), f"query {i}"
+
+
+def test_list_major_many_queries_per_list(vs, oracle):
+    """More queries on a list than a block has warps (several passes over the item), long lists cut into sub-items."""
+    n, d, C = 24000, 768, 6
+    rows, cent, lists, doc = _index_inputs(oracle, n, d, C, 77)
+    ix = vs.ivf.Index.build_assigned(rows, doc, lists, cent)
+    qs = oracle.quantize_matrix_f32(unit_rows(50, d, 3))
+    ids, sims, counts = _same_as_query_major(vs, ix, qs, 4, 10)
+    for i in (0, 13, 49):
+        want_ids, want_sims = oracle.search(qs[i], cent, rows, lists, doc, 4, 10)
+        assert ids[i, :counts[i]].tolist() == want_ids.tolist()
+        assert (f32_bits(sims[i, :counts[i]]) == f32_bits(want_sims)).all()
+
+
+def test_list_major_ragged_empty_ties_and_zero_vectors(vs, oracle):
+    d, C = 768, 10
+    rows = oracle.quantize_matrix_f32(unit_rows(3000, d, 2))
+    rows[100:140] = rows[100]
+    rows[200:204, 8:] = 0
+    cent = oracle.quantize_matrix_f32(unit_rows(C, d, 3))
+    sizes = [0, 1, 31, 32, 33, 0, 1500, 7, 1396, 0]
+    lists = np.repeat(np.arange(C), sizes).astype(np.uint32)
+    doc = np.random.default_rng(0).permutation(3000).astype(np.uint64)
+    offs = np.concatenate([[0], np.cumsum(sizes)]).astype(np.uint64)
+    ix = vs.ivf.Index.build(rows, doc, offs, cent)
+    q = unit_rows(20, d, 5)
+    q[3] = 0
+    qs = oracle.quantize_matrix_f32(q)
+    qs[4] = rows[100]
+    for nprobe, k in ((3, 10), (9, 25), (1, 5)):
+        _check(oracle, ix, qs, cent, rows, lists, doc, nprobe, k)
+
+
+@pytest.mark.parametrize("k,crowd,ndocs", [(10, 40, 1), (32, 300, 3)])
+def test_list_major_document_crowding(vs, oracle, k, crowd, ndocs):
+    n, d, C = 12000, 384, 12
+    rows, cent, lists, doc, q = _crowded_inputs(oracle, n, d, C, 300 + k, crowd, ndocs)
+    ix = vs.ivf.Index.build_assigned(rows, doc, lists, cent)
+    qs = np.concatenate([q[None, :], oracle.quantize_matrix_f32(unit_rows(19, d, 5))])
+    _check(oracle, ix, qs, cent, rows, lists, doc, 5, k)
+
+
+def test_list_major_uncertified_scores_go_to_the_literal_path(vs, oracle):
+    n, d, C = 6000, 768, 24
+    rows, cent, lists, doc = _index_inputs(oracle, n, d, C, 15, docs_per=2)
+    ctx = vs.compute.Context()
+    ix = vs.ivf.Index.build_assigned(rows, doc, lists, cent, ctx=ctx)
+    qs = oracle.quantize_matrix_f32(unit_rows(16, d, 77))
+    vs.compute.debug_set_certify_scale(1.0e7)
+    try:
+        ids, sims, counts = ix.Search(qs, 5, 12, ctx=ctx)
+    finally:
+        vs.compute.debug_set_certify_scale(1.0)
+    assert ctx.slowpath_count() > 0
+    for i in (0, 7, 15):
+        want_ids, want_sims = oracle.search(qs[i], cent, rows, lists, doc, 5, 12)
+        assert ids[i, :counts[i]].tolist() == want_ids.tolist()
+        assert (f32_bits(sims[i, :counts[i]]) == f32_bits(want_sims)).all()
+    ctx.close()
+
+
+def test_list_major_large_batch_equals_query_major(vs):
+    """256 queries x 16 probes over 512 lists of noop rows (no oracle at this size): same hits as the query-major scan,
+    three times in a row on one context (work queue, running bounds and candidate lists are re-armed every call)."""
+    n, d, C = 200000, 768, 512
+    rows = noop_rows(n, d, 3)
+    lists = (np.arange(n) * 2654435761 % C).astype(np.uint32)
+    ctx = vs.compute.Context()
+    ix = vs.ivf.Index.build_assigned(rows, None, lists, rows[:C], ctx=ctx)
+    for rep in range(3):
+        qs = noop_rows(256, d, 40 + rep)
+        ids, sims, counts = _same_as_query_major(vs, ix, qs, 16, 10, ctx=ctx)
+        assert (counts == 10).all()
+    ctx.close()
