@@ -10,7 +10,7 @@
 //   1. the (query, list) pairs are inverted on the device into ITEMS: (list, up to 1024 of its rows, the queries that
 //      probe it) -- lm_count / lm_items / lm_fill;
 //   2. persistent blocks (one per SM) claim items in order.  An item's rows stream through a shared-memory ring of
-//      16-row stages filled by bulk copies (cp.async.bulk, completion on an mbarrier).  With m queries on the item the
+//      32-row stages filled by bulk copies (cp.async.bulk, completion on an mbarrier).  With m queries on the item the
 //      16 warps form r = 16 / m phase groups of m warps: the group of phase p takes the chunks p, p + r, p + 2r, ... and
 //      owns its share of the ring stages; inside a group warp j scores the staged rows against query j (its codes live
 //      in the warp's registers), so a row is read from HBM once and from shared memory m times.  The last warp of a
@@ -37,7 +37,7 @@ namespace {
 
 constexpr int kLmWarps = 16;
 constexpr int kLmThreads = 32 * kLmWarps;
-constexpr int kLmStages = 16;
+constexpr int kLmStages = 8;        // ring stages of 32 rows (all 32 lanes finish a row's score; 16-row stages leave half idle)
 constexpr int kLmSubRows = 1024;   // rows per item (a longer list is cut: more, evener work items)
 constexpr int kLmCap = 32;         // distinct documents a warp's buffer is cut to (k <= 32 on this path)
 constexpr int kLmWB = kLmCap + 32; // candidates a warp can hold
@@ -192,7 +192,7 @@ lm_scan_kernel(const LmParams p) {
         const uint32_t nchunks = (it.nrows + TR - 1) / TR;
         for (uint32_t pass0 = 0; pass0 < it.m; pass0 += kLmWarps) {
             const int m = (int)min((uint32_t)kLmWarps, it.m - pass0);  // queries scored in this pass, one warp each per phase
-            const int r = kLmWarps / m;                                 // phase groups
+            const int r = min(kLmWarps / m, kLmStages);                 // phase groups (one query: 8 warps stream, 8 rest)
             const int depth = kLmStages / r;                            // ring stages a group owns
             const int j = warp % m, ph = warp / m;
             const bool active = ph < r;
@@ -246,9 +246,14 @@ lm_scan_kernel(const LmParams p) {
                 }
                 Pending cur;
                 if ((uint32_t)ph < nchunks) side((uint32_t)ph, cur);
-                for (uint32_t i = 0, c = (uint32_t)ph; c < nchunks; i++, c += r) {
-                    const uint32_t st = (uint32_t)(ph * depth) + i % (uint32_t)depth;
-                    mbar_wait(smem_u32(&ctl.full[st]), (ctl.base[st] + i / (uint32_t)depth) & 1u);
+                uint32_t slot = 0, turn = 0;  // chunk i of the group sits in stage ph * depth + i % depth, on ring turn i / depth
+                for (uint32_t c = (uint32_t)ph; c < nchunks; c += r) {
+                    const uint32_t st = (uint32_t)(ph * depth) + slot;
+                    mbar_wait(smem_u32(&ctl.full[st]), (ctl.base[st] + turn) & 1u);
+                    if (++slot == (uint32_t)depth) {
+                        slot = 0;
+                        turn++;
+                    }
                     const int iters = ((int)cur.nr + NG - 1) / NG;
                     const uint32_t mydot = stage_dots<G, CPL>(smem_u32(ring + (size_t)st * stage_bytes), (int)cur.nr, d_pad, qreg, lane, iters);
                     const int myr = (lane / G) * iters + (lane % G);
@@ -487,7 +492,7 @@ lm_final_kernel(const uint4 *__restrict__ gbuf, const unsigned int *__restrict__
 }
 
 // ---------------------------------------------------------------------------------------------------
-static int lm_tile_rows(int d_pad) { return d_pad <= 768 ? 16 : 8; }
+static int lm_tile_rows(int d_pad) { return d_pad <= 768 ? 32 : 16; }
 
 static bool lm_geometry(int d_pad, int *stage_bytes, size_t *smem) {
     const int sb = (lm_tile_rows(d_pad) * d_pad + 127) & ~127;
@@ -553,11 +558,11 @@ cudaError_t lm_enqueue_seed(const LmParams &p, const float *first_list_sims, con
 cudaError_t lm_enqueue_scan(const LmParams &p, int sm_count, cudaStream_t st, uint64_t *launches) {
     if (launches) *launches += 1;
     switch (p.rows.d_pad >> 4) {
-        case 48: return lm_launch_scan<16, 3, 16>(p, sm_count, st);  // 768-d (nomic-embed-text)
-        case 32: return lm_launch_scan<32, 1, 16>(p, sm_count, st);  // 512-d (noop/ai.go)
-        case 64: return lm_launch_scan<32, 2, 8>(p, sm_count, st);   // 1024-d
-        case 96: return lm_launch_scan<32, 3, 8>(p, sm_count, st);   // 1536-d
-        case 24: return lm_launch_scan<8, 3, 16>(p, sm_count, st);   // 384-d
+        case 48: return lm_launch_scan<16, 3, 32>(p, sm_count, st);  // 768-d (nomic-embed-text)
+        case 32: return lm_launch_scan<32, 1, 32>(p, sm_count, st);  // 512-d (noop/ai.go)
+        case 64: return lm_launch_scan<32, 2, 16>(p, sm_count, st);  // 1024-d
+        case 96: return lm_launch_scan<32, 3, 16>(p, sm_count, st);  // 1536-d
+        case 24: return lm_launch_scan<8, 3, 32>(p, sm_count, st);   // 384-d
         default: return cudaErrorInvalidValue;
     }
 }
