@@ -56,8 +56,8 @@ def parse():
                          "list-major one (listmajor.cu)")
     ap.add_argument("--contexts", type=int, default=0, choices=[0, 1, 2, 3, 4],
                     help="search contexts (one CUDA stream each) that take the steps in turn, like the reference's "
-                         "one-closure-per-goroutine searches running side by side (0 = 1 on one GPU, 4 on several, where "
-                         "the per-step exchange is worth hiding behind the other context's list scan)")
+                         "one-closure-per-goroutine searches running side by side (0 = 4: the small kernels of one batch -- "
+                         "probe selection, list inversion, exchange, merge -- overlap another batch's list scan)")
     return ap.parse_args()
 
 
@@ -251,16 +251,17 @@ def run_b200(a):
         qmats.append(m)
         qhost.append(m.ReadRows())
     # rows each step scores on this rank (for GB/s): probed lists x local list lengths
-    rows_scored = []
+    rows_scored, rows_unique = [], []
     for s in range(nsteps):
         probes, _ = ix.SelectProbes(qhost[s], a.nprobe, ctx=ctx)
         rows_scored.append(int(list_len[probes.astype(np.int64)].sum()))
+        rows_unique.append(int(list_len[np.unique(probes.astype(np.int64))].sum()))   # every probed list counted once
 
     # Search contexts: the reference runs every search in its own goroutine with its own `calculate` closure
     # (search.go:230); a closure is a vs_ctx = one CUDA stream + scratch.  Steps are handed to the contexts in turn, so
     # the small latency-bound kernels of one batch (probe selection, all-gather, merge) overlap the HBM-bound list scan
     # of the other.  Context 0 shares the stream the index was built on.
-    NC = a.contexts if a.contexts else (1 if world == 1 else 4)
+    NC = a.contexts if a.contexts else 4
     streams = [stream] + [torch.cuda.Stream(device=device) for _ in range(NC - 1)]
     ctxs = [ctx] + [cp.Context(cuda_stream=st.cuda_stream) for st in streams[1:]]
     hits_all = [pkg.shard.PackedHits(B, k, device, world) for _ in range(NC)]   # local hits (+ gathered / merged for N > 1)
@@ -270,7 +271,7 @@ def run_b200(a):
     d_status_all = torch.zeros((nsteps, B), device=device, dtype=torch.int32)   # one status row per step
     h_status_all = torch.zeros((nsteps, B), dtype=torch.int32).pin_memory()
 
-    def enqueue(s, resolve=False):  # (NC is rebound around the warm-up: nonlocal lookup at call time)
+    def enqueue_dev(s, resolve=False):  # (NC is rebound around the warm-up: nonlocal lookup at call time)
         """One step, fully asynchronous, on the context whose turn it is: both search stages (+ all-gather and merge
         for N > 1)."""
         i = s % NC
@@ -283,16 +284,24 @@ def run_b200(a):
             with torch.cuda.stream(streams[i]):
                 h.gather_and_merge(ctx=cx)
 
-    def finish(steps):
+    def finish(steps, enqueue=None):
         """Status check of a run of steps (one D2H + sync); a query whose float32 rounding could not be certified even
         after the in-kernel re-score (rare) is finished with literal arithmetic and its step is merged again."""
+        enqueue = enqueue or enqueue_dev
         lo, hi = steps[0], steps[-1] + 1
         for st in streams[1:]:
             stream.wait_stream(st)
         with torch.cuda.stream(stream):
             h_status_all[lo:hi].copy_(d_status_all[lo:hi], non_blocking=True)
         stream.synchronize()
-        redo = [s for s in steps if int((h_status_all[s] & 3).max()) != 0]
+        mask = [1 if int((h_status_all[s] & 3).max()) != 0 else 0 for s in steps]
+        if world > 1:
+            # list-stage ambiguity depends on a shard's own rows, so the ranks can disagree; a redo issues a collective (the
+            # all-gather of the step's hits): every rank redoes every step that any rank flagged
+            m = torch.tensor(mask, device=device, dtype=torch.int32)
+            dist.all_reduce(m, op=dist.ReduceOp.MAX)
+            mask = m.cpu().tolist()
+        redo = [s for s, f in zip(steps, mask) if f]
         for s in redo:
             enqueue(s, resolve=True)
         for st in streams[1:]:
@@ -300,7 +309,7 @@ def run_b200(a):
         return len(redo)
 
     def step(s):
-        enqueue(s)
+        enqueue_dev(s)
 
     def barrier():
         if world > 1:
@@ -328,15 +337,24 @@ def run_b200(a):
     barrier()
     # ---- single-query latency (batch 1), device resident; measured before the sustained throughput run, whose power
     # draw lowers the clocks for what follows ----
-    lat = []
-    one = cp.EmptyMatrix(1, D, ctx=ctx)
-    for i in range(min(64, B)):
-        one.LoadRows(0, qhost[0][i:i + 1], ctx=ctx)
-        ctx.sync()
-        ctx.timer_start()
-        ix.SearchDev(one, a.nprobe, k, d_ids.data_ptr(), d_sims.data_ptr(), d_counts.data_ptr(), d_status_all[0].data_ptr(), ctx=ctx)
-        lat.append(ctx.timer_stop() * 1e3)
-    lat = sorted(lat[4:]) if len(lat) > 8 else sorted(lat)
+    lat, lat_b2b = [], None
+    if world == 1:
+        one = cp.EmptyMatrix(1, D, ctx=ctx)
+        for i in range(min(64, B)):
+            one.LoadRows(0, qhost[0][i:i + 1], ctx=ctx)
+            ctx.sync()
+            ctx.timer_start()
+            ix.SearchDev(one, a.nprobe, k, d_ids.data_ptr(), d_sims.data_ptr(), d_counts.data_ptr(), d_status_all[0].data_ptr(), ctx=ctx)
+            lat.append(ctx.timer_stop() * 1e3)
+        lat = sorted(lat[4:]) if len(lat) > 8 else sorted(lat)
+        # the same search enqueued 50 times without a host sync in between: device time per query when single queries
+        # stream (the figure above starts from an idle stream and includes the host's launch latency, ~10 us)
+        for _ in range(2):
+            ctx.sync()
+            ctx.timer_start()
+            for _i in range(50):
+                ix.SearchDev(one, a.nprobe, k, d_ids.data_ptr(), d_sims.data_ptr(), d_counts.data_ptr(), d_status_all[0].data_ptr(), ctx=ctx)
+            lat_b2b = ctx.timer_stop() * 1e3 / 50
 
     barrier()
     for cx in ctxs:
@@ -351,7 +369,7 @@ def run_b200(a):
         step(s)                                  # asynchronous: the host runs ahead of the device
     redone = finish(list(range(W, W + K)))       # inside the timed region: status check + any literal-path redo
     if redone:                                   # the last step must be the one left in its result buffers
-        enqueue(W + K - 1)
+        enqueue_dev(W + K - 1)
         for st in streams[1:]:
             stream.wait_stream(st)
     with torch.cuda.stream(stream):
@@ -386,32 +404,69 @@ def run_b200(a):
     vp = lambda t: C.c_void_p(t.data_ptr())
     qdev = cp.EmptyMatrix(B, D, ctx=ctx)
 
+    # N > 1: the same pipeline as the device-resident run (steps handed to the search contexts in turn, status check and any
+    # literal-path redo at the end), with the step's query rows copied from pinned host memory first and its merged hits
+    # copied back to pinned host memory last; the host stays at most NC steps ahead (it waits for a context's previous step
+    # before it reuses that context's host buffers), like NC goroutines each making one synchronous search call at a time.
+    e_hq = [torch.empty((B, ROW_BYTES), dtype=torch.uint8).pin_memory() for _ in range(NC)]
+    e_q = [cp.EmptyMatrix(B, D, ctx=ctxs[i]) for i in range(NC)]
+    e_res = [(torch.empty((B, k), dtype=torch.int64).pin_memory(), torch.empty((B, k), dtype=torch.float32).pin_memory(),
+              torch.empty(B, dtype=torch.int32).pin_memory()) for _ in range(NC)]
+    e_ev = [None] * NC
+
+    def enqueue_e2e(s, resolve=False):
+        i = s % NC
+        h, cx = hits_all[i], ctxs[i]
+        if e_ev[i] is not None:
+            e_ev[i].synchronize()
+        e_hq[i].numpy()[:] = qhost[s]
+        e_q[i].LoadRows(0, e_hq[i].numpy(), ctx=cx)          # H2D from pinned memory + layout kernel, asynchronous
+        st = d_status_all[s]
+        ix.SearchDev(e_q[i], a.nprobe, k, h.ids.data_ptr(), h.sims.data_ptr(), h.counts.data_ptr(), st.data_ptr(), ctx=cx)
+        if resolve:
+            ix.Resolve(e_q[i], a.nprobe, k, h.ids.data_ptr(), h.sims.data_ptr(), h.counts.data_ptr(), st.data_ptr(), ctx=cx)
+        with torch.cuda.stream(streams[i]):
+            if world > 1:
+                h.gather_and_merge(ctx=cx)
+                src = (h.out_ids, h.out_sims, h.out_counts)
+            else:
+                src = (h.ids, h.sims, h.counts)
+            for dst, t_ in zip(e_res[i], src):
+                dst.copy_(t_, non_blocking=True)
+            e_ev[i] = torch.cuda.Event()
+            e_ev[i].record(streams[i])
+
     def e2e_step(s):
         hq.numpy()[:] = qhost[s]
-        if world == 1:
-            rc = L.vs_search(ctx.handle, ix.handle, vp(hq), B, a.nprobe, k, vp(h_ids), vp(h_sims), vp(h_counts))
-            assert rc == 0, pkg._lib.last_error()
-        else:
-            qdev.LoadRows(0, hq.numpy(), ctx=ctx)
-            st = d_status_all[s]
-            ix.SearchDev(qdev, a.nprobe, k, d_ids.data_ptr(), d_sims.data_ptr(), d_counts.data_ptr(), st.data_ptr(), ctx=ctx)
-            ix.Resolve(qdev, a.nprobe, k, d_ids.data_ptr(), d_sims.data_ptr(), d_counts.data_ptr(), st.data_ptr(), ctx=ctx)
-            with torch.cuda.stream(stream):
-                hits.gather_and_merge(ctx=ctx)
-                h_ids.copy_(hits.out_ids, non_blocking=True)
-                h_sims.copy_(hits.out_sims, non_blocking=True)
-                h_counts.copy_(hits.out_counts, non_blocking=True)
-            stream.synchronize()
+        rc = L.vs_search(ctx.handle, ix.handle, vp(hq), B, a.nprobe, k, vp(h_ids), vp(h_sims), vp(h_counts))
+        assert rc == 0, pkg._lib.last_error()
 
-    for s in range(min(W, 3)):
-        e2e_step(s)
-    barrier()
-    t0 = time.perf_counter()
-    for s in range(W, W + K):
-        e2e_step(s)
-    barrier()
-    e2e_s = time.perf_counter() - t0
-    if world > 1:
+    if world == 1:
+        for s in range(min(W, 3)):
+            e2e_step(s)
+        barrier()
+        t0 = time.perf_counter()
+        for s in range(W, W + K):
+            e2e_step(s)
+        barrier()
+        e2e_s = time.perf_counter() - t0
+    else:
+        for s in range(min(W, 3)):
+            enqueue_e2e(s)
+        finish(list(range(min(W, 3))), enqueue_e2e)
+        barrier()
+        t0 = time.perf_counter()
+        for s in range(W, W + K):
+            enqueue_e2e(s)
+        e_redone = finish(list(range(W, W + K)), enqueue_e2e)
+        if e_redone:
+            enqueue_e2e(W + K - 1)
+        for ev in e_ev:
+            if ev is not None:
+                ev.synchronize()
+        barrier()
+        e2e_s = time.perf_counter() - t0
+        h_ids, h_sims, h_counts = e_res[(W + K - 1) % NC]
         t = torch.tensor([e2e_s], device=device, dtype=torch.float64)
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         e2e_s = float(t.item())
@@ -419,6 +474,13 @@ def run_b200(a):
     e2e_match = bool((h_ids.numpy().view(np.uint64) == result_ids).all() and
                      (h_sims.numpy().view(np.uint32) == result_sims.view(np.uint32)).all())
     clocks = sampler.stop()
+    sharded_parity = None
+    if world > 1 and not a.no_cpu_baseline:
+        try:
+            sharded_parity = oracle_parity_sharded(pkg, torch, dist, ctx, ix, cent, a, qhost[W + K - 1], result_ids, result_sims, offsets,
+                                                   rank, world, device)
+        except Exception as e:  # noqa: BLE001 -- the measured line must still be printed
+            sharded_parity = {"error": repr(e)[:300]}
 
     if rank != 0:
         if world > 1:
@@ -434,13 +496,16 @@ def run_b200(a):
     peak = float(peaks.get("hbm_gbs", 6650.0))
     peak_src = "measured (MEASURED_PEAKS.json hbm_gbs)" if "hbm_gbs" in peaks else "fallback 6.65 TB/s (B200_PROFILING.md)"
     scored = rows_scored[W:W + K]
+    unique_bytes_per_launch = float(np.mean(rows_unique[W:W + K])) * ROW_BYTES
+    list_major = (not a.query_major) and B >= 16 and B <= 1024 and B * a.nprobe * 2 >= a.centroids and k <= 32
     bytes_per_launch = float(np.mean(scored)) * ROW_BYTES
     scan_ms_avg = scan_ms / max(1, scan_launches)
     achieved = bytes_per_launch / (scan_ms_avg * 1e-3) / 1e9 if scan_ms_avg > 0 else 0.0
     traffic = None
     try:
         tj = json.load(open(os.path.join(ROOT, "profiles", "scan_traffic.json")))
-        traffic = tj.get(f"dram_bytes_per_launch_batch{B}", tj.get("dram_bytes_per_launch") if B == 64 else None)
+        key = f"dram_bytes_per_launch_batch{B}" + ("_list_major" if list_major else "")
+        traffic = tj.get(key) if world == 1 and a.rows == 10_000_000 and a.centroids == 4096 and a.nprobe == 32 else None
     except Exception:  # noqa: BLE001
         pass
     scan_gbs_step = (float(np.mean(scored)) + B * a.centroids) * ROW_BYTES / (ms_per_step * 1e-3) / 1e9
@@ -458,11 +523,26 @@ def run_b200(a):
                    "build": build_info},
         "scan_gbs": round(scan_gbs_step, 1),
         "latency_us_batch1": {"p50": round(lat[len(lat) // 2], 1), "p99": round(lat[min(len(lat) - 1, int(len(lat) * 0.99))], 1),
-                              "n": len(lat)} if lat else None,
-        "roofline": {"bound": "hbm", "kernel": "stage_kernel (list scan + fused top-k)", "achieved": round(achieved, 1),
+                              "n": len(lat), "back_to_back_us_per_query": round(lat_b2b, 1) if lat_b2b else None,
+                              "what": "one query per launch, device-resident, CUDA events on the context's stream: p50/p99 from an idle "
+                                      "stream (includes the host's launch latency), and device time per query when 50 such searches "
+                                      "are enqueued back to back; one cooperative launch per query (csrc/fused.cu)"} if lat else None,
+        "roofline": {"bound": "hbm",
+                     "kernel": "lm_scan_kernel (list-major list scan: every probed list read once for the batch)" if list_major
+                               else "stage_kernel (query-major list scan + fused top-k)",
+                     "achieved": round(achieved, 1),
                      "peak": peak, "peak_source": peak_src, "unit": "GB/s", "frac": round(achieved / peak, 4),
-                     "traffic": traffic, "bytes_per_launch": round(bytes_per_launch), "ms_per_launch": round(scan_ms_avg, 5),
+                     "traffic": traffic,
+                     "traffic_source": "one ncu --set full capture of this kernel at N=1 on this workload (profiles/scan_traffic.json); "
+                                       "null for any other workload or world size",
+                     "bytes_per_launch": round(bytes_per_launch), "ms_per_launch": round(scan_ms_avg, 5),
                      "launches_timed": scan_launches,
+                     "per_unique_byte": {"achieved": round(unique_bytes_per_launch / (scan_ms_avg * 1e-3) / 1e9, 1) if scan_ms_avg > 0 else None,
+                                         "frac": round(unique_bytes_per_launch / (scan_ms_avg * 1e-3) / 1e9 / peak, 4) if scan_ms_avg > 0 else None,
+                                         "bytes_per_launch": round(unique_bytes_per_launch),
+                                         "what": "rows of every probed list counted ONCE per step x 776 B: what a list-major scan has "
+                                                 "to read; `achieved` above counts 776 B per (query, row) pair scored (SURVEY 8d), so a "
+                                                 "list-major launch can pass the HBM peak there"},
                      "alone": {"achieved": round(float(np.mean(rows_scored[:W])) * ROW_BYTES / (alone_ms / max(1, alone_launches) * 1e-3) / 1e9, 1)
                                if alone_ms > 0 else None,
                                "ms_per_launch": round(alone_ms / max(1, alone_launches), 5), "launches": alone_launches,
@@ -470,12 +550,12 @@ def run_b200(a):
                                        "overlapping; in the timed region two contexts take the steps in turn and a scan "
                                        "launch shares the SMs with the other context's kernels, so its own duration is longer "
                                        "than its share of the step"},
-                     "note": "achieved = rows scored x 776 B / launch time (algorithmic bytes); traffic = ncu dram bytes of one "
-                             "launch at this batch size (= algorithmic: L2 hit rate 1 %). peak is the driver's read+write copy "
-                             "figure; a read-only stream goes higher on this part (ncu: 7.07 TB/s, 86 % of its 8.17 TB/s "
-                             "ceiling, profiles/r01_scan_b256_summary.txt), so frac can pass 1"},
+                     "note": "achieved = (query, row) pairs scored x 776 B / launch time (algorithmic bytes, SURVEY 8d); traffic = ncu "
+                             "dram bytes of one such launch. peak is the driver's read+write copy figure; a read-only stream goes "
+                             "higher on this part (ncu: 7.07 TB/s), so a fraction can pass 1"},
         "e2e": {"value": round(e2e_qps, 1), "unit": "queries/s", "h2d_bytes_per_step": B * ROW_BYTES,
                 "d2h_bytes_per_step": B * k * 12 + B * 4 + B * 4, "results_match_device_path": e2e_match},
+        "parity_vs_oracle": sharded_parity,
         "gpu_launches": int(launches),
         "rescored_candidates": ctx.slowpath_count(), "steps_redone_literal": int(redone),
         "clocks": clocks,
@@ -738,6 +818,72 @@ def other_configs(pkg, torch, ctx, ix, a, device, peaks):
         out["upload"] = {"error": repr(e)[:300]}
     torch.cuda.empty_cache()
     return out
+
+
+def oracle_parity_sharded(pkg, torch, dist, ctx, ix, cent, a, queries, got_ids, got_sims, offsets, rank, world, device):
+    """N > 1: the merged hits of the last timed step against the oracle (server/search.go:202-273 restated), on rank 0.
+    The oracle picks the probed lists of a few queries; every rank reads its stripe of those lists back from its device
+    store; the stripes are gathered on rank 0 over the process group, put back in primary-key order and searched on the CPU."""
+    list_len = np.diff(offsets)
+    per_query = float(a.rows) / max(1, a.centroids) * a.nprobe
+    nchk = 1 if per_query > 300_000 else 2
+    box = [None]
+    if rank == 0:
+        import oracle
+        centroids = cent.ReadRows()
+        plists = [oracle.select_probes(q, centroids, a.nprobe)[0] for q in queries[:nchk]]
+        box = [sorted({int(x) for p_ in plists for x in p_})]
+    dist.broadcast_object_list(box, src=0)
+    lists = box[0]
+    rows, ids, lor = [], [], []
+    for Lx in lists:
+        n_ = int(list_len[Lx])
+        if n_ == 0:
+            continue
+        r, i = ix.ReadRows(int(offsets[Lx]), n_, ctx=ctx)
+        rows.append(r)
+        ids.append(i)
+        lor.append(np.full(n_, Lx, np.uint32))
+    rows = np.concatenate(rows) if rows else np.zeros((0, ROW_BYTES), np.uint8)
+    ids = np.concatenate(ids) if ids else np.zeros(0, np.uint64)
+    lor = np.concatenate(lor) if lor else np.zeros(0, np.uint32)
+    m = torch.tensor([rows.shape[0]], device=device, dtype=torch.int64)
+    ms = [torch.zeros_like(m) for _ in range(world)]
+    dist.all_gather(ms, m)
+    counts = [int(x.item()) for x in ms]
+    mx = max(max(counts), 1)
+
+    def gather(arr, width, dtype):
+        t = torch.zeros((mx, width) if width else (mx,), device=device, dtype=dtype)
+        if arr.shape[0]:
+            t[:arr.shape[0]] = torch.from_numpy(arr).to(device)
+        out = [torch.zeros_like(t) for _ in range(world)] if rank == 0 else None
+        dist.gather(t, out, dst=0)
+        if rank != 0:
+            return None
+        return np.concatenate([o[:c].cpu().numpy() for o, c in zip(out, counts)])
+
+    g_rows = gather(rows, ROW_BYTES, torch.uint8)
+    g_ids = gather(ids.view(np.int64), 0, torch.int64)
+    g_lor = gather(lor.view(np.int32), 0, torch.int32)
+    if rank != 0:
+        return None
+    import oracle
+    g_ids = g_ids.view(np.uint64)
+    g_lor = g_lor.view(np.uint32)
+    order = np.argsort(g_ids, kind="stable")      # the reference streams rows in primary-key order
+    g_rows, g_ids, g_lor = g_rows[order], g_ids[order], g_lor[order]
+    ok = True
+    t0 = time.perf_counter()
+    for qi in range(nchk):
+        w_ids, w_sims = oracle.search(queries[qi], centroids, g_rows, g_lor, g_ids, a.nprobe, a.k)
+        n_ = len(w_ids)
+        ok = ok and got_ids[qi, :n_].tolist() == w_ids.tolist() and \
+            bool((got_sims[qi, :n_].view(np.uint32) == w_sims.view(np.uint32)).all())
+    return {"queries_checked": nchk, "match": bool(ok), "rows_gathered_from_all_ranks": int(g_rows.shape[0]),
+            "oracle_seconds": round(time.perf_counter() - t0, 2),
+            "what": "merged top-k of the last timed step (NCCL all-gather + device merge) vs the CPU oracle over the probed lists "
+                    "read back from every rank's shard"}
 
 
 def cpu_baseline(pkg, ctx, ix, cent, a, queries, gpu_ids, gpu_sims, offsets):
