@@ -22,6 +22,8 @@ SYMBOLS = [
     "vs_index_rows", "vs_index_lists", "vs_index_cols", "vs_index_list_offsets", "vs_index_read_rows", "vs_index_upload", "vs_search", "vs_search_flat", "vs_search_flat_gemm", "vs_search_batch_dev", "vs_index_search_batch_dev", "vs_search_dev",
     "vs_search_resolve", "vs_select_probes", "vs_topk_merge_dev", "vs_topk_merge_packed_dev",
     "vs_kmeans_step", "vs_kmeans", "vs_kmeans_accumulate_dev", "vs_kmeans_finish_dev", "vs_recenter", "vs_debug_set_argmax_gemm_min", "vs_debug_set_fused", "vs_debug_set_list_major",
+    "vs_sharded_create", "vs_sharded_release", "vs_sharded_rows", "vs_sharded_shards", "vs_sharded_shard_rows", "vs_sharded_build_assigned",
+    "vs_sharded_upload", "vs_sharded_search", "vs_sharded_ctx_create", "vs_sharded_ctx_destroy", "vs_sharded_search_ctx",
 ]
 
 
@@ -111,6 +113,22 @@ def load():
         L.vs_debug_set_argmax_gemm_min.argtypes = [sz]
         L.vs_debug_set_fused.argtypes = [C.c_int]
         L.vs_debug_set_list_major.argtypes = [C.c_int]
+        L.vs_sharded_create.argtypes = [vp, sz, C.POINTER(vp)]
+        L.vs_sharded_release.argtypes = [vp]
+        L.vs_sharded_release.restype = None
+        L.vs_sharded_rows.argtypes = [vp]
+        L.vs_sharded_rows.restype = sz
+        L.vs_sharded_shards.argtypes = [vp]
+        L.vs_sharded_shards.restype = sz
+        L.vs_sharded_shard_rows.argtypes = [vp, sz]
+        L.vs_sharded_shard_rows.restype = sz
+        L.vs_sharded_build_assigned.argtypes = [vp, vp, sz, sz, vp, vp, vp, sz]
+        L.vs_sharded_upload.argtypes = [vp, vp, sz, sz, vp, vp]
+        L.vs_sharded_search.argtypes = [vp, vp, sz, sz, sz, vp, vp, vp]
+        L.vs_sharded_ctx_create.argtypes = [vp, C.POINTER(vp)]
+        L.vs_sharded_ctx_destroy.argtypes = [vp]
+        L.vs_sharded_ctx_destroy.restype = None
+        L.vs_sharded_search_ctx.argtypes = [vp, vp, sz, sz, sz, vp, vp, vp]
         L.vs_matrix_gather.argtypes = [vp, vp, vp, sz, C.POINTER(vp)]
         L.vs_matrix_split_dev.argtypes = [vp, vp, vp, sz, vp, vp]
         L.vs_matrix_split.argtypes = [vp, vp, vp, sz, vp, vp]

@@ -23,6 +23,17 @@ static thread_local char g_err[512] = "";
 static int g_device = -1;
 static int g_sm_count = 0;
 static std::mutex g_mu;
+// A thread driving several devices (vs_sharded_*, sharded.cu) overrides the process default for the calls it makes.
+static thread_local int tl_device = -1;
+static int cur_device() { return tl_device >= 0 ? tl_device : g_device; }
+namespace vs {
+void internal_set_thread_device(int device) {
+    tl_device = device;
+    if (cur_device() >= 0) cudaSetDevice(cur_device());
+}
+int internal_thread_device() { return cur_device(); }
+int internal_sm_count() { return g_sm_count; }
+}  // namespace vs
 
 static int fail(int code, const char *fmt, ...) {
     va_list ap;
@@ -31,6 +42,9 @@ static int fail(int code, const char *fmt, ...) {
     va_end(ap);
     return code;
 }
+namespace vs {
+int internal_fail(int code, const char *msg) { return fail(code, "%s", msg); }
+}  // namespace vs
 #define CU(call)                                                                                        \
     do {                                                                                                \
         cudaError_t _e = (call);                                                                        \
@@ -77,8 +91,8 @@ extern "C" int vs_device_info(char *name, size_t name_cap, int *sm_count, size_t
 }
 
 static int need_dev() {
-    if (g_device < 0) return fail(VS_ENODEV, "vs_init not called (or no CUDA device); libvscuda has no CPU fallback");
-    cudaSetDevice(g_device);
+    if (cur_device() < 0) return fail(VS_ENODEV, "vs_init not called (or no CUDA device); libvscuda has no CPU fallback");
+    cudaSetDevice(cur_device());
     return VS_OK;
 }
 
@@ -87,7 +101,7 @@ extern "C" int vs_ctx_create(vs_ctx **out) {
     VS(need_dev());
     if (!out) return fail(VS_EINVAL, "out is null");
     vs_ctx *c = new vs_ctx();
-    c->device = g_device;
+    c->device = cur_device();
     CU(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
     CU(cudaEventCreate(&c->ev0));
     CU(cudaEventCreate(&c->ev1));
@@ -104,7 +118,7 @@ extern "C" int vs_ctx_create_on_stream(void *cuda_stream, vs_ctx **out) {
     VS(need_dev());
     if (!out) return fail(VS_EINVAL, "out is null");
     vs_ctx *c = new vs_ctx();
-    c->device = g_device;
+    c->device = cur_device();
     c->stream = static_cast<cudaStream_t>(cuda_stream);
     c->owns_stream = false;
     CU(cudaEventCreate(&c->ev0));
@@ -365,7 +379,7 @@ static int matrix_alloc(size_t n, size_t d, vs_matrix **out) {
     if (d > 4096) return fail(VS_ERANGE, "d=%zu: kernels support d <= 4096", d);
     if (n > 0x7FFFFFFFull) return fail(VS_ERANGE, "n=%zu: a device matrix holds < 2^31 rows", n);
     vs_matrix *m = new vs_matrix();
-    m->device = g_device;
+    m->device = cur_device();
     m->n = n;
     m->d = (int)d;
     m->d_pad = (int)((d + 15) & ~size_t(15));
@@ -2112,7 +2126,9 @@ extern "C" int vs_topk_merge_packed_dev(vs_ctx *c, const void *d_packed, size_t 
     VS(need_dev());
     if (!c || !d_packed) return fail(VS_EINVAL, "null argument");
     if (k > 128) return fail(VS_ERANGE, "k=%zu > 128", k);
-    if ((ids_off | sims_off | counts_off | rank_stride_bytes) & 3) return fail(VS_EINVAL, "offsets must be 4-byte aligned");
+    if ((sims_off | counts_off) & 3) return fail(VS_EINVAL, "sims_off / counts_off must be 4-byte aligned");
+    if (((size_t)(uintptr_t)d_packed | ids_off | rank_stride_bytes) & 7)
+        return fail(VS_EINVAL, "the packed buffer, ids_off and rank_stride_bytes must be 8-byte aligned (uint64 ids)");
     if (nq == 0) return VS_OK;
     const char *b = static_cast<const char *>(d_packed);
     LAUNCH(c, launch_topk_merge(reinterpret_cast<const uint64_t *>(b + ids_off), reinterpret_cast<const float *>(b + sims_off),

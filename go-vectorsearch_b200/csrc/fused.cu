@@ -739,14 +739,16 @@ static cudaError_t launch_fused_t(FusedParams p, int grid, cudaStream_t st) {
     if (!fused_geometry(p.rows.d_pad, KPL, SPW, &p.stage_bytes, &smem)) return cudaErrorInvalidValue;
     p.stages = kFusedWarps * SPW;
     auto kern = fused_search_kernel<G, CPL, KPL, TR, SPW>;
-    static int max_grid = 0;  // per instantiation: blocks a cooperative launch can hold
+    static int max_grid_of[64] = {0};  // per instantiation and device (function attributes are per device): blocks a
+    int dev = 0;                        // cooperative launch can hold
+    cudaGetDevice(&dev);
+    int &max_grid = max_grid_of[dev & 63];
     if (!max_grid) {
         cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         if (e != cudaSuccess) return e;
-        int per_sm = 0, dev = 0, sms = 0;
+        int per_sm = 0, sms = 0;
         e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, kFusedThreads, smem);
         if (e != cudaSuccess) return e;
-        cudaGetDevice(&dev);
         cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
         if (per_sm < 1) return cudaErrorCooperativeLaunchTooLarge;
         max_grid = sms;  // one block per SM (its shared-memory ring fills the SM)

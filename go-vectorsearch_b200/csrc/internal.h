@@ -115,6 +115,12 @@ constexpr uint32_t kStatusProbeAmbiguous = 1u;
 constexpr uint32_t kStatusListAmbiguous = 2u;
 constexpr uint32_t kStatusNeedMore = 4u;
 
+// api.cu: hooks for sharded.cu (one host thread driving several devices)
+void internal_set_thread_device(int device);  // -1: back to the process default (vs_init)
+int internal_thread_device();
+int internal_sm_count();
+int internal_fail(int code, const char *msg);
+
 // scan.cu
 cudaError_t launch_stage(const StageParams &p, int kpl, bool exact, int grid_blocks, cudaStream_t st);
 int stage_lanes_per_row(int d_pad);
@@ -127,6 +133,8 @@ cudaError_t launch_cosine_fix(const MatView &rows, const double *qnorm, float *s
                               const unsigned int *work_count, int sm_count, cudaStream_t st);
 cudaError_t launch_topk_merge(const uint64_t *ids_in, const float *sims_in, const int32_t *counts_in, size_t rank_stride_bytes,
                               int G, int nq, int k, uint64_t *ids_out, float *sims_out, int32_t *counts_out, cudaStream_t st);
+cudaError_t launch_topk_merge_ptrs(const unsigned char *const *bufs, size_t ids_off, size_t sims_off, size_t counts_off, int G, int nq,
+                                   int k, uint64_t *ids_out, float *sims_out, int32_t *counts_out, cudaStream_t st);
 
 cudaError_t scan_set_certify_scale(float scale);
 cudaError_t argmax_set_certify_scale(float scale);

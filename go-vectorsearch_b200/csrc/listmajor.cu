@@ -519,11 +519,13 @@ static cudaError_t lm_launch_scan(LmParams p, int grid, cudaStream_t st) {
     size_t smem;
     if (!lm_geometry(p.rows.d_pad, &p.stage_bytes, &smem)) return cudaErrorInvalidValue;
     auto kern = lm_scan_kernel<G, CPL, TR>;
-    static bool attr = false;
-    if (!attr) {
+    static bool attr_of[64] = {false};  // (function attributes are per device)
+    int dev = 0;
+    cudaGetDevice(&dev);
+    if (!attr_of[dev & 63]) {
         cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         if (e != cudaSuccess) return e;
-        attr = true;
+        attr_of[dev & 63] = true;
     }
     kern<<<grid, kLmThreads, smem, st>>>(p);
     return cudaGetLastError();

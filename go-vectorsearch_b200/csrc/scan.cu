@@ -746,22 +746,35 @@ cudaError_t launch_cosine_fix(const MatView &rows, const double *qnorm, float *s
 }
 
 // ---------------------------------------------------------------------------------------------------
-// Multi-GPU merge: G shard-local hit lists per query -> global top-k (same order and dedup rule).
+// Multi-GPU merge: G shard-local hit lists per query -> global top-k (same order and dedup rule).  Shard g's arrays are
+// either at a fixed stride from one base (one process per GPU: the all-gathered buffer) or anywhere (`bufs`: one packed
+// buffer per shard, possibly in a PEER device's memory -- one process driving G devices reads them over NVLink).
 __global__ void topk_merge_kernel(const uint64_t *ids_in, const float *sims_in, const int32_t *counts_in,
-                                  size_t rank_stride_bytes, int G, int nq, int k, uint64_t *ids_out, float *sims_out,
+                                  size_t rank_stride_bytes, const unsigned char *const *bufs, size_t ids_off, size_t sims_off,
+                                  size_t counts_off, int G, int nq, int k, uint64_t *ids_out, float *sims_out,
                                   int32_t *counts_out) {
     const int qi = blockIdx.x;
     const int lane = threadIdx.x;
     WarpTopK<4> top;
     top.init();
     for (int g = 0; g < G; g++) {
-        // rank g's arrays: either [G][nq][k] contiguous (stride 0 = derive) or one packed buffer per rank
-        const uint64_t *gi = rank_stride_bytes ? reinterpret_cast<const uint64_t *>(reinterpret_cast<const char *>(ids_in) + g * rank_stride_bytes)
-                                               : ids_in + (size_t)g * nq * k;
-        const float *gs = rank_stride_bytes ? reinterpret_cast<const float *>(reinterpret_cast<const char *>(sims_in) + g * rank_stride_bytes)
-                                            : sims_in + (size_t)g * nq * k;
-        const int32_t *gc = rank_stride_bytes ? reinterpret_cast<const int32_t *>(reinterpret_cast<const char *>(counts_in) + g * rank_stride_bytes)
-                                              : counts_in + (size_t)g * nq;
+        const uint64_t *gi;
+        const float *gs;
+        const int32_t *gc;
+        if (bufs) {
+            const unsigned char *b = bufs[g];
+            gi = reinterpret_cast<const uint64_t *>(b + ids_off);
+            gs = reinterpret_cast<const float *>(b + sims_off);
+            gc = reinterpret_cast<const int32_t *>(b + counts_off);
+        } else if (rank_stride_bytes) {
+            gi = reinterpret_cast<const uint64_t *>(reinterpret_cast<const char *>(ids_in) + g * rank_stride_bytes);
+            gs = reinterpret_cast<const float *>(reinterpret_cast<const char *>(sims_in) + g * rank_stride_bytes);
+            gc = reinterpret_cast<const int32_t *>(reinterpret_cast<const char *>(counts_in) + g * rank_stride_bytes);
+        } else {
+            gi = ids_in + (size_t)g * nq * k;
+            gs = sims_in + (size_t)g * nq * k;
+            gc = counts_in + (size_t)g * nq;
+        }
         const int cnt = gc[qi];
         for (int base = 0; base < cnt; base += 32) {
             int j = base + lane;
@@ -790,7 +803,16 @@ __global__ void topk_merge_kernel(const uint64_t *ids_in, const float *sims_in, 
 cudaError_t launch_topk_merge(const uint64_t *ids_in, const float *sims_in, const int32_t *counts_in, size_t rank_stride_bytes,
                               int G, int nq, int k, uint64_t *ids_out, float *sims_out, int32_t *counts_out, cudaStream_t st) {
     if (k > 128) return cudaErrorInvalidValue;
-    topk_merge_kernel<<<nq, 32, 0, st>>>(ids_in, sims_in, counts_in, rank_stride_bytes, G, nq, k, ids_out, sims_out, counts_out);
+    topk_merge_kernel<<<nq, 32, 0, st>>>(ids_in, sims_in, counts_in, rank_stride_bytes, nullptr, 0, 0, 0, G, nq, k, ids_out, sims_out,
+                                         counts_out);
+    return cudaGetLastError();
+}
+
+cudaError_t launch_topk_merge_ptrs(const unsigned char *const *bufs, size_t ids_off, size_t sims_off, size_t counts_off, int G, int nq,
+                                   int k, uint64_t *ids_out, float *sims_out, int32_t *counts_out, cudaStream_t st) {
+    if (k > 128) return cudaErrorInvalidValue;
+    topk_merge_kernel<<<nq, 32, 0, st>>>(nullptr, nullptr, nullptr, 0, bufs, ids_off, sims_off, counts_off, G, nq, k, ids_out, sims_out,
+                                         counts_out);
     return cudaGetLastError();
 }
 

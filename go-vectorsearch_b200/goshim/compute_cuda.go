@@ -49,6 +49,10 @@ func cudaInit() {
 
 // check turns a C status into the reference's own failure mode: panic for the empty-input cases
 // (compute.go:13,26,30), logger Fatalf for a dimension mismatch (cosine.go:19-21,77-79).
+// check turns a C ABI status into the reference's error behaviour (panic on empty input, compute.go:13,26,30; Fatalf
+// on a dimension mismatch, cosine.go:19-21,77-79).  vs_last_error() is thread-local in the library and a goroutine may
+// be rescheduled onto another OS thread between two cgo calls, so every caller pins its goroutine to its OS thread
+// (pinned(), below) for the span "C call ... check": the message read here belongs to the call that failed.
 func check(rc C.int) {
 	switch rc {
 	case C.VS_OK:
@@ -58,6 +62,13 @@ func check(rc C.int) {
 	default:
 		panic(C.GoString(C.vs_last_error()))
 	}
+}
+
+// pinned runs f with the goroutine locked to its OS thread (see check).
+func pinned(f func()) {
+	runtime.LockOSThread()
+	defer runtime.UnlockOSThread()
+	f()
 }
 
 // ctx is one CUDA stream + scratch arena. The method-form calls (search.go:214, upload.go:245) share a
@@ -70,6 +81,8 @@ var (
 )
 
 func newCtx() *ctx {
+	runtime.LockOSThread()
+	defer runtime.UnlockOSThread()
 	cudaInit()
 	c := &ctx{}
 	check(C.vs_ctx_create(&c.h))
@@ -89,7 +102,7 @@ func withDefaultCtx(f func(c *ctx)) {
 	if defaultCtx == nil {
 		defaultCtx = newCtx()
 	}
-	f(defaultCtx)
+	pinned(func() { f(defaultCtx) })
 }
 
 // pack copies [][]uint8 into one C buffer: cgo forbids passing Go pointers to Go pointers.

@@ -50,8 +50,9 @@ func (vector *vectorContainer) MatrixCosineSimilarity(matrix Matrix) (similarity
 // (one per goroutine, server/search.go:230), done() releases it.
 func VectorMatrixCosineSimilarity() (calculate func(vector Vector, matrix Matrix) (similarity []float32), done func()) {
 	c := newCtx()
-	return func(vector Vector, matrix Matrix) []float32 {
-			return vectorMatrix(c, vector.(*vectorContainer), matrix.(*matrixContainer))
+	return func(vector Vector, matrix Matrix) (similarity []float32) {
+			pinned(func() { similarity = vectorMatrix(c, vector.(*vectorContainer), matrix.(*matrixContainer)) })
+			return
 		}, func() {
 			c.close()
 		}
@@ -68,8 +69,11 @@ func (matrix1 *matrixContainer) MatrixCosineSimilarity(matrix2 Matrix) (relative
 // MatrixCosineSimilarity returns (calculate, done) for the dnc workers (dnc/dnc.go:349, dnc/k_means.go:31).
 func MatrixCosineSimilarity() (calculate func(matrix1 Matrix, matrix2 Matrix) (relativeSimilaritieList []float32, nearestIndexList []int), done func()) {
 	c := newCtx()
-	return func(matrix1 Matrix, matrix2 Matrix) ([]float32, []int) {
-			return matrixMatrix(c, matrix1.(*matrixContainer), matrix2.(*matrixContainer))
+	return func(matrix1 Matrix, matrix2 Matrix) (relativeSimilaritieList []float32, nearestIndexList []int) {
+			pinned(func() {
+				relativeSimilaritieList, nearestIndexList = matrixMatrix(c, matrix1.(*matrixContainer), matrix2.(*matrixContainer))
+			})
+			return
 		}, func() {
 			c.close()
 		}

@@ -218,3 +218,72 @@ func ReassignRecenter(X Matrix, centroids [][]uint8) (assign []int32, recentred 
 	}
 	return assign, recentred, counts
 }
+
+// ShardedIndex is the device-resident store of one category striped over several GPUs of one box, driven from THIS
+// process (main.go:31 is one process; server/search.go:115 runs one Search per goroutine): rows go to device
+// primaryKey % len(devices), the centroid table is replicated, every device answers on its stripe and device 0 merges
+// the shard-local hits it reads from its peers over NVLink (vs_sharded_*, csrc/sharded.cu).  Same hits as one Index.
+type ShardedIndex struct{ h *C.vs_sharded }
+
+// NewShardedIndex: rows in primary-key order (row i has key i), their DocumentID and the position of their CentroidID
+// in `centroids`.
+func NewShardedIndex(devices []int, rows [][]uint8, documentIDs []uint64, centroidIndex []uint32, centroids [][]uint8) *ShardedIndex {
+	rbuf, n, rowBytes := pack(rows)
+	defer C.free(rbuf)
+	cbuf, nc, _ := pack(centroids)
+	defer C.free(cbuf)
+	devs := make([]C.int, len(devices))
+	for i, d := range devices {
+		devs[i] = C.int(d)
+	}
+	sh := &ShardedIndex{}
+	pinned(func() {
+		check(C.vs_sharded_create(&devs[0], C.size_t(len(devs)), &sh.h))
+		check(C.vs_sharded_build_assigned(sh.h, (*C.uint8_t)(rbuf), C.size_t(n), C.size_t(rowBytes),
+			(*C.uint64_t)(unsafe.Pointer(&documentIDs[0])), (*C.uint32_t)(unsafe.Pointer(&centroidIndex[0])),
+			(*C.uint8_t)(cbuf), C.size_t(nc)))
+	})
+	runtime.SetFinalizer(sh, func(sh *ShardedIndex) { C.vs_sharded_release(sh.h) })
+	return sh
+}
+
+// ShardedSearch returns the pair the reference's call sites use (search.go:230): calculate answers a batch of queries
+// (nprobe = req.Centroids, k = req.Count+req.Offset), done releases the per-device streams and buffers.  One pair per
+// goroutine; pairs run concurrently.
+func (sh *ShardedIndex) ShardedSearch() (calculate func(queries [][]uint8, nprobe int, k int) (documentIDs [][]uint64, similarities [][]float32), done func()) {
+	var sc *C.vs_sharded_ctx
+	pinned(func() { check(C.vs_sharded_ctx_create(sh.h, &sc)) })
+	return func(queries [][]uint8, nprobe int, k int) ([][]uint64, [][]float32) {
+			qbuf, nq, _ := pack(queries)
+			defer C.free(qbuf)
+			ids := make([]uint64, nq*k)
+			sims := make([]float32, nq*k)
+			counts := make([]C.int32_t, nq)
+			pinned(func() {
+				check(C.vs_sharded_search_ctx(sc, (*C.uint8_t)(qbuf), C.size_t(nq), C.size_t(nprobe), C.size_t(k),
+					(*C.uint64_t)(unsafe.Pointer(&ids[0])), (*C.float)(unsafe.Pointer(&sims[0])), &counts[0]))
+			})
+			outIDs := make([][]uint64, nq)
+			outSims := make([][]float32, nq)
+			for q := 0; q < nq; q++ {
+				outIDs[q] = ids[q*k : q*k+int(counts[q])]
+				outSims[q] = sims[q*k : q*k+int(counts[q])]
+			}
+			return outIDs, outSims
+		}, func() {
+			C.vs_sharded_ctx_destroy(sc)
+		}
+}
+
+// Upload is server/upload.go:239-279 on the striped store: the new embeddings take the next primary keys and join the
+// list of their nearest centroid on the device that owns their key.  Must not overlap searches on this index.
+func (sh *ShardedIndex) Upload(rows [][]uint8, documentIDs []uint64) (centroidIndex []int64) {
+	rbuf, n, rowBytes := pack(rows)
+	defer C.free(rbuf)
+	centroidIndex = make([]int64, n)
+	pinned(func() {
+		check(C.vs_sharded_upload(sh.h, (*C.uint8_t)(rbuf), C.size_t(n), C.size_t(rowBytes),
+			(*C.uint64_t)(unsafe.Pointer(&documentIDs[0])), (*C.int64_t)(unsafe.Pointer(&centroidIndex[0]))))
+	})
+	return
+}

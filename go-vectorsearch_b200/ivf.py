@@ -230,3 +230,78 @@ def TopKMergeDev(d_ids_in, d_sims_in, d_counts_in, G, nq, k, d_ids_out, d_sims_o
     vp = lambda x: C.c_void_p(int(x))
     _check(L.vs_topk_merge_dev(ctx.handle, vp(d_ids_in), vp(d_sims_in), vp(d_counts_in), int(G), int(nq), int(k),
                                vp(d_ids_out), vp(d_sims_out), vp(d_counts_out)))
+
+
+class ShardedIndex:
+    """One host process driving several GPUs (vs_sharded_*, csrc/sharded.cu): rows striped over the devices by primary
+    key, centroids replicated, shard-local top-k merged on device 0 over NVLink.  Mirrors what a `cuda`-tagged
+    server.Search would hold instead of a database handle."""
+
+    def __init__(self, devices):
+        self._L = _lib.init()
+        dev = np.ascontiguousarray(devices, dtype=np.int32)
+        h = C.c_void_p()
+        _check(self._L.vs_sharded_create(_p(dev), int(dev.shape[0]), C.byref(h)))
+        self._h = h
+        self.cols = 0
+
+    def close(self):
+        if self._h is not None:
+            self._L.vs_sharded_release(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:  # noqa: BLE001
+            pass
+
+    @property
+    def rows(self):
+        return int(self._L.vs_sharded_rows(self._h))
+
+    @property
+    def shards(self):
+        return int(self._L.vs_sharded_shards(self._h))
+
+    def shard_rows(self, g):
+        return int(self._L.vs_sharded_shard_rows(self._h, int(g)))
+
+    def build_assigned(self, rows, doc_ids, list_of_row, centroids):
+        rows = _rows_array(rows)
+        centroids = _rows_array(centroids)
+        lor = np.ascontiguousarray(list_of_row, dtype=np.uint32)
+        ids = None if doc_ids is None else np.ascontiguousarray(doc_ids, dtype=np.uint64)
+        _check(self._L.vs_sharded_build_assigned(self._h, _p(rows), rows.shape[0], rows.shape[1], _p(ids) if ids is not None else None,
+                                                 _p(lor), _p(centroids), centroids.shape[0]))
+        self.cols = rows.shape[1] - 8
+        return self
+
+    def Upload(self, rows, doc_ids=None):
+        rows = _rows_array(rows)
+        ids = None if doc_ids is None else np.ascontiguousarray(doc_ids, dtype=np.uint64)
+        assign = np.empty(rows.shape[0], np.int64)
+        _check(self._L.vs_sharded_upload(self._h, _p(rows), rows.shape[0], rows.shape[1], _p(ids) if ids is not None else None,
+                                         _p(assign)))
+        return assign
+
+    def Search(self, queries, nprobe, k, sctx=None):
+        """sctx: a handle from NewSearchContext() (one per concurrent caller); None = the index's own, one search at a time."""
+        q = _rows_array(queries)
+        nq = q.shape[0]
+        ids = np.zeros((nq, k), np.uint64)
+        sims = np.zeros((nq, k), np.float32)
+        counts = np.zeros(nq, np.int32)
+        if sctx is None:
+            _check(self._L.vs_sharded_search(self._h, _p(q), nq, int(nprobe), int(k), _p(ids), _p(sims), _p(counts)))
+        else:
+            _check(self._L.vs_sharded_search_ctx(sctx, _p(q), nq, int(nprobe), int(k), _p(ids), _p(sims), _p(counts)))
+        return ids, sims, counts
+
+    def NewSearchContext(self):
+        h = C.c_void_p()
+        _check(self._L.vs_sharded_ctx_create(self._h, C.byref(h)))
+        return h
+
+    def CloseSearchContext(self, sctx):
+        self._L.vs_sharded_ctx_destroy(sctx)

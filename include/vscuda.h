@@ -233,6 +233,40 @@ VS_API int vs_search_resolve(vs_ctx *ctx, const vs_index *ix, const vs_matrix *q
 /* Stage 1 only (search.go:202-227): probe_out[nq*min(nprobe,C)] list indices in rank order (host). */
 VS_API int vs_select_probes(vs_ctx *ctx, const vs_index *ix, const uint8_t *queries_packed, size_t nq, size_t nprobe,
                      uint32_t *probe_out, float *probe_sims_out);
+/* ---- one host process, several GPUs (csrc/sharded.cu) ---------------------------------------------------------------
+ * The reference is one Go process (main.go:31) that runs one search per goroutine (server/search.go:115): it cannot be
+ * split into a process per GPU.  A vs_sharded handle lets that one process drive G devices of one NVLink / NVSwitch box:
+ * rows are striped over the devices by primary key (key % G, so every posting list is split evenly for any probe set),
+ * the centroid table is replicated, every device answers a batch on its stripe, and device 0 merges the shard-local
+ * top-k lists, reading its peers' hit buffers in place over NVLink (peer access; no collective library, no staging copy).
+ * Same results as one vs_index holding all the rows.  `devices` may name a device more than once (several stripes on one
+ * GPU).  Calls on one handle must not overlap; different handles are independent. */
+typedef struct vs_sharded vs_sharded;
+VS_API int vs_sharded_create(const int *devices, size_t G, vs_sharded **out);
+VS_API void vs_sharded_release(vs_sharded *sh);
+VS_API size_t vs_sharded_rows(const vs_sharded *sh);
+VS_API size_t vs_sharded_shards(const vs_sharded *sh);
+VS_API size_t vs_sharded_shard_rows(const vs_sharded *sh, size_t shard);
+/* Replaces the loader side of server/search.go:241-243 for G devices: rows in primary-key order (row i has key i) with
+ * Embedding.CentroidID (database/model.go:16) as list_of_row; doc_ids NULL = the primary key is the document id. */
+VS_API int vs_sharded_build_assigned(vs_sharded *sh, const uint8_t *rows776, size_t n, size_t row_bytes, const uint64_t *doc_ids,
+                                     const uint32_t *list_of_row, const uint8_t *centroids776, size_t C);
+/* Replaces server/upload.go:239-279 on the striped store: the new rows take the next primary keys, each joins the list
+ * of its nearest centroid (upload.go:245) on the shard that owns its key.  assign_out (optional): int64[n]. */
+VS_API int vs_sharded_upload(vs_sharded *sh, const uint8_t *rows776, size_t n, size_t row_bytes, const uint64_t *doc_ids,
+                             int64_t *assign_out);
+/* Replaces server/search.go:202-273 for nq queries (host buffers in and out, like vs_search); one search at a time. */
+VS_API int vs_sharded_search(vs_sharded *sh, const uint8_t *queries776, size_t nq, size_t nprobe, size_t k, uint64_t *ids_out,
+                             float *sims_out, int32_t *counts_out);
+/* One search context over all the devices of a handle (a stream + scratch per device, merge buffers on device 0): what
+ * one `calculate` closure / goroutine holds (server/search.go:230; compute/cosine.go:60-66 for the single-device form).
+ * Searches through different contexts may overlap; uploads must not overlap searches. */
+typedef struct vs_sharded_ctx vs_sharded_ctx;
+VS_API int vs_sharded_ctx_create(vs_sharded *sh, vs_sharded_ctx **out);
+VS_API void vs_sharded_ctx_destroy(vs_sharded_ctx *sc);
+VS_API int vs_sharded_search_ctx(vs_sharded_ctx *sc, const uint8_t *queries776, size_t nq, size_t nprobe, size_t k, uint64_t *ids_out,
+                                 float *sims_out, int32_t *counts_out);
+
 /* Multi-GPU (row-striped shards): merge G gathered shard-local results per query into the global
  * top-k.  d_ids_in/d_sims_in [G][nq][k], d_counts_in [G][nq] device arrays. */
 VS_API int vs_topk_merge_dev(vs_ctx *ctx, const uint64_t *d_ids_in, const float *d_sims_in, const int32_t *d_counts_in,
