@@ -750,6 +750,65 @@ def other_configs(pkg, torch, ctx, ix, a, device, peaks):
     except Exception as e:  # noqa: BLE001
         out["brute_force_config1"] = {"error": repr(e)[:300]}
     try:
+        # prefTest() (main.go:247-286), the reference's only timing harness, through the plain `compute` API with host
+        # buffers in and out: 1000 noop rows (512-d, header -1/+1, uniform codes; noop/ai.go:47-64) -> two 500-row
+        # matrices; 1 warm-up + 10 timed MatrixCosineSimilarity calls with Clone() inside the timed region; then 50 x
+        # (QuantizeMatrixFloat32 + QuantizeMatrixFloat64) and 50 x (Dequantize...32 + ...64), each reported as total / 5
+        # like the reference's log lines.  The oracle (default-backend restatement, one thread) runs the same calls.
+        import oracle
+        rng = np.random.default_rng(7)
+        rows_p = np.empty((1000, 8 + 512), np.uint8)
+        rows_p[:, 0:4] = np.frombuffer(np.float32(-1).tobytes(), np.uint8)
+        rows_p[:, 4:8] = np.frombuffer(np.float32(1).tobytes(), np.uint8)
+        rows_p[:, 8:] = rng.integers(0, 256, (1000, 512), dtype=np.uint8)
+        m1, m2 = cp.NewMatrix(rows_p[:500]), cp.NewMatrix(rows_p[500:])
+        sim, done = cp.MatrixCosineSimilarity()
+        sim(m1.Clone(), m2.Clone())
+        t0 = time.perf_counter()
+        for _ in range(10):
+            _, nearest = sim(m1.Clone(), m2.Clone())
+        cos_s = time.perf_counter() - t0
+        done()
+        f32 = cp.DequantizeMatrixFloat32(rows_p)
+        f64 = cp.DequantizeMatrixFloat64(rows_p)
+        t0 = time.perf_counter()
+        for _ in range(50):
+            q32 = cp.QuantizeMatrixFloat32(f32)
+            q64 = cp.QuantizeMatrixFloat64(f64)
+        quant_s = (time.perf_counter() - t0) / 5
+        t0 = time.perf_counter()
+        for _ in range(50):
+            cp.DequantizeMatrixFloat32(rows_p)
+            cp.DequantizeMatrixFloat64(rows_p)
+        dequant_s = (time.perf_counter() - t0) / 5
+        t0 = time.perf_counter()
+        for _ in range(10):
+            _, nearest_o = oracle.argmax_MxN(rows_p[:500], rows_p[500:])
+        cos_o = time.perf_counter() - t0
+        of32, of64 = oracle.dequantize_matrix_f32(rows_p), oracle.dequantize_matrix_f64(rows_p)
+        t0 = time.perf_counter()
+        for _ in range(50):
+            o32 = oracle.quantize_matrix_f32(of32)
+            o64 = oracle.quantize_matrix_f64(of64)
+        quant_o = (time.perf_counter() - t0) / 5
+        t0 = time.perf_counter()
+        for _ in range(50):
+            oracle.dequantize_matrix_f32(rows_p)
+            oracle.dequantize_matrix_f64(rows_p)
+        dequant_o = (time.perf_counter() - t0) / 5
+        out["pref_test"] = {
+            "workload": "main.go:247-286 prefTest(): 10 x MatrixCosineSimilarity(500 x 512-d centroids, 500 x 512-d rows) with Clone() "
+                        "in the timed region; 50 x quantize f32+f64 of 1000 x 512 (/5); 50 x dequantize f32+f64 (/5); host buffers",
+            "cosine_10_calls_ms": round(cos_s * 1e3, 3), "quantization_ms": round(quant_s * 1e3, 3),
+            "dequantization_ms": round(dequant_s * 1e3, 3),
+            "cpu_oracle_one_thread": {"cosine_10_calls_ms": round(cos_o * 1e3, 3), "quantization_ms": round(quant_o * 1e3, 3),
+                                      "dequantization_ms": round(dequant_o * 1e3, 3)},
+            "parity_vs_oracle": bool((np.asarray(nearest) == nearest_o).all() and (q32 == o32).all() and (q64 == o64).all()
+                                     and (f32.view(np.uint32) == of32.view(np.uint32)).all()
+                                     and (f64.view(np.uint64) == of64.view(np.uint64)).all())}
+    except Exception as e:  # noqa: BLE001
+        out["pref_test"] = {"error": repr(e)[:300]}
+    try:
         # One query against every row of the store (nprobe = all lists): the streaming scan the single-query path is made
         # of, at a size where launch and merge latency no longer hide it.  776 B per row scored, device-timed.
         peak = float(peaks.get("hbm_gbs", 6650.0))

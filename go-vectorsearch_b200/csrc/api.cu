@@ -6,6 +6,7 @@
 #include <sys/stat.h>
 #include <unistd.h>
 
+#include <algorithm>
 #include <cerrno>
 #include <cstdarg>
 #include <cstdio>
@@ -1751,10 +1752,88 @@ static int search_host(vs_ctx *c, const vs_index *ix, const uint8_t *queries, si
     return VS_OK;
 }
 
+// Requests beyond what the fused top-k kernels hold (more than 128 probed lists without probing all of them, or more than
+// 128 hits: server/search.go:116-122 accepts any Centroids value and Count+Offset is unbounded by Offset).  Rare and
+// served for completeness, not speed: the exact float32 similarity of every centroid and of every row (vs_cosine_1xN's
+// kernels, bit-equal to compute/cosine.go:13-57) comes back to the host, which cuts the probe list (search.go:220-223),
+// walks the probed lists, sorts (similarity desc, id asc), keeps one hit per document and truncates (search.go:256-270).
+static int search_wide_host(vs_ctx *c, const vs_index *ix, const uint8_t *queries, size_t nq, size_t nprobe, size_t k,
+                            uint64_t *ids_out, float *sims_out, int32_t *counts_out) {
+    VS(search_check(c, ix));
+    if (!queries) return fail(VS_EINVAL, "queries is null");
+    if (nq == 0 || k == 0) return fail(VS_EINVAL, "nq == 0 or k == 0");
+    if (nprobe == 0) nprobe = 1;
+    const size_t n = ix->n, C = ix->C, rb = 8 + (size_t)ix->data->d;
+    const bool flat = nprobe >= C || !ix->centroids;
+    std::vector<uint64_t> off(C + 1, 0), ids;
+    if (!flat) CU(cudaMemcpy(off.data(), ix->list_off, (C + 1) * 8, cudaMemcpyDeviceToHost));
+    if (ix->doc_ids) {
+        ids.resize(n);
+        CU(cudaMemcpy(ids.data(), ix->doc_ids, n * 8, cudaMemcpyDeviceToHost));
+    }
+    std::vector<float> csims(C), rsims(n);
+    std::vector<uint32_t> order;
+    struct Hit {
+        uint32_t key;
+        uint64_t id;
+    };
+    std::vector<Hit> hits;
+    for (size_t q = 0; q < nq; q++) {
+        const uint8_t *qrow = queries + q * rb;
+        VS(vs_cosine_1xN(c, qrow, rb, ix->data, rsims.data()));
+        hits.clear();
+        auto take = [&](size_t lo, size_t hi) {
+            for (size_t r = lo; r < hi; r++) hits.push_back(Hit{f32_to_key(rsims[r]), ix->doc_ids ? ids[r] : ix->id_base + r});
+        };
+        if (flat) {
+            take(0, n);
+        } else {
+            VS(vs_cosine_1xN(c, qrow, rb, ix->centroids, csims.data()));
+            order.resize(C);
+            for (size_t i = 0; i < C; i++) order[i] = (uint32_t)i;
+            std::sort(order.begin(), order.end(), [&](uint32_t a, uint32_t b) {
+                const uint32_t ka = f32_to_key(csims[a]), kb = f32_to_key(csims[b]);
+                return ka > kb || (ka == kb && a < b);
+            });
+            for (size_t s = 0; s < nprobe; s++) take(off[order[s]], off[order[s] + 1]);
+        }
+        std::sort(hits.begin(), hits.end(), [](const Hit &a, const Hit &b) { return a.key > b.key || (a.key == b.key && a.id < b.id); });
+        size_t cnt = 0;
+        if (!ix->doc_ids) {  // ids are distinct
+            for (; cnt < k && cnt < hits.size(); cnt++) {
+                ids_out[q * k + cnt] = hits[cnt].id;
+                sims_out[q * k + cnt] = key_to_f32(hits[cnt].key);
+            }
+        } else {
+            std::vector<uint64_t> seen;  // (k is small next to the candidate list; sorted insert keeps the membership test cheap)
+            for (size_t i = 0; i < hits.size() && cnt < k; i++) {
+                auto it = std::lower_bound(seen.begin(), seen.end(), hits[i].id);
+                if (it != seen.end() && *it == hits[i].id) continue;
+                seen.insert(it, hits[i].id);
+                ids_out[q * k + cnt] = hits[i].id;
+                sims_out[q * k + cnt] = key_to_f32(hits[i].key);
+                cnt++;
+            }
+        }
+        counts_out[q] = (int32_t)cnt;
+    }
+    return VS_OK;
+}
+
 extern "C" int vs_search(vs_ctx *c, const vs_index *ix, const uint8_t *queries, size_t nq, size_t nprobe, size_t k,
                          uint64_t *ids_out, float *sims_out, int32_t *counts_out) {
     if (!ids_out || !sims_out || !counts_out) return fail(VS_EINVAL, "null output");
-    return search_host(c, ix, queries, nq, nprobe, k, ids_out, sims_out, counts_out, nullptr, nullptr, false);
+    if (ix && (k > 128 || (nprobe > 128 && nprobe < ix->C)))
+        return search_wide_host(c, ix, queries, nq, nprobe, k, ids_out, sims_out, counts_out);
+    // more queries than one launch takes: in turns of kMaxStageQueries
+    const size_t rb = ix ? 8 + (size_t)ix->data->d : 0;
+    for (size_t q0 = 0; q0 < nq || q0 == 0; q0 += kMaxStageQueries) {
+        const size_t m = nq - q0 < (size_t)kMaxStageQueries ? nq - q0 : (size_t)kMaxStageQueries;
+        VS(search_host(c, ix, queries ? queries + q0 * rb : nullptr, m, nprobe, k, ids_out + q0 * k, sims_out + q0 * k, counts_out + q0,
+                       nullptr, nullptr, false));
+        if (nq == 0) break;
+    }
+    return VS_OK;
 }
 
 extern "C" int vs_select_probes(vs_ctx *c, const vs_index *ix, const uint8_t *queries, size_t nq, size_t nprobe,

@@ -196,7 +196,11 @@ VS_API int vs_index_upload(vs_ctx *ctx, const vs_index *ix, const uint8_t *rows_
 /* Search (search.go:115-273 minus embedding/DB hops): nq query rows (row776, host), nprobe =
  * SearchRequest.Centroids (>= number of lists means "all"), k = Count+Offset.  Outputs (host):
  * ids_out[nq*k] document IDs, sims_out[nq*k] float32 similarities, counts_out[nq] valid entries.
- * Order: similarity desc (float32), then document ID asc; one entry per document (search.go:260-268). */
+ * Order: similarity desc (float32), then document ID asc; one entry per document (search.go:260-268), removed before the
+ * list is cut to k like the reference does (search.go:259-271).  Any nq (batches above 4096 run in turns), any nprobe and
+ * any k: up to 128 probed lists (or all of them) and up to 128 hits run in the fused kernels (one query: one launch,
+ * csrc/fused.cu; a batch: list-major, csrc/listmajor.cu); wider requests (search.go:116-122 accepts any Centroids value,
+ * and Count+Offset is unbounded by Offset) are served exactly through full similarity vectors and a host-side cut. */
 VS_API int vs_search(vs_ctx *ctx, const vs_index *ix, const uint8_t *queries_packed, size_t nq, size_t nprobe, size_t k,
               uint64_t *ids_out, float *sims_out, int32_t *counts_out);
 /* Brute force over a matrix (BASELINE config 1): same contract, ids = doc_ids[row] or row index. */

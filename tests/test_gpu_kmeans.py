@@ -104,3 +104,24 @@ def test_kmeans_row_blocks_relay_matches_one_device(vs, oracle, d, n, k, blocks)
         assert (f32_bits(d_means.cpu().numpy()) == f32_bits(means_o)).all()
         assert (cmat.ReadRows() == new_o).all() and conv == conv_o
         cent_o = new_o
+
+
+def test_kmeans_step_and_recenter_known_answers(vs):
+    """The hand-derived known answers of tests/golden/kat.json (plain Python IEEE arithmetic following the Go lines,
+    tests/golden/make_golden.py -- no oracle involved) through the CUDA path: one Lloyd iteration
+    (dnc/k_means.go:67-117) and recenterDbCentroid (dnc/dnc.go:417-449)."""
+    import json
+    import os
+    import struct
+    kat = json.load(open(os.path.join(os.path.dirname(__file__), "golden", "kat.json")))
+    c = kat["kmeans_step"]
+    cent = np.array(c["centroids"], np.uint8)
+    data = np.array(c["data"], np.uint8)
+    means = np.array(c["prev_means"], np.float32)
+    assign, counts, newc, conv = vs.dnc.KMeansStep(vs.compute.NewMatrix(data), cent, means)
+    assert assign.tolist() == c["assign"] and counts.tolist() == c["counts"], c["why"]
+    assert [[struct.pack(">f", v).hex() for v in m] for m in means] == c["means_f32"], c["why"]
+    assert newc.tolist() == c["new_centroids"] and conv == c["converged"], c["why"]
+    r = kat["recenter"]
+    rows = np.array(r["rows"], np.uint8)
+    assert vs.dnc.Recenter(vs.compute.NewMatrix(rows)).tolist() == r["expect"], r["why"]

@@ -419,3 +419,26 @@ def test_merge_removes_cross_shard_duplicates_before_the_cut(vs, oracle):
         assert int(out_counts[q]) == k
         assert got_ids[q].tolist() == [w[0] for w in want]
         assert got_sims[q].tolist() == [np.float32(w[1]) for w in want]
+
+
+# ---- requests beyond the fused kernels' capacities (server/search.go:116-122: any Centroids value, unbounded Offset) ----
+@pytest.mark.parametrize("nprobe,k", [(200, 10), (200, 200), (8, 300), (1000, 150)])
+def test_wide_requests(vs, oracle, nprobe, k):
+    """More than 128 probed lists (without probing all of them) and more than 128 hits per query."""
+    n, d, C = 20000, 256, 1000
+    rows, cent, lists, doc = _index_inputs(oracle, n, d, C, 91, docs_per=2)
+    ix = vs.ivf.Index.build_assigned(rows, doc, lists, cent)
+    qs = oracle.quantize_matrix_f32(unit_rows(3, d, 92))
+    _check(oracle, ix, qs, cent, rows, lists, doc, nprobe, k)
+
+
+def test_more_queries_than_one_launch_takes(vs, oracle):
+    n, d, C, nq = 6000, 128, 16, 4100
+    rows, cent, lists, doc = _index_inputs(oracle, n, d, C, 93)
+    ix = vs.ivf.Index.build_assigned(rows, doc, lists, cent)
+    qs = oracle.quantize_matrix_f32(unit_rows(nq, d, 94))
+    ids, sims, counts = ix.Search(qs, 4, 10)
+    for i in (0, 4095, 4096, 4099):
+        want_ids, want_sims = oracle.search(qs[i], cent, rows, lists, doc, 4, 10)
+        assert ids[i, :counts[i]].tolist() == want_ids.tolist()
+        assert (f32_bits(sims[i, :counts[i]]) == f32_bits(want_sims)).all()
