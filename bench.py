@@ -841,7 +841,7 @@ def other_configs(pkg, torch, ctx, ix, a, device, peaks):
             "workload": f"1 query x all {a.rows} rows ({a.rows * ROW_BYTES / 1e9:.2f} GB), top-{a.k}, device-resident, whole call "
                         f"(scan + merges + emit)",
             "ms_p50": round(ms, 4), "queries_per_s": round(1e3 / ms, 1),
-            "roofline": {"bound": "hbm", "kernel": "stage_kernel (flat scan + fused top-k)", "achieved": round(gbs, 1), "peak": peak,
+            "roofline": {"bound": "hbm", "kernel": "fused_search_kernel (flat scan through the TMA ring + top-k, one launch)", "achieved": round(gbs, 1), "peak": peak,
                          "unit": "GB/s", "frac": round(gbs / peak, 4), "bytes_per_launch": a.rows * ROW_BYTES, "launches_timed": len(times)},
             "matches_host_call": match}
         del one, qm

@@ -1721,33 +1721,37 @@ static int search_host(vs_ctx *c, const vs_index *ix, const uint8_t *queries, si
     float *d_psims = a.take<float>(nq * s.npe);
     VS(search_enqueue(c, ix, qv, nq, nullptr, s.npe, k, s.kpl1, s.kpl2, s.flat, false, s.b, d_ids, d_sims, d_counts, d_status,
                       stage1_only ? d_psims : nullptr, stage1_only));
-    VS(pinned_reserve(c, nq * 4));
-    uint32_t *h_status = static_cast<uint32_t *>(c->pinned);
-    CU(cudaMemcpyAsync(h_status, d_status, nq * 4, cudaMemcpyDeviceToHost, c->stream));
-    if (!stage1_only) {
-        CU(cudaMemcpyAsync(ids_out, d_ids, nq * k * 8, cudaMemcpyDeviceToHost, c->stream));
-        CU(cudaMemcpyAsync(sims_out, d_sims, nq * k * 4, cudaMemcpyDeviceToHost, c->stream));
-        CU(cudaMemcpyAsync(counts_out, d_counts, nq * 4, cudaMemcpyDeviceToHost, c->stream));
-    } else {
-        CU(cudaMemcpyAsync(probe_out, s.b.probe, nq * s.npe * 4, cudaMemcpyDeviceToHost, c->stream));
-        if (probe_sims_out) CU(cudaMemcpyAsync(probe_sims_out, d_psims, nq * s.npe * 4, cudaMemcpyDeviceToHost, c->stream));
-    }
-    CU(cudaStreamSynchronize(c->stream));
+    // hits, counts and status words sit next to each other in the arena: ONE copy into pinned memory brings them all back
+    // (four separate copies into pageable memory cost more than a single-query search itself)
+    const size_t span = stage1_only ? nq * 4 : (size_t)(reinterpret_cast<char *>(d_status + nq) - reinterpret_cast<char *>(d_ids));
+    VS(pinned_reserve(c, span + 16));
+    char *hp = static_cast<char *>(c->pinned);
+    uint32_t *h_status = stage1_only ? reinterpret_cast<uint32_t *>(hp)
+                                     : reinterpret_cast<uint32_t *>(hp + (reinterpret_cast<char *>(d_status) - reinterpret_cast<char *>(d_ids)));
+    auto fetch = [&]() -> int {
+        if (!stage1_only) {
+            CU(cudaMemcpyAsync(hp, d_ids, span, cudaMemcpyDeviceToHost, c->stream));
+        } else {
+            CU(cudaMemcpyAsync(h_status, d_status, nq * 4, cudaMemcpyDeviceToHost, c->stream));
+            CU(cudaMemcpyAsync(probe_out, s.b.probe, nq * s.npe * 4, cudaMemcpyDeviceToHost, c->stream));
+            if (probe_sims_out) CU(cudaMemcpyAsync(probe_sims_out, d_psims, nq * s.npe * 4, cudaMemcpyDeviceToHost, c->stream));
+        }
+        CU(cudaStreamSynchronize(c->stream));
+        return VS_OK;
+    };
+    VS(fetch());
     bool any = false;
     for (size_t i = 0; i < nq; i++) any |= (h_status[i] & (kStatusProbeAmbiguous | kStatusListAmbiguous)) != 0;
     if (any) {
         int nres = 0;
         VS(search_resolve_flagged(c, ix, qv, nq, h_status, s, k, d_ids, d_sims, d_counts, d_status,
                                   stage1_only ? d_psims : nullptr, stage1_only, &nres));
-        if (!stage1_only) {
-            CU(cudaMemcpyAsync(ids_out, d_ids, nq * k * 8, cudaMemcpyDeviceToHost, c->stream));
-            CU(cudaMemcpyAsync(sims_out, d_sims, nq * k * 4, cudaMemcpyDeviceToHost, c->stream));
-            CU(cudaMemcpyAsync(counts_out, d_counts, nq * 4, cudaMemcpyDeviceToHost, c->stream));
-        } else {
-            CU(cudaMemcpyAsync(probe_out, s.b.probe, nq * s.npe * 4, cudaMemcpyDeviceToHost, c->stream));
-            if (probe_sims_out) CU(cudaMemcpyAsync(probe_sims_out, d_psims, nq * s.npe * 4, cudaMemcpyDeviceToHost, c->stream));
-        }
-        CU(cudaStreamSynchronize(c->stream));
+        VS(fetch());
+    }
+    if (!stage1_only) {
+        memcpy(ids_out, hp, nq * k * 8);
+        memcpy(sims_out, hp + (reinterpret_cast<char *>(d_sims) - reinterpret_cast<char *>(d_ids)), nq * k * 4);
+        memcpy(counts_out, hp + (reinterpret_cast<char *>(d_counts) - reinterpret_cast<char *>(d_ids)), nq * 4);
     }
     return VS_OK;
 }
