@@ -34,10 +34,19 @@ class ComputeError(RuntimeError):
     """Any other backend failure (CUDA error, out of memory, unsupported size)."""
 
 
+VS_EFULL = -8
+
+
+class IndexFull(ComputeError):
+    """vs_index_append: a list (or the store) has no room for its new rows; the index is unchanged."""
+
+
 def _check(rc):
     if rc == VS_OK:
         return
     msg = _lib.last_error()
+    if rc == VS_EFULL:
+        raise IndexFull(msg)
     if rc == VS_EEMPTY:
         raise ComputePanic(msg)
     if rc == VS_EDIM:

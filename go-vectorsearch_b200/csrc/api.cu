@@ -864,12 +864,30 @@ extern "C" void vs_index_release(vs_index *ix) {
     if (ix->data) cudaSetDevice(ix->data->device);
     if (ix->doc_ids) cudaFree(ix->doc_ids);
     if (ix->list_off) cudaFree(ix->list_off);
+    if (ix->list_len && ix->list_len != ix->fill_cursor) cudaFree(ix->list_len);
     if (ix->fill_cursor) cudaFree(ix->fill_cursor);
     vs_matrix_release(ix->data);
     vs_matrix_release(ix->centroids);
     delete ix;
 }
-extern "C" size_t vs_index_rows(const vs_index *ix) { return ix ? ix->n : 0; }
+// rows present (an index with room to grow: rows placed so far; its capacity is vs_index_capacity)
+extern "C" size_t vs_index_rows(const vs_index *ix) { return !ix ? 0 : ix->fill_cursor ? ix->filled : ix->n; }
+extern "C" size_t vs_index_capacity(const vs_index *ix) { return ix ? ix->n : 0; }
+// holes between the lists: whole-store scans (flat, GEMM batch) would score rows that are not there
+static bool index_has_holes(const vs_index *ix) { return ix->fill_cursor && ix->filled != ix->n; }
+
+__global__ void list_lens_kernel(const uint64_t *off, size_t C, uint64_t *len) {
+    const size_t l = blockIdx.x * (size_t)blockDim.x + threadIdx.x;
+    if (l < C) len[l] = off[l + 1] - off[l];
+}
+// list_len of an index built in one piece (lists back to back): the differences of list_off
+static cudaError_t index_make_lens(vs_ctx *c, vs_index *ix) {
+    if (ix->C == 0) return cudaSuccess;
+    cudaError_t e = cudaMalloc(&ix->list_len, ix->C * 8);
+    if (e != cudaSuccess) return e;
+    list_lens_kernel<<<(unsigned)((ix->C + 255) / 256), 256, 0, c->stream>>>(ix->list_off, ix->C, ix->list_len);
+    return cudaGetLastError();
+}
 extern "C" size_t vs_index_lists(const vs_index *ix) { return ix ? ix->C : 0; }
 extern "C" size_t vs_index_cols(const vs_index *ix) { return ix && ix->centroids ? (size_t)ix->centroids->d : 0; }
 
@@ -877,6 +895,15 @@ extern "C" int vs_index_list_offsets(vs_ctx *c, const vs_index *ix, uint64_t *ou
     VS(need_dev());
     if (!c || !ix || !out) return fail(VS_EINVAL, "null argument");
     CU(cudaMemcpyAsync(out, ix->list_off, (ix->C + 1) * 8, cudaMemcpyDeviceToHost, c->stream));
+    CU(cudaStreamSynchronize(c->stream));
+    return VS_OK;
+}
+
+extern "C" int vs_index_list_lengths(vs_ctx *c, const vs_index *ix, uint64_t *out) {
+    VS(need_dev());
+    if (!c || !ix || !out) return fail(VS_EINVAL, "null argument");
+    if (ix->C == 0) return VS_OK;
+    CU(cudaMemcpyAsync(out, ix->list_len, ix->C * 8, cudaMemcpyDeviceToHost, c->stream));
     CU(cudaStreamSynchronize(c->stream));
     return VS_OK;
 }
@@ -931,6 +958,7 @@ extern "C" int vs_index_build_dev(vs_ctx *c, const vs_matrix *data, const int32_
             lower_bound_kernel<<<(unsigned)((C + 1 + 255) / 256), 256, 0, c->stream>>>(d_keys_sorted, n, ix->list_off, nullptr, C);
             e = cudaGetLastError();
         }
+        if (e == cudaSuccess) e = index_make_lens(c, ix);
         if (e == cudaSuccess) e = cudaStreamSynchronize(c->stream);
         if (e != cudaSuccess) rc = fail(VS_ECUDA, "index build: %s", cudaGetErrorString(e));
         c->launches += 2;
@@ -996,6 +1024,7 @@ extern "C" int vs_index_build(vs_ctx *c, const uint8_t *rows, size_t n, size_t r
             e = cudaMalloc(&ix->doc_ids, n * 8 + 8);
             if (e == cudaSuccess) e = cudaMemcpyAsync(ix->doc_ids, doc_ids, n * 8, cudaMemcpyHostToDevice, c->stream);
         }
+        if (e == cudaSuccess) e = index_make_lens(c, ix);
         if (e == cudaSuccess) e = cudaStreamSynchronize(c->stream);
         if (e != cudaSuccess) rc = fail(VS_ECUDA, "index upload: %s", cudaGetErrorString(e));
     }
@@ -1033,6 +1062,7 @@ extern "C" int vs_index_create_empty(vs_ctx *c, const vs_matrix *centroids, cons
         if (e == cudaSuccess) e = cudaMalloc(&ix->fill_cursor, (C + 1) * 8);  // [C] cursors + the overflow flag
         if (e == cudaSuccess) e = cudaMemcpyAsync(ix->list_off, off.data(), (C + 1) * 8, cudaMemcpyHostToDevice, c->stream);
         if (e == cudaSuccess) e = cudaMemsetAsync(ix->fill_cursor, 0, (C + 1) * 8, c->stream);
+        ix->list_len = ix->fill_cursor;
         if (e == cudaSuccess) e = cudaStreamSynchronize(c->stream);
         if (e != cudaSuccess) rc = fail(VS_ECUDA, "empty index of %zu rows: %s", n, cudaGetErrorString(e));
     }
@@ -1156,7 +1186,8 @@ static int index_upload_core(vs_ctx *c, const vs_index *ix, const vs_matrix *nm,
     CU(cudaGetLastError());
     merge_order_kernel<<<g_sm_count * 4, 256, 0, c->stream>>>(ix->list_off, d_add_off, nx->list_off, d_add_order, C, n_total, d_order);
     CU(cudaGetLastError());
-    c->launches += 3;
+    CU(index_make_lens(c, nx));
+    c->launches += 4;
     if (doc_ids) CU(cudaMemcpyAsync(d_new_ids, doc_ids, n * 8, cudaMemcpyHostToDevice, c->stream));
     LAUNCH(c, launch_merge_rows(ix->data->view(), ix->doc_ids, ix->id_base, nm->view(), d_new_ids, ix->id_base + ix->n, d_order, n_total,
                                 nx->data->codes, nx->data->hdr, nx->data->sums, nx->doc_ids, c->stream));
@@ -1175,7 +1206,7 @@ extern "C" int vs_index_upload(vs_ctx *c, const vs_index *ix, const uint8_t *row
     VS(need_dev());
     if (!c || !ix || !rows || !out) return fail(VS_EINVAL, "null argument");
     VS(check_rows(n, row_bytes));
-    if (ix->fill_cursor && ix->filled != ix->n) return fail(VS_EINVAL, "the index is still loading");
+    if (index_has_holes(ix)) return fail(VS_EINVAL, "the index has room to grow: vs_index_append adds rows in place");
     if (ix->C == 0) return fail(VS_EINVAL, "the index has no centroids");  // compute.go:26: NewMatrix panics on 0 rows
     if ((size_t)ix->centroids->d != row_bytes - 8)                          // cosine.go:77-79
         return fail(VS_EDIM, "matrix/matrix column size does not match: %d != %zu", ix->centroids->d, row_bytes - 8);
@@ -1203,6 +1234,138 @@ extern "C" int vs_index_upload(vs_ctx *c, const vs_index *ix, const uint8_t *row
     }
     *out = nx;
     return VS_OK;
+}
+
+// ---- Upload in place: lists with room to grow ---------------------------------------------------------------------
+// vs_index_upload copies the whole store for every batch of new rows.  A service that ingests continuously keeps the
+// store with slack behind every list instead (vs_index_with_room), appends new rows where their lists end
+// (vs_index_append: the loader's scatter, preceded by upload.go:245's assignment) and copies only when a list is full.
+__global__ void copy_lists_kernel(MatView src, const uint64_t *__restrict__ src_ids, uint64_t id_base,
+                                  const uint64_t *__restrict__ src_off, const uint64_t *__restrict__ src_len,
+                                  const uint64_t *__restrict__ dst_off, size_t C, uint8_t *__restrict__ codes,
+                                  float2 *__restrict__ hdr, uint2 *__restrict__ sums, uint64_t *__restrict__ ids) {
+    const size_t words_per_row = (size_t)src.d_pad >> 4;
+    for (size_t l = blockIdx.y; l < C; l += gridDim.y) {
+        const uint64_t s0 = src_off[l], d0 = dst_off[l], len = src_len[l];
+        // the slice of this list that block x of the row copies
+        const uint4 *sp = reinterpret_cast<const uint4 *>(src.codes + s0 * (size_t)src.d_pad);
+        uint4 *dp = reinterpret_cast<uint4 *>(codes + d0 * (size_t)src.d_pad);
+        const size_t words = len * words_per_row;
+        for (size_t w = blockIdx.x * (size_t)blockDim.x + threadIdx.x; w < words; w += (size_t)gridDim.x * blockDim.x) dp[w] = sp[w];
+        for (size_t r = blockIdx.x * (size_t)blockDim.x + threadIdx.x; r < len; r += (size_t)gridDim.x * blockDim.x) {
+            hdr[d0 + r] = src.hdr[s0 + r];
+            sums[d0 + r] = src.sums[s0 + r];
+            ids[d0 + r] = src_ids ? src_ids[s0 + r] : id_base + s0 + r;
+        }
+    }
+}
+
+extern "C" int vs_index_with_room(vs_ctx *c, const vs_index *ix, size_t percent, size_t min_rows, vs_index **out) {
+    VS(need_dev());
+    if (!c || !ix || !out) return fail(VS_EINVAL, "null argument");
+    if (!ix->centroids || ix->C == 0) return fail(VS_EINVAL, "the index has no centroids");
+    const size_t C = ix->C;
+    std::vector<uint64_t> len(C), cap(C);
+    CU(cudaMemcpyAsync(len.data(), ix->list_len, C * 8, cudaMemcpyDeviceToHost, c->stream));
+    CU(cudaStreamSynchronize(c->stream));
+    size_t live = 0;
+    for (size_t l = 0; l < C; l++) {
+        const size_t extra = len[l] * percent / 100;
+        cap[l] = len[l] + (extra > min_rows ? extra : min_rows);
+        live += len[l];
+    }
+    vs_index *nx = nullptr;
+    VS(vs_index_create_empty(c, ix->centroids, cap.data(), &nx));
+    nx->id_base = ix->id_base;
+    nx->implicit_ids = ix->implicit_ids || !ix->doc_ids;
+    if (nx->n > 0x3FFFFFFFull) {
+        vs_index_release(nx);
+        return fail(VS_ERANGE, "a device store holds < 2^30 rows per GPU");
+    }
+    const dim3 grid(8, (unsigned)(C < 4096 ? C : 4096));
+    copy_lists_kernel<<<grid, 256, 0, c->stream>>>(ix->data->view(), ix->doc_ids, ix->id_base, ix->list_off, ix->list_len, nx->list_off, C,
+                                                   nx->data->codes, nx->data->hdr, nx->data->sums, nx->doc_ids);
+    cudaError_t e = cudaGetLastError();
+    if (e == cudaSuccess) e = cudaMemcpyAsync(nx->fill_cursor, ix->list_len, C * 8, cudaMemcpyDeviceToDevice, c->stream);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(c->stream);
+    c->launches++;
+    if (e != cudaSuccess) {
+        vs_index_release(nx);
+        return fail(VS_ECUDA, "index copy: %s", cudaGetErrorString(e));
+    }
+    nx->filled = live;
+    *out = nx;
+    return VS_OK;
+}
+
+// flag = 1 when some list cannot take the rows this chunk brings it
+__global__ void lists_fit_kernel(const uint32_t *chunk_off, const uint64_t *list_off, const uint64_t *cursor, size_t C, unsigned int *flag) {
+    const size_t l = blockIdx.x * (size_t)blockDim.x + threadIdx.x;
+    if (l < C && cursor[l] + (chunk_off[l + 1] - chunk_off[l]) > list_off[l + 1] - list_off[l]) *flag = 1u;
+}
+
+extern "C" int vs_index_append(vs_ctx *c, vs_index *ix, const uint8_t *rows, size_t n, size_t row_bytes, const uint64_t *doc_ids,
+                               int64_t *assign_out) {
+    VS(need_dev());
+    if (!c || !ix || !rows) return fail(VS_EINVAL, "null argument");
+    VS(check_rows(n, row_bytes));
+    if (!ix->fill_cursor) return fail(VS_EFULL, "the index was built in one piece: no room to grow (see vs_index_with_room)");
+    if (ix->C == 0 || !ix->centroids) return fail(VS_EINVAL, "the index has no centroids");
+    if ((size_t)ix->centroids->d != row_bytes - 8)  // cosine.go:77-79
+        return fail(VS_EDIM, "matrix/matrix column size does not match: %d != %zu", ix->centroids->d, row_bytes - 8);
+    if (!ix->implicit_ids && !doc_ids) return fail(VS_EINVAL, "the index holds explicit document ids: doc_ids is required");
+    if (ix->filled + n > ix->n) return fail(VS_EFULL, "%zu rows do not fit: %zu of %zu places taken", n, ix->filled, ix->n);
+    const size_t C = ix->C, d = (size_t)ix->centroids->d;
+    vs_matrix *nm = nullptr;
+    VS(vs_matrix_create(c, rows, n, row_bytes, &nm));
+    auto body = [&]() -> int {
+        const size_t sort_ws = sort_rows_ws_bytes(n);
+        Arena a(c);
+        VS(a.reserve(argmax_bytes(C, n, d) + 3 * Arena::pad(n * 4) + sort_ws + Arena::pad((C + 1) * 4) + Arena::pad(n * 8) + 4096));
+        int32_t *d_assign = a.take<int32_t>(n);
+        uint32_t *d_order = a.take<uint32_t>(n);
+        uint32_t *d_keys_sorted = a.take<uint32_t>(n);
+        char *ws = a.take<char>(sort_ws);
+        uint32_t *d_chunk_off = a.take<uint32_t>(C + 1);
+        uint64_t *d_new_ids = doc_ids ? a.take<uint64_t>(n) : nullptr;
+        unsigned int *d_flag = a.take<unsigned int>(16);
+        unsigned int *d_overflow = reinterpret_cast<unsigned int *>(ix->fill_cursor + C);
+        // upload.go:245: nearest centroid of every new row, lowest index on ties
+        VS(argmax_dev(c, a, ix->centroids->view(), nm->view(), d_assign, nullptr));
+        VS(sort_rows_by_key(c, reinterpret_cast<const uint32_t *>(d_assign), n, bits_for(C), d_order, d_keys_sorted, ws, sort_ws));
+        const unsigned cb = (unsigned)((C + 1 + 255) / 256);
+        lower_bound_kernel<<<cb, 256, 0, c->stream>>>(d_keys_sorted, n, nullptr, d_chunk_off, C);
+        CU(cudaGetLastError());
+        CU(cudaMemsetAsync(d_flag, 0, 4, c->stream));
+        lists_fit_kernel<<<cb, 256, 0, c->stream>>>(d_chunk_off, ix->list_off, ix->fill_cursor, C, d_flag);
+        CU(cudaGetLastError());
+        c->launches += 2;
+        VS(pinned_reserve(c, 64));
+        unsigned int *h = static_cast<unsigned int *>(c->pinned);
+        CU(cudaMemcpyAsync(h, d_flag, 4, cudaMemcpyDeviceToHost, c->stream));
+        std::vector<int32_t> tmp;
+        if (assign_out) {
+            tmp.resize(n);
+            CU(cudaMemcpyAsync(tmp.data(), d_assign, n * 4, cudaMemcpyDeviceToHost, c->stream));
+        }
+        if (doc_ids) CU(cudaMemcpyAsync(d_new_ids, doc_ids, n * 8, cudaMemcpyHostToDevice, c->stream));
+        CU(cudaStreamSynchronize(c->stream));
+        if (h[0] != 0) return fail(VS_EFULL, "a list has no room for its new rows (the index is unchanged)");
+        for (size_t i = 0; i < tmp.size(); i++) assign_out[i] = tmp[i];
+        LAUNCH(c, launch_scatter_rows(nm->view(), d_order, d_keys_sorted, d_chunk_off, ix->list_off, ix->fill_cursor, ix->data->codes,
+                                      ix->data->hdr, ix->data->sums, d_new_ids, ix->id_base + ix->filled, ix->doc_ids, d_overflow, c->stream));
+        advance_cursor_kernel<<<cb, 256, 0, c->stream>>>(d_chunk_off, C, ix->fill_cursor);
+        CU(cudaGetLastError());
+        c->launches++;
+        CU(cudaStreamSynchronize(c->stream));
+        ix->filled += n;
+        if (doc_ids) ix->implicit_ids = false;
+        return VS_OK;
+    };
+    const int rc = body();
+    if (rc != VS_OK) cudaStreamSynchronize(c->stream);
+    vs_matrix_release(nm);
+    return rc;
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -1327,7 +1490,7 @@ static size_t search_bytes(size_t nq, size_t npe, int kpl1, int kpl2, int grid, 
 // selection).  A query the filter could not answer (unusable header, fewer than npe centroids above its threshold) gets
 // a valid placeholder list and the ambiguous bit: the caller's literal path redoes it.
 __global__ void probe_from_topk_kernel(const uint64_t *ids, const float *sims, const int32_t *counts, const uint32_t *gstatus, int npe,
-                                       uint32_t *out_probe, float *out_sims, uint32_t *out_qtiles, const uint64_t *list_off,
+                                       uint32_t *out_probe, float *out_sims, uint32_t *out_qtiles, const uint64_t *list_len,
                                        uint32_t tile_rows, uint32_t *out_status) {
     __shared__ uint32_t s_tiles;
     const uint32_t q = blockIdx.x;
@@ -1339,7 +1502,7 @@ __global__ void probe_from_topk_kernel(const uint64_t *ids, const float *sims, c
         const uint32_t L = ok ? (uint32_t)ids[(size_t)q * npe + r] : (uint32_t)r;
         out_probe[(size_t)q * npe + r] = L;
         if (out_sims) out_sims[(size_t)q * npe + r] = ok ? sims[(size_t)q * npe + r] : 0.0f;
-        mytiles += (uint32_t)((list_off[L + 1] - list_off[L] + tile_rows - 1) / tile_rows);
+        mytiles += (uint32_t)((list_len[L] + tile_rows - 1) / tile_rows);
     }
     for (int o = 16; o > 0; o >>= 1) mytiles += __shfl_xor_sync(0xFFFFFFFFu, mytiles, o);
     if ((threadIdx.x & 31) == 0 && mytiles) atomicAdd(&s_tiles, mytiles);
@@ -1373,6 +1536,7 @@ static int fused_enqueue(vs_ctx *c, const vs_index *ix, const MatView &qv, size_
     if (!flat) {
         p.cent = ix->centroids->view();
         p.list_off = ix->list_off;
+        p.list_len = ix->list_len;
         p.npe = (int)npe;
     } else {
         p.npe = 0;
@@ -1425,13 +1589,13 @@ static int search_enqueue(vs_ctx *c, const vs_index *ix, const MatView &qv, size
         CU(gemm_enqueue_select(cent, nullptr, 0, true, qv, b.gp, gb, (int)npe, b.gp_ids, b.gp_sims, b.gp_counts, b.gp_status,
                                c->d_fix_counter, g_sm_count, c->stream, &c->launches));
         probe_from_topk_kernel<<<(unsigned)qv.n, 128, 0, c->stream>>>(b.gp_ids, b.gp_sims, b.gp_counts, b.gp_status, (int)npe, b.probe,
-                                                                     d_probe_sims, b.qtiles, ix->list_off, tr2, d_status);
+                                                                     d_probe_sims, b.qtiles, ix->list_len, tr2, d_status);
         c->launches++;
         if (stage1_only) return VS_OK;
     } else if (!flat && !exact && !d_select && b.probe_keys && nq_launch == qv.n) {
         // a batch: score every (query, centroid) pair with the table read once, then select per query (probe.cu)
         LAUNCH(c, launch_probe_batch(ix->centroids->view(), qv, (int)npe, b.probe_keys, b.flag_cnt, b.flag_list, probe_flag_cap(ix->C), b.cand_keys, b.cand_ids, b.probe,
-                                     d_probe_sims, b.qtiles, ix->list_off, tr2, d_status, kStatusProbeAmbiguous, 1, c->d_fix_counter,
+                                     d_probe_sims, b.qtiles, ix->list_len, tr2, d_status, kStatusProbeAmbiguous, 1, c->d_fix_counter,
                                      g_sm_count, c->stream));
         c->launches++;
         if (stage1_only) return VS_OK;
@@ -1452,7 +1616,7 @@ static int search_enqueue(vs_ctx *c, const vs_index *ix, const MatView &qv, size
         p.out_probe = b.probe;
         p.out_sims = d_probe_sims;
         p.out_qtiles = b.qtiles;
-        p.next_list_off = ix->list_off;
+        p.next_list_len = ix->list_len;
         p.next_tile_rows = tr2;
         p.status_bit = kStatusProbeAmbiguous;
         p.status_init = 1;
@@ -1473,7 +1637,7 @@ static int search_enqueue(vs_ctx *c, const vs_index *ix, const MatView &qv, size
         lp.queries = qv;
         lp.k = (int)k;
         lp.pub = fused_pub((int)k, 1);
-        CU(lm_enqueue_prepare(lp, b.probe, (uint32_t)qv.n, (uint32_t)npe, (uint32_t)ix->C, ix->list_off, b.lm_count, b.lm_pair_off,
+        CU(lm_enqueue_prepare(lp, b.probe, (uint32_t)qv.n, (uint32_t)npe, (uint32_t)ix->C, ix->list_off, ix->list_len, b.lm_count, b.lm_pair_off,
                               b.lm_items_cap, c->stream, &c->launches));
         {
             // exact top k of the first 512 rows of every query's nearest list (query-major kernel, first probe only): its k-th
@@ -1491,6 +1655,7 @@ static int search_enqueue(vs_ctx *c, const vs_index *ix, const MatView &qv, size
             sp.seg_list = b.probe;
             sp.seg_stride = (int)npe;
             sp.list_off = ix->list_off;
+            sp.list_len = ix->list_len;
             sp.nseg = 1;
             sp.seg_cap = 512;
             sp.qtiles = b.qtiles;  // (tiles of all npe lists: an over-estimate only spreads the same work over fewer blocks)
@@ -1528,6 +1693,7 @@ static int search_enqueue(vs_ctx *c, const vs_index *ix, const MatView &qv, size
         p.seg_list = b.probe;
         p.seg_stride = (int)npe;
         p.list_off = ix->list_off;
+        p.list_len = ix->list_len;
         p.nseg = (int)npe;
         p.qtiles = b.qtiles;
         p.uniform_tiles = 0;
@@ -1566,12 +1732,16 @@ static int search_setup(vs_ctx *c, Arena &a, const vs_index *ix, size_t nq, size
     if (k == 0) return fail(VS_EINVAL, "k == 0");
     if (ix->n > 0x3FFFFFFFull) return fail(VS_ERANGE, "a device store holds < 2^30 rows per GPU");
     if (nprobe == 0) nprobe = 1;  // search.go:118-119
-    s->flat = nprobe >= ix->C && !rank_all;  // rank_all: stage 1 only, the caller wants the ranked list itself
+    // rank_all: stage 1 only, the caller wants the ranked list itself.  A store with holes between its lists is never
+    // scanned as one piece: every list is probed instead (same rows, same result).
+    s->flat = nprobe >= ix->C && !rank_all && !index_has_holes(ix);
     s->npe = nprobe >= ix->C ? ix->C : nprobe;
     s->kpl2 = kpl_for(k);
     s->kpl1 = s->flat ? 1 : kpl_for(s->npe);
     if (!s->kpl2) return fail(VS_ERANGE, "k=%zu: at most 128 hits (Count+Offset) per query", k);
-    if (!s->kpl1) return fail(VS_ERANGE, "nprobe=%zu: at most 128 probed lists unless nprobe >= number of lists", nprobe);
+    if (!s->kpl1)
+        return fail(VS_ERANGE, "nprobe=%zu: at most 128 probed lists unless nprobe >= number of lists%s", nprobe,
+                    index_has_holes(ix) ? " (and the lists are back to back: this index has room to grow; vs_search serves it)" : "");
     VS(search_plan(ix, nq, s->npe, s->flat, &s->b));
     VS(a.reserve(a.off + extra_bytes + search_bytes(nq, s->npe, s->kpl1, s->kpl2, s->b.grid, ix->data->d, ix->C) +
                  (use_probe_gemm(ix, nq, s->npe, s->flat) ? probe_gemm_bytes(ix, nq, s->npe)
@@ -1651,8 +1821,6 @@ static int search_resolve_flagged(vs_ctx *c, const vs_index *ix, const MatView &
 static int search_check(vs_ctx *c, const vs_index *ix) {
     VS(need_dev());
     if (!c || !ix) return fail(VS_EINVAL, "null argument");
-    if (ix->fill_cursor && ix->filled != ix->n)
-        return fail(VS_EINVAL, "the index is still loading: %zu of %zu rows placed", ix->filled, ix->n);
     return VS_OK;
 }
 
@@ -1703,7 +1871,7 @@ static int search_host(vs_ctx *c, const vs_index *ix, const uint8_t *queries, si
     VS(search_check(c, ix));
     if (!queries) return fail(VS_EINVAL, "queries is null");
     // a query batch over the whole store is a dense contraction: tensor cores (gemm.cu) instead of nq scans
-    if (!stage1_only && nprobe >= ix->C && nq >= kGemmMinQueries && ix->n >= kGemmMinRows && k <= 128 &&
+    if (!stage1_only && nprobe >= ix->C && nq >= kGemmMinQueries && ix->n >= kGemmMinRows && k <= 128 && !index_has_holes(ix) &&
         gemm_supported(ix->data->view(), nq))
         return gemm_search_host(c, ix, queries, nq, k, ids_out, sims_out, counts_out);
     const size_t row_bytes = 8 + (size_t)ix->data->d;
@@ -1768,9 +1936,13 @@ static int search_wide_host(vs_ctx *c, const vs_index *ix, const uint8_t *querie
     if (nq == 0 || k == 0) return fail(VS_EINVAL, "nq == 0 or k == 0");
     if (nprobe == 0) nprobe = 1;
     const size_t n = ix->n, C = ix->C, rb = 8 + (size_t)ix->data->d;
-    const bool flat = nprobe >= C || !ix->centroids;
-    std::vector<uint64_t> off(C + 1, 0), ids;
-    if (!flat) CU(cudaMemcpy(off.data(), ix->list_off, (C + 1) * 8, cudaMemcpyDeviceToHost));
+    const bool flat = (nprobe >= C && !index_has_holes(ix)) || !ix->centroids;
+    if (nprobe > C) nprobe = C;
+    std::vector<uint64_t> off(C + 1, 0), len(C, 0), ids;
+    if (!flat) {
+        CU(cudaMemcpy(off.data(), ix->list_off, (C + 1) * 8, cudaMemcpyDeviceToHost));
+        CU(cudaMemcpy(len.data(), ix->list_len, C * 8, cudaMemcpyDeviceToHost));
+    }
     if (ix->doc_ids) {
         ids.resize(n);
         CU(cudaMemcpy(ids.data(), ix->doc_ids, n * 8, cudaMemcpyDeviceToHost));
@@ -1799,7 +1971,7 @@ static int search_wide_host(vs_ctx *c, const vs_index *ix, const uint8_t *querie
                 const uint32_t ka = f32_to_key(csims[a]), kb = f32_to_key(csims[b]);
                 return ka > kb || (ka == kb && a < b);
             });
-            for (size_t s = 0; s < nprobe; s++) take(off[order[s]], off[order[s] + 1]);
+            for (size_t s = 0; s < nprobe; s++) take(off[order[s]], off[order[s]] + len[order[s]]);
         }
         std::sort(hits.begin(), hits.end(), [](const Hit &a, const Hit &b) { return a.key > b.key || (a.key == b.key && a.id < b.id); });
         size_t cnt = 0;
@@ -1827,7 +1999,7 @@ static int search_wide_host(vs_ctx *c, const vs_index *ix, const uint8_t *querie
 extern "C" int vs_search(vs_ctx *c, const vs_index *ix, const uint8_t *queries, size_t nq, size_t nprobe, size_t k,
                          uint64_t *ids_out, float *sims_out, int32_t *counts_out) {
     if (!ids_out || !sims_out || !counts_out) return fail(VS_EINVAL, "null output");
-    if (ix && (k > 128 || (nprobe > 128 && nprobe < ix->C)))
+    if (ix && (k > 128 || (nprobe > 128 && (nprobe < ix->C || (index_has_holes(ix) && ix->C > 128)))))
         return search_wide_host(c, ix, queries, nq, nprobe, k, ids_out, sims_out, counts_out);
     // more queries than one launch takes: in turns of kMaxStageQueries
     const size_t rb = ix ? 8 + (size_t)ix->data->d : 0;
@@ -2001,6 +2173,7 @@ extern "C" int vs_search_batch_dev(vs_ctx *c, const vs_matrix *m, const uint64_t
 extern "C" int vs_index_search_batch_dev(vs_ctx *c, const vs_index *ix, const vs_matrix *queries, size_t k, uint64_t *d_ids,
                                          float *d_sims, int32_t *d_counts, uint64_t *stats_out) {
     VS(search_check(c, ix));
+    if (index_has_holes(ix)) return fail(VS_EINVAL, "the index has room to grow: its store is not one piece (see vs_index_append)");
     return gemm_search_dev(c, ix, queries, k, d_ids, d_sims, d_counts, stats_out);
 }
 

@@ -200,7 +200,7 @@ fused_search_kernel(const FusedParams p) {
             t.h = p.cent.hdr[t.ci];
             t.sums = p.cent.sums[t.ci];
             t.l0 = __ldg(p.list_off + t.ci);
-            t.l1 = __ldg(p.list_off + t.ci + 1);
+            t.l1 = t.l0 + __ldg(p.list_len + t.ci);
         }
         t.dot = tile_dots<G, CPL>(p.cent.codes, (size_t)crow0, cn, d_pad, qreg, lane, iters);
         return t;

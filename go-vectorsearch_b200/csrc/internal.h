@@ -54,10 +54,13 @@ struct vs_index {
     uint64_t *doc_ids = nullptr;     // [n] device (may be null -> id = id_base + row)
     uint64_t id_base = 0;
     bool implicit_ids = false;       // built without document ids: rows are numbered id_base + primary-key order
-    uint64_t *list_off = nullptr;    // [C+1] device
+    uint64_t *list_off = nullptr;    // [C+1] device: where every list starts (and the capacity boundary of the one before)
+    uint64_t *list_len = nullptr;    // [C] device: rows every list holds; list_off[l] + list_len[l] <= list_off[l+1].  The
+                                     // streaming loader's cursor array when there is one (fill_cursor), else owned
     size_t n = 0, C = 0;
-    // streaming load (vs_index_create_empty / vs_index_fill*): rows placed so far per list (device, [C] + overflow flag) and
-    // in total; null once the index was built in one piece.  Searches are refused until filled == n.
+    // Lists with room to grow (vs_index_create_empty / vs_index_fill* / vs_index_append): n is the CAPACITY in rows, filled the
+    // rows placed so far, fill_cursor the rows placed per list (device, [C] + overflow flag); null for an index built in one
+    // piece (filled unused, no holes).  While filled < n the store has holes between the lists and searches go by lists only.
     uint64_t *fill_cursor = nullptr;
     size_t filled = 0;
 };
@@ -81,7 +84,8 @@ struct StageParams {
     // segments
     const uint32_t *seg_list;     // [q][seg_stride] list ids, or null = single segment
     int seg_stride;
-    const uint64_t *list_off;     // CSR offsets when seg_list != null
+    const uint64_t *list_off;     // list starts when seg_list != null
+    const uint64_t *list_len;     // rows per list
     int nseg;
     uint64_t single_start, single_count;
     uint32_t seg_cap;             // when non-zero: at most this many rows of every segment are scanned (a sample)
@@ -100,7 +104,7 @@ struct StageParams {
     int32_t *out_counts;          // mode 0: [q]
     uint32_t *out_probe;          // mode 1: [q][k]
     uint32_t *out_qtiles;         // mode 1 (optional): [q] tiles the next stage will scan for this query
-    const uint64_t *next_list_off;  // CSR of the store scanned by the next stage (for out_qtiles)
+    const uint64_t *next_list_len;  // rows per list of the store scanned by the next stage (for out_qtiles)
     uint32_t next_tile_rows;
     unsigned long long *trace;    // optional [gridDim.x][8] globaltimer phase stamps (profiling aid)
     unsigned long long *fix_counter;  // device counter: candidates re-scored with literal arithmetic in-kernel
@@ -147,7 +151,8 @@ struct FusedParams {
     const uint64_t *ids;       // per-row document id, or null -> id_base + row (distinct: no de-duplication needed)
     uint64_t id_base;
     MatView cent;              // centroid table (npe > 0)
-    const uint64_t *list_off;  // CSR of the lists (npe > 0)
+    const uint64_t *list_off;  // list starts (npe > 0)
+    const uint64_t *list_len;  // rows per list
     MatView query;             // one row
     int npe;                   // lists to probe (< number of centroids, <= kMaxSeg); 0 = flat scan of [flat_start, +flat_count)
     uint64_t flat_start, flat_count;
@@ -197,7 +202,8 @@ constexpr int kLmGbufCap = 4096;   // candidates per query the list-major scan m
 bool lm_supported(int d_pad, int k);
 size_t lm_items_cap(size_t n_rows, size_t nq, size_t npe);
 cudaError_t lm_enqueue_prepare(const LmParams &p, const uint32_t *probe, uint32_t nq, uint32_t npe, uint32_t C,
-                               const uint64_t *list_off, uint32_t *count, uint32_t *pair_off, uint32_t items_cap, cudaStream_t st,
+                               const uint64_t *list_off, const uint64_t *list_len, uint32_t *count, uint32_t *pair_off,
+                               uint32_t items_cap, cudaStream_t st,
                                uint64_t *launches);
 cudaError_t lm_enqueue_seed(const LmParams &p, const float *first_list_sims, const int32_t *first_list_counts, uint32_t nq,
                             cudaStream_t st, uint64_t *launches);
@@ -248,7 +254,7 @@ uint32_t probe_segments(size_t C);  // the select stage cuts a key row into this
 cudaError_t launch_probe_batch(const MatView &cent, const MatView &queries, int k, uint32_t *keys, unsigned int *flag_cnt,
                                uint32_t *flag_list, uint32_t flag_cap, uint32_t *cand_keys, uint32_t *cand_ids, uint32_t *out_probe,
                                float *out_sims, uint32_t *out_qtiles,
-                               const uint64_t *next_list_off, uint32_t next_tile_rows, uint32_t *out_status, uint32_t status_bit,
+                               const uint64_t *next_list_len, uint32_t next_tile_rows, uint32_t *out_status, uint32_t status_bit,
                                int status_init, unsigned long long *fix_counter, int sm_count, cudaStream_t st);
 cudaError_t probe_set_certify_scale(float scale);
 

@@ -50,6 +50,7 @@ __global__ void lm_count_kernel(const uint32_t *__restrict__ probe, uint32_t npa
 
 // One block: per list with at least one query, its items (<= kLmSubRows rows each) and the offset of its query list.
 __global__ void __launch_bounds__(1024) lm_items_kernel(const uint32_t *__restrict__ count, const uint64_t *__restrict__ list_off,
+                                                       const uint64_t *__restrict__ list_len,
                                                        uint32_t C, uint32_t *__restrict__ pair_off, LmItem *__restrict__ items,
                                                        uint32_t *__restrict__ nitems, uint32_t items_cap) {
     __shared__ uint32_t s_items[64], s_pairs[64];
@@ -59,7 +60,7 @@ __global__ void __launch_bounds__(1024) lm_items_kernel(const uint32_t *__restri
     for (uint32_t L = lo; L < hi; L++) {
         const uint32_t c = count[L];
         if (c) {
-            const uint64_t len = list_off[L + 1] - list_off[L];
+            const uint64_t len = list_len[L];
             my_items += (uint32_t)((len + kLmSubRows - 1) / kLmSubRows);
             my_pairs += c;
         }
@@ -99,7 +100,7 @@ __global__ void __launch_bounds__(1024) lm_items_kernel(const uint32_t *__restri
         const uint32_t c = count[L];
         pair_off[L] = pr;
         if (c) {
-            const uint64_t st = list_off[L], len = list_off[L + 1] - st;
+            const uint64_t st = list_off[L], len = list_len[L];
             for (uint64_t o = 0; o < len; o += kLmSubRows) {
                 if (it < items_cap) items[it] = LmItem{(uint32_t)(st + o), (uint32_t)min((uint64_t)kLmSubRows, len - o), pr, c};
                 it++;
@@ -534,7 +535,8 @@ static cudaError_t lm_launch_scan(LmParams p, int grid, cudaStream_t st) {
 // The list stage of a batch, list-major, in three steps (the caller brackets the scan with its profiling marks).
 // probe: [nq][npe] list ids (already selected); the status words already hold the probe stage's bits.
 cudaError_t lm_enqueue_prepare(const LmParams &p, const uint32_t *probe, uint32_t nq, uint32_t npe, uint32_t C,
-                               const uint64_t *list_off, uint32_t *count, uint32_t *pair_off, uint32_t items_cap, cudaStream_t st,
+                               const uint64_t *list_off, const uint64_t *list_len, uint32_t *count, uint32_t *pair_off,
+                               uint32_t items_cap, cudaStream_t st,
                                uint64_t *launches) {
     const uint32_t npairs = nq * npe;
     cudaError_t e;
@@ -543,7 +545,7 @@ cudaError_t lm_enqueue_prepare(const LmParams &p, const uint32_t *probe, uint32_
     if ((e = cudaMemsetAsync(p.gthr, 0, (size_t)nq * 4, st)) != cudaSuccess) return e;
     if ((e = cudaMemsetAsync(p.next_item, 0, 4, st)) != cudaSuccess) return e;
     lm_count_kernel<<<(npairs + 255) / 256, 256, 0, st>>>(probe, npairs, count);
-    lm_items_kernel<<<1, 1024, 0, st>>>(count, list_off, C, pair_off, p.items, p.nitems, items_cap);
+    lm_items_kernel<<<1, 1024, 0, st>>>(count, list_off, list_len, C, pair_off, p.items, p.nitems, items_cap);
     lm_fill_kernel<<<(npairs + 255) / 256, 256, 0, st>>>(probe, npairs, npe, count, pair_off, p.pairs);
     lm_side_kernel<<<(nq + 127) / 128, 128, 0, st>>>(p.queries, p.sides);
     if (launches) *launches += 4;

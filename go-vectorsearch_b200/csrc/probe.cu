@@ -122,7 +122,7 @@ __global__ void __launch_bounds__(kSelThreadsP)
 probe_select_kernel(MatView cent, MatView queries, uint32_t *__restrict__ keys, size_t key_stride,
                     const unsigned int *__restrict__ flag_cnt, const uint32_t *__restrict__ flag_list, uint32_t flag_cap, int k,
                     uint32_t *__restrict__ out_probe, float *__restrict__ out_sims, uint32_t *__restrict__ out_qtiles,
-                    const uint64_t *__restrict__ next_list_off, uint32_t next_tile_rows, uint32_t *__restrict__ out_status,
+                    const uint64_t *__restrict__ next_list_len, uint32_t next_tile_rows, uint32_t *__restrict__ out_status,
                     uint32_t status_bit, int status_init, unsigned long long *fix_counter, uint32_t nseg, uint32_t seg_len,
                     uint32_t *__restrict__ cand_keys, uint32_t *__restrict__ cand_ids) {
     extern __shared__ __align__(16) unsigned char sel_smem[];
@@ -300,7 +300,7 @@ probe_select_kernel(MatView cent, MatView queries, uint32_t *__restrict__ keys, 
         out_probe[(size_t)q * k + tid] = L;
         if (out_sims) out_sims[(size_t)q * k + tid] = key_to_f32(o_key[tid]);
         if (out_qtiles) {
-            const uint32_t len = (uint32_t)(next_list_off[L + 1] - next_list_off[L]);
+            const uint32_t len = (uint32_t)next_list_len[L];
             mytiles = (len + next_tile_rows - 1) / next_tile_rows;
         }
     }
@@ -318,7 +318,7 @@ probe_select_kernel(MatView cent, MatView queries, uint32_t *__restrict__ keys, 
 __global__ void __launch_bounds__(kSelThreadsP)
 probe_final_kernel(const uint32_t *__restrict__ cand_keys, const uint32_t *__restrict__ cand_ids, uint32_t ncand, uint32_t C,
                    const unsigned int *__restrict__ flag_cnt, uint32_t flag_cap, int k, uint32_t *__restrict__ out_probe,
-                   float *__restrict__ out_sims, uint32_t *__restrict__ out_qtiles, const uint64_t *__restrict__ next_list_off,
+                   float *__restrict__ out_sims, uint32_t *__restrict__ out_qtiles, const uint64_t *__restrict__ next_list_len,
                    uint32_t next_tile_rows, uint32_t *__restrict__ out_status, uint32_t status_bit, int status_init) {
     __shared__ unsigned int s_wcount[2][kSelThreadsP / 32];
     __shared__ uint32_t s_key[kMaxProbe], s_id[kMaxProbe], o_key[kMaxProbe], o_id[kMaxProbe];
@@ -383,7 +383,7 @@ probe_final_kernel(const uint32_t *__restrict__ cand_keys, const uint32_t *__res
         out_probe[(size_t)q * k + tid] = L;
         if (out_sims) out_sims[(size_t)q * k + tid] = key_to_f32(o_key[tid]);
         if (out_qtiles) {
-            const uint32_t len = (uint32_t)(next_list_off[L + 1] - next_list_off[L]);
+            const uint32_t len = (uint32_t)next_list_len[L];
             mytiles = (len + next_tile_rows - 1) / next_tile_rows;
         }
     }
@@ -417,7 +417,7 @@ bool probe_batch_supported(const MatView &cent, size_t nq, size_t k) {
 cudaError_t launch_probe_batch(const MatView &cent, const MatView &queries, int k, uint32_t *keys, unsigned int *flag_cnt,
                                uint32_t *flag_list, uint32_t flag_cap, uint32_t *cand_keys, uint32_t *cand_ids, uint32_t *out_probe,
                                float *out_sims, uint32_t *out_qtiles,
-                               const uint64_t *next_list_off, uint32_t next_tile_rows, uint32_t *out_status, uint32_t status_bit,
+                               const uint64_t *next_list_len, uint32_t next_tile_rows, uint32_t *out_status, uint32_t status_bit,
                                int status_init, unsigned long long *fix_counter, int sm_count, cudaStream_t st) {
     const size_t nq = queries.n, C = cent.n;
     cudaError_t e = cudaMemsetAsync(flag_cnt, 0, nq * sizeof(unsigned int), st);
@@ -462,7 +462,7 @@ cudaError_t launch_probe_batch(const MatView &cent, const MatView &queries, int 
             if (e != cudaSuccess) return e;                                                                                   \
         }                                                                                                                     \
         probe_select_kernel<KPT><<<(unsigned)(nq * nseg), kSelThreadsP, smem2, st>>>(                                         \
-            cent, queries, keys, C, flag_cnt, flag_list, flag_cap, k, out_probe, out_sims, out_qtiles, next_list_off,         \
+            cent, queries, keys, C, flag_cnt, flag_list, flag_cap, k, out_probe, out_sims, out_qtiles, next_list_len,         \
             next_tile_rows, out_status, status_bit, status_init, fix_counter, nseg, seg_len, cand_keys, cand_ids);            \
     } while (0)
     if (per <= 8) VS_PROBE_SELECT(8);
@@ -472,7 +472,7 @@ cudaError_t launch_probe_batch(const MatView &cent, const MatView &queries, int 
     e = cudaGetLastError();
     if (e != cudaSuccess || nseg == 1) return e;
     probe_final_kernel<<<(unsigned)nq, kSelThreadsP, 0, st>>>(cand_keys, cand_ids, nseg * (uint32_t)k, (uint32_t)C, flag_cnt, flag_cap, k,
-                                                             out_probe, out_sims, out_qtiles, next_list_off, next_tile_rows, out_status,
+                                                             out_probe, out_sims, out_qtiles, next_list_len, next_tile_rows, out_status,
                                                              status_bit, status_init);
     return cudaGetLastError();
 }

@@ -164,7 +164,7 @@ stage_kernel(const StageParams p) {
             if (p.seg_list) {
                 uint32_t L = p.seg_list[(size_t)qi * p.seg_stride + s];
                 st = p.list_off[L];
-                len = p.list_off[L + 1] - st;
+                len = p.list_len[L];
                 if (p.seg_cap && len > p.seg_cap) len = p.seg_cap;
             } else {
                 st = p.single_start;
@@ -483,7 +483,7 @@ stage_kernel(const StageParams p) {
                                 p.out_probe[(size_t)qi * p.k + r] = L;
                                 if (p.out_sims) p.out_sims[(size_t)qi * p.k + r] = key_to_f32(top.skey[s]);
                                 if (p.out_qtiles) {
-                                    uint32_t len = (uint32_t)(p.next_list_off[L + 1] - p.next_list_off[L]);
+                                    uint32_t len = (uint32_t)p.next_list_len[L];
                                     mytiles += (len + p.next_tile_rows - 1) / p.next_tile_rows;
                                 }
                             }

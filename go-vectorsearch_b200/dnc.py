@@ -117,31 +117,96 @@ def Split(X, centroids, ctx=None):
 
 
 def DivideAndConquer(data_matrix, target_size=CENTROID_SIZE, sample_size=SAMPLE_SIZE, split_size=SPLIT_SIZE, rng=None,
-                     iter_limit=KMEANS_ITTERATION_LIMIT, ctx=None):
+                     iter_limit=KMEANS_ITTERATION_LIMIT, ctx=None, workers=8):
     """divideNconquer (dnc/dnc.go:300-400) with every dataset resident in HBM instead of a temp file: a set of at most
     target_size rows yields one centroid, kMeans(sample, 1)[0] (dataset.go:93-98); a larger one is split by the
     min(split_size, max(2, rows / target_size)) centroids of kMeans(sample) and its children are treated the same way.
-    The reference runs the children concurrently and seeds every draw from the clock; here the order is depth-first with
-    children in index order and every draw comes from `rng`, so a build is reproducible.  A child that receives no row
-    is skipped (the reference would index an empty slice).  Returns the leaf centroids, (m, 8+d) uint8.
+
+    Like the reference (one goroutine per child behind a semaphore, dnc.go:30-33,346-358) the subproblems run concurrently:
+    `workers` host threads, each with its own compute.Context (a CUDA stream + scratch), take nodes from one queue, so the
+    latency-bound Lloyd iterations of different nodes overlap on the device.  The reference seeds every draw from the
+    clock; here every node owns a generator -- the root's is `rng`, a node hands its i-th non-empty child the i-th
+    generator of `rng.spawn()` after its own draws (sample, then the k-means superset) -- so the result does not depend on
+    the schedule or on `workers`, and the leaves are returned in depth-first order, children in index order.  A child that
+    receives no row is skipped (the reference would index an empty slice).  Returns the leaf centroids, (m, 8+d) uint8.
     """
+    import queue
+    import threading
+    from .compute import Context
     ctx = ctx or default_context()
     rng = rng or np.random.default_rng()
-    out = []
-    stack = [data_matrix]
-    while stack:
-        X = stack.pop()
-        S = _sample(X, sample_size, rng, ctx)
+
+    def node(X, g, c):
+        """-> (centroid, None) for a leaf, (None, [(child matrix, child generator)]) for a split."""
+        S = _sample(X, sample_size, g, c)
         if X.rows <= target_size:                                          # dnc.go:316-319
-            out.append(KMeans(S, 1, rng=rng, iter_limit=iter_limit, ctx=ctx)[0])
-            continue
+            return KMeans(S, 1, rng=g, iter_limit=iter_limit, ctx=c)[0], None
         k = min(split_size, max(2, X.rows // target_size))                 # dnc.go:330-339
-        cents = KMeans(S, k, rng=rng, iter_limit=iter_limit, ctx=ctx)
+        cents = KMeans(S, k, rng=g, iter_limit=iter_limit, ctx=c)
         del S
-        children = [ch for ch in Split(X, cents, ctx=ctx) if ch is not None]
-        del X
-        stack.extend(reversed(children))                                    # child 0 first
-    return np.stack(out)
+        kids = [ch for ch in Split(X, cents, ctx=c) if ch is not None]
+        return None, list(zip(kids, g.spawn(len(kids))))
+
+    leaves = {}                                                            # path in the tree -> leaf centroid
+    if workers <= 1:
+        stack = [(data_matrix, rng, ())]
+        while stack:
+            X, g, path = stack.pop()
+            cent, kids = node(X, g, ctx)
+            del X
+            if kids is None:
+                leaves[path] = cent
+            else:
+                stack.extend((ch, cg, path + (j,)) for j, (ch, cg) in reversed(list(enumerate(kids))))
+        return np.stack([leaves[p] for p in sorted(leaves)])
+
+    ctx.sync()                                                             # the rows may still be on their way on ctx's stream
+    todo = queue.Queue()
+    lock = threading.Lock()
+    state = {"open": 1, "error": None}
+    todo.put((data_matrix, rng, ()))
+
+    def work():
+        c = Context()
+        try:
+            while True:
+                item = todo.get()
+                if item is None:
+                    return
+                X, g, path = item
+                del item
+                try:
+                    if state["error"] is not None:
+                        cent, kids = None, []
+                    else:
+                        cent, kids = node(X, g, c)
+                except BaseException as e:                                  # noqa: BLE001 -- handed to the caller below
+                    with lock:
+                        state["error"] = state["error"] or e
+                    cent, kids = None, []
+                del X
+                with lock:
+                    if kids is None:
+                        leaves[path] = cent
+                    else:
+                        for j, (ch, cg) in enumerate(kids):
+                            todo.put((ch, cg, path + (j,)))
+                        state["open"] += len(kids)
+                    state["open"] -= 1
+                    if state["open"] == 0:
+                        for _ in range(workers):
+                            todo.put(None)
+        finally:
+            c.close()
+
+    threads = [threading.Thread(target=work, name=f"dnc-{i}") for i in range(workers)]
+    for t in threads:
+        t.start()
+    for t in threads:
+        t.join()
+    if state["error"] is not None:
+        raise state["error"]
+    return np.stack([leaves[p] for p in sorted(leaves)])
 
 
 def ReassignRecenter(data_matrix, centroids, d_assign=None, want_assign=True, ctx=None):

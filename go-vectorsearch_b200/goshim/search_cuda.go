@@ -91,6 +91,38 @@ func (ix *Index) Upload(rows [][]uint8, documentIDs []uint64) (next *Index, cent
 	return next, centroidIndex
 }
 
+// WithRoom copies the store into one whose every list can grow by max(percent % of its rows, minRows) rows, so that
+// Append can write new embeddings in place (vs_index_with_room).
+func (ix *Index) WithRoom(percent, minRows int) *Index {
+	next := &Index{}
+	withDefaultCtx(func(c *ctx) {
+		check(C.vs_index_with_room(c.h, ix.h, C.size_t(percent), C.size_t(minRows), &next.h))
+	})
+	runtime.SetFinalizer(next, func(ix *Index) { C.vs_index_release(ix.h) })
+	return next
+}
+
+// Append is Upload in place: the new embeddings are written behind the last row of their nearest centroid's list, a cost
+// proportional to the new rows only.  ok == false (VS_EFULL) means some list has no room and nothing was changed: the
+// caller appends to ix.WithRoom(...) instead and swaps the pointer, like growing a slice.  One appending goroutine per
+// index; searches on other contexts see every list either before or after the append.
+func (ix *Index) Append(rows [][]uint8, documentIDs []uint64) (centroidIndex []int64, ok bool) {
+	rbuf, n, rowBytes := pack(rows)
+	defer C.free(rbuf)
+	centroidIndex = make([]int64, n)
+	ok = true
+	withDefaultCtx(func(c *ctx) {
+		rc := C.vs_index_append(c.h, ix.h, (*C.uint8_t)(rbuf), C.size_t(n), C.size_t(rowBytes),
+			(*C.uint64_t)(unsafe.Pointer(&documentIDs[0])), (*C.int64_t)(unsafe.Pointer(&centroidIndex[0])))
+		if rc == C.VS_EFULL {
+			ok = false
+			return
+		}
+		check(rc)
+	})
+	return centroidIndex, ok
+}
+
 // KMeansStep is one iteration of dnc/k_means.go:67-117 on a device matrix. means is the [k][d] float32 state the
 // reference carries between iterations (flattened); it is updated in place.
 func KMeansStep(data Matrix, centroids [][]uint8, means []float32) (counts []int64, newCentroids [][]uint8, converged bool) {

@@ -66,7 +66,7 @@ class Index:
     @classmethod
     def create_empty(cls, centroids, list_counts, ctx=None):
         """Streaming loader, step 1: reserve the grouped store from the per-list row counts (centroids: compute.Matrix).
-        Fill it with Fill / FillDev in primary-key order; searches are refused until every row is placed."""
+        Fill it with Fill / FillDev in primary-key order; searches answer from the rows placed so far."""
         L = _lib.init()
         ctx = ctx or default_context()
         counts = np.ascontiguousarray(list_counts, dtype=np.uint64)
@@ -103,6 +103,52 @@ class Index:
         _check(self._L.vs_index_upload(ctx.handle, self._h, _p(rows), rows.shape[0], rows.shape[1],
                                        _p(ids) if ids is not None else None, _p(assign), C.byref(h)))
         return Index(h, self._L), assign
+
+    def WithRoom(self, percent=25, min_rows=64, ctx=None):
+        """A copy of this index in which every list can grow by max(percent % of its rows, min_rows) before anything has to
+        be copied again (vs_index_with_room)."""
+        ctx = ctx or default_context()
+        h = C.c_void_p()
+        _check(self._L.vs_index_with_room(ctx.handle, self._h, int(percent), int(min_rows), C.byref(h)))
+        return Index(h, self._L)
+
+    def Append(self, rows, doc_ids=None, ctx=None):
+        """Upload's assignment and insert (server/upload.go:239-279) in place: every new row is written behind the last row of
+        its nearest centroid's list.  Returns assign int64[n]; raises compute.IndexFull, with the index unchanged, when a
+        list has no room (UploadInPlace handles that)."""
+        ctx = ctx or default_context()
+        rows = _rows_array(rows)
+        ids = None if doc_ids is None else np.ascontiguousarray(doc_ids, dtype=np.uint64)
+        assert ids is None or ids.shape == (rows.shape[0],)
+        assign = np.empty(rows.shape[0], np.int64)
+        _check(self._L.vs_index_append(ctx.handle, self._h, _p(rows), rows.shape[0], rows.shape[1],
+                                       _p(ids) if ids is not None else None, _p(assign)))
+        return assign
+
+    def UploadInPlace(self, rows, doc_ids=None, percent=25, min_rows=64, ctx=None):
+        """Append, growing when needed: when a list is full (or this index was built without room) the store is copied once
+        into a roomier one -- amortised over the appends that follow, like a growing slice -- and this object continues as
+        the new index (searches in flight on the old store must have been waited for).  Returns (assign, copied: bool)."""
+        from .compute import IndexFull
+        rows = _rows_array(rows)
+        try:
+            return self.Append(rows, doc_ids, ctx=ctx), False
+        except IndexFull:
+            pass
+        grown = self.WithRoom(percent, max(min_rows, rows.shape[0]), ctx=ctx)      # every list can take all the new rows
+        old, self._h, grown._h = self._h, grown._h, None
+        self._L.vs_index_release(old)
+        return self.Append(rows, doc_ids, ctx=ctx), True
+
+    @property
+    def capacity(self):
+        return int(self._L.vs_index_capacity(self._h))
+
+    def ListLengths(self, ctx=None):
+        ctx = ctx or default_context()
+        out = np.empty(self.lists, np.uint64)
+        _check(self._L.vs_index_list_lengths(ctx.handle, self._h, _p(out)))
+        return out
 
     def ListOffsets(self, ctx=None):
         ctx = ctx or default_context()

@@ -37,6 +37,7 @@ extern "C" {
 #define VS_ENODEV (-5)   /* no CUDA device / library not initialised */
 #define VS_ENOMEM (-6)
 #define VS_ERANGE (-7)   /* k / nprobe / dimension beyond what the kernels support */
+#define VS_EFULL (-8)    /* vs_index_append: a list (or the store) has no room left; nothing was changed */
 
 typedef struct vs_ctx vs_ctx;       /* one CUDA stream + scratch arena; one per goroutine/closure */
 typedef struct vs_matrix vs_matrix; /* immutable device-resident quantized matrix, ref-counted */
@@ -165,10 +166,11 @@ VS_API int vs_index_build_dev(vs_ctx *ctx, const vs_matrix *data, const int32_t 
  * size from the per-list row counts (host, [C] -- SELECT centroid_id, COUNT(*) ... GROUP BY centroid_id, the query of
  * dnc.go:465-470); vs_index_fill* then places chunks of rows, handed over in primary-key order, straight into their
  * lists.  HBM holds the store once plus one chunk, so a shard can be sized for nearly all of the 180 GB (the one-piece
- * builds above hold the ungrouped rows and the grouped copy at the same time).  Searches are refused (VS_EINVAL) until
- * every reserved row is placed; the result is identical to vs_index_build_assigned over the same rows.  One loader
- * thread per index (the fill calls mutate it and are ordered); a fill that fails with VS_EINVAL because a list
- * overflowed its reservation leaves the index unusable -- release it.
+ * builds above hold the ungrouped rows and the grouped copy at the same time).  Once every reserved row is placed the
+ * result is identical to vs_index_build_assigned over the same rows; before that the index answers from the rows placed
+ * so far (every list knows how many rows it holds; see vs_index_append for what that costs).  One loader thread per
+ * index (the fill calls mutate it and are ordered); a fill that fails with VS_EINVAL because a list overflowed its
+ * reservation leaves the index unusable -- release it.
  * vs_index_fill_dev: chunk = device matrix, d_list_of_row[m] int32 list index per row (e.g. from vs_argmax_MxN_dev),
  * d_doc_ids[m] or NULL (id = id_base + row index in the chunk); vs_index_fill: the same from host buffers. */
 VS_API int vs_index_create_empty(vs_ctx *ctx, const vs_matrix *centroids, const uint64_t *list_counts, vs_index **out);
@@ -193,6 +195,23 @@ VS_API int vs_index_read_rows(vs_ctx *ctx, const vs_index *ix, size_t first, siz
  * upload.go:268-271 turns into Embedding.CentroidID.  Errors as NewMatrix / MatrixCosineSimilarity: VS_EEMPTY, VS_EDIM. */
 VS_API int vs_index_upload(vs_ctx *ctx, const vs_index *ix, const uint8_t *rows_packed, size_t n, size_t row_bytes,
                     const uint64_t *doc_ids, int64_t *assign_out, vs_index **out);
+/* Upload in place.  vs_index_upload copies the store once per call; a service that ingests continuously keeps room
+ * behind every list instead.  vs_index_with_room: a copy of ix (one pass at copy bandwidth) in which list l can hold
+ * len(l) + max(len(l) * percent / 100, min_rows) rows.  vs_index_append: the assignment of upload.go:245 and the insert,
+ * in place -- every new row is written behind the last row of its nearest centroid's list (a few launches, cost
+ * proportional to the new rows only); arguments and assign_out as vs_index_upload.  VS_EFULL when some list (or the store)
+ * cannot take its new rows: NOTHING was changed; make a roomier copy with vs_index_with_room (or merge with
+ * vs_index_upload) and append to that.  Searches see a list either before or after an append that runs concurrently on
+ * another context; one appending thread per index.
+ * While an index has room left its store has holes between the lists, so searches go list by list: nprobe >= number of
+ * lists probes every list (up to 128 lists on the device, more through vs_search's host path); the whole-store entry
+ * points (vs_index_search_batch_dev, the GEMM batch form of vs_search) are for indexes without holes.
+ * vs_index_rows = rows present, vs_index_capacity = places, vs_index_list_lengths = rows per list (C values). */
+VS_API int vs_index_with_room(vs_ctx *ctx, const vs_index *ix, size_t percent, size_t min_rows, vs_index **out);
+VS_API int vs_index_append(vs_ctx *ctx, vs_index *ix, const uint8_t *rows_packed, size_t n, size_t row_bytes,
+                    const uint64_t *doc_ids, int64_t *assign_out);
+VS_API size_t vs_index_capacity(const vs_index *ix);
+VS_API int vs_index_list_lengths(vs_ctx *ctx, const vs_index *ix, uint64_t *lengths_out);
 /* Search (search.go:115-273 minus embedding/DB hops): nq query rows (row776, host), nprobe =
  * SearchRequest.Centroids (>= number of lists means "all"), k = Count+Offset.  Outputs (host):
  * ids_out[nq*k] document IDs, sims_out[nq*k] float32 similarities, counts_out[nq] valid entries.

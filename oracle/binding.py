@@ -274,35 +274,36 @@ def kmeans(data, k, superset_rows, limit=1000):
 
 
 def divide_and_conquer(rows, target_size, sample_size, split_size, rng, limit=1000):
-    """divideNconquer (dnc/dnc.go:300-400) on host arrays, depth-first with children in index order, every draw from `rng`
-    in the order the device driver makes them (the reference seeds each draw from the clock and runs children
-    concurrently, so only a restatement with shared draws can be compared): sample() (sampling.go:12-74) = all rows or
-    sample_size sorted distinct rows; a set of at most target_size rows yields kMeans(sample, 1)[0] (dataset.go:93-98);
-    a larger one is split by nearest centroid of kMeans(sample, min(split, max(2, rows/target))) (dnc.go:330-389)."""
+    """divideNconquer (dnc/dnc.go:300-400) on host arrays.  The reference seeds each draw from the clock and runs children
+    concurrently, so only a restatement with agreed draws can be compared: every node owns a generator (the root's is
+    `rng`); it draws its sample (sampling.go:12-74: all rows or sample_size sorted distinct rows), then its k-means
+    superset, then hands its i-th non-empty child the i-th generator of `spawn()`.  A set of at most target_size rows
+    yields kMeans(sample, 1)[0] (dataset.go:93-98); a larger one is split by nearest centroid of
+    kMeans(sample, min(split, max(2, rows/target))) (dnc.go:330-389).  Leaves in depth-first order, children in index order."""
     rows = _u8(rows)
 
-    def sample(x):
+    def sample(x, g):
         if x.shape[0] <= sample_size:
             return x
-        return x[np.sort(rng.choice(x.shape[0], sample_size, replace=False))]
+        return x[np.sort(g.choice(x.shape[0], sample_size, replace=False))]
 
-    def km(x, k):
+    def km(x, k, g):
         if x.shape[0] == 0 or x.shape[0] <= k:
             return x
         ks = min(x.shape[0], 5 * k)
-        return kmeans(x, k, rng.choice(x.shape[0], ks, replace=False), limit)[0]
+        return kmeans(x, k, g.choice(x.shape[0], ks, replace=False), limit)[0]
 
-    out, stack = [], [rows]
+    out, stack = [], [(rows, rng)]
     while stack:
-        x = stack.pop()
-        s = sample(x)
+        x, g = stack.pop()
+        s = sample(x, g)
         if x.shape[0] <= target_size:
-            out.append(km(s, 1)[0])
+            out.append(km(s, 1, g)[0])
             continue
-        cents = km(s, min(split_size, max(2, x.shape[0] // target_size)))
+        cents = km(s, min(split_size, max(2, x.shape[0] // target_size)), g)
         _, idx = argmax_MxN(cents, x)
-        children = [x[idx == j] for j in range(cents.shape[0])]
-        stack.extend(reversed([c for c in children if c.shape[0]]))
+        children = [c for c in (x[idx == j] for j in range(cents.shape[0])) if c.shape[0]]
+        stack.extend(reversed(list(zip(children, g.spawn(len(children))))))
     return np.stack(out)
 
 

@@ -1,7 +1,7 @@
 """GPU parity: the divide-and-conquer centroid build (dnc/dnc.go:300-400 and the tail of KMeansDivideAndConquer, :177-291)
 with every dataset resident in HBM.  Upstream the build is seeded from the clock and runs its children concurrently; the
-device driver and the oracle's restatement make the same draws from the same generator in the same (depth-first) order,
-so their outputs can be compared bit for bit."""
+device driver (concurrent too: one host thread + CUDA stream per worker) and the oracle's restatement give every node of the
+tree its own generator, spawned from its parent's, so their outputs can be compared bit for bit whatever the schedule."""
 import numpy as np
 import pytest
 
@@ -10,13 +10,14 @@ from _util import clustered_rows, noop_rows, unit_rows
 pytestmark = pytest.mark.gpu
 
 
+@pytest.mark.parametrize("workers", [1, 6])
 @pytest.mark.parametrize("d,n,target,sample,seed", [(256, 6000, 500, 2000, 1), (768, 4000, 900, 1500, 2), (64, 3000, 200, 5000, 3)])
-def test_divide_and_conquer_matches_oracle(vs, oracle, d, n, target, sample, seed):
+def test_divide_and_conquer_matches_oracle(vs, oracle, d, n, target, sample, seed, workers):
     x, _ = clustered_rows(n, d, 7, seed)
     rows = oracle.quantize_matrix_f32(x)
     want = oracle.divide_and_conquer(rows, target, sample, 5, np.random.default_rng(seed), limit=6)
     got = vs.dnc.DivideAndConquer(vs.compute.NewMatrix(rows), target_size=target, sample_size=sample, split_size=5,
-                                  rng=np.random.default_rng(seed), iter_limit=6)
+                                  rng=np.random.default_rng(seed), iter_limit=6, workers=workers)
     assert got.shape == want.shape and (got == want).all()
     assert got.shape[0] >= n // target      # enough leaves that none can exceed the target on average
 

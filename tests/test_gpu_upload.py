@@ -131,3 +131,82 @@ def test_upload_errors_like_reference(vs, oracle):
     with pytest.raises(c.ComputeError, match="doc_ids is required"):
         ix.Upload(rows[:2])
     assert ix.rows == 100
+
+
+def _lists_equal_table(ix, all_rows, all_doc, lists, C):
+    """Every list of the (possibly holey) store holds exactly the table's rows of that list, in primary-key order."""
+    off, ln = ix.ListOffsets(), ix.ListLengths()
+    assert int(ln.sum()) == ix.rows == all_rows.shape[0]
+    for l in range(C):
+        members = np.flatnonzero(lists == l)
+        assert ln[l] == members.shape[0] and off[l] + ln[l] <= off[l + 1]
+        if ln[l]:
+            r, i = ix.ReadRows(int(off[l]), int(ln[l]))
+            assert (i == all_doc[members]).all() and (r == all_rows[members]).all()
+
+
+@pytest.mark.parametrize("n0,C,parts", [(20000, 96, 4), (3000, 300, 3), (64, 20, 5)])
+def test_upload_in_place_equals_rebuild(vs, oracle, n0, C, parts):
+    """vs_index_with_room + vs_index_append: after every append the lists are the embeddings table's lists and searches
+    (one query: fused launch; a batch: list-major; few queries: streaming scan; every list probed; wide requests) answer
+    like the oracle over that table.  A list that fills up raises IndexFull and leaves the index as it was."""
+    d, n1 = 768, 2400
+    rows, cent, doc = _table(oracle, n0 + n1, d, C, 21)
+    _, lists0 = oracle.argmax_MxN(cent, rows[:n0])
+    packed = vs.ivf.Index.build_assigned(rows[:n0], doc[:n0], lists0.astype(np.uint32), cent)
+    with pytest.raises(vs.compute.IndexFull):
+        packed.Append(rows[n0:n0 + 1], doc[n0:n0 + 1])
+    ix = packed.WithRoom(percent=10, min_rows=n1)                # enough for everything: no list can overflow
+    assert ix.rows == n0 and ix.capacity >= n0 + C * n1
+    cur_rows, cur_doc, cur_lists = rows[:n0], doc[:n0], lists0.astype(np.uint32)
+    qs = oracle.quantize_matrix_f32(unit_rows(24, d, 78))
+    for part in np.array_split(np.arange(n0, n0 + n1), parts):
+        assign = ix.Append(rows[part], doc[part])
+        want, cur_lists, cur_rows, cur_doc = oracle.upload(cent, rows[part], cur_lists, cur_rows, cur_doc, doc[part])
+        assert assign.tolist() == want.tolist()
+        assert ix.rows == cur_rows.shape[0]
+        _search_parity(oracle, ix, qs[:1], cent, cur_rows, cur_lists, cur_doc, nprobe=8, k=10)      # fused
+    _lists_equal_table(ix, cur_rows, cur_doc, cur_lists, C)
+    _search_parity(oracle, ix, qs[:3], cent, cur_rows, cur_lists, cur_doc, nprobe=8, k=10)           # streaming scan
+    _search_parity(oracle, ix, qs, cent, cur_rows, cur_lists, cur_doc, nprobe=min(C, 16), k=10)      # batch
+    _search_parity(oracle, ix, qs[:2], cent, cur_rows, cur_lists, cur_doc, nprobe=C, k=10)           # every list (holes: by lists)
+    _search_parity(oracle, ix, qs[:1], cent, cur_rows, cur_lists, cur_doc, nprobe=C + 5, k=200)      # wide request
+    # the packed index it was copied from is untouched
+    assert packed.rows == n0
+
+
+def test_append_refuses_what_does_not_fit(vs, oracle):
+    d, C, n0 = 256, 8, 800
+    rows, cent, doc = _table(oracle, n0 + 600, d, C, 31)
+    _, lists0 = oracle.argmax_MxN(cent, rows[:n0])
+    ix = vs.ivf.Index.build_assigned(rows[:n0], doc[:n0], lists0.astype(np.uint32), cent).WithRoom(percent=0, min_rows=10)
+    before = ix.ListLengths().copy()
+    with pytest.raises(vs.compute.IndexFull):
+        ix.Append(rows[n0:], doc[n0:])                           # 600 rows over 8 lists with 10 free places each
+    assert (ix.ListLengths() == before).all() and ix.rows == n0
+    qs = oracle.quantize_matrix_f32(unit_rows(2, d, 5))
+    _search_parity(oracle, ix, qs, cent, rows[:n0], lists0.astype(np.uint32), doc[:n0], nprobe=3, k=10)
+    # UploadInPlace copies once into a roomier store, then appends; later small uploads need no copy
+    assign, copied = ix.UploadInPlace(rows[n0:n0 + 500], doc[n0:n0 + 500])
+    assert copied
+    want, lists, all_rows, all_doc = oracle.upload(cent, rows[n0:n0 + 500], lists0, rows[:n0], doc[:n0], doc[n0:n0 + 500])
+    assert assign.tolist() == want.tolist()
+    assign2, copied2 = ix.UploadInPlace(rows[n0 + 500:], doc[n0 + 500:])
+    assert not copied2
+    want2, lists, all_rows, all_doc = oracle.upload(cent, rows[n0 + 500:], lists, all_rows, all_doc, doc[n0 + 500:])
+    assert assign2.tolist() == want2.tolist()
+    _lists_equal_table(ix, all_rows, all_doc, lists, C)
+    _search_parity(oracle, ix, qs, cent, all_rows, lists, all_doc, nprobe=3, k=10)
+
+
+def test_append_continues_implicit_numbering(vs, oracle):
+    """An index built without document ids numbers its rows in primary-key order; appended rows continue the count."""
+    d, C, n0, n1 = 128, 6, 500, 120
+    rows, cent, _ = _table(oracle, n0 + n1, d, C, 41)
+    _, lists0 = oracle.argmax_MxN(cent, rows[:n0])
+    ix = vs.ivf.Index.build_assigned(rows[:n0], None, lists0.astype(np.uint32), cent).WithRoom(percent=50, min_rows=n1)
+    ix.Append(rows[n0:])
+    ids = np.arange(n0 + n1, dtype=np.uint64)
+    _, lists, all_rows, all_doc = oracle.upload(cent, rows[n0:], lists0, rows[:n0], ids[:n0], ids[n0:])
+    qs = oracle.quantize_matrix_f32(unit_rows(3, d, 6))
+    _search_parity(oracle, ix, qs, cent, all_rows, lists, all_doc, nprobe=C, k=15)

@@ -13,6 +13,7 @@ def main():
     ap.add_argument("--rows", type=int, default=10_000_000)
     ap.add_argument("--target", type=int, default=10_000)
     ap.add_argument("--seed", type=int, default=7)
+    ap.add_argument("--workers", type=int, default=8, help="host threads (each with its own CUDA stream) walking the tree")
     a = ap.parse_args()
     import torch
     from __graft_entry__ import load_pkg
@@ -34,8 +35,7 @@ def main():
         del x
     torch.cuda.empty_cache()
     t1 = time.time()
-    l0 = ctx.launch_count()
-    cents = dnc.DivideAndConquer(data, target_size=a.target, rng=np.random.default_rng(a.seed), ctx=ctx)
+    cents = dnc.DivideAndConquer(data, target_size=a.target, rng=np.random.default_rng(a.seed), ctx=ctx, workers=a.workers)
     ctx.sync()
     t2 = time.time()
     assign = torch.empty(a.rows, dtype=torch.int32, device=device)
@@ -53,7 +53,7 @@ def main():
         "generate_s": round(t1 - t0, 2), "divide_and_conquer_s": round(t2 - t1, 2), "reassign_recenter_s": round(t3 - t2, 2),
         "group_into_lists_s": round(t4 - t3, 2), "total_build_s": round(t4 - t1, 2),
         "centroids": int(cents.shape[0]), "list_rows_min_median_max": [int(counts.min()), int(np.median(counts)), int(counts.max())],
-        "kernel_launches": int(ctx.launch_count() - l0),
+        "workers": a.workers,
         "query_rows_find_themselves": self_hit}), flush=True)
 
 
