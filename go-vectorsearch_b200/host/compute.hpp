@@ -180,6 +180,26 @@ class Index {
         check(vs_index_upload(c.handle(), h_.get(), buf.data(), rows.size(), rows[0].size(), documentIDs.data(), assign.data(), &h));
         return {Index(h), std::move(assign)};
     }
+    // Upload in place: a copy whose lists have room (vs_index_with_room), then appends behind the lists (vs_index_append).
+    // Append returns false -- and changes nothing -- when a list is full: append to WithRoom(...) of this index instead.
+    Index WithRoom(size_t percent, size_t minRows, Context *ctx = nullptr) const {
+        Context &c = ctx ? *ctx : DefaultContext();
+        vs_index *h = nullptr;
+        check(vs_index_with_room(c.handle(), h_.get(), percent, minRows, &h));
+        return Index(h);
+    }
+    bool Append(const Rows &rows, const std::vector<uint64_t> &documentIDs, std::vector<int64_t> *centroidIndex = nullptr,
+                Context *ctx = nullptr) {
+        Context &c = ctx ? *ctx : DefaultContext();
+        std::vector<uint8_t> buf = Pack(rows);
+        if (documentIDs.size() != rows.size()) throw Error("one document id per row");
+        std::vector<int64_t> assign(rows.size());
+        const int rc = vs_index_append(c.handle(), h_.get(), buf.data(), rows.size(), rows[0].size(), documentIDs.data(), assign.data());
+        if (rc == VS_EFULL) return false;
+        check(rc);
+        if (centroidIndex) *centroidIndex = std::move(assign);
+        return true;
+    }
     // streaming loader, step 2: one chunk of the embeddings table in primary-key order
     void Fill(const Rows &rows, const std::vector<uint64_t> &documentIDs, const std::vector<uint32_t> &centroidIndex, Context *ctx = nullptr) {
         Context &c = ctx ? *ctx : DefaultContext();

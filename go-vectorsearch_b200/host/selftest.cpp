@@ -71,13 +71,19 @@ int main() {
         EXPECT(h3.documentIDs == h2.documentIDs && h3.similarities == h2.similarities, "index after upload == index built from all rows");
         EXPECT(first3.rows() == 3 && up.first.rows() == 5, "upload leaves the old index untouched");
         Index ld = NewIndexLoader(NewMatrix(cents), {3, 2});
-        bool refused = false;
-        try { ld.Search(query, 2, 10); } catch (const Error &) { refused = true; }
-        EXPECT(refused, "a loading index refuses searches");
+        EXPECT(ld.Search(query, 2, 10).documentIDs.empty(), "an empty loader index answers with nothing");
         ld.Fill({drows[0], drows[1]}, {100, 101}, {1, 0});
+        EXPECT((ld.Search(query, 2, 10).documentIDs == std::vector<uint64_t>{101, 100}), "a half-loaded index answers from the rows placed so far");
         ld.Fill({drows[2], drows[3], drows[4]}, {102, 103, 104}, {0, 0, 1});
         Hits h4 = ld.Search(query, 2, 10);
         EXPECT(h4.documentIDs == h2.documentIDs && h4.similarities == h2.similarities, "streamed index == index built in one piece");
+        // upload in place: the same two rows appended behind their lists
+        Index roomy = first3.WithRoom(0, 2);
+        std::vector<int64_t> where;
+        EXPECT((roomy.Append({drows[3], drows[4]}, {103, 104}, &where) && where == std::vector<int64_t>{0, 1}), "append assignment");
+        Hits h5 = roomy.Search(query, 2, 10);
+        EXPECT(h5.documentIDs == h2.documentIDs && h5.similarities == h2.similarities, "index after append == index built from all rows");
+        EXPECT((!roomy.Append({drows[2], drows[2], drows[2]}, {105, 106, 107}) && roomy.rows() == 5), "a full list refuses and changes nothing");
         // error behaviour
         bool panicked = false;
         try { NewVector(compute::Row(8, 0)); } catch (const Panic &) { panicked = true; }
