@@ -210,6 +210,7 @@ def build_index(pkg, torch, ctx, a, rank, world, device):
         del ids
     del assign
     torch.cuda.empty_cache()
+    cp.release_cached_memory()
     return ix, cent, {"gen_quantize_s": round(gen_s, 2), "assign_s": round(assign_s, 2), "group_s": round(fill_s, 2),
                       "loader": "streaming (two passes over the generator; the store is held once)"}
 

@@ -69,6 +69,11 @@ def debug_set_argmax_gemm_min(min_centroids):
     _check(_lib.init().vs_debug_set_argmax_gemm_min(int(min_centroids)))
 
 
+def release_cached_memory():
+    """Hand the freed matrix / store memory the library keeps for reuse back to the driver (vs_release_cached_memory)."""
+    _check(_lib.init().vs_release_cached_memory())
+
+
 def debug_set_fused(on):
     """Test hook: False sends single-query searches through the two-launch streaming path instead of the fused kernel."""
     _check(_lib.init().vs_debug_set_fused(1 if on else 0))

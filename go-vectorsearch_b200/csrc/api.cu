@@ -375,6 +375,64 @@ extern "C" int vs_dequantize_f64(vs_ctx *c, const uint8_t *rows, size_t n, size_
 }
 
 // ------------------------------------------------------------------------------------------------
+// Matrix storage comes from the device's stream-ordered memory pool.  cudaMalloc / cudaFree cost milliseconds for the
+// sizes of a store (mapping and unmapping the pages) and cudaFree stalls every stream: the divide-and-conquer build, which
+// makes and drops a few thousand matrices, spent a third of its time there.  The pool keeps freed pages mapped (up to
+// VS_POOL_KEEP_GB, default 24) and hands them out again; vs_release_cached_memory returns them to the driver.
+static cudaStream_t g_pool_stream[64] = {};
+static std::mutex g_pool_mu;
+static cudaError_t pool_stream_for(int dev, cudaStream_t *out) {
+    if (dev < 0 || dev >= 64) return cudaErrorInvalidDevice;
+    std::lock_guard<std::mutex> lk(g_pool_mu);
+    if (!g_pool_stream[dev]) {
+        cudaMemPool_t pool;
+        cudaError_t e = cudaDeviceGetDefaultMemPool(&pool, dev);
+        if (e != cudaSuccess) return e;
+        const char *env = getenv("VS_POOL_KEEP_GB");
+        uint64_t keep = (uint64_t)(env ? atoll(env) : 24) << 30;
+        if ((e = cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &keep)) != cudaSuccess) return e;
+        if ((e = cudaStreamCreateWithFlags(&g_pool_stream[dev], cudaStreamNonBlocking)) != cudaSuccess) return e;
+    }
+    *out = g_pool_stream[dev];
+    return cudaSuccess;
+}
+// usable on every stream when it returns
+static cudaError_t pool_alloc(void **p, size_t bytes) {
+    const int dev = cur_device();
+    cudaStream_t st;
+    cudaError_t e = pool_stream_for(dev, &st);
+    if (e != cudaSuccess) return e;
+    e = cudaMallocAsync(p, bytes, st);
+    if (e == cudaErrorMemoryAllocation) {  // give the cached pages back and try once more
+        cudaGetLastError();
+        cudaMemPool_t pool;
+        if (cudaDeviceGetDefaultMemPool(&pool, dev) == cudaSuccess) {
+            cudaDeviceSynchronize();
+            cudaMemPoolTrimTo(pool, 0);
+        }
+        e = cudaMallocAsync(p, bytes, st);
+    }
+    if (e != cudaSuccess) return e;
+    return cudaStreamSynchronize(st);
+}
+// like cudaFree, waits for whatever may still be reading the memory (the device must be current)
+static void pool_free_all(int dev, void *a, void *b, void *c3) {
+    cudaStream_t st;
+    if (pool_stream_for(dev, &st) != cudaSuccess) return;
+    cudaDeviceSynchronize();
+    if (a) cudaFreeAsync(a, st);
+    if (b) cudaFreeAsync(b, st);
+    if (c3) cudaFreeAsync(c3, st);
+}
+extern "C" int vs_release_cached_memory(void) {
+    VS(need_dev());
+    cudaMemPool_t pool;
+    CU(cudaDeviceGetDefaultMemPool(&pool, cur_device()));
+    CU(cudaDeviceSynchronize());
+    CU(cudaMemPoolTrimTo(pool, 0));
+    return VS_OK;
+}
+
 // matrices
 static int matrix_alloc(size_t n, size_t d, vs_matrix **out) {
     if (d > 4096) return fail(VS_ERANGE, "d=%zu: kernels support d <= 4096", d);
@@ -384,13 +442,12 @@ static int matrix_alloc(size_t n, size_t d, vs_matrix **out) {
     m->n = n;
     m->d = (int)d;
     m->d_pad = (int)((d + 15) & ~size_t(15));
-    cudaError_t e = cudaMalloc(&m->codes, n * (size_t)m->d_pad + 256);
-    if (e == cudaSuccess) e = cudaMalloc(&m->hdr, n * sizeof(float2) + 256);
-    if (e == cudaSuccess) e = cudaMalloc(&m->sums, n * sizeof(uint2) + 256);
+    cudaError_t e = pool_alloc(reinterpret_cast<void **>(&m->codes), n * (size_t)m->d_pad + 256);
+    if (e == cudaSuccess) e = pool_alloc(reinterpret_cast<void **>(&m->hdr), n * sizeof(float2) + 256);
+    if (e == cudaSuccess) e = pool_alloc(reinterpret_cast<void **>(&m->sums), n * sizeof(uint2) + 256);
     if (e != cudaSuccess) {
-        if (m->codes) cudaFree(m->codes);
-        if (m->hdr) cudaFree(m->hdr);
-        if (m->sums) cudaFree(m->sums);
+        cudaGetLastError();
+        pool_free_all(m->device, m->codes, m->hdr, m->sums);
         delete m;
         return fail(VS_ENOMEM, "cudaMalloc for %zu x %zu matrix: %s", n, d, cudaGetErrorString(e));
     }
@@ -405,11 +462,7 @@ extern "C" void vs_matrix_release(vs_matrix *m) {
     if (!m) return;
     if (m->refs.fetch_sub(1) == 1) {
         cudaSetDevice(m->device);
-        if (m->owns) {
-            cudaFree(m->codes);
-            cudaFree(m->hdr);
-            cudaFree(m->sums);
-        }
+        if (m->owns) pool_free_all(m->device, m->codes, m->hdr, m->sums);
         delete m;
     }
 }

@@ -117,7 +117,7 @@ def Split(X, centroids, ctx=None):
 
 
 def DivideAndConquer(data_matrix, target_size=CENTROID_SIZE, sample_size=SAMPLE_SIZE, split_size=SPLIT_SIZE, rng=None,
-                     iter_limit=KMEANS_ITTERATION_LIMIT, ctx=None, workers=8):
+                     iter_limit=KMEANS_ITTERATION_LIMIT, ctx=None, workers=8, stats=None):
     """divideNconquer (dnc/dnc.go:300-400) with every dataset resident in HBM instead of a temp file: a set of at most
     target_size rows yields one centroid, kMeans(sample, 1)[0] (dataset.go:93-98); a larger one is split by the
     min(split_size, max(2, rows / target_size)) centroids of kMeans(sample) and its children are treated the same way.
@@ -129,22 +129,46 @@ def DivideAndConquer(data_matrix, target_size=CENTROID_SIZE, sample_size=SAMPLE_
     generator of `rng.spawn()` after its own draws (sample, then the k-means superset) -- so the result does not depend on
     the schedule or on `workers`, and the leaves are returned in depth-first order, children in index order.  A child that
     receives no row is skipped (the reference would index an empty slice).  Returns the leaf centroids, (m, 8+d) uint8.
+    `stats`: optional dict that receives where the time went (host seconds per phase summed over the workers, Lloyd
+    iterations, device microseconds of the assign / update halves of the iterations).
     """
     import queue
     import threading
+    import time
     from .compute import Context
     ctx = ctx or default_context()
     rng = rng or np.random.default_rng()
+    tally = threading.Lock()
+
+    def note(**kw):
+        if stats is not None:
+            with tally:
+                for key, v in kw.items():
+                    stats[key] = stats.get(key, 0) + v
+
+    def km(S, k, g, c):
+        if stats is None or S.rows <= k:
+            return KMeans(S, k, rng=g, iter_limit=iter_limit, ctx=c)
+        out, st = KMeans(S, k, rng=g, iter_limit=iter_limit, ctx=c, want_stats=True)
+        note(kmeans_calls=1, iterations=st["superset_iterations"] + st["set_iterations"], assign_us=st["assign_us"],
+             update_us=st["update_us"])
+        return out
 
     def node(X, g, c):
         """-> (centroid, None) for a leaf, (None, [(child matrix, child generator)]) for a split."""
+        t0 = time.perf_counter()
         S = _sample(X, sample_size, g, c)
+        t1 = time.perf_counter()
         if X.rows <= target_size:                                          # dnc.go:316-319
-            return KMeans(S, 1, rng=g, iter_limit=iter_limit, ctx=c)[0], None
+            cent = km(S, 1, g, c)[0]
+            note(sample_s=t1 - t0, leaf_kmeans_s=time.perf_counter() - t1, leaves=1)
+            return cent, None
         k = min(split_size, max(2, X.rows // target_size))                 # dnc.go:330-339
-        cents = KMeans(S, k, rng=g, iter_limit=iter_limit, ctx=c)
+        cents = km(S, k, g, c)
         del S
+        t2 = time.perf_counter()
         kids = [ch for ch in Split(X, cents, ctx=c) if ch is not None]
+        note(sample_s=t1 - t0, split_kmeans_s=t2 - t1, split_s=time.perf_counter() - t2, splits=1)
         return None, list(zip(kids, g.spawn(len(kids))))
 
     leaves = {}                                                            # path in the tree -> leaf centroid
@@ -153,7 +177,9 @@ def DivideAndConquer(data_matrix, target_size=CENTROID_SIZE, sample_size=SAMPLE_
         while stack:
             X, g, path = stack.pop()
             cent, kids = node(X, g, ctx)
+            t0 = time.perf_counter()
             del X
+            note(release_s=time.perf_counter() - t0)
             if kids is None:
                 leaves[path] = cent
             else:
@@ -184,7 +210,9 @@ def DivideAndConquer(data_matrix, target_size=CENTROID_SIZE, sample_size=SAMPLE_
                     with lock:
                         state["error"] = state["error"] or e
                     cent, kids = None, []
+                t0 = time.perf_counter()
                 del X
+                note(release_s=time.perf_counter() - t0)
                 with lock:
                     if kids is None:
                         leaves[path] = cent

@@ -48,6 +48,10 @@ VS_API int vs_init(int device);            /* select device (LOCAL_RANK); idempo
 VS_API void vs_shutdown(void);
 VS_API const char *vs_last_error(void);
 VS_API int vs_device_info(char *name, size_t name_cap, int *sm_count, size_t *total_mem);
+/* Matrices and index stores live in the device's stream-ordered memory pool, which keeps up to VS_POOL_KEEP_GB (environment,
+ * default 24) of freed memory mapped for the next allocation.  This hands it back to the driver (e.g. before another
+ * library in the process needs the room). */
+VS_API int vs_release_cached_memory(void);
 
 /* compute/cosine.go:60-66,129-135: VectorMatrixCosineSimilarity()/MatrixCosineSimilarity()
  * return (calculate, done).  calculate-closure creation == vs_ctx_create, done() == vs_ctx_destroy.

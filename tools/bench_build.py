@@ -35,7 +35,8 @@ def main():
         del x
     torch.cuda.empty_cache()
     t1 = time.time()
-    cents = dnc.DivideAndConquer(data, target_size=a.target, rng=np.random.default_rng(a.seed), ctx=ctx, workers=a.workers)
+    stats = {}
+    cents = dnc.DivideAndConquer(data, target_size=a.target, rng=np.random.default_rng(a.seed), ctx=ctx, workers=a.workers, stats=stats)
     ctx.sync()
     t2 = time.time()
     assign = torch.empty(a.rows, dtype=torch.int32, device=device)
@@ -53,7 +54,8 @@ def main():
         "generate_s": round(t1 - t0, 2), "divide_and_conquer_s": round(t2 - t1, 2), "reassign_recenter_s": round(t3 - t2, 2),
         "group_into_lists_s": round(t4 - t3, 2), "total_build_s": round(t4 - t1, 2),
         "centroids": int(cents.shape[0]), "list_rows_min_median_max": [int(counts.min()), int(np.median(counts)), int(counts.max())],
-        "workers": a.workers,
+        "workers": a.workers, "host_cores": os.cpu_count(),
+        "where_the_time_went": {k: (round(v, 2) if isinstance(v, float) else int(v)) for k, v in sorted(stats.items())},
         "query_rows_find_themselves": self_hit}), flush=True)
 
 
