@@ -45,6 +45,7 @@ struct vs_matrix {
     int d = 0;
     int d_pad = 0;
     bool owns = true;
+    bool pooled = false;             // storage from the device memory pool (api.cu:pool_alloc) rather than cudaMalloc
     vs::MatView view() const { return vs::MatView{codes, hdr, sums, n, d, d_pad}; }
 };
 
