@@ -285,6 +285,8 @@ def run_b200(a):
             with torch.cuda.stream(streams[i]):
                 h.gather_and_merge(ctx=cx)
 
+    status_bits = {1: 0, 2: 0, 4: 0}
+
     def finish(steps, enqueue=None):
         """Status check of a run of steps (one D2H + sync); a query whose float32 rounding could not be certified even
         after the in-kernel re-score (rare) is finished with literal arithmetic and its step is merged again."""
@@ -296,6 +298,9 @@ def run_b200(a):
             h_status_all[lo:hi].copy_(d_status_all[lo:hi], non_blocking=True)
         stream.synchronize()
         mask = [1 if int((h_status_all[s] & 3).max()) != 0 else 0 for s in steps]
+        for s in steps:
+            for bit in (1, 2, 4):
+                status_bits[bit] += int(((h_status_all[s] & bit) != 0).sum())
         if world > 1:
             # list-stage ambiguity depends on a shard's own rows, so the ranks can disagree; a redo issues a collective (the
             # all-gather of the step's hits): every rank redoes every step that any rank flagged
@@ -594,6 +599,8 @@ def run_b200(a):
         "parity_vs_oracle": sharded_parity,
         "gpu_launches": int(launches),
         "rescored_candidates": ctx.slowpath_count(), "steps_redone_literal": int(redone),
+        "queries_flagged": {"probe_ambiguous": status_bits[1], "list_ambiguous": status_bits[2], "need_more": status_bits[4],
+                            "what": "status words over every step checked (warm-up, timed and end-to-end runs); the first two send a step through the literal path"},
         "clocks": clocks,
     }
 

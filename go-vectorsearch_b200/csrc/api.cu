@@ -149,6 +149,12 @@ extern "C" void vs_ctx_destroy(vs_ctx *c) {
         if (e) cudaEventDestroy(e);
     cudaEventDestroy(c->ev0);
     cudaEventDestroy(c->ev1);
+    if (c->side_stream) {
+        cudaStreamSynchronize(c->side_stream);
+        cudaStreamDestroy(c->side_stream);
+    }
+    if (c->fork_ev) cudaEventDestroy(c->fork_ev);
+    if (c->join_ev) cudaEventDestroy(c->join_ev);
     if (c->owns_stream) cudaStreamDestroy(c->stream);
     delete c;
 }
@@ -1703,13 +1709,30 @@ static int search_enqueue(vs_ctx *c, const vs_index *ix, const MatView &qv, size
         lp.queries = qv;
         lp.k = (int)k;
         lp.pub = fused_pub((int)k, 1);
+        static const bool seed_by_stage = getenv("VS_LM_SEED_STAGE") != nullptr;  // (the first form of the seed, kept for A/B timing)
+        if (!seed_by_stage) {
+            if (!c->side_stream) {
+                CU(cudaStreamCreateWithFlags(&c->side_stream, cudaStreamNonBlocking));
+                CU(cudaEventCreateWithFlags(&c->fork_ev, cudaEventDisableTiming));
+                CU(cudaEventCreateWithFlags(&c->join_ev, cudaEventDisableTiming));
+            }
+            CU(cudaEventRecord(c->fork_ev, c->stream));  // the probe lists are ready here: the seed below forks off this point
+        }
         CU(lm_enqueue_prepare(lp, b.probe, (uint32_t)qv.n, (uint32_t)npe, (uint32_t)ix->C, ix->list_off, ix->list_len, b.lm_count, b.lm_pair_off,
                               b.lm_items_cap, c->stream, &c->launches));
-        {
-            // exact top k of the first 512 rows of every query's nearest list (query-major kernel, first probe only): its k-th
-            // best -- the ~2 % quantile of the query's scores -- seeds the query's running bound, so that the list-major
-            // warps keep almost nothing from their first row on (without it a warp, which sees ~128 rows of an item, keeps
-            // and sorts half of them)
+        // The k-th best document among the first 512 rows of every query's nearest list -- the ~2 % quantile of the query's
+        // scores -- seeds the query's running bound, so that the list-major warps keep almost nothing from their first row
+        // on (without it a warp, which sees ~128 rows of an item, keeps and sorts half of them).
+        if (!seed_by_stage) {
+            // beside the inversion (lm_enqueue_prepare above): both need only the probe lists, and each is a latency chain of
+            // a few tens of microseconds on a fraction of the SMs
+            CU(cudaStreamWaitEvent(c->side_stream, c->fork_ev, 0));
+            CU(lm_enqueue_seed_scan(lp, b.probe, (uint32_t)qv.n, (uint32_t)npe, ix->list_off, ix->list_len, 512, c->side_stream,
+                                    &c->launches));
+            CU(cudaEventRecord(c->join_ev, c->side_stream));
+            CU(cudaStreamWaitEvent(c->stream, c->join_ev, 0));
+        } else {
+            // an exact top k from the query-major kernel, first probe only
             StageParams sp{};
             sp.queries = qv;
             sp.nq = (int)qv.n;

@@ -33,6 +33,9 @@ struct vs_ctx {
     std::vector<cudaEvent_t> prof_events;  // pairs (start, stop), recycled
     size_t prof_used = 0;
     cudaEvent_t phase_ev[6] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};  // batch-search phase boundaries
+    // a second stream for work that is independent of what runs on `stream` (fork / join by events), created on first use
+    cudaStream_t side_stream = nullptr;
+    cudaEvent_t fork_ev = nullptr, join_ev = nullptr;
 };
 
 struct vs_matrix {
@@ -208,6 +211,8 @@ cudaError_t lm_enqueue_prepare(const LmParams &p, const uint32_t *probe, uint32_
                                uint64_t *launches);
 cudaError_t lm_enqueue_seed(const LmParams &p, const float *first_list_sims, const int32_t *first_list_counts, uint32_t nq,
                             cudaStream_t st, uint64_t *launches);
+cudaError_t lm_enqueue_seed_scan(const LmParams &p, const uint32_t *probe, uint32_t nq, uint32_t npe, const uint64_t *list_off,
+                                 const uint64_t *list_len, uint32_t sample, cudaStream_t st, uint64_t *launches);
 cudaError_t lm_enqueue_scan(const LmParams &p, int sm_count, cudaStream_t st, uint64_t *launches);
 cudaError_t lm_enqueue_final(const LmParams &p, uint32_t nq, uint64_t *out_ids, float *out_sims, int32_t *out_counts,
                              uint32_t *out_status, unsigned long long *fix_counter, cudaStream_t st, uint64_t *launches);

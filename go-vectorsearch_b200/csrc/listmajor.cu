@@ -57,13 +57,12 @@ __global__ void __launch_bounds__(1024) lm_items_kernel(const uint32_t *__restri
     const uint32_t per = (C + 1023u) / 1024u;
     const uint32_t lo = threadIdx.x * per, hi = min(C, lo + per);
     uint32_t my_items = 0, my_pairs = 0;
-    for (uint32_t L = lo; L < hi; L++) {
+#pragma unroll 4
+    for (uint32_t L = lo; L < hi; L++) {  // (both loads unconditional: independent, so they fly together)
         const uint32_t c = count[L];
-        if (c) {
-            const uint64_t len = list_len[L];
-            my_items += (uint32_t)((len + kLmSubRows - 1) / kLmSubRows);
-            my_pairs += c;
-        }
+        const uint64_t len = list_len[L];
+        my_items += c ? (uint32_t)((len + kLmSubRows - 1) / kLmSubRows) : 0u;
+        my_pairs += c;
     }
     // exclusive scans over the 1024 threads: shuffles inside a warp, the 32 warp totals by warp 0
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -111,6 +110,93 @@ __global__ void __launch_bounds__(1024) lm_items_kernel(const uint32_t *__restri
     if (threadIdx.x == 1023) *nitems = min(s_items[32 + 31], items_cap);
 }
 
+// The whole inversion in ONE single-block launch when the per-list counters fit in shared memory (C <= kLmFusedMaxC):
+// histogram of the probe lists, items and pair offsets by the same scans as lm_items_kernel, the fill, the per-query
+// side constants and the zeroing of the per-step counters -- instead of four memsets and four launches on the critical
+// path of every step (each a few microseconds that no longer shrink when the store is sharded).
+constexpr uint32_t kLmFusedMaxC = 12288;  // 2 x 4 B per list of dynamic shared memory
+__global__ void __launch_bounds__(1024) lm_prepare_fused_kernel(const uint32_t *__restrict__ probe, uint32_t nq, uint32_t npe,
+                                                               const uint64_t *__restrict__ list_off,
+                                                               const uint64_t *__restrict__ list_len, uint32_t C, LmParams p,
+                                                               uint32_t items_cap) {
+    extern __shared__ uint32_t lm_sm[];
+    uint32_t *hist = lm_sm, *poff = lm_sm + C;
+    __shared__ uint32_t s_items[64], s_pairs[64];
+    const uint32_t npairs = nq * npe;
+    for (uint32_t L = threadIdx.x; L < C; L += 1024) hist[L] = 0;
+    for (uint32_t q = threadIdx.x; q < nq; q += 1024) {
+        p.gcnt[q] = 0;  // (gthr belongs to the seed kernel, which may run beside this one)
+        const float2 h = p.queries.hdr[q];
+        const uint2 sm = p.queries.sums[q];
+        p.sides[q] = make_side(h.x, h.y, sm.x, sm.y, p.queries.d);
+    }
+    if (threadIdx.x == 0) *p.next_item = 0;
+    __syncthreads();
+    for (uint32_t i = threadIdx.x; i < npairs; i += 1024) atomicAdd(&hist[probe[i]], 1u);
+    __syncthreads();
+    const uint32_t per = (C + 1023u) / 1024u;
+    const uint32_t lo = threadIdx.x * per, hi = min(C, lo + per);
+    uint32_t my_items = 0, my_pairs = 0;
+#pragma unroll 4
+    for (uint32_t L = lo; L < hi; L++) {
+        const uint32_t c = hist[L];
+        const uint64_t len = list_len[L];
+        my_items += c ? (uint32_t)((len + kLmSubRows - 1) / kLmSubRows) : 0u;
+        my_pairs += c;
+    }
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    uint32_t vi = my_items, vp = my_pairs;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        const uint32_t a = __shfl_up_sync(FULL, vi, o), b = __shfl_up_sync(FULL, vp, o);
+        if (lane >= o) {
+            vi += a;
+            vp += b;
+        }
+    }
+    if (lane == 31) {
+        s_items[warp] = vi;
+        s_pairs[warp] = vp;
+    }
+    __syncthreads();
+    if (warp == 0) {
+        uint32_t wi = s_items[lane], wp = s_pairs[lane];
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            const uint32_t a = __shfl_up_sync(FULL, wi, o), b = __shfl_up_sync(FULL, wp, o);
+            if (lane >= o) {
+                wi += a;
+                wp += b;
+            }
+        }
+        s_items[32 + lane] = wi;
+        s_pairs[32 + lane] = wp;
+    }
+    __syncthreads();
+    uint32_t it = vi - my_items + (warp ? s_items[32 + warp - 1] : 0u), pr = vp - my_pairs + (warp ? s_pairs[32 + warp - 1] : 0u);
+#pragma unroll 4
+    for (uint32_t L = lo; L < hi; L++) {
+        const uint32_t c = hist[L];
+        const uint64_t st = list_off[L], len = list_len[L];
+        poff[L] = pr;
+        if (c) {
+            for (uint64_t o = 0; o < len; o += kLmSubRows) {
+                if (it < items_cap) p.items[it] = LmItem{(uint32_t)(st + o), (uint32_t)min((uint64_t)kLmSubRows, len - o), pr, c};
+                it++;
+            }
+            pr += c;
+        }
+    }
+    if (threadIdx.x == 1023) *p.nitems = min(s_items[32 + 31], items_cap);
+    __syncthreads();
+    // the fill: hist[L] is consumed as a cursor (from the end)
+    for (uint32_t i = threadIdx.x; i < npairs; i += 1024) {
+        const uint32_t L = probe[i];
+        const uint32_t pos = atomicSub(&hist[L], 1u) - 1u;
+        p.pairs[poff[L] + pos] = i / npe;
+    }
+}
+
 // count[L] is consumed as a cursor (filled from the end): pairs[pair_off[L] + ...] = query
 __global__ void lm_fill_kernel(const uint32_t *__restrict__ probe, uint32_t npairs, uint32_t npe, uint32_t *__restrict__ count,
                                const uint32_t *__restrict__ pair_off, uint32_t *__restrict__ pairs) {
@@ -134,6 +220,82 @@ __global__ void lm_seed_kernel(const float *__restrict__ sims, const int32_t *__
         t = key > 2u ? key - 1u : 0u;
     }
     gthr[q] = t;
+}
+
+// The same bound without the query-major kernel's machinery.  ANY k distinct documents with certified scores bound the
+// k-th best score from below, so nothing here has to be an exact selection: one block of eight warps per query scores
+// the first `sample` rows of the query's nearest list (probe[q][0]) in tiles of 32 rows, a warp sorts each of its tiles in
+// registers (bitonic, shuffles) and contributes the tile's best 16 rows, and the block ranks the 256 contributions, one per
+// document.  Rows whose float32 rounding is not certified are left out (the bound only gets lower).
+constexpr int kSeedWarps = 8, kSeedKeep = 16, kSeedTiles = 16;  // 16 tiles x 32 rows = 512 rows at most
+template <int G, int CPL>
+__global__ void __launch_bounds__(32 * kSeedWarps, 2)
+lm_seed_scan_kernel(MatView rows, const uint64_t *__restrict__ ids, uint64_t id_base, MatView queries,
+                    const uint32_t *__restrict__ probe, uint32_t npe,
+                    const uint64_t *__restrict__ list_off, const uint64_t *__restrict__ list_len, uint32_t sample, int k,
+                    uint32_t *__restrict__ gthr) {
+    constexpr int NG = 32 / G, TR = 32, N = kSeedTiles * kSeedKeep;  // 256 = blockDim.x
+    __shared__ uint64_t s_id[N + 32];
+    __shared__ uint32_t s_key[N + 32], s_meta[N + 32];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const uint32_t q = blockIdx.x;
+    const int D = rows.d, d_pad = rows.d_pad;
+    const bool dedup = ids != nullptr;
+    const uint32_t L = probe[(size_t)q * npe];
+    const uint64_t st = list_off[L];
+    const uint32_t len = (uint32_t)min((uint64_t)min(sample, (uint32_t)(kSeedTiles * TR)), list_len[L]);
+    uint4 qreg[CPL];
+    const uint8_t *qc = queries.codes + (size_t)q * d_pad;
+#pragma unroll
+    for (int t = 0; t < CPL; t++) qreg[t] = *reinterpret_cast<const uint4 *>(qc + ((lane % G) + G * t) * 16);
+    // (its own copy of the query's side constants: this kernel runs beside lm_prepare*, which writes p.sides)
+    const float2 qh = queries.hdr[q];
+    const uint2 qs = queries.sums[q];
+    const SideConst xq = make_side(qh.x, qh.y, qs.x, qs.y, queries.d);
+    for (int tile = warp; tile < kSeedTiles; tile += kSeedWarps) {
+        const uint32_t r0 = (uint32_t)tile * TR;
+        uint32_t key = 0, meta = 0;
+        uint64_t id = kEmptyId;
+        if (r0 < len) {
+            const int nr = (int)min((uint32_t)TR, len - r0);
+            const int iters = (nr + NG - 1) / NG;
+            const uint32_t mydot = tile_dots<G, CPL>(rows.codes, (size_t)(st + r0), nr, d_pad, qreg, lane, iters);
+            const int myr = (lane / G) * iters + (lane % G);
+            if ((lane % G) < iters && myr < nr) {
+                const uint64_t row = st + r0 + (uint32_t)myr;
+                const float2 h = rows.hdr[row];
+                const uint2 sm = rows.sums[row];
+                bool flag;
+                const float sim = score_fast(xq, h.x, h.y, sm.x, sm.y, mydot, D, &flag);
+                if (!flag) {
+                    key = f32_to_key(sim);
+                    meta = (uint32_t)row;
+                    id = ids ? ids[row] : id_base + row;
+                }
+            }
+            warp_sort32(key, meta, id, lane);
+        }
+        if (lane < kSeedKeep) {
+            s_key[tile * kSeedKeep + lane] = key;
+            s_meta[tile * kSeedKeep + lane] = meta;
+            s_id[tile * kSeedKeep + lane] = id;
+        }
+    }
+    __syncthreads();
+    CandBuf src{s_key, s_meta, s_id};
+    // ranked in place of a second buffer: only the k-th key is needed, so dst is a 32-entry window
+    __shared__ uint64_t d_id[32];
+    __shared__ uint32_t d_key[32], d_meta[32];
+    CandBuf dst{d_key, d_meta, d_id};
+    const int uniq = block_rank_small(src, N, dst, 32, dedup);
+    if (threadIdx.x == 0) {
+        uint32_t t = 0;
+        if (uniq >= k && k <= 32) {
+            const uint32_t kk = d_key[k - 1];
+            t = kk > 2u ? kk - 1u : 0u;
+        }
+        gthr[q] = t;
+    }
 }
 
 // The query side of the score identity, once per query and step (compute/cosine.go:26,138-149 folded into integers).
@@ -408,7 +570,10 @@ lm_final_kernel(const uint4 *__restrict__ gbuf, const unsigned int *__restrict__
         if (part == 0 && rk == k - 1) s_thr = mine;
     }
     __syncthreads();
-    const uint32_t thr = s_thr;
+    // The net is cast two keys below the k-th group maximum: a literal re-score moves an uncertified score down by at most
+    // one float32 step (two keys across zero), so the k-th best after re-scoring still lies inside the net and nothing
+    // outside it can matter.
+    const uint32_t thr = s_thr > 2u ? s_thr - 2u : 0u;
     for (uint32_t e = threadIdx.x; e < n; e += kLmFinalThreads) {
         const uint4 v = __ldcg(src + e);
         if (v.x != 0 && v.x >= thr) {
@@ -540,9 +705,18 @@ cudaError_t lm_enqueue_prepare(const LmParams &p, const uint32_t *probe, uint32_
                                uint64_t *launches) {
     const uint32_t npairs = nq * npe;
     cudaError_t e;
+    if (C <= kLmFusedMaxC) {
+        const size_t smem = (size_t)C * 8;
+        if (smem > 40 * 1024) {
+            e = cudaFuncSetAttribute(lm_prepare_fused_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+            if (e != cudaSuccess) return e;
+        }
+        lm_prepare_fused_kernel<<<1, 1024, smem, st>>>(probe, nq, npe, list_off, list_len, C, p, items_cap);
+        if (launches) *launches += 1;
+        return cudaGetLastError();
+    }
     if ((e = cudaMemsetAsync(count, 0, (size_t)C * 4, st)) != cudaSuccess) return e;
     if ((e = cudaMemsetAsync(p.gcnt, 0, (size_t)nq * 4, st)) != cudaSuccess) return e;
-    if ((e = cudaMemsetAsync(p.gthr, 0, (size_t)nq * 4, st)) != cudaSuccess) return e;
     if ((e = cudaMemsetAsync(p.next_item, 0, 4, st)) != cudaSuccess) return e;
     lm_count_kernel<<<(npairs + 255) / 256, 256, 0, st>>>(probe, npairs, count);
     lm_items_kernel<<<1, 1024, 0, st>>>(count, list_off, list_len, C, pair_off, p.items, p.nitems, items_cap);
@@ -556,6 +730,24 @@ cudaError_t lm_enqueue_seed(const LmParams &p, const float *first_list_sims, con
                             cudaStream_t st, uint64_t *launches) {
     lm_seed_kernel<<<(nq + 127) / 128, 128, 0, st>>>(first_list_sims, first_list_counts, nq, p.k, p.gthr);
     if (launches) *launches += 1;
+    return cudaGetLastError();
+}
+
+cudaError_t lm_enqueue_seed_scan(const LmParams &p, const uint32_t *probe, uint32_t nq, uint32_t npe, const uint64_t *list_off,
+                                 const uint64_t *list_len, uint32_t sample, cudaStream_t st, uint64_t *launches) {
+    if (launches) *launches += 1;
+#define VS_LM_SEED(G, CPL)                                                                                                       \
+    lm_seed_scan_kernel<G, CPL><<<nq, 32 * kSeedWarps, 0, st>>>(p.rows, p.ids, p.id_base, p.queries, probe, npe, list_off,          \
+                                                                list_len, sample, p.k, p.gthr)
+    switch (p.rows.d_pad >> 4) {
+        case 48: VS_LM_SEED(16, 3); break;
+        case 32: VS_LM_SEED(32, 1); break;
+        case 64: VS_LM_SEED(32, 2); break;
+        case 96: VS_LM_SEED(32, 3); break;
+        case 24: VS_LM_SEED(8, 3); break;
+        default: return cudaErrorInvalidValue;
+    }
+#undef VS_LM_SEED
     return cudaGetLastError();
 }
 
