@@ -38,7 +38,23 @@ namespace {
 constexpr int kLmWarps = 16;
 constexpr int kLmThreads = 32 * kLmWarps;
 constexpr int kLmStages = 8;        // ring stages of 32 rows (all 32 lanes finish a row's score; 16-row stages leave half idle)
-constexpr int kLmSubRows = 1024;   // rows per item (a longer list is cut: more, evener work items)
+// Rows per work item at most: a longer list is cut into equal parts.  An item costs a fixed ~3 us (the ring drains and
+// refills, the warps load their queries), so fewer, longer items scan faster until the tail of the launch (one item per SM
+// at the end) outweighs it.  VS_LM_SUB_ROWS overrides for experiments.
+static uint32_t lm_sub_rows() {
+    static const uint32_t v = [] {
+        const char *e = getenv("VS_LM_SUB_ROWS");
+        const long x = e ? atol(e) : 0;
+        return (uint32_t)(x >= 64 && x <= (1 << 20) ? x : 1024);
+    }();
+    return v;
+}
+// items of a list of `len` rows: n parts of `per` rows (a multiple of 32) each, the last one shorter
+__device__ __forceinline__ void lm_split(uint64_t len, uint32_t sub, uint32_t *n, uint32_t *per) {
+    const uint32_t cnt = (uint32_t)((len + sub - 1) / sub);
+    *n = cnt;
+    *per = cnt ? (uint32_t)((((len + cnt - 1) / cnt) + 31) & ~(uint64_t)31) : 0u;
+}
 constexpr int kLmCap = 32;         // distinct documents a warp's buffer is cut to (k <= 32 on this path)
 constexpr int kLmWB = kLmCap + 32; // candidates a warp can hold
 
@@ -48,11 +64,11 @@ __global__ void lm_count_kernel(const uint32_t *__restrict__ probe, uint32_t npa
     if (i < npairs) atomicAdd(&count[probe[i]], 1u);
 }
 
-// One block: per list with at least one query, its items (<= kLmSubRows rows each) and the offset of its query list.
+// One block: per list with at least one query, its items (<= sub rows each) and the offset of its query list.
 __global__ void __launch_bounds__(1024) lm_items_kernel(const uint32_t *__restrict__ count, const uint64_t *__restrict__ list_off,
                                                        const uint64_t *__restrict__ list_len,
                                                        uint32_t C, uint32_t *__restrict__ pair_off, LmItem *__restrict__ items,
-                                                       uint32_t *__restrict__ nitems, uint32_t items_cap) {
+                                                       uint32_t *__restrict__ nitems, uint32_t items_cap, uint32_t sub) {
     __shared__ uint32_t s_items[64], s_pairs[64];
     const uint32_t per = (C + 1023u) / 1024u;
     const uint32_t lo = threadIdx.x * per, hi = min(C, lo + per);
@@ -61,7 +77,7 @@ __global__ void __launch_bounds__(1024) lm_items_kernel(const uint32_t *__restri
     for (uint32_t L = lo; L < hi; L++) {  // (both loads unconditional: independent, so they fly together)
         const uint32_t c = count[L];
         const uint64_t len = list_len[L];
-        my_items += c ? (uint32_t)((len + kLmSubRows - 1) / kLmSubRows) : 0u;
+        my_items += c ? (uint32_t)((len + sub - 1) / sub) : 0u;
         my_pairs += c;
     }
     // exclusive scans over the 1024 threads: shuffles inside a warp, the 32 warp totals by warp 0
@@ -100,8 +116,10 @@ __global__ void __launch_bounds__(1024) lm_items_kernel(const uint32_t *__restri
         pair_off[L] = pr;
         if (c) {
             const uint64_t st = list_off[L], len = list_len[L];
-            for (uint64_t o = 0; o < len; o += kLmSubRows) {
-                if (it < items_cap) items[it] = LmItem{(uint32_t)(st + o), (uint32_t)min((uint64_t)kLmSubRows, len - o), pr, c};
+            uint32_t cnt, part;
+            lm_split(len, sub, &cnt, &part);
+            for (uint64_t o = 0; o < len; o += part) {
+                if (it < items_cap) items[it] = LmItem{(uint32_t)(st + o), (uint32_t)min((uint64_t)part, len - o), pr, c};
                 it++;
             }
             pr += c;
@@ -118,7 +136,7 @@ constexpr uint32_t kLmFusedMaxC = 12288;  // 2 x 4 B per list of dynamic shared 
 __global__ void __launch_bounds__(1024) lm_prepare_fused_kernel(const uint32_t *__restrict__ probe, uint32_t nq, uint32_t npe,
                                                                const uint64_t *__restrict__ list_off,
                                                                const uint64_t *__restrict__ list_len, uint32_t C, LmParams p,
-                                                               uint32_t items_cap) {
+                                                               uint32_t items_cap, uint32_t sub) {
     extern __shared__ uint32_t lm_sm[];
     uint32_t *hist = lm_sm, *poff = lm_sm + C;
     __shared__ uint32_t s_items[64], s_pairs[64];
@@ -141,7 +159,7 @@ __global__ void __launch_bounds__(1024) lm_prepare_fused_kernel(const uint32_t *
     for (uint32_t L = lo; L < hi; L++) {
         const uint32_t c = hist[L];
         const uint64_t len = list_len[L];
-        my_items += c ? (uint32_t)((len + kLmSubRows - 1) / kLmSubRows) : 0u;
+        my_items += c ? (uint32_t)((len + sub - 1) / sub) : 0u;
         my_pairs += c;
     }
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -180,8 +198,10 @@ __global__ void __launch_bounds__(1024) lm_prepare_fused_kernel(const uint32_t *
         const uint64_t st = list_off[L], len = list_len[L];
         poff[L] = pr;
         if (c) {
-            for (uint64_t o = 0; o < len; o += kLmSubRows) {
-                if (it < items_cap) p.items[it] = LmItem{(uint32_t)(st + o), (uint32_t)min((uint64_t)kLmSubRows, len - o), pr, c};
+            uint32_t cnt, part;
+            lm_split(len, sub, &cnt, &part);
+            for (uint64_t o = 0; o < len; o += part) {
+                if (it < items_cap) p.items[it] = LmItem{(uint32_t)(st + o), (uint32_t)min((uint64_t)part, len - o), pr, c};
                 it++;
             }
             pr += c;
@@ -317,10 +337,13 @@ struct LmCtl {
 }  // namespace
 
 // ---- 2./3. the scan ------------------------------------------------------------------------------------------------
-template <int G, int CPL, int TR>
-__global__ void __launch_bounds__(kLmThreads, 1)
+// WARPS x STAGES: 16 x 8 = one block per SM; 8 x 4 = two independent blocks per SM with half the ring each, so that one
+// block streams while the other sits in the fixed part of an item (ring drained, queries loading).
+template <int G, int CPL, int TR, int WARPS, int STAGES>
+__global__ void __launch_bounds__(32 * WARPS, 16 / WARPS)
 lm_scan_kernel(const LmParams p) {
     extern __shared__ __align__(128) unsigned char lsm[];
+    constexpr int kLmWarps = WARPS, kLmStages = STAGES;  // (shadow the defaults)
     constexpr int NG = 32 / G;
     constexpr int CAP = kLmCap, WB = kLmWB;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -660,11 +683,11 @@ lm_final_kernel(const uint4 *__restrict__ gbuf, const unsigned int *__restrict__
 // ---------------------------------------------------------------------------------------------------
 static int lm_tile_rows(int d_pad) { return d_pad <= 768 ? 32 : 16; }
 
-static bool lm_geometry(int d_pad, int *stage_bytes, size_t *smem) {
+static bool lm_geometry(int d_pad, int *stage_bytes, size_t *smem, int warps = kLmWarps, int stages = kLmStages) {
     const int sb = (lm_tile_rows(d_pad) * d_pad + 127) & ~127;
     *stage_bytes = sb;
-    *smem = (size_t)kLmStages * sb + (size_t)kLmWarps * kLmWB * 16 + ((sizeof(LmCtl) + 127) & ~size_t(127));
-    return *smem <= (size_t)227 * 1024;
+    *smem = (size_t)stages * sb + (size_t)warps * kLmWB * 16 + ((sizeof(LmCtl) + 127) & ~size_t(127));
+    return (*smem + 1024) * (size_t)(kLmWarps / warps) <= (size_t)227 * 1024;  // (1 KB per block is the system's)
 }
 
 bool lm_supported(int d_pad, int k) {
@@ -678,13 +701,13 @@ bool lm_supported(int d_pad, int k) {
     return k >= 1 && k <= kLmCap && lm_geometry(d_pad, &sb, &smem);
 }
 
-size_t lm_items_cap(size_t n_rows, size_t nq, size_t npe) { return n_rows / kLmSubRows + nq * npe + 16; }
+size_t lm_items_cap(size_t n_rows, size_t nq, size_t npe) { return n_rows / lm_sub_rows() + nq * npe + 16; }
 
-template <int G, int CPL, int TR>
-static cudaError_t lm_launch_scan(LmParams p, int grid, cudaStream_t st) {
+template <int G, int CPL, int TR, int WARPS, int STAGES>
+static cudaError_t lm_launch_scan_t(LmParams p, int grid, cudaStream_t st) {
     size_t smem;
-    if (!lm_geometry(p.rows.d_pad, &p.stage_bytes, &smem)) return cudaErrorInvalidValue;
-    auto kern = lm_scan_kernel<G, CPL, TR>;
+    if (!lm_geometry(p.rows.d_pad, &p.stage_bytes, &smem, WARPS, STAGES)) return cudaErrorInvalidValue;
+    auto kern = lm_scan_kernel<G, CPL, TR, WARPS, STAGES>;
     static bool attr_of[64] = {false};  // (function attributes are per device)
     int dev = 0;
     cudaGetDevice(&dev);
@@ -693,8 +716,19 @@ static cudaError_t lm_launch_scan(LmParams p, int grid, cudaStream_t st) {
         if (e != cudaSuccess) return e;
         attr_of[dev & 63] = true;
     }
-    kern<<<grid, kLmThreads, smem, st>>>(p);
+    kern<<<grid * (kLmWarps / WARPS), 32 * WARPS, smem, st>>>(p);
     return cudaGetLastError();
+}
+template <int G, int CPL, int TR>
+static cudaError_t lm_launch_scan(const LmParams &p, int grid, cudaStream_t st) {
+    static const bool one_block = [] {
+        const char *e = getenv("VS_LM_ONE_BLOCK");
+        return e && atoi(e) != 0;
+    }();
+    int sb;
+    size_t smem;
+    if (!one_block && lm_geometry(p.rows.d_pad, &sb, &smem, 8, 4)) return lm_launch_scan_t<G, CPL, TR, 8, 4>(p, grid, st);
+    return lm_launch_scan_t<G, CPL, TR, 16, 8>(p, grid, st);
 }
 
 // The list stage of a batch, list-major, in three steps (the caller brackets the scan with its profiling marks).
@@ -711,7 +745,7 @@ cudaError_t lm_enqueue_prepare(const LmParams &p, const uint32_t *probe, uint32_
             e = cudaFuncSetAttribute(lm_prepare_fused_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
             if (e != cudaSuccess) return e;
         }
-        lm_prepare_fused_kernel<<<1, 1024, smem, st>>>(probe, nq, npe, list_off, list_len, C, p, items_cap);
+        lm_prepare_fused_kernel<<<1, 1024, smem, st>>>(probe, nq, npe, list_off, list_len, C, p, items_cap, lm_sub_rows());
         if (launches) *launches += 1;
         return cudaGetLastError();
     }
@@ -719,7 +753,7 @@ cudaError_t lm_enqueue_prepare(const LmParams &p, const uint32_t *probe, uint32_
     if ((e = cudaMemsetAsync(p.gcnt, 0, (size_t)nq * 4, st)) != cudaSuccess) return e;
     if ((e = cudaMemsetAsync(p.next_item, 0, 4, st)) != cudaSuccess) return e;
     lm_count_kernel<<<(npairs + 255) / 256, 256, 0, st>>>(probe, npairs, count);
-    lm_items_kernel<<<1, 1024, 0, st>>>(count, list_off, list_len, C, pair_off, p.items, p.nitems, items_cap);
+    lm_items_kernel<<<1, 1024, 0, st>>>(count, list_off, list_len, C, pair_off, p.items, p.nitems, items_cap, lm_sub_rows());
     lm_fill_kernel<<<(npairs + 255) / 256, 256, 0, st>>>(probe, npairs, npe, count, pair_off, p.pairs);
     lm_side_kernel<<<(nq + 127) / 128, 128, 0, st>>>(p.queries, p.sides);
     if (launches) *launches += 4;
