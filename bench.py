@@ -585,10 +585,13 @@ def run_b200(a):
                      "alone": {"achieved": round(float(np.mean(rows_scored[:W])) * ROW_BYTES / (alone_ms / max(1, alone_launches) * 1e-3) / 1e9, 1)
                                if alone_ms > 0 else None,
                                "ms_per_launch": round(alone_ms / max(1, alone_launches), 5), "launches": alone_launches,
+                               "per_unique_byte": {"achieved": round(unique_bytes_per_launch / (alone_ms / max(1, alone_launches) * 1e-3) / 1e9, 1),
+                                                   "frac": round(unique_bytes_per_launch / (alone_ms / max(1, alone_launches) * 1e-3) / 1e9 / peak, 4)}
+                               if alone_ms > 0 else None,
                                "what": "the same kernel during the warm-up steps, which run on one context with nothing "
-                                       "overlapping; in the timed region two contexts take the steps in turn and a scan "
-                                       "launch shares the SMs with the other context's kernels, so its own duration is longer "
-                                       "than its share of the step"},
+                                       "overlapping -- the figure that describes the kernel; in the timed region the contexts "
+                                       "take the steps in turn and a scan launch shares the SMs with the other contexts' kernels, "
+                                       "so its own duration stretches beyond its share of the step"},
                      "note": "achieved = (query, row) pairs scored x 776 B / launch time (algorithmic bytes, SURVEY 8d); traffic = ncu "
                              "dram bytes of one such launch. peak is the driver's read+write copy figure; a read-only stream goes "
                              "higher on this part (ncu: 7.07 TB/s), so a fraction can pass 1"},
