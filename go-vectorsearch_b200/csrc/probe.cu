@@ -424,7 +424,14 @@ cudaError_t launch_probe_batch(const MatView &cent, const MatView &queries, int 
     if (e != cudaSuccess) return e;
     const int qc = nq >= 128 ? 32 : 8;
     const size_t items = ((C + kPsRows - 1) / kPsRows) * ((nq + qc - 1) / qc);
-    const unsigned grid = (unsigned)(items < (size_t)sm_count * 4 ? items : (size_t)sm_count * 4);
+    // (the work items are equal: a grid that does not divide them leaves the last wave part empty -- 1024 items on 592
+    // blocks cost two items' time; VS_PROBE_GRID_MUL: blocks per SM at most, for experiments)
+    static const int grid_mul = [] {
+        const char *e = getenv("VS_PROBE_GRID_MUL");
+        const int v = e ? atoi(e) : 0;
+        return v >= 1 && v <= 32 ? v : 8;
+    }();
+    const unsigned grid = (unsigned)(items < (size_t)sm_count * grid_mul ? items : (size_t)sm_count * grid_mul);
     const size_t smem = (size_t)qc * cent.d_pad + qc * sizeof(SideConst);
 #define VS_PROBE_SCORE2(CPL, QC)                                                                                              \
     do {                                                                                                                      \
