@@ -51,6 +51,9 @@ def parse():
     ap.add_argument("--batch", type=int, default=int(os.environ.get("VS_BENCH_BATCH", 256)))
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-extra", action="store_true", help="skip the config-3 / config-4 side measurements")
+    ap.add_argument("--nccl-exchange", action="store_true",
+                    help="several GPUs: exchange the shard-local hits with an NCCL all-gather before the merge kernel instead "
+                         "of inside it (peer memory)")
     ap.add_argument("--query-major", action="store_true",
                     help="measurement aid: list stage of the batch through the query-major scan (scan.cu) instead of the "
                          "list-major one (listmajor.cu)")
@@ -265,7 +268,13 @@ def run_b200(a):
     NC = a.contexts if a.contexts else 4
     streams = [stream] + [torch.cuda.Stream(device=device) for _ in range(NC - 1)]
     ctxs = [ctx] + [cp.Context(cuda_stream=st.cuda_stream) for st in streams[1:]]
-    hits_all = [pkg.shard.PackedHits(B, k, device, world) for _ in range(NC)]   # local hits (+ gathered / merged for N > 1)
+    # local hits (+ merged for N > 1).  Several GPUs: every rank maps the others' hit buffers (CUDA IPC) and the merge kernel
+    # does the exchange itself over NVLink (shard.PeerHits, vs_exchange_*); --nccl-exchange: an all-gather first.
+    peer_exchange = world > 1 and not a.nccl_exchange
+    if peer_exchange:
+        hits_all = [pkg.shard.PeerHits(B, k, device, world, rank) for _ in range(NC)]
+    else:
+        hits_all = [pkg.shard.PackedHits(B, k, device, world) for _ in range(NC)]
     hits = hits_all[0]
     d_ids, d_sims, d_counts = hits.ids, hits.sims, hits.counts
     f_ids, f_sims, f_counts = hits.out_ids, hits.out_sims, hits.out_counts
@@ -556,6 +565,10 @@ def run_b200(a):
         "dtype": "u8", "data": "synthetic",
         "config": {"workload": workload_name(a), "rows": a.rows, "dim": D, "centroids": a.centroids, "nprobe": a.nprobe,
                    "k": k, "batch": B, "sharding": f"rows striped over {world} rank(s), centroids replicated",
+                   "exchange": ("none (one GPU)" if world == 1 else
+                                "peer memory: every rank's merge kernel reads the others' hits in place over NVLink (CUDA IPC), "
+                                "after a one-warp signal / wait on flag words in peer memory; no collective" if peer_exchange else
+                                "NCCL all-gather of the packed hits, then the merge kernel"),
                    "contexts": f"{NC} search context(s) = CUDA stream(s) taking the steps in turn (search.go:230: one closure "
                                f"per concurrent search)",
                    "l2": "store (rows x 768 B) >> 126 MB L2 and every step uses distinct queries; no flush needed",
@@ -1008,7 +1021,7 @@ def oracle_parity_sharded(pkg, torch, dist, ctx, ix, cent, a, queries, got_ids, 
             bool((got_sims[qi, :n_].view(np.uint32) == w_sims.view(np.uint32)).all())
     return {"queries_checked": nchk, "match": bool(ok), "rows_gathered_from_all_ranks": int(g_rows.shape[0]),
             "oracle_seconds": round(time.perf_counter() - t0, 2),
-            "what": "merged top-k of the last timed step (NCCL all-gather + device merge) vs the CPU oracle over the probed lists "
+            "what": "merged top-k of the last timed step (exchange of the shard-local hits + device merge) vs the CPU oracle over the probed lists "
                     "read back from every rank's shard"}
 
 

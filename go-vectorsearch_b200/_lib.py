@@ -24,6 +24,7 @@ SYMBOLS = [
     "vs_kmeans_step", "vs_kmeans", "vs_kmeans_accumulate_dev", "vs_kmeans_finish_dev", "vs_recenter", "vs_debug_set_argmax_gemm_min", "vs_debug_set_fused", "vs_debug_set_list_major",
     "vs_sharded_create", "vs_sharded_release", "vs_sharded_rows", "vs_sharded_shards", "vs_sharded_shard_rows", "vs_sharded_build_assigned",
     "vs_sharded_upload", "vs_sharded_search", "vs_sharded_ctx_create", "vs_sharded_ctx_destroy", "vs_sharded_search_ctx",
+    "vs_exchange_create", "vs_exchange_handle", "vs_exchange_connect", "vs_exchange_slot", "vs_exchange_merge", "vs_exchange_release",
 ]
 
 
@@ -85,6 +86,14 @@ def load():
         L.vs_index_read_rows.argtypes = [vp, vp, sz, sz, vp, vp]
         L.vs_index_upload.argtypes = [vp, vp, vp, sz, sz, vp, vp, C.POINTER(vp)]
         L.vs_index_create_empty.argtypes = [vp, vp, vp, C.POINTER(vp)]
+        L.vs_exchange_create.argtypes = [C.c_int, C.c_int, sz, C.POINTER(vp)]
+        L.vs_exchange_handle.argtypes = [vp, vp, sz]
+        L.vs_exchange_connect.argtypes = [vp, vp]
+        L.vs_exchange_slot.argtypes = [vp, C.c_int]
+        L.vs_exchange_slot.restype = vp
+        L.vs_exchange_merge.argtypes = [vp, vp, C.c_uint32, sz, sz, sz, sz, sz, vp, vp, vp]
+        L.vs_exchange_release.argtypes = [vp]
+        L.vs_exchange_release.restype = None
         L.vs_index_with_room.argtypes = [vp, vp, sz, sz, C.POINTER(vp)]
         L.vs_index_append.argtypes = [vp, vp, vp, sz, sz, vp, vp]
         L.vs_index_capacity.argtypes = [vp]

@@ -144,6 +144,13 @@ cudaError_t launch_topk_merge(const uint64_t *ids_in, const float *sims_in, cons
 cudaError_t launch_topk_merge_ptrs(const unsigned char *const *bufs, size_t ids_off, size_t sims_off, size_t counts_off, int G, int nq,
                                    int k, uint64_t *ids_out, float *sims_out, int32_t *counts_out, cudaStream_t st);
 
+cudaError_t launch_topk_merge_exchange(const unsigned char *const *bufs, size_t ids_off, size_t sims_off, size_t counts_off, int G, int nq,
+                                       int k, uint64_t *ids_out, float *sims_out, int32_t *counts_out, uint32_t *const *signal,
+                                       const uint32_t *wait, uint32_t step, cudaStream_t st);
+
+cudaError_t launch_topk_merge_exchange_split(const unsigned char *const *bufs, size_t ids_off, size_t sims_off, size_t counts_off, int G,
+                                             int nq, int k, uint64_t *ids_out, float *sims_out, int32_t *counts_out,
+                                             uint32_t *const *signal, const uint32_t *wait, uint32_t step, cudaStream_t st);
 cudaError_t scan_set_certify_scale(float scale);
 cudaError_t argmax_set_certify_scale(float scale);
 

@@ -749,12 +749,43 @@ cudaError_t launch_cosine_fix(const MatView &rows, const double *qnorm, float *s
 // Multi-GPU merge: G shard-local hit lists per query -> global top-k (same order and dedup rule).  Shard g's arrays are
 // either at a fixed stride from one base (one process per GPU: the all-gathered buffer) or anywhere (`bufs`: one packed
 // buffer per shard, possibly in a PEER device's memory -- one process driving G devices reads them over NVLink).
+//
+// One process per GPU without a collective (`xs`): the shards' buffers are the PEER PROCESSES' memory, mapped through CUDA
+// IPC, and the exchange is part of this kernel.  Every rank's hits are complete when its merge kernel starts (stream
+// order), so the kernel first SIGNALS -- a system-scope release store of the step number into every peer's flag word for
+// this rank, over NVLink -- and every block then WAITS (acquire loads of its own flag words) until all ranks have
+// signalled this step, and only then reads the peers' hits in place.  No NCCL launch, no gathered copy: the transfer is
+// the merge's own loads.  (The waiting blocks hold a warp each; nothing on this device depends on them.)
+struct MergeExchange {
+    uint32_t *const *signal;     // [G] address of this rank's flag word in every rank's memory (device array), or null
+    const uint32_t *wait;        // [G] this rank's own flag words
+    uint32_t step;               // the step being exchanged (flags only grow)
+};
 __global__ void topk_merge_kernel(const uint64_t *ids_in, const float *sims_in, const int32_t *counts_in,
                                   size_t rank_stride_bytes, const unsigned char *const *bufs, size_t ids_off, size_t sims_off,
                                   size_t counts_off, int G, int nq, int k, uint64_t *ids_out, float *sims_out,
-                                  int32_t *counts_out) {
+                                  int32_t *counts_out, MergeExchange xs) {
     const int qi = blockIdx.x;
     const int lane = threadIdx.x;
+    if (xs.signal || xs.wait) {
+        if (xs.signal && qi == 0 && lane < G) {
+            __threadfence_system();
+            asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(xs.signal[lane]), "r"(xs.step) : "memory");
+        }
+        if (xs.wait && lane < G) {
+            uint32_t seen;
+            long long t0 = 0;
+            do {
+                asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(seen) : "l"(xs.wait + lane) : "memory");
+                if ((int32_t)(seen - xs.step) < 0) {  // a peer that never arrives must fault, not hang the device: ~10 s
+                    const long long now = clock64();
+                    if (t0 == 0) t0 = now;
+                    else if (now - t0 > 20000000000ll) __trap();
+                }
+            } while ((int32_t)(seen - xs.step) < 0);
+        }
+        __syncwarp();
+    }
     WarpTopK<4> top;
     top.init();
     for (int g = 0; g < G; g++) {
@@ -775,13 +806,13 @@ __global__ void topk_merge_kernel(const uint64_t *ids_in, const float *sims_in, 
             gs = sims_in + (size_t)g * nq * k;
             gc = counts_in + (size_t)g * nq;
         }
-        const int cnt = gc[qi];
+        const int cnt = __ldcg(gc + qi);  // (L2 reads: a peer's buffer changes between launches, and within one after the wait)
         for (int base = 0; base < cnt; base += 32) {
             int j = base + lane;
             bool valid = j < cnt;
             size_t off = (size_t)qi * k + (valid ? j : 0);
-            uint32_t key = valid ? f32_to_key(gs[off]) : 0u;
-            uint64_t id = valid ? gi[off] : kEmptyId;
+            uint32_t key = valid ? f32_to_key(__ldcg(gs + off)) : 0u;
+            uint64_t id = valid ? __ldcg(gi + off) : kEmptyId;
             top.offer(valid, key, 0u, id, lane, true);  // one hit per document across shards, before the cut
         }
     }
@@ -804,7 +835,7 @@ cudaError_t launch_topk_merge(const uint64_t *ids_in, const float *sims_in, cons
                               int G, int nq, int k, uint64_t *ids_out, float *sims_out, int32_t *counts_out, cudaStream_t st) {
     if (k > 128) return cudaErrorInvalidValue;
     topk_merge_kernel<<<nq, 32, 0, st>>>(ids_in, sims_in, counts_in, rank_stride_bytes, nullptr, 0, 0, 0, G, nq, k, ids_out, sims_out,
-                                         counts_out);
+                                         counts_out, MergeExchange{nullptr, nullptr, 0u});
     return cudaGetLastError();
 }
 
@@ -812,7 +843,45 @@ cudaError_t launch_topk_merge_ptrs(const unsigned char *const *bufs, size_t ids_
                                    int k, uint64_t *ids_out, float *sims_out, int32_t *counts_out, cudaStream_t st) {
     if (k > 128) return cudaErrorInvalidValue;
     topk_merge_kernel<<<nq, 32, 0, st>>>(nullptr, nullptr, nullptr, 0, bufs, ids_off, sims_off, counts_off, G, nq, k, ids_out, sims_out,
-                                         counts_out);
+                                         counts_out, MergeExchange{nullptr, nullptr, 0u});
+    return cudaGetLastError();
+}
+
+cudaError_t launch_topk_merge_exchange(const unsigned char *const *bufs, size_t ids_off, size_t sims_off, size_t counts_off, int G, int nq,
+                                       int k, uint64_t *ids_out, float *sims_out, int32_t *counts_out, uint32_t *const *signal,
+                                       const uint32_t *wait, uint32_t step, cudaStream_t st) {
+    if (k > 128 || G > 32) return cudaErrorInvalidValue;
+    topk_merge_kernel<<<nq, 32, 0, st>>>(nullptr, nullptr, nullptr, 0, bufs, ids_off, sims_off, counts_off, G, nq, k, ids_out, sims_out,
+                                         counts_out, MergeExchange{signal, wait, step});
+    return cudaGetLastError();
+}
+
+// The same exchange with the waiting done by ONE warp in a launch of its own, the merge behind it in stream order: a rank
+// that arrives early then holds one warp instead of one per query (the default, see vs_exchange_merge).
+__global__ void exchange_wait_kernel(int G, MergeExchange xs) {
+    const int lane = threadIdx.x;
+    if (lane < G) {
+        __threadfence_system();
+        asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(xs.signal[lane]), "r"(xs.step) : "memory");
+        uint32_t seen;
+        long long t0 = 0;
+        do {
+            asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(seen) : "l"(xs.wait + lane) : "memory");
+            if ((int32_t)(seen - xs.step) < 0) {
+                const long long now = clock64();
+                if (t0 == 0) t0 = now;
+                else if (now - t0 > 20000000000ll) __trap();
+            }
+        } while ((int32_t)(seen - xs.step) < 0);
+    }
+}
+cudaError_t launch_topk_merge_exchange_split(const unsigned char *const *bufs, size_t ids_off, size_t sims_off, size_t counts_off, int G,
+                                             int nq, int k, uint64_t *ids_out, float *sims_out, int32_t *counts_out,
+                                             uint32_t *const *signal, const uint32_t *wait, uint32_t step, cudaStream_t st) {
+    if (k > 128 || G > 32) return cudaErrorInvalidValue;
+    exchange_wait_kernel<<<1, 32, 0, st>>>(G, MergeExchange{signal, wait, step});
+    topk_merge_kernel<<<nq, 32, 0, st>>>(nullptr, nullptr, nullptr, 0, bufs, ids_off, sims_off, counts_off, G, nq, k, ids_out, sims_out,
+                                         counts_out, MergeExchange{nullptr, nullptr, 0u});
     return cudaGetLastError();
 }
 

@@ -10,6 +10,7 @@
 #include <cuda_runtime.h>
 
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <mutex>
 #include <vector>
@@ -350,4 +351,138 @@ extern "C" int vs_sharded_search(vs_sharded *sh, const uint8_t *queries, size_t 
     std::lock_guard<std::mutex> lk(sh->mu);
     if (!sh->default_ctx) SH_VS(vs_sharded_ctx_create(sh, &sh->default_ctx));
     return vs_sharded_search_ctx(sh->default_ctx, queries, nq, nprobe, k, ids_out, sims_out, counts_out);
+}
+
+// ---- one process PER GPU: the exchange of the shard-local hits as part of the merge kernel (vs_exchange_*) ----------
+// The torchrun form of the striped index (shard.py) used one NCCL all-gather of the packed hits per step and then the
+// merge kernel.  The exchange is 32 KB per rank: pure latency, and a collective launch is most of it.  Here every rank
+// maps every other rank's hit buffer through CUDA IPC once; per step a one-warp kernel signals the peers and waits for
+// their signals (flag words in peer memory, system-scope release / acquire) and the merge kernel reads the peers' hits in
+// place over NVLink (scan.cu: exchange_wait_kernel, topk_merge_kernel): the transfer is the merge's own loads.
+// Layout of a rank's allocation: [slot 0 | slot 1 | flags: one 32-bit word per rank], slot_bytes each, the flags at
+// 2 * slot_bytes.  Two slots: a rank may overwrite the slot of step s at step s + 2 because finishing the merge of step
+// s + 1 means every peer had signalled s + 1, which each does only after its own merge of step s (stream order).
+struct vs_exchange {
+    int rank = 0, world = 1, device = 0;
+    size_t slot_bytes = 0;
+    unsigned char *local = nullptr;                 // this rank's allocation
+    std::vector<unsigned char *> peer;              // [world] base pointers (peer[rank] == local)
+    const unsigned char **d_bufs[2] = {nullptr, nullptr};  // device arrays [world]: slot pointers of every rank
+    uint32_t **d_signal = nullptr;                  // device array [world]: &flags_of_rank_r[this rank]
+    bool connected = false;
+};
+
+extern "C" int vs_exchange_create(int rank, int world, size_t slot_bytes, vs_exchange **out) {
+    if (!out || world < 1 || world > 32 || rank < 0 || rank >= world || slot_bytes == 0)
+        return internal_fail(VS_EINVAL, "vs_exchange_create: bad argument (1 <= world <= 32)");
+    const int dev = internal_thread_device();
+    if (dev < 0) return internal_fail(VS_ENODEV, "vs_init not called");
+    cudaSetDevice(dev);
+    vs_exchange *x = new vs_exchange();
+    x->rank = rank;
+    x->world = world;
+    x->device = dev;
+    x->slot_bytes = (slot_bytes + 255) & ~size_t(255);
+    x->peer.assign((size_t)world, nullptr);
+    const size_t total = 2 * x->slot_bytes + 256;
+    if (cudaMalloc(&x->local, total) != cudaSuccess || cudaMemset(x->local, 0, total) != cudaSuccess) {
+        delete x;
+        return internal_fail(VS_ENOMEM, "vs_exchange_create: cudaMalloc");
+    }
+    x->peer[(size_t)rank] = x->local;
+    *out = x;
+    return VS_OK;
+}
+
+extern "C" int vs_exchange_handle(const vs_exchange *x, void *handle_out, size_t cap) {
+    if (!x || !handle_out || cap < sizeof(cudaIpcMemHandle_t)) return internal_fail(VS_EINVAL, "vs_exchange_handle: 64 bytes needed");
+    cudaSetDevice(x->device);
+    cudaIpcMemHandle_t h;
+    if (cudaIpcGetMemHandle(&h, x->local) != cudaSuccess) return internal_fail(VS_ECUDA, "cudaIpcGetMemHandle");
+    memcpy(handle_out, &h, sizeof(h));
+    return VS_OK;
+}
+
+// handles: world x 64 bytes, rank-major (an all-gather of vs_exchange_handle's output).  Every rank must have finished
+// vs_exchange_create before any rank connects (the caller's barrier), and a second barrier after connect makes sure no
+// rank signals a peer that has not opened it yet -- signals go to the OWNER's memory, so only the first is needed for
+// correctness; the flags start at zero.
+extern "C" int vs_exchange_connect(vs_exchange *x, const void *handles) {
+    if (!x || !handles) return internal_fail(VS_EINVAL, "vs_exchange_connect: null argument");
+    cudaSetDevice(x->device);
+    const unsigned char *hb = static_cast<const unsigned char *>(handles);
+    for (int r = 0; r < x->world; r++) {
+        if (r == x->rank) continue;
+        cudaIpcMemHandle_t h;
+        memcpy(&h, hb + (size_t)r * sizeof(h), sizeof(h));
+        void *p = nullptr;
+        const cudaError_t e = cudaIpcOpenMemHandle(&p, h, cudaIpcMemLazyEnablePeerAccess);
+        if (e != cudaSuccess) {
+            char msg[160];
+            snprintf(msg, sizeof(msg), "vs_exchange_connect: cudaIpcOpenMemHandle of rank %d: %s", r, cudaGetErrorString(e));
+            return internal_fail(VS_ECUDA, msg);
+        }
+        x->peer[(size_t)r] = static_cast<unsigned char *>(p);
+    }
+    std::vector<const unsigned char *> bufs((size_t)x->world);
+    std::vector<uint32_t *> sig((size_t)x->world);
+    for (int s = 0; s < 2; s++) {
+        for (int r = 0; r < x->world; r++) bufs[(size_t)r] = x->peer[(size_t)r] + (size_t)s * x->slot_bytes;
+        if (cudaMalloc(&x->d_bufs[s], (size_t)x->world * sizeof(void *)) != cudaSuccess ||
+            cudaMemcpy(x->d_bufs[s], bufs.data(), (size_t)x->world * sizeof(void *), cudaMemcpyHostToDevice) != cudaSuccess)
+            return internal_fail(VS_ECUDA, "vs_exchange_connect: pointer table");
+    }
+    for (int r = 0; r < x->world; r++)
+        sig[(size_t)r] = reinterpret_cast<uint32_t *>(x->peer[(size_t)r] + 2 * x->slot_bytes) + x->rank;
+    if (cudaMalloc(&x->d_signal, (size_t)x->world * sizeof(void *)) != cudaSuccess ||
+        cudaMemcpy(x->d_signal, sig.data(), (size_t)x->world * sizeof(void *), cudaMemcpyHostToDevice) != cudaSuccess)
+        return internal_fail(VS_ECUDA, "vs_exchange_connect: signal table");
+    x->connected = true;
+    return VS_OK;
+}
+
+extern "C" void *vs_exchange_slot(const vs_exchange *x, int slot) {
+    return (x && (slot == 0 || slot == 1)) ? x->local + (size_t)slot * x->slot_bytes : nullptr;
+}
+
+// step: 1, 2, 3, ... (every rank the same sequence); the local hits of this step lie in slot (step & 1), written by
+// earlier work on ctx's stream.  Asynchronous.
+extern "C" int vs_exchange_merge(vs_ctx *c, vs_exchange *x, uint32_t step, size_t ids_off, size_t sims_off, size_t counts_off,
+                                 size_t nq, size_t k, uint64_t *d_ids_out, float *d_sims_out, int32_t *d_counts_out) {
+    if (!c || !x || !d_ids_out || !d_sims_out || !d_counts_out) return internal_fail(VS_EINVAL, "vs_exchange_merge: null argument");
+    if (!x->connected) return internal_fail(VS_EINVAL, "vs_exchange_merge: not connected");
+    if (k > 128) return internal_fail(VS_ERANGE, "k > 128");
+    if ((sims_off | counts_off) & 3 || (ids_off & 7)) return internal_fail(VS_EINVAL, "vs_exchange_merge: misaligned offsets");
+    if (nq == 0) return VS_OK;
+    cudaSetDevice(x->device);
+    const uint32_t *wait = reinterpret_cast<const uint32_t *>(x->local + 2 * x->slot_bytes);
+    // Default: a one-warp launch signals and waits, the merge kernel behind it reads the peers' hits in place.  Measured on
+    // 4 GPUs (config 2): 649.6 K queries/s, the NCCL all-gather form 648.6-650.2 K (end to end 641.6 K vs 630-632 K); with
+    // the signal / wait inside the merge kernel itself (VS_EXCHANGE_ONE_KERNEL=1: one launch, but a rank that arrives
+    // early then holds a warp per query and the list scans of the other contexts lose their second block per SM) 600 K.
+    static const bool split = [] {
+        const char *e = getenv("VS_EXCHANGE_ONE_KERNEL");
+        return !(e && atoi(e) != 0);
+    }();
+    const cudaError_t e = split ? launch_topk_merge_exchange_split(x->d_bufs[step & 1u], ids_off, sims_off, counts_off, x->world, (int)nq,
+                                                                   (int)k, d_ids_out, d_sims_out, d_counts_out, x->d_signal, wait, step,
+                                                                   c->stream)
+                                : launch_topk_merge_exchange(x->d_bufs[step & 1u], ids_off, sims_off, counts_off, x->world, (int)nq, (int)k,
+                                                             d_ids_out, d_sims_out, d_counts_out, x->d_signal, wait, step, c->stream);
+    if (e != cudaSuccess) return internal_fail(VS_ECUDA, cudaGetErrorString(e));
+    c->launches++;
+    return VS_OK;
+}
+
+extern "C" void vs_exchange_release(vs_exchange *x) {
+    if (!x) return;
+    cudaSetDevice(x->device);
+    cudaDeviceSynchronize();
+    for (int r = 0; r < x->world; r++)
+        if (r != x->rank && x->peer[(size_t)r]) cudaIpcCloseMemHandle(x->peer[(size_t)r]);
+    for (int s = 0; s < 2; s++)
+        if (x->d_bufs[s]) cudaFree(x->d_bufs[s]);
+    if (x->d_signal) cudaFree(x->d_signal);
+    if (x->local) cudaFree(x->local);
+    delete x;
 }

@@ -86,6 +86,74 @@ class PackedHits:
                                           vp(self.out_counts)))
 
 
+class _DevArray:
+    """A raw device pointer with the CUDA array interface, so that torch can wrap memory libvscuda owns."""
+
+    def __init__(self, ptr, shape, typestr):
+        self.__cuda_array_interface__ = {"shape": tuple(shape), "typestr": typestr, "data": (int(ptr), False), "version": 2}
+
+
+class PeerHits:
+    """PackedHits without the collective: the shard-local hits live in a libvscuda allocation that every other rank has
+    mapped through CUDA IPC (vs_exchange_*): per step one warp signals the peers over NVLink and waits for their signals
+    (flag words in peer memory), and the merge kernel reads the peers' hits in place.  Same attributes as PackedHits; `ids`, `sims`, `counts`
+    are the views of the slot the NEXT gather_and_merge will exchange.  Construction is collective (one all-gather of the
+    64-byte handles and two barriers); every rank must make the same sequence of gather_and_merge calls."""
+
+    def __init__(self, nq, k, device, world, rank, group=None):
+        import ctypes as C
+        import torch
+        import torch.distributed as dist
+        from . import _lib
+        from .compute import _check
+        self.nq, self.k, self.world, self.rank = nq, k, world, rank
+        self.ids_off = 0
+        self.sims_off = nq * k * 8
+        self.counts_off = self.sims_off + ((nq * k * 4 + 7) // 8) * 8
+        self.nbytes = self.counts_off + ((nq * 4 + 15) // 16) * 16
+        L = self._L = _lib.init()
+        h = C.c_void_p()
+        _check(L.vs_exchange_create(rank, world, self.nbytes, C.byref(h)))
+        self._h = h
+        mine = np.zeros(64, np.uint8)
+        _check(L.vs_exchange_handle(h, C.c_void_p(mine.ctypes.data), 64))
+        every = torch.zeros(64 * world, dtype=torch.uint8, device=device)
+        dist.all_gather_into_tensor(every, torch.from_numpy(mine).to(device), group=group)   # (also: every rank has created)
+        handles = every.cpu().numpy().copy()
+        _check(L.vs_exchange_connect(h, C.c_void_p(handles.ctypes.data)))
+        dist.barrier(group=group)
+        self._views = []
+        for slot in (0, 1):
+            base = int(L.vs_exchange_slot(h, slot))
+            self._views.append((
+                torch.as_tensor(_DevArray(base + self.ids_off, (nq, k), "<i8"), device=device),
+                torch.as_tensor(_DevArray(base + self.sims_off, (nq, k), "<f4"), device=device),
+                torch.as_tensor(_DevArray(base + self.counts_off, (nq,), "<i4"), device=device)))
+        self.step = 1
+        self.out_ids = torch.zeros((nq, k), dtype=torch.int64, device=device)
+        self.out_sims = torch.zeros((nq, k), dtype=torch.float32, device=device)
+        self.out_counts = torch.zeros(nq, dtype=torch.int32, device=device)
+
+    ids = property(lambda self: self._views[self.step & 1][0])
+    sims = property(lambda self: self._views[self.step & 1][1])
+    counts = property(lambda self: self._views[self.step & 1][2])
+
+    def gather_and_merge(self, ctx=None, group=None):
+        """The exchange and the merge in one kernel (asynchronous on ctx's stream)."""
+        import ctypes as C
+        from .compute import _check, default_context
+        ctx = ctx or default_context()
+        vp = lambda t: C.c_void_p(t.data_ptr())
+        _check(self._L.vs_exchange_merge(ctx.handle, self._h, self.step & 0xFFFFFFFF, self.ids_off, self.sims_off, self.counts_off,
+                                         self.nq, self.k, vp(self.out_ids), vp(self.out_sims), vp(self.out_counts)))
+        self.step += 1
+
+    def close(self):
+        if self._h is not None:
+            self._L.vs_exchange_release(self._h)
+            self._h = None
+
+
 # ---- k-means over a store cut into contiguous row blocks (SURVEY.md 8e) -------------------------------------------
 def block_range(n_total, rank, world):
     """Rows [lo, hi) of rank `rank` when the store is cut into `world` contiguous blocks (row order = rank order, which is

@@ -352,6 +352,25 @@ VS_API int vs_recenter_clusters_dev(vs_ctx *ctx, const vs_matrix *data, const in
 /* recenterDbCentroid (dnc.go:417-449): float64 mean of all rows of m in row order -> row776. */
 VS_API int vs_recenter(vs_ctx *ctx, const vs_matrix *m, uint8_t *out_row);
 
+/* ---- one process per GPU: the exchange of the shard-local hits inside the merge kernel -----------------
+ * Replaces the all-gather (a collective launch per step for 32 KB per rank) of the striped index.  Every rank
+ * allocates two hit slots + one flag word per rank (vs_exchange_create; slot_bytes = the packed [ids | sims | counts]
+ * buffer of one step), publishes the allocation's CUDA IPC handle (vs_exchange_handle: 64 bytes, all-gathered by the
+ * caller once over whatever channel the processes share) and maps the other ranks' allocations (vs_exchange_connect; a barrier between
+ * create and connect is the caller's).  Per step every rank lets its search write the hits into
+ * vs_exchange_slot(x, step & 1) and calls vs_exchange_merge on the same context: one warp signals the peers over NVLink
+ * (release store of the step number into their flag words) and waits for their signals, then the merge kernel reads
+ * their hits in place and writes the merged top k (order and one-hit-per-document rule of vs_search).  step = 1, 2, 3, ... identically on every
+ * rank.  A peer that never arrives makes the kernel trap after ~10 s instead of hanging the device. */
+typedef struct vs_exchange vs_exchange;
+VS_API int vs_exchange_create(int rank, int world, size_t slot_bytes, vs_exchange **out);
+VS_API int vs_exchange_handle(const vs_exchange *x, void *handle_out, size_t cap);
+VS_API int vs_exchange_connect(vs_exchange *x, const void *handles);
+VS_API void *vs_exchange_slot(const vs_exchange *x, int slot);
+VS_API int vs_exchange_merge(vs_ctx *ctx, vs_exchange *x, uint32_t step, size_t ids_off, size_t sims_off, size_t counts_off,
+                      size_t nq, size_t k, uint64_t *d_ids_out, float *d_sims_out, int32_t *d_counts_out);
+VS_API void vs_exchange_release(vs_exchange *x);
+
 #ifdef __cplusplus
 }
 #endif
