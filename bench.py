@@ -3,9 +3,12 @@
 
 Workload (BASELINE.json configs[1]): IVF-Flat search on 10M synthetic 768-d uint8-quantized vectors,
 4096 centroids, nprobe=32, top-10.  A "step" is one call of the search path over a batch of `--batch`
-independent queries (default 256: what a server at ~100K queries/s has in flight in 2.5 ms; distinct queries every
-step; the 7.7 GB store is >> the 126 MB L2).  The config's single-query latency is reported beside it
-(`latency_us_batch1`).
+independent queries (default 1024: with 32 probes each over 4096 lists every list is wanted by ~8 queries of the
+batch, so a step streams the whole 7.7 GB store ONCE -- 1.2 ms at the HBM peak -- and scores it for all of them on the
+tensor cores (listmajor.cu, lm_dense_kernel); this is the largest batch whose list scan is still bound by HBM, what a
+server at ~700K queries/s has in flight in 1.5 ms.  `--batch 256` reproduces the earlier lines, `other_configs.
+ivf_batch_sweep` shows 256 and 4096 beside it.  Distinct queries every step; the store is >> the 126 MB L2).  The
+config's single-query latency is reported beside it (`latency_us_batch1`).
 
   value   queries/s with the index and the queries resident in HBM (vs_search_dev + status check)
   e2e     queries/s through the host-buffer C ABI call vs_search (H2D of the query rows and D2H of the
@@ -48,7 +51,7 @@ def parse():
     ap.add_argument("--centroids", type=int, default=4096)
     ap.add_argument("--nprobe", type=int, default=32)
     ap.add_argument("--k", type=int, default=10)
-    ap.add_argument("--batch", type=int, default=int(os.environ.get("VS_BENCH_BATCH", 256)))
+    ap.add_argument("--batch", type=int, default=int(os.environ.get("VS_BENCH_BATCH", 1024)))
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-extra", action="store_true", help="skip the config-3 / config-4 side measurements")
     ap.add_argument("--nccl-exchange", action="store_true",
@@ -545,7 +548,8 @@ def run_b200(a):
     peak_src = "measured (MEASURED_PEAKS.json hbm_gbs)" if "hbm_gbs" in peaks else "fallback 6.65 TB/s (B200_PROFILING.md)"
     scored = rows_scored[W:W + K]
     unique_bytes_per_launch = float(np.mean(rows_unique[W:W + K])) * ROW_BYTES
-    list_major = (not a.query_major) and B >= 16 and B <= 1024 and B * a.nprobe * 2 >= a.centroids and k <= 32
+    list_major = (not a.query_major) and B >= 16 and B <= 4096 and B * a.nprobe * 2 >= a.centroids and k <= 32
+    dense = list_major and B * a.nprobe >= 4 * a.centroids and int(os.environ.get("VS_LM_DENSE_MIN", "4")) > 0
     bytes_per_launch = float(np.mean(scored)) * ROW_BYTES
     scan_ms_avg = scan_ms / max(1, scan_launches)
     achieved = bytes_per_launch / (scan_ms_avg * 1e-3) / 1e9 if scan_ms_avg > 0 else 0.0
@@ -580,8 +584,10 @@ def run_b200(a):
                                       "stream (includes the host's launch latency), and device time per query when 50 such searches "
                                       "are enqueued back to back; one cooperative launch per query (csrc/fused.cu)"} if lat else None,
         "roofline": {"bound": "hbm",
-                     "kernel": "lm_scan_kernel (list-major list scan: every probed list read once for the batch)" if list_major
-                               else "stage_kernel (query-major list scan + fused top-k)",
+                     "kernel": ("lm_dense_kernel (list-major list scan, tensor-core form: every probed list read once and scored "
+                                "against up to 16 of its queries per mma.sync.m16n8k32 pass)" if dense else
+                                "lm_scan_kernel (list-major list scan: every probed list read once for the batch)" if list_major
+                                else "stage_kernel (query-major list scan + fused top-k)"),
                      "achieved": round(achieved, 1),
                      "peak": peak, "peak_source": peak_src, "unit": "GB/s", "frac": round(achieved / peak, 4),
                      "traffic": traffic,
@@ -640,6 +646,46 @@ def other_configs(pkg, torch, ctx, ix, a, device, peaks):
     (profiles/r01_tensor_peaks.json; MEASURED_PEAKS.json carries no int8 figure) and the 4.5 POPS nominal."""
     cp = pkg.compute
     out = {}
+    try:
+        # the headline workload at other batch sizes, one search context, device resident (the headline itself runs on four
+        # contexts; `single_context` repeats its batch size here so that the points are comparable)
+        sweep = {}
+        for nq in sorted({256, a.batch, 4096}):
+            reps = 12
+            qms = []
+            for s in range(reps + 2):
+                x = gen_unit_rows(torch, SEED_QUERY, 9000 + s, nq, device)
+                torch.cuda.synchronize()
+                m = cp.EmptyMatrix(nq, D, ctx=ctx)
+                m.FillFloat32Dev(0, x.data_ptr(), nq, ctx=ctx)
+                ctx.sync()
+                qms.append(m)
+                del x
+            d_ids = torch.zeros((nq, a.k), dtype=torch.int64, device=device)
+            d_sims = torch.zeros((nq, a.k), dtype=torch.float32, device=device)
+            d_counts = torch.zeros(nq, dtype=torch.int32, device=device)
+            d_st = torch.zeros(nq, dtype=torch.int32, device=device)
+            args = (a.nprobe, a.k, d_ids.data_ptr(), d_sims.data_ptr(), d_counts.data_ptr(), d_st.data_ptr())
+            for s in range(2):
+                ix.SearchDev(qms[s], *args, ctx=ctx)
+            ctx.sync()
+            ctx.profile_enable(True)
+            ctx.timer_start()
+            for s in range(reps):
+                ix.SearchDev(qms[2 + s], *args, ctx=ctx)
+            ms = ctx.timer_stop() / reps
+            scan_ms, scan_l = ctx.profile_read()
+            ctx.profile_enable(False)
+            sweep[f"batch_{nq}"] = {"queries_per_s": round(nq / (ms * 1e-3), 1), "ms_per_step": round(ms, 4),
+                                     "list_scan_ms": round(scan_ms / max(1, scan_l), 4),
+                                     "queries_per_probed_list": round(nq * a.nprobe / a.centroids, 1),
+                                     "flagged": int((d_st != 0).sum().item())}
+            del qms, d_ids, d_sims, d_counts, d_st
+        sweep["what"] = ("one search context; the list scan runs its dp4a form below 4 queries per probed list and its tensor-core "
+                         "form (mma.sync m16n8k32, float32 screen, certified float64 score for the pairs that pass) from there on")
+        out["ivf_batch_sweep"] = sweep
+    except Exception as e:  # noqa: BLE001
+        out["ivf_batch_sweep"] = {"error": repr(e)[:300]}
     try:
         tp = json.load(open(os.path.join(ROOT, "profiles", "r01_tensor_peaks.json")))
         int8_peak, src = float(tp["int8_tops_8192"]), "measured cuBLASLt int8 8192^3 (profiles/r01_tensor_peaks.json)"

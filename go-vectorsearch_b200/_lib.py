@@ -21,7 +21,7 @@ SYMBOLS = [
     "vs_index_build", "vs_index_build_assigned", "vs_index_build_dev", "vs_index_create_empty", "vs_index_fill_dev", "vs_index_fill", "vs_index_release",
     "vs_index_rows", "vs_index_lists", "vs_index_cols", "vs_index_list_offsets", "vs_index_read_rows", "vs_index_upload", "vs_index_with_room", "vs_index_append", "vs_index_capacity", "vs_index_list_lengths", "vs_release_cached_memory", "vs_search", "vs_search_flat", "vs_search_flat_gemm", "vs_search_batch_dev", "vs_index_search_batch_dev", "vs_search_dev",
     "vs_search_resolve", "vs_select_probes", "vs_topk_merge_dev", "vs_topk_merge_packed_dev",
-    "vs_kmeans_step", "vs_kmeans", "vs_kmeans_accumulate_dev", "vs_kmeans_finish_dev", "vs_recenter", "vs_debug_set_argmax_gemm_min", "vs_debug_set_fused", "vs_debug_set_list_major",
+    "vs_kmeans_step", "vs_kmeans", "vs_kmeans_accumulate_dev", "vs_kmeans_finish_dev", "vs_recenter", "vs_debug_set_argmax_gemm_min", "vs_debug_set_fused", "vs_debug_set_list_major", "vs_debug_set_lm_dense_min",
     "vs_sharded_create", "vs_sharded_release", "vs_sharded_rows", "vs_sharded_shards", "vs_sharded_shard_rows", "vs_sharded_build_assigned",
     "vs_sharded_upload", "vs_sharded_search", "vs_sharded_ctx_create", "vs_sharded_ctx_destroy", "vs_sharded_search_ctx",
     "vs_exchange_create", "vs_exchange_handle", "vs_exchange_connect", "vs_exchange_slot", "vs_exchange_merge", "vs_exchange_release",
@@ -127,6 +127,7 @@ def load():
         L.vs_debug_set_argmax_gemm_min.argtypes = [sz]
         L.vs_debug_set_fused.argtypes = [C.c_int]
         L.vs_debug_set_list_major.argtypes = [C.c_int]
+        L.vs_debug_set_lm_dense_min.argtypes = [C.c_int]
         L.vs_sharded_create.argtypes = [vp, sz, C.POINTER(vp)]
         L.vs_sharded_release.argtypes = [vp]
         L.vs_sharded_release.restype = None

@@ -84,6 +84,11 @@ def debug_set_list_major(on):
     _check(_lib.init().vs_debug_set_list_major(1 if on else 0))
 
 
+def debug_set_lm_dense_min(queries_per_list):
+    """Test hook: (query, list) pairs per list from which the list-major scan runs on the tensor cores (0 = never; default 4)."""
+    _check(_lib.init().vs_debug_set_lm_dense_min(int(queries_per_list)))
+
+
 class Context:
     """One CUDA stream + scratch arena (vs_ctx). One per closure / goroutine (dnc/dnc.go:349)."""
 

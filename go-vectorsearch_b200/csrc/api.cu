@@ -1542,8 +1542,23 @@ extern "C" int vs_debug_set_list_major(int on) {
     g_lm_enabled = on != 0;
     return VS_OK;
 }
+// Queries per probed list (batch x nprobe / lists) from which the list-major scan takes its tensor-core form; 0 = never.
+static long g_lm_dense_min = [] {
+    const char *e = getenv("VS_LM_DENSE_MIN");
+    return e ? atol(e) : 4l;
+}();
+extern "C" int vs_debug_set_lm_dense_min(int queries_per_list) {
+    g_lm_dense_min = queries_per_list;
+    return VS_OK;
+}
 static bool lm_eligible(const vs_index *ix, size_t nq, size_t npe, size_t k, bool flat) {
-    if (!g_lm_enabled || flat || !ix->centroids || nq < 16 || nq > 1024 || nq < kProbeBatchMin) return false;
+    // (VS_LM_MAX_NQ: measurement aid -- larger batches through the query-major scan)
+    static const size_t max_nq = [] {
+        const char *e = getenv("VS_LM_MAX_NQ");
+        const long v = e ? atol(e) : 0;
+        return (size_t)(v >= 16 && v <= (long)kMaxStageQueries ? v : kMaxStageQueries);
+    }();
+    if (!g_lm_enabled || flat || !ix->centroids || nq < 16 || nq > max_nq || nq < kProbeBatchMin) return false;
     if (nq * npe * 2 < ix->C || ix->n >= (1ull << 30) || ix->C >= (1ull << 30)) return false;
     return lm_supported(ix->data->d_pad, (int)k);
 }
@@ -1762,7 +1777,9 @@ static int search_enqueue(vs_ctx *c, const vs_index *ix, const MatView &qv, size
             CU(lm_enqueue_seed(lp, b.lm_seed_sims, b.lm_seed_counts, (uint32_t)qv.n, c->stream, &c->launches));
         }
         VS(prof_mark(c));
-        CU(lm_enqueue_scan(lp, g_sm_count, c->stream, &c->launches));
+        // several queries per probed list: the tensor-core form of the scan (listmajor.cu, lm_dense_kernel)
+        const bool dense = g_lm_dense_min > 0 && lm_dense_supported(ix->data->d_pad) && qv.n * npe >= (size_t)g_lm_dense_min * ix->C;
+        CU(lm_enqueue_scan(lp, g_sm_count, c->stream, &c->launches, dense));
         VS(prof_mark(c));
         CU(lm_enqueue_final(lp, (uint32_t)qv.n, d_ids, d_sims, d_counts, d_status, c->d_fix_counter, c->stream, &c->launches));
         return VS_OK;

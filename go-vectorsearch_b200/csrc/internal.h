@@ -220,7 +220,8 @@ cudaError_t lm_enqueue_seed(const LmParams &p, const float *first_list_sims, con
                             cudaStream_t st, uint64_t *launches);
 cudaError_t lm_enqueue_seed_scan(const LmParams &p, const uint32_t *probe, uint32_t nq, uint32_t npe, const uint64_t *list_off,
                                  const uint64_t *list_len, uint32_t sample, cudaStream_t st, uint64_t *launches);
-cudaError_t lm_enqueue_scan(const LmParams &p, int sm_count, cudaStream_t st, uint64_t *launches);
+bool lm_dense_supported(int d_pad);
+cudaError_t lm_enqueue_scan(const LmParams &p, int sm_count, cudaStream_t st, uint64_t *launches, bool dense);
 cudaError_t lm_enqueue_final(const LmParams &p, uint32_t nq, uint64_t *out_ids, float *out_sims, int32_t *out_counts,
                              uint32_t *out_status, unsigned long long *fix_counter, cudaStream_t st, uint64_t *launches);
 cudaError_t lm_set_certify_scale(float scale);

@@ -545,6 +545,264 @@ lm_scan_kernel(const LmParams p) {
     }
 }
 
+// ---- 2b. the scan of a DENSE batch: several queries per probed list, scored on the tensor cores ------------------------
+// From about four queries per probed list on (1024 queries x 32 probes over 4096 lists: eight) the dp4a scan above is bound
+// by instruction issue, not by HBM: 28 warp instructions per (query, row) pair.  Here the staged rows of an item are the A
+// operand and up to 16 of the item's queries the B operand of mma.sync.m16n8k32 (u8 x u8 -> s32, exact): a warp takes one
+// 16-row tile of a stage against all the queries of the pass, ~1 warp instruction per pair, and the scan is HBM-bound again
+// up to a few dozen queries per list.  (An m16n8k32 fragment wants, per lane, 4 consecutive K bytes of a row; a lane loads
+// 16 B of its row instead and feeds the four words to two instructions -- the same permutation of K on both operands, which
+// a dot product does not see -- so a row tile costs one 128-bit shared load per instruction.)
+// Same ring as above (4 stages x 32 rows, one bulk copy each, two blocks per SM); warps 2s and 2s+1 own stage s, one row
+// tile each, and the second of them to finish its instructions re-arms the stage before either scores.  A pair at or above
+// the query's bound (the seed of lm_seed_scan_kernel; raised by whoever finds k documents) is appended to the query's
+// candidate list directly -- there is no per-warp list when a warp serves 16 queries -- and lm_final_kernel picks the top k
+// as before: the kept set is a superset of what the dp4a scan keeps, so the emitted hits are the same.
+constexpr int kDnWarps = 8, kDnStages = 4, kDnRows = 32, kDnQ = 16;
+constexpr int kDnQStride(int d_pad) { return d_pad + 64; }  // query rows 64 B apart in bank phase: conflict-free 128-bit loads
+
+struct DnCtl {
+    uint64_t full[kDnStages];
+    unsigned int done[kDnStages];
+    unsigned int item, next_item;
+};
+
+__device__ __forceinline__ void mma_u8(int (&d)[4], uint32_t a0, uint32_t a1, uint32_t a2, uint32_t a3, uint32_t b0, uint32_t b1) {
+    asm volatile("mma.sync.aligned.m16n8k32.row.col.s32.u8.u8.s32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
+                 : "+r"(d[0]), "+r"(d[1]), "+r"(d[2]), "+r"(d[3])
+                 : "r"(a0), "r"(a1), "r"(a2), "r"(a3), "r"(b0), "r"(b1));
+}
+
+// A float32 screen in front of the certified float64 score.  With r = 1/sqrt(P) per side the cosine is
+//   c = (Rx rx D)(Ry ry) dot - (Rx rx s1x)(Ry ry s1y) + (ux rx)(uy ry)  =  t1 - t2 + t3,
+// and a pair is skipped only if  t1 - t2 + t3 + E < bound  in float32, where E covers (a) the float32 evaluation, 2^-20 of
+// |t1| + |t2| + |t3| and of the cancellation scales M r inside ux and uy (at most ~7 float32 roundings per term: 16 are
+// budgeted), (b) everything the certified half-width delta of score_core can hold besides those terms (the per-side parts
+// Ex, Ey, with |c| <= 2) and (c) one float32 step of the final rounding (4e-6).  So a skipped pair's reference score lies
+// strictly below the query's bound whether or not its float32 rounding could have been certified; NaN or Inf anywhere (P <= 0,
+// all-zero vectors, overflow) makes the comparison false and the pair takes the certified path.  ~16 instructions instead of
+// ~150, for the 99 % of the pairs that are nowhere near the bound.
+struct DnRowSide {
+    float Ay, AyS, By, Myp, Ey;
+};
+__device__ __forceinline__ DnRowSide dn_row_side(float mn, float mx, uint32_t s1, uint32_t s2, int D) {
+    const double a = (double)mn, R = (double)mx - a;
+    const double DA = (double)D * (255.0 * a), rs = R * (double)s1, ux = DA + rs, Md = fabs(DA) + fabs(rs);
+    const long long I = (long long)D * (long long)s2 - (long long)s1 * (long long)s1;
+    const double r2i = R * R * (double)I, u2 = ux * ux, P = r2i + u2;
+    const float rP = rsqrtf((float)P);
+    const float eP = 2.0f * fabsf((float)r2i) + 4.0f * fabsf((float)ux) * (float)Md + (float)u2 + fabsf((float)P);
+    DnRowSide o;
+    o.Ay = (float)R * rP;
+    o.AyS = o.Ay * (float)s1;
+    o.By = (float)ux * rP;
+    o.Myp = (float)Md * rP * 1.0001f;
+    o.Ey = 1.5e-16f * (eP * rP * rP + 3.5f * (float)D * (255.0f * (fabsf(mn) + fabsf((float)R)) * rP) + 3.0f * (float)D + 16.0f) + 4.0e-6f;
+    return o;
+}
+struct DnQuerySide {
+    float Ax, Cx, Bx, Mxp, Ex, bound;
+};
+__device__ __forceinline__ DnQuerySide dn_query_side(const SideConst &x, int D, uint32_t thr_key) {
+    const double rx = rsqrt(x.P);
+    DnQuerySide o;
+    o.Ax = (float)(x.R * rx * (double)D);
+    o.Cx = (float)(x.R * rx * (double)x.s1);
+    o.Bx = (float)(x.ux * rx);
+    o.Mxp = (float)((double)x.M * rx) * 1.0001f;
+    o.Ex = 1.5e-16f * ((float)x.epP + 3.5f * (float)D * (float)x.mgs + 3.0f * (float)D + 16.0f);
+    o.bound = thr_key < 2u ? __int_as_float(0xFF800000) : key_to_f32(thr_key);
+    return o;
+}
+// true: the pair cannot reach the query's bound
+__device__ __forceinline__ bool dn_skip(const DnQuerySide &x, const DnRowSide &y, uint32_t dot) {
+    const float t1 = (x.Ax * y.Ay) * __uint2float_rn(dot), t2 = x.Cx * y.AyS, t3 = x.Bx * y.By;
+    const float mag = fabsf(t1) + fabsf(t2) + fabsf(t3) + fmaf(fabsf(y.By), x.Mxp, fabsf(x.Bx) * y.Myp);
+    const float E = fmaf(9.5367431640625e-7f, mag, x.Ex + y.Ey);
+    return (t1 - t2) + t3 + E < x.bound;
+}
+
+// (a broken ring must fault, not hang the device: ~4 s)
+__device__ __forceinline__ void dn_wait(uint32_t bar, uint32_t parity) {
+    uint32_t done, spins = 0;
+    do {
+        asm volatile(
+            "{\n\t.reg .pred p;\n\t"
+            "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+            "selp.u32 %0, 1, 0, p;\n\t}"
+            : "=r"(done)
+            : "r"(bar), "r"(parity)
+            : "memory");
+        if (!done && ++spins > (1u << 28)) __trap();
+    } while (!done);
+}
+
+__global__ void __launch_bounds__(32 * kDnWarps, 2)
+lm_dense_kernel(const LmParams p) {
+    extern __shared__ __align__(128) unsigned char dsm[];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int D = p.rows.d, d_pad = p.rows.d_pad;
+    const int nj = d_pad >> 6;                      // 64 K bytes per step: two instructions
+    const uint32_t stage_bytes = (uint32_t)(kDnRows * d_pad);
+    const uint32_t qstride = (uint32_t)kDnQStride(d_pad);
+    unsigned char *ring = dsm;
+    unsigned char *qsm = dsm + (size_t)kDnStages * stage_bytes;                  // [kDnQ][qstride] query codes of the pass
+    SideConst *sq = reinterpret_cast<SideConst *>(qsm + (size_t)kDnQ * qstride);  // [kDnQ]
+    uint32_t *sqid = reinterpret_cast<uint32_t *>(sq + kDnQ);                     // [kDnQ] query numbers
+    uint32_t *sthr = sqid + kDnQ;                                                 // [kDnQ] bounds (score keys)
+    DnQuerySide *spre = reinterpret_cast<DnQuerySide *>(sthr + kDnQ);             // [kDnQ] float32 screen, query side
+    DnCtl &ctl = *reinterpret_cast<DnCtl *>(spre + kDnQ);
+    const uint32_t nitems = *p.nitems;
+    const int st = warp >> 1, tile = warp & 1;      // my stage, my row tile
+    const int g = lane >> 2, c4 = lane & 3;
+    const uint32_t full = smem_u32(&ctl.full[st]);
+    uint32_t phase = 0;                             // parity of my stage's barrier (only its two warps ever wait on it)
+
+    if (threadIdx.x == 0) {
+        for (int i = 0; i < kDnStages; i++) {
+            mbar_init(smem_u32(&ctl.full[i]), 1);
+            ctl.done[i] = 0;
+        }
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        ctl.item = atomicAdd(p.next_item, 1u);
+    }
+    __syncthreads();
+
+    for (;;) {
+        const uint32_t item = ctl.item;
+        if (item >= nitems) break;
+        const LmItem it = p.items[item];
+        if (threadIdx.x == 0) ctl.next_item = atomicAdd(p.next_item, 1u);
+        const uint32_t nchunks = (it.nrows + kDnRows - 1) / kDnRows;
+        auto arm = [&](uint32_t c) {  // (one lane) chunk c of the item into my stage
+            const uint32_t nr = min((uint32_t)kDnRows, it.nrows - c * kDnRows);
+            const uint32_t cb = nr * (uint32_t)d_pad;
+            mbar_expect_tx(full, cb);
+            bulk_g2s(smem_u32(ring + (size_t)st * stage_bytes), p.rows.codes + (uint64_t)(it.row0 + c * kDnRows) * d_pad, cb, full);
+        };
+        for (uint32_t pass0 = 0; pass0 < it.m; pass0 += kDnQ) {
+            const int mq = (int)min((uint32_t)kDnQ, it.m - pass0);
+            const int ngr = (mq + 7) >> 3;
+            // the rows start to stream while the queries of the pass are fetched
+            if (tile == 0 && lane == 0 && (uint32_t)st < nchunks) arm((uint32_t)st);
+            for (int i = threadIdx.x; i < mq * (d_pad >> 4); i += 32 * kDnWarps) {
+                const int qi = i / (d_pad >> 4), ch = i % (d_pad >> 4);
+                const uint32_t q = p.pairs[it.pair_off + pass0 + qi];
+                *reinterpret_cast<uint4 *>(qsm + (size_t)qi * qstride + ch * 16) =
+                    *reinterpret_cast<const uint4 *>(p.queries.codes + (size_t)q * d_pad + ch * 16);
+            }
+            if ((int)threadIdx.x < mq) {
+                const uint32_t q = p.pairs[it.pair_off + pass0 + threadIdx.x];
+                sqid[threadIdx.x] = q;
+                sq[threadIdx.x] = p.sides[q];
+                const uint32_t thr = __ldcg(p.gthr + q);
+                sthr[threadIdx.x] = thr;
+                spre[threadIdx.x] = dn_query_side(p.sides[q], D, thr);
+            }
+            __syncthreads();
+            const uint32_t a_base = smem_u32(ring + (size_t)st * stage_bytes) + (uint32_t)((tile * 16 + g) * d_pad + c4 * 16);
+            const uint32_t b_base = smem_u32(qsm) + (uint32_t)g * qstride + (uint32_t)c4 * 16u;
+            for (uint32_t c = (uint32_t)st; c < nchunks; c += kDnStages) {
+                // side data of this lane's two rows (tile rows g and g + 8), in flight during the wait
+                const uint32_t nr = min((uint32_t)kDnRows, it.nrows - c * kDnRows);
+                const uint32_t r0 = (uint32_t)(tile * 16 + g), r1 = r0 + 8;
+                const uint32_t row0 = it.row0 + c * kDnRows + r0, row1 = row0 + 8;
+                float2 h0 = make_float2(0.f, 0.f), h1 = h0;
+                uint2 s0 = make_uint2(0, 0), s1 = s0;
+                if (r0 < nr) {
+                    h0 = p.rows.hdr[row0];
+                    s0 = p.rows.sums[row0];
+                }
+                if (r1 < nr) {
+                    h1 = p.rows.hdr[row1];
+                    s1 = p.rows.sums[row1];
+                }
+                dn_wait(full, phase);
+                phase ^= 1u;
+                int acc[2][4];
+#pragma unroll
+                for (int gr = 0; gr < 2; gr++)
+#pragma unroll
+                    for (int e = 0; e < 4; e++) acc[gr][e] = 0;
+                if ((uint32_t)(tile * 16) < nr) {
+                    if (ngr == 1) {
+#pragma unroll 4
+                        for (int j = 0; j < nj; j++) {
+                            const uint4 a0 = lds_u4(a_base + (uint32_t)j * 64u), a1 = lds_u4(a_base + (uint32_t)(8 * d_pad) + (uint32_t)j * 64u);
+                            const uint4 b = lds_u4(b_base + (uint32_t)j * 64u);
+                            mma_u8(acc[0], a0.x, a1.x, a0.y, a1.y, b.x, b.y);
+                            mma_u8(acc[0], a0.z, a1.z, a0.w, a1.w, b.z, b.w);
+                        }
+                    } else {
+#pragma unroll 4
+                        for (int j = 0; j < nj; j++) {
+                            const uint4 a0 = lds_u4(a_base + (uint32_t)j * 64u), a1 = lds_u4(a_base + (uint32_t)(8 * d_pad) + (uint32_t)j * 64u);
+                            const uint4 b = lds_u4(b_base + (uint32_t)j * 64u), b2 = lds_u4(b_base + 8u * qstride + (uint32_t)j * 64u);
+                            mma_u8(acc[0], a0.x, a1.x, a0.y, a1.y, b.x, b.y);
+                            mma_u8(acc[0], a0.z, a1.z, a0.w, a1.w, b.z, b.w);
+                            mma_u8(acc[1], a0.x, a1.x, a0.y, a1.y, b2.x, b2.y);
+                            mma_u8(acc[1], a0.z, a1.z, a0.w, a1.w, b2.z, b2.w);
+                        }
+                    }
+                }
+                __syncwarp();
+                if (lane == 0) {  // the second warp of the stage to get here hands it to the next chunk
+                    const unsigned int old = atomicAdd(&ctl.done[st], 1u);
+                    if (old == 1u) {
+                        ctl.done[st] = 0;
+                        if (c + kDnStages < nchunks) arm(c + kDnStages);
+                    }
+                }
+                const DnRowSide y0 = dn_row_side(h0.x, h0.y, s0.x, s0.y, D), y1 = dn_row_side(h1.x, h1.y, s1.x, s1.y, D);
+                // ---- scores: accumulator e of group gr = (row g + 8 (e >> 1), query 8 gr + 2 c4 + (e & 1)) ----
+                // the screen over this lane's pairs (static register indices), then the few that pass it one by one
+                uint32_t need = 0;
+#pragma unroll
+                for (int gr = 0; gr < 2; gr++) {
+#pragma unroll
+                    for (int e = 0; e < 4; e++) {
+                        const int qi = gr * 8 + c4 * 2 + (e & 1);
+                        const bool hi = (e & 2) != 0;
+                        if (gr < ngr && qi < mq && (hi ? r1 : r0) < nr && !dn_skip(spre[qi], hi ? y1 : y0, (uint32_t)acc[gr][e]))
+                            need |= 1u << (gr * 4 + e);
+                    }
+                }
+                while (need) {
+                    const int bit = __ffs((int)need) - 1;
+                    need &= need - 1u;
+                    const int gr = bit >> 2, e = bit & 3;
+                    const int lo4 = gr ? acc[1][0] : acc[0][0], lo5 = gr ? acc[1][1] : acc[0][1], lo6 = gr ? acc[1][2] : acc[0][2],
+                              lo7 = gr ? acc[1][3] : acc[0][3];
+                    const uint32_t dot = (uint32_t)((e & 2) ? ((e & 1) ? lo7 : lo6) : ((e & 1) ? lo5 : lo4));
+                    const int qi = gr * 8 + c4 * 2 + (e & 1);
+                    const bool hi = (e & 2) != 0;
+                    const float2 h = hi ? h1 : h0;
+                    const uint2 sm = hi ? s1 : s0;
+                    bool flag;
+                    const float sim = score_fast(sq[qi], h.x, h.y, sm.x, sm.y, dot, D, &flag);
+                    const uint32_t key = f32_to_key(sim);
+                    if (key < sthr[qi]) continue;
+                    const uint32_t row = hi ? row1 : row0;
+                    const uint32_t q = sqid[qi];
+                    const uint64_t id = p.ids ? p.ids[row] : p.id_base + row;
+                    const unsigned int at = atomicAdd(p.gcnt + q, 1u);
+                    if (at < (unsigned)p.gcap) {
+                        uint4 v;
+                        v.x = key;
+                        v.y = row | (flag ? kFlagBit : 0u);
+                        v.z = (uint32_t)id;
+                        v.w = (uint32_t)(id >> 32);
+                        p.gbuf[(size_t)q * p.gcap + at] = v;
+                    }
+                }
+            }
+            __syncthreads();  // every chunk of the pass is scored: the ring is idle, the query buffers are free
+        }
+        if (threadIdx.x == 0) ctl.item = ctl.next_item;
+        __syncthreads();
+    }
+}
+
 // ---- 4. per query: best k distinct documents of its candidate list ----------------------------------------------------
 constexpr int kLmFinalThreads = 256;
 constexpr int kLmFinalSurv = 256;  // survivors of the threshold cut that are ranked (more: the caller's literal path)
@@ -785,8 +1043,27 @@ cudaError_t lm_enqueue_seed_scan(const LmParams &p, const uint32_t *probe, uint3
     return cudaGetLastError();
 }
 
-cudaError_t lm_enqueue_scan(const LmParams &p, int sm_count, cudaStream_t st, uint64_t *launches) {
+// Dense form: d_pad a multiple of 64 (two instructions per step) and a 32-row stage of at most 24 KB.
+bool lm_dense_supported(int d_pad) { return d_pad >= 64 && (d_pad & 63) == 0 && d_pad <= 768; }
+
+static cudaError_t lm_launch_dense(const LmParams &p, int sm_count, cudaStream_t st) {
+    const size_t smem = (size_t)kDnStages * kDnRows * p.rows.d_pad + (size_t)kDnQ * kDnQStride(p.rows.d_pad) + kDnQ * sizeof(SideConst) +
+                        2 * kDnQ * 4 + kDnQ * sizeof(DnQuerySide) + ((sizeof(DnCtl) + 127) & ~size_t(127));
+    static bool attr_of[64] = {false};
+    int dev = 0;
+    cudaGetDevice(&dev);
+    if (!attr_of[dev & 63]) {
+        cudaError_t e = cudaFuncSetAttribute(lm_dense_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (e != cudaSuccess) return e;
+        attr_of[dev & 63] = true;
+    }
+    lm_dense_kernel<<<2 * sm_count, 32 * kDnWarps, smem, st>>>(p);
+    return cudaGetLastError();
+}
+
+cudaError_t lm_enqueue_scan(const LmParams &p, int sm_count, cudaStream_t st, uint64_t *launches, bool dense) {
     if (launches) *launches += 1;
+    if (dense) return lm_launch_dense(p, sm_count, st);
     switch (p.rows.d_pad >> 4) {
         case 48: return lm_launch_scan<16, 3, 32>(p, sm_count, st);  // 768-d (nomic-embed-text)
         case 32: return lm_launch_scan<32, 1, 32>(p, sm_count, st);  // 512-d (noop/ai.go)

@@ -78,6 +78,10 @@ VS_API int vs_debug_set_fused(int on);
  * list-major one (listmajor.cu: every probed list read once for all the queries of the batch that probe it; replaces
  * server/search.go:241-273 for a batch).  Default 1. */
 VS_API int vs_debug_set_list_major(int on);
+/* Test hook: the list-major scan takes its tensor-core form (lm_dense_kernel: the staged rows of a list against up to 16
+ * of its queries per mma.sync.m16n8k32 pass) when the batch has at least this many (query, list) pairs per list; 0 = never
+ * (always the dp4a form), 1 = whenever the row width allows.  Default 4.  Same hits either way. */
+VS_API int vs_debug_set_lm_dense_min(int queries_per_list);
 /* CUDA-event timing on the ctx stream (bench.py): start/stop bracket, elapsed in ms after sync. */
 VS_API int vs_ctx_timer_start(vs_ctx *ctx);
 VS_API int vs_ctx_timer_stop(vs_ctx *ctx, float *ms_out);

@@ -9,6 +9,15 @@ from test_gpu_search import _check, _crowded_inputs, _index_inputs
 pytestmark = pytest.mark.gpu
 
 
+@pytest.fixture(params=["dp4a", "dense"], autouse=True)
+def scan_form(request, vs):
+    """Every test runs twice: with the dp4a form of the scan (lm_scan_kernel) and with the tensor-core form
+    (lm_dense_kernel) wherever the row width allows it -- the library picks by queries per list on its own."""
+    vs.compute.debug_set_lm_dense_min(0 if request.param == "dp4a" else 1)
+    yield request.param
+    vs.compute.debug_set_lm_dense_min(4)
+
+
 def _same_as_query_major(vs, ix, qs, nprobe, k, ctx=None):
     a = ix.Search(qs, nprobe, k, ctx=ctx)
     vs.compute.debug_set_list_major(False)
@@ -134,3 +143,72 @@ def test_list_major_large_batch_equals_query_major(vs):
         ids, sims, counts = _same_as_query_major(vs, ix, qs, 16, 10, ctx=ctx)
         assert (counts == 10).all()
     ctx.close()
+
+
+def test_dense_form_passes_and_partial_groups(vs, oracle, scan_form):
+    """Queries per list around the pass and group sizes of the tensor-core form (8 per instruction group, 16 per pass):
+    1, 7, 8, 9, 16, 17 and 33 queries on the lists of one small index; list lengths around the 16-row tiles and 32-row stages."""
+    d, C = 768, 7
+    sizes = [15, 16, 17, 33, 1100, 64, 2049]
+    n = sum(sizes)
+    rows = oracle.quantize_matrix_f32(unit_rows(n, d, 21))
+    lists = np.repeat(np.arange(C), sizes).astype(np.uint32)
+    doc = np.random.default_rng(4).permutation(n).astype(np.uint64)
+    offs = np.concatenate([[0], np.cumsum(sizes)]).astype(np.uint64)
+    cent = oracle.quantize_matrix_f32(unit_rows(C, d, 22))
+    ix = vs.ivf.Index.build(rows, doc, offs, cent)
+    for nq in (16, 17, 33, 91):
+        qs = oracle.quantize_matrix_f32(unit_rows(nq, d, 23 + nq))
+        for nprobe in (1, 3, 7):
+            _check(oracle, ix, qs, cent, rows, lists, doc, nprobe, 10)
+
+
+def test_default_form_follows_queries_per_list(vs, oracle):
+    """With the default setting a sparse batch runs the dp4a kernel and a dense one the tensor-core kernel; both give the
+    query-major hits (launch counts are equal, so the forms are told apart only by their results being checked here)."""
+    vs.compute.debug_set_lm_dense_min(4)
+    n, d, C = 40000, 768, 128
+    rows, cent, lists, doc = _index_inputs(oracle, n, d, C, 31)
+    ix = vs.ivf.Index.build_assigned(rows, doc, lists, cent)
+    for nq, nprobe in ((32, 8), (128, 8), (512, 16)):   # 2, 8 and 64 queries per list
+        qs = oracle.quantize_matrix_f32(unit_rows(nq, d, 100 + nq))
+        _same_as_query_major(vs, ix, qs, nprobe, 10)
+
+
+def _hard_rows(n, d, seed):
+    """Rows that stress the score identity and the float32 screen of the dense form: large common offsets (strong
+    cancellation inside the identity), tiny and huge ranges, all-positive data, constant rows, all-zero rows, a few
+    near-duplicates (scores a float32 step apart)."""
+    rng = np.random.default_rng(seed)
+    x = rng.standard_normal((n, d)).astype(np.float64)
+    fam = rng.integers(0, 8, n)
+    x[fam == 0] += 40.0                                   # offset >> spread
+    x[fam == 1] = np.abs(x[fam == 1]) * 1e-6              # tiny, all positive
+    x[fam == 2] *= 1e6                                    # huge
+    x[fam == 3] = x[fam == 3] * 1e-3 + 7.0                # nearly constant
+    x[fam == 4] = np.round(x[fam == 4] * 3)               # few distinct values
+    x[fam == 5, : d // 2] = 0                             # half zero
+    const = np.flatnonzero(fam == 6)[:5]
+    x[const] = 3.25                                       # constant rows (range 0)
+    zero = np.flatnonzero(fam == 6)[5:9]
+    x[zero] = 0.0                                         # all-zero rows
+    base = np.flatnonzero(fam == 7)
+    for i in range(0, len(base) - 1, 2):                  # near-duplicates
+        x[base[i + 1]] = x[base[i]] * (1.0 + 1e-7 * rng.standard_normal(d))
+    return x.astype(np.float32)
+
+
+def test_screen_never_drops_a_hit_on_hard_data(vs, oracle):
+    """The dense form's float32 screen against data families chosen to break it; every query against the oracle."""
+    d, C, n = 768, 6, 4200
+    rows = oracle.quantize_matrix_f32(_hard_rows(n, d, 5))
+    cent = oracle.quantize_matrix_f32(_hard_rows(C, d, 6))
+    lists = (np.arange(n) % C).astype(np.uint32)
+    order = np.argsort(lists, kind="stable")
+    rows, lists = rows[order], lists[order]
+    doc = np.random.default_rng(1).permutation(n).astype(np.uint64)
+    offs = np.concatenate([[0], np.cumsum(np.bincount(lists, minlength=C))]).astype(np.uint64)
+    ix = vs.ivf.Index.build(rows, doc, offs, cent)
+    qs = oracle.quantize_matrix_f32(_hard_rows(40, d, 7))
+    for nprobe, k in ((2, 10), (6, 32)):
+        _check(oracle, ix, qs, cent, rows, lists, doc, nprobe, k)
