@@ -57,6 +57,9 @@ def parse():
     ap.add_argument("--nccl-exchange", action="store_true",
                     help="several GPUs: exchange the shard-local hits with an NCCL all-gather before the merge kernel instead "
                          "of inside it (peer memory)")
+    ap.add_argument("--replicated-probe", action="store_true",
+                    help="several GPUs: every rank selects the probe lists of the whole batch (the earlier form) instead of "
+                         "its 1/N of the batch followed by an all-gather of the lists")
     ap.add_argument("--query-major", action="store_true",
                     help="measurement aid: list stage of the batch through the query-major scan (scan.cu) instead of the "
                          "list-major one (listmajor.cu)")
@@ -282,6 +285,28 @@ def run_b200(a):
     d_ids, d_sims, d_counts = hits.ids, hits.sims, hits.counts
     f_ids, f_sims, f_counts = hits.out_ids, hits.out_sims, hits.out_counts
     d_status_all = torch.zeros((nsteps, B), device=device, dtype=torch.int32)   # one status row per step
+    # Several GPUs: the probe stage is shared -- every rank selects the probe lists of its 1/N of the batch, the lists are
+    # all-gathered (shard.SharedProbes), and every rank scans its stripe of the lists for the whole batch.
+    shared_probe = world > 1 and not a.replicated_probe and B % world == 0 and 0 < a.nprobe < a.centroids
+    if shared_probe:
+        probes_all = [pkg.shard.SharedProbes(B, a.nprobe, device, world, rank) for _ in range(NC)]
+        mine = probes_all[0].rows_of()
+        qslices = []
+        for s in range(nsteps):
+            m = cp.EmptyMatrix(B // world, D, ctx=ctx)
+            m.LoadRows(0, np.ascontiguousarray(qhost[s][mine]), ctx=ctx)
+            ctx.sync()
+            qslices.append(m)
+
+    def search_dev(i, cx, q, q_share, st, h):
+        """Both stages of one step on context i (asynchronous)."""
+        if shared_probe:
+            with torch.cuda.stream(streams[i]):
+                d_probe = probes_all[i].select_and_gather(ix, q_share, st, cx)
+            ix.SearchDevProbed(q, a.nprobe, k, d_probe.data_ptr(), h.ids.data_ptr(), h.sims.data_ptr(), h.counts.data_ptr(),
+                               st.data_ptr(), ctx=cx)
+        else:
+            ix.SearchDev(q, a.nprobe, k, h.ids.data_ptr(), h.sims.data_ptr(), h.counts.data_ptr(), st.data_ptr(), ctx=cx)
     h_status_all = torch.zeros((nsteps, B), dtype=torch.int32).pin_memory()
 
     def enqueue_dev(s, resolve=False):  # (NC is rebound around the warm-up: nonlocal lookup at call time)
@@ -290,7 +315,7 @@ def run_b200(a):
         i = s % NC
         h, cx = hits_all[i], ctxs[i]
         q, st = qmats[s], d_status_all[s]
-        ix.SearchDev(q, a.nprobe, k, h.ids.data_ptr(), h.sims.data_ptr(), h.counts.data_ptr(), st.data_ptr(), ctx=cx)
+        search_dev(i, cx, q, qslices[s] if shared_probe else None, st, h)
         if resolve:
             ix.Resolve(q, a.nprobe, k, h.ids.data_ptr(), h.sims.data_ptr(), h.counts.data_ptr(), st.data_ptr(), ctx=cx)
         if world > 1:
@@ -349,8 +374,7 @@ def run_b200(a):
     ctx.profile_enable(False)
     NC = NC_run
     for i in range(1, NC):      # the other contexts grow their scratch before the clock starts
-        ix.SearchDev(qmats[0], a.nprobe, k, hits_all[i].ids.data_ptr(), hits_all[i].sims.data_ptr(), hits_all[i].counts.data_ptr(),
-                     d_status_all[0].data_ptr(), ctx=ctxs[i])
+        search_dev(i, ctxs[i], qmats[0], qslices[0] if shared_probe else None, d_status_all[0], hits_all[i])
         ctxs[i].sync()
     barrier()
     # ---- single-query latency (batch 1), device resident; measured before the sustained throughput run, whose power
@@ -428,6 +452,7 @@ def run_b200(a):
     # before it reuses that context's host buffers), like NC goroutines each making one synchronous search call at a time.
     e_hq = [torch.empty((B, ROW_BYTES), dtype=torch.uint8).pin_memory() for _ in range(NC)]
     e_q = [cp.EmptyMatrix(B, D, ctx=ctxs[i]) for i in range(NC)]
+    e_qs = [cp.EmptyMatrix(B // world, D, ctx=ctxs[i]) for i in range(NC)] if shared_probe else None
     e_res = [(torch.empty((B, k), dtype=torch.int64).pin_memory(), torch.empty((B, k), dtype=torch.float32).pin_memory(),
               torch.empty(B, dtype=torch.int32).pin_memory()) for _ in range(NC)]
     e_ev = [None] * NC
@@ -439,8 +464,10 @@ def run_b200(a):
             e_ev[i].synchronize()
         e_hq[i].numpy()[:] = qhost[s]
         e_q[i].LoadRows(0, e_hq[i].numpy(), ctx=cx)          # H2D from pinned memory + layout kernel, asynchronous
+        if shared_probe:                                      # (this rank's share once more, as the probe stage's own matrix)
+            e_qs[i].LoadRows(0, e_hq[i].numpy()[mine], ctx=cx)
         st = d_status_all[s]
-        ix.SearchDev(e_q[i], a.nprobe, k, h.ids.data_ptr(), h.sims.data_ptr(), h.counts.data_ptr(), st.data_ptr(), ctx=cx)
+        search_dev(i, cx, e_q[i], e_qs[i] if shared_probe else None, st, h)
         if resolve:
             ix.Resolve(e_q[i], a.nprobe, k, h.ids.data_ptr(), h.sims.data_ptr(), h.counts.data_ptr(), st.data_ptr(), ctx=cx)
         with torch.cuda.stream(streams[i]):
@@ -569,6 +596,10 @@ def run_b200(a):
         "dtype": "u8", "data": "synthetic",
         "config": {"workload": workload_name(a), "rows": a.rows, "dim": D, "centroids": a.centroids, "nprobe": a.nprobe,
                    "k": k, "batch": B, "sharding": f"rows striped over {world} rank(s), centroids replicated",
+                   "probe_stage": ("one GPU" if world == 1 else
+                                   f"shared: every rank selects the probe lists of its {B // world} queries of the batch, two NCCL "
+                                   f"all-gathers ({B // world * a.nprobe * 4} + {B // world * 4} B per rank) hand every rank the lists of "
+                                   f"all {B}" if shared_probe else "replicated on every rank"),
                    "exchange": ("none (one GPU)" if world == 1 else
                                 "peer memory: every rank's merge kernel reads the others' hits in place over NVLink (CUDA IPC), "
                                 "after a one-warp signal / wait on flag words in peer memory; no collective" if peer_exchange else

@@ -19,7 +19,7 @@ SYMBOLS = [
     "vs_matrix_release", "vs_matrix_rows", "vs_matrix_cols", "vs_matrix_read_rows", "vs_matrix_load_spool", "vs_matrix_save_spool", "vs_matrix_gather", "vs_matrix_split_dev", "vs_matrix_split", "vs_reassign_recenter", "vs_recenter_clusters_dev",
     "vs_cosine_1xN", "vs_dot_1xN", "vs_argmax_MxN", "vs_argmax_MxN_dev",
     "vs_index_build", "vs_index_build_assigned", "vs_index_build_dev", "vs_index_create_empty", "vs_index_fill_dev", "vs_index_fill", "vs_index_release",
-    "vs_index_rows", "vs_index_lists", "vs_index_cols", "vs_index_list_offsets", "vs_index_read_rows", "vs_index_upload", "vs_index_with_room", "vs_index_append", "vs_index_capacity", "vs_index_list_lengths", "vs_release_cached_memory", "vs_search", "vs_search_flat", "vs_search_flat_gemm", "vs_search_batch_dev", "vs_index_search_batch_dev", "vs_search_dev",
+    "vs_index_rows", "vs_index_lists", "vs_index_cols", "vs_index_list_offsets", "vs_index_read_rows", "vs_index_upload", "vs_index_with_room", "vs_index_append", "vs_index_capacity", "vs_index_list_lengths", "vs_release_cached_memory", "vs_search", "vs_search_flat", "vs_search_flat_gemm", "vs_search_batch_dev", "vs_index_search_batch_dev", "vs_search_dev", "vs_probe_dev", "vs_search_dev_probed",
     "vs_search_resolve", "vs_select_probes", "vs_topk_merge_dev", "vs_topk_merge_packed_dev",
     "vs_kmeans_step", "vs_kmeans", "vs_kmeans_accumulate_dev", "vs_kmeans_finish_dev", "vs_recenter", "vs_debug_set_argmax_gemm_min", "vs_debug_set_fused", "vs_debug_set_list_major", "vs_debug_set_lm_dense_min",
     "vs_sharded_create", "vs_sharded_release", "vs_sharded_rows", "vs_sharded_shards", "vs_sharded_shard_rows", "vs_sharded_build_assigned",
@@ -156,6 +156,8 @@ def load():
         L.vs_kmeans_finish_dev.argtypes = [vp, vp, vp, vp, vp, C.POINTER(vp), C.POINTER(C.c_int)]
         L.vs_index_search_batch_dev.argtypes = [vp, vp, vp, sz, vp, vp, vp, vp]
         L.vs_search_dev.argtypes = [vp, vp, vp, sz, sz, vp, vp, vp, vp]
+        L.vs_probe_dev.argtypes = [vp, vp, vp, sz, vp, vp]
+        L.vs_search_dev_probed.argtypes = [vp, vp, vp, sz, sz, vp, vp, vp, vp, vp]
         L.vs_search_resolve.argtypes = [vp, vp, vp, sz, sz, vp, vp, vp, vp, C.POINTER(C.c_int)]
         L.vs_select_probes.argtypes = [vp, vp, vp, sz, sz, vp, vp]
         L.vs_topk_merge_dev.argtypes = [vp, vp, vp, vp, sz, sz, sz, vp, vp, vp]

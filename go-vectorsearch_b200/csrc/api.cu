@@ -1600,6 +1600,32 @@ __global__ void probe_from_topk_kernel(const uint64_t *ids, const float *sims, c
     }
 }
 
+// Next-stage tile count of every query from probe lists that were selected elsewhere (one warp per query).  A list number
+// outside the index (a corrupted exchange) becomes list 0 and flags the query for the literal path.
+__global__ void probe_qtiles_kernel(uint32_t *probe, uint32_t nq, int npe, uint32_t C, const uint64_t *list_len, uint32_t tile_rows,
+                                    uint32_t *out_qtiles, uint32_t *status) {
+    const uint32_t q = blockIdx.x * 4 + (threadIdx.x >> 5);
+    const int lane = threadIdx.x & 31;
+    if (q >= nq) return;
+    uint32_t tiles = 0;
+    bool bad = false;
+    for (int r = lane; r < npe; r += 32) {
+        uint32_t L = probe[(size_t)q * npe + r];
+        if (L >= C) {
+            bad = true;
+            L = 0;
+            probe[(size_t)q * npe + r] = 0;
+        }
+        tiles += (uint32_t)((list_len[L] + tile_rows - 1) / tile_rows);
+    }
+    for (int o = 16; o > 0; o >>= 1) tiles += __shfl_xor_sync(0xFFFFFFFFu, tiles, o);
+    bad = __any_sync(0xFFFFFFFFu, bad);
+    if (lane == 0) {
+        out_qtiles[q] = tiles ? tiles : 1u;
+        if (bad) status[q] |= kStatusProbeAmbiguous;
+    }
+}
+
 // One query: probe stage, selection, list stage and top-k in ONE cooperative launch (fused.cu).  Queries it cannot decide
 // (an uncertified score inside a window) get the usual status bits and are finished by the resolve path.
 static bool g_fused_enabled = true;
@@ -1654,8 +1680,11 @@ static int fused_enqueue(vs_ctx *c, const vs_index *ix, const MatView &qv, size_
 static int search_enqueue(vs_ctx *c, const vs_index *ix, const MatView &qv, size_t nq_launch, const uint32_t *d_select,
                           size_t npe, size_t k, int kpl1, int kpl2, bool flat, bool exact, const SearchBufs &b,
                           uint64_t *d_ids, float *d_sims, int32_t *d_counts, uint32_t *d_status, float *d_probe_sims,
-                          bool stage1_only) {
-    if (fused_eligible(c, ix, nq_launch, d_select, npe, flat, exact, stage1_only, kpl2))
+                          bool stage1_only, const uint32_t *d_probe_in = nullptr) {
+    // d_probe_in: the probe lists were selected elsewhere (another device's share of a sharded probe stage, vs_probe_dev);
+    // d_status already holds that stage's bits.  Only the plain batch form (no selection, certified arithmetic).
+    const bool given = d_probe_in != nullptr && !flat && !exact && !d_select && nq_launch == qv.n && !stage1_only;
+    if (!given && fused_eligible(c, ix, nq_launch, d_select, npe, flat, exact, stage1_only, kpl2))
         return fused_enqueue(c, ix, qv, npe, k, kpl2, flat, b, d_ids, d_sims, d_counts, d_status);
     StageParams p{};
     bool chained = false;
@@ -1667,7 +1696,12 @@ static int search_enqueue(vs_ctx *c, const vs_index *ix, const MatView &qv, size
     p.out_status = d_status;
     p.fix_counter = c->d_fix_counter;
     const uint32_t tr1 = exact ? 32 : b.tile_rows1, tr2 = exact ? 32 : b.tile_rows2;
-    if (!flat && !exact && !d_select && b.gemm_probe && nq_launch == qv.n) {
+    if (given) {
+        CU(cudaMemcpyAsync(b.probe, d_probe_in, qv.n * npe * sizeof(uint32_t), cudaMemcpyDeviceToDevice, c->stream));
+        probe_qtiles_kernel<<<(unsigned)((qv.n + 3) / 4), 128, 0, c->stream>>>(b.probe, (uint32_t)qv.n, (int)npe, (uint32_t)ix->C, ix->list_len,
+                                                                             tr2, b.qtiles, d_status);
+        c->launches++;
+    } else if (!flat && !exact && !d_select && b.gemm_probe && nq_launch == qv.n) {
         const MatView cent = ix->centroids->view();
         GemmBufs gb;
         gemm_take(b.gp_scratch, b.gp, qv.n, &gb);
@@ -1943,6 +1977,46 @@ extern "C" int vs_search_dev(vs_ctx *c, const vs_index *ix, const vs_matrix *que
     search_take(a, ix, nq, &s);
     return search_enqueue(c, ix, queries->view(), nq, nullptr, s.npe, k, s.kpl1, s.kpl2, s.flat, false, s.b, d_ids, d_sims,
                           d_counts, d_status, nullptr, false);
+}
+
+// The probe stage alone, device to device: the nprobe nearest lists of every query (search.go:205-223) and the stage's
+// status bits.  With vs_search_dev_probed it lets G devices that hold stripes of one index share the probe stage: each
+// scores the centroid table for 1/G of the batch, the lists are exchanged, and every device scans its stripe for all.
+extern "C" int vs_probe_dev(vs_ctx *c, const vs_index *ix, const vs_matrix *queries, size_t nprobe, uint32_t *d_probe,
+                            uint32_t *d_status) {
+    VS(search_check(c, ix));
+    if (!queries || !d_probe || !d_status) return fail(VS_EINVAL, "null argument");
+    if (queries->d != ix->data->d)
+        return fail(VS_EDIM, "vector/matrix column size does not match: %d != %d", queries->d, ix->data->d);
+    if (!ix->centroids || nprobe == 0 || nprobe >= ix->C) return fail(VS_ERANGE, "vs_probe_dev: 1 <= nprobe < number of lists");
+    const size_t nq = queries->n;
+    Arena a(c);
+    SearchSetup s;
+    VS(search_setup(c, a, ix, nq, nprobe, 1, 0, &s, true));
+    search_take(a, ix, nq, &s);
+    VS(search_enqueue(c, ix, queries->view(), nq, nullptr, s.npe, 1, s.kpl1, s.kpl2, s.flat, false, s.b, nullptr, nullptr, nullptr,
+                      d_status, nullptr, true));
+    CU(cudaMemcpyAsync(d_probe, s.b.probe, nq * s.npe * sizeof(uint32_t), cudaMemcpyDeviceToDevice, c->stream));
+    return VS_OK;
+}
+
+// The list stage alone for probe lists selected elsewhere (vs_probe_dev on this or another device): d_probe = [nq][nprobe]
+// list numbers, d_status = the probe stage's status words on entry, the search's on return (as vs_search_dev leaves them;
+// vs_search_resolve finishes flagged queries the same way, it redoes both stages).
+extern "C" int vs_search_dev_probed(vs_ctx *c, const vs_index *ix, const vs_matrix *queries, size_t nprobe, size_t k,
+                                    const uint32_t *d_probe, uint64_t *d_ids, float *d_sims, int32_t *d_counts, uint32_t *d_status) {
+    VS(search_check(c, ix));
+    if (!queries || !d_probe || !d_ids || !d_sims || !d_counts || !d_status) return fail(VS_EINVAL, "null argument");
+    if (queries->d != ix->data->d)
+        return fail(VS_EDIM, "vector/matrix column size does not match: %d != %d", queries->d, ix->data->d);
+    if (!ix->centroids || nprobe == 0 || nprobe >= ix->C) return fail(VS_ERANGE, "vs_search_dev_probed: 1 <= nprobe < number of lists");
+    const size_t nq = queries->n;
+    Arena a(c);
+    SearchSetup s;
+    VS(search_setup(c, a, ix, nq, nprobe, k, 0, &s));
+    search_take(a, ix, nq, &s);
+    return search_enqueue(c, ix, queries->view(), nq, nullptr, s.npe, k, s.kpl1, s.kpl2, s.flat, false, s.b, d_ids, d_sims,
+                          d_counts, d_status, nullptr, false, d_probe);
 }
 
 extern "C" int vs_search_resolve(vs_ctx *c, const vs_index *ix, const vs_matrix *queries, size_t nprobe, size_t k,

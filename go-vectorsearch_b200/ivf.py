@@ -171,6 +171,21 @@ class Index:
         _check(self._L.vs_search_dev(ctx.handle, self._h, queries.handle, int(nprobe), int(k), C.c_void_p(int(d_ids)),
                                      C.c_void_p(int(d_sims)), C.c_void_p(int(d_counts)), C.c_void_p(int(d_status))))
 
+    def ProbeDev(self, queries, nprobe, d_probe, d_status, ctx=None):
+        """The centroid stage alone (search.go:205-223), device to device and asynchronous: d_probe[nq*nprobe] list numbers
+        in rank order, d_status[nq] the stage's status bits.  For an index striped over several devices, each of which
+        selects the probe lists of its share of the batch (see SearchDevProbed)."""
+        ctx = ctx or default_context()
+        _check(self._L.vs_probe_dev(ctx.handle, self._h, queries.handle, int(nprobe), C.c_void_p(int(d_probe)), C.c_void_p(int(d_status))))
+
+    def SearchDevProbed(self, queries, nprobe, k, d_probe, d_ids, d_sims, d_counts, d_status, ctx=None):
+        """The posting-list stage alone (search.go:239-273) for probe lists selected elsewhere (ProbeDev on this or another
+        device); d_status holds the probe stage's words on entry.  Same hits as SearchDev."""
+        ctx = ctx or default_context()
+        _check(self._L.vs_search_dev_probed(ctx.handle, self._h, queries.handle, int(nprobe), int(k), C.c_void_p(int(d_probe)),
+                                            C.c_void_p(int(d_ids)), C.c_void_p(int(d_sims)), C.c_void_p(int(d_counts)),
+                                            C.c_void_p(int(d_status))))
+
     def SearchBatchDev(self, queries, k, d_ids, d_sims, d_counts, ctx=None):
         """Query batch over the whole store (all lists) as a tensor-core GEMM; device-resident outputs (raw pointers).
         Returns (candidates, queries finished by the scan, store tiles, sampled tiles, us pre-pass, us GEMM, us resolve, 0)."""

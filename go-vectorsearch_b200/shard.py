@@ -154,6 +154,37 @@ class PeerHits:
             self._h = None
 
 
+class SharedProbes:
+    """The probe stage of a batch shared between the ranks of a striped index (every rank holds the whole centroid table):
+    rank r selects the probe lists of queries [r * nq / world, (r + 1) * nq / world) only (Index.ProbeDev), and two small
+    all-gathers (list numbers, status words) hand every rank the lists of the whole batch for its list stage
+    (Index.SearchDevProbed).  The replicated form costs every rank the centroid scoring of the WHOLE batch, a per-step
+    constant that does not shrink with the shard.  nq must be a multiple of world."""
+
+    def __init__(self, nq, nprobe, device, world, rank):
+        import torch
+        if nq % world:
+            raise ValueError("SharedProbes: the batch must divide evenly among the ranks")
+        self.nq, self.nprobe, self.world, self.rank, self.per = nq, nprobe, world, rank, nq // world
+        self.local_probe = torch.zeros(self.per * nprobe, dtype=torch.int32, device=device)
+        self.local_status = torch.zeros(self.per, dtype=torch.int32, device=device)
+        self.probe = torch.zeros(nq * nprobe, dtype=torch.int32, device=device)
+
+    def rows_of(self, rank=None):
+        """Query rows of the batch whose probe lists `rank` (default: this rank) selects."""
+        r = self.rank if rank is None else rank
+        return slice(r * self.per, (r + 1) * self.per)
+
+    def select_and_gather(self, ix, q_slice, d_status, ctx, group=None):
+        """q_slice: device matrix of this rank's share of the batch; d_status: [nq] int32 device tensor that receives the
+        probe stage's status words of the WHOLE batch.  Asynchronous on the CURRENT torch stream, which must be ctx's."""
+        import torch.distributed as dist
+        ix.ProbeDev(q_slice, self.nprobe, self.local_probe.data_ptr(), self.local_status.data_ptr(), ctx=ctx)
+        dist.all_gather_into_tensor(self.probe, self.local_probe, group=group)
+        dist.all_gather_into_tensor(d_status, self.local_status, group=group)
+        return self.probe
+
+
 # ---- k-means over a store cut into contiguous row blocks (SURVEY.md 8e) -------------------------------------------
 def block_range(n_total, rank, world):
     """Rows [lo, hi) of rank `rank` when the store is cut into `world` contiguous blocks (row order = rank order, which is

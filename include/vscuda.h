@@ -261,6 +261,17 @@ VS_API int vs_search_dev(vs_ctx *ctx, const vs_index *ix, const vs_matrix *queri
                   uint64_t *d_ids, float *d_sims, int32_t *d_counts, uint32_t *d_status);
 VS_API int vs_search_resolve(vs_ctx *ctx, const vs_index *ix, const vs_matrix *queries, size_t nprobe, size_t k,
                       uint64_t *d_ids, float *d_sims, int32_t *d_counts, uint32_t *d_status, int *n_resolved_out);
+/* The two stages of vs_search_dev as separate calls, for an index striped over several devices (every device holds the
+ * whole centroid table and 1/G of every posting list).  Device g runs vs_probe_dev on ITS share of the batch -- the
+ * centroid stage of server/search.go:205-223: d_probe[nq*nprobe] list numbers in rank order, d_status[nq] the stage's
+ * status bits -- the shares are exchanged (an all-gather of nq*(nprobe+1) words; the caller's transport), and every
+ * device runs vs_search_dev_probed on the WHOLE batch with the gathered lists: the posting-list stage of
+ * search.go:239-273 on its stripe.  d_status holds the gathered probe-stage words on entry and is left as vs_search_dev
+ * leaves it.  The hits are the ones vs_search_dev returns (the probe stage is deterministic); needs 1 <= nprobe < lists. */
+VS_API int vs_probe_dev(vs_ctx *ctx, const vs_index *ix, const vs_matrix *queries, size_t nprobe, uint32_t *d_probe,
+                 uint32_t *d_status);
+VS_API int vs_search_dev_probed(vs_ctx *ctx, const vs_index *ix, const vs_matrix *queries, size_t nprobe, size_t k,
+                         const uint32_t *d_probe, uint64_t *d_ids, float *d_sims, int32_t *d_counts, uint32_t *d_status);
 /* Stage 1 only (search.go:202-227): probe_out[nq*min(nprobe,C)] list indices in rank order (host). */
 VS_API int vs_select_probes(vs_ctx *ctx, const vs_index *ix, const uint8_t *queries_packed, size_t nq, size_t nprobe,
                      uint32_t *probe_out, float *probe_sims_out);

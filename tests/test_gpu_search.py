@@ -442,3 +442,57 @@ def test_more_queries_than_one_launch_takes(vs, oracle):
         want_ids, want_sims = oracle.search(qs[i], cent, rows, lists, doc, 4, 10)
         assert ids[i, :counts[i]].tolist() == want_ids.tolist()
         assert (f32_bits(sims[i, :counts[i]]) == f32_bits(want_sims)).all()
+
+
+@pytest.mark.parametrize("G,nq,nprobe,C", [(2, 64, 8, 96), (4, 16, 3, 40), (4, 8, 2, 40), (8, 1024, 32, 256)])
+def test_split_probe_and_list_stage_match_oracle(vs, oracle, G, nq, nprobe, C):
+    """The sharded probe stage emulated on one GPU: shard g selects the probe lists of ITS 1/G of the batch
+    (vs_probe_dev), the lists and status words are put side by side (the all-gather of an N-GPU run), every shard runs
+    the list stage on the WHOLE batch with them (vs_search_dev_probed) and the shard-local hits are merged -- equal to
+    the oracle's search over the whole store, and the gathered probe lists equal to what one device selects for all."""
+    import torch
+    n, d, k = 24000, 768, 10
+    rows, cent, lists, doc = _index_inputs(oracle, n, d, C, 171, docs_per=2)
+    qs = oracle.quantize_matrix_f32(unit_rows(nq, d, 172))
+    dev = torch.device("cuda", 0)
+    ctx = vs.compute.default_context()
+    shards = []
+    for r in range(G):
+        mine = vs.shard.stripe(n, r, G)
+        shards.append(vs.ivf.Index.build_assigned(rows[mine], doc[mine], lists[mine], cent))
+    per = nq // G
+    q_all = vs.compute.NewMatrix(qs, ctx=ctx)
+    d_probe = torch.zeros((nq, nprobe), dtype=torch.int32, device=dev)
+    d_pstat = torch.zeros(nq, dtype=torch.int32, device=dev)
+    torch.cuda.synchronize()
+    slices = []
+    for r in range(G):
+        q_r = vs.compute.NewMatrix(qs[r * per:(r + 1) * per], ctx=ctx)
+        slices.append(q_r)
+        shards[r].ProbeDev(q_r, nprobe, d_probe[r * per:].data_ptr(), d_pstat[r * per:].data_ptr(), ctx=ctx)
+    ctx.sync()
+    want_probe, _ = shards[0].SelectProbes(qs, nprobe, ctx=ctx)
+    assert (d_probe.cpu().numpy().astype(np.uint32) == want_probe).all()
+    g_ids = torch.zeros((G, nq, k), dtype=torch.int64, device=dev)
+    g_sims = torch.zeros((G, nq, k), dtype=torch.float32, device=dev)
+    g_counts = torch.zeros((G, nq), dtype=torch.int32, device=dev)
+    g_stat = d_pstat.repeat(G, 1).contiguous()
+    torch.cuda.synchronize()
+    for r in range(G):
+        shards[r].SearchDevProbed(q_all, nprobe, k, d_probe.data_ptr(), g_ids[r].data_ptr(), g_sims[r].data_ptr(), g_counts[r].data_ptr(),
+                                  g_stat[r].data_ptr(), ctx=ctx)
+        shards[r].Resolve(q_all, nprobe, k, g_ids[r].data_ptr(), g_sims[r].data_ptr(), g_counts[r].data_ptr(), g_stat[r].data_ptr(), ctx=ctx)
+    out_ids = torch.zeros((nq, k), dtype=torch.int64, device=dev)
+    out_sims = torch.zeros((nq, k), dtype=torch.float32, device=dev)
+    out_counts = torch.zeros(nq, dtype=torch.int32, device=dev)
+    ctx.sync()
+    vs.shard.merge_hits_dev(g_ids, g_sims, g_counts, k, out_ids, out_sims, out_counts, ctx=ctx)
+    ctx.sync()
+    ids = out_ids.cpu().numpy().view(np.uint64)
+    sims = out_sims.cpu().numpy()
+    counts = out_counts.cpu().numpy()
+    for i in range(0, nq, max(1, nq // 16)):
+        wi, ws = oracle.search(qs[i], cent, rows, lists, doc, nprobe, k)
+        assert counts[i] == len(wi)
+        assert ids[i, :counts[i]].tolist() == wi.tolist()
+        assert (f32_bits(sims[i, :counts[i]]) == f32_bits(ws)).all()

@@ -215,3 +215,61 @@ def test_block_partition():
             r = [pkg.shard.block_range(n, i, world) for i in range(world)]
             assert r[0][0] == 0 and r[-1][1] == n and all(r[i][1] == r[i + 1][0] for i in range(world - 1))
             assert max(b - a for a, b in r) - min(b - a for a, b in r) <= 1
+
+
+# ---- the probe stage shared between the ranks: shard.SharedProbes -------------------------------------------------------
+def _probe_worker(rank, world, port, q):
+    """On the GPU box Index.ProbeDev is vs_probe_dev; here the oracle's select_probes writes into the same buffers, so the
+    gather layout (rank-major = query order), the status words and the share each rank takes are checked without a GPU."""
+    try:
+        os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world))
+        import ctypes as C
+        import torch
+        import torch.distributed as dist
+        import oracle
+        from conftest import load_pkg
+        from _util import unit_rows
+        pkg = load_pkg()
+        dist.init_process_group("gloo", rank=rank, world_size=world)
+        d, Cn, nprobe, nq = 64, 20, 5, 12
+        cent = oracle.quantize_matrix_f32(unit_rows(Cn, d, 2))
+        qs = oracle.quantize_matrix_f32(unit_rows(nq, d, 3))
+
+        class FakeIndex:
+            def ProbeDev(self, q_slice, npb, d_probe, d_status, ctx=None):
+                out = np.ctypeslib.as_array(C.cast(d_probe, C.POINTER(C.c_int32)), shape=(len(q_slice) * npb,))
+                st = np.ctypeslib.as_array(C.cast(d_status, C.POINTER(C.c_int32)), shape=(len(q_slice),))
+                for i, row in enumerate(q_slice):
+                    p, _ = oracle.select_probes(row, cent, npb)
+                    out[i * npb:(i + 1) * npb] = p
+                    st[i] = 1 if (rank == 1 and i == 0) else 0          # one flagged query, owned by rank 1
+
+        sp = pkg.shard.SharedProbes(nq, nprobe, torch.device("cpu"), world, rank)
+        assert sp.rows_of() == slice(rank * nq // world, (rank + 1) * nq // world)
+        status = torch.full((nq,), 7, dtype=torch.int32)
+        probe = sp.select_and_gather(FakeIndex(), qs[sp.rows_of()], status, ctx=None).numpy().reshape(nq, nprobe)
+        for i in range(nq):
+            want, _ = oracle.select_probes(qs[i], cent, nprobe)
+            assert probe[i].tolist() == want.tolist(), f"rank {rank} query {i}"
+        want_status = [0] * nq
+        want_status[nq // world] = 1
+        assert status.tolist() == want_status
+        with pytest.raises(ValueError):
+            pkg.shard.SharedProbes(nq + 1, nprobe, torch.device("cpu"), world, rank)
+        dist.destroy_process_group()
+        q.put((rank, "ok"))
+    except Exception as e:  # noqa: BLE001
+        import traceback
+        q.put((rank, "error: " + repr(e) + "\n" + traceback.format_exc()))
+
+
+def test_shared_probe_stage_world2_gloo():
+    import torch.multiprocessing as mp
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_probe_worker, args=(r, 2, port, q)) for r in range(2)]
+    [p.start() for p in procs]
+    res = [q.get(timeout=180) for _ in procs]
+    [p.join(timeout=60) for p in procs]
+    assert all(r[1] == "ok" for r in res), res
