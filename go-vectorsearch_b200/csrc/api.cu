@@ -1767,6 +1767,15 @@ static int search_enqueue(vs_ctx *c, const vs_index *ix, const MatView &qv, size
             }
             CU(cudaEventRecord(c->fork_ev, c->stream));  // the probe lists are ready here: the seed below forks off this point
         }
+        // several queries per probed list: the tensor-core form of the scan (listmajor.cu, lm_dense_kernel)
+        const bool dense = g_lm_dense_min > 0 && lm_dense_supported(ix->data->d_pad) && qv.n * npe >= (size_t)g_lm_dense_min * ix->C;
+        if (dense) {
+            // a query's bound is recomputed from its own candidate list when that has grown to 512, 1024 and 2048 entries (a weak
+            // seed then costs a longer list, not an overflow): those reads must not see a previous step's entries
+            lp.tighten_at = 512;
+            // (here, in front of the inversion, the zeroing hides behind the seed kernel of the side stream)
+            CU(cudaMemset2DAsync(lp.gbuf, (size_t)lp.gcap * sizeof(uint4), 0, (size_t)4 * lp.tighten_at * sizeof(uint4), qv.n, c->stream));
+        }
         CU(lm_enqueue_prepare(lp, b.probe, (uint32_t)qv.n, (uint32_t)npe, (uint32_t)ix->C, ix->list_off, ix->list_len, b.lm_count, b.lm_pair_off,
                               b.lm_items_cap, c->stream, &c->launches));
         // The k-th best document among the first 512 rows of every query's nearest list -- the ~2 % quantile of the query's
@@ -1776,7 +1785,12 @@ static int search_enqueue(vs_ctx *c, const vs_index *ix, const MatView &qv, size
             // beside the inversion (lm_enqueue_prepare above): both need only the probe lists, and each is a latency chain of
             // a few tens of microseconds on a fraction of the SMs
             CU(cudaStreamWaitEvent(c->side_stream, c->fork_ev, 0));
-            CU(lm_enqueue_seed_scan(lp, b.probe, (uint32_t)qv.n, (uint32_t)npe, ix->list_off, ix->list_len, 512, c->side_stream,
+            static const uint32_t seed_rows = [] {  // (VS_LM_SEED_ROWS: measurement aid)
+                const char *e = getenv("VS_LM_SEED_ROWS");
+                const long v = e ? atol(e) : 0;
+                return (uint32_t)(v >= 32 && v <= 512 ? v : 512);
+            }();
+            CU(lm_enqueue_seed_scan(lp, b.probe, (uint32_t)qv.n, (uint32_t)npe, ix->list_off, ix->list_len, seed_rows, c->side_stream,
                                     &c->launches));
             CU(cudaEventRecord(c->join_ev, c->side_stream));
             CU(cudaStreamWaitEvent(c->stream, c->join_ev, 0));
@@ -1811,8 +1825,6 @@ static int search_enqueue(vs_ctx *c, const vs_index *ix, const MatView &qv, size
             CU(lm_enqueue_seed(lp, b.lm_seed_sims, b.lm_seed_counts, (uint32_t)qv.n, c->stream, &c->launches));
         }
         VS(prof_mark(c));
-        // several queries per probed list: the tensor-core form of the scan (listmajor.cu, lm_dense_kernel)
-        const bool dense = g_lm_dense_min > 0 && lm_dense_supported(ix->data->d_pad) && qv.n * npe >= (size_t)g_lm_dense_min * ix->C;
         CU(lm_enqueue_scan(lp, g_sm_count, c->stream, &c->launches, dense));
         VS(prof_mark(c));
         CU(lm_enqueue_final(lp, (uint32_t)qv.n, d_ids, d_sims, d_counts, d_status, c->d_fix_counter, c->stream, &c->launches));

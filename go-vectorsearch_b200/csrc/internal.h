@@ -208,6 +208,8 @@ struct LmParams {
     int gcap;
     int k, pub;
     int stage_bytes;           // ring geometry (filled by the launcher)
+    int tighten_at;            // dense form: candidates of a query after which its bound is recomputed (0: never); the first
+                               // 4 * tighten_at entries of every query's list are zeroed before the scan
 };
 constexpr int kLmGbufCap = 4096;   // candidates per query the list-major scan may append (more: the literal path)
 bool lm_supported(int d_pad, int k);

@@ -717,6 +717,11 @@ lm_dense_kernel(const LmParams p) {
                     h1 = p.rows.hdr[row1];
                     s1 = p.rows.sums[row1];
                 }
+                // the bounds of the pass's queries may have been raised since the pass began (by any block: the recomputation
+                // below); a stale value is still a valid bound, so the unsynchronised update is harmless
+                // (the load is issued here and used after the instructions of the tile: its latency hides behind them)
+                uint32_t fresh = 0;
+                if (p.tighten_at > 0 && lane < mq) fresh = __ldcg(p.gthr + sqid[lane]);
                 dn_wait(full, phase);
                 phase ^= 1u;
                 int acc[2][4];
@@ -753,10 +758,15 @@ lm_dense_kernel(const LmParams p) {
                         if (c + kDnStages < nchunks) arm(c + kDnStages);
                     }
                 }
+                if (lane < mq && fresh > sthr[lane]) {
+                    sthr[lane] = fresh;
+                    spre[lane].bound = key_to_f32(fresh);
+                }
+                __syncwarp();
                 const DnRowSide y0 = dn_row_side(h0.x, h0.y, s0.x, s0.y, D), y1 = dn_row_side(h1.x, h1.y, s1.x, s1.y, D);
                 // ---- scores: accumulator e of group gr = (row g + 8 (e >> 1), query 8 gr + 2 c4 + (e & 1)) ----
                 // the screen over this lane's pairs (static register indices), then the few that pass it one by one
-                uint32_t need = 0;
+                uint32_t need = 0, tq = 0, tn = 0;
 #pragma unroll
                 for (int gr = 0; gr < 2; gr++) {
 #pragma unroll
@@ -793,6 +803,31 @@ lm_dense_kernel(const LmParams p) {
                         v.z = (uint32_t)id;
                         v.w = (uint32_t)(id >> 32);
                         p.gbuf[(size_t)q * p.gcap + at] = v;
+                    }
+                    // the candidate that fills the list to 1x, 2x or 4x tighten_at makes its warp recompute the bound
+                    if (p.tighten_at > 0 && (at + 1u == (unsigned)p.tighten_at || at + 1u == 2u * (unsigned)p.tighten_at || at + 1u == 4u * (unsigned)p.tighten_at)) {
+                        tq = q;
+                        tn = at + 1u;
+                    }
+                }
+                // ---- a query's list has grown long: its bound becomes the k-th best certified document among what the list
+                // holds so far (entries still in flight read as zero and are left out: the bound only gets lower) ----
+                for (unsigned tm = __ballot_sync(FULL, tn != 0u); tm; tm &= tm - 1u) {
+                    const int src = __ffs((int)tm) - 1;
+                    const uint32_t q = __shfl_sync(FULL, tq, src), n = __shfl_sync(FULL, tn, src);
+                    const uint4 *src_buf = p.gbuf + (size_t)q * p.gcap;
+                    WarpTopK<1> top;
+                    top.init();
+                    for (uint32_t base = 0; base < n; base += 32) {
+                        const uint32_t e2 = base + (uint32_t)lane;
+                        uint4 v = make_uint4(0, 0, 0, 0);
+                        if (e2 < n) v = __ldcg(src_buf + e2);
+                        const bool have = v.x != 0u && !(v.y & kFlagBit);
+                        top.offer(have, v.x, v.y, (uint64_t)v.z | ((uint64_t)v.w << 32), lane, p.ids != nullptr);
+                    }
+                    if (top.count() >= p.k) {
+                        const uint32_t kth = __shfl_sync(FULL, top.skey[0], p.k - 1);
+                        if (lane == 0 && kth > 2u) atomicMax(p.gthr + q, kth - 1u);
                     }
                 }
             }

@@ -212,3 +212,39 @@ def test_screen_never_drops_a_hit_on_hard_data(vs, oracle):
     qs = oracle.quantize_matrix_f32(_hard_rows(40, d, 7))
     for nprobe, k in ((2, 10), (6, 32)):
         _check(oracle, ix, qs, cent, rows, lists, doc, nprobe, k)
+
+
+def test_weak_seed_is_repaired_by_the_running_bound(vs, oracle, scan_form):
+    """Most queries' nearest list is shorter than k, so the seed gives no bound, while one list holds more rows than a
+    query's candidate list can: the dp4a form limits itself through its per-warp lists, the tensor-core form by recomputing
+    the query's bound from its own candidate list -- neither may overflow into the literal path, and the hits are the
+    oracle's."""
+    d, C, k, nprobe, nq = 768, 6, 32, 5, 32
+    sizes = [20, 9000, 20, 20, 20, 20]
+    n = sum(sizes)
+    rows = oracle.quantize_matrix_f32(unit_rows(n, d, 61))
+    lists = np.repeat(np.arange(C), sizes).astype(np.uint32)
+    doc = np.random.default_rng(6).permutation(n).astype(np.uint64)
+    offs = np.concatenate([[0], np.cumsum(sizes)]).astype(np.uint64)
+    cent = oracle.quantize_matrix_f32(unit_rows(C, d, 62))
+    import torch
+    ctx = vs.compute.Context()
+    ix = vs.ivf.Index.build(rows, doc, offs, cent, ctx=ctx)
+    qs = oracle.quantize_matrix_f32(unit_rows(nq, d, 63))
+    dev = torch.device("cuda", 0)
+    d_ids = torch.zeros((nq, k), dtype=torch.int64, device=dev)
+    d_sims = torch.zeros((nq, k), dtype=torch.float32, device=dev)
+    d_counts = torch.zeros(nq, dtype=torch.int32, device=dev)
+    d_status = torch.zeros(nq, dtype=torch.int32, device=dev)
+    torch.cuda.synchronize()
+    qm = vs.compute.NewMatrix(qs, ctx=ctx)
+    ix.SearchDev(qm, nprobe, k, d_ids.data_ptr(), d_sims.data_ptr(), d_counts.data_ptr(), d_status.data_ptr(), ctx=ctx)
+    ctx.sync()
+    status = d_status.cpu().numpy()
+    assert (status & 2).sum() == 0, f"candidate lists overflowed: {status.tolist()}"
+    ids, sims, counts = d_ids.cpu().numpy().view(np.uint64), d_sims.cpu().numpy(), d_counts.cpu().numpy()
+    for i in range(0, nq, 3):
+        want_ids, want_sims = oracle.search(qs[i], cent, rows, lists, doc, nprobe, k)
+        assert ids[i, :counts[i]].tolist() == want_ids.tolist()
+        assert (f32_bits(sims[i, :counts[i]]) == f32_bits(want_sims)).all()
+    ctx.close()
