@@ -261,9 +261,29 @@ lm_seed_scan_kernel(MatView rows, const uint64_t *__restrict__ ids, uint64_t id_
     const uint32_t q = blockIdx.x;
     const int D = rows.d, d_pad = rows.d_pad;
     const bool dedup = ids != nullptr;
-    const uint32_t L = probe[(size_t)q * npe];
-    const uint64_t st = list_off[L];
-    const uint32_t len = (uint32_t)min((uint64_t)min(sample, (uint32_t)(kSeedTiles * TR)), list_len[L]);
+    // The sample: the first rows of the query's nearest list -- and, where that list is short, of its next lists in rank
+    // order, until `sample` rows or kSeedTiles tiles are taken (a tile never spans two lists).  A query whose nearest list
+    // holds fewer than k documents would otherwise start the scan without any bound.
+    __shared__ uint64_t t_row0[kSeedTiles];
+    __shared__ uint32_t t_nr[kSeedTiles];
+    if (threadIdx.x == 0) {
+        const uint32_t want = min(sample, (uint32_t)(kSeedTiles * TR));
+        uint32_t taken = 0;
+        int nt = 0;
+        for (uint32_t j = 0; j < npe && nt < kSeedTiles && taken < want; j++) {
+            const uint32_t L = probe[(size_t)q * npe + j];
+            const uint64_t st = list_off[L];
+            const uint32_t len = (uint32_t)min((uint64_t)(want - taken), list_len[L]);
+            for (uint32_t r0 = 0; r0 < len && nt < kSeedTiles; r0 += TR) {
+                t_row0[nt] = st + r0;
+                t_nr[nt] = min((uint32_t)TR, len - r0);
+                taken += t_nr[nt];
+                nt++;
+            }
+        }
+        for (; nt < kSeedTiles; nt++) t_nr[nt] = 0;
+    }
+    __syncthreads();
     uint4 qreg[CPL];
     const uint8_t *qc = queries.codes + (size_t)q * d_pad;
 #pragma unroll
@@ -273,16 +293,16 @@ lm_seed_scan_kernel(MatView rows, const uint64_t *__restrict__ ids, uint64_t id_
     const uint2 qs = queries.sums[q];
     const SideConst xq = make_side(qh.x, qh.y, qs.x, qs.y, queries.d);
     for (int tile = warp; tile < kSeedTiles; tile += kSeedWarps) {
-        const uint32_t r0 = (uint32_t)tile * TR;
         uint32_t key = 0, meta = 0;
         uint64_t id = kEmptyId;
-        if (r0 < len) {
-            const int nr = (int)min((uint32_t)TR, len - r0);
+        if (t_nr[tile] != 0) {
+            const int nr = (int)t_nr[tile];
+            const uint64_t first = t_row0[tile];
             const int iters = (nr + NG - 1) / NG;
-            const uint32_t mydot = tile_dots<G, CPL>(rows.codes, (size_t)(st + r0), nr, d_pad, qreg, lane, iters);
+            const uint32_t mydot = tile_dots<G, CPL>(rows.codes, (size_t)first, nr, d_pad, qreg, lane, iters);
             const int myr = (lane / G) * iters + (lane % G);
             if ((lane % G) < iters && myr < nr) {
-                const uint64_t row = st + r0 + (uint32_t)myr;
+                const uint64_t row = first + (uint32_t)myr;
                 const float2 h = rows.hdr[row];
                 const uint2 sm = rows.sums[row];
                 bool flag;
