@@ -1788,9 +1788,13 @@ static int search_enqueue(vs_ctx *c, const vs_index *ix, const MatView &qv, size
             static const uint32_t seed_rows = [] {  // (VS_LM_SEED_ROWS: measurement aid)
                 const char *e = getenv("VS_LM_SEED_ROWS");
                 const long v = e ? atol(e) : 0;
-                return (uint32_t)(v >= 32 && v <= 512 ? v : 512);
+                return (uint32_t)(v >= 32 && v <= 512 ? v : 0);
             }();
-            CU(lm_enqueue_seed_scan(lp, b.probe, (uint32_t)qv.n, (uint32_t)npe, ix->list_off, ix->list_len, seed_rows, c->side_stream,
+            // 512 rows for the dp4a form (whose per-warp lists want a tight start); 256 for the tensor-core form, which
+            // recomputes a query's bound from its candidate list as that grows -- there the seed kernel's own time (164 us
+            // at 1024 queries x 512 rows, a constant of the step that does not shrink with the shard) matters more
+            const uint32_t seed_n = seed_rows ? seed_rows : (dense ? 256u : 512u);
+            CU(lm_enqueue_seed_scan(lp, b.probe, (uint32_t)qv.n, (uint32_t)npe, ix->list_off, ix->list_len, seed_n, c->side_stream,
                                     &c->launches));
             CU(cudaEventRecord(c->join_ev, c->side_stream));
             CU(cudaStreamWaitEvent(c->stream, c->join_ev, 0));
