@@ -207,3 +207,50 @@ def test_row_spool_load_and_save(vs, oracle, tmp_path):
         vs.compute.LoadSpool(path, d)
     with pytest.raises(vs.compute.ComputePanic):
         vs.compute.LoadSpool(out, d, first_row=n)   # no rows: compute.go:25-27
+
+
+def _near_midpoint_rows(oracle, qrow, d, n_total, keep, seed):
+    """Adversarial search for rows the certified scorer could get wrong: out of n_total random rows, the `keep` whose
+    float64 cosine with the query lies closest to a float32 rounding boundary (the midpoint of two adjacent float32
+    values) -- there a float64 error of a few 1e-16 flips the float32 result, so the kernel must either have certified a
+    half-width that really is smaller than the distance or have sent the row through the literal arithmetic."""
+    def deq(rows):
+        h = np.ascontiguousarray(rows[:, :8]).view(np.float32).astype(np.float64)
+        return h[:, :1] + (h[:, 1:2] - h[:, :1]) * rows[:, 8:].astype(np.float64) / 255.0
+    q = deq(qrow[None, :])[0]
+    q /= np.linalg.norm(q)
+    best_rows, best_dist = [], []
+    for c in range(0, n_total, 20000):
+        rows = oracle.quantize_matrix_f32(unit_rows(min(20000, n_total - c), d, seed + c))
+        x = deq(rows)
+        cos = (x @ q) / np.linalg.norm(x, axis=1)
+        f = cos.astype(np.float32)
+        up = np.nextafter(f, np.float32(2)).astype(np.float64)
+        dn = np.nextafter(f, np.float32(-2)).astype(np.float64)
+        f64 = f.astype(np.float64)
+        dist = np.minimum(np.abs(cos - (f64 + up) / 2), np.abs(cos - (f64 + dn) / 2)) / (up - f64)   # in float32 steps
+        idx = np.argsort(dist)[:keep]
+        best_rows.append(rows[idx])
+        best_dist.append(dist[idx])
+    rows, dist = np.concatenate(best_rows), np.concatenate(best_dist)
+    order = np.argsort(dist)[:keep]
+    return rows[order], dist[order]
+
+
+@pytest.mark.parametrize("d", [768, 384])
+def test_cosine_near_float32_rounding_boundaries(vs, oracle, d):
+    qrow = oracle.quantize_vector_f32(unit_rows(1, d, 4242)[0])
+    rows, dist = _near_midpoint_rows(oracle, qrow, d, 200000, 2000, 77)
+    assert dist[0] < 1e-4 and dist[-1] < 2e-2          # the set really hugs the boundaries (distances in float32 steps)
+    ctx = vs.compute.Context()
+    m = vs.compute.NewMatrix(rows, ctx=ctx)
+    q = vs.compute.NewVector(qrow)
+    got, want = q.MatrixCosineSimilarity(m, ctx=ctx), oracle.cosine_1xN(qrow, rows)
+    bad = np.flatnonzero(f32_bits(got) != f32_bits(want))
+    assert bad.size == 0, f"{bad.size} rows differ, e.g. row {bad[:3]}: distance {dist[bad[:3]]} float32 steps"
+    # the same rows through the search path (top-k over a flat store: sort order by float32 similarity, ties by id)
+    ids, sims, counts = vs.ivf.SearchFlat(m, qrow[None, :], 100, ctx=ctx)
+    w_ids, w_sims = oracle.search_flat(qrow, rows, np.arange(len(rows), dtype=np.uint64), 100)
+    assert ids[0, :counts[0]].tolist() == w_ids.tolist()
+    assert (f32_bits(sims[0, :counts[0]]) == f32_bits(w_sims)).all()
+    ctx.close()

@@ -16,6 +16,7 @@ PAT = {
     "UBLKPF (cp.async.bulk.prefetch)": r"\bUBLKPF",
     "SYNCS (mbarrier)": r"\bSYNCS",
     "IDP.4A (dp4a)": r"\bIDP\.4A",
+    "IMMA (mma.sync m16n8k32 u8)": r"\bIMMA\.16832",
     "DFMA/DMUL/DADD (float64)": r"\bD(FMA|MUL|ADD)\b",
     "REDG/ATOMG (global atomics)": r"\b(REDG|ATOMG|RED\.E|ATOM\.E)",
 }
@@ -27,12 +28,12 @@ def main():
     a = ap.parse_args()
     lines = ["# SASS mnemonic counts per object (cuobjdump -sass, sm_100a); built by csrc/Makefile", ""]
     objs = sorted(glob.glob(os.path.join(ROOT, "go-vectorsearch_b200", "build", "*.o")))
-    hdr = f"{'object':14s}" + "".join(f"{k.split(' ')[0]:>10s}" for k in PAT)
+    hdr = f"{'object':14s}" + "".join(f"{k.split(' ')[0]:>15s}" for k in PAT)
     lines.append(hdr)
     for o in objs:
         sass = subprocess.run(["cuobjdump", "-sass", o], capture_output=True, text=True).stdout
         kernels = len(re.findall(r"^\s*Function : ", sass, flags=re.M))
-        row = f"{os.path.basename(o):14s}" + "".join(f"{len(re.findall(p, sass)):10d}" for p in PAT.values())
+        row = f"{os.path.basename(o):14s}" + "".join(f"{len(re.findall(p, sass)):15d}" for p in PAT.values())
         lines.append(row + f"   ({kernels} kernels)")
     lines += ["", "legend:"] + [f"  {k}" for k in PAT]
     txt = "\n".join(lines)
