@@ -579,6 +579,7 @@ lm_scan_kernel(const LmParams p) {
 // candidate list directly -- there is no per-warp list when a warp serves 16 queries -- and lm_final_kernel picks the top k
 // as before: the kept set is a superset of what the dp4a scan keeps, so the emitted hits are the same.
 constexpr int kDnWarps = 8, kDnStages = 4, kDnRows = 32, kDnQ = 16;
+constexpr int kDnReserveDefault = 0;  // blocks of the 2-per-SM grid left out (VS_LM_DENSE_RESERVE)
 constexpr int kDnQStride(int d_pad) { return d_pad + 64; }  // query rows 64 B apart in bank phase: conflict-free 128-bit loads
 
 struct DnCtl {
@@ -1112,7 +1113,18 @@ static cudaError_t lm_launch_dense(const LmParams &p, int sm_count, cudaStream_t
         if (e != cudaSuccess) return e;
         attr_of[dev & 63] = true;
     }
-    lm_dense_kernel<<<2 * sm_count, 32 * kDnWarps, smem, st>>>(p);
+    // Two blocks per SM fill every SM's shared memory and registers, so nothing of another search context (its probe
+    // selection, inversion, seed, final selection: a quarter of a step's kernel time) can run beside the scan.  Leaving a few
+    // blocks out -- those SMs then hold ONE scan block and have half their resources free -- lets the next step's small
+    // kernels run during this step's scan; the scan itself is bound by HBM and does not need every block.
+    static const int reserve = [] {
+        const char *e = getenv("VS_LM_DENSE_RESERVE");
+        const int v = e ? atoi(e) : -1;
+        return v >= 0 && v <= 1024 ? v : kDnReserveDefault;
+    }();
+    int blocks = 2 * sm_count - reserve;
+    if (blocks < sm_count) blocks = sm_count;
+    lm_dense_kernel<<<blocks, 32 * kDnWarps, smem, st>>>(p);
     return cudaGetLastError();
 }
 
