@@ -721,6 +721,7 @@ lm_dense_kernel(const LmParams p) {
                 spre[threadIdx.x] = dn_query_side(p.sides[q], D, thr);
             }
             __syncthreads();
+            uint32_t fresh = 0;  // bound of query `lane` of the pass as last read from global memory (0: nothing newer)
             const uint32_t a_base = smem_u32(ring + (size_t)st * stage_bytes) + (uint32_t)((tile * 16 + g) * d_pad + c4 * 16);
             const uint32_t b_base = smem_u32(qsm) + (uint32_t)g * qstride + (uint32_t)c4 * 16u;
             for (uint32_t c = (uint32_t)st; c < nchunks; c += kDnStages) {
@@ -740,8 +741,14 @@ lm_dense_kernel(const LmParams p) {
                 }
                 // the bounds of the pass's queries may have been raised since the pass began (by any block: the recomputation
                 // below); a stale value is still a valid bound, so the unsynchronised update is harmless
-                // (the load is issued here and used after the instructions of the tile: its latency hides behind them)
-                uint32_t fresh = 0;
+                // (software-pipelined: the value loaded during the previous chunk is applied here and the next load is issued
+                // for the chunk after this one, so the round trip to L2 never sits in front of anything -- on short per-rank
+                // lists the scan is bound by latency, not by HBM, and a load used within the chunk cost a fifth of it)
+                if (lane < mq && fresh > sthr[lane]) {
+                    sthr[lane] = fresh;
+                    spre[lane].bound = key_to_f32(fresh);
+                }
+                __syncwarp();
                 if (p.tighten_at > 0 && lane < mq) fresh = __ldcg(p.gthr + sqid[lane]);
                 dn_wait(full, phase);
                 phase ^= 1u;
@@ -779,11 +786,6 @@ lm_dense_kernel(const LmParams p) {
                         if (c + kDnStages < nchunks) arm(c + kDnStages);
                     }
                 }
-                if (lane < mq && fresh > sthr[lane]) {
-                    sthr[lane] = fresh;
-                    spre[lane].bound = key_to_f32(fresh);
-                }
-                __syncwarp();
                 const DnRowSide y0 = dn_row_side(h0.x, h0.y, s0.x, s0.y, D), y1 = dn_row_side(h1.x, h1.y, s1.x, s1.y, D);
                 // ---- scores: accumulator e of group gr = (row g + 8 (e >> 1), query 8 gr + 2 c4 + (e & 1)) ----
                 // the screen over this lane's pairs (static register indices), then the few that pass it one by one
