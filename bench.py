@@ -17,9 +17,11 @@ config's single-query latency is reported beside it (`latency_us_batch1`).
   cpu_baseline  the oracle (CPU restatement of the reference's default backend) on the host cores
 
 N > 1 (torchrun): strong scaling -- the same 10M-row store striped across the ranks by row id, the
-centroid table replicated, shard-local top-k all-gathered over NCCL and merged on device.  On several GPUs four
-search contexts (one CUDA stream each, the reference's one-closure-per-goroutine model) take the steps in turn, so
-one batch's exchange and probe selection overlap another batch's list scan.
+centroid table replicated.  Every rank selects the probe lists of its 1/N of the batch and two small NCCL all-gathers
+hand every rank the lists of the whole batch (`--replicated-probe`: every rank selects all); every rank scans its stripe
+for the whole batch; the shard-local top-k are exchanged through peer memory inside the merge kernel (`--nccl-exchange`:
+one all-gather first).  Four search contexts (one CUDA stream each, the reference's one-closure-per-goroutine model)
+take the steps in turn.
 
 `--impl reference` times the reference's own CPU algorithm (the oracle port; Go is not in this image).
 """
