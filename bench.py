@@ -647,7 +647,8 @@ def run_b200(a):
                      "note": "achieved = (query, row) pairs scored x 776 B / launch time (algorithmic bytes, SURVEY 8d); traffic = ncu "
                              "dram bytes of one such launch. peak is the driver's read+write copy figure; a read-only stream goes "
                              "higher on this part (ncu: 7.07 TB/s), so a fraction can pass 1"},
-        "e2e": {"value": round(e2e_qps, 1), "unit": "queries/s", "h2d_bytes_per_step": B * ROW_BYTES,
+        "e2e": {"value": round(e2e_qps, 1), "unit": "queries/s",
+                "h2d_bytes_per_step": B * ROW_BYTES + ((B // world) * ROW_BYTES if shared_probe else 0),   # (per rank)
                 "d2h_bytes_per_step": B * k * 12 + B * 4 + B * 4, "results_match_device_path": e2e_match,
                 **({"callers": f"{NC} threads, one synchronous vs_search call at a time each (one context per thread)",
                     "single_caller": round(e2e_single, 1)} if e2e_single else {})},
