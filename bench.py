@@ -762,6 +762,7 @@ def other_configs(pkg, torch, ctx, ix, a, device, peaks):
             "roofline": {"bound": "tensor", "kernel": "gemm_kernel<MODE_FILTER> (tcgen05.mma kind::i8)",
                          "achieved": round(tops, 1), "peak": int8_peak, "peak_source": src, "unit": "TOP/s",
                          "frac": round(tops / int8_peak, 4), "frac_of_nominal_4500": round(tops / 4500.0, 4),
+                         "frac_of_own_mainloop_3310": round(tops / 3310.0, 4),   # the kernel with its epilogue switched off
                          "int_ops_per_launch": ops, "ms_per_launch": round(gemm_ms / max(1, gemm_launches), 3),
                          "launches_timed": gemm_launches},
             "whole_batch_tops": round(ops / (ms * 1e-3) / 1e12, 1),
